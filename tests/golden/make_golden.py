@@ -1,0 +1,169 @@
+"""Generate the golden fixtures in this directory from the LIVE, UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
+Every ``*.npz`` holds the inputs (weights, noise tensor G, initial particles, injected standard-normal draws)
+and the reference's outputs for one case of the hot path, plus a ``meta`` JSON string.  The reference has no
+golden vectors of its own; these are outputs of the reference itself.
+
+Noise is recorded by RNG replay: the reference samplers draw exactly one ``randn_like(x)`` per step
+(sde_scheme.py:84,144,227), so re-seeding and drawing the same shapes reproduces what they consumed.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_live  # noqa: E402
+
+
+def _boost(net, k):
+    with torch.no_grad():
+        net.main[6].weight.mul_(k)
+        net.main[6].bias.mul_(k)
+
+
+def _net_arrays(net):
+    lin = [m for m in net.main if isinstance(m, torch.nn.Linear)]
+    out = {}
+    for i, l in enumerate(lin):
+        out[f"W{i}"] = l.weight.detach().numpy().copy()
+        out[f"b{i}"] = l.bias.detach().numpy().copy()
+    return out
+
+
+def _sde_arrays(base):
+    out = {}
+    if type(base).__name__ == "MSGMsde":
+        out["r_T"] = base.r_T.numpy().copy()
+        if not base.sparseTensor:
+            out["G"] = base.G.numpy().copy()
+            out["L_G"] = base.L_G.numpy().copy()
+    return out
+
+
+def _save(name, meta, **arrays):
+    arrays = {k: np.asarray(v) for k, v in arrays.items()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), **arrays)
+    print(f"wrote {name}.npz  ({sum(a.nbytes for a in arrays.values()) / 1024:.0f} KiB raw)")
+
+
+def sampler_case(ref, name, kind, dim, pre, scheme, N, B, lmbd, nc, seed, forward=False, boost=8.0,
+                 beta=(0.1, 20.0), keep=None, T_=None):
+    torch.manual_seed(seed)
+    x_init = torch.randn(1024, dim) * 1.5
+    base, gen, net = ref_live.build(ref, kind, dim, x_init, pre, beta_min=beta[0], beta_max=beta[1])
+    _boost(net, boost)
+    proc = ref.SDEs.forward_SDE(base, base.T) if forward else gen
+    x0 = torch.randn(B, dim) * 1.2
+    fn = {"em": ref.sde_scheme.euler_maruyama_sampler, "heun": ref.sde_scheme.heun_sampler,
+          "rk4": ref.sde_scheme.rk4_stratonovich_sampler}[scheme]
+    kw = dict(lmbd=lmbd, include_t0=True, norm_correction=nc)
+    if keep is not None:
+        g = torch.Generator().manual_seed(seed + 1)
+        keep_t = torch.randint(0, N + 1, (B, 1), generator=g).to(torch.int)
+        kw.update(keep_all_samples=False, samplesToKeep=keep_t)
+    else:
+        kw.update(keep_all_samples=True)
+    if T_ is not None:
+        kw.update(T_=torch.tensor([T_]))
+    torch.manual_seed(seed + 2)
+    xs = fn(proc, x0, N, **kw)
+    torch.manual_seed(seed + 2)
+    noise = torch.stack([torch.randn_like(x0) for _ in range(N)])
+    meta = dict(kind=kind, dim=dim, premodule=pre is not None, scheme=scheme, num_steps=N, lmbd=lmbd,
+                norm_correction=nc, include_t0=True, forward=forward, beta_min=beta[0], beta_max=beta[1],
+                T=1.0, T_=T_, keep_all=keep is None)
+    arrays = dict(x0=x0.numpy(), noise=noise.numpy(), out=xs.numpy(), **_sde_arrays(base))
+    if not forward:
+        arrays.update(_net_arrays(net))
+    if keep is not None:
+        arrays["samplesToKeep"] = keep_t.numpy()
+    _save(name, meta, **arrays)
+
+
+def ssm_case(ref, name, kind, dim, pre, B, seed, n_fwd=16, boost=3.0):
+    torch.manual_seed(seed)
+    x_init = torch.randn(1024, dim) * 1.5
+    base, gen, net = ref_live.build(ref, kind, dim, x_init, pre, n_fwd=n_fwd)
+    _boost(net, boost)
+    x = torch.randn(B, dim)
+    # --- forward noising with replayable noise (SDEs.py:648-682, 78-122)
+    torch.manual_seed(seed + 1)
+    t_, _, y = gen.sample_txy(x)
+    state = torch.get_rng_state()
+    v = ref.SDEs.sample_rademacher(x.shape, "cpu")
+    torch.manual_seed(seed + 1)
+    u_t = torch.rand(B, 1)
+    if kind == "sgm":
+        fwd_noise = torch.randn(1, B, dim)
+        singles = torch.zeros(0, dim)
+    else:
+        fwd_noise = torch.stack([torch.randn(B, dim) for _ in range(n_fwd)])
+        n_int = torch.trunc(n_fwd * t_ / base.T).to(torch.int).flatten()
+        singles = torch.cat([torch.randn(1, dim) for k in range(B) if n_int[k] == 0] + [torch.zeros(0, dim)])
+    # --- loss and gradients with the same v (SDEs.py:616-646)
+    torch.set_rng_state(state)
+    y = y.detach().clone().requires_grad_()
+    gen.train()
+    loss = gen.ssm_loss(t_, x, y)
+    gen.zero_grad()
+    loss.mean().backward()
+    arrays = dict(x=x.numpy(), u_t=u_t.numpy(), t=t_.numpy(), y=y.detach().numpy(), v=v.numpy(),
+                  fwd_noise=fwd_noise.numpy(), singles=singles.numpy(), loss=loss.detach().numpy(),
+                  **_sde_arrays(base), **_net_arrays(net))
+    lin = [m for m in net.main if isinstance(m, torch.nn.Linear)]
+    for i, l in enumerate(lin):
+        arrays[f"gW{i}"] = l.weight.grad.numpy().copy()
+        arrays[f"gb{i}"] = l.bias.grad.numpy().copy()
+    meta = dict(kind=kind, dim=dim, premodule=pre is not None, beta_min=0.1, beta_max=20.0, T=1.0,
+                t_epsilon=1e-3, num_steps_forward=n_fwd, vtype="rademacher")
+    _save(name, meta, **arrays)
+
+
+def misc_case(ref):
+    torch.manual_seed(31)
+    x_init = torch.randn(4096, 2) * torch.tensor([1.5, 0.7])
+    base, gen, net = ref_live.build(ref, "msgm_dense", 2, x_init, "NormalizeLogRadius")
+    torch.manual_seed(32)
+    x0 = gen.latent_sample(512, 2)
+    torch.manual_seed(32)
+    U = torch.rand(512)
+    Z = torch.randn(512, 2)
+    a, b = torch.randn(300, 4), torch.randn(257, 4) * 1.2 + 0.3
+    mmd = ref.qc.compute_mmd(a, b)
+    _save("misc_latent_mmd", dict(norm_map="log"), r_T=base.r_T.numpy(), U=U.numpy(), Z=Z.numpy(),
+          x0=x0.numpy(), mmd_a=a.numpy(), mmd_b=b.numpy(), mmd=np.float32(mmd))
+
+
+def main():
+    ref = ref_live.load()
+    P = "NormalizeLogRadius"
+    sampler_case(ref, "s01_msgm_d2_rk4", "msgm_dense", 2, P, "rk4", 16, 64, 0.0, True, 1)
+    sampler_case(ref, "s02_sgm_d2_rk4", "sgm", 2, None, "rk4", 16, 64, 0.0, False, 2)
+    sampler_case(ref, "s03_msgm_d16_rk4", "msgm_dense", 16, P, "rk4", 8, 32, 0.0, True, 3)
+    sampler_case(ref, "s04_sparse_d32_rk4", "msgm_sparse", 32, P, "rk4", 8, 32, 0.0, True, 4)
+    sampler_case(ref, "s05_msgm_d2_heun", "msgm_dense", 2, P, "heun", 16, 64, 0.0, True, 5)
+    sampler_case(ref, "s06_msgm_d4_em_l05", "msgm_dense", 4, P, "em", 16, 48, 0.5, False, 6)
+    sampler_case(ref, "s07_sparse_d8_em_l05", "msgm_sparse", 8, P, "em", 16, 48, 0.5, True, 7)
+    sampler_case(ref, "s08_fwd_msgm_d2_rk4", "msgm_dense", 2, P, "rk4", 16, 64, 0.0, True, 8, forward=True)
+    sampler_case(ref, "s09_fwd_keep_d2_rk4", "msgm_dense", 2, P, "rk4", 16, 64, 0.0, False, 9, forward=True,
+                 keep=True)
+    sampler_case(ref, "s10_msgm_d32_rk4", "msgm_dense", 32, P, "rk4", 4, 16, 0.0, True, 10)
+    sampler_case(ref, "s11_sgm_d16_heun_l03", "sgm", 16, None, "heun", 8, 32, 0.3, False, 11)
+    sampler_case(ref, "s12_msgm_d2_rk4_Tov", "msgm_dense", 2, P, "rk4", 3, 40, 0.0, False, 12, T_=0.37)
+    sampler_case(ref, "s13_fwd_sgm_d4_rk4", "sgm", 4, None, "rk4", 8, 32, 0.0, False, 13, forward=True)
+    ssm_case(ref, "t01_ssm_msgm_d2", "msgm_dense", 2, P, 32, 21)
+    ssm_case(ref, "t02_ssm_sgm_d2", "sgm", 2, None, 32, 22)
+    ssm_case(ref, "t03_ssm_sparse_d8", "msgm_sparse", 8, P, 24, 23)
+    ssm_case(ref, "t04_ssm_msgm_d16", "msgm_dense", 16, P, 16, 24)
+    misc_case(ref)
+
+
+if __name__ == "__main__":
+    main()

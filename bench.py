@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Headline benchmark: reverse-SDE sampling throughput (particle-steps/s) of the MSGM hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dim D] [--precision P]
+
+Workload (BASELINE.json configs[1]): synthetic higher-dimensional Gaussian-mixture data, MLP score net
+(NN.py, hidden 128, NormalizeLogRadius), dense multiplicative SDE, 2^20 particles per GPU, RK4-Stratonovich with
+128 reverse steps, lambda = 0, radius correction on, final state only (keep_all_samples=False).  One bench "step"
+is one full sampler call over the batch.  Weights are random-init (no checkpoints offline), data synthetic.
+
+* ``value``      whole-job particle-steps/s with x_0 already resident in HBM (kernel launch -> completion).
+* ``e2e``        the same through the public API ``rk4_stratonovich_sampler`` with HOST buffers: pinned x_0 H2D
+                 and the final states D2H are inside the timed region.
+* ``roofline``   tensor-pipe roofline of the sampler kernel: algorithmic FLOP / CUDA-event duration vs the
+                 measured cuBLAS bf16 peak in MEASURED_PEAKS.json (sustained figure: the kernel runs for >100 ms).
+* ``cpu_baseline`` the CPU oracle port of the reference (oracle/msgm_oracle.py, same ATen op sequence as the
+                 reference) timed on this host on a bounded sample of the same workload.
+* ``--impl reference`` times that CPU port alone, on the same config, as the reference arm.
+
+Multi-GPU: launched by torchrun, one rank per GPU; particles are sharded (weak scaling, B per GPU fixed), no
+data-path collective; Philox noise is keyed by the global particle index.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SDE_STEPS = 128
+PARTICLES_PER_GPU = 1 << 20
+STAGES = {"em": 1, "heun": 2, "rk4": 4}
+
+
+def flop_per_particle_step(d: int, pre: int, dense: bool, scheme: str = "rk4") -> float:
+    """S * (F_net + [dense] (2 d^3 + 4 d^2)), F_net = 2*128*(2d+1+pre) + 65536."""
+    f_net = 2 * 128 * (2 * d + 1 + pre) + 65536
+    return STAGES[scheme] * (f_net + ((2 * d ** 3 + 4 * d ** 2) if dense else 0))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        j = json.load(open(p))
+        return dict(tflops=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), hbm=float(j["hbm_gbs"]),
+                    src="measured(sustained)")
+    return dict(tflops=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_problem(d: int, seed: int = 0):
+    """Synthetic config-2 problem, identical on every rank (CPU tensors): data -> r_T, dense G, MLP weights."""
+    from oracle import msgm_oracle as O  # data + init helpers only; the measured GPU path never calls the oracle
+    torch.manual_seed(seed)
+    data = O.gaussian_mixture(100_000, d, seed=seed)
+    sde = O.make_msgm(data, dense=True, num_steps_forward=16)
+    mlp = O.init_mlp(d, True, seed=seed, scale=6.0)
+    return sde, mlp
+
+
+def package_objects(sde, mlp, device):
+    import sdeflow_light_b200 as P
+    T = torch.nn.Parameter(torch.FloatTensor([sde.T]), requires_grad=False)
+    base = P.MSGMsde(torch.randn(8, sde.dim), beta_min=sde.beta_min, beta_max=sde.beta_max, T=T,
+                     t_epsilon=sde.t_epsilon, denseTensor=True, norm_sampler="ecdf", norm_map="log",
+                     num_steps_forward=sde.num_steps_forward, device=device, estim_cst_norm_dens_r_T=False)
+    base.G, base.L_G, base.r_T = sde.G.to(device), sde.L_G.to(device), sde.r_T.to(device)
+    net = P.MLP(input_dim=sde.dim, premodule="NormalizeLogRadius")
+    with torch.no_grad():
+        for i, l in enumerate(net.linears()):
+            l.weight.copy_(mlp.W[i])
+            l.bias.copy_(mlp.b[i])
+    gen = P.PluginReverseSDE(base, net.to(device), T, deviceReverseSDE=device).to(device)
+    return P, gen
+
+
+def time_cpu_port(sde, mlp, B: int, n_steps: int, reps: int):
+    """particle-steps/s of the CPU oracle port (reference op sequence) with all host threads."""
+    from oracle import msgm_oracle as O
+    rev = O.OReverse(sde, mlp)
+    torch.manual_seed(1)
+    x0 = O.latent_sample(sde, B)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.integrate(rev, x0, n_steps, "rk4", 0.0, keep_all_samples=False, norm_correction=True)
+        best = min(best, time.perf_counter() - t0)
+    return B * n_steps / best, best
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sde, mlp = build_problem(args.dim)
+    B, n = 50_000, 4
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, t = time_cpu_port(sde, mlp, B, n, 1)
+        if i >= args.warmup:
+            times.append(t)
+    ms = 1e3 * sum(times) / len(times)
+    value = B * n / (ms / 1e3)
+    sample = f"{B} particles x {n} RK4 steps per bench step (same net/SDE as the GPU arm)"
+    print(json.dumps({
+        "impl": "reference", "metric": "reverse_sde_particle_steps_per_sec", "value": value,
+        "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, "cpu"),
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(args, where):
+    return {"workload": f"gaussmix_d{args.dim}_msgm_dense_mlp128_rk4_n{N_SDE_STEPS}_{PARTICLES_PER_GPU}particles_per_gpu",
+            "dim": args.dim, "particles_per_gpu": PARTICLES_PER_GPU, "sde_steps": N_SDE_STEPS, "scheme": "rk4",
+            "lmbd": 0.0, "norm_correction": True, "precision": args.precision if where == "gpu" else "fp32",
+            "l2_policy": "working set is on-chip (weights in smem, state in registers); x_0/x_N (2 x 4*B*d bytes) "
+                         "streamed once per call; a 256 MB buffer is rewritten between timed calls to flush L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dim", type=int, default=16)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "f16tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (sdeflow_light_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    sde, mlp = build_problem(args.dim)
+    P, gen = package_objects(sde, mlp, dev)
+    B, N = PARTICLES_PER_GPU, N_SDE_STEPS
+    torch.manual_seed(1234 + rank)
+    x0_host = (torch.randn(B, args.dim) * 1.5).pin_memory()
+    x0_dev = x0_host.to(dev)
+    flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)  # 256 MB > 126 MB L2
+    kw = dict(lmbd=0.0, keep_all_samples=False, norm_correction=True, precision=args.precision,
+              particle_offset=rank * B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_call(seed):
+        return P.rk4_stratonovich_sampler(gen, x0_dev, N, seed=seed, device_out=True, **kw)
+
+    for i in range(args.warmup):
+        one_call(i)
+    barrier()
+
+    # ---- device-resident timing (value, roofline) ----------------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = P._lib.launch_count(dev)
+    with ClockSampler(local) as clk:
+        barrier()
+        for i in range(args.steps):
+            flush.fill_(float(i))
+            ev[i][0].record()
+            one_call(100 + i)
+            ev[i][1].record()
+        barrier()
+    launches = P._lib.launch_count(dev) - launches0
+    kern_ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = torch.tensor([sum(kern_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+    value = world * B * N * args.steps / (total_ms / 1e3)
+
+    # ---- end-to-end through the public API with host buffers -------------------------------------------------
+    out_host = torch.empty(B, args.dim).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        xd = x0_host.to(dev, non_blocking=True)
+        res = P.rk4_stratonovich_sampler(gen, xd, N, seed=200 + i, device_out=True, **kw)
+        out_host.copy_(res, non_blocking=True)
+    e1.record()
+    barrier()
+    t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * N * args.steps / (float(t_e2e.item()) / 1e3)
+    assert torch.isfinite(out_host).all()
+
+    if rank == 0:
+        peaks = load_peaks()
+        fl = flop_per_particle_step(args.dim, 1, True) * B * N  # per launch
+        kms = sum(kern_ms) / len(kern_ms)
+        achieved = fl / (kms / 1e3) / 1e12
+        line = {
+            "metric": "reverse_sde_particle_steps_per_sec", "value": value, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16",
+            "data": "synthetic", "config": workload_config(args, "gpu"),
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": B * args.dim * 4,
+                    "d2h_bytes_per_step": B * args.dim * 4},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                         "kernel": "sample_fp32_kernel" if args.precision == "fp32" else "sample_tc_kernel",
+                         "flop_per_launch": fl, "kernel_ms": kms},
+        }
+        if not args.no_cpu_baseline:
+            v, t = time_cpu_port(sde, mlp, 50_000, 4, 3)
+            line["cpu_baseline"] = {"value": v, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
+                                    "kind": "port",
+                                    "sample": "50000 particles x 4 RK4 steps, best of 3, same net/SDE (oracle port of "
+                                              "the reference's op sequence, torch CPU fp32)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+/* msgm_b200.h -- C ABI of libmsgm_b200.so: the B200 (sm_100a) replacement for the data-parallel hot path of
+ * vressegu/sdeflow-light (MSGM): reverse/forward SDE sampling loops and the sliced-score-matching train step.
+ *
+ * The reference has no FFI of its own (it is pure Python); its "plugin" boundary is the duck-typed Python
+ * surface of sde_scheme.py / SDEs.py / NN.py.  Each entry point below names the reference interface it
+ * replaces (file:line under the reference root).  The Python shims in sdeflow_light_b200/ bind these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every pointer marked "device" is a CUDA device pointer owned by the caller; the library owns
+ * only the opaque msgm_ctx (small device workspace).  All calls are stream-ordered on `stream` (a cudaStream_t
+ * passed as void*), never synchronise the host, and are re-entrant per ctx.  Return 0 on success, a negative
+ * msgm_status otherwise; msgm_last_error() gives a thread-local message.  No C++ exception crosses the ABI.
+ */
+#ifndef MSGM_B200_H
+#define MSGM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSGM_ABI_VERSION 1
+#define MSGM_HIDDEN 128   /* NN.py:77 hidden_dim (the only width the reference driver uses) */
+#define MSGM_MAX_DIM_MLP 32
+
+typedef enum {
+  MSGM_OK = 0,
+  MSGM_ERR_INVALID = -1,     /* bad argument (maps to ValueError in the Python shim) */
+  MSGM_ERR_UNSUPPORTED = -2, /* valid in the reference, not built here (maps to NotImplementedError) */
+  MSGM_ERR_CUDA = -3,        /* a CUDA runtime call failed */
+  MSGM_ERR_NO_DEVICE = -4    /* no sm_100 device: there is NO CPU fallback */
+} msgm_status;
+
+typedef enum { MSGM_SDE_SGM = 0, MSGM_SDE_MSGM_DENSE = 1, MSGM_SDE_MSGM_SPARSE = 2 } msgm_sde_kind;
+typedef enum { MSGM_SCHEME_EM = 0, MSGM_SCHEME_HEUN = 1, MSGM_SCHEME_RK4 = 2 } msgm_scheme;
+typedef enum {
+  MSGM_PREC_FP32 = 0, /* CUDA-core fp32 everywhere: the parity mode (reference is fp32 end to end) */
+  MSGM_PREC_F16TC = 1 /* tcgen05 tensor cores, fp16 operands / fp32 accumulate for the 128-wide layers */
+} msgm_precision;
+
+/* Base SDE coefficients.  Replaces SGMsde / MSGMsde.{beta,f,f_strato,div_Sigma,g,IJK}
+ * (SDEs.py:72-73,183-194,401-432).  The sparse cyclic tensor (SDEs.py:369-399) needs no arrays: it is the
+ * 3-point stencil  (g w)_i = c sqrt(beta) (y_{i+1} w_i - y_{i-1} w_{i-1}),  c = sqrt(2)/2. */
+typedef struct {
+  int32_t kind;       /* msgm_sde_kind */
+  int32_t dim;        /* state dimension d */
+  float beta_min;     /* SDEs.py:58 */
+  float beta_delta;   /* (float)(beta_max - beta_min), difference taken in double like the reference */
+  float T;            /* horizon, SDEs.py:57 */
+  const float* G;     /* device (d,d,d) row-major [i][j][k]; MSGM dense only (SDEs.py:315-341) */
+  const float* L_G;   /* device (d,d); MSGM dense only; Ito correction (SDEs.py:246) */
+} msgm_sde_desc;
+
+/* NN.MLP weights in torch.nn.Linear layout (NN.py:98-106): W[l] is (out,in) row-major, b[l] is (out,).
+ * Layer sizes: (d + premodule + 1) -> 128 -> 128 -> 128 -> d.  All device pointers, fp32. */
+typedef struct {
+  int32_t input_dim;
+  int32_t premodule;  /* 1 = NormalizeLogRadius (NN.py:56-70), 0 = none */
+  const float* W[4];
+  const float* b[4];
+} msgm_mlp_desc;
+
+/* One sampler call.  Replaces euler_maruyama_sampler / heun_sampler / rk4_stratonovich_sampler
+ * (sde_scheme.py:43-99,101-172,174-269) driving PluginReverseSDE.{mu,mu_Strato,sigma} (SDEs.py:556-588) or,
+ * with forward_only=1, the forward_SDE adapter (SDEs.py:30-47; `mlp` may then be NULL). */
+typedef struct {
+  int32_t scheme;          /* msgm_scheme */
+  int32_t num_steps;       /* N */
+  float lmbd;              /* lambda family, SDEs.py:561,584,588 */
+  int32_t norm_correction; /* re-pin |x| to its initial value after every step (sde_scheme.py:254-255) */
+  int32_t include_t0;      /* trajectory slot 0 holds x_0 (sde_scheme.py:207-212) */
+  int32_t forward_only;    /* integrate the forward (noising) SDE instead of the reverse one */
+  int32_t precision;       /* msgm_precision */
+  float T_;                /* integration horizon override (sde_scheme.py:196-199); < 0 = sde.T */
+  const float* ts;         /* device (N+1,) time grid = linspace(0,1,N+1)*T_ as the caller computed it
+                              (sde_scheme.py:201); NULL = computed in-kernel as i*(T_/N) */
+  const float* noise;      /* device (N,B,d) standard normals, one draw per step shared by all stages
+                              (sde_scheme.py:227); NULL = in-kernel Philox4x32-10 keyed
+                              (seed, particle_offset + row, step) so results do not depend on sharding */
+  uint64_t seed;
+  uint64_t particle_offset;
+  float* traj;             /* device (N + include_t0, B, d) or NULL (keep_all_samples, sde_scheme.py:257) */
+  const int32_t* keep_step;/* device (B,) or NULL: samplesToKeep (sde_scheme.py:259-262) */
+  float* keep_out;         /* device (B,d), caller-zeroed; row k written when step index == keep_step[k] */
+  const float* T_rows;     /* device (B,) or NULL: per-particle horizon T_ (batched form of the reference's
+                              one-sample calls with T_=t[k], SDEs.py:114-116); `ts` then holds the UNIT grid
+                              linspace(0,1,N+1) and row k uses ts[i]*T_rows[k] */
+} msgm_sample_args;
+
+typedef struct msgm_ctx msgm_ctx;
+
+int msgm_abi_version(void);
+const char* msgm_last_error(void);
+/* Create / destroy the per-GPU context.  Fails with MSGM_ERR_NO_DEVICE when `device` is not sm_100. */
+int msgm_create(msgm_ctx** out, int device);
+int msgm_destroy(msgm_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t msgm_launch_count(const msgm_ctx* ctx);
+
+/* Whole sampling loop for an MLP score net, all N steps in one persistent launch; x_inout (B,d) device fp32
+ * holds x_0 on entry and x_N on exit. */
+int msgm_sample_mlp(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp,
+                    const msgm_sample_args* args, float* x_inout, int64_t B, void* stream);
+
+/* Stand-alone score-net forward a(y, s) -> (B,d) for NN.MLP.forward (NN.py:108-120); s is (B,). */
+int msgm_mlp_forward(msgm_ctx* ctx, const msgm_mlp_desc* mlp, const float* y, const float* s, float* out,
+                     int64_t B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSGM_B200_H */

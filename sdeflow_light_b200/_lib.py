@@ -1,0 +1,116 @@
+"""ctypes binding of libmsgm_b200.so (include/msgm_b200.h).  PyTorch is used only for device memory / streams.
+
+There is no CPU fallback: importing this module is cheap, but the first call that needs a kernel raises
+``RuntimeError`` if the library was not built or no sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmsgm_b200.so")
+
+SDE_SGM, SDE_MSGM_DENSE, SDE_MSGM_SPARSE = 0, 1, 2
+SCHEME_EM, SCHEME_HEUN, SCHEME_RK4 = 0, 1, 2
+PREC_FP32, PREC_F16TC = 0, 1
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
+
+
+class SdeDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("beta_min", C.c_float), ("beta_delta", C.c_float),
+                ("T", C.c_float), ("G", C.c_void_p), ("L_G", C.c_void_p)]
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [("input_dim", C.c_int32), ("premodule", C.c_int32), ("W", C.c_void_p * 4), ("b", C.c_void_p * 4)]
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [("scheme", C.c_int32), ("num_steps", C.c_int32), ("lmbd", C.c_float),
+                ("norm_correction", C.c_int32), ("include_t0", C.c_int32), ("forward_only", C.c_int32),
+                ("precision", C.c_int32), ("T_", C.c_float), ("ts", C.c_void_p), ("noise", C.c_void_p),
+                ("seed", C.c_uint64), ("particle_offset", C.c_uint64), ("traj", C.c_void_p),
+                ("keep_step", C.c_void_p), ("keep_out", C.c_void_p), ("T_rows", C.c_void_p)]
+
+
+_lib = None
+_lock = threading.Lock()
+_ctx = {}
+
+# every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
+SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
+           "msgm_sample_mlp", "msgm_mlp_forward"]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.isfile(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -m sdeflow_light_b200.build` "
+                        "(sdeflow_light_b200 has no CPU / eager fallback)")
+                L = C.CDLL(LIB_PATH)
+                L.msgm_last_error.restype = C.c_char_p
+                L.msgm_launch_count.restype = C.c_int64
+                L.msgm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+                L.msgm_destroy.argtypes = [C.c_void_p]
+                L.msgm_launch_count.argtypes = [C.c_void_p]
+                L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
+                                              C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]
+                L.msgm_mlp_forward.argtypes = [C.c_void_p, C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_int64, C.c_void_p]
+                _lib = L
+    return _lib
+
+
+def check(rc: int):
+    """Translate a negative msgm_status into the exception the reference would raise for the same misuse."""
+    if rc == 0:
+        return
+    msg = lib().msgm_last_error().decode()
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def ctx(device) -> C.c_void_p:
+    """Per-device library context (created on first use)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"sdeflow_light_b200 runs on CUDA (sm_100a) only; got device '{device}'. "
+                           "There is no CPU fallback.")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _ctx:
+        h = C.c_void_p()
+        check(lib().msgm_create(C.byref(h), idx))
+        _ctx[idx] = h
+    return _ctx[idx]
+
+
+def launch_count(device=None) -> int:
+    if device is None:
+        return sum(int(lib().msgm_launch_count(h)) for h in _ctx.values())
+    return int(lib().msgm_launch_count(ctx(device)))
+
+
+def stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor expected"
+    return C.c_void_p(t.data_ptr())
+
+
+def f32c(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()

@@ -1,0 +1,120 @@
+// C-ABI entry points of libmsgm_b200.so (see include/msgm_b200.h).  Validation + dispatch only.
+#include <cstdio>
+#include <cstring>
+
+#include "msgm_common.cuh"
+
+namespace msgm {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return MSGM_ERR_CUDA;
+}
+
+int sample_mlp_fp32(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const msgm_sample_args*, float*, int64_t,
+                    cudaStream_t);
+int mlp_forward_fp32(msgm_ctx*, const msgm_mlp_desc*, const float*, const float*, float*, int64_t, cudaStream_t);
+
+static int invalid(const char* msg) {
+  set_error(msg);
+  return MSGM_ERR_INVALID;
+}
+
+}  // namespace msgm
+
+using namespace msgm;
+
+extern "C" {
+
+int msgm_abi_version(void) { return MSGM_ABI_VERSION; }
+const char* msgm_last_error(void) { return g_err.c_str(); }
+
+int msgm_create(msgm_ctx** out, int device) {
+  if (!out) return invalid("msgm_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    set_error("msgm_create: no CUDA device (this library has no CPU fallback)");
+    return MSGM_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  MSGM_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "msgm_create: device %d is sm_%d%d; libmsgm_b200 is built for sm_100a only", device,
+             prop.major, prop.minor);
+    set_error(buf);
+    return MSGM_ERR_NO_DEVICE;
+  }
+  msgm_ctx* c = new msgm_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->launches = 0;
+  c->ws = nullptr;
+  c->ws_bytes = 0;
+  *out = c;
+  return MSGM_OK;
+}
+
+int msgm_destroy(msgm_ctx* ctx) {
+  if (!ctx) return MSGM_OK;
+  if (ctx->ws) cudaFree(ctx->ws);
+  delete ctx;
+  return MSGM_OK;
+}
+
+int64_t msgm_launch_count(const msgm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static int check_mlp(const msgm_mlp_desc* m, int d) {
+  if (!m) return invalid("mlp descriptor is NULL");
+  if (m->input_dim != d) return invalid("mlp.input_dim != sde.dim");
+  for (int l = 0; l < 4; ++l)
+    if (!m->W[l] || !m->b[l]) return invalid("mlp weight pointer is NULL");
+  return MSGM_OK;
+}
+
+int msgm_sample_mlp(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const msgm_sample_args* a,
+                    float* x, int64_t B, void* stream) {
+  if (!ctx || !sde || !a || !x) return invalid("msgm_sample_mlp: NULL argument");
+  if (B < 0) return invalid("msgm_sample_mlp: B < 0");
+  if (sde->dim < 1) return invalid("msgm_sample_mlp: dim < 1");
+  if (sde->dim > MSGM_MAX_DIM_MLP) {
+    set_error("msgm_sample_mlp: dim > 32 is not built for the MLP path (use the stage-update kernels)");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (sde->kind < MSGM_SDE_SGM || sde->kind > MSGM_SDE_MSGM_SPARSE) return invalid("unknown sde kind");
+  if (sde->kind == MSGM_SDE_MSGM_DENSE && (!sde->G || !sde->L_G)) return invalid("dense MSGM needs G and L_G");
+  if (a->scheme < MSGM_SCHEME_EM || a->scheme > MSGM_SCHEME_RK4) return invalid("unknown scheme");
+  if (a->num_steps < 1) return invalid("num_steps < 1");
+  if (a->lmbd < 0.0f || a->lmbd > 1.0f) return invalid("lmbd must be in [0,1]");
+  if ((a->keep_step == nullptr) != (a->keep_out == nullptr)) return invalid("keep_step and keep_out go together");
+  if (a->T_rows && !a->ts) return invalid("T_rows needs the unit time grid in ts");
+  if (!a->forward_only) {
+    int rc = check_mlp(mlp, sde->dim);
+    if (rc) return rc;
+  }
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (a->precision == MSGM_PREC_FP32) return sample_mlp_fp32(ctx, sde, mlp, a, x, B, (cudaStream_t)stream);
+  set_error("msgm_sample_mlp: precision mode not built");
+  return MSGM_ERR_UNSUPPORTED;
+}
+
+int msgm_mlp_forward(msgm_ctx* ctx, const msgm_mlp_desc* mlp, const float* y, const float* s, float* out, int64_t B,
+                     void* stream) {
+  if (!ctx || !mlp || !y || !s || !out) return invalid("msgm_mlp_forward: NULL argument");
+  if (mlp->input_dim < 1 || mlp->input_dim > MSGM_MAX_DIM_MLP) {
+    set_error("msgm_mlp_forward: input_dim must be in [1,32]");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  int rc = check_mlp(mlp, mlp->input_dim);
+  if (rc) return rc;
+  if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return mlp_forward_fp32(ctx, mlp, y, s, out, B, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -160,8 +160,8 @@ def run_reference(args, rank):
 
 
 def workload_config(args, where):
-    return {"workload": f"gaussmix_d{args.dim}_msgm_dense_mlp128_rk4_n{N_SDE_STEPS}_{PARTICLES_PER_GPU}particles_per_gpu",
-            "dim": args.dim, "particles_per_gpu": PARTICLES_PER_GPU, "sde_steps": N_SDE_STEPS, "scheme": "rk4",
+    return {"workload": f"gaussmix_d{args.dim}_msgm_dense_mlp128_rk4_n{N_SDE_STEPS}_{args.particles}particles_per_gpu",
+            "dim": args.dim, "particles_per_gpu": args.particles, "sde_steps": N_SDE_STEPS, "scheme": "rk4",
             "lmbd": 0.0, "norm_correction": True, "precision": args.precision if where == "gpu" else "fp32",
             "l2_policy": "working set is on-chip (weights in smem, state in registers); x_0/x_N (2 x 4*B*d bytes) "
                          "streamed once per call; a 256 MB buffer is rewritten between timed calls to flush L2"}
@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--dim", type=int, default=16)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "f16tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU (default 2^20)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -197,7 +198,7 @@ def main():
 
     sde, mlp = build_problem(args.dim)
     P, gen = package_objects(sde, mlp, dev)
-    B, N = PARTICLES_PER_GPU, N_SDE_STEPS
+    B, N = args.particles, N_SDE_STEPS
     torch.manual_seed(1234 + rank)
     x0_host = (torch.randn(B, args.dim) * 1.5).pin_memory()
     x0_dev = x0_host.to(dev)

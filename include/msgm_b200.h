@@ -97,6 +97,9 @@ int msgm_create(msgm_ctx** out, int device);
 int msgm_destroy(msgm_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t msgm_launch_count(const msgm_ctx* ctx);
+/* Debug: synchronises the device and returns the kernel-side flag word (bit 0: a bounded mbarrier wait inside
+ * the tensor-core sampler timed out).  Used by the tests; 0 in a healthy run. */
+int msgm_debug_flags(msgm_ctx* ctx, int32_t* out_host);
 
 /* Whole sampling loop for an MLP score net, all N steps in one persistent launch; x_inout (B,d) device fp32
  * holds x_0 on entry and x_N on exit. */

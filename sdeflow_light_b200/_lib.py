@@ -43,7 +43,7 @@ _ctx = {}
 
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
-           "msgm_sample_mlp", "msgm_mlp_forward"]
+           "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags"]
 
 
 def lib() -> C.CDLL:
@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
                 L.msgm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
                 L.msgm_destroy.argtypes = [C.c_void_p]
                 L.msgm_launch_count.argtypes = [C.c_void_p]
+                L.msgm_debug_flags.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]
                 L.msgm_mlp_forward.argtypes = [C.c_void_p, C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -99,6 +100,12 @@ def launch_count(device=None) -> int:
     if device is None:
         return sum(int(lib().msgm_launch_count(h)) for h in _ctx.values())
     return int(lib().msgm_launch_count(ctx(device)))
+
+
+def debug_flags(device) -> int:
+    out = C.c_int32(0)
+    check(lib().msgm_debug_flags(ctx(device), C.byref(out)))
+    return int(out.value)
 
 
 def stream_ptr(device) -> C.c_void_p:

@@ -15,6 +15,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 int sample_mlp_fp32(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const msgm_sample_args*, float*, int64_t,
                     cudaStream_t);
+int sample_mlp_tc(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const msgm_sample_args*, float*, int64_t,
+                  cudaStream_t);
 int mlp_forward_fp32(msgm_ctx*, const msgm_mlp_desc*, const float*, const float*, float*, int64_t, cudaStream_t);
 
 static int invalid(const char* msg) {
@@ -55,6 +57,15 @@ int msgm_create(msgm_ctx** out, int device) {
   c->launches = 0;
   c->ws = nullptr;
   c->ws_bytes = 0;
+  // fixed device workspace: [0,256) debug flags, [256,256K) packed fp16 weight image, [256K,512K) padded G
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&c->ws, 1 << 19);
+  if (e == cudaSuccess) e = cudaMemset(c->ws, 0, 1 << 19);
+  if (e != cudaSuccess) {
+    delete c;
+    return cuda_fail(e, "msgm_create workspace");
+  }
+  c->ws_bytes = 1 << 19;
   *out = c;
   return MSGM_OK;
 }
@@ -67,6 +78,14 @@ int msgm_destroy(msgm_ctx* ctx) {
 }
 
 int64_t msgm_launch_count(const msgm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int msgm_debug_flags(msgm_ctx* ctx, int32_t* out_host) {
+  if (!ctx || !out_host) return invalid("msgm_debug_flags: NULL argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  MSGM_CUDA_TRY(cudaDeviceSynchronize());
+  MSGM_CUDA_TRY(cudaMemcpy(out_host, ctx->ws, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return MSGM_OK;
+}
 
 static int check_mlp(const msgm_mlp_desc* m, int d) {
   if (!m) return invalid("mlp descriptor is NULL");
@@ -99,8 +118,8 @@ int msgm_sample_mlp(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   if (a->precision == MSGM_PREC_FP32) return sample_mlp_fp32(ctx, sde, mlp, a, x, B, (cudaStream_t)stream);
-  set_error("msgm_sample_mlp: precision mode not built");
-  return MSGM_ERR_UNSUPPORTED;
+  if (a->precision == MSGM_PREC_F16TC) return sample_mlp_tc(ctx, sde, mlp, a, x, B, (cudaStream_t)stream);
+  return invalid("msgm_sample_mlp: unknown precision");
 }
 
 int msgm_mlp_forward(msgm_ctx* ctx, const msgm_mlp_desc* mlp, const float* y, const float* s, float* out, int64_t B,

@@ -562,18 +562,16 @@ int sample_mlp_fp32(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc
   P.B = B;
   const int DP = d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32;
   if (sde->kind == MSGM_SDE_MSGM_DENSE && DP == 32) {
-    const size_t need = sizeof(float) * 32 * 32 * 32;
-    if (ctx->ws_bytes < need) {
-      if (ctx->ws) cudaFree(ctx->ws);
-      ctx->ws = nullptr;
-      ctx->ws_bytes = 0;
-      MSGM_CUDA_TRY(cudaMalloc(&ctx->ws, need));
-      ctx->ws_bytes = need;
+    const size_t off = 1 << 18;  // second half of the context workspace (first half: tensor-core weight image)
+    if (ctx->ws_bytes < off + sizeof(float) * 32 * 32 * 32) {
+      set_error("internal: context workspace too small");
+      return MSGM_ERR_INVALID;
     }
-    pad_G32_kernel<<<128, 256, 0, stream>>>(sde->G, d, (float*)ctx->ws);
+    float* gpad = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ctx->ws) + off);
+    pad_G32_kernel<<<128, 256, 0, stream>>>(sde->G, d, gpad);
     ctx->launches += 1;
     MSGM_CUDA_TRY(cudaGetLastError());
-    P.G = (const float*)ctx->ws;
+    P.G = gpad;
   }
   switch (DP) {
     case 2: return launch_sample_kind<2>(ctx, sde->kind, P, stream);

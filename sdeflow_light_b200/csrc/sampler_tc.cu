@@ -1,0 +1,664 @@
+// Tensor-core sampler (MSGM_PREC_F16TC): the whole EM / Heun / RK4-Stratonovich loop of sde_scheme.py:43-269
+// for the MLP score net (NN.py:73-120) in ONE persistent launch, with the four dense layers on tcgen05.
+//
+//   * one CTA = one tile of 128 particles, TWO CTAs per SM (each allocates 256 TMEM columns) so that one CTA's
+//     activation epilogue (MUFU-bound) overlaps the other CTA's MMAs;
+//   * warps 0-3: thread == particle row == TMEM lane.  The thread keeps x, the RK sum, dW and r0 in registers for
+//     all N steps, so a particle makes one HBM round trip per sampler call;
+//   * warp 4: lane 0 issues tcgen05.mma (A operand = activations in TMEM, written there by the epilogue threads
+//     as packed fp16; B operand = weights resident in shared memory as canonical no-swizzle K-major core matrices,
+//     loaded once per CTA with TMA bulk copies); accumulators live in TMEM (fp32);
+//   * biases ride on the tensor pipe: an extra K=16 slice whose A operand is a constant "ones" TMEM block;
+//   * Swish(z) = h tanh(h) + h with h = z/2; the 1/2 is folded into the packed weights, so one MUFU per activation;
+//   * layer 1 (K = d+2) is evaluated in split precision (u_hi, u_lo) x (W_hi, W_lo) so that time, log-radius and
+//     direction inputs keep ~22 mantissa bits at no extra cost (they fit the zero padding of the K=16 slices).
+//
+// Handshake per layer: epilogue threads -> bar_a (128 arrivals: "A operand complete, D consumed") -> MMA warp
+// issues -> tcgen05.commit -> bar_d -> epilogue threads read D.  All waits are bounded; a timeout sets a flag in
+// the context workspace (msgm_debug_flags) instead of hanging the GPU.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "msgm_common.cuh"
+
+namespace msgm {
+
+constexpr int TM = 128;            // particles per CTA tile (= UMMA M = TMEM lanes)
+constexpr int TC_THREADS = 160;    // 4 epilogue warps + 1 MMA warp
+constexpr uint32_t COL_D = 0;      // accumulator: 128 fp32 columns
+constexpr uint32_t COL_A = 128;    // activations / layer-1 operand: 64 columns of packed fp16 pairs
+constexpr uint32_t COL_ONES = 192; // constant K=16 slice [1,1,0,...,0]
+constexpr uint32_t TMEM_COLS = 256;
+
+template <int DP>
+struct TcLayout {
+  static constexpr int MP = DP + 2;                            // layer-1 slots: y_0..y_{DP-1}, log r, s
+  static constexpr int K1 = ((3 * MP + 2 + 15) / 16) * 16;     // [u_hi | u_lo | u_hi | 1 | 1 | 0...]
+  static constexpr int W1_BYTES = K1 * 128 * 2;                // K1/8 chunks x 2048 B
+  static constexpr int WH_BYTES = (128 + 16) * 128 * 2;        // bias slice + 8 slices
+  static constexpr int W4_BYTES = (128 + 16) * 16 * 2;         // N = 16 rows
+  static constexpr int oW1 = 0;
+  static constexpr int oW2 = oW1 + W1_BYTES;
+  static constexpr int oW3 = oW2 + WH_BYTES;
+  static constexpr int oW4 = oW3 + WH_BYTES;
+  static constexpr int IMG_BYTES = oW4 + W4_BYTES;             // what the pack kernel writes / TMA copies
+  static constexpr int oG = IMG_BYTES;                         // fp32 [DP][DP][DP] (dense)
+  static constexpr int oLG = oG + 4 * DP * DP * DP;            // fp32 [DP][DP]
+  static constexpr int oBar = oLG + 4 * DP * DP;               // 3 mbarriers + tmem slot
+  static constexpr int SMEM_BYTES = oBar + 64;
+};
+
+struct TcParams {
+  int d, pre;
+  float bmin, bdel, Tsde;
+  const float* G;
+  const float* LG;
+  const unsigned char* img;  // packed weight image (global)
+  int scheme, N, nc, inc_t0;
+  float lmbd, delta, delta_half, sqrt_delta;
+  const float* ts;
+  const float* noise;
+  unsigned long long seed, poff;
+  float* traj;
+  const int* keep_step;
+  float* keep_out;
+  float* x;
+  long long B;
+  int* flags;  // [0] = wait timeout seen
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: returns false (and raises the debug flag) instead of hanging if the partner never arrives.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* flags) {
+  if (mbar_try(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (clock64() - t0 < 4000000000LL)  // ~2 s at 2 GHz
+    if (mbar_try(bar, parity)) return true;
+  atomicExch(flags, 1);
+  return false;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle smem matrix descriptor (validated on B200 by tools/tc_probe.cu):
+// LBO = bytes between the two 8-element k-chunks of a K=16 slice, SBO = bytes between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);  // D=f32, A=B=f16, K-major both
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+#define TMEM_LD32(taddr, r)                                                                                         \
+  asm volatile(                                                                                                     \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28," \
+      "%29,%30,%31}, [%32];"                                                                                        \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),      \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),     \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                   \
+      : "r"(taddr)                                                                                                  \
+      : "memory")
+#define TMEM_LD16(taddr, r)                                                                                      \
+  asm volatile(                                                                                                  \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"   \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),           \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])     \
+      : "r"(taddr)                                                                                               \
+      : "memory")
+#define TMEM_ST8(taddr, r)                                                                                  \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                     \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),   \
+                 "r"(r[7])                                                                                  \
+               : "memory")
+#define TMEM_ST16(taddr, r)                                                                                      \
+  asm volatile(                                                                                                  \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"   \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),      \
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])             \
+      : "memory")
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
+  return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+}
+
+// Activation epilogue of one hidden layer: D (128 fp32 cols, = z/2) -> Swish -> packed fp16 -> A (64 cols).
+__device__ __forceinline__ void swish_epilogue(uint32_t lane_base) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32], q[16];
+    TMEM_LD32(lane_base + COL_D + c * 32, r);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float h0 = __uint_as_float(r[2 * j]), h1 = __uint_as_float(r[2 * j + 1]);
+      const float s0 = fmaf(h0, tanh_fast(h0), h0);  // z sigmoid(z) with z = 2h   (NN.py:52-53)
+      const float s1 = fmaf(h1, tanh_fast(h1), h1);
+      q[j] = pack_f16x2(s0, s1);
+    }
+    TMEM_ST16(lane_base + COL_A + c * 16, q);
+  }
+  tc_wait_st();
+}
+
+template <int DP, int KIND>
+__global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_constant__ TcParams P) {
+  using L = TcLayout<DP>;
+  constexpr int MP = L::MP, K1 = L::K1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* sG = reinterpret_cast<float*>(smem + L::oG);
+  float* sLG = reinterpret_cast<float*>(smem + L::oLG);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  uint64_t* bar_a = bar_w + 1;
+  uint64_t* bar_d = bar_w + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = P.d;
+  const int nstage = P.scheme == MSGM_SCHEME_RK4 ? 4 : (P.scheme == MSGM_SCHEME_HEUN ? 2 : 1);
+  const long long ntiles = (P.B + TM - 1) / TM;
+
+  // ---- setup ----------------------------------------------------------------------------------------------------
+  if (tid == 128) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a, 128);
+    mbar_init(bar_d, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (KIND == MSGM_SDE_MSGM_DENSE) {
+    for (int e = tid; e < DP * DP * DP; e += TC_THREADS) {
+      int i = e / (DP * DP), j = (e / DP) % DP, k = e % DP;
+      sG[e] = (i < d && j < d && k < d) ? __ldg(P.G + (i * d + j) * d + k) : 0.0f;
+    }
+    for (int e = tid; e < DP * DP; e += TC_THREADS) {
+      int i = e / DP, j = e % DP;
+      sLG[e] = (i < d && j < d) ? __ldg(P.LG + i * d + j) : 0.0f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  if (tid == 128) {  // weights: one TMA bulk copy per layer image, all landing on bar_w
+    mbar_expect_tx(bar_w, (uint32_t)L::IMG_BYTES);
+    tma_bulk_g2s(smem + L::oW1, P.img + L::oW1, L::W1_BYTES, bar_w);
+    tma_bulk_g2s(smem + L::oW2, P.img + L::oW2, L::WH_BYTES, bar_w);
+    tma_bulk_g2s(smem + L::oW3, P.img + L::oW3, L::WH_BYTES, bar_w);
+    tma_bulk_g2s(smem + L::oW4, P.img + L::oW4, L::W4_BYTES, bar_w);
+  }
+
+  if (warp == 4) {
+    // =========================================== MMA issuer ===================================================
+    if (lane == 0) {
+      bool ok = mbar_wait(bar_w, 0, P.flags);
+      const uint32_t idesc_h = umma_idesc_f16(128, 128), idesc_o = umma_idesc_f16(128, 16);
+      const uint32_t sW1 = smem_u32(smem + L::oW1), sW2 = smem_u32(smem + L::oW2), sW3 = smem_u32(smem + L::oW3),
+                     sW4 = smem_u32(smem + L::oW4);
+      uint32_t ph = 0;
+      for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+        for (int it = 0; it < P.N * nstage && ok; ++it) {
+          // layer 1: K1/16 slices, bias rides in the padding of the last one
+          ok = mbar_wait(bar_a, ph, P.flags); ph ^= 1; tc_fence_after();
+#pragma unroll
+          for (int s = 0; s < K1 / 16; ++s)
+            umma_ts(tbase + COL_D, tbase + COL_A + 8 * s, umma_desc(sW1 + s * 4096, 2048, 128), idesc_h, s > 0);
+          umma_commit(bar_d);
+          // layers 2, 3: ones-slice (bias) + 8 slices
+#pragma unroll
+          for (int l = 0; l < 2; ++l) {
+            const uint32_t sW = l == 0 ? sW2 : sW3;
+            ok = ok && mbar_wait(bar_a, ph, P.flags); ph ^= 1; tc_fence_after();
+            umma_ts(tbase + COL_D, tbase + COL_ONES, umma_desc(sW, 2048, 128), idesc_h, 0);
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              umma_ts(tbase + COL_D, tbase + COL_A + 8 * s, umma_desc(sW + (s + 1) * 4096, 2048, 128), idesc_h, 1);
+            umma_commit(bar_d);
+          }
+          // output layer: N = 16
+          ok = ok && mbar_wait(bar_a, ph, P.flags); ph ^= 1; tc_fence_after();
+          umma_ts(tbase + COL_D, tbase + COL_ONES, umma_desc(sW4, 256, 128), idesc_o, 0);
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            umma_ts(tbase + COL_D, tbase + COL_A + 8 * s, umma_desc(sW4 + (s + 1) * 512, 256, 128), idesc_o, 1);
+          umma_commit(bar_d);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================================= particle threads ================================================
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    {  // constant ones slice: k = 0,1 -> 1.0 ; rest 0
+      uint32_t o[8] = {0x3C003C00u, 0, 0, 0, 0, 0, 0, 0};
+      TMEM_ST8(lane_base + COL_ONES, o);
+      tc_wait_st();
+    }
+    const float lm = P.lmbd;
+    const float c_w = sqrtf(1.0f - lm);
+    const bool ito = (P.scheme == MSGM_SCHEME_EM);
+    const float c_f = ito ? (1.0f - 2.0f * lm) : -lm;
+    const float delta = P.delta;
+    const float c_a = delta * (1.0f - 0.5f * lm);
+    uint32_t ph = 0;
+    bool ok = true;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long gp = tile * TM + tid;
+      const bool live = gp < P.B;
+      float x[DP], y[DP], ks[DP], dw[DP];
+#pragma unroll
+      for (int c = 0; c < DP; ++c) {
+        x[c] = (live && c < d) ? P.x[gp * d + c] : ((c == 0 && !live) ? 1.0f : 0.0f);
+        y[c] = x[c];
+        ks[c] = 0.0f;
+      }
+      float r0 = 0.0f;
+      if (P.nc) {
+#pragma unroll
+        for (int c = 0; c < DP; ++c) r0 = fmaf(x[c], x[c], r0);
+        r0 = sqrtf(r0);
+      }
+      if (P.traj && P.inc_t0 && live)
+        for (int c = 0; c < d; ++c) P.traj[gp * d + c] = x[c];
+      const int keep = (P.keep_step && live) ? P.keep_step[gp] : -1;
+
+      for (int step = 0; step < P.N; ++step) {
+        const float tcur = P.ts ? __ldg(P.ts + step) : __fmul_rn((float)step, delta);
+#pragma unroll
+        for (int c4 = 0; c4 < DP; c4 += 4) {
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (P.noise) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c4 + c < d && live) z[c] = __ldg(P.noise + ((long long)step * P.B + gp) * d + c4 + c);
+          } else {
+            const float4 n4 = philox_normal4(P.seed, P.poff + (unsigned long long)gp, (uint32_t)step, (uint32_t)(c4 >> 2));
+            z[0] = n4.x; z[1] = n4.y; z[2] = n4.z; z[3] = n4.w;
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c4 + c < DP) dw[c4 + c] = (c4 + c < d) ? P.sqrt_delta * z[c] : 0.0f;
+        }
+
+        for (int st = 0; st < nstage; ++st) {
+          float tst = tcur;
+          if (st > 0) tst = (nstage == 4 && st < 3) ? __fadd_rn(tcur, P.delta_half) : __fadd_rn(tcur, delta);
+          const float sv = __fsub_rn(P.Tsde, tst);
+          const float bt = beta_of(P.bmin, P.bdel, sv);
+          const float sb = sqrtf(bt);
+
+          // ---- layer-1 operand: u = [y / (|y|+eps) (or y), log(|y|+eps) (or 0), s], split hi/lo ------------------
+          {
+            float u[MP];
+            if (P.pre) {
+              float r = 0.0f;
+#pragma unroll
+              for (int c = 0; c < DP; ++c) r = fmaf(y[c], y[c], r);
+              const float rn = sqrtf(r) + 1e-6f;
+#pragma unroll
+              for (int c = 0; c < DP; ++c) u[c] = y[c] / rn;
+              u[DP] = logf(rn);
+            } else {
+#pragma unroll
+              for (int c = 0; c < DP; ++c) u[c] = y[c];
+              u[DP] = 0.0f;
+            }
+            u[DP + 1] = sv;
+            __half hk[K1];
+#pragma unroll
+            for (int k = 0; k < K1; ++k) hk[k] = __ushort_as_half(0);
+#pragma unroll
+            for (int j = 0; j < MP; ++j) {
+              __half hi, lo;
+              split_f16(u[j], hi, lo);
+              hk[j] = hi;
+              hk[MP + j] = lo;
+              hk[2 * MP + j] = hi;
+            }
+            hk[3 * MP] = __ushort_as_half(0x3C00);
+            hk[3 * MP + 1] = __ushort_as_half(0x3C00);
+            uint32_t q[K1 / 2];
+#pragma unroll
+            for (int j = 0; j < K1 / 2; ++j) q[j] = pack_h2(hk[2 * j], hk[2 * j + 1]);
+#pragma unroll
+            for (int c = 0; c < K1 / 16; ++c) TMEM_ST8(lane_base + COL_A + 8 * c, (q + 8 * c));
+            tc_wait_st();
+          }
+          tc_fence_before();
+          mbar_arrive(bar_a);
+
+          // ---- hidden layers ---------------------------------------------------------------------------------------
+#pragma unroll 1
+          for (int l = 0; l < 3; ++l) {
+            ok = ok && mbar_wait(bar_d, ph, P.flags); ph ^= 1; tc_fence_after();
+            swish_epilogue(lane_base);
+            tc_fence_before();
+            mbar_arrive(bar_a);
+          }
+          // ---- output layer -> a ----------------------------------------------------------------------------------------
+          float a[DP];
+          {
+            ok = ok && mbar_wait(bar_d, ph, P.flags); ph ^= 1; tc_fence_after();
+            uint32_t r[16];
+            TMEM_LD16(lane_base + COL_D, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < DP; ++c) a[c] = __uint_as_float(r[c]);
+          }
+
+          // ---- stage increment K = delta * drift + sigma . dW (same algebra as sampler_fp32.cu) --------------------------
+          float K[DP];
+          if (KIND == MSGM_SDE_SGM) {
+#pragma unroll
+            for (int c = 0; c < DP; ++c)
+              K[c] = delta * ((1.0f - 0.5f * lm) * (sb * a[c]) + 0.5f * bt * y[c]) + (c_w * sb) * dw[c];
+          } else {
+            float w[DP];
+#pragma unroll
+            for (int c = 0; c < DP; ++c) w[c] = fmaf(c_a, a[c], c_w * dw[c]);
+            if (KIND == MSGM_SDE_MSGM_SPARSE) {
+#pragma unroll
+              for (int c = 0; c < DP; ++c) {
+                // cyclic neighbours with the runtime dimension d (SDEs.py:369-399)
+                float yn = 0.f, yp = 0.f, wp = 0.f;
+#pragma unroll
+                for (int e = 0; e < DP; ++e) {
+                  const int cn = (c + 1 == d) ? 0 : c + 1, cp = (c == 0) ? d - 1 : c - 1;
+                  yn = (e == cn) ? y[e] : yn;
+                  yp = (e == cp) ? y[e] : yp;
+                  wp = (e == cp) ? w[e] : wp;
+                }
+                float acc = (SQRT_HALF * (sb * yn)) * w[c] + (-SQRT_HALF * (sb * yp)) * wp;
+                acc = fmaf(delta * c_f, 0.5f * bt * y[c], acc);
+                K[c] = c < d ? acc : 0.0f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < DP; ++i) {
+                float acc = 0.0f, fc = 0.0f;
+                if constexpr (DP >= 4) {
+#pragma unroll
+                  for (int k4 = 0; k4 < DP; k4 += 4) {
+                    float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < DP; ++j) {
+                      const float4 g4 = *reinterpret_cast<const float4*>(sG + (i * DP + j) * DP + k4);
+                      u4.x = fmaf(g4.x, y[j], u4.x);
+                      u4.y = fmaf(g4.y, y[j], u4.y);
+                      u4.z = fmaf(g4.z, y[j], u4.z);
+                      u4.w = fmaf(g4.w, y[j], u4.w);
+                    }
+                    acc = fmaf(u4.x, w[k4], acc);
+                    acc = fmaf(u4.y, w[k4 + 1], acc);
+                    acc = fmaf(u4.z, w[k4 + 2], acc);
+                    acc = fmaf(u4.w, w[k4 + 3], acc);
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < DP; ++k) {
+                    float uu = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < DP; ++j) uu = fmaf(sG[(i * DP + j) * DP + k], y[j], uu);
+                    acc = fmaf(uu, w[k], acc);
+                  }
+                }
+                if (c_f != 0.0f) {
+#pragma unroll
+                  for (int j = 0; j < DP; ++j) fc = fmaf(sLG[i * DP + j], y[j], fc);
+                }
+                K[i] = fmaf(delta * c_f, bt * fc, sb * acc);
+              }
+            }
+          }
+
+          // ---- Runge-Kutta bookkeeping --------------------------------------------------------------------------------------
+#pragma unroll
+          for (int c = 0; c < DP; ++c) {
+            if (nstage == 1) {
+              x[c] = x[c] + K[c];
+            } else if (nstage == 2) {
+              if (st == 0) { ks[c] = K[c]; y[c] = x[c] + K[c]; }
+              else { x[c] = x[c] + (ks[c] + K[c]) / 2.0f; }
+            } else {
+              if (st == 0) { ks[c] = K[c]; y[c] = x[c] + K[c] / 2.0f; }
+              else if (st == 1) { ks[c] = ks[c] + 2.0f * K[c]; y[c] = x[c] + K[c] / 2.0f; }
+              else if (st == 2) { ks[c] = ks[c] + 2.0f * K[c]; y[c] = x[c] + K[c]; }
+              else { x[c] = x[c] + (ks[c] + K[c]) / 6.0f; }
+            }
+          }
+        }  // stages
+
+        if (P.nc) {
+          float r = 0.0f;
+#pragma unroll
+          for (int c = 0; c < DP; ++c) r = fmaf(x[c], x[c], r);
+          const float sc = r0 / sqrtf(r);
+#pragma unroll
+          for (int c = 0; c < DP; ++c) x[c] *= sc;
+        }
+#pragma unroll
+        for (int c = 0; c < DP; ++c) y[c] = x[c];
+        if (P.traj && live) {
+          float* dst = P.traj + ((long long)(step + P.inc_t0) * P.B + gp) * d;
+#pragma unroll
+          for (int c = 0; c < DP; ++c)
+            if (c < d) dst[c] = x[c];
+        }
+        if (keep >= 0 && keep == step + P.inc_t0) {
+#pragma unroll
+          for (int c = 0; c < DP; ++c)
+            if (c < d) P.keep_out[gp * d + c] = x[c];
+        }
+      }  // steps
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < DP; ++c)
+          if (c < d) P.x[gp * d + c] = x[c];
+      }
+    }  // tiles
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(TMEM_COLS));
+}
+
+// ---- weight packing: torch Linear layout -> fp16 core-matrix images ----------------------------------------------
+// Image element order: [k/8][n/8][n%8][k%8] (K-major core matrices, 128 B each; LBO = N*16 B, SBO = 128 B).
+template <int DP>
+__global__ void pack_mlp_tc_kernel(int d, int pre, const float* W0, const float* b0, const float* W1, const float* b1,
+                                   const float* W2, const float* b2, const float* W3, const float* b3,
+                                   unsigned char* img) {
+  using L = TcLayout<DP>;
+  constexpr int MP = L::MP, K1 = L::K1;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // one fp16 element of the image
+  if (e >= L::IMG_BYTES / 2) return;
+  const int byte = e * 2;
+  int layer, off, Nrows;
+  if (byte < L::oW2) { layer = 0; off = (byte - L::oW1) / 2; Nrows = 128; }
+  else if (byte < L::oW3) { layer = 1; off = (byte - L::oW2) / 2; Nrows = 128; }
+  else if (byte < L::oW4) { layer = 2; off = (byte - L::oW3) / 2; Nrows = 128; }
+  else { layer = 3; off = (byte - L::oW4) / 2; Nrows = 16; }
+  const int chunk = off / (Nrows * 8), rem = off % (Nrows * 8);
+  const int n = (rem / 64) * 8 + (rem % 64) / 8, k = chunk * 8 + (rem % 8);
+  float v = 0.0f;
+  bool want_lo = false;
+  if (layer == 0) {
+    // k slots: [hi(MP) | lo(MP) | hi(MP) | 1 | 1]; B rows: [W_hi | W_hi | W_lo | b_hi | b_lo]; all scaled by 1/2
+    const int kin = d + 1 + pre;
+    auto col_of_slot = [&](int j) -> int {  // reference column feeding slot j, or -1
+      if (j < DP) return j < d ? j : -1;
+      if (j == DP) return pre ? d : -1;
+      return d + pre;  // time
+    };
+    if (k < 3 * MP) {
+      const int j = k % MP, col = col_of_slot(j);
+      want_lo = (k >= 2 * MP);
+      v = col >= 0 ? 0.5f * W0[n * kin + col] : 0.0f;
+    } else if (k == 3 * MP) { v = 0.5f * b0[n]; }
+    else if (k == 3 * MP + 1) { v = 0.5f * b0[n]; want_lo = true; }
+  } else {
+    const float* W = layer == 1 ? W1 : (layer == 2 ? W2 : W3);
+    const float* b = layer == 1 ? b1 : (layer == 2 ? b2 : b3);
+    const float sc = layer == 3 ? 1.0f : 0.5f;
+    const bool valid = layer < 3 || n < d;
+    if (k == 0) { v = valid ? sc * b[n] : 0.0f; }
+    else if (k == 1) { v = valid ? sc * b[n] : 0.0f; want_lo = true; }
+    else if (k >= 16) { v = valid ? sc * W[n * 128 + (k - 16)] : 0.0f; }
+  }
+  __half hi = __float2half_rn(v);
+  __half out = want_lo ? __float2half_rn(v - __half2float(hi)) : hi;
+  reinterpret_cast<__half*>(img)[e] = out;
+  (void)K1;
+}
+
+// ---- host dispatch ---------------------------------------------------------------------------------------------------
+static int ensure_ws(msgm_ctx* ctx, size_t need) {
+  if (ctx->ws_bytes >= need) return MSGM_OK;
+  set_error("internal: context workspace too small");
+  return MSGM_ERR_INVALID;
+}
+
+template <int DP, int KIND>
+static int launch_tc(msgm_ctx* ctx, const msgm_mlp_desc* m, TcParams& P, cudaStream_t stream) {
+  using L = TcLayout<DP>;
+  const size_t need = 256 + (size_t)L::IMG_BYTES;
+  int rc = ensure_ws(ctx, need);
+  if (rc) return rc;
+  P.flags = reinterpret_cast<int*>(ctx->ws);
+  unsigned char* img = reinterpret_cast<unsigned char*>(ctx->ws) + 256;
+  P.img = img;
+  MSGM_CUDA_TRY(cudaMemsetAsync(ctx->ws, 0, 256, stream));
+  const int nel = L::IMG_BYTES / 2;
+  pack_mlp_tc_kernel<DP><<<(nel + 255) / 256, 256, 0, stream>>>(P.d, P.pre, m->W[0], m->b[0], m->W[1], m->b[1], m->W[2],
+                                                                m->b[2], m->W[3], m->b[3], img);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  auto kern = sample_tc_kernel<DP, KIND>;
+  MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES));
+  const long long ntiles = (P.B + TM - 1) / TM;
+  const int grid = (int)std::min<long long>(ntiles, 2LL * ctx->num_sms);
+  kern<<<grid, TC_THREADS, L::SMEM_BYTES, stream>>>(P);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+template <int DP>
+static int launch_tc_kind(msgm_ctx* ctx, int kind, const msgm_mlp_desc* m, TcParams& P, cudaStream_t stream) {
+  switch (kind) {
+    case MSGM_SDE_SGM: return launch_tc<DP, MSGM_SDE_SGM>(ctx, m, P, stream);
+    case MSGM_SDE_MSGM_DENSE: return launch_tc<DP, MSGM_SDE_MSGM_DENSE>(ctx, m, P, stream);
+    case MSGM_SDE_MSGM_SPARSE: return launch_tc<DP, MSGM_SDE_MSGM_SPARSE>(ctx, m, P, stream);
+  }
+  set_error("unknown sde kind");
+  return MSGM_ERR_INVALID;
+}
+
+int sample_mlp_tc(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const msgm_sample_args* a, float* x,
+                  int64_t B, cudaStream_t stream) {
+  const int d = sde->dim;
+  if (a->forward_only || a->T_rows) {
+    set_error("f16tc precision: the forward adapter / per-row horizons have no net and run in fp32 mode");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (d > 16 || (sde->kind == MSGM_SDE_MSGM_DENSE && d > 8)) {
+    set_error("f16tc precision is built for d <= 8 (dense MSGM) or d <= 16 (SGM / sparse MSGM); use fp32");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  TcParams P{};
+  P.d = d;
+  P.pre = mlp->premodule;
+  P.bmin = sde->beta_min;
+  P.bdel = sde->beta_delta;
+  P.Tsde = sde->T;
+  P.G = sde->G;
+  P.LG = sde->L_G;
+  P.scheme = a->scheme;
+  P.N = a->num_steps;
+  P.nc = a->norm_correction;
+  P.inc_t0 = a->include_t0 ? 1 : 0;
+  P.lmbd = a->lmbd;
+  const double Trun = a->T_ >= 0.0f ? (double)a->T_ : (double)sde->T;
+  const double delta = Trun / (double)a->num_steps;
+  P.delta = (float)delta;
+  P.delta_half = (float)(delta / 2.0);
+  P.sqrt_delta = (float)std::sqrt(delta);
+  P.ts = a->ts;
+  P.noise = a->noise;
+  P.seed = a->seed;
+  P.poff = a->particle_offset;
+  P.traj = a->traj;
+  P.keep_step = a->keep_step;
+  P.keep_out = a->keep_out;
+  P.x = x;
+  P.B = B;
+  if (d <= 2) return launch_tc_kind<2>(ctx, sde->kind, mlp, P, stream);
+  if (d <= 4) return launch_tc_kind<4>(ctx, sde->kind, mlp, P, stream);
+  if (d <= 8) return launch_tc_kind<8>(ctx, sde->kind, mlp, P, stream);
+  return launch_tc_kind<16>(ctx, sde->kind, mlp, P, stream);
+}
+
+}  // namespace msgm

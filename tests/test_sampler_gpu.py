@@ -144,3 +144,55 @@ def test_mlp_forward_kernel():
         with torch.no_grad():
             out = net(y.to(DEV), s.to(DEV))
         _close(f"mlp-fwd-d{d}", out, ref, 2e-5, 2e-5)
+
+
+# ---- tensor-core (tcgen05, fp16 operands / fp32 accumulate) mode ---------------------------------------------------
+# Stated tolerance of the f16tc mode: the hidden layers round weights and activations to fp16 (11-bit mantissa), so
+# per-stage score values agree to ~1e-3 relative; trajectories are compared at TC_ATOL + TC_RTOL |x| after N steps.
+TC_ATOL, TC_RTOL = 2e-2, 2e-2
+TC_CASES = [
+    ("msgm_dense", 2, True, "rk4", 0.0, True, 1000, 16),
+    ("msgm_dense", 2, True, "em", 0.0, True, 300, 1),
+    ("msgm_dense", 4, True, "heun", 0.25, True, 130, 16),
+    ("msgm_dense", 8, True, "rk4", 0.0, True, 257, 12),
+    ("msgm_dense", 5, False, "em", 0.5, True, 77, 16),
+    ("msgm_sparse", 2, True, "rk4", 0.0, True, 100, 16),
+    ("msgm_sparse", 16, True, "rk4", 0.0, True, 129, 8),
+    ("msgm_sparse", 7, True, "em", 0.3, True, 100, 16),
+    ("sgm", 2, False, "rk4", 0.0, False, 1000, 16),
+    ("sgm", 16, False, "heun", 0.5, False, 63, 8),
+]
+
+
+@pytest.mark.parametrize("kind,d,pre,scheme,lmbd,nc,B,N", TC_CASES)
+def test_tc_against_oracle(kind, d, pre, scheme, lmbd, nc, B, N):
+    torch.manual_seed(2000 + d)
+    sde = O.make_sgm(d) if kind == "sgm" else O.make_msgm(torch.randn(256, d) * 1.5, dense=(kind == "msgm_dense"))
+    mlp = O.init_mlp(d, pre, seed=d, scale=6.0)
+    x0 = torch.randn(B, d) * 1.3
+    noise = torch.randn(N, B, d)
+    ref = O.integrate(O.OReverse(sde, mlp), x0, N, scheme, lmbd, True, None, True, None, nc, noise=noise)
+    _, _, gen = Bd.from_oracle(sde, mlp, DEV)
+    out = Bd.SAMPLERS[scheme](gen, x0.to(DEV), N, lmbd=lmbd, keep_all_samples=True, include_t0=True,
+                              norm_correction=nc, noise=noise, precision="f16tc")
+    assert P._lib.debug_flags(DEV) == 0, "tensor-core sampler: a bounded mbarrier wait timed out"
+    _close(f"tc-{kind}-d{d}-{scheme}-N{N}", out, ref, TC_ATOL, TC_RTOL)
+
+
+def test_tc_matches_fp32_statistics():
+    """f16tc vs fp32 kernels with the same Philox noise: per-particle agreement and identical ensemble moments."""
+    torch.manual_seed(11)
+    d, B, N = 2, 200_000, 32
+    sde = O.make_msgm(O.swiss_roll(4000), dense=True)
+    mlp = O.init_mlp(d, True, seed=11, scale=6.0)
+    _, _, gen = Bd.from_oracle(sde, mlp, DEV)
+    x0 = O.latent_sample(sde, B).to(DEV)
+    kw = dict(keep_all_samples=False, norm_correction=True, seed=5, device_out=True)
+    a = P.rk4_stratonovich_sampler(gen, x0, N, precision="fp32", **kw)
+    b = P.rk4_stratonovich_sampler(gen, x0, N, precision="f16tc", **kw)
+    assert P._lib.debug_flags(DEV) == 0
+    err = (a - b).abs()
+    Bd.report(test="tc-vs-fp32-200k", max_abs=float(err.max()), mean_abs=float(err.mean()), ref_max=float(a.abs().max()))
+    assert float(err.mean()) < 5e-3
+    assert float((a.mean(0) - b.mean(0)).abs().max()) < 2e-3
+    assert float((torch.cov(a.T) - torch.cov(b.T)).abs().max()) < 5e-3

@@ -173,8 +173,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dim", type=int, default=16)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "f16tc"])
+    ap.add_argument("--dim", type=int, default=8)
+    ap.add_argument("--precision", default="f16tc", choices=["fp32", "f16tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU (default 2^20)")
     args = ap.parse_args()

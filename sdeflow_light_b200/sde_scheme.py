@@ -64,6 +64,10 @@ def _run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, inc
                                    T_run, norm_correction, noise, seed, particle_offset, device_out)
 
     x = _lib.f32c(x_0, device).clone()
+    if B == 0:  # nothing to launch; shapes as the reference would return them
+        n_out = num_steps + (1 if include_t0 else 0)
+        out = x.new_zeros((n_out, 0, d)) if keep_all_samples else x
+        return out if device_out else out.to("cpu")
     sd, keep_alive = base.desc(device)
     a = _lib.SampleArgs()
     a.scheme, a.num_steps, a.lmbd = scheme, int(num_steps), float(lmbd)

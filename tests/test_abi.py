@@ -1,0 +1,106 @@
+"""CPU: the C-ABI library loads and exports every symbol include/msgm_b200.h declares; the Python mirror keeps the
+reference's surface; the product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import sdeflow_light_b200 as P
+from sdeflow_light_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    h = open(os.path.join(ROOT, "include", "msgm_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(msgm_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    decl = _declared_symbols()
+    assert len(decl) >= 7
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in msgm_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == decl
+    assert lib.msgm_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    # sizes follow from the field lists in the header on LP64
+    assert ctypes.sizeof(_lib.SdeDesc) == 40
+    assert ctypes.sizeof(_lib.MlpDesc) == 8 + 8 * 8
+    assert ctypes.sizeof(_lib.SampleArgs) == 32 + 8 * 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    h = ctypes.c_void_p()
+    rc = _lib.lib().msgm_create(ctypes.byref(h), 0)
+    assert rc == _lib.ERR_NO_DEVICE and b"no CPU fallback" in _lib.lib().msgm_last_error()
+    T = torch.nn.Parameter(torch.FloatTensor([1.0]), requires_grad=False)
+    base = P.SGMsde(T=T, device="cpu")
+    base.dim = 2
+    gen = P.PluginReverseSDE(base, P.MLP(2), T)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.rk4_stratonovich_sampler(gen, torch.zeros(4, 2), 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        with torch.no_grad():
+            P.MLP(2)(torch.zeros(4, 2), torch.zeros(4))
+
+
+def test_surface_matches_reference_signatures():
+    """Argument names/defaults of the reference's public callables."""
+    ref_args = ["sde", "x_0", "num_steps", "lmbd", "keep_all_samples", "samplesToKeep", "include_t0", "T_",
+                "norm_correction"]
+    for fn in (P.euler_maruyama_sampler, P.heun_sampler, P.rk4_stratonovich_sampler):
+        sig = inspect.signature(fn)
+        pos = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+        assert pos == ref_args
+        assert sig.parameters["num_steps"].default == 1000 and sig.parameters["keep_all_samples"].default is True
+        assert sig.parameters["T_"].default == -1 and sig.parameters["include_t0"].default is False
+    assert list(inspect.signature(P.MSGMsde.__init__).parameters)[1:] == [
+        "y0", "beta_min", "beta_max", "T", "t_epsilon", "denseTensor", "norm_sampler", "norm_map", "kernel",
+        "plot_validate", "num_steps_forward", "device", "estim_cst_norm_dens_r_T"]
+    assert list(inspect.signature(P.PluginReverseSDE.__init__).parameters)[1:] == [
+        "base_sde", "drift_a", "T", "vtype", "debias", "ssm_intT", "deviceReverseSDE"]
+    assert list(inspect.signature(P.MLP.__init__).parameters)[1:] == [
+        "input_dim", "index_dim", "hidden_dim", "act", "premodule"]
+    for m in ("mu", "ga_m_drift", "ga", "mu_Strato", "sigma", "ssm", "ssm_loss", "sample_txy", "sample_t",
+              "elbo_random_t_slice", "latent_sample", "cond_latent_sample"):
+        assert hasattr(P.PluginReverseSDE, m)
+    for m in ("beta", "f", "f_strato", "g", "div_Sigma", "IJK", "sample", "sample_scheme", "sample_scheme_allt",
+              "latent_sample", "cond_latent_sample", "log_latent_pdf", "to"):
+        assert hasattr(P.MSGMsde, m)
+
+
+def test_state_dict_keys_match_reference():
+    T = torch.nn.Parameter(torch.FloatTensor([1.0]), requires_grad=False)
+    torch.manual_seed(0)
+    base = P.MSGMsde(torch.randn(64, 2), T=T, norm_map="log", estim_cst_norm_dens_r_T=False)
+    gen = P.PluginReverseSDE(base, P.MLP(2, premodule="NormalizeLogRadius"), T)
+    keys = sorted(gen.state_dict().keys())
+    assert keys == sorted(["T", "base_sde.T"] + [f"a.main.{i}.{w}" for i in (0, 2, 4, 6) for w in ("weight", "bias")])
+
+
+def test_coefficient_methods_agree_with_oracle_on_cpu_tensors():
+    """The thin coefficient methods are plain tensor expressions; check them against the oracle's."""
+    from oracle import msgm_oracle as O
+    torch.manual_seed(1)
+    y0 = torch.randn(128, 4)
+    T = torch.nn.Parameter(torch.FloatTensor([1.0]), requires_grad=False)
+    for dense in (True, False):
+        torch.manual_seed(2)
+        base = P.MSGMsde(y0, T=T, denseTensor=dense, norm_map="log", estim_cst_norm_dens_r_T=False)
+        torch.manual_seed(2)
+        sde = O.make_msgm(y0, dense=dense, num_steps_forward=100)
+        if dense:
+            assert torch.equal(base.G, sde.G)  # same RNG consumption order as the reference's new_G
+        s, y = torch.rand(16, 1), torch.randn(16, 4)
+        assert torch.allclose(base.f(s, y), O.coef_f(sde, s, y))
+        assert torch.allclose(base.div_Sigma(s, y), O.coef_div_sigma(sde, s, y))
+        assert torch.allclose(base.g(s, y, sparse=not dense), O.coef_g(sde, s, y, sparse=not dense))

@@ -1,8 +1,9 @@
 """GPU parity of the fused samplers (through the C ABI) against the reference's golden fixtures and the oracle.
 
-Tolerance (fp32 mode): |x_cuda - x_ref| <= ATOL + RTOL |x_ref| on every captured state.  The kernel sums the
-128-term dot products in a different order than MKL and merges g.a and g.dW into one contraction, so agreement is
-at accumulated-rounding level, not bitwise.
+Tolerance (fp32 mode): |x_cuda - x_ref| <= ATOL + RTOL * max_c |x_ref[.., c]| on every captured state (the error of
+a state vector is measured against that particle's own magnitude: the SDE couples the components).  The kernel
+sums the 128-term dot products in a different order than MKL and merges g.a and g.dW into one contraction, so
+agreement is at accumulated-rounding level (observed <= 2e-6 relative), not bitwise.
 """
 import pytest
 import torch
@@ -23,7 +24,8 @@ def _close(name, out, ref, atol=ATOL, rtol=RTOL):
     err = (out - ref).abs()
     Bd.report(test=name, max_abs=float(err.max()), ref_max=float(ref.abs().max()), atol=atol, rtol=rtol)
     assert torch.isfinite(out).all()
-    assert bool((err <= atol + rtol * ref.abs()).all()), f"{name}: max abs err {float(err.max()):.3e}"
+    scale = ref.abs().amax(dim=-1, keepdim=True) if ref.dim() > 1 else ref.abs()
+    assert bool((err <= atol + rtol * scale).all()), f"{name}: max abs err {float(err.max()):.3e}"
 
 
 @pytest.mark.parametrize("name", G.names("s"))
@@ -148,8 +150,8 @@ def test_mlp_forward_kernel():
 
 # ---- tensor-core (tcgen05, fp16 operands / fp32 accumulate) mode ---------------------------------------------------
 # Stated tolerance of the f16tc mode: the hidden layers round weights and activations to fp16 (11-bit mantissa), so
-# per-stage score values agree to ~1e-3 relative; trajectories are compared at TC_ATOL + TC_RTOL |x| after N steps.
-TC_ATOL, TC_RTOL = 2e-2, 2e-2
+# per-stage score values agree to ~1e-3 relative; trajectories are compared at TC_ATOL + TC_RTOL max_c|x_c| after N steps.
+TC_ATOL, TC_RTOL = 3e-3, 3e-3  # observed: <= 7e-4 abs on |x| ~ 5, 1.4e-4 relative on |x| ~ 1e3
 TC_CASES = [
     ("msgm_dense", 2, True, "rk4", 0.0, True, 1000, 16),
     ("msgm_dense", 2, True, "em", 0.0, True, 300, 1),

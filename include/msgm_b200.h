@@ -100,6 +100,9 @@ int64_t msgm_launch_count(const msgm_ctx* ctx);
 /* Debug: synchronises the device and returns the kernel-side flag word (bit 0: a bounded mbarrier wait inside
  * the tensor-core sampler timed out).  Used by the tests; 0 in a healthy run. */
 int msgm_debug_flags(msgm_ctx* ctx, int32_t* out_host);
+/* Debug: cycle counters of the tensor-core sampler (CTA 0), filled only while the environment variable
+ * MSGM_TC_PROF is set; n <= 24.  [0..7] owner thread, [8..15] MMA thread, [16..23] helper thread. */
+int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n);
 
 /* Whole sampling loop for an MLP score net, all N steps in one persistent launch; x_inout (B,d) device fp32
  * holds x_0 on entry and x_N on exit. */

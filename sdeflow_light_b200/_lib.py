@@ -43,7 +43,7 @@ _ctx = {}
 
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
-           "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags"]
+           "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters"]
 
 
 def lib() -> C.CDLL:
@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
                 L.msgm_destroy.argtypes = [C.c_void_p]
                 L.msgm_launch_count.argtypes = [C.c_void_p]
                 L.msgm_debug_flags.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+                L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]
                 L.msgm_mlp_forward.argtypes = [C.c_void_p, C.POINTER(MlpDesc), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -106,6 +107,12 @@ def debug_flags(device) -> int:
     out = C.c_int32(0)
     check(lib().msgm_debug_flags(ctx(device), C.byref(out)))
     return int(out.value)
+
+
+def debug_counters(device):
+    out = (C.c_int64 * 24)()
+    check(lib().msgm_debug_counters(ctx(device), out, 24))
+    return list(out)
 
 
 def stream_ptr(device) -> C.c_void_p:

@@ -136,4 +136,13 @@ int msgm_mlp_forward(msgm_ctx* ctx, const msgm_mlp_desc* mlp, const float* y, co
   return mlp_forward_fp32(ctx, mlp, y, s, out, B, (cudaStream_t)stream);
 }
 
+int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {
+  if (!ctx || !out_host || n < 0 || n > 24) return invalid("msgm_debug_counters: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  MSGM_CUDA_TRY(cudaDeviceSynchronize());
+  MSGM_CUDA_TRY(cudaMemcpy(out_host, reinterpret_cast<unsigned char*>(ctx->ws) + 64, sizeof(int64_t) * n,
+                           cudaMemcpyDeviceToHost));
+  return MSGM_OK;
+}
+
 }  // extern "C"

@@ -3,33 +3,41 @@
 //
 //   * one CTA = one tile of 128 particles, TWO CTAs per SM (each allocates 256 TMEM columns) so that one CTA's
 //     activation epilogue (MUFU-bound) overlaps the other CTA's MMAs;
-//   * warps 0-3: thread == particle row == TMEM lane.  The thread keeps x, the RK sum, dW and r0 in registers for
-//     all N steps, so a particle makes one HBM round trip per sampler call;
-//   * warp 4: lane 0 issues tcgen05.mma (A operand = activations in TMEM, written there by the epilogue threads
+//   * warps 0-3 ("owners"): thread == particle row == TMEM lane.  The thread keeps x, the RK sum, dW and r0 in registers
+//     for all N steps, so a particle makes one HBM round trip per sampler call; it also runs the activation epilogue
+//     of accumulator columns 0-63.  Warps 4-7 ("helpers") run the epilogue of columns 64-127 of the same lanes, so
+//     every SM sub-partition always has several warps feeding the MUFU pipe;
+//   * warp 8: lane 0 issues tcgen05.mma (A operand = activations in TMEM, written there by the epilogue threads
 //     as packed fp16; B operand = weights resident in shared memory as canonical no-swizzle K-major core matrices,
 //     loaded once per CTA with TMA bulk copies); accumulators live in TMEM (fp32);
-//   * biases ride on the tensor pipe: an extra K=16 slice whose A operand is a constant "ones" TMEM block;
+//   * biases ride on the tensor pipe: an extra K=16 slice whose A operand is a constant "ones" block in shared memory
+//     (.ss MMA accumulating into the same TMEM tile as the .ts MMAs);
+//   * every hidden layer is issued as two N=64 halves with the activation buffer double-buffered in TMEM, so the
+//     MMAs of one half (and the first K-slices of the NEXT layer) run underneath the MUFU epilogue of the other half;
+//   * for d <= 4 the 128->d output layer is accumulated on the CUDA cores inside the last epilogue (one handshake less);
 //   * Swish(z) = h tanh(h) + h with h = z/2; the 1/2 is folded into the packed weights, so one MUFU per activation;
 //   * layer 1 (K = d+2) is evaluated in split precision (u_hi, u_lo) x (W_hi, W_lo) so that time, log-radius and
 //     direction inputs keep ~22 mantissa bits at no extra cost (they fit the zero padding of the K=16 slices).
 //
-// Handshake per layer: epilogue threads -> bar_a (128 arrivals: "A operand complete, D consumed") -> MMA warp
-// issues -> tcgen05.commit -> bar_d -> epilogue threads read D.  All waits are bounded; a timeout sets a flag in
-// the context workspace (msgm_debug_flags) instead of hanging the GPU.
+// Handshake per layer and half h: particle threads -> bar_a[h] (128 arrivals: "K-slices 4h..4h+3 of the next A operand
+// written, D half h consumed") -> MMA warp issues -> tcgen05.commit -> bar_d[h] -> particle threads read D half h.
+// All waits are bounded; a timeout sets a flag in the context workspace (msgm_debug_flags) instead of hanging.
 #include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "msgm_common.cuh"
 
 namespace msgm {
 
 constexpr int TM = 128;            // particles per CTA tile (= UMMA M = TMEM lanes)
-constexpr int TC_THREADS = 160;    // 4 epilogue warps + 1 MMA warp
-constexpr uint32_t COL_D = 0;      // accumulator: 128 fp32 columns
-constexpr uint32_t COL_A = 128;    // activations / layer-1 operand: 64 columns of packed fp16 pairs
-constexpr uint32_t COL_ONES = 192; // constant K=16 slice [1,1,0,...,0]
+constexpr int TC_THREADS = 288;    // 4 owner warps (D half 0 + particle state) + 4 helper warps (D half 1) + 1 MMA warp
+constexpr int TC_MMA_TID = 256;    // lane 0 of warp 8 issues the MMAs
+constexpr uint32_t COL_D = 0;      // accumulator: 128 fp32 columns (two N=64 halves)
+constexpr uint32_t COL_A0 = 128;   // activation buffer 0: 64 columns of packed fp16 pairs (layer-1 operand, act 2)
+constexpr uint32_t COL_A1 = 192;   // activation buffer 1 (act 1, act 3)
 constexpr uint32_t TMEM_COLS = 256;
 
 template <int DP>
@@ -44,10 +52,14 @@ struct TcLayout {
   static constexpr int oW3 = oW2 + WH_BYTES;
   static constexpr int oW4 = oW3 + WH_BYTES;
   static constexpr int IMG_BYTES = oW4 + W4_BYTES;             // what the pack kernel writes / TMA copies
-  static constexpr int oG = IMG_BYTES;                         // fp32 [DP][DP][DP] (dense)
+  static constexpr int oOnes = IMG_BYTES;                      // fp16 [2][16][8][8]: A operand of the bias slices
+  static constexpr int oG = oOnes + 4096;                      // fp32 [DP][DP][DP] (dense)
   static constexpr int oLG = oG + 4 * DP * DP * DP;            // fp32 [DP][DP]
-  static constexpr int oBar = oLG + 4 * DP * DP;               // 3 mbarriers + tmem slot
-  static constexpr int SMEM_BYTES = oBar + 64;
+  static constexpr int oW4f = oLG + 4 * DP * DP;               // fp32 [128][DP] + b4[DP]: CUDA-core output layer
+  static constexpr int oPart = oW4f + 4 * (128 * DP + DP);     // fp32 [128][DP]: helper warps' partial output layer
+  static constexpr int oBar = oPart + 4 * 128 * DP;            // 5 mbarriers + tmem slot
+  static constexpr int SMEM_BYTES = oBar + 96;
+  static constexpr bool L4_CC = DP <= 4;                       // output layer on CUDA cores
 };
 
 struct TcParams {
@@ -55,6 +67,8 @@ struct TcParams {
   float bmin, bdel, Tsde;
   const float* G;
   const float* LG;
+  const float* W4;           // reference output layer (d,128) and bias (d,), fp32 (CUDA-core output layer)
+  const float* b4;
   const unsigned char* img;  // packed weight image (global)
   int scheme, N, nc, inc_t0;
   float lmbd, delta, delta_half, sqrt_delta;
@@ -67,6 +81,7 @@ struct TcParams {
   float* x;
   long long B;
   int* flags;  // [0] = wait timeout seen
+  long long* prof;  // NULL or 24 cycle counters (see Prof)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
@@ -92,11 +107,15 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: returns false (and raises the debug flag) instead of hanging if the partner never arrives.
+// Normal waits last microseconds; the limit is ~0.2 s, and a raised flag makes every other waiter bail out at once.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* flags) {
   if (mbar_try(bar, parity)) return true;
   const long long t0 = clock64();
-  while (clock64() - t0 < 4000000000LL)  // ~2 s at 2 GHz
+  int spins = 0;
+  while (clock64() - t0 < 400000000LL) {
     if (mbar_try(bar, parity)) return true;
+    if ((++spins & 255) == 0 && *reinterpret_cast<volatile int*>(flags) != 0) return false;
+  }
   atomicExch(flags, 1);
   return false;
 }
@@ -110,6 +129,17 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Optional cycle accounting (MSGM_TC_PROF=1 in the environment of the caller): CTA 0 only, one thread per role,
+// counters in the context workspace at byte 64.  tick() returns elapsed cycles since the previous tick.
+struct Prof {
+  long long* c;
+  long long t;
+  __device__ __forceinline__ void start() { if (c) t = clock64(); }
+  __device__ __forceinline__ void tick(int slot) {
+    if (c) { const long long n = clock64(); c[slot] += n - t; t = n; }
+  }
+};
+
 // K-major, no-swizzle smem matrix descriptor (validated on B200 by tools/tc_probe.cu):
 // LBO = bytes between the two 8-element k-chunks of a K=16 slice, SBO = bytes between 8-row groups.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -119,16 +149,30 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);  // D=f32, A=B=f16, K-major both
 }
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// The MMA warp runs converged so that descriptor arithmetic stays warp-uniform (uniform datapath); only the
+// instruction itself is predicated on the leader lane (`lead` != 0 in exactly one lane).
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                        uint32_t lead) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc), "r"(lead)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                        uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(lead)
+      : "memory");
 }
 
 #define TMEM_LD32(taddr, r)                                                                                         \
@@ -179,10 +223,15 @@ __device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
   return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
 }
 
-// Activation epilogue of one hidden layer: D (128 fp32 cols, = z/2) -> Swish -> packed fp16 -> A (64 cols).
-__device__ __forceinline__ void swish_epilogue(uint32_t lane_base) {
+// Activation epilogue of one N=64 half of a hidden layer: D half (64 fp32 cols, = z/2) -> Swish -> packed fp16 ->
+// 32 columns of the next activation buffer.  With ACC_OUT the 128->d output layer is accumulated on the fly from the
+// fp32 activations (a_c += W4[n][c] s_n) and nothing is stored.
+template <int DP, bool ACC_OUT>
+__device__ __forceinline__ void swish_half(uint32_t lane_base, int half, uint32_t col_out, const float* __restrict__ sW4f,
+                                           float* a) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = half * 2 + cc;
     uint32_t r[32], q[16];
     TMEM_LD32(lane_base + COL_D + c * 32, r);
     tc_wait_ld();
@@ -191,11 +240,20 @@ __device__ __forceinline__ void swish_epilogue(uint32_t lane_base) {
       const float h0 = __uint_as_float(r[2 * j]), h1 = __uint_as_float(r[2 * j + 1]);
       const float s0 = fmaf(h0, tanh_fast(h0), h0);  // z sigmoid(z) with z = 2h   (NN.py:52-53)
       const float s1 = fmaf(h1, tanh_fast(h1), h1);
-      q[j] = pack_f16x2(s0, s1);
+      if constexpr (ACC_OUT) {
+        const int n = c * 32 + 2 * j;
+#pragma unroll
+        for (int e = 0; e < DP; ++e) {
+          a[e] = fmaf(sW4f[n * DP + e], s0, a[e]);
+          a[e] = fmaf(sW4f[(n + 1) * DP + e], s1, a[e]);
+        }
+      } else {
+        q[j] = pack_f16x2(s0, s1);
+      }
     }
-    TMEM_ST16(lane_base + COL_A + c * 16, q);
+    if constexpr (!ACC_OUT) TMEM_ST16(lane_base + col_out + c * 16, q);
   }
-  tc_wait_st();
+  if constexpr (!ACC_OUT) tc_wait_st();
 }
 
 template <int DP, int KIND>
@@ -205,10 +263,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
   extern __shared__ __align__(128) unsigned char smem[];
   float* sG = reinterpret_cast<float*>(smem + L::oG);
   float* sLG = reinterpret_cast<float*>(smem + L::oLG);
+  float* sW4f = reinterpret_cast<float*>(smem + L::oW4f);
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + L::oBar);
-  uint64_t* bar_a = bar_w + 1;
-  uint64_t* bar_d = bar_w + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
+  uint64_t* bar_a0 = bar_w + 1;
+  uint64_t* bar_a1 = bar_w + 2;
+  uint64_t* bar_d0 = bar_w + 3;
+  uint64_t* bar_d1 = bar_w + 4;
+  uint64_t* bar_p = bar_w + 5;  // [4]: helper warp q -> owner warp q, partial output-layer sums are in smem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 9);
+  constexpr bool L4_CC = L::L4_CC;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = P.d;
@@ -216,10 +279,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
   const long long ntiles = (P.B + TM - 1) / TM;
 
   // ---- setup ----------------------------------------------------------------------------------------------------
-  if (tid == 128) {
+  if (tid == TC_MMA_TID) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_a, 128);
-    mbar_init(bar_d, 1);
+    mbar_init(bar_a0, 128);
+    mbar_init(bar_a1, 128);
+    mbar_init(bar_d0, 1);
+    mbar_init(bar_d1, 1);
+    for (int q4 = 0; q4 < 4; ++q4) mbar_init(bar_p + q4, 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -237,11 +303,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
       sLG[e] = (i < d && j < d) ? __ldg(P.LG + i * d + j) : 0.0f;
     }
   }
+  {  // "ones" A operand of the bias slices: rows x k, k = 0,1 -> 1.0 (the bias rides there split hi+lo), rest 0
+    __half* ones = reinterpret_cast<__half*>(smem + L::oOnes);
+    for (int e = tid; e < 2048; e += TC_THREADS) ones[e] = __ushort_as_half((e < 1024 && (e & 7) < 2) ? 0x3C00 : 0);
+  }
+  if (L4_CC) {
+    for (int e = tid; e < 128 * DP; e += TC_THREADS) {
+      int n = e / DP, c = e % DP;
+      sW4f[e] = c < d ? __ldg(P.W4 + c * 128 + n) : 0.0f;
+    }
+    if (tid < DP) sW4f[128 * DP + tid] = tid < d ? __ldg(P.b4 + tid) : 0.0f;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
-  if (tid == 128) {  // weights: one TMA bulk copy per layer image, all landing on bar_w
+  if (tid == TC_MMA_TID) {  // weights: one TMA bulk copy per layer image, all landing on bar_w
     mbar_expect_tx(bar_w, (uint32_t)L::IMG_BYTES);
     tma_bulk_g2s(smem + L::oW1, P.img + L::oW1, L::W1_BYTES, bar_w);
     tma_bulk_g2s(smem + L::oW2, P.img + L::oW2, L::WH_BYTES, bar_w);
@@ -249,62 +327,132 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
     tma_bulk_g2s(smem + L::oW4, P.img + L::oW4, L::W4_BYTES, bar_w);
   }
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =========================================== MMA issuer ===================================================
-    if (lane == 0) {
+    {
+      const uint32_t lead = lane == 0 ? 1u : 0u;
       bool ok = mbar_wait(bar_w, 0, P.flags);
       const uint32_t idesc_h = umma_idesc_f16(128, 128), idesc_o = umma_idesc_f16(128, 16);
       const uint32_t sW1 = smem_u32(smem + L::oW1), sW2 = smem_u32(smem + L::oW2), sW3 = smem_u32(smem + L::oW3),
                      sW4 = smem_u32(smem + L::oW4);
-      uint32_t ph = 0;
+      const uint32_t idesc_64 = umma_idesc_f16(128, 64);
+      const uint64_t ones_desc = umma_desc(smem_u32(smem + L::oOnes), 2048, 128);
+      uint32_t pa0 = 0, pa1 = 0;
+      (void)idesc_h;
+      Prof pf{(P.prof && blockIdx.x == 0 && lane == 0) ? P.prof + 8 : nullptr, 0};
+      pf.start();
       for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
         for (int it = 0; it < P.N * nstage && ok; ++it) {
-          // layer 1: K1/16 slices, bias rides in the padding of the last one
-          ok = mbar_wait(bar_a, ph, P.flags); ph ^= 1; tc_fence_after();
+          // ---- layer 1 (operand in buffer 0): K1/16 slices per half, bias rides in the padding of the last slice
+          // (waits for the owners only: the helpers' last reads of D were ordered before the owners' arrival)
+          ok = mbar_wait(bar_a0, pa0, P.flags); pa0 ^= 1;
+          tc_fence_after();
+          pf.tick(0);  // wait for the layer-1 operand
 #pragma unroll
-          for (int s = 0; s < K1 / 16; ++s)
-            umma_ts(tbase + COL_D, tbase + COL_A + 8 * s, umma_desc(sW1 + s * 4096, 2048, 128), idesc_h, s > 0);
-          umma_commit(bar_d);
-          // layers 2, 3: ones-slice (bias) + 8 slices
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int s = 0; s < K1 / 16; ++s)
+              umma_ts(tbase + COL_D + 64 * h, tbase + COL_A0 + 8 * s, umma_desc(sW1 + s * 4096 + h * 1024, 2048, 128),
+                      idesc_64, s > 0, lead);
+            umma_commit(h == 0 ? bar_d0 : bar_d1, lead);
+          }
+          // ---- layers 2 (operand in buffer 1) and 3 (buffer 0): ones-slice (bias) + 8 slices, two N=64 halves.
+          // Output half 0 starts as soon as the first four K-slices of the operand exist (bar_a0).
 #pragma unroll
           for (int l = 0; l < 2; ++l) {
             const uint32_t sW = l == 0 ? sW2 : sW3;
-            ok = ok && mbar_wait(bar_a, ph, P.flags); ph ^= 1; tc_fence_after();
-            umma_ts(tbase + COL_D, tbase + COL_ONES, umma_desc(sW, 2048, 128), idesc_h, 0);
+            const uint32_t Ain = tbase + (l == 0 ? COL_A1 : COL_A0);
+            pf.tick(1);  // issue
+            ok = ok && mbar_wait(bar_a0, pa0, P.flags); pa0 ^= 1; tc_fence_after();
+            pf.tick(2);  // wait a0 (hidden)
+            umma_ss(tbase + COL_D, ones_desc, umma_desc(sW, 2048, 128), idesc_64, 0, lead);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              umma_ts(tbase + COL_D, Ain + 8 * s, umma_desc(sW + (s + 1) * 4096, 2048, 128), idesc_64, 1, lead);
+            pf.tick(1);
+            ok = ok && mbar_wait(bar_a1, pa1, P.flags); pa1 ^= 1; tc_fence_after();
+            pf.tick(3);  // wait a1 (hidden)
+#pragma unroll
+            for (int s = 4; s < 8; ++s)
+              umma_ts(tbase + COL_D, Ain + 8 * s, umma_desc(sW + (s + 1) * 4096, 2048, 128), idesc_64, 1, lead);
+            umma_commit(bar_d0, lead);
+            umma_ss(tbase + COL_D + 64, ones_desc, umma_desc(sW + 1024, 2048, 128), idesc_64, 0, lead);
 #pragma unroll
             for (int s = 0; s < 8; ++s)
-              umma_ts(tbase + COL_D, tbase + COL_A + 8 * s, umma_desc(sW + (s + 1) * 4096, 2048, 128), idesc_h, 1);
-            umma_commit(bar_d);
+              umma_ts(tbase + COL_D + 64, Ain + 8 * s, umma_desc(sW + (s + 1) * 4096 + 1024, 2048, 128), idesc_64, 1, lead);
+            umma_commit(bar_d1, lead);
           }
-          // output layer: N = 16
-          ok = ok && mbar_wait(bar_a, ph, P.flags); ph ^= 1; tc_fence_after();
-          umma_ts(tbase + COL_D, tbase + COL_ONES, umma_desc(sW4, 256, 128), idesc_o, 0);
+          pf.tick(1);
+          // ---- output layer on the tensor pipe (d > 4): N = 16, operand in buffer 1
+          if (!L4_CC) {
+            ok = ok && mbar_wait(bar_a0, pa0, P.flags); pa0 ^= 1;
+            ok = ok && mbar_wait(bar_a1, pa1, P.flags); pa1 ^= 1;
+            tc_fence_after();
+            pf.tick(4);  // wait for act3
+            umma_ss(tbase + COL_D, ones_desc, umma_desc(sW4, 256, 128), idesc_o, 0, lead);
 #pragma unroll
-          for (int s = 0; s < 8; ++s)
-            umma_ts(tbase + COL_D, tbase + COL_A + 8 * s, umma_desc(sW4 + (s + 1) * 512, 256, 128), idesc_o, 1);
-          umma_commit(bar_d);
+            for (int s = 0; s < 8; ++s)
+              umma_ts(tbase + COL_D, tbase + COL_A1 + 8 * s, umma_desc(sW4 + (s + 1) * 512, 256, 128), idesc_o, 1, lead);
+            umma_commit(bar_d0, lead);
+            pf.tick(1);
+          }
         }
       }
     }
     __syncwarp();
-  } else {
-    // ======================================= particle threads ================================================
-    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
-    {  // constant ones slice: k = 0,1 -> 1.0 ; rest 0
-      uint32_t o[8] = {0x3C003C00u, 0, 0, 0, 0, 0, 0, 0};
-      TMEM_ST8(lane_base + COL_ONES, o);
-      tc_wait_st();
+  } else if (warp >= 4) {
+    // ======================================= helper warps: D columns 64..127 ================================
+    const int q = warp - 4;
+    const uint32_t lane_base = tbase + ((uint32_t)(q * 32) << 16);
+    float* part = reinterpret_cast<float*>(smem + L::oPart) + (q * 32 + lane) * DP;
+    uint32_t pd1 = 0;
+    bool ok = true;
+    Prof pf{(P.prof && blockIdx.x == 0 && tid == 128) ? P.prof + 16 : nullptr, 0};
+    pf.start();
+    for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+      for (int it = 0; it < P.N * nstage && ok; ++it) {
+        float a[DP];
+#pragma unroll
+        for (int c = 0; c < DP; ++c) a[c] = 0.0f;
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {
+          ok = ok && mbar_wait(bar_d1, pd1, P.flags); pd1 ^= 1; tc_fence_after();
+          pf.tick(0);  // wait d1
+          swish_half<DP, false>(lane_base, 1, l == 0 ? COL_A1 : COL_A0, sW4f, a);
+          tc_fence_before();
+          mbar_arrive(bar_a1);
+          pf.tick(1);  // epilogue
+        }
+        ok = ok && mbar_wait(bar_d1, pd1, P.flags); pd1 ^= 1; tc_fence_after();
+        pf.tick(0);
+        swish_half<DP, L4_CC>(lane_base, 1, COL_A1, sW4f, a);
+        pf.tick(1);
+        if (L4_CC) {
+#pragma unroll
+          for (int c = 0; c < DP; ++c) part[c] = a[c];
+          mbar_arrive(bar_p + q);  // release: the owner warp of the same lanes acquires through the mbarrier
+        } else {
+          tc_fence_before();
+          mbar_arrive(bar_a1);
+        }
+      }
     }
+  } else {
+    // ======================================= owner warps: particle state + D columns 0..63 ==================
+    const float* part = reinterpret_cast<const float*>(smem + L::oPart) + tid * DP;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
     const float lm = P.lmbd;
     const float c_w = sqrtf(1.0f - lm);
     const bool ito = (P.scheme == MSGM_SCHEME_EM);
     const float c_f = ito ? (1.0f - 2.0f * lm) : -lm;
     const float delta = P.delta;
     const float c_a = delta * (1.0f - 0.5f * lm);
-    uint32_t ph = 0;
+    uint32_t pd0 = 0, pp = 0;
     bool ok = true;
+    Prof pf{(P.prof && blockIdx.x == 0 && tid == 0) ? P.prof : nullptr, 0};
+    pf.start();
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
       const long long gp = tile * TM + tid;
       const bool live = gp < P.B;
       float x[DP], y[DP], ks[DP], dw[DP];
@@ -324,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
         for (int c = 0; c < d; ++c) P.traj[gp * d + c] = x[c];
       const int keep = (P.keep_step && live) ? P.keep_step[gp] : -1;
 
-      for (int step = 0; step < P.N; ++step) {
+      for (int step = 0; step < P.N && ok; ++step) {
         const float tcur = P.ts ? __ldg(P.ts + step) : __fmul_rn((float)step, delta);
 #pragma unroll
         for (int c4 = 0; c4 < DP; c4 += 4) {
@@ -342,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
             if (c4 + c < DP) dw[c4 + c] = (c4 + c < d) ? P.sqrt_delta * z[c] : 0.0f;
         }
 
-        for (int st = 0; st < nstage; ++st) {
+        for (int st = 0; st < nstage && ok; ++st) {
           float tst = tcur;
           if (st > 0) tst = (nstage == 4 && st < 3) ? __fadd_rn(tcur, P.delta_half) : __fadd_rn(tcur, delta);
           const float sv = __fsub_rn(P.Tsde, tst);
@@ -383,24 +531,41 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < K1 / 2; ++j) q[j] = pack_h2(hk[2 * j], hk[2 * j + 1]);
 #pragma unroll
-            for (int c = 0; c < K1 / 16; ++c) TMEM_ST8(lane_base + COL_A + 8 * c, (q + 8 * c));
+            for (int c = 0; c < K1 / 16; ++c) TMEM_ST8(lane_base + COL_A0 + 8 * c, (q + 8 * c));
             tc_wait_st();
           }
           tc_fence_before();
-          mbar_arrive(bar_a);
+          mbar_arrive(bar_a0);
+          pf.tick(0);  // SDE update + layer-1 operand
 
-          // ---- hidden layers ---------------------------------------------------------------------------------------
-#pragma unroll 1
-          for (int l = 0; l < 3; ++l) {
-            ok = ok && mbar_wait(bar_d, ph, P.flags); ph ^= 1; tc_fence_after();
-            swish_epilogue(lane_base);
-            tc_fence_before();
-            mbar_arrive(bar_a);
-          }
-          // ---- output layer -> a ----------------------------------------------------------------------------------------
+          // ---- hidden layers: act1 -> buffer 1, act2 -> buffer 0, act3 -> buffer 1 (or straight into a) -----------
           float a[DP];
-          {
-            ok = ok && mbar_wait(bar_d, ph, P.flags); ph ^= 1; tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < DP; ++c) a[c] = L4_CC ? sW4f[128 * DP + c] : 0.0f;
+#pragma unroll 1
+          for (int l = 0; l < 2; ++l) {
+            ok = ok && mbar_wait(bar_d0, pd0, P.flags); pd0 ^= 1; tc_fence_after();
+            pf.tick(1 + l);  // wait d0 of layer 1 / layer 2
+            swish_half<DP, false>(lane_base, 0, l == 0 ? COL_A1 : COL_A0, sW4f, a);
+            tc_fence_before();
+            mbar_arrive(bar_a0);
+            pf.tick(4);  // epilogue
+          }
+          ok = ok && mbar_wait(bar_d0, pd0, P.flags); pd0 ^= 1; tc_fence_after();
+          pf.tick(3);  // wait d0 of layer 3
+          swish_half<DP, L4_CC>(lane_base, 0, COL_A1, sW4f, a);
+          tc_fence_before();
+          pf.tick(4);
+          if (L4_CC) {
+            ok = ok && mbar_wait(bar_p + warp, pp, P.flags); pp ^= 1;  // helper's partial sums are in smem
+#pragma unroll
+            for (int c = 0; c < DP; ++c) a[c] += part[c];
+          } else {
+            mbar_arrive(bar_a0);
+          }
+          // ---- output layer result (tensor-pipe variant) ---------------------------------------------------------------------
+          if (!L4_CC) {
+            ok = ok && mbar_wait(bar_d0, pd0, P.flags); pd0 ^= 1; tc_fence_after();
             uint32_t r[16];
             TMEM_LD16(lane_base + COL_D, r);
             tc_wait_ld();
@@ -408,6 +573,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
             for (int c = 0; c < DP; ++c) a[c] = __uint_as_float(r[c]);
           }
 
+          pf.tick(5);  // output layer hand-off
           // ---- stage increment K = delta * drift + sigma . dW (same algebra as sampler_fp32.cu) --------------------------
           float K[DP];
           if (KIND == MSGM_SDE_SGM) {
@@ -588,6 +754,7 @@ static int launch_tc(msgm_ctx* ctx, const msgm_mlp_desc* m, TcParams& P, cudaStr
   int rc = ensure_ws(ctx, need);
   if (rc) return rc;
   P.flags = reinterpret_cast<int*>(ctx->ws);
+  P.prof = std::getenv("MSGM_TC_PROF") ? reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(ctx->ws) + 64) : nullptr;
   unsigned char* img = reinterpret_cast<unsigned char*>(ctx->ws) + 256;
   P.img = img;
   MSGM_CUDA_TRY(cudaMemsetAsync(ctx->ws, 0, 256, stream));
@@ -636,6 +803,8 @@ int sample_mlp_tc(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* 
   P.Tsde = sde->T;
   P.G = sde->G;
   P.LG = sde->L_G;
+  P.W4 = mlp->W[3];
+  P.b4 = mlp->b[3];
   P.scheme = a->scheme;
   P.N = a->num_steps;
   P.nc = a->norm_correction;

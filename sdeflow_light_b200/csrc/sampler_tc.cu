@@ -1,26 +1,22 @@
 // Tensor-core sampler (MSGM_PREC_F16TC): the whole EM / Heun / RK4-Stratonovich loop of sde_scheme.py:43-269
-// for the MLP score net (NN.py:73-120) in ONE persistent launch, with the four dense layers on tcgen05.
+// for the MLP score net (NN.py:73-120) in ONE persistent launch, with the dense layers on tcgen05.
 //
-//   * one CTA = one tile of 128 particles, TWO CTAs per SM (each allocates 256 TMEM columns) so that one CTA's
-//     activation epilogue (MUFU-bound) overlaps the other CTA's MMAs;
-//   * warps 0-3 ("owners"): thread == particle row == TMEM lane.  The thread keeps x, the RK sum, dW and r0 in registers
-//     for all N steps, so a particle makes one HBM round trip per sampler call; it also runs the activation epilogue
-//     of accumulator columns 0-63.  Warps 4-7 ("helpers") run the epilogue of columns 64-127 of the same lanes, so
-//     every SM sub-partition always has several warps feeding the MUFU pipe;
-//   * warp 8: lane 0 issues tcgen05.mma (A operand = activations in TMEM, written there by the epilogue threads
-//     as packed fp16; B operand = weights resident in shared memory as canonical no-swizzle K-major core matrices,
-//     loaded once per CTA with TMA bulk copies); accumulators live in TMEM (fp32);
-//   * biases ride on the tensor pipe: an extra K=16 slice whose A operand is a constant "ones" block in shared memory
-//     (.ss MMA accumulating into the same TMEM tile as the .ts MMAs);
-//   * every hidden layer is issued as two N=64 halves with the activation buffer double-buffered in TMEM, so the
-//     MMAs of one half (and the first K-slices of the NEXT layer) run underneath the MUFU epilogue of the other half;
-//   * for d <= 4 the 128->d output layer is accumulated on the CUDA cores inside the last epilogue (one handshake less);
+//   * one persistent CTA per SM owns NSLOT independent tiles of 128 particles at a time ("slots").  Each slot has four
+//     warps in which thread == particle row == TMEM lane: the thread keeps x, the RK sum, dW and r0 in registers for
+//     all N steps (one HBM round trip per particle per sampler call) and runs the activation epilogues of its row;
+//   * one extra warp multiplexes the tensor pipe over the slots: it polls each slot's "operand ready" mbarrier and
+//     issues that slot's next layer (tcgen05.mma, .ss form: A = the slot's fp16 activation tile in shared memory,
+//     B = fp16 weights resident in shared memory, both canonical no-swizzle K-major core matrices; D = the slot's 128
+//     fp32 accumulator columns in TMEM), then tcgen05.commit's to the slot's "accumulator ready" mbarrier;
+//   * the layers of ONE slot are strictly sequential (MMA -> commit latency -> epilogue), so NSLOT = 3..4 slots are
+//     what keeps the MUFU pipe (the binding unit: one tanh per activation) and the tensor pipe busy;
+//   * weights are brought in once per CTA by TMA bulk copies (cp.async.bulk) from the image pack_mlp_tc_kernel writes;
+//   * biases ride on the tensor pipe: an extra K=16 slice whose A operand is a constant "ones" block in shared memory;
 //   * Swish(z) = h tanh(h) + h with h = z/2; the 1/2 is folded into the packed weights, so one MUFU per activation;
 //   * layer 1 (K = d+2) is evaluated in split precision (u_hi, u_lo) x (W_hi, W_lo) so that time, log-radius and
-//     direction inputs keep ~22 mantissa bits at no extra cost (they fit the zero padding of the K=16 slices).
+//     direction inputs keep ~22 mantissa bits at no extra cost (they fit the zero padding of the K=16 slices);
+//   * for d <= 4 the 128->d output layer is accumulated on the CUDA cores inside the last epilogue (one handshake less).
 //
-// Handshake per layer and half h: particle threads -> bar_a[h] (128 arrivals: "K-slices 4h..4h+3 of the next A operand
-// written, D half h consumed") -> MMA warp issues -> tcgen05.commit -> bar_d[h] -> particle threads read D half h.
 // All waits are bounded; a timeout sets a flag in the context workspace (msgm_debug_flags) instead of hanging.
 #include <cuda_fp16.h>
 
@@ -32,13 +28,8 @@
 
 namespace msgm {
 
-constexpr int TM = 128;            // particles per CTA tile (= UMMA M = TMEM lanes)
-constexpr int TC_THREADS = 288;    // 4 owner warps (D half 0 + particle state) + 4 helper warps (D half 1) + 1 MMA warp
-constexpr int TC_MMA_TID = 256;    // lane 0 of warp 8 issues the MMAs
-constexpr uint32_t COL_D = 0;      // accumulator: 128 fp32 columns (two N=64 halves)
-constexpr uint32_t COL_A0 = 128;   // activation buffer 0: 64 columns of packed fp16 pairs (layer-1 operand, act 2)
-constexpr uint32_t COL_A1 = 192;   // activation buffer 1 (act 1, act 3)
-constexpr uint32_t TMEM_COLS = 256;
+constexpr int TM = 128;            // particles per tile (= UMMA M = TMEM lanes)
+constexpr int A_BYTES = 128 * 128 * 2;  // one slot's activation tile: fp16 [k/8][row/8][8][8]
 
 template <int DP>
 struct TcLayout {
@@ -56,10 +47,12 @@ struct TcLayout {
   static constexpr int oG = oOnes + 4096;                      // fp32 [DP][DP][DP] (dense)
   static constexpr int oLG = oG + 4 * DP * DP * DP;            // fp32 [DP][DP]
   static constexpr int oW4f = oLG + 4 * DP * DP;               // fp32 [128][DP] + b4[DP]: CUDA-core output layer
-  static constexpr int oPart = oW4f + 4 * (128 * DP + DP);     // fp32 [128][DP]: helper warps' partial output layer
-  static constexpr int oBar = oPart + 4 * 128 * DP;            // 5 mbarriers + tmem slot
-  static constexpr int SMEM_BYTES = oBar + 96;
+  static constexpr int oBar = ((oW4f + 4 * (128 * DP + DP) + 15) / 16) * 16;  // 1 + 2*NSLOT mbarriers + tmem slot
+  static constexpr int oA = oBar + 128;                        // NSLOT activation tiles
   static constexpr bool L4_CC = DP <= 4;                       // output layer on CUDA cores
+  static constexpr int NSLOT = DP <= 4 ? 4 : 3;                // tiles in flight per CTA (registers / smem bound)
+  static constexpr int THREADS = 128 * NSLOT + 32;             // 4 particle warps per slot + 1 MMA issuer warp
+  static constexpr int SMEM_BYTES = oA + NSLOT * A_BYTES;
 };
 
 struct TcParams {
@@ -223,17 +216,23 @@ __device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
   return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
 }
 
-// Activation epilogue of one N=64 half of a hidden layer: D half (64 fp32 cols, = z/2) -> Swish -> packed fp16 ->
-// 32 columns of the next activation buffer.  With ACC_OUT the 128->d output layer is accumulated on the fly from the
-// fp32 activations (a_c += W4[n][c] s_n) and nothing is stored.
-template <int DP, bool ACC_OUT>
-__device__ __forceinline__ void swish_half(uint32_t lane_base, int half, uint32_t col_out, const float* __restrict__ sW4f,
-                                           float* a) {
+// 16 packed activation registers (32 fp16 = 4 k-chunks of 8) -> the slot's smem A tile, row `row`.
+__device__ __forceinline__ void store_a_chunks(unsigned char* sA, int row, int first_chunk, const uint32_t* q) {
+  unsigned char* base = sA + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int c = half * 2 + cc;
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<uint4*>(base + (first_chunk + i) * 2048) = make_uint4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+}
+
+// Activation epilogue of one hidden layer for one particle row: D (128 fp32 cols, = z/2) -> Swish -> either packed
+// fp16 into the slot's smem A tile, or (ACC_OUT) straight into the 128->d output layer a_c += W4[n][c] s_n.
+template <int DP, bool ACC_OUT>
+__device__ __forceinline__ void swish_epilogue(uint32_t taddr, unsigned char* sA, int row, const float* __restrict__ sW4f,
+                                               float* a) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
     uint32_t r[32], q[16];
-    TMEM_LD32(lane_base + COL_D + c * 32, r);
+    TMEM_LD32(taddr + c * 32, r);
     tc_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -251,64 +250,62 @@ __device__ __forceinline__ void swish_half(uint32_t lane_base, int half, uint32_
         q[j] = pack_f16x2(s0, s1);
       }
     }
-    if constexpr (!ACC_OUT) TMEM_ST16(lane_base + col_out + c * 16, q);
+    if constexpr (!ACC_OUT) store_a_chunks(sA, row, 4 * c, q);
   }
-  if constexpr (!ACC_OUT) tc_wait_st();
 }
 
 template <int DP, int KIND>
-__global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_constant__ TcParams P) {
+__global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(const __grid_constant__ TcParams P) {
   using L = TcLayout<DP>;
-  constexpr int MP = L::MP, K1 = L::K1;
+  constexpr int MP = L::MP, K1 = L::K1, NSLOT = L::NSLOT;
+  constexpr bool L4_CC = L::L4_CC;
   extern __shared__ __align__(128) unsigned char smem[];
   float* sG = reinterpret_cast<float*>(smem + L::oG);
   float* sLG = reinterpret_cast<float*>(smem + L::oLG);
   float* sW4f = reinterpret_cast<float*>(smem + L::oW4f);
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + L::oBar);
-  uint64_t* bar_a0 = bar_w + 1;
-  uint64_t* bar_a1 = bar_w + 2;
-  uint64_t* bar_d0 = bar_w + 3;
-  uint64_t* bar_d1 = bar_w + 4;
-  uint64_t* bar_p = bar_w + 5;  // [4]: helper warp q -> owner warp q, partial output-layer sums are in smem
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 9);
-  constexpr bool L4_CC = L::L4_CC;
+  uint64_t* bar_a = bar_w + 1;          // [NSLOT] operand of the slot's next layer is in smem, D consumed
+  uint64_t* bar_d = bar_a + NSLOT;      // [NSLOT] the slot's accumulator is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + NSLOT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = P.d;
   const int nstage = P.scheme == MSGM_SCHEME_RK4 ? 4 : (P.scheme == MSGM_SCHEME_HEUN ? 2 : 1);
   const long long ntiles = (P.B + TM - 1) / TM;
+  const long long tstride = (long long)gridDim.x * NSLOT;
 
   // ---- setup ----------------------------------------------------------------------------------------------------
-  if (tid == TC_MMA_TID) {
+  if (tid == 128 * NSLOT) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_a0, 128);
-    mbar_init(bar_a1, 128);
-    mbar_init(bar_d0, 1);
-    mbar_init(bar_d1, 1);
-    for (int q4 = 0; q4 < 4; ++q4) mbar_init(bar_p + q4, 32);
+    for (int sl = 0; sl < NSLOT; ++sl) {
+      mbar_init(bar_a + sl, 128);
+      mbar_init(bar_d + sl, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (KIND == MSGM_SDE_MSGM_DENSE) {
-    for (int e = tid; e < DP * DP * DP; e += TC_THREADS) {
+    for (int e = tid; e < DP * DP * DP; e += L::THREADS) {
       int i = e / (DP * DP), j = (e / DP) % DP, k = e % DP;
       sG[e] = (i < d && j < d && k < d) ? __ldg(P.G + (i * d + j) * d + k) : 0.0f;
     }
-    for (int e = tid; e < DP * DP; e += TC_THREADS) {
+    for (int e = tid; e < DP * DP; e += L::THREADS) {
       int i = e / DP, j = e % DP;
       sLG[e] = (i < d && j < d) ? __ldg(P.LG + i * d + j) : 0.0f;
     }
   }
   {  // "ones" A operand of the bias slices: rows x k, k = 0,1 -> 1.0 (the bias rides there split hi+lo), rest 0
     __half* ones = reinterpret_cast<__half*>(smem + L::oOnes);
-    for (int e = tid; e < 2048; e += TC_THREADS) ones[e] = __ushort_as_half((e < 1024 && (e & 7) < 2) ? 0x3C00 : 0);
+    for (int e = tid; e < 2048; e += L::THREADS) ones[e] = __ushort_as_half((e < 1024 && (e & 7) < 2) ? 0x3C00 : 0);
+    // zero the activation tiles once: the layer-1 operand only ever rewrites its first K1/8 k-chunks
+    uint4* za = reinterpret_cast<uint4*>(smem + L::oA);
+    for (int e = tid; e < NSLOT * A_BYTES / 16; e += L::THREADS) za[e] = make_uint4(0, 0, 0, 0);
   }
   if (L4_CC) {
-    for (int e = tid; e < 128 * DP; e += TC_THREADS) {
+    for (int e = tid; e < 128 * DP; e += L::THREADS) {
       int n = e / DP, c = e % DP;
       sW4f[e] = c < d ? __ldg(P.W4 + c * 128 + n) : 0.0f;
     }
@@ -319,7 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
-  if (tid == TC_MMA_TID) {  // weights: one TMA bulk copy per layer image, all landing on bar_w
+  if (tid == 128 * NSLOT) {  // weights: one TMA bulk copy per layer image, all landing on bar_w
     mbar_expect_tx(bar_w, (uint32_t)L::IMG_BYTES);
     tma_bulk_g2s(smem + L::oW1, P.img + L::oW1, L::W1_BYTES, bar_w);
     tma_bulk_g2s(smem + L::oW2, P.img + L::oW2, L::WH_BYTES, bar_w);
@@ -327,133 +324,101 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
     tma_bulk_g2s(smem + L::oW4, P.img + L::oW4, L::W4_BYTES, bar_w);
   }
 
-  if (warp == 8) {
+  if (warp == 4 * NSLOT) {
     // =========================================== MMA issuer ===================================================
-    {
-      const uint32_t lead = lane == 0 ? 1u : 0u;
-      bool ok = mbar_wait(bar_w, 0, P.flags);
-      const uint32_t idesc_h = umma_idesc_f16(128, 128), idesc_o = umma_idesc_f16(128, 16);
-      const uint32_t sW1 = smem_u32(smem + L::oW1), sW2 = smem_u32(smem + L::oW2), sW3 = smem_u32(smem + L::oW3),
-                     sW4 = smem_u32(smem + L::oW4);
-      const uint32_t idesc_64 = umma_idesc_f16(128, 64);
-      const uint64_t ones_desc = umma_desc(smem_u32(smem + L::oOnes), 2048, 128);
-      uint32_t pa0 = 0, pa1 = 0;
-      (void)idesc_h;
-      Prof pf{(P.prof && blockIdx.x == 0 && lane == 0) ? P.prof + 8 : nullptr, 0};
-      pf.start();
-      for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
-        for (int it = 0; it < P.N * nstage && ok; ++it) {
-          // ---- layer 1 (operand in buffer 0): K1/16 slices per half, bias rides in the padding of the last slice
-          // (waits for the owners only: the helpers' last reads of D were ordered before the owners' arrival)
-          ok = mbar_wait(bar_a0, pa0, P.flags); pa0 ^= 1;
-          tc_fence_after();
-          pf.tick(0);  // wait for the layer-1 operand
+    // The warp runs converged: it polls the slots' "operand ready" barriers round-robin, issues whatever layer is
+    // ready (the tcgen05 instructions themselves are predicated on lane 0) and commits to that slot's accumulator
+    // barrier.  Measured on B200 this beats a single-lane issue branch and one issuer warp per slot.
+    constexpr int NLAYER = L4_CC ? 3 : 4;  // MMA layers per stage
+    const uint32_t lead = lane == 0 ? 1u : 0u;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint32_t sbase = smem_u32(smem);
+    bool ok = mbar_wait(bar_w, 0, P.flags);
+    const uint32_t idesc_h = umma_idesc_f16(128, 128), idesc_o = umma_idesc_f16(128, 16);
+    // descriptors of K-slice s are base + s * (slice bytes >> 4): only the 14-bit address field moves
+    const uint64_t ones_desc = umma_desc(sbase + L::oOnes, 2048, 128);
+    const uint64_t w1_desc = umma_desc(sbase + L::oW1, 2048, 128);
+    const uint64_t w2_desc = umma_desc(sbase + L::oW2, 2048, 128);
+    const uint64_t w3_desc = umma_desc(sbase + L::oW3, 2048, 128);
+    const uint64_t w4_desc = umma_desc(sbase + L::oW4, 256, 128);
+    Prof pf{(P.prof && blockIdx.x == 0 && lane == 0) ? P.prof + 8 : nullptr, 0};
+    pf.start();
+    // per-slot progress: number of layers issued so far, and how many the slot will need in total
+    long long done[NSLOT], total[NSLOT];
+    long long remaining = 0;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+    for (int sl = 0; sl < NSLOT; ++sl) {
+      const long long first = (long long)blockIdx.x * NSLOT + sl;
+      const long long nt = first < ntiles ? (ntiles - first + tstride - 1) / tstride : 0;
+      done[sl] = 0;
+      total[sl] = nt * P.N * nstage * NLAYER;
+      remaining += total[sl];
+    }
+    long long idle_since = clock64();
+    while (remaining > 0 && ok) {
+      bool progressed = false;
 #pragma unroll
-            for (int s = 0; s < K1 / 16; ++s)
-              umma_ts(tbase + COL_D + 64 * h, tbase + COL_A0 + 8 * s, umma_desc(sW1 + s * 4096 + h * 1024, 2048, 128),
-                      idesc_64, s > 0, lead);
-            umma_commit(h == 0 ? bar_d0 : bar_d1, lead);
-          }
-          // ---- layers 2 (operand in buffer 1) and 3 (buffer 0): ones-slice (bias) + 8 slices, two N=64 halves.
-          // Output half 0 starts as soon as the first four K-slices of the operand exist (bar_a0).
-#pragma unroll
-          for (int l = 0; l < 2; ++l) {
-            const uint32_t sW = l == 0 ? sW2 : sW3;
-            const uint32_t Ain = tbase + (l == 0 ? COL_A1 : COL_A0);
-            pf.tick(1);  // issue
-            ok = ok && mbar_wait(bar_a0, pa0, P.flags); pa0 ^= 1; tc_fence_after();
-            pf.tick(2);  // wait a0 (hidden)
-            umma_ss(tbase + COL_D, ones_desc, umma_desc(sW, 2048, 128), idesc_64, 0, lead);
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-              umma_ts(tbase + COL_D, Ain + 8 * s, umma_desc(sW + (s + 1) * 4096, 2048, 128), idesc_64, 1, lead);
-            pf.tick(1);
-            ok = ok && mbar_wait(bar_a1, pa1, P.flags); pa1 ^= 1; tc_fence_after();
-            pf.tick(3);  // wait a1 (hidden)
-#pragma unroll
-            for (int s = 4; s < 8; ++s)
-              umma_ts(tbase + COL_D, Ain + 8 * s, umma_desc(sW + (s + 1) * 4096, 2048, 128), idesc_64, 1, lead);
-            umma_commit(bar_d0, lead);
-            umma_ss(tbase + COL_D + 64, ones_desc, umma_desc(sW + 1024, 2048, 128), idesc_64, 0, lead);
-#pragma unroll
-            for (int s = 0; s < 8; ++s)
-              umma_ts(tbase + COL_D + 64, Ain + 8 * s, umma_desc(sW + (s + 1) * 4096 + 1024, 2048, 128), idesc_64, 1, lead);
-            umma_commit(bar_d1, lead);
-          }
-          pf.tick(1);
-          // ---- output layer on the tensor pipe (d > 4): N = 16, operand in buffer 1
-          if (!L4_CC) {
-            ok = ok && mbar_wait(bar_a0, pa0, P.flags); pa0 ^= 1;
-            ok = ok && mbar_wait(bar_a1, pa1, P.flags); pa1 ^= 1;
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        if (done[sl] < total[sl]) {
+          const int ready = __shfl_sync(0xffffffffu, (int)mbar_try(bar_a + sl, (uint32_t)(done[sl] & 1)), 0);
+          if (ready) {
             tc_fence_after();
-            pf.tick(4);  // wait for act3
-            umma_ss(tbase + COL_D, ones_desc, umma_desc(sW4, 256, 128), idesc_o, 0, lead);
+            const int layer = (int)(done[sl] % NLAYER);
+            const uint32_t dcol = tb + 128 * sl;
+            const uint64_t a_desc = umma_desc(sbase + L::oA + sl * A_BYTES, 2048, 128);
+            if (layer == 0) {  // layer 1: K1/16 slices, bias rides in the padding of the last one
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
-              umma_ts(tbase + COL_D, tbase + COL_A1 + 8 * s, umma_desc(sW4 + (s + 1) * 512, 256, 128), idesc_o, 1, lead);
-            umma_commit(bar_d0, lead);
-            pf.tick(1);
+              for (int s = 0; s < K1 / 16; ++s) umma_ss(dcol, a_desc + s * 256, w1_desc + s * 256, idesc_h, s > 0, lead);
+            } else if (layer < 3) {  // layers 2, 3: ones-slice (bias) + 8 slices
+              const uint64_t w_desc = layer == 1 ? w2_desc : w3_desc;
+              umma_ss(dcol, ones_desc, w_desc, idesc_h, 0, lead);
+#pragma unroll
+              for (int s = 0; s < 8; ++s) umma_ss(dcol, a_desc + s * 256, w_desc + (s + 1) * 256, idesc_h, 1, lead);
+            } else {  // output layer on the tensor pipe (d > 4): N = 16, slices of 512 B
+              umma_ss(dcol, ones_desc, w4_desc, idesc_o, 0, lead);
+#pragma unroll
+              for (int s = 0; s < 8; ++s) umma_ss(dcol, a_desc + s * 256, w4_desc + (s + 1) * 32, idesc_o, 1, lead);
+            }
+            umma_commit(bar_d + sl, lead);
+            done[sl] += 1;
+            remaining -= 1;
+            progressed = true;
+            pf.tick(1);  // issue
           }
+        }
+      }
+      if (progressed) {
+        idle_since = clock64();
+      } else {
+        pf.tick(0);  // polling with nothing ready
+        if (clock64() - idle_since > 400000000LL || *reinterpret_cast<volatile int*>(P.flags) != 0) {
+          if (lane == 0) atomicExch(P.flags, 1);
+          ok = false;
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ======================================= helper warps: D columns 64..127 ================================
-    const int q = warp - 4;
-    const uint32_t lane_base = tbase + ((uint32_t)(q * 32) << 16);
-    float* part = reinterpret_cast<float*>(smem + L::oPart) + (q * 32 + lane) * DP;
-    uint32_t pd1 = 0;
-    bool ok = true;
-    Prof pf{(P.prof && blockIdx.x == 0 && tid == 128) ? P.prof + 16 : nullptr, 0};
-    pf.start();
-    for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
-      for (int it = 0; it < P.N * nstage && ok; ++it) {
-        float a[DP];
-#pragma unroll
-        for (int c = 0; c < DP; ++c) a[c] = 0.0f;
-#pragma unroll 1
-        for (int l = 0; l < 2; ++l) {
-          ok = ok && mbar_wait(bar_d1, pd1, P.flags); pd1 ^= 1; tc_fence_after();
-          pf.tick(0);  // wait d1
-          swish_half<DP, false>(lane_base, 1, l == 0 ? COL_A1 : COL_A0, sW4f, a);
-          tc_fence_before();
-          mbar_arrive(bar_a1);
-          pf.tick(1);  // epilogue
-        }
-        ok = ok && mbar_wait(bar_d1, pd1, P.flags); pd1 ^= 1; tc_fence_after();
-        pf.tick(0);
-        swish_half<DP, L4_CC>(lane_base, 1, COL_A1, sW4f, a);
-        pf.tick(1);
-        if (L4_CC) {
-#pragma unroll
-          for (int c = 0; c < DP; ++c) part[c] = a[c];
-          mbar_arrive(bar_p + q);  // release: the owner warp of the same lanes acquires through the mbarrier
-        } else {
-          tc_fence_before();
-          mbar_arrive(bar_a1);
-        }
-      }
-    }
   } else {
-    // ======================================= owner warps: particle state + D columns 0..63 ==================
-    const float* part = reinterpret_cast<const float*>(smem + L::oPart) + tid * DP;
-    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    // ======================================= particle threads ================================================
+    const int sl = warp >> 2;          // slot
+    const int row = tid & 127;         // particle row in the tile == TMEM lane
+    const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 128 * sl;
+    unsigned char* sA = smem + L::oA + sl * A_BYTES;
+    uint64_t* my_a = bar_a + sl;
+    uint64_t* my_d = bar_d + sl;
     const float lm = P.lmbd;
     const float c_w = sqrtf(1.0f - lm);
     const bool ito = (P.scheme == MSGM_SCHEME_EM);
     const float c_f = ito ? (1.0f - 2.0f * lm) : -lm;
     const float delta = P.delta;
     const float c_a = delta * (1.0f - 0.5f * lm);
-    uint32_t pd0 = 0, pp = 0;
+    uint32_t pd = 0;
     bool ok = true;
     Prof pf{(P.prof && blockIdx.x == 0 && tid == 0) ? P.prof : nullptr, 0};
     pf.start();
 
-    for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
-      const long long gp = tile * TM + tid;
+    for (long long tile = (long long)blockIdx.x * NSLOT + sl; tile < ntiles && ok; tile += tstride) {
+      const long long gp = tile * TM + row;
       const bool live = gp < P.B;
       float x[DP], y[DP], ks[DP], dw[DP];
 #pragma unroll
@@ -505,9 +470,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
 #pragma unroll
               for (int c = 0; c < DP; ++c) r = fmaf(y[c], y[c], r);
               const float rn = sqrtf(r) + 1e-6f;
+              const float inv = __frcp_rn(rn);
 #pragma unroll
-              for (int c = 0; c < DP; ++c) u[c] = y[c] / rn;
-              u[DP] = logf(rn);
+              for (int c = 0; c < DP; ++c) u[c] = y[c] * inv;
+              u[DP] = __logf(rn);
             } else {
 #pragma unroll
               for (int c = 0; c < DP; ++c) u[c] = y[c];
@@ -527,53 +493,49 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
             }
             hk[3 * MP] = __ushort_as_half(0x3C00);
             hk[3 * MP + 1] = __ushort_as_half(0x3C00);
-            uint32_t q[K1 / 2];
+            unsigned char* base = sA + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
-            for (int j = 0; j < K1 / 2; ++j) q[j] = pack_h2(hk[2 * j], hk[2 * j + 1]);
-#pragma unroll
-            for (int c = 0; c < K1 / 16; ++c) TMEM_ST8(lane_base + COL_A0 + 8 * c, (q + 8 * c));
-            tc_wait_st();
+            for (int ch = 0; ch < K1 / 8; ++ch)
+              *reinterpret_cast<uint4*>(base + ch * 2048) =
+                  make_uint4(pack_h2(hk[8 * ch], hk[8 * ch + 1]), pack_h2(hk[8 * ch + 2], hk[8 * ch + 3]),
+                             pack_h2(hk[8 * ch + 4], hk[8 * ch + 5]), pack_h2(hk[8 * ch + 6], hk[8 * ch + 7]));
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           tc_fence_before();
-          mbar_arrive(bar_a0);
+          mbar_arrive(my_a);
           pf.tick(0);  // SDE update + layer-1 operand
 
-          // ---- hidden layers: act1 -> buffer 1, act2 -> buffer 0, act3 -> buffer 1 (or straight into a) -----------
+          // ---- hidden layers ---------------------------------------------------------------------------------------
           float a[DP];
 #pragma unroll
           for (int c = 0; c < DP; ++c) a[c] = L4_CC ? sW4f[128 * DP + c] : 0.0f;
 #pragma unroll 1
           for (int l = 0; l < 2; ++l) {
-            ok = ok && mbar_wait(bar_d0, pd0, P.flags); pd0 ^= 1; tc_fence_after();
-            pf.tick(1 + l);  // wait d0 of layer 1 / layer 2
-            swish_half<DP, false>(lane_base, 0, l == 0 ? COL_A1 : COL_A0, sW4f, a);
+            ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
+            pf.tick(1);  // wait for the accumulator
+            swish_epilogue<DP, false>(taddr, sA, row, sW4f, a);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(bar_a0);
-            pf.tick(4);  // epilogue
+            mbar_arrive(my_a);
+            pf.tick(2);  // epilogue
           }
-          ok = ok && mbar_wait(bar_d0, pd0, P.flags); pd0 ^= 1; tc_fence_after();
-          pf.tick(3);  // wait d0 of layer 3
-          swish_half<DP, L4_CC>(lane_base, 0, COL_A1, sW4f, a);
-          tc_fence_before();
-          pf.tick(4);
-          if (L4_CC) {
-            ok = ok && mbar_wait(bar_p + warp, pp, P.flags); pp ^= 1;  // helper's partial sums are in smem
-#pragma unroll
-            for (int c = 0; c < DP; ++c) a[c] += part[c];
-          } else {
-            mbar_arrive(bar_a0);
-          }
-          // ---- output layer result (tensor-pipe variant) ---------------------------------------------------------------------
+          ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
+          pf.tick(1);
+          swish_epilogue<DP, L4_CC>(taddr, sA, row, sW4f, a);
+          pf.tick(2);
           if (!L4_CC) {
-            ok = ok && mbar_wait(bar_d0, pd0, P.flags); pd0 ^= 1; tc_fence_after();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(my_a);
+            ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
             uint32_t r[16];
-            TMEM_LD16(lane_base + COL_D, r);
+            TMEM_LD16(taddr, r);
             tc_wait_ld();
 #pragma unroll
             for (int c = 0; c < DP; ++c) a[c] = __uint_as_float(r[c]);
+            pf.tick(3);  // output layer on the tensor pipe
           }
 
-          pf.tick(5);  // output layer hand-off
           // ---- stage increment K = delta * drift + sigma . dW (same algebra as sampler_fp32.cu) --------------------------
           float K[DP];
           if (KIND == MSGM_SDE_SGM) {
@@ -651,7 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
               if (st == 0) { ks[c] = K[c]; y[c] = x[c] + K[c] / 2.0f; }
               else if (st == 1) { ks[c] = ks[c] + 2.0f * K[c]; y[c] = x[c] + K[c] / 2.0f; }
               else if (st == 2) { ks[c] = ks[c] + 2.0f * K[c]; y[c] = x[c] + K[c]; }
-              else { x[c] = x[c] + (ks[c] + K[c]) / 6.0f; }
+              else { x[c] = fmaf(ks[c] + K[c], 1.0f / 6.0f, x[c]); }
             }
           }
         }  // stages
@@ -660,7 +622,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
           float r = 0.0f;
 #pragma unroll
           for (int c = 0; c < DP; ++c) r = fmaf(x[c], x[c], r);
-          const float sc = r0 / sqrtf(r);
+          const float sc = r0 * rsqrtf(r);
 #pragma unroll
           for (int c = 0; c < DP; ++c) x[c] *= sc;
         }
@@ -686,9 +648,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) sample_tc_kernel(const __grid_c
     }  // tiles
   }
 
+
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(TMEM_COLS));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
 // ---- weight packing: torch Linear layout -> fp16 core-matrix images ----------------------------------------------
@@ -766,8 +729,8 @@ static int launch_tc(msgm_ctx* ctx, const msgm_mlp_desc* m, TcParams& P, cudaStr
   auto kern = sample_tc_kernel<DP, KIND>;
   MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES));
   const long long ntiles = (P.B + TM - 1) / TM;
-  const int grid = (int)std::min<long long>(ntiles, 2LL * ctx->num_sms);
-  kern<<<grid, TC_THREADS, L::SMEM_BYTES, stream>>>(P);
+  const int grid = (int)std::min<long long>((ntiles + L::NSLOT - 1) / L::NSLOT, (long long)ctx->num_sms);
+  kern<<<grid, L::THREADS, L::SMEM_BYTES, stream>>>(P);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

@@ -113,6 +113,21 @@ int msgm_sample_mlp(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc
 int msgm_mlp_forward(msgm_ctx* ctx, const msgm_mlp_desc* mlp, const float* y, const float* s, float* out,
                      int64_t B, void* stream);
 
+/* Sliced-score-matching train step for the MLP score net.  Replaces PluginReverseSDE.ssm_loss (SDEs.py:616-646):
+ *   loss[b] = v_b^T d/dy[ mu_to_div(y_b) ] v_b + |a(y_b, t_b)|^2 / 2
+ * evaluated in forward mode (primal + tangent through the net) instead of autograd's VJP, and differentiated by hand
+ * instead of double backward.  y (B,d) are the noised samples, v (B,d) the Hutchinson probes (SDEs.py:514-536), t (B,)
+ * the noise times.  `scratch` is caller-owned device memory of msgm_ssm_scratch_bytes(B) bytes that carries the
+ * activations from the forward to the backward call.  The backward call takes the upstream gradient of the per-sample
+ * loss, grad_out (B,) (1/B for `.mean().backward()`), and writes d(sum_b grad_out[b] loss[b])/d(theta) into grad_flat in
+ * torch parameter order [W0 (128,d+1+pre), b0, W1, b1, W2, b2, W3 (d,128), b3]. */
+uint64_t msgm_ssm_scratch_bytes(int64_t B);
+int msgm_ssm_mlp_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const float* y,
+                         const float* v, const float* t, float* loss_out, void* scratch, int64_t B, void* stream);
+int msgm_ssm_mlp_backward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const float* y,
+                          const float* v, const float* t, const float* grad_out, void* scratch, float* grad_flat,
+                          int64_t B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,11 +79,12 @@ class SDE(torch.nn.Module):
 
     # ---- forward noising by simulation (reference SDEs.py:78-132) ------------------------------------------------
     @torch.no_grad()
-    def sample_scheme(self, t, y0, keep_all_samples, return_noise=False):
+    def sample_scheme(self, t, y0, keep_all_samples, return_noise=False, *, noise=None, noise_rows=None):
         """y_t | y_0: the state after trunc(N_fwd t/T) RK4 steps; rows with 0 steps take ONE step of size t.
 
         Two launches replace the reference's per-row Python loop: the whole batch with a per-row capture index,
-        then all zero-step rows together with a per-row horizon (args.T_rows).
+        then all zero-step rows together with a per-row horizon (args.T_rows).  ``noise`` (N_fwd,B,d) and
+        ``noise_rows`` (n_zero_step_rows,d) inject the standard normals the reference would have drawn (parity tests).
         """
         if return_noise:
             raise NotImplementedError('See the official repository.')
@@ -97,18 +98,21 @@ class SDE(torch.nn.Module):
             print('warning : t >= T')
             n_int[late] = n_tot
         yt = self.sample_scheme_allt(y0, include_t0=True, keep_all_samples=False, samplesToKeep=n_int,
-                                     _device_out=True)
+                                     _device_out=True, _noise=noise)
         small = (n_int == 0).nonzero().reshape(-1)
         if small.numel():
             from . import sde_scheme
-            yt[small] = sde_scheme._run_rows(forward_SDE(self, self.T), y0[small], t.reshape(-1)[small])
+            yt[small] = sde_scheme._run_rows(forward_SDE(self, self.T), y0[small], t.reshape(-1)[small],
+                                             noise=None if noise_rows is None else noise_rows.reshape(1, -1, y0.shape[1]))
         return yt.to(self.device)
 
     @torch.no_grad()
-    def sample_scheme_allt(self, y0, include_t0=True, keep_all_samples=True, samplesToKeep=None, _device_out=False):
+    def sample_scheme_allt(self, y0, include_t0=True, keep_all_samples=True, samplesToKeep=None, _device_out=False,
+                           _noise=None):
         return rk4_stratonovich_sampler(forward_SDE(self, self.T).to(self.device), y0,
                                         num_steps=self.num_steps_forward, lmbd=0, keep_all_samples=keep_all_samples,
-                                        samplesToKeep=samplesToKeep, include_t0=include_t0, device_out=_device_out)
+                                        samplesToKeep=samplesToKeep, include_t0=include_t0, device_out=_device_out,
+                                        noise=_noise)
 
     def sample_Song_et_al(self, t, y0, return_noise=False):
         """Closed-form VP marginal (reference SDEs.py:134-146)."""

@@ -43,7 +43,8 @@ _ctx = {}
 
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
-           "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters"]
+           "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
+           "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward"]
 
 
 def lib() -> C.CDLL:
@@ -62,6 +63,12 @@ def lib() -> C.CDLL:
                 L.msgm_destroy.argtypes = [C.c_void_p]
                 L.msgm_launch_count.argtypes = [C.c_void_p]
                 L.msgm_debug_flags.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+                L.msgm_ssm_scratch_bytes.restype = C.c_uint64
+                L.msgm_ssm_scratch_bytes.argtypes = [C.c_int64]
+                L.msgm_ssm_mlp_forward.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc)] + [C.c_void_p] * 5 + \
+                    [C.c_int64, C.c_void_p]
+                L.msgm_ssm_mlp_backward.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc)] + [C.c_void_p] * 6 + \
+                    [C.c_int64, C.c_void_p]
                 L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]

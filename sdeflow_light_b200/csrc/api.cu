@@ -19,6 +19,12 @@ int sample_mlp_tc(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const m
                   cudaStream_t);
 int mlp_forward_fp32(msgm_ctx*, const msgm_mlp_desc*, const float*, const float*, float*, int64_t, cudaStream_t);
 
+size_t ssm_scratch_floats(long long B);
+int ssm_forward(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const float*, const float*, const float*, float*,
+                float*, int64_t, cudaStream_t);
+int ssm_backward(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const float*, const float*, const float*,
+                 const float*, float*, float*, int64_t, cudaStream_t);
+
 static int invalid(const char* msg) {
   set_error(msg);
   return MSGM_ERR_INVALID;
@@ -134,6 +140,42 @@ int msgm_mlp_forward(msgm_ctx* ctx, const msgm_mlp_desc* mlp, const float* y, co
   if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return mlp_forward_fp32(ctx, mlp, y, s, out, B, (cudaStream_t)stream);
+}
+
+static int check_ssm(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, int64_t B) {
+  if (!ctx || !sde || !mlp) return invalid("msgm_ssm: NULL argument");
+  if (B < 0) return invalid("msgm_ssm: B < 0");
+  if (sde->dim < 1 || sde->dim > MSGM_MAX_DIM_MLP) {
+    set_error("msgm_ssm: dim must be in [1,32] for the MLP path");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (sde->kind < MSGM_SDE_SGM || sde->kind > MSGM_SDE_MSGM_SPARSE) return invalid("unknown sde kind");
+  if (sde->kind == MSGM_SDE_MSGM_DENSE && !sde->G) return invalid("dense MSGM needs G");
+  return check_mlp(mlp, sde->dim);
+}
+
+uint64_t msgm_ssm_scratch_bytes(int64_t B) { return sizeof(float) * (uint64_t)ssm_scratch_floats(B < 1 ? 1 : B); }
+
+int msgm_ssm_mlp_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const float* y,
+                         const float* v, const float* t, float* loss_out, void* scratch, int64_t B, void* stream) {
+  int rc = check_ssm(ctx, sde, mlp, B);
+  if (rc) return rc;
+  if (B == 0) return MSGM_OK;
+  if (!y || !v || !t || !loss_out || !scratch) return invalid("msgm_ssm_mlp_forward: NULL buffer");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return ssm_forward(ctx, sde, mlp, y, v, t, loss_out, (float*)scratch, B, (cudaStream_t)stream);
+}
+
+int msgm_ssm_mlp_backward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const float* y,
+                          const float* v, const float* t, const float* grad_out, void* scratch, float* grad_flat,
+                          int64_t B, void* stream) {
+  int rc = check_ssm(ctx, sde, mlp, B);
+  if (rc) return rc;
+  if (!grad_flat) return invalid("msgm_ssm_mlp_backward: NULL buffer");
+  if (B == 0) return MSGM_OK;
+  if (!y || !v || !t || !grad_out || !scratch) return invalid("msgm_ssm_mlp_backward: NULL buffer");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return ssm_backward(ctx, sde, mlp, y, v, t, grad_out, (float*)scratch, grad_flat, B, (cudaStream_t)stream);
 }
 
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {

@@ -1,0 +1,77 @@
+"""Sliced score matching through the fused CUDA kernels (msgm_ssm_mlp_forward / _backward).
+
+``ssm(gen, x)`` follows ``PluginReverseSDE.ssm`` of the reference (SDEs.py:607-646): draw t, noise x forward to y_t,
+draw the Hutchinson probe v (same RNG call order as the reference), and return the per-sample loss (B,).  The loss
+is a ``torch.autograd.Function`` node: ``loss.mean().backward()`` fills ``.grad`` of the score net's parameters from
+the hand-derived backward kernels, so ``torch.optim.Adam(gen.parameters())`` trains exactly as in the reference driver
+(MSGM_higherDim.py:803-809).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class _SsmMlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gen, t, y, v, *params):
+        dev = y.device
+        handle = _lib.ctx(dev)
+        base, net = gen.base_sde, gen.a
+        B = y.shape[0]
+        sd, keep = base.desc(dev)
+        md, k2 = net.desc(dev)
+        yc, vc, tc = _lib.f32c(y, dev), _lib.f32c(v, dev), _lib.f32c(t.reshape(-1), dev)
+        loss = torch.empty(B, device=dev, dtype=torch.float32)
+        scratch = torch.empty(int(_lib.lib().msgm_ssm_scratch_bytes(B)) // 4, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().msgm_ssm_mlp_forward(handle, C.byref(sd), C.byref(md), _lib.ptr(yc), _lib.ptr(vc),
+                                                   _lib.ptr(tc), _lib.ptr(loss), _lib.ptr(scratch), B,
+                                                   _lib.stream_ptr(dev)))
+        ctx.gen, ctx.saved = gen, (yc, vc, tc, scratch, keep + k2)
+        ctx.shapes = [p.shape for p in params]
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        yc, vc, tc, scratch, _ = ctx.saved
+        dev = yc.device
+        gen = ctx.gen
+        base, net = gen.base_sde, gen.a
+        sd, keep = base.desc(dev)
+        md, k2 = net.desc(dev)
+        n = sum(int(torch.Size(s).numel()) for s in ctx.shapes)
+        flat = torch.empty(n, device=dev, dtype=torch.float32)
+        g = _lib.f32c(gout, dev)
+        _lib.check(_lib.lib().msgm_ssm_mlp_backward(_lib.ctx(dev), C.byref(sd), C.byref(md), _lib.ptr(yc),
+                                                    _lib.ptr(vc), _lib.ptr(tc), _lib.ptr(g), _lib.ptr(scratch),
+                                                    _lib.ptr(flat), yc.shape[0], _lib.stream_ptr(dev)))
+        grads, o = [], 0
+        for s in ctx.shapes:
+            k = int(torch.Size(s).numel())
+            grads.append(flat[o:o + k].view(s))
+            o += k
+        return (None, None, None, None, *grads)
+
+
+def ssm_loss(gen, t_, x, y, v=None):
+    """Per-sample SSM loss for given (t, y); ``v`` defaults to a fresh probe like the reference (SDEs.py:637-638)."""
+    from . import NN, SDEs
+    net = gen.a
+    if not (isinstance(net, NN.MLP) and net.fused_ok()):
+        raise NotImplementedError("fused SSM is built for the MLP score net (NN.MLP, hidden 128, d <= 32)")
+    if v is None:
+        with torch.no_grad():
+            v = SDEs.sample_v(x.shape, vtype=gen.vtype, device=gen.deviceReverseSDE)
+        if v is None:
+            raise ValueError(f"vtype {gen.vtype} not supported")
+    v = v.to(y)
+    params = [p for l in net.linears() for p in (l.weight, l.bias)]
+    return _SsmMlp.apply(gen, t_, y.detach(), v, *params)
+
+
+def ssm(gen, x):
+    t_, x, y = gen.sample_txy(x)
+    return ssm_loss(gen, t_, x, y)

@@ -135,6 +135,55 @@ def time_cpu_port(sde, mlp, B: int, n_steps: int, reps: int):
     return B * n_steps / best, best
 
 
+def time_cpu_train(sde, mlp, data, batch: int, iters: int):
+    """samples/s of the reference's train step on the CPU port: ssm -> mean -> backward -> Adam (MSGM_higherDim.py:803-809)."""
+    from oracle import msgm_oracle as O
+    params = [p.clone().requires_grad_(True) for p in mlp.parameters()]
+    net = O.OMlp(params[0::2], params[1::2], mlp.premodule, mlp.input_dim)
+    rev = O.OReverse(sde, net)
+    opt = torch.optim.Adam(params, lr=1e-3)
+    torch.manual_seed(2)
+    t0 = None
+    for it in range(iters + 1):
+        if it == 1:
+            t0 = time.perf_counter()
+        opt.zero_grad()
+        x = data[torch.randint(0, data.shape[0], (batch,))]
+        loss, _ = O.ssm(rev, x)
+        loss.mean().backward()
+        opt.step()
+    return batch * iters / (time.perf_counter() - t0)
+
+
+def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev):
+    """samples/s (all ranks) of gen.ssm(x).mean().backward(); [all-reduce]; Adam.step() on the fused SSM kernels."""
+    from sdeflow_light_b200 import dist as D
+    opt = torch.optim.Adam(gen.parameters(), lr=1e-3)
+    params = [p for p in gen.parameters() if p.requires_grad]
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        x = data_dev[torch.randint(0, data_dev.shape[0], (batch,), device=dev)]
+        loss = gen.ssm(x).mean()
+        loss.backward()
+        D.allreduce_grads_(params)
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    l0 = P._lib.launch_count(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    return world * batch * iters / (ms / 1e3), ms / iters, (P._lib.launch_count(dev) - l0) / iters, float(loss)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -254,6 +303,19 @@ def main():
     e2e_value = world * B * N * args.steps / (float(t_e2e.item()) / 1e3)
     assert torch.isfinite(out_host).all()
 
+    # ---- secondary metric of BASELINE.json: score-matching train samples/s (SSM is the reference's live loss) -----
+    from oracle import msgm_oracle as O
+    data_host = O.gaussian_mixture(100_000, args.dim, seed=0)
+    data_dev = data_host.to(dev)
+    gen.train()
+    train = {"metric": "ssm_train_samples_per_sec", "unit": "samples/s", "precision": "fp32",
+             "step": "gen.ssm(x).mean().backward(); flat-grad all-reduce (N>1); torch.optim.Adam.step()", "runs": []}
+    for batch in (256, 16384):
+        v_, ms_, launches_, loss_ = time_gpu_train(P, gen, data_dev, batch, 20, world, dev)
+        train["runs"].append({"batch_per_gpu": batch, "value": v_, "ms_per_iter": ms_, "gpu_launches_per_iter": launches_,
+                              "loss": loss_})
+    train["value"] = train["runs"][-1]["value"]
+
     if rank == 0:
         peaks = load_peaks()
         fl = flop_per_particle_step(args.dim, 1, True) * B * N  # per launch
@@ -273,7 +335,11 @@ def main():
                          "kernel": "sample_fp32_kernel" if args.precision == "fp32" else "sample_tc_kernel",
                          "flop_per_launch": fl, "kernel_ms": kms},
         }
+        line["train"] = train
         if not args.no_cpu_baseline:
+            train["cpu_baseline"] = {"value": time_cpu_train(sde, mlp, data_host, 256, 10), "unit": "samples/s",
+                                     "cores": torch.get_num_threads(), "kind": "port",
+                                     "sample": "batch 256, 10 iterations after 1 warm-up (oracle port, torch CPU fp32)"}
             v, t = time_cpu_port(sde, mlp, 50_000, 4, 3)
             line["cpu_baseline"] = {"value": v, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
                                     "kind": "port",

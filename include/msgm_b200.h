@@ -128,6 +128,20 @@ int msgm_ssm_mlp_backward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_ml
                           const float* v, const float* t, const float* grad_out, void* scratch, float* grad_flat,
                           int64_t B, void* stream);
 
+/* Per-stage SDE update for score nets that are not fused into the sampler (U-Nets, d up to 4096; SGM and sparse MSGM).
+ * One call per Runge-Kutta stage replaces EMstep + PluginReverseSDE.{mu_Strato,sigma} + the stage bookkeeping
+ * (sde_scheme.py:18-40,223-255; SDEs.py:556-588).  `a` is the score-net output at (stage input, s); x (B,d) is the state
+ * at the start of the step and receives the new state on the last stage (with the radius re-pinned to r0 when
+ * norm_correction); y (B,d) is a separate buffer holding the stage input of stages > 0; ks (B,d) the running RK sum. */
+int msgm_stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,
+                      int32_t norm_correction, int32_t forward_only, float s, float delta, const float* a,
+                      const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B, void* stream);
+/* r[b] = |x[b,:]|  (torch.norm(x_t, dim=1), sde_scheme.py:66,124,205). */
+int msgm_row_norm(msgm_ctx* ctx, const float* x, float* r, int32_t d, int64_t B, void* stream);
+/* out (B,d) = scale * N(0,1) with the samplers' Philox keying (seed, particle_offset + row, step). */
+int msgm_philox_normal(msgm_ctx* ctx, float* out, int32_t d, int64_t B, float scale, uint64_t seed,
+                       uint64_t particle_offset, uint32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

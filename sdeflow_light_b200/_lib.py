@@ -44,7 +44,8 @@ _ctx = {}
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
            "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
-           "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward"]
+           "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward",
+           "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal"]
 
 
 def lib() -> C.CDLL:
@@ -69,6 +70,11 @@ def lib() -> C.CDLL:
                     [C.c_int64, C.c_void_p]
                 L.msgm_ssm_mlp_backward.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc)] + [C.c_void_p] * 6 + \
                     [C.c_int64, C.c_void_p]
+                L.msgm_stage_update.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                                C.c_int32, C.c_float, C.c_float] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
+                L.msgm_row_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+                L.msgm_philox_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64,
+                                                 C.c_uint64, C.c_uint32, C.c_void_p]
                 L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]

@@ -25,6 +25,11 @@ int ssm_forward(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const flo
 int ssm_backward(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const float*, const float*, const float*,
                  const float*, float*, float*, int64_t, cudaStream_t);
 
+int stage_update(msgm_ctx*, const msgm_sde_desc*, int, int, float, int, int, float, float, const float*, const float*,
+                 const float*, float*, float*, float*, int64_t, cudaStream_t);
+int row_norm(msgm_ctx*, const float*, float*, int, int64_t, cudaStream_t);
+int philox_normal(msgm_ctx*, float*, int, int64_t, float, uint64_t, uint64_t, uint32_t, cudaStream_t);
+
 static int invalid(const char* msg) {
   set_error(msg);
   return MSGM_ERR_INVALID;
@@ -176,6 +181,44 @@ int msgm_ssm_mlp_backward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_ml
   if (!y || !v || !t || !grad_out || !scratch) return invalid("msgm_ssm_mlp_backward: NULL buffer");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return ssm_backward(ctx, sde, mlp, y, v, t, grad_out, (float*)scratch, grad_flat, B, (cudaStream_t)stream);
+}
+
+int msgm_stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,
+                      int32_t norm_correction, int32_t forward_only, float s, float delta, const float* a,
+                      const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B, void* stream) {
+  if (!ctx || !sde || !dW || !x || !y || !ks) return invalid("msgm_stage_update: NULL argument");
+  if (!forward_only && !a) return invalid("msgm_stage_update: score-net output missing");
+  if (norm_correction && !r0) return invalid("msgm_stage_update: r0 missing");
+  if (sde->kind != MSGM_SDE_SGM && sde->kind != MSGM_SDE_MSGM_SPARSE) {
+    set_error("msgm_stage_update: built for SGM and sparse MSGM (dense G with d > 32 is O(d^3) per particle)");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (sde->dim < 1 || sde->dim > 4096) {
+    set_error("msgm_stage_update: d must be in [1,4096]");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (scheme < MSGM_SCHEME_EM || scheme > MSGM_SCHEME_RK4) return invalid("unknown scheme");
+  const int nstage = scheme == MSGM_SCHEME_RK4 ? 4 : (scheme == MSGM_SCHEME_HEUN ? 2 : 1);
+  if (stage < 0 || stage >= nstage) return invalid("stage out of range");
+  if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return stage_update(ctx, sde, scheme, stage, lmbd, norm_correction, forward_only, s, delta, a, dW, r0, x, y, ks, B,
+                      (cudaStream_t)stream);
+}
+
+int msgm_row_norm(msgm_ctx* ctx, const float* x, float* r, int32_t d, int64_t B, void* stream) {
+  if (!ctx || !x || !r || d < 1) return invalid("msgm_row_norm: bad argument");
+  if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return row_norm(ctx, x, r, d, B, (cudaStream_t)stream);
+}
+
+int msgm_philox_normal(msgm_ctx* ctx, float* out, int32_t d, int64_t B, float scale, uint64_t seed,
+                       uint64_t particle_offset, uint32_t step, void* stream) {
+  if (!ctx || !out || d < 1) return invalid("msgm_philox_normal: bad argument");
+  if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return philox_normal(ctx, out, d, B, scale, seed, particle_offset, step, (cudaStream_t)stream);
 }
 
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {

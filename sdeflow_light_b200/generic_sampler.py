@@ -1,0 +1,85 @@
+"""Sampler loop for score nets that are not fused into the persistent kernels (U-Nets, d up to 4096).
+
+The net is called once per Runge-Kutta stage (4 per RK4 step, sde_scheme.py:230-250); everything else of the step --
+the reference's three g() evaluations, two f() evaluations, gather/scatter_add with atomics, the RK bookkeeping and
+the radius re-pin (sde_scheme.py:18-40,223-255; SDEs.py:556-588) -- is ONE hand-written kernel per stage
+(msgm_stage_update), plus in-kernel Philox noise and a row-norm kernel.  State, noise and trajectory stay on the GPU;
+there is one device->host copy at the end instead of one per step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_NSTAGE = {_lib.SCHEME_EM: 1, _lib.SCHEME_HEUN: 2, _lib.SCHEME_RK4: 4}
+
+
+def run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, include_t0, T_run, norm_correction, noise,
+        seed, particle_offset, device_out):
+    from .sde_scheme import _describe
+    base, net, fwd = _describe(sde)
+    device = sde.T.device
+    handle, L = _lib.ctx(device), _lib.lib()
+    stream = _lib.stream_ptr(device)
+    B, d = x_0.size(0), x_0.size(1)
+    sd, keep_alive = base.desc(device)
+    if sd.kind == _lib.SDE_MSGM_DENSE:
+        raise NotImplementedError("dense G with a non-fused score net is not built (O(d^3) per particle); "
+                                  "use denseTensor=False as the reference does for d >= 256")
+    sd.dim = d
+    x = _lib.f32c(x_0, device).clone()
+    y, ks, dW = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    r0 = None
+    if norm_correction:
+        r0 = torch.empty(B, device=device, dtype=torch.float32)
+        _lib.check(L.msgm_row_norm(handle, _lib.ptr(x), _lib.ptr(r0), d, B, stream))
+    # time grid and step sizes exactly as the reference rounds them (sde_scheme.py:200-201,224,236,248)
+    delta = T_run / num_steps
+    ts = (torch.linspace(0, 1, num_steps + 1) * T_run).numpy().astype(np.float32)
+    f32 = np.float32
+    T_sde = f32(sde.T.item())
+    nstage = _NSTAGE[scheme]
+    if noise is not None:
+        noise = _lib.f32c(noise, device)
+        if tuple(noise.shape) != (num_steps, B, d):
+            raise ValueError(f"noise must have shape {(num_steps, B, d)}")
+    elif seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    traj = keep_out = keep_step = None
+    if keep_all_samples:
+        traj = torch.empty((num_steps + (1 if include_t0 else 0), B, d), device=device, dtype=torch.float32)
+        if include_t0:
+            traj[0].copy_(x)
+    elif samplesToKeep is not None:
+        keep_step = torch.as_tensor(samplesToKeep).reshape(-1).to(device)
+        keep_out = torch.zeros((B, d), device=device, dtype=torch.float32)
+    s_vec = torch.empty(B, device=device, dtype=torch.float32)
+    for i in range(num_steps):
+        if noise is not None:
+            torch.mul(noise[i], float(f32(delta ** 0.5)), out=dW)
+        else:
+            _lib.check(L.msgm_philox_normal(handle, _lib.ptr(dW), d, B, float(f32(delta ** 0.5)), int(seed),
+                                            int(particle_offset), i, stream))
+        for st in range(nstage):
+            t_s = ts[i]
+            if st > 0:
+                t_s = f32(t_s + f32(delta / 2)) if (nstage == 4 and st < 3) else f32(t_s + f32(delta))
+            s = float(t_s) if fwd else float(f32(T_sde - t_s))
+            a = None
+            if not fwd:
+                s_vec.fill_(s)
+                a = _lib.f32c(net(x if st == 0 else y, s_vec), device).reshape(B, d)
+            _lib.check(L.msgm_stage_update(handle, C.byref(sd), scheme, st, float(lmbd), int(bool(norm_correction)),
+                                           int(fwd), s, float(f32(delta)), _lib.ptr(a), _lib.ptr(dW), _lib.ptr(r0),
+                                           _lib.ptr(x), _lib.ptr(y), _lib.ptr(ks), B, stream))
+        if traj is not None:
+            traj[i + (1 if include_t0 else 0)].copy_(x)
+        elif keep_step is not None:
+            m = keep_step == (i + (1 if include_t0 else 0))
+            keep_out[m] = x[m]
+    out = traj if keep_all_samples else (keep_out if samplesToKeep is not None else x)
+    return out if device_out else out.to("cpu")

@@ -58,7 +58,7 @@ def _run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, inc
     T_run = sde.T.item() if (not torch.is_tensor(T_) and T_ == -1) else T_.item()
     if keep_all_samples is False and samplesToKeep is not None and len(samplesToKeep) != B:
         raise ValueError("Error: len(samplesToKeep) must correspond to batch size.")
-    if not fwd and not (isinstance(net, NN.MLP) and net.fused_ok()):
+    if (fwd and d > 32) or (not fwd and not (isinstance(net, NN.MLP) and net.fused_ok())):
         from . import generic_sampler
         return generic_sampler.run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, include_t0,
                                    T_run, norm_correction, noise, seed, particle_offset, device_out)
@@ -112,6 +112,12 @@ def _run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, inc
 def _run_rows(sde, y0, t_rows, noise=None, seed=None):
     """One RK4 step of size t_rows[k] for every row k: the batched form of the reference's per-row calls
     ``rk4_stratonovich_sampler(forward_SDE, y0[k][None], 1, T_=t[k])`` (SDEs.py:114-116).  Returns a device tensor."""
+    if y0.shape[1] > 32:  # stage-kernel path takes one horizon per launch: few rows, one launch group each
+        out = torch.empty_like(y0)
+        for k in range(y0.shape[0]):
+            out[k:k + 1] = _run(_lib.SCHEME_RK4, sde, y0[k:k + 1], 1, 0., False, None, False, t_rows[k:k + 1], False,
+                                None if noise is None else noise[:, k:k + 1], "fp32", seed, k, True)
+        return out
     return _run(_lib.SCHEME_RK4, sde, y0, 1, 0., False, None, False, -1, False, noise, "fp32", seed, 0, True,
                 T_rows=t_rows)
 

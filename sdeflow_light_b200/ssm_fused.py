@@ -56,18 +56,40 @@ class _SsmMlp(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+def _ssm_loss_autograd(gen, t_, y, v):
+    """SSM loss for score nets without a fused kernel (U-Nets): the reference's recipe (SDEs.py:616-646) -- a VJP through
+    the net with create_graph -- on GPU tensors, with the drift written in its cancelled form mu_to_div = g.a (+ beta y/2
+    for SGM) and the net evaluated once instead of twice.  Library autograd, not a hand-written kernel."""
+    base = gen.base_sde
+    if not y.is_cuda:
+        raise RuntimeError("sdeflow_light_b200 runs on CUDA only (no CPU fallback)")
+    with torch.enable_grad():
+        y = y.detach().requires_grad_()
+        a = gen.a(y, t_.squeeze())
+        g = base.g(t_, y, base.sparseTensor)
+        if base.sparseTensor:
+            I, _, K = base.IJK()
+            mu = torch.zeros_like(y).scatter_add(1, I.unsqueeze(0).expand(y.shape[0], -1), g * a[:, K])
+        elif g.dim() > 2:
+            mu = torch.einsum('bij, bj -> bi', g, a)
+        else:
+            mu = g * a + 0.5 * base.beta(t_) * y
+        jv = torch.autograd.grad(mu, y, v, create_graph=gen.training)[0]
+        return (jv * v).reshape(y.size(0), -1).sum(1) + (a ** 2).reshape(y.size(0), -1).sum(1) / 2
+
+
 def ssm_loss(gen, t_, x, y, v=None):
     """Per-sample SSM loss for given (t, y); ``v`` defaults to a fresh probe like the reference (SDEs.py:637-638)."""
     from . import NN, SDEs
     net = gen.a
-    if not (isinstance(net, NN.MLP) and net.fused_ok()):
-        raise NotImplementedError("fused SSM is built for the MLP score net (NN.MLP, hidden 128, d <= 32)")
     if v is None:
         with torch.no_grad():
             v = SDEs.sample_v(x.shape, vtype=gen.vtype, device=gen.deviceReverseSDE)
         if v is None:
             raise ValueError(f"vtype {gen.vtype} not supported")
     v = v.to(y)
+    if not (isinstance(net, NN.MLP) and net.fused_ok()):
+        return _ssm_loss_autograd(gen, t_.to(y), y, v)
     params = [p for l in net.linears() for p in (l.weight, l.bias)]
     return _SsmMlp.apply(gen, t_, y.detach(), v, *params)
 

@@ -141,8 +141,53 @@ def misc_case(ref):
           x0=x0.numpy(), mmd_a=a.numpy(), mmd_b=b.numpy(), mmd=np.float32(mmd))
 
 
+def unet1d_case(ref, name, kind, L, B, N, seed, pre="NormalizeLogRadius"):
+    """UNet1D score net (NNUnet1D.py) on 1-D signals of length L: forward, RK4 reverse sampling, SSM loss + gradients."""
+    torch.manual_seed(seed)
+    sig = torch.sin(torch.linspace(0, 6.28, L)[None] * torch.randint(1, 4, (256, 1)) + 6.28 * torch.rand(256, 1)) \
+        + 0.1 * torch.randn(256, L)
+    net = ref.NNUnet1D.UNet1D(input_dim=L, base_channels=8, channel_mults=(1, 2, 4), num_res_blocks=2,
+                              premodule=pre, emb_dim=16)
+    with torch.no_grad():
+        net.final.weight.mul_(4.0)
+    base, gen, _ = ref_live.build(ref, kind, L, sig, pre, net=net)
+    x0 = sig[:B].clone() + 0.3 * torch.randn(B, L)
+    s = torch.rand(B)
+    with torch.no_grad():
+        fwd = net(x0, s)
+    torch.manual_seed(seed + 1)
+    xs = ref.sde_scheme.rk4_stratonovich_sampler(gen, x0, N, lmbd=0., keep_all_samples=True, include_t0=True,
+                                                 norm_correction=(kind != "sgm"))
+    torch.manual_seed(seed + 1)
+    noise = torch.stack([torch.randn_like(x0) for _ in range(N)])
+    # SSM loss and gradients for given (t, y, v)
+    t_ = torch.rand(B, 1).clamp_min(1e-3)
+    y = (x0 + 0.2 * torch.randn(B, L)).requires_grad_()
+    state = torch.get_rng_state()
+    v = ref.SDEs.sample_rademacher(x0.shape, "cpu")
+    torch.set_rng_state(state)
+    gen.train()
+    loss = gen.ssm_loss(t_, x0, y)
+    gen.zero_grad()
+    loss.mean().backward()
+    arrays = dict(x0=x0.numpy(), s=s.numpy(), fwd=fwd.numpy(), noise=noise.numpy(), out=xs.numpy(), t=t_.numpy(),
+                  y=y.detach().numpy(), v=v.numpy(), loss=loss.detach().numpy(), **_sde_arrays(base))
+    for k, p_ in net.state_dict().items():
+        arrays["sd." + k] = p_.numpy().copy()
+    for k, p_ in net.named_parameters():
+        arrays["grad." + k] = p_.grad.numpy().copy()
+    meta = dict(kind=kind, dim=L, premodule=pre is not None, scheme="rk4", num_steps=N, lmbd=0.0,
+                norm_correction=(kind != "sgm"), include_t0=True, beta_min=0.1, beta_max=20.0, T=1.0,
+                base_channels=8, emb_dim=16)
+    _save(name, meta, **arrays)
+
+
 def main():
     ref = ref_live.load()
+    if "--unet-only" in sys.argv:
+        unet1d_case(ref, "u01_unet1d_sparse_L64", "msgm_sparse", 64, 6, 4, 41)
+        unet1d_case(ref, "u02_unet1d_sgm_L48", "sgm", 48, 5, 3, 42, pre=None)
+        return
     P = "NormalizeLogRadius"
     sampler_case(ref, "s01_msgm_d2_rk4", "msgm_dense", 2, P, "rk4", 16, 64, 0.0, True, 1)
     sampler_case(ref, "s02_sgm_d2_rk4", "sgm", 2, None, "rk4", 16, 64, 0.0, False, 2)
@@ -163,6 +208,8 @@ def main():
     ssm_case(ref, "t03_ssm_sparse_d8", "msgm_sparse", 8, P, 24, 23)
     ssm_case(ref, "t04_ssm_msgm_d16", "msgm_dense", 16, P, 16, 24)
     misc_case(ref)
+    unet1d_case(ref, "u01_unet1d_sparse_L64", "msgm_sparse", 64, 6, 4, 41)
+    unet1d_case(ref, "u02_unet1d_sgm_L48", "sgm", 48, 5, 3, 42, pre=None)
 
 
 if __name__ == "__main__":

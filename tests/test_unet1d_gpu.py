@@ -1,0 +1,86 @@
+"""GPU parity of the 1-D U-Net score path (BASELINE config 3) against golden fixtures of the reference: the UNet1D
+forward, RK4 reverse sampling with the sparse multiplicative SDE through the hand-written per-stage update kernels, and
+the SSM loss + gradients.  fp32 tolerances: 2e-4 + 2e-4 max|ref| (cuDNN convolutions vs the reference's CPU convolutions).
+"""
+import pytest
+import torch
+
+import sdeflow_light_b200 as P
+from oracle import msgm_oracle as O
+from tests import _build as Bd
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _unet_gen(meta, arr):
+    base, T = Bd.base_from(meta, arr, DEV)
+    base.dim = meta["dim"]
+    net = P.UNet1D(input_dim=meta["dim"], base_channels=meta["base_channels"], channel_mults=(1, 2, 4), num_res_blocks=2,
+                   premodule="NormalizeLogRadius" if meta["premodule"] else None, emb_dim=meta["emb_dim"])
+    sd = {k[3:]: v for k, v in arr.items() if k.startswith("sd.")}
+    assert sorted(sd) == sorted(net.state_dict().keys())  # same parameter names as the reference module
+    net.load_state_dict(sd)
+    gen = P.PluginReverseSDE(base, net.to(DEV), T, deviceReverseSDE=DEV).to(DEV)
+    return base, net, gen
+
+
+def _rel(a, b):
+    return float((a.cpu() - b).abs().max()) / max(1e-12, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("name", G.names("u"))
+def test_unet1d_forward_sampler_ssm(name):
+    meta, arr = G.load(name)
+    base, net, gen = _unet_gen(meta, arr)
+    with torch.no_grad():
+        fwd = net(arr["x0"].to(DEV), arr["s"].to(DEV))
+    e_f = _rel(fwd, arr["fwd"])
+    out = P.rk4_stratonovich_sampler(gen, arr["x0"].to(DEV), meta["num_steps"], lmbd=0., keep_all_samples=True,
+                                     include_t0=True, norm_correction=meta["norm_correction"], noise=arr["noise"])
+    e_s = _rel(out, arr["out"])
+    gen.train()
+    gen.zero_grad()
+    loss = gen.ssm_loss(arr["t"].to(DEV), arr["x0"].to(DEV), arr["y"].to(DEV), arr["v"].to(DEV))
+    e_l = _rel(loss.detach(), arr["loss"])
+    loss.mean().backward()
+    e_g = max(_rel(p.grad, arr["grad." + k]) for k, p in net.named_parameters())
+    Bd.report(test=name, fwd_rel=e_f, sampler_rel=e_s, loss_rel=e_l, grad_rel=e_g)
+    assert e_f < 2e-4 and e_s < 2e-4 and e_l < 2e-4 and e_g < 1e-3
+
+
+@pytest.mark.parametrize("kind,d,scheme,lmbd,nc", [("msgm_sparse", 1000, "rk4", 0.0, True), ("msgm_sparse", 257, "heun", 0.3, True),
+                                                   ("sgm", 1024, "em", 0.5, False), ("msgm_sparse", 40, "em", 0.5, False)])
+def test_stage_kernels_against_oracle(kind, d, scheme, lmbd, nc):
+    """The per-stage update kernels alone (forward adapter: no net), at U-Net sizes, all schemes."""
+    torch.manual_seed(7)
+    sde = O.make_sgm(d) if kind == "sgm" else O.make_msgm(torch.randn(32, d), dense=False)
+    x0, noise = torch.randn(9, d), torch.randn(6, 9, d)
+    ref = O.integrate(O.OForward(sde), x0, 6, scheme, lmbd, True, None, True, None, nc, noise=noise)
+    _, _, fwd = Bd.from_oracle(sde, None, DEV)
+    out = Bd.SAMPLERS[scheme](fwd, x0.to(DEV), 6, lmbd=lmbd, keep_all_samples=True, include_t0=True, norm_correction=nc,
+                              noise=noise)
+    err = _rel(out, ref)
+    Bd.report(test=f"stage-{kind}-d{d}-{scheme}", rel=err)
+    assert err < 2e-5
+
+
+def test_unet1d_full_size_runs_and_keeps_radius():
+    """Config-3 size: L = 1000, UNet1D(base 32, emb 128), sparse MSGM, Philox noise; radius is pinned per particle."""
+    torch.manual_seed(0)
+    L, B = 1000, 64
+    sig = torch.sin(torch.linspace(0, 6.28, L)[None] * torch.randint(1, 4, (B, 1))) + 0.1 * torch.randn(B, L)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(sig, T=T, denseTensor=False, norm_map="log", num_steps_forward=16, device=DEV,
+                     estim_cst_norm_dens_r_T=False)
+    net = P.UNet1D(L, premodule="NormalizeLogRadius").to(DEV)
+    gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
+    x0 = gen.latent_sample(B, L)
+    out = P.rk4_stratonovich_sampler(gen, x0, 4, keep_all_samples=False, norm_correction=True, seed=3, device_out=True)
+    assert torch.isfinite(out).all()
+    assert float(((out.norm(dim=1) - x0.norm(dim=1)).abs() / x0.norm(dim=1)).max()) < 1e-5
+    gen.train()
+    loss = gen.ssm(sig.to(DEV)[:8]).mean()
+    loss.backward()
+    assert torch.isfinite(loss) and all(torch.isfinite(p.grad).all() for p in net.parameters())

@@ -60,6 +60,11 @@ class UNet1D(nn.Module):
     def forward(self, x, t):
         if not x.is_cuda:
             raise RuntimeError("sdeflow_light_b200.NNUnet1D.UNet1D runs on CUDA only (no CPU fallback)")
+        # the reference is fp32 end to end: keep cuDNN from silently using TF32 for the convolutions
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return self._forward(x, t)
+
+    def _forward(self, x, t):
         h = x.unsqueeze(1) if x.ndim == 2 else x
         emb = self.time_mlp(t.view(-1, 1))
         if self.premodule is not None:

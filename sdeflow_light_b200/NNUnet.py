@@ -1,0 +1,91 @@
+"""2-D U-Net score net on flattened square images: drop-in for the reference's NNUnet.py (VorticityUNet,
+UNetModelWithLogNorm, flat_to_img / img_to_flat; reference NNUnet.py:19-77,80-142,145-245).
+
+Conventions kept from the reference: inputs are divided by 5 on the way in and outputs multiplied by 5 on the way out;
+(B, H*W) vectors are reshaped in C or Fortran order; with premodule="NormalizeLogRadius" the image is x/(|x|+eps)*sqrt(d)
+and the embedding is time_embed(sin-emb(t)) + scale_embed(sin-emb(log(|x|+eps))).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .model.unet import SiLU, UNetModel, timestep_embedding
+from .NN import NormalizeLogRadius, evaluate  # noqa: F401
+
+scale_image = 5
+
+
+def flat_to_img(x, H, W, order="C"):
+    B, d = x.shape
+    assert d == H * W, f"Expected d={H*W}, got {d}"
+    x = x / scale_image
+    return x.view(B, 1, H, W) if order == "C" else x.view(B, 1, W, H).transpose(2, 3).contiguous()
+
+
+def img_to_flat(y, order="C"):
+    B, C, H, W = y.shape
+    assert C == 1, f"Expected 1 channel, got {C}"
+    y = scale_image * y
+    return y.reshape(B, H * W) if order == "C" else y.transpose(2, 3).contiguous().view(B, H * W)
+
+
+class UNetModelWithLogNorm(UNetModel):
+    def __init__(self, *args, use_log_norm: bool = False, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.use_log_norm = use_log_norm
+        if use_log_norm:
+            ted = self.model_channels * 4
+            self.scale_embed = nn.Sequential(nn.Linear(self.model_channels, ted), SiLU(), nn.Linear(ted, ted))
+
+    def forward(self, x, timesteps, y=None, log_norm: Optional[torch.Tensor] = None):
+        emb = self.embedding(timesteps)
+        if self.use_log_norm:
+            assert log_norm is not None, "log_norm must be provided when use_log_norm=True"
+            emb = emb + self.scale_embed(timestep_embedding(log_norm.view(-1), self.model_channels))
+        return self.run_blocks(x, emb)
+
+
+class VorticityUNet(nn.Module):
+    def __init__(self, base_channels: int = 32, channel_mults=(1, 2, 4), num_res_blocks: int = 2,
+                 emb_dim_ignored: int = 128, dropout: float = 0.0, premodule: Optional[str] = None, in_space: int = 16,
+                 attention_resolutions=(2, 4), conv_resample: bool = True, num_heads: int = 1,
+                 use_checkpoint: bool = False, learn_potential: bool = False, flatten_order="C"):
+        super().__init__()
+        assert premodule in (None, "NormalizeLogRadius") and flatten_order in ("C", "F")
+        self.pre = NormalizeLogRadius() if premodule == "NormalizeLogRadius" else None
+        self.in_space, self.flatten_order = int(in_space), flatten_order
+        self.core = UNetModelWithLogNorm(
+            in_channels=1, model_channels=base_channels, out_channels=1, in_space=int(in_space),
+            num_res_blocks=num_res_blocks, attention_resolutions=attention_resolutions, dropout=dropout,
+            channel_mult=tuple(channel_mults), conv_resample=conv_resample, dims=2, num_classes=None,
+            use_checkpoint=False, num_heads=num_heads, use_scale_shift_norm=False, learn_potential=learn_potential,
+            use_log_norm=(premodule == "NormalizeLogRadius"))
+
+    def forward(self, x, t):
+        if not x.is_cuda:
+            raise RuntimeError("sdeflow_light_b200.NNUnet.VorticityUNet runs on CUDA only (no CPU fallback)")
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):  # the reference is fp32 end to end
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                return self._forward(x, t.view(-1))
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+
+    def _forward(self, x, t):
+        log_norm = None
+        if self.pre is not None:
+            x, log_norm = self.pre(x)
+            x = x * torch.sqrt(torch.tensor(x.shape[-1], dtype=log_norm.dtype, device=log_norm.device))
+        flat = x.dim() == 2
+        if flat:
+            img = flat_to_img(x, self.in_space, self.in_space, order=self.flatten_order)
+        elif x.dim() == 4 and x.size(1) == 1:
+            img = x
+        else:
+            raise ValueError(f"Unexpected input shape {tuple(x.shape)}")
+        out = self.core(img, timesteps=t, log_norm=log_norm) if self.pre is not None else self.core(img, timesteps=t)
+        return img_to_flat(out, order=self.flatten_order) if flat else out

@@ -1,0 +1,193 @@
+"""Guided-diffusion style 2-D U-Net: drop-in for the reference's model/unet.py + model/nn_utils.py, restricted to what the
+driver configures (MSGM_higherDim.py:703-716 via NNUnet.VorticityUNet: dims=2, no class conditioning, no gradient
+checkpointing, no scale-shift norm, no potential parameterisation).  Module / parameter names are identical to the
+reference so that its checkpoints load: ``input_blocks.i.j.*``, ``middle_block.*``, ``output_blocks.i.j.*``, ``out.*``,
+``time_embed.*``; ResBlock = ``in_layers(GN,SiLU,conv3x3) + emb_layers(SiLU,Linear) -> out_layers(GN,SiLU,Dropout,
+zero conv3x3)`` with identity / 1x1 skip; AttentionBlock = GN -> 1x1 qkv -> single-head softmax(q k / sqrt(C)) v -> zero
+1x1 proj (+ residual); Up/Downsample = nearest x2 + conv3x3 / stride-2 conv3x3.
+
+Round-1 status: convolutions / GroupNorm / attention matmuls run through torch's GPU library calls (fp32, TF32 off);
+hand-written kernels for these layers are the next step.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class SiLU(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(x)
+
+
+class GroupNorm32(nn.GroupNorm):
+    """GroupNorm evaluated in fp32 (reference model/nn_utils.py:39-41)."""
+
+    def forward(self, x):
+        return super().forward(x.float()).type(x.dtype)
+
+
+def normalization(channels):
+    return GroupNorm32(min(channels, 32), channels)
+
+
+def zero_module(m):
+    for p in m.parameters():
+        p.detach().zero_()
+    return m
+
+
+def timestep_embedding(timesteps, dim, max_period=10000):
+    """[cos(t w_k), sin(t w_k)], w_k = max_period^(-k/half) (reference model/nn_utils.py:130-148)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
+    ang = timesteps[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
+    return torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1) if dim % 2 else emb
+
+
+class TimestepBlock(nn.Module):
+    """Marker: forward(x, emb)."""
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    def forward(self, x, emb):
+        for layer in self:
+            x = layer(x, emb) if isinstance(layer, TimestepBlock) else layer(x)
+        return x
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, odd_size=False):
+        super().__init__()
+        self.channels, self.use_conv, self.dims, self.odd_size = channels, use_conv, dims, odd_size
+        if use_conv:
+            self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+
+    def forward(self, x):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        if self.use_conv:
+            x = self.conv(x)
+        return x[..., :-1, :-1] if self.odd_size else x
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2):
+        super().__init__()
+        self.channels = channels
+        self.op = nn.Conv2d(channels, channels, 3, stride=2, padding=1) if use_conv else nn.AvgPool2d(2)
+
+    def forward(self, x):
+        return self.op(x)
+
+
+class ResBlock(TimestepBlock):
+    def __init__(self, channels, emb_channels, dropout, out_channels=None):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels or channels
+        co = self.out_channels
+        self.in_layers = nn.Sequential(normalization(channels), SiLU(), nn.Conv2d(channels, co, 3, padding=1))
+        self.emb_layers = nn.Sequential(SiLU(), nn.Linear(emb_channels, co))
+        self.out_layers = nn.Sequential(normalization(co), SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(nn.Conv2d(co, co, 3, padding=1)))
+        self.skip_connection = nn.Identity() if co == channels else nn.Conv2d(channels, co, 1)
+
+    def forward(self, x, emb):
+        h = self.in_layers(x) + self.emb_layers(emb)[:, :, None, None]
+        return self.skip_connection(x) + self.out_layers(h)
+
+
+class QKVAttention(nn.Module):
+    def forward(self, qkv):
+        ch = qkv.shape[1] // 3
+        q, k, v = torch.split(qkv, ch, dim=1)
+        scale = 1 / math.sqrt(math.sqrt(ch))
+        w = torch.softmax(torch.einsum("bct,bcs->bts", q * scale, k * scale).float(), dim=-1).type(qkv.dtype)
+        return torch.einsum("bts,bcs->bct", w, v)
+
+
+class AttentionBlock(nn.Module):
+    def __init__(self, channels, num_heads=1):
+        super().__init__()
+        self.channels, self.num_heads = channels, num_heads
+        self.norm = normalization(channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.attention = QKVAttention()
+        self.proj_out = zero_module(nn.Conv1d(channels, channels, 1))
+
+    def forward(self, x):
+        b, c, *spatial = x.shape
+        x = x.reshape(b, c, -1)
+        qkv = self.qkv(self.norm(x))
+        h = self.attention(qkv.reshape(b * self.num_heads, -1, qkv.shape[2])).reshape(b, -1, qkv.shape[2])
+        return (x + self.proj_out(h)).reshape(b, c, *spatial)
+
+
+class UNetModel(nn.Module):
+    def __init__(self, in_channels, model_channels, out_channels, in_space, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
+                 num_heads=1, num_heads_upsample=-1, use_scale_shift_norm=False, learn_potential=False):
+        super().__init__()
+        if dims != 2 or num_classes is not None or use_scale_shift_norm or learn_potential:
+            raise NotImplementedError("only the configuration the reference driver uses is built "
+                                      "(dims=2, unconditional, additive embedding, score output)")
+        heads_up = num_heads if num_heads_upsample == -1 else num_heads_upsample
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions = num_res_blocks, attention_resolutions
+        self.dropout, self.channel_mult, self.conv_resample = dropout, channel_mult, conv_resample
+        self.num_classes, self.use_checkpoint, self.num_heads = None, False, num_heads
+        self.num_heads_upsample, self.learn_potential = heads_up, False
+        ted = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), SiLU(), nn.Linear(ted, ted))
+        sizes = [in_space]
+        for _ in channel_mult:
+            sizes.append(sizes[-1] // 2)
+        ch = model_channels * channel_mult[0]
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, ch, 3, padding=1))])
+        skip_chans, ds = [ch], 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [ResBlock(ch, ted, dropout, out_channels=mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    layers.append(AttentionBlock(ch, num_heads=num_heads))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                skip_chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample)))
+                skip_chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(ResBlock(ch, ted, dropout), AttentionBlock(ch, num_heads=num_heads),
+                                                    ResBlock(ch, ted, dropout))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [ResBlock(ch + skip_chans.pop(), ted, dropout, out_channels=model_channels * mult)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers.append(AttentionBlock(ch, num_heads=heads_up))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, odd_size=sizes[level] % 2))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(normalization(ch), SiLU(),
+                                 zero_module(nn.Conv2d(model_channels * channel_mult[0], out_channels, 3, padding=1)))
+
+    def embedding(self, timesteps):
+        return self.time_embed(timestep_embedding(timesteps, self.model_channels))
+
+    def run_blocks(self, x, emb):
+        skips, h = [], x
+        for blk in self.input_blocks:
+            h = blk(h, emb)
+            skips.append(h)
+        h = self.middle_block(h, emb)
+        for blk in self.output_blocks:
+            h = blk(torch.cat([h, skips.pop()], dim=1), emb)
+        return self.out(h)
+
+    def forward(self, x, timesteps, y=None):
+        return self.run_blocks(x, self.embedding(timesteps))

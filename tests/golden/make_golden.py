@@ -182,8 +182,53 @@ def unet1d_case(ref, name, kind, L, B, N, seed, pre="NormalizeLogRadius"):
     _save(name, meta, **arrays)
 
 
+def unet2d_case(ref, name, S, B, N, seed, pre="NormalizeLogRadius", order="F"):
+    """VorticityUNet (NNUnet.py + model/unet.py) on flattened SxS images with the sparse multiplicative SDE."""
+    torch.manual_seed(seed)
+    L = S * S
+    img = torch.nn.functional.avg_pool2d(torch.randn(128, 1, S + 4, S + 4), 5, stride=1).reshape(128, L) * 4.0
+    net = ref.NNUnet.VorticityUNet(base_channels=8, channel_mults=(1, 2, 4), num_res_blocks=1, premodule=pre,
+                                   in_space=S, attention_resolutions=(2, 4), flatten_order=order)
+    with torch.no_grad():  # the reference zero-initialises these; randomise them so that every path is exercised
+        for k, p_ in net.named_parameters():
+            if p_.abs().sum() == 0 and p_.dim() > 1:
+                p_.copy_(torch.randn_like(p_) * (0.5 / p_[0].numel() ** 0.5))
+    base, gen, _ = ref_live.build(ref, "msgm_sparse", L, img, pre, net=net)
+    x0 = img[:B].clone() + 0.2 * torch.randn(B, L)
+    s = torch.rand(B)
+    with torch.no_grad():
+        fwd = net(x0, s)
+    torch.manual_seed(seed + 1)
+    xs = ref.sde_scheme.rk4_stratonovich_sampler(gen, x0, N, lmbd=0., keep_all_samples=True, include_t0=True,
+                                                 norm_correction=True)
+    torch.manual_seed(seed + 1)
+    noise = torch.stack([torch.randn_like(x0) for _ in range(N)])
+    t_ = torch.rand(B, 1).clamp_min(1e-3)
+    y = (x0 + 0.2 * torch.randn(B, L)).requires_grad_()
+    state = torch.get_rng_state()
+    v = ref.SDEs.sample_rademacher(x0.shape, "cpu")
+    torch.set_rng_state(state)
+    gen.train()
+    loss = gen.ssm_loss(t_, x0, y)
+    gen.zero_grad()
+    loss.mean().backward()
+    arrays = dict(x0=x0.numpy(), s=s.numpy(), fwd=fwd.numpy(), noise=noise.numpy(), out=xs.numpy(), t=t_.numpy(),
+                  y=y.detach().numpy(), v=v.numpy(), loss=loss.detach().numpy(), **_sde_arrays(base))
+    for k, p_ in net.state_dict().items():
+        arrays["sd." + k] = p_.numpy().copy()
+    for k, p_ in net.named_parameters():
+        arrays["grad." + k] = p_.grad.numpy().copy()
+    meta = dict(kind="msgm_sparse", dim=L, in_space=S, premodule=pre is not None, scheme="rk4", num_steps=N, lmbd=0.0,
+                norm_correction=True, include_t0=True, beta_min=0.1, beta_max=20.0, T=1.0, base_channels=8,
+                num_res_blocks=1, flatten_order=order)
+    _save(name, meta, **arrays)
+
+
 def main():
     ref = ref_live.load()
+    if "--unet2d-only" in sys.argv:
+        unet2d_case(ref, "w01_unet2d_sparse_16x16", 16, 4, 2, 51)
+        return
     if "--unet-only" in sys.argv:
         unet1d_case(ref, "u01_unet1d_sparse_L64", "msgm_sparse", 64, 6, 4, 41)
         unet1d_case(ref, "u02_unet1d_sgm_L48", "sgm", 48, 5, 3, 42, pre=None)
@@ -210,6 +255,7 @@ def main():
     misc_case(ref)
     unet1d_case(ref, "u01_unet1d_sparse_L64", "msgm_sparse", 64, 6, 4, 41)
     unet1d_case(ref, "u02_unet1d_sgm_L48", "sgm", 48, 5, 3, 42, pre=None)
+    unet2d_case(ref, "w01_unet2d_sparse_16x16", 16, 4, 2, 51)
 
 
 if __name__ == "__main__":

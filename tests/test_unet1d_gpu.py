@@ -84,3 +84,54 @@ def test_unet1d_full_size_runs_and_keeps_radius():
     loss = gen.ssm(sig.to(DEV)[:8]).mean()
     loss.backward()
     assert torch.isfinite(loss) and all(torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+# ---- 2-D U-Net (BASELINE config 4): VorticityUNet on flattened 16x16 / 32x32 fields ------------------------------------
+@pytest.mark.parametrize("name", G.names("w"))
+def test_unet2d_forward_sampler_ssm(name):
+    from sdeflow_light_b200.NNUnet import VorticityUNet
+    meta, arr = G.load(name)
+    base, T = Bd.base_from(meta, arr, DEV)
+    base.dim = meta["dim"]
+    net = VorticityUNet(base_channels=meta["base_channels"], channel_mults=(1, 2, 4), num_res_blocks=meta["num_res_blocks"],
+                        premodule="NormalizeLogRadius" if meta["premodule"] else None, in_space=meta["in_space"],
+                        attention_resolutions=(2, 4), flatten_order=meta["flatten_order"])
+    sd = {k[3:]: v for k, v in arr.items() if k.startswith("sd.")}
+    assert sorted(sd) == sorted(net.state_dict().keys())  # the reference's checkpoint keys load unchanged
+    net.load_state_dict(sd)
+    gen = P.PluginReverseSDE(base, net.to(DEV), T, deviceReverseSDE=DEV).to(DEV)
+    with torch.no_grad():
+        fwd = net(arr["x0"].to(DEV), arr["s"].to(DEV))
+    e_f = _rel(fwd, arr["fwd"])
+    out = P.rk4_stratonovich_sampler(gen, arr["x0"].to(DEV), meta["num_steps"], lmbd=0., keep_all_samples=True,
+                                     include_t0=True, norm_correction=True, noise=arr["noise"])
+    e_s = _rel(out, arr["out"])
+    gen.train()
+    gen.zero_grad()
+    loss = gen.ssm_loss(arr["t"].to(DEV), arr["x0"].to(DEV), arr["y"].to(DEV), arr["v"].to(DEV))
+    e_l = _rel(loss.detach(), arr["loss"])
+    loss.mean().backward()
+    e_g = max(_rel(p.grad, arr["grad." + k]) for k, p in net.named_parameters())
+    Bd.report(test=name, fwd_rel=e_f, sampler_rel=e_s, loss_rel=e_l, grad_rel=e_g)
+    assert e_f < 2e-4 and e_s < 2e-4 and e_l < 5e-4 and e_g < 2e-3
+
+
+def test_unet2d_full_size_runs():
+    """Config-4 size: 32x32 fields (d = 1024), VorticityUNet(32, (1,2,4), 2 res blocks, attention at 16x16 and 8x8)."""
+    from sdeflow_light_b200.NNUnet import VorticityUNet
+    torch.manual_seed(0)
+    S, B = 32, 16
+    img = torch.nn.functional.avg_pool2d(torch.randn(B, 1, S + 4, S + 4), 5, stride=1).reshape(B, S * S) * 4.0
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(img, beta_min=0.8, beta_max=160., T=T, t_epsilon=8e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=128, device=DEV, estim_cst_norm_dens_r_T=False)
+    net = VorticityUNet(32, (1, 2, 4), 2, premodule="NormalizeLogRadius", in_space=S, attention_resolutions=(2, 4),
+                        flatten_order="F").to(DEV)
+    assert sum(p.numel() for p in net.parameters()) == 4043969
+    with torch.no_grad():
+        net.core.out[2].weight.normal_(0, 0.05)
+    gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
+    x0 = gen.latent_sample(B, S * S)
+    out = P.rk4_stratonovich_sampler(gen, x0, 4, keep_all_samples=False, norm_correction=True, seed=3, device_out=True)
+    assert torch.isfinite(out).all()
+    assert float(((out.norm(dim=1) - x0.norm(dim=1)).abs() / x0.norm(dim=1)).max()) < 1e-5

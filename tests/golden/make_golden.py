@@ -182,26 +182,37 @@ def unet1d_case(ref, name, kind, L, B, N, seed, pre="NormalizeLogRadius"):
     _save(name, meta, **arrays)
 
 
-def unet2d_case(ref, name, S, B, N, seed, pre="NormalizeLogRadius", order="F"):
-    """VorticityUNet (NNUnet.py + model/unet.py) on flattened SxS images with the sparse multiplicative SDE."""
+def build_unet2d(module, S, pre, order, seed):
+    """Seeded construction shared by the fixture writer (reference module) and the tests (drop-in module): the same
+    constructor order consumes the global RNG identically, so the 4.04 M weights need not be stored."""
     torch.manual_seed(seed)
-    L = S * S
-    img = torch.nn.functional.avg_pool2d(torch.randn(128, 1, S + 4, S + 4), 5, stride=1).reshape(128, L) * 4.0
-    net = ref.NNUnet.VorticityUNet(base_channels=8, channel_mults=(1, 2, 4), num_res_blocks=1, premodule=pre,
-                                   in_space=S, attention_resolutions=(2, 4), flatten_order=order)
+    net = module.VorticityUNet(base_channels=32, channel_mults=(1, 2, 4), num_res_blocks=2, premodule=pre, in_space=S,
+                               attention_resolutions=(2, 4), flatten_order=order)
+    g = torch.Generator().manual_seed(seed + 100)
     with torch.no_grad():  # the reference zero-initialises these; randomise them so that every path is exercised
         for k, p_ in net.named_parameters():
             if p_.abs().sum() == 0 and p_.dim() > 1:
-                p_.copy_(torch.randn_like(p_) * (0.5 / p_[0].numel() ** 0.5))
+                p_.copy_(torch.randn(p_.shape, generator=g) * (0.5 / p_[0].numel() ** 0.5))
+    return net
+
+
+def unet2d_case(ref, name, S, B, N, seed, pre="NormalizeLogRadius", order="F"):
+    """VorticityUNet (NNUnet.py + model/unet.py, the driver's 4.04 M-parameter configuration) on flattened SxS images
+    with the sparse multiplicative SDE.  Weights are reproduced from the seed; gradients are stored as per-tensor norms
+    and leading entries."""
+    L = S * S
+    net = build_unet2d(ref.NNUnet, S, pre, order, seed)
+    torch.manual_seed(seed + 1)
+    img = torch.nn.functional.avg_pool2d(torch.randn(64, 1, S + 4, S + 4), 5, stride=1).reshape(64, L) * 4.0
     base, gen, _ = ref_live.build(ref, "msgm_sparse", L, img, pre, net=net)
     x0 = img[:B].clone() + 0.2 * torch.randn(B, L)
     s = torch.rand(B)
     with torch.no_grad():
         fwd = net(x0, s)
-    torch.manual_seed(seed + 1)
+    torch.manual_seed(seed + 2)
     xs = ref.sde_scheme.rk4_stratonovich_sampler(gen, x0, N, lmbd=0., keep_all_samples=True, include_t0=True,
                                                  norm_correction=True)
-    torch.manual_seed(seed + 1)
+    torch.manual_seed(seed + 2)
     noise = torch.stack([torch.randn_like(x0) for _ in range(N)])
     t_ = torch.rand(B, 1).clamp_min(1e-3)
     y = (x0 + 0.2 * torch.randn(B, L)).requires_grad_()
@@ -214,13 +225,14 @@ def unet2d_case(ref, name, S, B, N, seed, pre="NormalizeLogRadius", order="F"):
     loss.mean().backward()
     arrays = dict(x0=x0.numpy(), s=s.numpy(), fwd=fwd.numpy(), noise=noise.numpy(), out=xs.numpy(), t=t_.numpy(),
                   y=y.detach().numpy(), v=v.numpy(), loss=loss.detach().numpy(), **_sde_arrays(base))
-    for k, p_ in net.state_dict().items():
-        arrays["sd." + k] = p_.numpy().copy()
-    for k, p_ in net.named_parameters():
-        arrays["grad." + k] = p_.grad.numpy().copy()
+    arrays["wsum"] = np.array([float(p_.double().sum()) for p_ in net.state_dict().values()])
+    names = [k for k, _ in net.named_parameters()]
+    arrays["gradnorm"] = np.array([float(p_.grad.norm()) for _, p_ in net.named_parameters()], dtype=np.float32)
+    arrays["gradhead"] = np.stack([torch.nn.functional.pad(p_.grad.flatten()[:8], (0, max(0, 8 - p_.numel()))).numpy()
+                                   for _, p_ in net.named_parameters()])
     meta = dict(kind="msgm_sparse", dim=L, in_space=S, premodule=pre is not None, scheme="rk4", num_steps=N, lmbd=0.0,
-                norm_correction=True, include_t0=True, beta_min=0.1, beta_max=20.0, T=1.0, base_channels=8,
-                num_res_blocks=1, flatten_order=order)
+                norm_correction=True, include_t0=True, beta_min=0.1, beta_max=20.0, T=1.0, flatten_order=order,
+                seed=seed, param_names=names)
     _save(name, meta, **arrays)
 
 

@@ -15,7 +15,10 @@
 //   * Swish(z) = h tanh(h) + h with h = z/2; the 1/2 is folded into the packed weights, so one MUFU per activation;
 //   * layer 1 (K = d+2) is evaluated in split precision (u_hi, u_lo) x (W_hi, W_lo) so that time, log-radius and
 //     direction inputs keep ~22 mantissa bits at no extra cost (they fit the zero padding of the K=16 slices);
-//   * for d <= 4 the 128->d output layer is accumulated on the CUDA cores inside the last epilogue (one handshake less).
+//   * for d <= 4 the 128->d output layer is accumulated on the CUDA cores inside the last epilogue (one handshake less);
+//   * for dense G with 5 <= d <= 8 the state-dependent diffusion g(s,y)[i,k] = sqrt(beta) sum_j G[i,j,k] y_j (what the
+//     reference materialises as a (B,d,d) tensor, SDEs.py:432) is itself a tensor-core product: A = y split hi/lo,
+//     B = G split hi/lo (fp32-level accuracy), issued with the output layer into the free accumulator columns 64-127.
 //
 // All waits are bounded; a timeout sets a flag in the context workspace (msgm_debug_flags) instead of hanging.
 #include <cuda_fp16.h>
@@ -42,7 +45,10 @@ struct TcLayout {
   static constexpr int oW2 = oW1 + W1_BYTES;
   static constexpr int oW3 = oW2 + WH_BYTES;
   static constexpr int oW4 = oW3 + WH_BYTES;
-  static constexpr int IMG_BYTES = oW4 + W4_BYTES;             // what the pack kernel writes / TMA copies
+  static constexpr bool TCG = DP == 8;                         // dense G . y on the tensor pipe (d in 5..8)
+  static constexpr int GI_BYTES = 4096;                        // fp16 [4][8][8][8]: rows n = i*8+k, k-index = split j
+  static constexpr int oGI = oW4 + W4_BYTES;
+  static constexpr int IMG_BYTES = oGI + GI_BYTES;             // what the pack kernel writes / TMA copies
   static constexpr int oOnes = IMG_BYTES;                      // fp16 [2][16][8][8]: A operand of the bias slices
   static constexpr int oG = oOnes + 4096;                      // fp32 [DP][DP][DP] (dense)
   static constexpr int oLG = oG + 4 * DP * DP * DP;            // fp32 [DP][DP]
@@ -52,7 +58,9 @@ struct TcLayout {
   static constexpr bool L4_CC = DP <= 4;                       // output layer on CUDA cores
   static constexpr int NSLOT = DP <= 4 ? 4 : 3;                // tiles in flight per CTA (registers / smem bound)
   static constexpr int THREADS = 128 * NSLOT + 32;             // 4 particle warps per slot + 1 MMA issuer warp
-  static constexpr int SMEM_BYTES = oA + NSLOT * A_BYTES;
+  static constexpr int AG_BYTES = 8192;                        // per slot: split y operand, fp16 [4][16][8][8]
+  static constexpr int oAg = oA + NSLOT * A_BYTES;
+  static constexpr int SMEM_BYTES = oAg + (TCG ? NSLOT * AG_BYTES : 0);
 };
 
 struct TcParams {
@@ -322,6 +330,7 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
     tma_bulk_g2s(smem + L::oW2, P.img + L::oW2, L::WH_BYTES, bar_w);
     tma_bulk_g2s(smem + L::oW3, P.img + L::oW3, L::WH_BYTES, bar_w);
     tma_bulk_g2s(smem + L::oW4, P.img + L::oW4, L::W4_BYTES, bar_w);
+    tma_bulk_g2s(smem + L::oGI, P.img + L::oGI, L::GI_BYTES, bar_w);
   }
 
   if (warp == 4 * NSLOT) {
@@ -341,6 +350,9 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
     const uint64_t w2_desc = umma_desc(sbase + L::oW2, 2048, 128);
     const uint64_t w3_desc = umma_desc(sbase + L::oW3, 2048, 128);
     const uint64_t w4_desc = umma_desc(sbase + L::oW4, 256, 128);
+    const uint64_t gi_desc = umma_desc(sbase + L::oGI, 1024, 128);
+    const uint32_t idesc_g = umma_idesc_f16(128, 64);
+    constexpr bool TCG = L::TCG && KIND == MSGM_SDE_MSGM_DENSE;
     Prof pf{(P.prof && blockIdx.x == 0 && lane == 0) ? P.prof + 8 : nullptr, 0};
     pf.start();
     // per-slot progress: number of layers issued so far, and how many the slot will need in total
@@ -378,6 +390,11 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
               umma_ss(dcol, ones_desc, w4_desc, idesc_o, 0, lead);
 #pragma unroll
               for (int s = 0; s < 8; ++s) umma_ss(dcol, a_desc + s * 256, w4_desc + (s + 1) * 32, idesc_o, 1, lead);
+              if (TCG) {  // g(y)[i,k] / sqrt(beta) = sum_j G[i,j,k] y_j into accumulator columns 64..127 (n = 8 i + k)
+                const uint64_t ag_desc = umma_desc(sbase + L::oAg + sl * L::AG_BYTES, 2048, 128);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) umma_ss(dcol + 64, ag_desc + s * 256, gi_desc + s * 128, idesc_g, s > 0, lead);
+              }
             }
             umma_commit(bar_d + sl, lead);
             done[sl] += 1;
@@ -500,6 +517,23 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
                   make_uint4(pack_h2(hk[8 * ch], hk[8 * ch + 1]), pack_h2(hk[8 * ch + 2], hk[8 * ch + 3]),
                              pack_h2(hk[8 * ch + 4], hk[8 * ch + 5]), pack_h2(hk[8 * ch + 6], hk[8 * ch + 7]));
           }
+          if constexpr (L::TCG && KIND == MSGM_SDE_MSGM_DENSE) {
+            // split stage input for the G . y product: k-index [y_hi | y_lo | y_hi | 0]
+            unsigned char* gb = smem + L::oAg + sl * L::AG_BYTES + (row >> 3) * 128 + (row & 7) * 16;
+            uint32_t hi2[4], lo2[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              __half h0, l0, h1, l1;
+              split_f16(y[2 * c], h0, l0);
+              split_f16(y[2 * c + 1], h1, l1);
+              hi2[c] = pack_h2(h0, h1);
+              lo2[c] = pack_h2(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(gb) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+            *reinterpret_cast<uint4*>(gb + 2048) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+            *reinterpret_cast<uint4*>(gb + 4096) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+            *reinterpret_cast<uint4*>(gb + 6144) = make_uint4(0, 0, 0, 0);
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           tc_fence_before();
           mbar_arrive(my_a);
@@ -535,6 +569,15 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
             for (int c = 0; c < DP; ++c) a[c] = __uint_as_float(r[c]);
             pf.tick(3);  // output layer on the tensor pipe
           }
+          [[maybe_unused]] float gy[L::TCG ? 64 : 1];  // sum_j G[i,j,k] y_j at index 8 i + k (tensor-pipe product)
+          if constexpr (L::TCG && KIND == MSGM_SDE_MSGM_DENSE) {
+            uint32_t r0[32], r1[32];
+            TMEM_LD32(taddr + 64, r0);
+            TMEM_LD32(taddr + 96, r1);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { gy[c] = __uint_as_float(r0[c]); gy[32 + c] = __uint_as_float(r1[c]); }
+          }
 
           // ---- stage increment K = delta * drift + sigma . dW (same algebra as sampler_fp32.cu) --------------------------
           float K[DP];
@@ -566,7 +609,10 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
 #pragma unroll
               for (int i = 0; i < DP; ++i) {
                 float acc = 0.0f, fc = 0.0f;
-                if constexpr (DP >= 4) {
+                if constexpr (L::TCG) {
+#pragma unroll
+                  for (int k = 0; k < DP; ++k) acc = fmaf(gy[8 * i + k], w[k], acc);
+                } else if constexpr (DP >= 4) {
 #pragma unroll
                   for (int k4 = 0; k4 < DP; k4 += 4) {
                     float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -659,12 +705,25 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
 template <int DP>
 __global__ void pack_mlp_tc_kernel(int d, int pre, const float* W0, const float* b0, const float* W1, const float* b1,
                                    const float* W2, const float* b2, const float* W3, const float* b3,
-                                   unsigned char* img) {
+                                   const float* G, unsigned char* img) {
   using L = TcLayout<DP>;
   constexpr int MP = L::MP, K1 = L::K1;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // one fp16 element of the image
   if (e >= L::IMG_BYTES / 2) return;
   const int byte = e * 2;
+  if (byte >= L::oGI) {
+    // G image for the tensor-core g(y) product: rows n = 8 i + k (N = 64), k-index kk = [hi(j) | hi(j) | lo(j) | 0]
+    // against the operand [y_hi | y_lo | y_hi | 0]; element order [kk/8][n/8][n%8][kk%8]
+    const int off = (byte - L::oGI) / 2;
+    const int chunk = off / 512, rem = off % 512;
+    const int n = (rem / 64) * 8 + (rem % 64) / 8, j = rem % 8;
+    const int i = n >> 3, k = n & 7;
+    float v = 0.0f;
+    if (G != nullptr && chunk < 3 && i < d && j < d && k < d) v = G[(i * d + j) * d + k];
+    const __half hi = __float2half_rn(v);
+    reinterpret_cast<__half*>(img)[e] = chunk == 2 ? __float2half_rn(v - __half2float(hi)) : hi;
+    return;
+  }
   int layer, off, Nrows;
   if (byte < L::oW2) { layer = 0; off = (byte - L::oW1) / 2; Nrows = 128; }
   else if (byte < L::oW3) { layer = 1; off = (byte - L::oW2) / 2; Nrows = 128; }
@@ -723,7 +782,8 @@ static int launch_tc(msgm_ctx* ctx, const msgm_mlp_desc* m, TcParams& P, cudaStr
   MSGM_CUDA_TRY(cudaMemsetAsync(ctx->ws, 0, 256, stream));
   const int nel = L::IMG_BYTES / 2;
   pack_mlp_tc_kernel<DP><<<(nel + 255) / 256, 256, 0, stream>>>(P.d, P.pre, m->W[0], m->b[0], m->W[1], m->b[1], m->W[2],
-                                                                m->b[2], m->W[3], m->b[3], img);
+                                                                m->b[2], m->W[3], m->b[3],
+                                                                (KIND == MSGM_SDE_MSGM_DENSE && L::TCG) ? P.G : nullptr, img);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   auto kern = sample_tc_kernel<DP, KIND>;

@@ -89,14 +89,21 @@ def test_ssm_end_to_end_trains():
             base.dim = d
             net = P.MLP(d).to(DEV)
         gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
-        opt = torch.optim.Adam(gen.parameters(), lr=1e-3)
-        losses = []
-        for it in range(60):
+        opt = torch.optim.Adam(gen.parameters(), lr=2e-3)
+        # fixed evaluation set (same t, y, v before and after): the per-batch loss itself is a noisy Hutchinson estimate
+        xe = data[:4096].to(DEV)
+        te, _, ye = gen.sample_txy(xe)
+        ve = P.SDEs.sample_v(xe.shape, DEV)
+        with torch.no_grad():
+            before = float(gen.ssm_loss(te, xe, ye, ve).mean())
+        for it in range(200):
             opt.zero_grad()
             x = data[torch.randint(0, 4096, (256,))].to(DEV)
             loss = gen.ssm(x).mean()
             loss.backward()
             opt.step()
-            losses.append(float(loss))
-        assert all(map(lambda v: v == v, losses))
-        assert sum(losses[-10:]) / 10 < sum(losses[:10]) / 10, (make, losses[:3], losses[-3:])
+            assert bool(torch.isfinite(loss))
+        with torch.no_grad():
+            after = float(gen.ssm_loss(te, xe, ye, ve).mean())
+        Bd.report(test=f"train-{make}", eval_loss_before=before, eval_loss_after=after)
+        assert after < before - 0.005, (make, before, after)  # observed: msgm 0.003 -> -0.02, sgm 10.2 -> 0.7

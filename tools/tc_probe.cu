@@ -248,7 +248,42 @@ __global__ void __launch_bounds__(256) probe_mufu(float* out, int iters) {
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc += v[j];
-  } else {  // full packed swish epilogue: cvt.f16x2 + tanh.f16x2 + hfma2 on 2 inputs
+  } else if (MODE == 4) {  // F2FP only: cvt.rn.f16x2.f32
+    float a[8];
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.001f * (threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t h;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(a[j]), "f"(a[(j + 1) & 7]));
+        o ^= h;
+        a[j] = __uint_as_float(__float_as_uint(a[j]) ^ (h & 1));
+      }
+    }
+    acc = __uint_as_float(o);
+  } else if (MODE == 5) {  // the sampler's epilogue mix per pair: 2 tanh.f32 + 2 ffma + 1 cvt.f16x2
+    float a[8];
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.001f * (threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float t0, t1;
+        asm volatile("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a[j]));
+        asm volatile("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a[j + 1]));
+        const float s0 = fmaf(a[j], t0, a[j]), s1 = fmaf(a[j + 1], t1, a[j + 1]);
+        uint32_t h;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(s1), "f"(s0));
+        o ^= h;
+        a[j] += 1e-3f;
+        a[j + 1] += 1e-3f;
+      }
+    }
+    acc = __uint_as_float(o);
+  } else {  // MODE 3: full packed swish epilogue: cvt.f16x2 + tanh.f16x2 + hfma2 on 2 inputs
     float a[8], b[8];
     uint32_t o = 0;
 #pragma unroll
@@ -351,5 +386,7 @@ int main() {
   run_mufu<1>("tanh.approx.f16x2 (x2 elems)", 8);
   run_mufu<2>("ex2.approx.f32", 8);
   run_mufu<3>("cvt+tanh.f16x2+hfma2 (pairs)", 8);
+  run_mufu<4>("cvt.rn.f16x2.f32 only", 8);
+  run_mufu<5>("2 tanh.f32 + 2 ffma + cvt (elems)", 8);
   return 0;
 }

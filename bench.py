@@ -170,7 +170,7 @@ def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev):
         opt.step()
         return loss
 
-    for _ in range(3):
+    for _ in range(5):
         step()
     torch.cuda.synchronize(dev)
     l0 = P._lib.launch_count(dev)
@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--dim", type=int, default=8)
     ap.add_argument("--precision", default="f16tc", choices=["fp32", "f16tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the SSM training leg (profiling runs)")
     ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU (default 2^20)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -310,11 +311,11 @@ def main():
     gen.train()
     train = {"metric": "ssm_train_samples_per_sec", "unit": "samples/s", "precision": "fp32",
              "step": "gen.ssm(x).mean().backward(); flat-grad all-reduce (N>1); torch.optim.Adam.step()", "runs": []}
-    for batch in (256, 16384):
+    for batch in (() if args.no_train else (256, 16384)):
         v_, ms_, launches_, loss_ = time_gpu_train(P, gen, data_dev, batch, 20, world, dev)
         train["runs"].append({"batch_per_gpu": batch, "value": v_, "ms_per_iter": ms_, "gpu_launches_per_iter": launches_,
                               "loss": loss_})
-    train["value"] = train["runs"][-1]["value"]
+    train["value"] = train["runs"][-1]["value"] if train["runs"] else None
 
     if rank == 0:
         peaks = load_peaks()
@@ -337,7 +338,7 @@ def main():
         }
         line["train"] = train
         if not args.no_cpu_baseline:
-            train["cpu_baseline"] = {"value": time_cpu_train(sde, mlp, data_host, 256, 10), "unit": "samples/s",
+            train["cpu_baseline"] = {"value": None if args.no_train else time_cpu_train(sde, mlp, data_host, 256, 10), "unit": "samples/s",
                                      "cores": torch.get_num_threads(), "kind": "port",
                                      "sample": "batch 256, 10 iterations after 1 warm-up (oracle port, torch CPU fp32)"}
             v, t = time_cpu_port(sde, mlp, 50_000, 4, 3)

@@ -154,8 +154,10 @@ probe_mma(const __half* __restrict__ Aimg, const __half* __restrict__ Arow, cons
 
   const uint32_t lbo = (variant & 2) ? 128u : (uint32_t)(N * 16);  // bytes between the two k-chunks of a slice
   const uint32_t sbo = (variant & 2) ? (uint32_t)(N * 16) : 128u;  // bytes between 8-row groups
-  const uint32_t idesc = make_idesc(M, N);
+  const int Nmma = (variant & 16) ? 64 : ((variant & 32) ? 32 : N);
+  const uint32_t idesc = make_idesc(M, Nmma);
   long long t2 = clock64();
+  long long t_issued = t2;
   if (tid == 0) {
     for (int rep = 0; rep < reps; ++rep) {
 #pragma unroll
@@ -169,6 +171,7 @@ probe_mma(const __half* __restrict__ Aimg, const __half* __restrict__ Arow, cons
         }
       }
     }
+    t_issued = clock64();
     mma_commit(bar);
   }
   bool ok = mbar_wait_bounded(bar, 0, err);
@@ -207,6 +210,7 @@ probe_mma(const __half* __restrict__ Aimg, const __half* __restrict__ Arow, cons
   if (tid == 0) {
     cycles[0] = t1 - t0;  // A store (64 cols)
     cycles[1] = t3 - t2;  // MMA chain issue -> completion observed
+    cycles[4] = t_issued - t2;  // time spent issuing
     cycles[2] = t4 - t3;  // D load (128 cols) + global stores
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -352,7 +356,7 @@ int main() {
   CK(cudaMalloc(&dAimg, sizeof(__half) * M * K));
   CK(cudaMalloc(&dBimg, sizeof(__half) * N * K));
   CK(cudaMalloc(&dout, sizeof(float) * M * N));
-  CK(cudaMalloc(&dcyc, sizeof(long long) * 4));
+  CK(cudaMalloc(&dcyc, sizeof(long long) * 8));
   CK(cudaMalloc(&derr, sizeof(int)));
   CK(cudaMemcpy(dA, A.data(), sizeof(__half) * M * K, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dAimg, Aimg.data(), sizeof(__half) * M * K, cudaMemcpyHostToDevice));
@@ -371,7 +375,7 @@ int main() {
         return 3;
       }
       std::vector<float> out(M * N);
-      long long cyc[4];
+      long long cyc[8];
       int err;
       CK(cudaMemcpy(out.data(), dout, sizeof(float) * M * N, cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(cyc, dcyc, sizeof(cyc), cudaMemcpyDeviceToHost));
@@ -381,6 +385,16 @@ int main() {
       printf("variant %d (%-26s) reps=%d: timeout=%d max|err|=%.3e  [%s]  cycles: A-st=%lld mma=%lld D-ld=%lld tmem-epi-traffic/layer=%lld\n", variant,
              names[variant], reps, err, maxerr, maxerr < 1e-3 ? "MATCH" : "mismatch", cyc[0], cyc[1], cyc[2], cyc[3]);
     }
+  }
+  // MMA rate vs N (results are only checked for N = 128): issue time vs completion time of 64 back-to-back MMAs
+  for (int variant : {0, 1, 16, 17, 32, 33}) {
+    CK(cudaMemset(derr, 0, sizeof(int)));
+    probe_mma<<<1, 128, smem>>>(dAimg, dA, dBimg, dout, variant, 8, dcyc, derr);
+    CK(cudaDeviceSynchronize());
+    long long cyc[8];
+    CK(cudaMemcpy(cyc, dcyc, sizeof(cyc), cudaMemcpyDeviceToHost));
+    printf("mma-rate %s N=%d: 64 MMAs issue=%lld clk, issue->complete=%lld clk  (%.1f clk/MMA)\n", (variant & 1) ? "SS" : "TS",
+           (variant & 16) ? 64 : ((variant & 32) ? 32 : 128), cyc[4], cyc[1], cyc[1] / 64.0);
   }
   run_mufu<0>("tanh.approx.f32", 8);
   run_mufu<1>("tanh.approx.f16x2 (x2 elems)", 8);

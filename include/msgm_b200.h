@@ -142,6 +142,18 @@ int msgm_row_norm(msgm_ctx* ctx, const float* x, float* r, int32_t d, int64_t B,
 int msgm_philox_normal(msgm_ctx* ctx, float* out, int32_t d, int64_t B, float scale, uint64_t seed,
                        uint64_t particle_offset, uint32_t step, void* stream);
 
+/* Prior sampling.  Replaces MSGMsde.latent_sample / gen_radial_distribution / randu_on_sphere (SDEs.py:438-493,520-526;
+ * msgm=1: x0 = quantile(r_T, U) [exp(.) - 1e-6 if log_map] * z/|z|) and SGMsde.latent_sample (SDEs.py:201-203; msgm=0:
+ * x0 = z).  rT_sorted: device (n_r,) ascending.  U (B,) / Z (B,d) inject the uniform / normal draws (parity tests); NULL
+ * = in-kernel Philox keyed by (seed, particle_offset + row). */
+int msgm_latent_sample(msgm_ctx* ctx, const float* rT_sorted, int32_t n_r, int32_t log_map, int32_t msgm, const float* U,
+                       const float* Z, float* out, int32_t d, int64_t B, uint64_t seed, uint64_t particle_offset,
+                       void* stream);
+/* MMD metric.  Replaces compute_kernel / compute_mmd (quantitative_comparison.py:22-47): sums_out (device, 3 doubles)
+ * receives the pair sums of exp(-|a-b|^2/d^2) over (x,x), (y,y), (x,y); mmd = s0/N^2 + s1/M^2 - 2 s2/(N M). */
+int msgm_mmd_sums(msgm_ctx* ctx, const float* x, int64_t N, const float* y, int64_t M, int32_t d, double* sums_out,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

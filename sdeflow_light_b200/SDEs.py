@@ -161,8 +161,9 @@ class SGMsde(SDE):
     def sample(self, t, y0, return_noise=False):
         return self.sample_Song_et_al(t, y0, return_noise)
 
-    def latent_sample(self, num_samples, n):
-        return torch.randn(num_samples, n, device=self.device)
+    def latent_sample(self, num_samples, n, *, seed=None, particle_offset=0):
+        """x_0 ~ N(0, I) (reference SDEs.py:201-203), drawn in-kernel (Philox keyed by the global particle index)."""
+        return _latent(self, num_samples, n, None, False, seed, particle_offset)
 
     def cond_latent_sample(self, t_, T, x):
         return self.sample(torch.ones_like(t_) * T, x)
@@ -297,8 +298,19 @@ class MSGMsde(SDE):
             r_gen = torch.exp(r_gen) - 1e-6
         return r_gen
 
-    def latent_sample(self, num_samples, n):
-        return self.gen_radial_distribution(num_samples) * randu_on_sphere((num_samples, self.dim), device=self.device)
+    def latent_sample(self, num_samples, n, *, seed=None, particle_offset=0, U=None, Z=None):
+        """x_0 = r s with r from the empirical radius law and s uniform on the sphere (reference SDEs.py:438-493): one
+        fused kernel (sorted radius table, in-kernel Philox keyed by the global particle index).  ``U`` / ``Z`` inject the
+        reference's uniform / normal draws.  The KDE radius sampler keeps the reference's sklearn path."""
+        if self.norm_sampler != "ecdf":
+            return self.gen_radial_distribution(num_samples) * randu_on_sphere((num_samples, self.dim), device=self.device)
+        return _latent(self, num_samples, self.dim, self._sorted_radii(), self.norm_map == "log", seed, particle_offset, U, Z)
+
+    def _sorted_radii(self):
+        cache = getattr(self, "_rT_sorted", None)
+        if cache is None or cache[0] is not self.r_T:
+            self._rT_sorted = (self.r_T, torch.sort(self.r_T.to(self.device).float().contiguous())[0])
+        return self._rT_sorted[1]
 
     def cond_latent_sample(self, t_, T, x):
         r_x = torch.linalg.norm(x.detach().to(self.device), dim=1).reshape(x.shape[0], 1)
@@ -307,6 +319,22 @@ class MSGMsde(SDE):
     def log_latent_pdf(self, yT):
         r = torch.linalg.norm(yT.detach(), dim=1).reshape(-1, 1)
         return torch.tensor(self.kde.score_samples(r.cpu())).to(torch.float32).to(self.device) - self.cst_log_dens
+
+
+def _latent(sde, num_samples, d, r_sorted, log_map, seed, particle_offset, U=None, Z=None):
+    import ctypes as C
+    dev = sde.device
+    handle = _lib.ctx(dev)
+    out = torch.empty((num_samples, d), device=dev, dtype=torch.float32)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    U = None if U is None else _lib.f32c(U.reshape(-1), dev)
+    Z = None if Z is None else _lib.f32c(Z, dev)
+    _lib.check(_lib.lib().msgm_latent_sample(handle, _lib.ptr(r_sorted), 0 if r_sorted is None else r_sorted.numel(),
+                                             int(bool(log_map)), int(r_sorted is not None), _lib.ptr(U), _lib.ptr(Z),
+                                             _lib.ptr(out), d, num_samples, int(seed), int(particle_offset),
+                                             _lib.stream_ptr(dev)))
+    return out
 
 
 # ---- Hutchinson probes (reference SDEs.py:514-536) ---------------------------------------------------------------

@@ -45,7 +45,7 @@ _ctx = {}
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
            "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward",
-           "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal"]
+           "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums"]
 
 
 def lib() -> C.CDLL:
@@ -75,6 +75,10 @@ def lib() -> C.CDLL:
                 L.msgm_row_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
                 L.msgm_philox_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64,
                                                  C.c_uint64, C.c_uint32, C.c_void_p]
+                L.msgm_latent_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]
+                L.msgm_mmd_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                            C.c_void_p]
                 L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]

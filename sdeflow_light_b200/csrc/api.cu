@@ -30,6 +30,10 @@ int stage_update(msgm_ctx*, const msgm_sde_desc*, int, int, float, int, int, flo
 int row_norm(msgm_ctx*, const float*, float*, int, int64_t, cudaStream_t);
 int philox_normal(msgm_ctx*, float*, int, int64_t, float, uint64_t, uint64_t, uint32_t, cudaStream_t);
 
+int latent_sample(msgm_ctx*, const float*, int, int, int, const float*, const float*, float*, int, int64_t, uint64_t,
+                  uint64_t, cudaStream_t);
+int mmd_sums(msgm_ctx*, const float*, int64_t, const float*, int64_t, int, double*, cudaStream_t);
+
 static int invalid(const char* msg) {
   set_error(msg);
   return MSGM_ERR_INVALID;
@@ -219,6 +223,23 @@ int msgm_philox_normal(msgm_ctx* ctx, float* out, int32_t d, int64_t B, float sc
   if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return philox_normal(ctx, out, d, B, scale, seed, particle_offset, step, (cudaStream_t)stream);
+}
+
+int msgm_latent_sample(msgm_ctx* ctx, const float* rT_sorted, int32_t n_r, int32_t log_map, int32_t msgm, const float* U,
+                       const float* Z, float* out, int32_t d, int64_t B, uint64_t seed, uint64_t particle_offset,
+                       void* stream) {
+  if (!ctx || !out || d < 1) return invalid("msgm_latent_sample: bad argument");
+  if (msgm && (!rT_sorted || n_r < 1)) return invalid("msgm_latent_sample: radius table missing");
+  if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return latent_sample(ctx, rT_sorted, n_r, log_map, msgm, U, Z, out, d, B, seed, particle_offset, (cudaStream_t)stream);
+}
+
+int msgm_mmd_sums(msgm_ctx* ctx, const float* x, int64_t N, const float* y, int64_t M, int32_t d, double* sums_out,
+                  void* stream) {
+  if (!ctx || !x || !y || !sums_out || d < 1 || N < 1 || M < 1) return invalid("msgm_mmd_sums: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return mmd_sums(ctx, x, N, y, M, d, sums_out, (cudaStream_t)stream);
 }
 
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {

@@ -154,6 +154,28 @@ int msgm_latent_sample(msgm_ctx* ctx, const float* rT_sorted, int32_t n_r, int32
 int msgm_mmd_sums(msgm_ctx* ctx, const float* x, int64_t N, const float* y, int64_t M, int32_t d, double* sums_out,
                   void* stream);
 
+/* ---- 1-D U-Net score net layers (NNUnet1D.py:13-179), fp32, NCL layout -----------------------------------------------
+ * One msgm_conv1d call = nn.Conv1d (+ optional exact GELU) over the channel concatenation [x1, x2, emb] WITHOUT building
+ * it: x2 (decoder skip) may be NULL; the Cemb embedding channels, constant along the signal, enter through the folded
+ * table E (B,Cout,K) produced by msgm_emb_fold (NULL when Cemb == 0).  W is the module's weight (Cout, C1+C2+Cemb, K). */
+typedef struct {
+  const float* x1; const float* x2; const float* W; const float* bias; const float* E; float* out;
+  int32_t B, C1, C2, Cemb, Cout, K, stride, pad, Lin, Lout, gelu;
+} msgm_conv1d_desc;
+int msgm_conv1d(msgm_ctx* ctx, const msgm_conv1d_desc* desc, void* stream);
+/* E[b,co,k] = sum_ci W[co, Coff+ci, k] emb[b,ci] : the embedding channels of a conv block folded into a bias table. */
+int msgm_emb_fold(msgm_ctx* ctx, const float* W, const float* emb, float* E, int32_t Cw, int32_t Coff, int32_t Cemb,
+                  int32_t Cout, int32_t K, int32_t B, void* stream);
+/* nn.ConvTranspose1d(Cin, Cout, kernel_size=4, stride=2, padding=1) followed by right zero padding to Lout
+ * (NNUnet1D.py:98,165-169).  W is (Cin, Cout, 4). */
+int msgm_convt1d_k4s2(msgm_ctx* ctx, const float* x, const float* W, const float* bias, float* out, int32_t B, int32_t Cin,
+                      int32_t Cout, int32_t Lin, int32_t Lout, void* stream);
+/* out (B,E) (+)= Linear(E,E)(GELU(Linear(1,E)(t))) : time_mlp / scale_embed (NNUnet1D.py:52-68); E <= 256. */
+int msgm_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float* b1, const float* W2, const float* b2,
+                   float* out, int32_t B, int32_t E, int32_t accumulate, void* stream);
+/* xn = x / (|x| + 1e-6) * sqrt(L), lognorm = log(|x| + 1e-6) per row (NN.py:64-70, NNUnet1D.py:136-139). */
+int msgm_normalize_log_radius(msgm_ctx* ctx, const float* x, float* xn, float* lognorm, int32_t B, int32_t L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,17 +5,23 @@ log|x| when premodule="NormalizeLogRadius"]; three encoder blocks (conv3-GELU-co
 k=4 convolution; a middle block; three decoder stages (transposed k=4 s=2 conv, concat skip, block); a 1x1 projection.
 The embedding vector is concatenated as ``emb_dim`` extra channels in front of EVERY block.  No normalisation layers.
 
-Round-1 status: the layer arithmetic runs through torch's convolution library calls on the GPU; the hand-written part
-of this path is the per-stage SDE update (csrc/stage_ops.cu).  Hand-written conv kernels are the next step.
+Inference (no autograd: the sampling hot path) runs entirely on hand-written kernels (csrc/conv1d_fp32.cu): the
+embedding MLPs, the premodule, every Conv1d / ConvTranspose1d with fused exact-GELU epilogue.  The embedding channels,
+constant along the signal, are folded into a per-(sample, out-channel, tap) table instead of being concatenated, and the
+decoder's skip concatenation is read from two tensors in place.  With autograd enabled (training) the same layers run
+as torch modules so that autograd can trace them.
 """
 from __future__ import annotations
 
 from typing import Optional
 
+import ctypes as C
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .NN import NormalizeLogRadius, evaluate  # noqa: F401
 
 
@@ -60,9 +66,80 @@ class UNet1D(nn.Module):
     def forward(self, x, t):
         if not x.is_cuda:
             raise RuntimeError("sdeflow_light_b200.NNUnet1D.UNet1D runs on CUDA only (no CPU fallback)")
-        # the reference is fp32 end to end: keep cuDNN from silently using TF32 for the convolutions
+        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not needs_graph:
+            return self._forward_kernels(x, t)
+        # autograd path: the reference is fp32 end to end, keep cuDNN from silently using TF32 for the convolutions
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             return self._forward(x, t)
+
+    # ---- hand-written kernel path (inference) -------------------------------------------------------------------
+    def _conv(self, h, dev, conv, x1, x2=None, emb=None, gelu=False):
+        L = _lib.lib()
+        B, C1, Lin = x1.shape
+        C2 = 0 if x2 is None else x2.shape[1]
+        W, bias = _lib.f32c(conv.weight, dev), _lib.f32c(conv.bias, dev)
+        Cout, Cw, K = W.shape
+        stride, pad = conv.stride[0], conv.padding[0]
+        Lout = (Lin + 2 * pad - K) // stride + 1
+        Cemb = Cw - C1 - C2
+        E = None
+        if Cemb > 0:
+            E = torch.empty((B, Cout, K), device=dev, dtype=torch.float32)
+            _lib.check(L.msgm_emb_fold(h, _lib.ptr(W), _lib.ptr(emb), _lib.ptr(E), Cw, C1 + C2, Cemb, Cout, K, B,
+                                       _lib.stream_ptr(dev)))
+        out = torch.empty((B, Cout, Lout), device=dev, dtype=torch.float32)
+        d = _lib.Conv1dDesc(x1.data_ptr(), None if x2 is None else x2.data_ptr(), W.data_ptr(), bias.data_ptr(),
+                            None if E is None else E.data_ptr(), out.data_ptr(), B, C1, C2, Cemb, Cout, K, stride, pad,
+                            Lin, Lout, int(gelu))
+        _lib.check(L.msgm_conv1d(h, C.byref(d), _lib.stream_ptr(dev)))
+        return out
+
+    def _block(self, h, dev, block, x1, x2, emb):
+        y = self._conv(h, dev, block.net[0], x1, x2, emb, gelu=True)
+        return self._conv(h, dev, block.net[2], y, gelu=True)
+
+    def _embed(self, h, dev, mlp, t, out, accumulate):
+        L = _lib.lib()
+        l1, l2 = mlp[0], mlp[2]
+        _lib.check(L.msgm_embed_mlp(h, _lib.ptr(t), _lib.ptr(_lib.f32c(l1.weight, dev)), _lib.ptr(_lib.f32c(l1.bias, dev)),
+                                    _lib.ptr(_lib.f32c(l2.weight, dev)), _lib.ptr(_lib.f32c(l2.bias, dev)), _lib.ptr(out),
+                                    t.shape[0], l2.weight.shape[0], int(accumulate), _lib.stream_ptr(dev)))
+
+    @torch.no_grad()
+    def _forward_kernels(self, x, t):
+        dev = x.device
+        h, L = _lib.ctx(dev), _lib.lib()
+        xs = _lib.f32c(x.reshape(x.shape[0], -1), dev)
+        B, Lsig = xs.shape
+        tt = _lib.f32c(t.reshape(-1), dev)
+        if tt.numel() == 1 and B != 1:
+            tt = tt.expand(B).contiguous()
+        E = self.time_mlp[2].weight.shape[0]
+        emb = torch.empty((B, E), device=dev, dtype=torch.float32)
+        self._embed(h, dev, self.time_mlp, tt, emb, False)
+        if self.premodule is not None:
+            xn, logn = torch.empty_like(xs), torch.empty(B, device=dev, dtype=torch.float32)
+            _lib.check(L.msgm_normalize_log_radius(h, _lib.ptr(xs), _lib.ptr(xn), _lib.ptr(logn), B, Lsig,
+                                                   _lib.stream_ptr(dev)))
+            self._embed(h, dev, self.scale_embed, logn, emb, True)
+            xs = xn
+        cur, skips = xs.view(B, 1, Lsig), []
+        for block, down in zip(self.enc_blocks, self.downs):
+            cur = self._block(h, dev, block, cur, None, emb)
+            skips.append(cur)
+            cur = self._conv(h, dev, down, cur)
+        cur = self._block(h, dev, self.middle, cur, None, emb)
+        for up, block in zip(self.up_convs, self.dec_blocks):
+            skip = skips.pop()
+            Bc, Cin, Lin = cur.shape
+            W, bias = _lib.f32c(up.weight, dev), _lib.f32c(up.bias, dev)
+            upo = torch.empty((Bc, W.shape[1], skip.shape[-1]), device=dev, dtype=torch.float32)
+            _lib.check(L.msgm_convt1d_k4s2(h, _lib.ptr(cur), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(upo), Bc, Cin, W.shape[1],
+                                           Lin, skip.shape[-1], _lib.stream_ptr(dev)))
+            cur = self._block(h, dev, block, upo, skip, emb)
+        out = self._conv(h, dev, self.final, cur)
+        return out.squeeze(1)
 
     def _forward(self, x, t):
         h = x.unsqueeze(1) if x.ndim == 2 else x

@@ -37,6 +37,12 @@ class SampleArgs(C.Structure):
                 ("keep_step", C.c_void_p), ("keep_out", C.c_void_p), ("T_rows", C.c_void_p)]
 
 
+class Conv1dDesc(C.Structure):
+    _fields_ = [("x1", C.c_void_p), ("x2", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("E", C.c_void_p),
+                ("out", C.c_void_p)] + [(n, C.c_int32) for n in ("B", "C1", "C2", "Cemb", "Cout", "K", "stride", "pad",
+                                                                 "Lin", "Lout", "gelu")]
+
+
 _lib = None
 _lock = threading.Lock()
 _ctx = {}
@@ -45,7 +51,8 @@ _ctx = {}
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
            "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward",
-           "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums"]
+           "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums",
+           "msgm_conv1d", "msgm_emb_fold", "msgm_convt1d_k4s2", "msgm_embed_mlp", "msgm_normalize_log_radius"]
 
 
 def lib() -> C.CDLL:
@@ -79,6 +86,11 @@ def lib() -> C.CDLL:
                                                  C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]
                 L.msgm_mmd_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                             C.c_void_p]
+                L.msgm_conv1d.argtypes = [C.c_void_p, C.POINTER(Conv1dDesc), C.c_void_p]
+                L.msgm_emb_fold.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 6 + [C.c_void_p]
+                L.msgm_convt1d_k4s2.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]
+                L.msgm_embed_mlp.argtypes = [C.c_void_p] * 7 + [C.c_int32] * 3 + [C.c_void_p]
+                L.msgm_normalize_log_radius.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 2 + [C.c_void_p]
                 L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]

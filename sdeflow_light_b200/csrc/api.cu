@@ -34,6 +34,13 @@ int latent_sample(msgm_ctx*, const float*, int, int, int, const float*, const fl
                   uint64_t, cudaStream_t);
 int mmd_sums(msgm_ctx*, const float*, int64_t, const float*, int64_t, int, double*, cudaStream_t);
 
+int conv1d(msgm_ctx*, const msgm_conv1d_desc*, cudaStream_t);
+int emb_fold(msgm_ctx*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int convt1d(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int embed_mlp(msgm_ctx*, const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
+              cudaStream_t);
+int normalize_log_radius(msgm_ctx*, const float*, float*, float*, int, int, cudaStream_t);
+
 static int invalid(const char* msg) {
   set_error(msg);
   return MSGM_ERR_INVALID;
@@ -240,6 +247,49 @@ int msgm_mmd_sums(msgm_ctx* ctx, const float* x, int64_t N, const float* y, int6
   if (!ctx || !x || !y || !sums_out || d < 1 || N < 1 || M < 1) return invalid("msgm_mmd_sums: bad argument");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return mmd_sums(ctx, x, N, y, M, d, sums_out, (cudaStream_t)stream);
+}
+
+int msgm_conv1d(msgm_ctx* ctx, const msgm_conv1d_desc* D, void* stream) {
+  if (!ctx || !D || !D->x1 || !D->W || !D->out) return invalid("msgm_conv1d: NULL argument");
+  if (D->K < 1 || D->K > 4 || D->stride < 1 || D->stride > 2 || D->B < 0 || D->Cout < 1 || D->C1 < 1 || D->Lin < 1 ||
+      D->Lout < 1)
+    return invalid("msgm_conv1d: unsupported shape (k <= 4, stride <= 2)");
+  if ((D->Cemb > 0) != (D->E != nullptr)) return invalid("msgm_conv1d: Cemb and E go together");
+  if (D->B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv1d(ctx, D, (cudaStream_t)stream);
+}
+
+int msgm_emb_fold(msgm_ctx* ctx, const float* W, const float* emb, float* E, int32_t Cw, int32_t Coff, int32_t Cemb,
+                  int32_t Cout, int32_t K, int32_t B, void* stream) {
+  if (!ctx || !W || !emb || !E || Cemb < 1 || Cout < 1 || K < 1 || B < 0) return invalid("msgm_emb_fold: bad argument");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return emb_fold(ctx, W, emb, E, Cw, Coff, Cemb, Cout, K, B, (cudaStream_t)stream);
+}
+
+int msgm_convt1d_k4s2(msgm_ctx* ctx, const float* x, const float* W, const float* bias, float* out, int32_t B, int32_t Cin,
+                      int32_t Cout, int32_t Lin, int32_t Lout, void* stream) {
+  if (!ctx || !x || !W || !bias || !out || Cin < 1 || Cout < 1 || Lin < 1 || Lout < 2 * Lin || B < 0)
+    return invalid("msgm_convt1d_k4s2: bad argument");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return convt1d(ctx, x, W, bias, out, B, Cin, Cout, Lin, Lout, (cudaStream_t)stream);
+}
+
+int msgm_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float* b1, const float* W2, const float* b2,
+                   float* out, int32_t B, int32_t E, int32_t accumulate, void* stream) {
+  if (!ctx || !t || !W1 || !b1 || !W2 || !b2 || !out || E < 1 || E > 256 || B < 0) return invalid("msgm_embed_mlp: bad argument");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return embed_mlp(ctx, t, W1, b1, W2, b2, out, B, E, accumulate, (cudaStream_t)stream);
+}
+
+int msgm_normalize_log_radius(msgm_ctx* ctx, const float* x, float* xn, float* lognorm, int32_t B, int32_t L, void* stream) {
+  if (!ctx || !x || !xn || !lognorm || L < 1 || B < 0) return invalid("msgm_normalize_log_radius: bad argument");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return normalize_log_radius(ctx, x, xn, lognorm, B, L, (cudaStream_t)stream);
 }
 
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {

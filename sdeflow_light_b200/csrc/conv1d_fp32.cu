@@ -1,0 +1,244 @@
+// 1-D convolution kernels for the UNet1D score net (NNUnet1D.py:13-179), fp32 CUDA cores (the reference is fp32).
+//
+// The reference concatenates the 128-channel time(+scale) embedding, constant along the signal, in front of every conv
+// block (NNUnet1D.py:81,90,102,156,162,175): for the first conv of a block that is 128 of its 129..384 input channels.
+// A channel that is constant along l contributes  sum_k W[co,ci,k] e[ci]  to every interior output position and loses
+// one tap at each zero-padded border, so those channels are folded into a per-(sample, out-channel, tap) table
+//     E[b,co,k] = sum_{ci in emb} W[co, C_real + ci, k] * emb[b,ci]
+// (emb_fold_kernel) and never materialised: 30-99 % fewer MACs in those layers and no (B,128,L) broadcast / concat.
+// The remaining real channels may come from two tensors (decoder: upsampled features + skip), again without a concat.
+//
+// conv1d_kernel       Conv1d  k in {1,3,4}, stride in {1,2}, zero padding, optional second input, optional folded
+//                     embedding, bias, optional exact (erf) GELU epilogue.  NCL layout, fp32.
+// convt1d_kernel      ConvTranspose1d k=4, stride=2, padding=1 (NNUnet1D.py:98) with right zero-pad to a given length.
+// embed_mlp_kernel    Linear(1,E) -> GELU -> Linear(E,E) of the time / log-radius embeddings (NNUnet1D.py:52-68).
+#include <algorithm>
+
+#include "msgm_common.cuh"
+
+namespace msgm {
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+constexpr int CT_CO = 32;    // output channels per CTA
+constexpr int CT_L = 128;    // output positions per CTA
+constexpr int CT_CI = 8;     // input channels per shared-memory stage
+
+struct Conv1dParams {
+  const float* x1; int C1;      // (B,C1,Lin)
+  const float* x2; int C2;      // (B,C2,Lin) or NULL
+  const float* W;               // (Cout, C1+C2+Cemb, K)
+  const float* bias;            // (Cout)
+  const float* E;               // (B,Cout,K) folded embedding or NULL
+  float* out;                   // (B,Cout,Lout)
+  int Cw;                       // C1 + C2 + Cemb: channel stride of W
+  int Cout, K, stride, pad, Lin, Lout, gelu;
+};
+
+__global__ void __launch_bounds__(256) conv1d_kernel(const __grid_constant__ Conv1dParams P) {
+  // grid: x = position tile, y = out-channel tile, z = sample
+  __shared__ float sx[CT_CI][CT_L * 2 + 8];       // input stage: positions l0*stride - pad .. (+ CT_L*stride + K)
+  __shared__ float sw[CT_CI][4][CT_CO + 1];        // weight stage: [ci][k][co]
+  const int tid = threadIdx.x;
+  const int tl = tid & 31, tc = tid >> 5;          // thread: positions tl + 32 j (j<4), out channels tc*4 + i (i<4)
+  const int l0 = blockIdx.x * CT_L, co0 = blockIdx.y * CT_CO, b = blockIdx.z;
+  const int span = (CT_L - 1) * P.stride + P.K;    // input positions needed by this tile
+  const int in0 = l0 * P.stride - P.pad;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  const int Creal = P.C1 + P.C2;
+  for (int c0 = 0; c0 < Creal; c0 += CT_CI) {
+    __syncthreads();
+    for (int e = tid; e < CT_CI * span; e += 256) {
+      const int ci = e / span, p = e % span, c = c0 + ci, li = in0 + p;
+      float v = 0.0f;
+      if (c < Creal && li >= 0 && li < P.Lin)
+        v = c < P.C1 ? P.x1[((size_t)b * P.C1 + c) * P.Lin + li] : P.x2[((size_t)b * P.C2 + (c - P.C1)) * P.Lin + li];
+      sx[ci][p] = v;
+    }
+    for (int e = tid; e < CT_CI * P.K * CT_CO; e += 256) {
+      const int co = e % CT_CO, k = (e / CT_CO) % P.K, ci = e / (CT_CO * P.K), c = c0 + ci;
+      sw[ci][k][co] = (c < Creal && co0 + co < P.Cout) ? P.W[((size_t)(co0 + co) * P.Cw + c) * P.K + k] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ci = 0; ci < CT_CI; ++ci) {
+      for (int k = 0; k < P.K; ++k) {
+        float wv[4], xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wv[i] = sw[ci][k][tc * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = sx[ci][(tl + 32 * j) * P.stride + k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + tc * 4 + i;
+    if (co >= P.Cout) continue;
+    const float bv = P.bias ? P.bias[co] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = l0 + tl + 32 * j;
+      if (l >= P.Lout) continue;
+      float v = acc[i][j] + bv;
+      if (P.E) {  // folded constant channels: a tap contributes unless it falls into the zero padding
+        for (int k = 0; k < P.K; ++k) {
+          const int li = l * P.stride - P.pad + k;
+          if (li >= 0 && li < P.Lin) v += P.E[((size_t)b * P.Cout + co) * P.K + k];
+        }
+      }
+      P.out[((size_t)b * P.Cout + co) * P.Lout + l] = P.gelu ? gelu_erf(v) : v;
+    }
+  }
+}
+
+// E[b,co,k] = sum_ci W[co, Coff + ci, k] * emb[b,ci]
+__global__ void __launch_bounds__(128) emb_fold_kernel(const float* __restrict__ W, const float* __restrict__ emb,
+                                                       float* __restrict__ E, int Cw, int Coff, int Cemb, int Cout, int K,
+                                                       int B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (b, co, k)
+  if (idx >= B * Cout * K) return;
+  const int k = idx % K, co = (idx / K) % Cout, b = idx / (K * Cout);
+  float s = 0.0f;
+  for (int ci = 0; ci < Cemb; ++ci) s = fmaf(W[((size_t)co * Cw + Coff + ci) * K + k], emb[(size_t)b * Cemb + ci], s);
+  E[idx] = s;
+}
+
+// ConvTranspose1d(k=4, s=2, p=1): out[b,co,l] = bias[co] + sum_ci sum_{k: (l+1-k) even, 0 <= (l+1-k)/2 < Lin} W[ci,co,k] x[b,ci,(l+1-k)/2]
+// Positions l >= 2*Lin (right zero padding up to Lout, NNUnet1D.py:168-169) are written as 0.
+__global__ void __launch_bounds__(256) convt1d_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                      const float* __restrict__ bias, float* __restrict__ out, int Cin,
+                                                      int Cout, int Lin, int Lout) {
+  __shared__ float sx[CT_CI][CT_L / 2 + 4];
+  __shared__ float sw[CT_CI][4][CT_CO + 1];
+  const int tid = threadIdx.x, tl = tid & 31, tc = tid >> 5;
+  const int l0 = blockIdx.x * CT_L, co0 = blockIdx.y * CT_CO, b = blockIdx.z;
+  const int m0 = l0 / 2 - 1;  // first input position needed: (l0 + 1 - 3) / 2
+  float acc[4][4] = {};
+  for (int c0 = 0; c0 < Cin; c0 += CT_CI) {
+    __syncthreads();
+    for (int e = tid; e < CT_CI * (CT_L / 2 + 2); e += 256) {
+      const int ci = e / (CT_L / 2 + 2), p = e % (CT_L / 2 + 2), c = c0 + ci, m = m0 + p;
+      sx[ci][p] = (c < Cin && m >= 0 && m < Lin) ? x[((size_t)b * Cin + c) * Lin + m] : 0.0f;
+    }
+    for (int e = tid; e < CT_CI * 4 * CT_CO; e += 256) {
+      const int co = e % CT_CO, k = (e / CT_CO) % 4, ci = e / (CT_CO * 4), c = c0 + ci;
+      sw[ci][k][co] = (c < Cin && co0 + co < Cout) ? W[((size_t)c * Cout + co0 + co) * 4 + k] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ci = 0; ci < CT_CI; ++ci) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int l = l0 + tl + 32 * j;
+        // even l: taps k=1 (m = l/2) and k=3 (m = l/2 - 1); odd l: k=0 (m = (l+1)/2) and k=2 (m = (l-1)/2)
+        const int ka = (l & 1) ? 0 : 1, kb = ka + 2;
+        const int ma = (l + 1 - ka) / 2 - m0, mb = (l + 1 - kb) / 2 - m0;
+        const float xa = sx[ci][ma], xb = sx[ci][mb];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(sw[ci][ka][tc * 4 + i], xa, fmaf(sw[ci][kb][tc * 4 + i], xb, acc[i][j]));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + tc * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = l0 + tl + 32 * j;
+      if (l < Lout) out[((size_t)b * Cout + co) * Lout + l] = l < 2 * Lin ? acc[i][j] + bias[co] : 0.0f;
+    }
+  }
+}
+
+// out[b,:] (+)= W2 gelu(W1 t[b] + b1) + b2,  W1 (E,1), W2 (E,E);  one CTA per sample, E <= 256
+__global__ void __launch_bounds__(256) embed_mlp_kernel(const float* __restrict__ t, const float* __restrict__ W1,
+                                                        const float* __restrict__ b1, const float* __restrict__ W2,
+                                                        const float* __restrict__ b2, float* __restrict__ out, int E,
+                                                        int accumulate) {
+  __shared__ float h[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < E) h[tid] = gelu_erf(fmaf(W1[tid], t[b], b1[tid]));
+  __syncthreads();
+  if (tid < E) {
+    float s = b2[tid];
+    for (int j = 0; j < E; ++j) s = fmaf(W2[(size_t)tid * E + j], h[j], s);
+    out[(size_t)b * E + tid] = accumulate ? out[(size_t)b * E + tid] + s : s;
+  }
+}
+
+// x -> x / (|x| + eps) * sqrt(L), lognorm = log(|x| + eps)   (NN.py:64-70 + NNUnet1D.py:139)
+__global__ void __launch_bounds__(256) normalize_log_radius_kernel(const float* __restrict__ x, float* __restrict__ xn,
+                                                                   float* __restrict__ lognorm, int L) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float sq = 0.0f;
+  for (int c = tid; c < L; c += 256) sq = fmaf(x[(size_t)b * L + c], x[(size_t)b * L + c], sq);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  __syncthreads();
+  float tot = 0.0f;
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float rn = sqrtf(tot) + 1e-6f, sc = sqrtf((float)L);
+  for (int c = tid; c < L; c += 256) xn[(size_t)b * L + c] = x[(size_t)b * L + c] / rn * sc;
+  if (tid == 0) lognorm[b] = logf(rn);
+}
+
+// ---- host wrappers -----------------------------------------------------------------------------------------------
+int conv1d(msgm_ctx* ctx, const msgm_conv1d_desc* D, cudaStream_t stream) {
+  Conv1dParams P{};
+  P.x1 = D->x1; P.C1 = D->C1; P.x2 = D->x2; P.C2 = D->x2 ? D->C2 : 0;
+  P.W = D->W; P.bias = D->bias; P.E = D->E; P.out = D->out;
+  P.Cw = D->C1 + P.C2 + D->Cemb;
+  P.Cout = D->Cout; P.K = D->K; P.stride = D->stride; P.pad = D->pad; P.Lin = D->Lin; P.Lout = D->Lout; P.gelu = D->gelu;
+  dim3 grid((D->Lout + CT_L - 1) / CT_L, (D->Cout + CT_CO - 1) / CT_CO, D->B);
+  conv1d_kernel<<<grid, 256, 0, stream>>>(P);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int emb_fold(msgm_ctx* ctx, const float* W, const float* emb, float* E, int Cw, int Coff, int Cemb, int Cout, int K, int B,
+             cudaStream_t stream) {
+  const int n = B * Cout * K;
+  emb_fold_kernel<<<(n + 127) / 128, 128, 0, stream>>>(W, emb, E, Cw, Coff, Cemb, Cout, K, B);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int convt1d(msgm_ctx* ctx, const float* x, const float* W, const float* bias, float* out, int B, int Cin, int Cout, int Lin,
+            int Lout, cudaStream_t stream) {
+  dim3 grid((Lout + CT_L - 1) / CT_L, (Cout + CT_CO - 1) / CT_CO, B);
+  convt1d_kernel<<<grid, 256, 0, stream>>>(x, W, bias, out, Cin, Cout, Lin, Lout);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float* b1, const float* W2, const float* b2, float* out,
+              int B, int E, int accumulate, cudaStream_t stream) {
+  embed_mlp_kernel<<<B, 256, 0, stream>>>(t, W1, b1, W2, b2, out, E, accumulate);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int normalize_log_radius(msgm_ctx* ctx, const float* x, float* xn, float* lognorm, int B, int L, cudaStream_t stream) {
+  normalize_log_radius_kernel<<<B, 256, 0, stream>>>(x, xn, lognorm, L);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+}  // namespace msgm

@@ -154,3 +154,19 @@ def test_unet2d_full_size_runs():
     out = P.rk4_stratonovich_sampler(gen, x0, 4, keep_all_samples=False, norm_correction=True, seed=3, device_out=True)
     assert torch.isfinite(out).all()
     assert float(((out.norm(dim=1) - x0.norm(dim=1)).abs() / x0.norm(dim=1)).max()) < 1e-5
+
+
+@pytest.mark.parametrize("L,B,pre", [(1000, 16, True), (125, 5, False), (257, 3, True)])
+def test_unet1d_kernel_path_matches_module_path(L, B, pre):
+    """Hand-written conv / GELU / embedding-fold kernels (inference path) vs the same module evaluated by torch's fp32
+    library path (the autograd path), at the driver's size and at odd lengths that exercise the decoder padding."""
+    torch.manual_seed(L)
+    net = P.UNet1D(L, premodule="NormalizeLogRadius" if pre else None).to(DEV)
+    x, t = torch.randn(B, L, device=DEV) * 1.3, torch.rand(B, device=DEV)
+    with torch.no_grad():
+        got = net(x, t)                       # kernels
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            ref = net._forward(x, t)          # torch modules
+    err = _rel(got, ref.cpu())
+    Bd.report(test=f"unet1d-kernels-L{L}", rel=err)
+    assert got.shape == (B, L) and err < 2e-5

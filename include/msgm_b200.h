@@ -176,6 +176,33 @@ int msgm_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float* 
 /* xn = x / (|x| + 1e-6) * sqrt(L), lognorm = log(|x| + 1e-6) per row (NN.py:64-70, NNUnet1D.py:136-139). */
 int msgm_normalize_log_radius(msgm_ctx* ctx, const float* x, float* xn, float* lognorm, int32_t B, int32_t L, void* stream);
 
+/* ---- 2-D U-Net score net layers (NNUnet.py:80-245, model/unet.py:40-517), fp32, NCHW ---------------------------------
+ * msgm_conv2d = nn.Conv2d 3x3 (padding 1, stride 1|2) or 1x1 over the channel concat [x1, x2] read in place, with
+ *   prologue 0: none | 1: GroupNorm (stats from msgm_gn_stats, affine gamma/beta) | 2: GroupNorm + SiLU applied while
+ *   the input tile is staged; up = 2 folds Upsample's nearest interpolation (model/unet.py:57-64) into the indexing;
+ *   epilogue adds bias[co], ebias[b,co] (ResBlock's embedding term, model/unet.py:181-192) and the residual tensor res. */
+typedef struct {
+  const float* x1; const float* x2; const float* W; const float* bias; const float* ebias; const float* res;
+  const float* stats; const float* gamma; const float* beta; float* out;
+  int32_t B, C1, C2, Cout, K, stride, up, Hs, Ws, G, prologue;
+} msgm_conv2d_desc;
+int msgm_conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* desc, void* stream);
+/* GroupNorm32 statistics (model/nn_utils.py:39-41,107-114): stats (B,G,2) = mean, 1/sqrt(var + 1e-5) of [x1, x2]. */
+int msgm_gn_stats(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G, int32_t B,
+                  float* stats, void* stream);
+/* out (B,Cout) = Linear(SiLU(emb)) : ResBlock.emb_layers. */
+int msgm_emb_proj(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int32_t E, int32_t Cout,
+                  int32_t B, void* stream);
+/* out (B,E) (+)= Linear(E,E)(SiLU(Linear(dim,E)(timestep_embedding(t, dim)))) : time_embed / scale_embed. */
+int msgm_sincos_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float* b1, const float* W2, const float* b2,
+                          float* out, int32_t B, int32_t dim, int32_t E, int32_t accumulate, void* stream);
+/* QKVAttention, single head: qkv (B,3C,T) -> out (B,C,T) = v softmax(q^T k / sqrt(C))^T (model/unet.py:236-250). */
+int msgm_attention(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32_t C, int32_t T, void* stream);
+/* VorticityUNet wrapper: flat (B,H*W) -> image (B,1,H,W) / 5 [after x/(|x|+eps)*sqrt(d) when pre] and back (x5). */
+int msgm_vort_pre(msgm_ctx* ctx, const float* x, float* img, float* lognorm, int32_t B, int32_t H, int32_t W, int32_t forder,
+                  int32_t pre, void* stream);
+int msgm_vort_post(msgm_ctx* ctx, const float* img, float* y, int32_t B, int32_t H, int32_t W, int32_t forder, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

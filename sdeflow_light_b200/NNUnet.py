@@ -40,6 +40,10 @@ class UNetModelWithLogNorm(UNetModel):
             ted = self.model_channels * 4
             self.scale_embed = nn.Sequential(nn.Linear(self.model_channels, ted), SiLU(), nn.Linear(ted, ted))
 
+    def forward_kernels(self, x, timesteps, log_norm=None):
+        emb = self.embedding_kernels(timesteps, log_norm, self.scale_embed if self.use_log_norm else None)
+        return self.run_blocks_kernels(x, emb)
+
     def forward(self, x, timesteps, y=None, log_norm: Optional[torch.Tensor] = None):
         emb = self.embedding(timesteps)
         if self.use_log_norm:
@@ -67,6 +71,9 @@ class VorticityUNet(nn.Module):
     def forward(self, x, t):
         if not x.is_cuda:
             raise RuntimeError("sdeflow_light_b200.NNUnet.VorticityUNet runs on CUDA only (no CPU fallback)")
+        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not needs_graph and x.dim() == 2:
+            return self._forward_kernels(x, t.view(-1))
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):  # the reference is fp32 end to end
             prev = torch.backends.cuda.matmul.allow_tf32
             torch.backends.cuda.matmul.allow_tf32 = False
@@ -74,6 +81,31 @@ class VorticityUNet(nn.Module):
                 return self._forward(x, t.view(-1))
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = prev
+
+    @torch.no_grad()
+    def _forward_kernels(self, x, t):
+        """Inference on the hand-written kernels: wrapper (normalise, x sqrt(d), / 5, reshape) -> U-Net -> x 5, flatten."""
+        import ctypes as C  # noqa: F401
+        from . import _lib
+        dev = x.device
+        h, L = _lib.ctx(dev), _lib.lib()
+        B, d = x.shape
+        S = self.in_space
+        assert d == S * S, f"Flat dim {d} != {S}*{S}"
+        xs = _lib.f32c(x, dev)
+        tt = _lib.f32c(t, dev)
+        if tt.numel() == 1 and B != 1:
+            tt = tt.expand(B).contiguous()
+        pre = self.pre is not None
+        img = torch.empty((B, 1, S, S), device=dev, dtype=torch.float32)
+        logn = torch.empty(B, device=dev, dtype=torch.float32) if pre else None
+        forder = int(self.flatten_order == "F")
+        _lib.check(L.msgm_vort_pre(h, _lib.ptr(xs), _lib.ptr(img), _lib.ptr(logn), B, S, S, forder, int(pre),
+                                   _lib.stream_ptr(dev)))
+        y_img = self.core.forward_kernels(img, tt, logn)
+        out = torch.empty((B, d), device=dev, dtype=torch.float32)
+        _lib.check(L.msgm_vort_post(h, _lib.ptr(y_img), _lib.ptr(out), B, S, S, forder, _lib.stream_ptr(dev)))
+        return out
 
     def _forward(self, x, t):
         log_norm = None

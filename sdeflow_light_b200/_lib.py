@@ -43,6 +43,11 @@ class Conv1dDesc(C.Structure):
                                                                  "Lin", "Lout", "gelu")]
 
 
+class Conv2dDesc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x1", "x2", "W", "bias", "ebias", "res", "stats", "gamma", "beta", "out")] + \
+               [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "stride", "up", "Hs", "Ws", "G", "prologue")]
+
+
 _lib = None
 _lock = threading.Lock()
 _ctx = {}
@@ -52,7 +57,9 @@ SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy",
            "msgm_sample_mlp", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward",
            "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums",
-           "msgm_conv1d", "msgm_emb_fold", "msgm_convt1d_k4s2", "msgm_embed_mlp", "msgm_normalize_log_radius"]
+           "msgm_conv1d", "msgm_emb_fold", "msgm_convt1d_k4s2", "msgm_embed_mlp", "msgm_normalize_log_radius",
+           "msgm_conv2d", "msgm_gn_stats", "msgm_emb_proj", "msgm_sincos_embed_mlp", "msgm_attention", "msgm_vort_pre",
+           "msgm_vort_post"]
 
 
 def lib() -> C.CDLL:
@@ -91,6 +98,13 @@ def lib() -> C.CDLL:
                 L.msgm_convt1d_k4s2.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]
                 L.msgm_embed_mlp.argtypes = [C.c_void_p] * 7 + [C.c_int32] * 3 + [C.c_void_p]
                 L.msgm_normalize_log_radius.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 2 + [C.c_void_p]
+                L.msgm_conv2d.argtypes = [C.c_void_p, C.POINTER(Conv2dDesc), C.c_void_p]
+                L.msgm_gn_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2
+                L.msgm_emb_proj.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_void_p]
+                L.msgm_sincos_embed_mlp.argtypes = [C.c_void_p] * 7 + [C.c_int32] * 4 + [C.c_void_p]
+                L.msgm_attention.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p]
+                L.msgm_vort_pre.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_void_p]
+                L.msgm_vort_post.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p]
                 L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]

@@ -41,6 +41,15 @@ int embed_mlp(msgm_ctx*, const float*, const float*, const float*, const float*,
               cudaStream_t);
 int normalize_log_radius(msgm_ctx*, const float*, float*, float*, int, int, cudaStream_t);
 
+int gn_stats(msgm_ctx*, const float*, int, const float*, int, int, int, int, float*, cudaStream_t);
+int conv2d(msgm_ctx*, const msgm_conv2d_desc*, cudaStream_t);
+int emb_proj(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+int sincos_embed_mlp(msgm_ctx*, const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
+                     int, cudaStream_t);
+int attention(msgm_ctx*, const float*, float*, int, int, int, cudaStream_t);
+int vort_pre(msgm_ctx*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+int vort_post(msgm_ctx*, const float*, float*, int, int, int, int, cudaStream_t);
+
 static int invalid(const char* msg) {
   set_error(msg);
   return MSGM_ERR_INVALID;
@@ -290,6 +299,75 @@ int msgm_normalize_log_radius(msgm_ctx* ctx, const float* x, float* xn, float* l
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return normalize_log_radius(ctx, x, xn, lognorm, B, L, (cudaStream_t)stream);
+}
+
+int msgm_conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* D, void* stream) {
+  if (!ctx || !D || !D->x1 || !D->W || !D->out) return invalid("msgm_conv2d: NULL argument");
+  if ((D->K != 1 && D->K != 3) || D->stride < 1 || D->stride > 2 || (D->up != 1 && D->up != 2) || D->Cout < 1 || D->C1 < 1 ||
+      D->Hs < 1 || D->Ws < 1 || D->B < 0)
+    return invalid("msgm_conv2d: unsupported shape (k in {1,3}, stride <= 2, up in {1,2})");
+  {  // the staged input tile (rows touched by 128 consecutive output positions x padded width) must fit the kernel's buffer
+    const int pad = D->K == 3 ? 1 : 0, wcols = D->Ws * D->up + 2 * pad;
+    const int Ho = (D->Hs * D->up + 2 * pad - D->K) / D->stride + 1, Wo = (D->Ws * D->up + 2 * pad - D->K) / D->stride + 1;
+    int span = (128 % Wo == 0) ? 128 / Wo - 1 : 127 / Wo + 1;
+    span = span < Ho - 1 ? span : Ho - 1;
+    if ((long long)(span * D->stride + D->K) * wcols > 17 * 34) {
+      set_error("msgm_conv2d: image too wide for the staged tile (built for the reference's 32x32 / 16x16 / 8x8 levels)");
+      return MSGM_ERR_UNSUPPORTED;
+    }
+  }
+  if (D->prologue && (!D->stats || !D->gamma || !D->beta || D->G < 1)) return invalid("msgm_conv2d: GroupNorm inputs missing");
+  if (D->B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv2d(ctx, D, (cudaStream_t)stream);
+}
+
+int msgm_gn_stats(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G, int32_t B,
+                  float* stats, void* stream) {
+  if (!ctx || !x1 || !stats || C1 < 1 || G < 1 || HW < 1 || B < 0) return invalid("msgm_gn_stats: bad argument");
+  if ((C1 + (x2 ? C2 : 0)) % G) return invalid("msgm_gn_stats: channels not divisible by groups");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return gn_stats(ctx, x1, C1, x2, C2, HW, G, B, stats, (cudaStream_t)stream);
+}
+
+int msgm_emb_proj(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int32_t E, int32_t Cout,
+                  int32_t B, void* stream) {
+  if (!ctx || !emb || !W || !bias || !out || E < 1 || Cout < 1 || B < 0) return invalid("msgm_emb_proj: bad argument");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return emb_proj(ctx, emb, W, bias, out, E, Cout, B, (cudaStream_t)stream);
+}
+
+int msgm_sincos_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float* b1, const float* W2, const float* b2,
+                          float* out, int32_t B, int32_t dim, int32_t E, int32_t accumulate, void* stream) {
+  if (!ctx || !t || !W1 || !b1 || !W2 || !b2 || !out || dim < 2 || dim > 64 || (dim & 1) || E < 1 || E > 256 || B < 0)
+    return invalid("msgm_sincos_embed_mlp: bad argument (even dim <= 64, E <= 256)");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return sincos_embed_mlp(ctx, t, W1, b1, W2, b2, out, B, dim, E, accumulate, (cudaStream_t)stream);
+}
+
+int msgm_attention(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32_t C, int32_t T, void* stream) {
+  if (!ctx || !qkv || !out || C < 1 || T < 1 || T > 4096 || B < 0) return invalid("msgm_attention: bad argument");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return attention(ctx, qkv, out, B, C, T, (cudaStream_t)stream);
+}
+
+int msgm_vort_pre(msgm_ctx* ctx, const float* x, float* img, float* lognorm, int32_t B, int32_t H, int32_t W, int32_t forder,
+                  int32_t pre, void* stream) {
+  if (!ctx || !x || !img || (pre && !lognorm) || H < 1 || W < 1 || B < 0) return invalid("msgm_vort_pre: bad argument");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return vort_pre(ctx, x, img, lognorm, B, H, W, forder, pre, (cudaStream_t)stream);
+}
+
+int msgm_vort_post(msgm_ctx* ctx, const float* img, float* y, int32_t B, int32_t H, int32_t W, int32_t forder, void* stream) {
+  if (!ctx || !img || !y || H < 1 || W < 1 || B < 0) return invalid("msgm_vort_post: bad argument");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return vort_post(ctx, img, y, B, H, W, forder, (cudaStream_t)stream);
 }
 
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {

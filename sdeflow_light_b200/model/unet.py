@@ -6,16 +6,21 @@ reference so that its checkpoints load: ``input_blocks.i.j.*``, ``middle_block.*
 zero conv3x3)`` with identity / 1x1 skip; AttentionBlock = GN -> 1x1 qkv -> single-head softmax(q k / sqrt(C)) v -> zero
 1x1 proj (+ residual); Up/Downsample = nearest x2 + conv3x3 / stride-2 conv3x3.
 
-Round-1 status: convolutions / GroupNorm / attention matmuls run through torch's GPU library calls (fp32, TF32 off);
-hand-written kernels for these layers are the next step.
+Inference (no autograd: the sampling hot path) runs on hand-written kernels (csrc/unet2d_fp32.cu, ``run_blocks_kernels``):
+GroupNorm statistics -> conv with normalise+SiLU fused into the input staging, embedding term / bias / residual fused
+into the epilogue, concatenations and nearest upsampling read in place, a small single-head attention kernel.  With
+autograd enabled (training) the same modules run through torch's fp32 library path so that autograd can trace them.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from .. import _lib
 
 
 class SiLU(nn.Module):
@@ -191,3 +196,115 @@ class UNetModel(nn.Module):
 
     def forward(self, x, timesteps, y=None):
         return self.run_blocks(x, self.embedding(timesteps))
+
+    # ---- hand-written kernel path (inference) -----------------------------------------------------------------------
+    @torch.no_grad()
+    def embedding_kernels(self, timesteps, log_norm=None, scale_embed=None):
+        dev = timesteps.device
+        h, L = _lib.ctx(dev), _lib.lib()
+        B, E = timesteps.shape[0], self.time_embed[2].weight.shape[0]
+        emb = torch.empty((B, E), device=dev, dtype=torch.float32)
+        for mlp, val, acc in ((self.time_embed, timesteps, 0), (scale_embed, log_norm, 1)):
+            if mlp is None:
+                continue
+            l1, l2 = mlp[0], mlp[2]
+            _lib.check(L.msgm_sincos_embed_mlp(h, _lib.ptr(_lib.f32c(val.reshape(-1), dev)), _lib.ptr(_lib.f32c(l1.weight, dev)),
+                                               _lib.ptr(_lib.f32c(l1.bias, dev)), _lib.ptr(_lib.f32c(l2.weight, dev)),
+                                               _lib.ptr(_lib.f32c(l2.bias, dev)), _lib.ptr(emb), B, self.model_channels, E, acc,
+                                               _lib.stream_ptr(dev)))
+        return emb
+
+    def _k_conv(self, dev, conv, x1, x2=None, gn=None, silu=True, ebias=None, res=None, up=1):
+        """conv over [x1, x2] with optional fused GroupNorm(+SiLU) prologue, embedding term and residual."""
+        h, L = _lib.ctx(dev), _lib.lib()
+        B, C1, Hs, Ws = x1.shape
+        C2 = 0 if x2 is None else x2.shape[1]
+        W = _lib.f32c(conv.weight, dev)
+        Cout, K = W.shape[0], W.shape[-1]
+        bias = None if conv.bias is None else _lib.f32c(conv.bias, dev)
+        stride = conv.stride[0]
+        stats = gamma = beta = None
+        G = 0
+        if gn is not None:
+            G = gn.num_groups
+            stats = torch.empty((B, G, 2), device=dev, dtype=torch.float32)
+            _lib.check(L.msgm_gn_stats(h, _lib.ptr(x1), C1, _lib.ptr(x2), C2, Hs * Ws, G, B, _lib.ptr(stats),
+                                       _lib.stream_ptr(dev)))
+            gamma, beta = _lib.f32c(gn.weight, dev), _lib.f32c(gn.bias, dev)
+        pad = 1 if K == 3 else 0
+        Ho, Wo = (Hs * up + 2 * pad - K) // stride + 1, (Ws * up + 2 * pad - K) // stride + 1
+        out = torch.empty((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
+        p = lambda t_: None if t_ is None else t_.data_ptr()  # noqa: E731
+        d = _lib.Conv2dDesc(p(x1), p(x2), p(W), p(bias), p(ebias), p(res), p(stats), p(gamma), p(beta), p(out), B, C1, C2,
+                            Cout, K, stride, up, Hs, Ws, G, 0 if gn is None else (2 if silu else 1))
+        _lib.check(L.msgm_conv2d(h, C.byref(d), _lib.stream_ptr(dev)))
+        return out
+
+    def _k_resblock(self, dev, blk, x1, x2, emb):
+        h, L = _lib.ctx(dev), _lib.lib()
+        B, E = emb.shape
+        lin = blk.emb_layers[1]
+        eb = torch.empty((B, blk.out_channels), device=dev, dtype=torch.float32)
+        _lib.check(L.msgm_emb_proj(h, _lib.ptr(emb), _lib.ptr(_lib.f32c(lin.weight, dev)), _lib.ptr(_lib.f32c(lin.bias, dev)),
+                                   _lib.ptr(eb), E, blk.out_channels, B, _lib.stream_ptr(dev)))
+        h1 = self._k_conv(dev, blk.in_layers[2], x1, x2, gn=blk.in_layers[0], ebias=eb)
+        if isinstance(blk.skip_connection, nn.Identity):
+            skip = x1  # channels unchanged: the block input is a single tensor
+        else:
+            skip = self._k_conv(dev, blk.skip_connection, x1, x2)
+        return self._k_conv(dev, blk.out_layers[3], h1, gn=blk.out_layers[0], res=skip)
+
+    def _k_attention(self, dev, blk, x):
+        h, L = _lib.ctx(dev), _lib.lib()
+        B, Cc, Hh, Ww = x.shape
+        qkv = self._k_conv(dev, _as2d(blk.qkv), x, gn=blk.norm, silu=False)
+        att = torch.empty((B, Cc, Hh, Ww), device=dev, dtype=torch.float32)
+        _lib.check(L.msgm_attention(h, _lib.ptr(qkv), _lib.ptr(att), B, Cc, Hh * Ww, _lib.stream_ptr(dev)))
+        return self._k_conv(dev, _as2d(blk.proj_out), att, res=x)
+
+    def _k_sequential(self, dev, seq, x1, x2, emb):
+        cur, second = x1, x2
+        for layer in seq:
+            if isinstance(layer, ResBlock):
+                cur = self._k_resblock(dev, layer, cur, second, emb)
+            elif isinstance(layer, AttentionBlock):
+                cur = self._k_attention(dev, layer, cur)
+            elif isinstance(layer, Downsample):
+                cur = self._k_conv(dev, layer.op, cur)
+            elif isinstance(layer, Upsample):
+                cur = self._k_conv(dev, layer.conv, cur, up=2)
+                if layer.odd_size:
+                    cur = cur[..., :-1, :-1].contiguous()
+            elif isinstance(layer, nn.Conv2d):
+                cur = self._k_conv(dev, layer, cur, second)
+            else:
+                raise NotImplementedError(type(layer).__name__)
+            second = None
+        return cur
+
+    @torch.no_grad()
+    def run_blocks_kernels(self, x, emb):
+        dev = x.device
+        if self.num_heads != 1 or not self.conv_resample:
+            raise NotImplementedError("kernel path is built for the driver's configuration (1 head, learned resampling)")
+        skips, cur = [], _lib.f32c(x, dev)
+        for blk in self.input_blocks:
+            cur = self._k_sequential(dev, blk, cur, None, emb)
+            skips.append(cur)
+        cur = self._k_sequential(dev, self.middle_block, cur, None, emb)
+        for blk in self.output_blocks:
+            cur = self._k_sequential(dev, blk, cur, skips.pop(), emb)
+        return self._k_conv(dev, self.out[2], cur, gn=self.out[0])
+
+
+class _Conv1x1View:
+    """Conv1d(k=1) over (B,C,T) presented as a 1x1 Conv2d to the conv kernel wrapper."""
+
+    def __init__(self, conv1d):
+        self.weight = conv1d.weight.unsqueeze(-1)
+        self.bias = conv1d.bias
+        self.stride = (1, 1)
+
+
+def _as2d(conv1d):
+    return _Conv1x1View(conv1d)

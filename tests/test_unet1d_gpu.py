@@ -170,3 +170,22 @@ def test_unet1d_kernel_path_matches_module_path(L, B, pre):
     err = _rel(got, ref.cpu())
     Bd.report(test=f"unet1d-kernels-L{L}", rel=err)
     assert got.shape == (B, L) and err < 2e-5
+
+
+@pytest.mark.parametrize("S,B,pre,order", [(32, 8, True, "F"), (16, 5, False, "C")])
+def test_unet2d_kernel_path_matches_module_path(S, B, pre, order):
+    """Hand-written GroupNorm-stats / fused conv2d / attention / embedding kernels (inference path) vs the same module
+    evaluated by torch's fp32 library path, at the driver's 32x32 configuration."""
+    net = _build_unet2d(S, "NormalizeLogRadius" if pre else None, order, 77).to(DEV)
+    torch.manual_seed(S)
+    x, t = torch.randn(B, S * S, device=DEV) * 2.0, torch.rand(B, device=DEV)
+    with torch.no_grad():
+        got = net(x, t)                                   # kernels
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            ref = net._forward(x, t)                      # torch modules
+            torch.backends.cuda.matmul.allow_tf32 = prev
+    err = _rel(got, ref.cpu())
+    Bd.report(test=f"unet2d-kernels-{S}x{S}", rel=err)
+    assert got.shape == (B, S * S) and err < 5e-5

@@ -311,7 +311,7 @@ int msgm_conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* D, void* stream) {
     const int Ho = (D->Hs * D->up + 2 * pad - D->K) / D->stride + 1, Wo = (D->Ws * D->up + 2 * pad - D->K) / D->stride + 1;
     int span = (128 % Wo == 0) ? 128 / Wo - 1 : 127 / Wo + 1;
     span = span < Ho - 1 ? span : Ho - 1;
-    if ((long long)(span * D->stride + D->K) * wcols > 17 * 34) {
+    if ((long long)(span * D->stride + D->K) * wcols > (D->K == 3 ? 17 * 34 : 160)) {
       set_error("msgm_conv2d: image too wide for the staged tile (built for the reference's 32x32 / 16x16 / 8x8 levels)");
       return MSGM_ERR_UNSUPPORTED;
     }

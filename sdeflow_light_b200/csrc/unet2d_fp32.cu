@@ -63,79 +63,99 @@ struct Conv2dParams {
   int Cout, K, stride, up, Hs, Ws, Ho, Wo;  // Hs, Ws: stored input size; the conv sees (Hs*up, Ws*up)
 };
 
+// Thread = a strip of 4 consecutive output columns of one output row x NCO output channels: the three horizontal taps of
+// a 3x3 filter share the 6 (stride 1) / 9 (stride 2) staged inputs of the strip, weights come as broadcast float4s.
+// CTA = 32 strips (128 output positions, row-major) x 8 channel groups (COT = 32 or 64 output channels); CI input channels
+// are staged per shared-memory round (8 for 3x3, 32 for 1x1 where a channel's tile is only 128 floats).
+template <int K, int STRIDE, int COT, int CI>
 __global__ void __launch_bounds__(256) conv2d_kernel(const __grid_constant__ Conv2dParams P) {
-  __shared__ float sx[C2_CI][C2_STAGE];
-  __shared__ float sw[C2_CI][9][C2_CO + 1];
-  const int tid = threadIdx.x, tl = tid & 31, tc = tid >> 5;
-  const int p0 = blockIdx.x * C2_P, co0 = blockIdx.y * C2_CO, b = blockIdx.z;
-  const int Hi = P.Hs * P.up, Wi = P.Ws * P.up, pad = P.K == 3 ? 1 : 0, KK = P.K * P.K;
+  constexpr int KK = K * K, PAD = K == 3 ? 1 : 0, NIN = 3 * STRIDE + K, NCO = COT / 8;
+  constexpr int XS = K == 3 ? C2_STAGE : 160;  // floats staged per input channel
+  __shared__ __align__(16) float sx[CI * XS];
+  __shared__ __align__(16) float sw[CI][KK][COT + 4];  // +4: the transposing store is 4-way instead of 32-way conflicted
+  const int tid = threadIdx.x, strip = tid & 31, cg = tid >> 5;
+  const int p0 = blockIdx.x * C2_P, co0 = blockIdx.y * COT, b = blockIdx.z;
+  const int Hi = P.Hs * P.up, Wi = P.Ws * P.up;
   const int HWo = P.Ho * P.Wo, HWs = P.Hs * P.Ws;
-  // input rows covered by this tile of output positions
   const int oy0 = p0 / P.Wo, oy1 = min(P.Ho - 1, (p0 + C2_P - 1) / P.Wo);
-  const int iy0 = oy0 * P.stride - pad, rows = (oy1 - oy0) * P.stride + P.K, wcols = Wi + 2 * pad;
-  int oy[4], ox[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int p = min(p0 + tl + 32 * j, HWo - 1);
-    oy[j] = p / P.Wo - oy0;
-    ox[j] = p % P.Wo;
-  }
-  float acc[4][4] = {};
+  const int iy0 = oy0 * STRIDE - PAD, rows = (oy1 - oy0) * STRIDE + K, wcols = Wi + 2 * PAD;
+  const int pstrip = p0 + strip * 4;                       // first output position of this strip (Wo % 4 == 0)
+  const bool live = pstrip < HWo;
+  const int oy = live ? pstrip / P.Wo - oy0 : 0, ox = live ? pstrip % P.Wo : 0;
+  const int xbase = (oy * STRIDE) * wcols + ox * STRIDE;
+  float acc[NCO][4] = {};
   const int Cin = P.C1 + P.C2, cpg = P.G > 0 ? Cin / P.G : 1;
-  for (int c0 = 0; c0 < Cin; c0 += C2_CI) {
+  for (int c0 = 0; c0 < Cin; c0 += CI) {
     __syncthreads();
-    for (int e = tid; e < C2_CI * rows * wcols; e += 256) {
-      const int ci = e / (rows * wcols), r = (e / wcols) % rows, cx = e % wcols, c = c0 + ci;
-      const int iy = iy0 + r, ix = cx - pad;
-      float v = 0.0f;
-      if (c < Cin && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) {
-        const int sy = iy / P.up, sxx = ix / P.up;
-        v = c < P.C1 ? P.x1[((size_t)b * P.C1 + c) * HWs + sy * P.Ws + sxx]
-                     : P.x2[((size_t)b * P.C2 + (c - P.C1)) * HWs + sy * P.Ws + sxx];
+    // ---- stage CI input channels: rows x wcols patch, normalise(+SiLU) fused, zero padding after the activation
+    for (int cr = tid / 32; cr < CI * rows; cr += 8) {   // one warp per (channel, row)
+      const int ci = cr / rows, r = cr % rows, c = c0 + ci, iy = iy0 + r;
+      const bool rowok = c < Cin && iy >= 0 && iy < Hi;
+      float mean = 0.f, rstd = 1.f, ga = 1.f, be = 0.f;
+      const float* src = nullptr;
+      if (rowok) {
+        src = (c < P.C1 ? P.x1 + ((size_t)b * P.C1 + c) * HWs : P.x2 + ((size_t)b * P.C2 + (c - P.C1)) * HWs) + (iy / P.up) * P.Ws;
         if (P.prologue) {
-          const float mean = P.stats[((size_t)b * P.G + c / cpg) * 2], rstd = P.stats[((size_t)b * P.G + c / cpg) * 2 + 1];
-          v = fmaf((v - mean) * rstd, P.gamma[c], P.beta[c]);
-          if (P.prologue == 2) v = siluf(v);
+          mean = P.stats[((size_t)b * P.G + c / cpg) * 2];
+          rstd = P.stats[((size_t)b * P.G + c / cpg) * 2 + 1];
+          ga = P.gamma[c];
+          be = P.beta[c];
         }
       }
-      sx[ci][r * wcols + cx] = v;
+      for (int cx = tid & 31; cx < wcols; cx += 32) {
+        const int ix = cx - PAD;
+        float v = 0.0f;
+        if (rowok && ix >= 0 && ix < Wi) {
+          v = src[ix / P.up];
+          if (P.prologue) {
+            v = fmaf((v - mean) * rstd, ga, be);
+            if (P.prologue == 2) v = siluf(v);
+          }
+        }
+        sx[ci * XS + r * wcols + cx] = v;
+      }
     }
-    for (int e = tid; e < C2_CI * KK * C2_CO; e += 256) {
-      const int co = e % C2_CO, k = (e / C2_CO) % KK, ci = e / (C2_CO * KK), c = c0 + ci;
+    for (int e = tid; e < CI * KK * COT; e += 256) {
+      const int k = e % KK, ci = (e / KK) % CI, co = e / (KK * CI), c = c0 + ci;  // k fastest: coalesced over W
       sw[ci][k][co] = (c < Cin && co0 + co < P.Cout) ? P.W[((size_t)(co0 + co) * Cin + c) * KK + k] : 0.0f;
     }
     __syncthreads();
+#pragma unroll 4
+    for (int ci = 0; ci < CI; ++ci) {
 #pragma unroll
-    for (int ci = 0; ci < C2_CI; ++ci) {
-      for (int ky = 0; ky < P.K; ++ky)
-        for (int kx = 0; kx < P.K; ++kx) {
-          float wv[4], xv[4];
+      for (int ky = 0; ky < K; ++ky) {
+        float xin[NIN];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) wv[i] = sw[ci][ky * P.K + kx][tc * 4 + i];
+        for (int q = 0; q < NIN; ++q) xin[q] = sx[ci * XS + xbase + ky * wcols + q];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) xv[j] = sx[ci][(oy[j] * P.stride + ky) * wcols + ox[j] * P.stride + kx];
+        for (int kx = 0; kx < K; ++kx) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int h4 = 0; h4 < NCO / 4; ++h4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&sw[ci][ky * K + kx][cg * NCO + h4 * 4]);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[h4 * 4 + i][j] = fmaf(wv[i], xin[j * STRIDE + kx], acc[h4 * 4 + i][j]);
+          }
         }
+      }
     }
   }
+  if (!live) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int co = co0 + tc * 4 + i;
+  for (int i = 0; i < NCO; ++i) {
+    const int co = co0 + cg * NCO + i;
     if (co >= P.Cout) continue;
     float add = P.bias ? P.bias[co] : 0.0f;
     if (P.ebias) add += P.ebias[(size_t)b * P.Cout + co];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int p = p0 + tl + 32 * j;
-      if (p >= HWo) continue;
-      const size_t o = ((size_t)b * P.Cout + co) * HWo + p;
-      float v = acc[i][j] + add;
-      if (P.res) v += P.res[o];
-      P.out[o] = v;
+    const size_t o = ((size_t)b * P.Cout + co) * HWo + pstrip;
+    float4 v = make_float4(acc[i][0] + add, acc[i][1] + add, acc[i][2] + add, acc[i][3] + add);
+    if (P.res) {
+      const float4 r4 = *reinterpret_cast<const float4*>(P.res + o);
+      v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
     }
+    *reinterpret_cast<float4*>(P.out + o) = v;
   }
 }
 
@@ -180,12 +200,16 @@ __global__ void __launch_bounds__(256) sincos_embed_mlp_kernel(const float* __re
 }
 
 // ---- single-head attention over T = H*W tokens (QKVAttention, model/unet.py:236-250) ---------------------------------
-// qkv (B, 3C, T) -> out (B, C, T).  One CTA per (sample, 16 queries).
-constexpr int AT_Q = 16;
+// qkv (B, 3C, T) -> out (B, C, T).  One CTA per (sample, 32 queries): S = q^T k / sqrt(C) by 64-key chunks with K staged
+// in shared memory (2 queries x 4 keys per thread), row softmax in shared memory, then out = V P^T with V staged per
+// 64-key chunk (thread = one query x C/8 channels).  S is kept transposed [key][query] (+1 pad) so that the P.V phase
+// reads it conflict-free.
+constexpr int AT_Q = 32, AT_K = 64;
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int C, int T) {
-  extern __shared__ float sm[];
-  float* sq = sm;                 // [C][AT_Q]
-  float* sc = sm + C * AT_Q;      // [AT_Q][T]
+  extern __shared__ __align__(16) float sm[];
+  float* sq = sm;                          // [C][AT_Q]
+  float* skv = sq + C * AT_Q;              // [C][AT_K]   K chunk, later V chunk
+  float* ss = skv + C * AT_K;              // [T][AT_Q + 1]
   const int b = blockIdx.y, t0 = blockIdx.x * AT_Q, tid = threadIdx.x;
   const float* q = qkv + (size_t)b * 3 * C * T;
   const float* k = q + (size_t)C * T;
@@ -195,33 +219,72 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
     const int c = e / AT_Q, tq = e % AT_Q;
     sq[e] = t0 + tq < T ? q[(size_t)c * T + t0 + tq] : 0.0f;
   }
-  __syncthreads();
-  const int tq = tid >> 4, sl = tid & 15;
-  for (int s = sl; s < T; s += 16) {
-    float d = 0.0f;
-    for (int c = 0; c < C; ++c) d = fmaf(sq[c * AT_Q + tq], k[(size_t)c * T + s], d);
-    sc[tq * T + s] = d * scale2;
+  const int tq2 = (tid >> 4) * 2, tk4 = (tid & 15) * 4;
+  for (int s0 = 0; s0 < T; s0 += AT_K) {
+    __syncthreads();
+    for (int e = tid; e < C * AT_K; e += 256) {
+      const int c = e / AT_K, sk = e % AT_K;
+      skv[e] = s0 + sk < T ? k[(size_t)c * T + s0 + sk] : 0.0f;
+    }
+    __syncthreads();
+    float d[2][4] = {};
+    for (int c = 0; c < C; ++c) {
+      const float2 q2 = *reinterpret_cast<const float2*>(sq + c * AT_Q + tq2);
+      const float4 k4 = *reinterpret_cast<const float4*>(skv + c * AT_K + tk4);
+      d[0][0] = fmaf(q2.x, k4.x, d[0][0]); d[0][1] = fmaf(q2.x, k4.y, d[0][1]);
+      d[0][2] = fmaf(q2.x, k4.z, d[0][2]); d[0][3] = fmaf(q2.x, k4.w, d[0][3]);
+      d[1][0] = fmaf(q2.y, k4.x, d[1][0]); d[1][1] = fmaf(q2.y, k4.y, d[1][1]);
+      d[1][2] = fmaf(q2.y, k4.z, d[1][2]); d[1][3] = fmaf(q2.y, k4.w, d[1][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (s0 + tk4 + j < T) ss[(s0 + tk4 + j) * (AT_Q + 1) + tq2 + i] = d[i][j] * scale2;
   }
   __syncthreads();
-  // softmax over s for each query row: 16 threads per row
-  float mx = -INFINITY;
-  for (int s = sl; s < T; s += 16) mx = fmaxf(mx, sc[tq * T + s]);
+  {  // softmax over keys for each query row: 8 threads per row
+    const int row = tid >> 3, sub = tid & 7;
+    float mx = -INFINITY;
+    for (int s = sub; s < T; s += 8) mx = fmaxf(mx, ss[s * (AT_Q + 1) + row]);
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.0f;
-  for (int s = sl; s < T; s += 16) {
-    const float e = expf(sc[tq * T + s] - mx);
-    sc[tq * T + s] = e;
-    sum += e;
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+    for (int s = sub; s < T; s += 8) {
+      const float e = expf(ss[s * (AT_Q + 1) + row] - mx);
+      ss[s * (AT_Q + 1) + row] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    __syncthreads();
+    for (int s = sub; s < T; s += 8) ss[s * (AT_Q + 1) + row] *= inv;
   }
+  // out[c][t] = sum_s P[t][s] V[c][s]: thread = query (lane) x channel group (warp): C/8 channels each, C <= 128
+  const int tq = tid & 31, cgp = tid >> 5, cpw = C / 8;
+  float acc[16];
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float inv = 1.0f / sum;
-  __syncthreads();
-  for (int c = sl; c < C; c += 16) {
-    float a = 0.0f;
-    for (int s = 0; s < T; ++s) a = fmaf(sc[tq * T + s], v[(size_t)c * T + s], a);
-    if (t0 + tq < T) out[((size_t)b * C + c) * T + t0 + tq] = a * inv;
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+  for (int s0 = 0; s0 < T; s0 += AT_K) {
+    __syncthreads();
+    for (int e = tid; e < C * AT_K; e += 256) {
+      const int c = e / AT_K, sk = e % AT_K;
+      skv[e] = s0 + sk < T ? v[(size_t)c * T + s0 + sk] : 0.0f;
+    }
+    __syncthreads();
+    const int smax = min(AT_K, T - s0);
+    for (int sk = 0; sk < smax; ++sk) {
+      const float p = ss[(s0 + sk) * (AT_Q + 1) + tq];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < cpw) acc[i] = fmaf(p, skv[(cgp * cpw + i) * AT_K + sk], acc[i]);
+    }
+  }
+  if (t0 + tq < T) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < cpw) out[((size_t)b * C + cgp * cpw + i) * T + t0 + tq] = acc[i];
   }
 }
 
@@ -282,8 +345,26 @@ int conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* D, cudaStream_t stream) {
   const int pad = D->K == 3 ? 1 : 0;
   P.Ho = (D->Hs * D->up + 2 * pad - D->K) / D->stride + 1;
   P.Wo = (D->Ws * D->up + 2 * pad - D->K) / D->stride + 1;
-  dim3 grid((P.Ho * P.Wo + C2_P - 1) / C2_P, (D->Cout + C2_CO - 1) / C2_CO, D->B);
-  conv2d_kernel<<<grid, 256, 0, stream>>>(P);
+  if (P.Wo % 4) {
+    set_error("msgm_conv2d: output width must be a multiple of 4");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  const bool wide = D->Cout >= 64;  // 64 output channels per CTA (8 per thread) when there are that many
+  dim3 grid((P.Ho * P.Wo + C2_P - 1) / C2_P, (D->Cout + (wide ? 64 : 32) - 1) / (wide ? 64 : 32), D->B);
+  if (D->K == 3 && D->stride == 1) {
+    if (wide) conv2d_kernel<3, 1, 64, 8><<<grid, 256, 0, stream>>>(P);
+    else conv2d_kernel<3, 1, 32, 8><<<grid, 256, 0, stream>>>(P);
+  } else if (D->K == 3) {
+    if (wide) conv2d_kernel<3, 2, 64, 8><<<grid, 256, 0, stream>>>(P);
+    else conv2d_kernel<3, 2, 32, 8><<<grid, 256, 0, stream>>>(P);
+  } else {
+    if (D->stride != 1) {
+      set_error("msgm_conv2d: 1x1 convolutions are built for stride 1");
+      return MSGM_ERR_UNSUPPORTED;
+    }
+    if (wide) conv2d_kernel<1, 1, 64, 32><<<grid, 256, 0, stream>>>(P);
+    else conv2d_kernel<1, 1, 32, 32><<<grid, 256, 0, stream>>>(P);
+  }
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;
@@ -306,7 +387,11 @@ int sincos_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float
 }
 
 int attention(msgm_ctx* ctx, const float* qkv, float* out, int B, int C, int T, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * ((size_t)C * AT_Q + (size_t)AT_Q * T);
+  const size_t smem = sizeof(float) * ((size_t)C * AT_Q + (size_t)C * AT_K + (size_t)T * (AT_Q + 1));
+  if (C % 8 || C > 128 || smem > 200 * 1024) {
+    set_error("msgm_attention: built for C in {8..128} multiple of 8 and T up to ~1000");
+    return MSGM_ERR_UNSUPPORTED;
+  }
   if (smem > 48 * 1024)
     MSGM_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_kernel<<<dim3((T + AT_Q - 1) / AT_Q, B), 256, smem, stream>>>(qkv, out, C, T);

@@ -158,7 +158,7 @@ def time_cpu_train(sde, mlp, data, batch: int, iters: int):
 def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev):
     """samples/s (all ranks) of gen.ssm(x).mean().backward(); [all-reduce]; Adam.step() on the fused SSM kernels."""
     from sdeflow_light_b200 import dist as D
-    opt = torch.optim.Adam(gen.parameters(), lr=1e-3)
+    opt = torch.optim.Adam([p for p in gen.parameters() if p.requires_grad], lr=1e-3, fused=True)
     params = [p for p in gen.parameters() if p.requires_grad]
 
     def step():

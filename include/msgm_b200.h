@@ -109,6 +109,16 @@ int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n);
 int msgm_sample_mlp(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp,
                     const msgm_sample_args* args, float* x_inout, int64_t B, void* stream);
 
+/* Forward noising for training, whole batch in ONE launch.  Replaces SDE.sample_scheme / MSGMsde.sample
+ * (SDEs.py:78-122,434-436): row k is integrated (RK4-Stratonovich, forward SDE, no radius correction) for
+ * n_k = trunc(N t_k / T) steps of size T/N and stops there; a row with n_k == 0 takes one step of size t_k instead.
+ * t (B,) device; y_inout (B,d) holds x on entry and y_t on exit.  noise (N,B,d) / noise_single (B,d) inject the normals
+ * of the common grid / of the one-step rows; NULL = in-kernel Philox keyed by (seed, particle_offset + row). */
+int msgm_noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, float* y_inout, int32_t num_steps_forward,
+                       const float* ts /* (N+1,) grid linspace(0,1,N+1)*T as the caller computed it, or NULL */,
+                       const float* noise, const float* noise_single, uint64_t seed, uint64_t particle_offset, int64_t B,
+                       void* stream);
+
 /* Stand-alone score-net forward a(y, s) -> (B,d) for NN.MLP.forward (NN.py:108-120); s is (B,). */
 int msgm_mlp_forward(msgm_ctx* ctx, const msgm_mlp_desc* mlp, const float* y, const float* s, float* out,
                      int64_t B, void* stream);

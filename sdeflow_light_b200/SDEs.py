@@ -82,9 +82,10 @@ class SDE(torch.nn.Module):
     def sample_scheme(self, t, y0, keep_all_samples, return_noise=False, *, noise=None, noise_rows=None):
         """y_t | y_0: the state after trunc(N_fwd t/T) RK4 steps; rows with 0 steps take ONE step of size t.
 
-        Two launches replace the reference's per-row Python loop: the whole batch with a per-row capture index,
-        then all zero-step rows together with a per-row horizon (args.T_rows).  ``noise`` (N_fwd,B,d) and
+        ONE launch (msgm_noise_forward) replaces the reference's batch sampler call plus its per-row Python loop of
+        one-sample sampler calls; states with d > 32 use the per-stage kernels in two passes.  ``noise`` (N_fwd,B,d) and
         ``noise_rows`` (n_zero_step_rows,d) inject the standard normals the reference would have drawn (parity tests).
+        (The reference's 'warning : t >= T' print is dropped: it would cost a host synchronisation per call.)
         """
         if return_noise:
             raise NotImplementedError('See the official repository.')
@@ -92,11 +93,32 @@ class SDE(torch.nn.Module):
         dev = self.device
         t = t.to(dev)
         y0 = y0.to(dev)
+        d = y0.shape[1]
+        if d <= 32:
+            import ctypes as C
+            handle = _lib.ctx(dev)
+            y = _lib.f32c(y0, dev).clone()
+            tt = _lib.f32c(t.reshape(-1), dev)
+            sd, keep = self.desc(dev)
+            if noise is not None:
+                noise = _lib.f32c(noise, dev)
+            single = None
+            if noise_rows is not None:  # (m,d) draws of the zero-step rows in index order -> (B,d) by row
+                n_int = torch.trunc(n_tot * t / self.T.to(dev)).to(torch.int).reshape(-1)
+                single = torch.zeros_like(y)
+                single[n_int == 0] = _lib.f32c(noise_rows, dev)
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            grid = getattr(self, "_fwd_grid", None)  # the reference's fp32 time grid (sde_scheme.py:201), cached on device
+            if grid is None or grid[0] != (n_tot, float(self.T.item()), str(dev)):
+                self._fwd_grid = ((n_tot, float(self.T.item()), str(dev)),
+                                  (torch.linspace(0, 1, n_tot + 1) * self.T.item()).to(dev))
+            _lib.check(_lib.lib().msgm_noise_forward(handle, C.byref(sd), _lib.ptr(tt), _lib.ptr(y), int(n_tot),
+                                                     _lib.ptr(self._fwd_grid[1]), _lib.ptr(noise), _lib.ptr(single), seed,
+                                                     0, y.shape[0], _lib.stream_ptr(dev)))
+            return y
+        # large states (U-Net configs): per-stage kernels, two passes
         n_int = torch.trunc(n_tot * t / self.T.to(dev)).to(torch.int).reshape(-1)
-        late = (t >= self.T.to(dev)).reshape(-1)
-        if bool(late.any()):
-            print('warning : t >= T')
-            n_int[late] = n_tot
+        n_int[(t >= self.T.to(dev)).reshape(-1)] = n_tot
         yt = self.sample_scheme_allt(y0, include_t0=True, keep_all_samples=False, samplesToKeep=n_int,
                                      _device_out=True, _noise=noise)
         small = (n_int == 0).nonzero().reshape(-1)

@@ -14,7 +14,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int sample_mlp_fp32(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const msgm_sample_args*, float*, int64_t,
-                    cudaStream_t);
+                    cudaStream_t, const float* t_noise = nullptr, const float* noise_single = nullptr);
 int sample_mlp_tc(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const msgm_sample_args*, float*, int64_t,
                   cudaStream_t);
 int mlp_forward_fp32(msgm_ctx*, const msgm_mlp_desc*, const float*, const float*, float*, int64_t, cudaStream_t);
@@ -368,6 +368,33 @@ int msgm_vort_post(msgm_ctx* ctx, const float* img, float* y, int32_t B, int32_t
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return vort_post(ctx, img, y, B, H, W, forder, (cudaStream_t)stream);
+}
+
+int msgm_noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, float* y_inout, int32_t num_steps_forward,
+                       const float* ts, const float* noise, const float* noise_single, uint64_t seed,
+                       uint64_t particle_offset, int64_t B, void* stream) {
+  if (!ctx || !sde || !t || !y_inout) return invalid("msgm_noise_forward: NULL argument");
+  if (sde->kind != MSGM_SDE_MSGM_DENSE && sde->kind != MSGM_SDE_MSGM_SPARSE)
+    return invalid("msgm_noise_forward: the additive SDE has a closed-form marginal (SDEs.py:134-146)");
+  if (sde->dim < 1 || sde->dim > MSGM_MAX_DIM_MLP) {
+    set_error("msgm_noise_forward: dim must be in [1,32] (larger states go through msgm_stage_update)");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (sde->kind == MSGM_SDE_MSGM_DENSE && (!sde->G || !sde->L_G)) return invalid("dense MSGM needs G and L_G");
+  if (num_steps_forward < 1) return invalid("num_steps_forward < 1");
+  if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  msgm_sample_args a{};
+  a.scheme = MSGM_SCHEME_RK4;
+  a.num_steps = num_steps_forward;
+  a.forward_only = 1;
+  a.precision = MSGM_PREC_FP32;
+  a.T_ = -1.0f;
+  a.ts = ts;
+  a.noise = noise;
+  a.seed = seed;
+  a.particle_offset = particle_offset;
+  return sample_mlp_fp32(ctx, sde, nullptr, &a, y_inout, B, (cudaStream_t)stream, t, noise_single);
 }
 
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {

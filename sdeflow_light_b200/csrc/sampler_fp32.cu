@@ -40,6 +40,8 @@ struct SampleParams {
   const int* keep_step;
   float* keep_out;
   const float* T_rows;
+  const float* t_noise;       // noising mode: per-row noise time t_k (SDEs.py:78-122), see msgm_noise_forward
+  const float* noise_single;  // noising mode: (B,d) normals of the one-step rows, or NULL
   float* x;
   long long B;
 };
@@ -208,21 +210,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) sample_fp32_kernel(const __grid_c
       delta_half = (float)(dd * 0.5);
       sqrt_delta = (float)sqrt(dd);
     }
+    // noising mode (SDE.sample_scheme, SDEs.py:86-118): row k stops after n_k = trunc(N t_k / T) steps of the common
+    // grid; a row with n_k == 0 takes ONE step of size t_k instead (the reference's per-row sampler call with T_ = t[k]).
+    int my_steps = P.N;
+    bool single = false;
+    if (P.t_noise) {
+      const float tk = live ? P.t_noise[gp] : 0.0f;
+      const int nk = tk >= P.Tsde ? P.N : (int)truncf(__fdiv_rn(__fmul_rn((float)P.N, tk), P.Tsde));
+      single = nk == 0;
+      my_steps = single ? 1 : nk;
+      if (single) {
+        delta = tk;                       // T_/1 with T_ = t_k
+        delta_half = (float)((double)tk * 0.5);
+        sqrt_delta = (float)sqrt((double)tk);
+      }
+    }
     const float c_a = delta * (1.0f - 0.5f * lm);  // weight of a in w
 
     for (int step = 0; step < P.N; ++step) {
-      const float tcur = P.T_rows ? __fmul_rn(__ldg(P.ts + step), Trow)
-                                   : (P.ts ? __ldg(P.ts + step) : __fmul_rn((float)step, delta));
+      const bool active = step < my_steps;
+      const float tcur = single ? 0.0f
+                                : (P.T_rows ? __fmul_rn(__ldg(P.ts + step), Trow)
+                                            : (P.ts ? __ldg(P.ts + step) : __fmul_rn((float)step, delta)));
       // ---- Wiener increment, shared by all stages of the step (sde_scheme.py:227) --------------------------
 #pragma unroll
       for (int m = 0; m < NC; ++m) {
         const int c = c0 + 4 * m;
         float xi = 0.0f;
         if (c < d) {
-          if (P.noise) {
+          if (single && P.noise_single) {
+            xi = (live && step == 0) ? __ldg(P.noise_single + gp * d + c) : 0.0f;
+          } else if (P.noise && !(single && P.t_noise)) {
             xi = live ? __ldg(P.noise + ((long long)step * P.B + gp) * d + c) : 0.0f;
           } else {
-            float4 z = philox_normal4(P.seed, P.poff + (unsigned long long)gp, (uint32_t)step, (uint32_t)m);
+            // one-step rows draw from their own stream id so that they do not reuse step 0 of the common grid
+            float4 z = philox_normal4(P.seed, P.poff + (unsigned long long)gp, single ? 0xFFFF0002u : (uint32_t)step, (uint32_t)m);
             xi = c0 == 0 ? z.x : (c0 == 1 ? z.y : (c0 == 2 ? z.z : z.w));
           }
         }
@@ -360,6 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sample_fp32_kernel(const __grid_c
         // ---- Runge-Kutta bookkeeping (sde_scheme.py:86 | 147,156 | 232-253) ----------------------------------
 #pragma unroll
         for (int m = 0; m < NC; ++m) {
+          if (!active) K[m] = 0.0f;  // noising mode: this row has already reached its noise time
           if (nstage == 1) {
             x[m] = x[m] + K[m];
           } else if (nstage == 2) {
@@ -524,7 +547,7 @@ static int launch_sample_kind(msgm_ctx* ctx, int kind, const SampleParams& P, cu
 }
 
 int sample_mlp_fp32(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const msgm_sample_args* a,
-                    float* x, int64_t B, cudaStream_t stream) {
+                    float* x, int64_t B, cudaStream_t stream, const float* t_noise, const float* noise_single) {
   SampleParams P{};
   const int d = sde->dim;
   P.d = d;
@@ -558,6 +581,8 @@ int sample_mlp_fp32(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc
   P.keep_step = a->keep_step;
   P.keep_out = a->keep_out;
   P.T_rows = a->T_rows;
+  P.t_noise = t_noise;
+  P.noise_single = noise_single;
   P.x = x;
   P.B = B;
   const int DP = d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32;

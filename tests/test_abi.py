@@ -35,6 +35,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.SdeDesc) == 40
     assert ctypes.sizeof(_lib.MlpDesc) == 8 + 8 * 8
     assert ctypes.sizeof(_lib.SampleArgs) == 32 + 8 * 8
+    assert ctypes.sizeof(_lib.Conv1dDesc) == 6 * 8 + 11 * 4 + 4   # 11 int32 + tail padding to 8
+    assert ctypes.sizeof(_lib.Conv2dDesc) == 10 * 8 + 11 * 4 + 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

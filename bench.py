@@ -46,6 +46,16 @@ def flop_per_particle_step(d: int, pre: int, dense: bool, scheme: str = "rk4") -
     return STAGES[scheme] * (f_net + ((2 * d ** 3 + 4 * d ** 2) if dense else 0))
 
 
+def load_traffic(workload: str, precision: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this exact workload."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.isfile(p):
+        ent = json.load(open(p)).get(f"{workload}/{precision}")
+        if ent:
+            return ent["traffic_bytes"]
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -332,7 +342,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["src"],
+                         "frac": achieved / peaks["tflops"],
+                         "traffic": load_traffic(workload_config(args, "gpu")["workload"], args.precision),
+                         "algorithmic_bytes": 8 * args.dim * B, "peak_source": peaks["src"],
                          "kernel": "sample_fp32_kernel" if args.precision == "fp32" else "sample_tc_kernel",
                          "flop_per_launch": fl, "kernel_ms": kms},
         }

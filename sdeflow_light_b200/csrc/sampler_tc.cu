@@ -83,6 +83,7 @@ struct TcParams {
   long long B;
   int* flags;  // [0] = wait timeout seen
   long long* prof;  // NULL or 24 cycle counters (see Prof)
+  uint32_t smem_base;  // shared-window address of the dynamic smem block, as a launch-uniform value (see smem_base_probe)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
@@ -319,9 +320,16 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
     // barrier.  Measured on B200 this beats a single-lane issue branch and one issuer warp per slot.
     constexpr int NLAYER = L4_CC ? 3 : 4;  // MMA layers per stage
     const uint32_t lead = lane == 0 ? 1u : 0u;
-    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
-    const uint32_t sbase = smem_u32(smem);
+    // Descriptor operands must be warp-uniform for ptxas to feed UTCHMMA from uniform registers without a per-MMA
+    // "waterfall" loop: the smem base comes in as a kernel parameter and the TMEM base of a 512-column allocation is 0.
+    // Both assumptions are verified here; a mismatch raises the debug flag instead of computing garbage.
+    const uint32_t tb = 0u;
+    const uint32_t sbase = P.smem_base;
     bool ok = mbar_wait(bar_w, 0, P.flags);
+    if (tbase != 0u || sbase != smem_u32(smem)) {
+      if (lane == 0) atomicExch(P.flags, 2);
+      ok = false;
+    }
     const uint32_t idesc_h = umma_idesc_f16(128, 128), idesc_o = umma_idesc_f16(128, 16);
     // descriptors of K-slice s are base + s * (slice bytes >> 4): only the 14-bit address field moves
     const uint64_t ones_desc = umma_desc(sbase + L::oOnes, 2048, 128);
@@ -334,27 +342,30 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
     constexpr bool TCG = L::TCG && KIND == MSGM_SDE_MSGM_DENSE;
     Prof pf{(P.prof && blockIdx.x == 0 && lane == 0) ? P.prof + 8 : nullptr, 0};
     pf.start();
-    // per-slot progress: number of layers issued so far, and how many the slot will need in total
-    long long done[NSLOT], total[NSLOT];
-    long long remaining = 0;
+    // Static cyclic schedule: (stage-iteration, layer, slot) in a fixed order, blocking on that slot's "operand ready"
+    // barrier.  The slots run the same program with the same period, so they fall into a staggered pipeline and the
+    // fixed order costs nothing, while the issue code stays free of data-dependent branches: the warp is converged at
+    // every tcgen05.mma, descriptors are launch-uniform, and ptxas feeds them from uniform registers (measured with
+    // tools/tc_probe.cu: 74 clk per MMA issued this way vs 96-113 from a single-lane branch).
+    long long iters[NSLOT];
+    long long max_iters = 0;
 #pragma unroll
     for (int sl = 0; sl < NSLOT; ++sl) {
       const long long first = (long long)blockIdx.x * NSLOT + sl;
       const long long nt = first < ntiles ? (ntiles - first + tstride - 1) / tstride : 0;
-      done[sl] = 0;
-      total[sl] = nt * P.N * nstage * NLAYER;
-      remaining += total[sl];
+      iters[sl] = nt * P.N * nstage;
+      max_iters = iters[sl] > max_iters ? iters[sl] : max_iters;
     }
-    long long idle_since = clock64();
-    while (remaining > 0 && ok) {
-      bool progressed = false;
+    uint32_t par = 0;  // all slot barriers flip once per layer, in lock step with this loop
+    for (long long it = 0; it < max_iters && ok; ++it) {
 #pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) {
-        if (done[sl] < total[sl]) {
-          const int ready = __shfl_sync(0xffffffffu, (int)mbar_try(bar_a + sl, (uint32_t)(done[sl] & 1)), 0);
-          if (ready) {
+      for (int layer = 0; layer < NLAYER; ++layer) {
+#pragma unroll
+        for (int sl = 0; sl < NSLOT; ++sl) {
+          if (it < iters[sl] && ok) {
+            ok = mbar_wait(bar_a + sl, par, P.flags);
             tc_fence_after();
-            const int layer = (int)(done[sl] % NLAYER);
+            pf.tick(0);  // waiting for an operand
             const uint32_t dcol = tb + 128 * sl;
             const uint64_t a_desc = umma_desc(sbase + L::oA + sl * A_BYTES, 2048, 128);
             if (layer == 0) {  // layer 1: K1/16 slices, bias rides in the padding of the last one
@@ -376,21 +387,10 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
               }
             }
             umma_commit(bar_d + sl, lead);
-            done[sl] += 1;
-            remaining -= 1;
-            progressed = true;
             pf.tick(1);  // issue
           }
         }
-      }
-      if (progressed) {
-        idle_since = clock64();
-      } else {
-        pf.tick(0);  // polling with nothing ready
-        if (clock64() - idle_since > 400000000LL || *reinterpret_cast<volatile int*>(P.flags) != 0) {
-          if (lane == 0) atomicExch(P.flags, 1);
-          ok = false;
-        }
+        par ^= 1;
       }
     }
     __syncwarp();
@@ -741,6 +741,12 @@ __global__ void pack_mlp_tc_kernel(int d, int pre, const float* W0, const float*
   (void)K1;
 }
 
+// Shared-window address of the dynamic shared memory block for kernels without static __shared__ data.
+__global__ void smem_base_probe(uint32_t* out) {
+  extern __shared__ __align__(128) unsigned char probe_smem[];
+  if (threadIdx.x == 0) *out = smem_u32(probe_smem);
+}
+
 // ---- host dispatch ---------------------------------------------------------------------------------------------------
 static int ensure_ws(msgm_ctx* ctx, size_t need) {
   if (ctx->ws_bytes >= need) return MSGM_OK;
@@ -767,6 +773,17 @@ static int launch_tc(msgm_ctx* ctx, const msgm_mlp_desc* m, TcParams& P, cudaStr
   MSGM_CUDA_TRY(cudaGetLastError());
   auto kern = sample_tc_kernel<DP, KIND>;
   MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES));
+  static uint32_t smem_base_cached = 0xFFFFFFFFu;
+  if (smem_base_cached == 0xFFFFFFFFu) {  // once per process: where does a dynamic-smem-only kernel's block start?
+    uint32_t* dptr = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ctx->ws) + 8);
+    smem_base_probe<<<1, 32, 1024, stream>>>(dptr);
+    MSGM_CUDA_TRY(cudaGetLastError());
+    uint32_t h = 0;
+    MSGM_CUDA_TRY(cudaMemcpyAsync(&h, dptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    MSGM_CUDA_TRY(cudaStreamSynchronize(stream));
+    smem_base_cached = h;
+  }
+  P.smem_base = smem_base_cached;
   const long long ntiles = (P.B + TM - 1) / TM;
   const int grid = (int)std::min<long long>((ntiles + L::NSLOT - 1) / L::NSLOT, (long long)ctx->num_sms);
   kern<<<grid, L::THREADS, L::SMEM_BYTES, stream>>>(P);

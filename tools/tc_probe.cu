@@ -218,6 +218,67 @@ probe_mma(const __half* __restrict__ Aimg, const __half* __restrict__ Arow, cons
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
 }
 
+// ---- issue patterns: how fast can 64 SS MMAs be issued? ------------------------------------------------------------------
+__device__ __forceinline__ void mma_ss_pred(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc, uint32_t lead) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(lead)
+      : "memory");
+}
+// mode 0: one lane in a divergent branch, descriptors rebuilt per MMA; 1: same, descriptors = base + s*256;
+// mode 2: converged warp, instruction predicated on lane 0; 3: one lane, 4 MMAs per descriptor pair reused (no desc math)
+__global__ void __launch_bounds__(128, 1) probe_issue(int mode, long long* cycles, int* err) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 65536);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 65536 / 16; i += 128) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t idesc = make_idesc(128, 128);
+  const uint32_t sA = smem_u32(smem_raw), sB = sA + 32768;
+  long long t0 = 0, t1 = 0;
+  if (warp == 1) {
+    t0 = clock64();
+    if (mode == 2) {
+      const uint32_t lead = lane == 0;
+      const uint64_t a0 = make_desc(sA, 2048, 128), b0 = make_desc(sB, 2048, 128);
+      for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2) mma_ss_pred(tbase, a0 + s2 * 256, b0 + s2 * 256, idesc, s2 > 0, lead);
+      t1 = clock64();
+      if (lane == 0) mma_commit(bar);
+    } else if (lane == 0) {
+      const uint64_t a0 = make_desc(sA, 2048, 128), b0 = make_desc(sB, 2048, 128);
+      for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+        for (int s2 = 0; s2 < 8; ++s2) {
+          if (mode == 0) mma_ss(tbase, make_desc(sA + s2 * 4096, 2048, 128), make_desc(sB + s2 * 4096, 2048, 128), idesc, s2 > 0);
+          else if (mode == 1) mma_ss(tbase, a0 + s2 * 256, b0 + s2 * 256, idesc, s2 > 0);
+          else mma_ss(tbase, a0, b0, idesc, s2 > 0);
+        }
+      t1 = clock64();
+      mma_commit(bar);
+    }
+  }
+  bool ok = mbar_wait_bounded(bar, 0, err);
+  long long t2 = clock64();
+  if (warp == 1 && lane == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t0; }
+  (void)ok;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
+}
+
 // ---- MUFU throughput ---------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256) probe_mufu(float* out, int iters) {
@@ -395,6 +456,19 @@ int main() {
     CK(cudaMemcpy(cyc, dcyc, sizeof(cyc), cudaMemcpyDeviceToHost));
     printf("mma-rate %s N=%d: 64 MMAs issue=%lld clk, issue->complete=%lld clk  (%.1f clk/MMA)\n", (variant & 1) ? "SS" : "TS",
            (variant & 16) ? 64 : ((variant & 32) ? 32 : 128), cyc[4], cyc[1], cyc[1] / 64.0);
+  }
+  {
+    CK(cudaFuncSetAttribute(probe_issue, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 64));
+    const char* mn[4] = {"one lane, desc rebuilt", "one lane, desc = base + s*256", "converged warp, @lane0 predicate", "one lane, same desc (no math)"};
+    for (int mode = 0; mode < 4; ++mode) {
+      CK(cudaMemset(derr, 0, sizeof(int)));
+      probe_issue<<<1, 128, 65536 + 64>>>(mode, dcyc, derr);
+      CK(cudaDeviceSynchronize());
+      long long cyc[8];
+      CK(cudaMemcpy(cyc, dcyc, sizeof(cyc), cudaMemcpyDeviceToHost));
+      printf("issue-pattern SS N=128 (%s): 64 MMAs issued in %lld clk (%.1f/MMA), complete after %lld clk\n", mn[mode], cyc[0],
+             cyc[0] / 64.0, cyc[1]);
+    }
   }
   run_mufu<0>("tanh.approx.f32", 8);
   run_mufu<1>("tanh.approx.f16x2 (x2 elems)", 8);

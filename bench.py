@@ -191,7 +191,7 @@ def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev):
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
-    return world * batch * iters / (ms / 1e3), ms / iters, (P._lib.launch_count(dev) - l0) / iters, float(loss)
+    return world * batch * iters / (ms / 1e3), ms / iters, (P._lib.launch_count(dev) - l0) / iters, float(loss.detach())
 
 
 def run_reference(args, rank):

@@ -165,24 +165,35 @@ def time_cpu_train(sde, mlp, data, batch: int, iters: int):
     return batch * iters / (time.perf_counter() - t0)
 
 
-def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev):
-    """samples/s (all ranks) of gen.ssm(x).mean().backward(); [all-reduce]; Adam.step() on the fused SSM kernels."""
+def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev, graphed: bool = False):
+    """samples/s (all ranks) of gen.ssm(x).mean().backward(); [all-reduce]; Adam.step() on the fused SSM kernels,
+    eagerly (the reference's loop verbatim) or replayed as a CUDA graph (sdeflow_light_b200.train.GraphedSsmStep)."""
+    import torch.distributed as dist
     from sdeflow_light_b200 import dist as D
-    opt = torch.optim.Adam([p for p in gen.parameters() if p.requires_grad], lr=1e-3, fused=True)
     params = [p for p in gen.parameters() if p.requires_grad]
+    if graphed:
+        from sdeflow_light_b200.train import GraphedSsmStep
+        gstep = GraphedSsmStep(gen, (batch, data_dev.shape[1]), lr=1e-3)
 
-    def step():
-        opt.zero_grad(set_to_none=False)
-        x = data_dev[torch.randint(0, data_dev.shape[0], (batch,), device=dev)]
-        loss = gen.ssm(x).mean()
-        loss.backward()
-        D.allreduce_grads_(params)
-        opt.step()
-        return loss
+        def step():
+            return gstep(data_dev[torch.randint(0, data_dev.shape[0], (batch,), device=dev)])
+    else:
+        opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+
+        def step():
+            opt.zero_grad(set_to_none=False)
+            x = data_dev[torch.randint(0, data_dev.shape[0], (batch,), device=dev)]
+            loss = gen.ssm(x).mean()
+            loss.backward()
+            D.allreduce_grads_(params)
+            opt.step()
+            return loss
 
     for _ in range(5):
         step()
     torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     l0 = P._lib.launch_count(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -191,7 +202,12 @@ def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev):
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
-    return world * batch * iters / (ms / 1e3), ms / iters, (P._lib.launch_count(dev) - l0) / iters, float(loss.detach())
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    n_launch = gstep.launches_per_iter if graphed else (P._lib.launch_count(dev) - l0) / iters
+    return world * batch * iters / (ms / 1e3), ms / iters, n_launch, float(loss.detach())
 
 
 def run_reference(args, rank):
@@ -321,11 +337,11 @@ def main():
     gen.train()
     train = {"metric": "ssm_train_samples_per_sec", "unit": "samples/s", "precision": "fp32",
              "step": "gen.ssm(x).mean().backward(); flat-grad all-reduce (N>1); torch.optim.Adam.step()", "runs": []}
-    for batch in (() if args.no_train else (256, 16384)):
-        v_, ms_, launches_, loss_ = time_gpu_train(P, gen, data_dev, batch, 20, world, dev)
-        train["runs"].append({"batch_per_gpu": batch, "value": v_, "ms_per_iter": ms_, "gpu_launches_per_iter": launches_,
-                              "loss": loss_})
-    train["value"] = train["runs"][-1]["value"] if train["runs"] else None
+    for batch, graphed in (() if args.no_train else ((256, False), (256, True), (16384, False), (16384, True))):
+        v_, ms_, launches_, loss_ = time_gpu_train(P, gen, data_dev, batch, 100 if graphed else 20, world, dev, graphed)
+        train["runs"].append({"batch_per_gpu": batch, "mode": "cuda_graph" if graphed else "eager", "value": v_,
+                              "ms_per_iter": ms_, "gpu_launches_per_iter": launches_, "loss": loss_})
+    train["value"] = max((r["value"] for r in train["runs"]), default=None)
 
     if rank == 0:
         peaks = load_peaks()

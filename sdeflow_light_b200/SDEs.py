@@ -74,12 +74,13 @@ class SDE(torch.nn.Module):
         d.kind, d.dim = self._kind(), int(getattr(self, "dim", 0))
         d.beta_min = float(self.beta_min)
         d.beta_delta = float(self.beta_max - self.beta_min)  # difference in double, as beta() does
-        d.T = float(self.T.item()) if torch.is_tensor(self.T) else float(self.T)
+        d.T = _lib.host_float(self, "T")
         return d, []
 
     # ---- forward noising by simulation (reference SDEs.py:78-132) ------------------------------------------------
     @torch.no_grad()
-    def sample_scheme(self, t, y0, keep_all_samples, return_noise=False, *, noise=None, noise_rows=None):
+    def sample_scheme(self, t, y0, keep_all_samples, return_noise=False, *, noise=None, noise_rows=None,
+                      _single=None):
         """y_t | y_0: the state after trunc(N_fwd t/T) RK4 steps; rows with 0 steps take ONE step of size t.
 
         ONE launch (msgm_noise_forward) replaces the reference's batch sampler call plus its per-row Python loop of
@@ -102,16 +103,16 @@ class SDE(torch.nn.Module):
             sd, keep = self.desc(dev)
             if noise is not None:
                 noise = _lib.f32c(noise, dev)
-            single = None
+            single = None if _single is None else _lib.f32c(_single, dev)  # (B,d): row k's draw if it takes 0 steps
             if noise_rows is not None:  # (m,d) draws of the zero-step rows in index order -> (B,d) by row
                 n_int = torch.trunc(n_tot * t / self.T.to(dev)).to(torch.int).reshape(-1)
                 single = torch.zeros_like(y)
                 single[n_int == 0] = _lib.f32c(noise_rows, dev)
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             grid = getattr(self, "_fwd_grid", None)  # the reference's fp32 time grid (sde_scheme.py:201), cached on device
-            if grid is None or grid[0] != (n_tot, float(self.T.item()), str(dev)):
-                self._fwd_grid = ((n_tot, float(self.T.item()), str(dev)),
-                                  (torch.linspace(0, 1, n_tot + 1) * self.T.item()).to(dev))
+            T_host = _lib.host_float(self, "T")
+            if grid is None or grid[0] != (n_tot, T_host, str(dev)):
+                self._fwd_grid = ((n_tot, T_host, str(dev)), (torch.linspace(0, 1, n_tot + 1) * T_host).to(dev))
             _lib.check(_lib.lib().msgm_noise_forward(handle, C.byref(sd), _lib.ptr(tt), _lib.ptr(y), int(n_tot),
                                                      _lib.ptr(self._fwd_grid[1]), _lib.ptr(noise), _lib.ptr(single), seed,
                                                      0, y.shape[0], _lib.stream_ptr(dev)))
@@ -438,11 +439,22 @@ class PluginReverseSDE(torch.nn.Module):
             raise NotImplementedError("ssm_intT=True raises NameError in the reference (SDEs.py:700); not built")
         with torch.no_grad():
             t_ = self.sample_t(x)
-            y = self.base_sde.sample(t_, x)
+            if getattr(self, "device_rng", False) and isinstance(self.base_sde, MSGMsde) and x.shape[1] <= 32:
+                # every draw from the CUDA generator, no host round trip: what train.GraphedSsmStep records
+                n = self.base_sde.num_steps_forward
+                y = self.base_sde.sample_scheme(t_, x, keep_all_samples=False,
+                                                noise=torch.randn(n, *x.shape, device=x.device),
+                                                _single=torch.randn(*x.shape, device=x.device))
+            else:
+                y = self.base_sde.sample(t_, x)
         return t_, x, y
 
     def sample_t(self, x):
-        t_ = torch.rand([x.size(0), ] + [1 for _ in range(x.ndim - 1)]).to(x) * self.T
+        shape = [x.size(0), ] + [1 for _ in range(x.ndim - 1)]
+        if getattr(self, "device_rng", False):
+            t_ = torch.rand(shape, device=x.device, dtype=x.dtype) * self.T
+        else:  # the reference draws on the host (SDEs.py:686); kept so that seeded runs consume the same CPU stream
+            t_ = torch.rand(shape).to(x) * self.T
         m = (t_ <= self.base_sde.t_epsilon).float()
         return m * self.base_sde.t_epsilon + (1. - m) * t_
 

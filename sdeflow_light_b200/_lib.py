@@ -171,5 +171,21 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def host_float(owner, name: str) -> float:
+    """``float(owner.<name>)`` without a device synchronisation per call: the value of a 1-element CUDA tensor (the
+    horizon ``T``) is read back once and cached on its owner until the tensor is replaced or written in place."""
+    t = getattr(owner, name)
+    if not torch.is_tensor(t):
+        return float(t)
+    if not t.is_cuda:
+        return float(t.item())
+    key = (id(t), t.data_ptr(), t._version)
+    cache = owner.__dict__.get("_hf_" + name)
+    if cache is None or cache[0] != key:
+        cache = (key, float(t.item()))
+        owner.__dict__["_hf_" + name] = cache
+    return cache[1]
+
+
 def f32c(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).contiguous()

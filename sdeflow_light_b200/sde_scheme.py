@@ -55,7 +55,7 @@ def _run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, inc
     device = sde.T.device
     handle = _lib.ctx(device)  # RuntimeError on CPU: there is no CPU fallback
     B, d = x_0.size(0), x_0.size(1)
-    T_run = sde.T.item() if (not torch.is_tensor(T_) and T_ == -1) else T_.item()
+    T_run = _lib.host_float(sde, "T") if (not torch.is_tensor(T_) and T_ == -1) else T_.item()
     if keep_all_samples is False and samplesToKeep is not None and len(samplesToKeep) != B:
         raise ValueError("Error: len(samplesToKeep) must correspond to batch size.")
     if (fwd and d > 32) or (not fwd and not (isinstance(net, NN.MLP) and net.fused_ok())):

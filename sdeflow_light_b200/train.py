@@ -1,0 +1,140 @@
+"""One score-matching training iteration as a CUDA graph.
+
+The reference's training loop (MSGM_higherDim.py:803-809) is
+
+    optim.zero_grad(); loss = gen_sde.ssm(x).mean(); loss.backward(); optim.step()
+
+At the reference's batch size (256) that iteration is a handful of ~10 us kernels and the host (Python, the allocator,
+~25 launches) is the bottleneck.  ``GraphedSsmStep`` records exactly that sequence once -- device-side draws of t, the
+forward-noising launch, the probe v, the fused SSM forward/backward kernels, the flat gradient all-reduce when several
+ranks train together, and the fused Adam update -- into CUDA graphs and replays them, one ``cudaGraphLaunch`` per
+iteration.  Every random draw inside the graph comes from torch's CUDA Philox generator, whose offset advances with
+each replay, so iterations see fresh t / noise / v.
+
+    step = GraphedSsmStep(gen_sde, lr=1e-3, batch_shape=(256, d))
+    for it in range(n):
+        loss = step(x_batch)        # x_batch: (256, d) tensor on the device (or host: copied into the static input)
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class _SsmModule(torch.nn.Module):
+    """``forward = gen.ssm`` so that torch.func.functional_call can run the loss on substitute parameter leaves."""
+
+    def __init__(self, gen):
+        super().__init__()
+        self.gen = gen
+
+    def forward(self, x):
+        return self.gen.ssm(x)
+
+
+class GraphedSsmStep:
+    def __init__(self, gen, batch_shape, lr: float = 1e-3, optimizer: torch.optim.Optimizer | None = None,
+                 warmup: int = 3, group=None):
+        dev = torch.device(gen.deviceReverseSDE)
+        if dev.type != "cuda":
+            raise RuntimeError("sdeflow_light_b200 runs on CUDA only (no CPU fallback)")
+        self.gen, self.dev, self.group = gen, dev, group
+        self._names = [n for n, p in gen.named_parameters() if p.requires_grad]
+        self.params = [p for n, p in gen.named_parameters() if p.requires_grad]
+        self._mod = _SsmModule(gen)
+        # lr lives in a device tensor so that schedulers can change it between replays (set_lr)
+        self.opt = optimizer if optimizer is not None else torch.optim.Adam(
+            self.params, lr=torch.tensor(float(lr), device=dev), fused=True, capturable=True)
+        for g in self.opt.param_groups:
+            if not g.get("capturable", False):
+                raise ValueError("the optimizer must be built with capturable=True to be replayed inside a CUDA graph")
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.x = torch.zeros(*batch_shape, device=dev, dtype=torch.float32)
+        self.loss = torch.zeros((), device=dev, dtype=torch.float32)
+        # every .grad is a view into ONE flat buffer: the all-reduce needs no gather/scatter, Adam reads it in place
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self._grads = [p.grad for p in self.params]
+        self.launches_per_iter = 0
+
+        gen.train()
+        was = getattr(gen, "device_rng", False)
+        gen.device_rng = True
+        # Warm-up runs real iterations (allocator pools, lazy module loads, optimizer state creation) on stand-in data:
+        # snapshot parameters and optimizer state, and put them back -- in place, the graphs hold the addresses.
+        saved_p = [p.detach().clone() for p in self.params]
+        saved_s = {id(q): {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
+                   for q, st in self.opt.state.items()}
+        self.x.normal_()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._fwd_bwd()
+                if self.world > 1:
+                    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                    self.flat /= self.world
+                self.opt.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+
+        l0 = _lib.launch_count(dev)
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self._fwd_bwd()
+            if self.world == 1:
+                self.opt.step()
+        self.g_opt = None
+        if self.world > 1:  # the collective stays outside the graphs: fwd/bwd graph -> all-reduce -> Adam graph
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt):
+                self.opt.step()
+        self.launches_per_iter = _lib.launch_count(dev) - l0
+        with torch.no_grad():
+            for p, q in zip(self.params, saved_p):
+                p.copy_(q)
+            for q, st in self.opt.state.items():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        old = saved_s.get(id(q), {}).get(k)
+                        v.copy_(old) if old is not None else v.zero_()
+        self.x.zero_()
+        gen.device_rng = was
+
+    # -- the recorded part of the iteration ---------------------------------------------------------------------
+    def _fwd_bwd(self):
+        # The loss runs on fresh leaves aliasing the parameters, and autograd.grad + one multi-tensor copy replaces
+        # .backward(): a parameter's AccumulateGrad node remembers the stream it was first used on, and one kept alive
+        # by an earlier eager iteration (a retained loss, a live optimizer) would tie this capture to the default stream.
+        leaves = [p.detach().requires_grad_(True) for p in self.params]
+        loss = torch.func.functional_call(self._mod, {"gen." + n: l for n, l in zip(self._names, leaves)},
+                                          (self.x,)).mean()
+        grads = torch.autograd.grad(loss, leaves)
+        torch._foreach_copy_(self._grads, list(grads))
+        self.loss.copy_(loss.detach())
+
+    def set_lr(self, lr: float):
+        """Change the learning rate seen by the recorded Adam update (in place, on the device)."""
+        for g in self.opt.param_groups:
+            if isinstance(g["lr"], torch.Tensor):
+                g["lr"].fill_(float(lr))
+            else:
+                raise ValueError("this optimizer was built with a Python-float lr, which the graph has baked in")
+
+    # -- one iteration -----------------------------------------------------------------------------------------
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """Run one iteration on batch ``x``; returns the (device, 0-dim) mean loss of this rank's shard."""
+        if x.shape != self.x.shape:
+            raise ValueError(f"batch shape {tuple(x.shape)} differs from the recorded {tuple(self.x.shape)}")
+        self.x.copy_(x, non_blocking=True)
+        self.g_fb.replay()
+        if self.g_opt is not None:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat /= self.world  # Adam reads the averaged gradient through the .grad views
+            self.g_opt.replay()
+        return self.loss

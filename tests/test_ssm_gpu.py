@@ -107,3 +107,64 @@ def test_ssm_end_to_end_trains():
             after = float(gen.ssm_loss(te, xe, ye, ve).mean())
         Bd.report(test=f"train-{make}", eval_loss_before=before, eval_loss_after=after)
         assert after < before - 0.005, (make, before, after)  # observed: msgm 0.003 -> -0.02, sgm 10.2 -> 0.7
+
+
+def test_graphed_train_step_matches_eager_and_trains():
+    """train.GraphedSsmStep replays the reference loop (MSGM_higherDim.py:803-809) as one CUDA graph: (1) with the
+    CUDA generator reseeded identically, a replay produces the same loss as the eager iteration;
+    (2) successive replays draw fresh t / noise / v; (3) training through replays reduces the held-out loss."""
+    from sdeflow_light_b200.train import GraphedSsmStep
+    d = 2
+    data = O.swiss_roll(4096).to(DEV)
+    T = Bd.T_param(1.0)
+    for make in ("msgm", "sgm"):
+        torch.manual_seed(1)
+
+        def build():
+            torch.manual_seed(1)
+            if make == "msgm":
+                base = P.MSGMsde(data.cpu(), beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=True,
+                                 norm_map="log", num_steps_forward=16, device=DEV, estim_cst_norm_dens_r_T=False)
+                net = P.MLP(d, premodule="NormalizeLogRadius").to(DEV)
+            else:
+                base = P.SGMsde(beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, num_steps_forward=16, device=DEV)
+                base.dim = d
+                net = P.MLP(d).to(DEV)
+            return P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
+
+        gen_g, gen_e = build(), build()
+        if make == "msgm":  # G is random: share it so both replicas integrate the same SDE
+            gen_e.base_sde.G, gen_e.base_sde.L_G = gen_g.base_sde.G, gen_g.base_sde.L_G
+        gen_e.load_state_dict(gen_g.state_dict())
+        step = GraphedSsmStep(gen_g, (256, d), lr=0.0)          # lr = 0 during warm-up: parameters stay equal
+        step.set_lr(2e-3)
+        opt_e = torch.optim.Adam(gen_e.parameters(), lr=2e-3)
+        gen_e.train()
+        gen_e.device_rng = True
+        x = data[:256]
+        torch.cuda.manual_seed(7)
+        l_g = float(step(x))
+        torch.cuda.manual_seed(7)
+        opt_e.zero_grad()
+        l = gen_e.ssm(x).mean()
+        l.backward()
+        l_e = float(l.detach())
+        Bd.report(test=f"graphed-vs-eager-{make}", loss_graph=l_g, loss_eager=l_e)
+        assert abs(l_g - l_e) <= 1e-5 + 1e-4 * abs(l_e), (make, l_g, l_e)  # observed: msgm identical, sgm 1.6e-5 rel
+        # (2) fresh randomness per replay
+        l2 = float(step(x))
+        assert l2 != l_g
+        # (3) trains
+        xe = data
+        te, _, ye = gen_g.sample_txy(xe)
+        ve = P.SDEs.sample_v(xe.shape, DEV)
+        with torch.no_grad():
+            before = float(gen_g.ssm_loss(te, xe, ye, ve).mean())
+        for it in range(200):
+            loss = step(data[torch.randint(0, 4096, (256,), device=DEV)])
+        assert bool(torch.isfinite(loss))
+        with torch.no_grad():
+            after = float(gen_g.ssm_loss(te, xe, ye, ve).mean())
+        Bd.report(test=f"graphed-train-{make}", eval_loss_before=before, eval_loss_after=after,
+                  own_launches_per_iter=step.launches_per_iter)
+        assert after < before - 0.005, (make, before, after)

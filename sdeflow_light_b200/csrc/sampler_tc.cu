@@ -203,6 +203,13 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
 }
+// Two fp32 values -> packed fp16 (hi, hi) and packed fp16 residuals (lo, lo).  Uses the paired conversion
+// (F2FP.PACK_AB) and HADD2.F32 only: the scalar cvt.f16.f32 is an XU-pipe op (F2F) and would queue behind the tanh stream.
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = pack_f16x2(a, b);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+  lo2 = pack_f16x2(a - f.x, b - f.y);
+}
 __device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
   return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
 }
@@ -481,38 +488,31 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
               u[DP] = 0.0f;
             }
             u[DP + 1] = sv;
-            __half hk[K1];
+            // K1/2 packed words: [hi pairs | lo pairs | hi pairs | (1,1) | 0...]  (MP is even)
+            static_assert(MP % 2 == 0, "layer-1 slots are packed in pairs");
+            uint32_t hw[K1 / 2];
 #pragma unroll
-            for (int k = 0; k < K1; ++k) hk[k] = __ushort_as_half(0);
+            for (int k = 0; k < K1 / 2; ++k) hw[k] = 0u;
 #pragma unroll
-            for (int j = 0; j < MP; ++j) {
-              __half hi, lo;
-              split_f16(u[j], hi, lo);
-              hk[j] = hi;
-              hk[MP + j] = lo;
-              hk[2 * MP + j] = hi;
+            for (int j = 0; j < MP / 2; ++j) {
+              uint32_t hi2, lo2;
+              split2_f16(u[2 * j], u[2 * j + 1], hi2, lo2);
+              hw[j] = hi2;
+              hw[MP / 2 + j] = lo2;
+              hw[MP + j] = hi2;
             }
-            hk[3 * MP] = __ushort_as_half(0x3C00);
-            hk[3 * MP + 1] = __ushort_as_half(0x3C00);
+            hw[3 * MP / 2] = 0x3C003C00u;
             unsigned char* base = sA + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
             for (int ch = 0; ch < K1 / 8; ++ch)
-              *reinterpret_cast<uint4*>(base + ch * 2048) =
-                  make_uint4(pack_h2(hk[8 * ch], hk[8 * ch + 1]), pack_h2(hk[8 * ch + 2], hk[8 * ch + 3]),
-                             pack_h2(hk[8 * ch + 4], hk[8 * ch + 5]), pack_h2(hk[8 * ch + 6], hk[8 * ch + 7]));
+              *reinterpret_cast<uint4*>(base + ch * 2048) = make_uint4(hw[4 * ch], hw[4 * ch + 1], hw[4 * ch + 2], hw[4 * ch + 3]);
           }
           if constexpr (L::TCG && KIND == MSGM_SDE_MSGM_DENSE) {
             // split stage input for the G . y product: k-index [y_hi | y_lo | y_hi | 0]
             unsigned char* gb = smem + L::oAg + sl * L::AG_BYTES + (row >> 3) * 128 + (row & 7) * 16;
             uint32_t hi2[4], lo2[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              __half h0, l0, h1, l1;
-              split_f16(y[2 * c], h0, l0);
-              split_f16(y[2 * c + 1], h1, l1);
-              hi2[c] = pack_h2(h0, h1);
-              lo2[c] = pack_h2(l0, l1);
-            }
+            for (int c = 0; c < 4; ++c) split2_f16(y[2 * c], y[2 * c + 1], hi2[c], lo2[c]);
             *reinterpret_cast<uint4*>(gb) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
             *reinterpret_cast<uint4*>(gb + 2048) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
             *reinterpret_cast<uint4*>(gb + 4096) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);

@@ -8,7 +8,8 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-N, B = 32, 148 * 4 * 128
+N = 32
+B = 148 * (4 if d <= 4 else 3) * 128  # one tile per slot
 sde, mlp = bench.build_problem(d)
 P, gen = bench.package_objects(sde, mlp, torch.device("cuda", 0))
 x0 = (torch.randn(B, d) * 1.5).cuda()
@@ -17,9 +18,11 @@ for _ in range(2):
                                device_out=True)
 c = P._lib.debug_counters("cuda:0")
 stages = 4 * N
-names = {0: "particle: SDE update + L1 operand", 1: "particle: wait for accumulators", 2: "particle: 3 epilogues",
-         3: "particle: output layer (tensor)", 8: "issuer: polling, nothing ready", 9: "issuer: issue"}
+names = {6: "particle: step boundary (re-pin, noise) /4", 7: "particle: L1 operand build + stores",
+         0: "particle: fence + arrive", 1: "particle: wait for accumulators", 2: "particle: 3 epilogues",
+         3: "particle: output layer (tensor)", 4: "particle: G.y read back", 5: "particle: stage increment + RK",
+         8: "issuer: waiting for an operand", 9: "issuer: issue"}
 print(f"d={d}: cycles per RK4 stage (CTA 0, flags={P._lib.debug_flags('cuda:0')})")
 for k, n in names.items():
     print(f"  {n:34s} {c[k] / stages:9.0f}")
-print(f"  particle total {sum(c[0:6]) / stages:9.0f}   issuer total {sum(c[8:13]) / stages:9.0f}")
+print(f"  particle total {sum(c[0:8]) / stages:9.0f}   issuer total {sum(c[8:13]) / stages:9.0f}")

@@ -15,6 +15,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 int sample_mlp_fp32(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const msgm_sample_args*, float*, int64_t,
                     cudaStream_t, const float* t_noise = nullptr, const float* noise_single = nullptr);
+int noise_forward(msgm_ctx*, const msgm_sde_desc*, const float*, float*, int, const float*, const float*, const float*,
+                  uint64_t, uint64_t, int64_t, cudaStream_t);
 int sample_mlp_tc(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const msgm_sample_args*, float*, int64_t,
                   cudaStream_t);
 int mlp_forward_fp32(msgm_ctx*, const msgm_mlp_desc*, const float*, const float*, float*, int64_t, cudaStream_t);
@@ -384,17 +386,8 @@ int msgm_noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, 
   if (num_steps_forward < 1) return invalid("num_steps_forward < 1");
   if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
-  msgm_sample_args a{};
-  a.scheme = MSGM_SCHEME_RK4;
-  a.num_steps = num_steps_forward;
-  a.forward_only = 1;
-  a.precision = MSGM_PREC_FP32;
-  a.T_ = -1.0f;
-  a.ts = ts;
-  a.noise = noise;
-  a.seed = seed;
-  a.particle_offset = particle_offset;
-  return sample_mlp_fp32(ctx, sde, nullptr, &a, y_inout, B, (cudaStream_t)stream, t, noise_single);
+  return noise_forward(ctx, sde, t, y_inout, num_steps_forward, ts, noise, noise_single, seed, particle_offset, B,
+                       (cudaStream_t)stream);
 }
 
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {

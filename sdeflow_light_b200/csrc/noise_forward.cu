@@ -1,0 +1,214 @@
+// Forward noising y_t | y_0 of the multiplicative SDE by simulation: SDE.sample_scheme (SDEs.py:78-122) =
+// rk4_stratonovich_sampler (sde_scheme.py:174-269) on the forward_SDE adapter (SDEs.py:30-47), all num_steps_forward
+// steps of every row in ONE launch.  This is the training-time prologue of the score-matching step.
+//
+// The forward Stratonovich drift of the MSGM SDE is zero (f_strato = 0), so a stage increment is pure diffusion:
+//     K_i = sqrt(beta(t_s)) * sum_{j,k} G_ijk y_j dW_k.
+// dW is shared by the four stages of a step (sde_scheme.py:227), so the k-contraction is hoisted out of the stage
+// loop:  M_ij = sum_k G_ijk dW_k  once per step (d^3 flop per particle), then K = sqrt(beta) M y per stage (d^2).
+// Work decomposition: DP = pow2(d) lanes per particle, lane i owns component i (row i of M, y_i); a stage gathers y
+// with DP warp shuffles.  A batch of 256 rows is 256*DP threads spread over many SMs instead of 4 CTAs of the fused
+// sampler kernel, and nothing but G lives in shared memory.
+//
+// Row semantics follow sampler_fp32.cu (the parity kernel): row k runs n_k = trunc(N t_k / T) steps of the common grid;
+// a row with n_k == 0 takes one step of size t_k; noise is injected (parity tests, CUDA-graphed training) or Philox.
+#include <algorithm>
+#include <cmath>
+
+#include "msgm_common.cuh"
+
+namespace msgm {
+
+struct NoiseParams {
+  int d, N;
+  float bmin, bdel, Tsde;
+  float delta, delta_half, sqrt_delta;
+  const float* G;             // dense: (d,d,d)
+  const float* ts;            // (N+1) fp32 time grid of the reference (sde_scheme.py:201)
+  const float* t_noise;       // (B) noise time of each row
+  const float* noise;         // (N,B,d) or NULL
+  const float* noise_single;  // (B,d) or NULL
+  unsigned long long seed, poff;
+  float* x;                   // (B,d) in/out
+  long long B;
+};
+
+template <int DP>
+struct GLayout {
+  static constexpr int SLAB = DP * DP + 4;  // floats per row-slab i, padded so that the DP lanes hit distinct banks
+  static constexpr size_t BYTES = sizeof(float) * DP * SLAB;
+};
+
+template <int DP, int KIND>
+__global__ void __launch_bounds__(128) noise_forward_kernel(const __grid_constant__ NoiseParams P) {
+  extern __shared__ __align__(16) float sG[];
+  constexpr int SLAB = GLayout<DP>::SLAB;
+  constexpr int PPB = 128 / DP;  // particles per block pass
+  const int tid = threadIdx.x;
+  const int i = tid % DP;        // component owned by this lane
+  const int d = P.d;
+  if (KIND == MSGM_SDE_MSGM_DENSE) {
+    for (int e = tid; e < DP * DP * DP; e += 128) {
+      const int a = e / (DP * DP), j = (e / DP) % DP, k = e % DP;
+      sG[a * SLAB + j * DP + k] = (a < d && j < d && k < d) ? __ldg(P.G + ((long long)a * d + j) * d + k) : 0.0f;
+    }
+    __syncthreads();
+  }
+  const unsigned full = 0xffffffffu;
+  const long long ngroups = (P.B + PPB - 1) / PPB;
+  for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const long long gp = grp * PPB + tid / DP;
+    const bool live = gp < P.B;
+    const bool mine = live && i < d;
+    float x = mine ? P.x[gp * d + i] : 0.0f;
+    float y = x, ks = 0.0f;
+
+    // row schedule (SDEs.py:86-118)
+    float delta = P.delta, delta_half = P.delta_half, sqrt_delta = P.sqrt_delta;
+    const float tk = live ? __ldg(P.t_noise + gp) : 0.0f;
+    const int nk = tk >= P.Tsde ? P.N : (int)truncf(__fdiv_rn(__fmul_rn((float)P.N, tk), P.Tsde));
+    const bool single = nk == 0;
+    const int my_steps = single ? 1 : nk;
+    if (single) {
+      delta = tk;
+      delta_half = (float)((double)tk * 0.5);
+      sqrt_delta = (float)sqrt((double)tk);
+    }
+    // the warp walks as many steps as its longest row needs
+    int steps_here = live ? my_steps : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) steps_here = max(steps_here, __shfl_xor_sync(full, steps_here, o));
+
+    for (int step = 0; step < steps_here; ++step) {
+      const bool active = step < my_steps;
+      const float tcur = single ? 0.0f : (P.ts ? __ldg(P.ts + step) : __fmul_rn((float)step, delta));
+      // ---- this lane's normal, then the whole increment vector by shuffles -------------------------------------
+      float xi = 0.0f;
+      if (i < d) {
+        if (single && P.noise_single) {
+          xi = (live && step == 0) ? __ldg(P.noise_single + gp * d + i) : 0.0f;
+        } else if (P.noise && !single) {
+          xi = live ? __ldg(P.noise + ((long long)step * P.B + gp) * d + i) : 0.0f;
+        } else {
+          const float4 z = philox_normal4(P.seed, P.poff + (unsigned long long)gp, single ? 0xFFFF0002u : (uint32_t)step,
+                                          (uint32_t)(i >> 2));
+          const int q = i & 3;
+          xi = q == 0 ? z.x : (q == 1 ? z.y : (q == 2 ? z.z : z.w));
+        }
+      }
+      const float dw = sqrt_delta * xi;
+
+      [[maybe_unused]] float M[DP];
+      [[maybe_unused]] float dw_prev = 0.0f;
+      if (KIND == MSGM_SDE_MSGM_DENSE) {
+        float dwv[DP];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) dwv[k] = __shfl_sync(full, dw, k, DP);
+        const float* Gi = sG + i * SLAB;
+#pragma unroll
+        for (int j = 0; j < DP; ++j) {
+          float m = 0.0f;
+          if constexpr (DP >= 4) {
+#pragma unroll
+            for (int k4 = 0; k4 < DP; k4 += 4) {
+              const float4 g4 = *reinterpret_cast<const float4*>(Gi + j * DP + k4);
+              m = fmaf(g4.x, dwv[k4], m);
+              m = fmaf(g4.y, dwv[k4 + 1], m);
+              m = fmaf(g4.z, dwv[k4 + 2], m);
+              m = fmaf(g4.w, dwv[k4 + 3], m);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < DP; ++k) m = fmaf(Gi[j * DP + k], dwv[k], m);
+          }
+          M[j] = m;
+        }
+      } else {
+        const int cp = (i == 0) ? d - 1 : i - 1;
+        dw_prev = __shfl_sync(full, dw, cp & (DP - 1), DP);
+      }
+
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        float tst = tcur;
+        if (st > 0) tst = st < 3 ? __fadd_rn(tcur, delta_half) : __fadd_rn(tcur, delta);
+        const float sb = sqrtf(beta_of(P.bmin, P.bdel, tst));
+        float K;
+        if (KIND == MSGM_SDE_MSGM_DENSE) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int j = 0; j < DP; ++j) acc = fmaf(M[j], __shfl_sync(full, y, j, DP), acc);
+          K = sb * acc;
+        } else {
+          // cyclic stencil of SDEs.py:369-399 with the runtime dimension d
+          const int cn = (i + 1 == d) ? 0 : i + 1, cp = (i == 0) ? d - 1 : i - 1;
+          const float yn = __shfl_sync(full, y, cn & (DP - 1), DP), yp = __shfl_sync(full, y, cp & (DP - 1), DP);
+          K = (SQRT_HALF * (sb * yn)) * dw + (-SQRT_HALF * (sb * yp)) * dw_prev;
+        }
+        if (!active || i >= d) K = 0.0f;
+        if (st == 0) { ks = K; y = x + K / 2.0f; }
+        else if (st == 1) { ks = ks + 2.0f * K; y = x + K / 2.0f; }
+        else if (st == 2) { ks = ks + 2.0f * K; y = x + K; }
+        else { x = x + (ks + K) / 6.0f; }
+      }
+      y = x;
+    }
+    if (mine) P.x[gp * d + i] = x;
+  }
+}
+
+template <int DP, int KIND>
+static int launch_noise(msgm_ctx* ctx, const NoiseParams& P, cudaStream_t stream) {
+  auto kern = noise_forward_kernel<DP, KIND>;
+  const size_t smem = KIND == MSGM_SDE_MSGM_DENSE ? GLayout<DP>::BYTES : 0;
+  if (smem > 48 * 1024) MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long ngroups = (P.B + 128 / DP - 1) / (128 / DP);
+  // G is re-staged per CTA: cap the grid where that staging would dominate (d > 8), otherwise one pass per CTA
+  const long long cap = (long long)ctx->num_sms * (DP >= 32 ? 1 : (DP >= 16 ? 8 : 64));
+  kern<<<(int)std::min<long long>(ngroups, cap), 128, smem, stream>>>(P);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+template <int DP>
+static int launch_noise_kind(msgm_ctx* ctx, int kind, const NoiseParams& P, cudaStream_t stream) {
+  if (kind == MSGM_SDE_MSGM_DENSE) return launch_noise<DP, MSGM_SDE_MSGM_DENSE>(ctx, P, stream);
+  return launch_noise<DP, MSGM_SDE_MSGM_SPARSE>(ctx, P, stream);
+}
+
+int noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, float* y_inout, int num_steps, const float* ts,
+                  const float* noise, const float* noise_single, uint64_t seed, uint64_t poff, int64_t B,
+                  cudaStream_t stream) {
+  NoiseParams P{};
+  const int d = sde->dim;
+  P.d = d;
+  P.N = num_steps;
+  P.bmin = sde->beta_min;
+  P.bdel = sde->beta_delta;
+  P.Tsde = sde->T;
+  // delta = T/N is a Python double in the reference (sde_scheme.py:200), rounded to fp32 where it meets tensors
+  const double delta = (double)sde->T / (double)num_steps;
+  P.delta = (float)delta;
+  P.delta_half = (float)(delta / 2.0);
+  P.sqrt_delta = (float)std::sqrt(delta);
+  P.G = sde->G;
+  P.ts = ts;
+  P.t_noise = t;
+  P.noise = noise;
+  P.noise_single = noise_single;
+  P.seed = seed;
+  P.poff = poff;
+  P.x = y_inout;
+  P.B = B;
+  const int DP = d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32;
+  switch (DP) {
+    case 2: return launch_noise_kind<2>(ctx, sde->kind, P, stream);
+    case 4: return launch_noise_kind<4>(ctx, sde->kind, P, stream);
+    case 8: return launch_noise_kind<8>(ctx, sde->kind, P, stream);
+    case 16: return launch_noise_kind<16>(ctx, sde->kind, P, stream);
+    default: return launch_noise_kind<32>(ctx, sde->kind, P, stream);
+  }
+}
+
+}  // namespace msgm

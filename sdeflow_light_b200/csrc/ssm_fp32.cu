@@ -110,8 +110,17 @@ __global__ void __launch_bounds__(SSM_THREADS, 1) ssm_forward_kernel(const __gri
   const int tid = threadIdx.x, ng = tid & 15, pg = tid >> 4;
   const int d = P.d, K1 = d + 1 + P.pre;
 
+  // W (torch layout [n][k]) -> [k][n].  A warp reads 8 rows x 64 contiguous bytes per request (every sector fully used;
+  // the element-wise transposing gather it replaces fetched each 32-byte sector eight times) and takes a 4-way bank
+  // conflict on the four scalar stores instead -- this prologue is what a 256-row batch mostly consists of.
   for (int l = 0; l < 2; ++l)
-    for (int e = tid; e < HID * HID; e += SSM_THREADS) sWh[l * HID * HID + e] = __ldg(P.W[1 + l] + (e & 127) * HID + (e >> 7));
+    for (int q = tid; q < HID * HID / 4; q += SSM_THREADS) {
+      const int kq = q & 3, ns = (q >> 2) & 7, r = q >> 5;
+      const int k = (r & 7) * 16 + 4 * kq, n = (r >> 3) * 8 + ns;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(P.W[1 + l] + n * HID + k));
+      float* dst = sWh + l * HID * HID + k * HID + n;
+      dst[0] = w.x; dst[HID] = w.y; dst[2 * HID] = w.z; dst[3 * HID] = w.w;
+    }
   for (int e = tid; e < K1 * HID; e += SSM_THREADS) sW1[e] = __ldg(P.W[0] + (e & 127) * K1 + (e >> 7));
   for (int e = tid; e < HID * DP32; e += SSM_THREADS) sW4[e] = (e & 31) < d ? __ldg(P.W[3] + (e & 31) * HID + (e >> 5)) : 0.0f;
   for (int e = tid; e < 3 * HID; e += SSM_THREADS) sB[e] = __ldg(P.b[e >> 7] + (e & 127));
@@ -356,14 +365,29 @@ __global__ void __launch_bounds__(256) ssm_wgrad_kernel(const __grid_constant__ 
   float bacc = 0.0f;  // bias partial: thread tid < 64 sums column tm+tid over primal rows
   const long long r_begin = (long long)blockIdx.z * P.rows_per_slice;
   const long long r_end = min(P.R, r_begin + P.rows_per_slice);
-  for (long long r0 = r_begin; r0 < r_end; r0 += 32) {
-    for (int e = tid; e < 32 * 64; e += 256) {
-      const int rr = e >> 6, cc = e & 63;
+  // 32-row chunks, software-pipelined through registers: the global loads of chunk c+1 are in flight while chunk c
+  // is multiplied out of shared memory (at the reference's batch of 256 a slice is only a few chunks long and the
+  // load latency would otherwise be the whole run time).
+  float pc[8], pu[8];
+  auto fetch = [&](long long r0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = tid + 256 * q, rr = e >> 6, cc = e & 63;
       const long long r = r0 + rr;
-      sC[rr][cc] = (r < r_end && tm + cc < J.M) ? J.cot[r * J.ldc + tm + cc] : 0.0f;
-      sU[rr][cc] = (r < r_end && tn + cc < J.N) ? J.u[r * J.ldu + tn + cc] : 0.0f;
+      pc[q] = (r < r_end && tm + cc < J.M) ? __ldg(J.cot + r * J.ldc + tm + cc) : 0.0f;
+      pu[q] = (r < r_end && tn + cc < J.N) ? __ldg(J.u + r * J.ldu + tn + cc) : 0.0f;
+    }
+  };
+  if (r_begin < r_end) fetch(r_begin);
+  for (long long r0 = r_begin; r0 < r_end; r0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = tid + 256 * q;
+      sC[e >> 6][e & 63] = pc[q];
+      sU[e >> 6][e & 63] = pu[q];
     }
     __syncthreads();
+    if (r0 + 32 < r_end) fetch(r0 + 32);
 #pragma unroll 8
     for (int rr = 0; rr < 32; ++rr) {
       float c4[4], u4[4];
@@ -465,7 +489,7 @@ int ssm_backward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* m
   W.R = 2 * B;
   const int max_slices = 64;
   long long rps = (W.R + max_slices - 1) / max_slices;
-  rps = std::max<long long>(512, (rps + 31) / 32 * 32);
+  rps = std::max<long long>(64, (rps + 31) / 32 * 32);  // >= 2 chunks per slice; small batches still fill the GPU
   W.rows_per_slice = (int)rps;
   const int nslice = (int)((W.R + rps - 1) / rps);
   W.atomic = nslice > 1;

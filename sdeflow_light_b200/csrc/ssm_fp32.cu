@@ -179,77 +179,106 @@ __global__ void __launch_bounds__(SSM_THREADS, 1) ssm_forward_kernel(const __gri
       __syncthreads();  // all reads of the input tile done (sAct is overwritten below)
       const float* bias = sB + l * HID;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int f = ng * 4 + (j & 3) + 64 * (j >> 2);
-        float o[4];
+      for (int jh = 0; jh < 2; ++jh) {  // the thread's two quads of 4 contiguous features: 16-byte global stores
+        const int f0 = ng * 4 + 64 * jh;
+        float o[4][4];                  // [feature in quad][row in the thread's 4-row group]
 #pragma unroll
         for (int si = 0; si < 2; ++si) {
-          const float z = acc[2 * si][j] + bias[f], zd = acc[2 * si + 1][j];
-          const SwishD sw = swish_derivs(z);
-          o[2 * si] = sw.h;
-          o[2 * si + 1] = sw.d1 * zd;
+          float4 z4, zd4, h4, hd4;
+          float* zp = &z4.x; float* zdp = &zd4.x; float* hp = &h4.x; float* hdp = &hd4.x;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float z = acc[2 * si][4 * jh + q] + bias[f0 + q], zd = acc[2 * si + 1][4 * jh + q];
+            const SwishD sw = swish_derivs(z);
+            zp[q] = z; zdp[q] = zd; hp[q] = sw.h; hdp[q] = sw.d1 * zd;
+            o[q][2 * si] = sw.h;
+            o[q][2 * si + 1] = sw.d1 * zd;
+          }
           const long long gr = 2 * b0 + 4 * pg + 2 * si;
           if (gr < 2 * P.B) {
-            P.Z[l][gr * HID + f] = z;
-            P.Z[l][(gr + 1) * HID + f] = zd;
-            P.U[l][gr * HID + f] = o[2 * si];
-            P.U[l][(gr + 1) * HID + f] = o[2 * si + 1];
+            *reinterpret_cast<float4*>(P.Z[l] + gr * HID + f0) = z4;
+            *reinterpret_cast<float4*>(P.Z[l] + (gr + 1) * HID + f0) = zd4;
+            *reinterpret_cast<float4*>(P.U[l] + gr * HID + f0) = h4;
+            *reinterpret_cast<float4*>(P.U[l] + (gr + 1) * HID + f0) = hd4;
           }
         }
-        *reinterpret_cast<float4*>(sAct + f * TR + (((pg ^ (f >> 2)) & 15) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(sAct + (f0 + q) * TR + (((pg ^ ((f0 + q) >> 2)) & 15) << 2)) =
+              make_float4(o[q][0], o[q][1], o[q][2], o[q][3]);
       }
       __syncthreads();
     }
 
     // ---- output layer: a = W4 h3 + b4 (primal rows), adot = W4 hdot3 (tangent rows) -----------------------------------------
     {
-      const int r = tid & 63, c0 = tid >> 6;
+      const int r = tid & 63, c0 = tid >> 6;  // thread: row r, components 8 c0 .. 8 c0 + 7 (a warp shares c0)
       float o[8];
 #pragma unroll
-      for (int m = 0; m < 8; ++m) o[m] = (r & 1) ? 0.0f : sB[3 * HID + c0 + 4 * m];
-      for (int k = 0; k < HID; ++k) {
-        const float h = sAct[tile_idx(k, r)];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) o[m] = fmaf(h, sW4[k * DP32 + c0 + 4 * m], o[m]);
+      for (int m = 0; m < 8; ++m) o[m] = (r & 1) ? 0.0f : sB[3 * HID + 8 * c0 + m];
+      if (8 * c0 < d) {
+#pragma unroll 4
+        for (int k = 0; k < HID; ++k) {
+          const float h = sAct[tile_idx(k, r)];
+          const float4 w0 = *reinterpret_cast<const float4*>(sW4 + k * DP32 + 8 * c0);
+          const float4 w1 = *reinterpret_cast<const float4*>(sW4 + k * DP32 + 8 * c0 + 4);
+          o[0] = fmaf(h, w0.x, o[0]); o[1] = fmaf(h, w0.y, o[1]); o[2] = fmaf(h, w0.z, o[2]); o[3] = fmaf(h, w0.w, o[3]);
+          o[4] = fmaf(h, w1.x, o[4]); o[5] = fmaf(h, w1.y, o[5]); o[6] = fmaf(h, w1.z, o[6]); o[7] = fmaf(h, w1.w, o[7]);
+        }
       }
       const long long gr = 2 * b0 + r;
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        sOut[(c0 + 4 * m) * TR + r] = o[m];
-        if (gr < 2 * P.B) P.A[gr * DP32 + c0 + 4 * m] = o[m];
+      for (int m = 0; m < 8; ++m) sOut[(8 * c0 + m) * TR + r] = o[m];
+      if (gr < 2 * P.B) {
+        *reinterpret_cast<float4*>(P.A + gr * DP32 + 8 * c0) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(P.A + gr * DP32 + 8 * c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
       }
     }
     __syncthreads();
 
-    // ---- per-sample loss and the cotangent direction of adot -----------------------------------------------------------------
+    // ---- cotangent direction q of adot: one (sample, k) pair per thread pass (sIn is free: reused as q[k][sample]) ----
+    float* sQ = sIn;
+    for (int e = tid; e < TS * d; e += SSM_THREADS) {
+      const int si = e / d, k = e - si * d;
+      const long long b = b0 + si;
+      float q = 0.0f;
+      if (b < P.B) {
+        const float sb = sqrtf(beta_of(P.bmin, P.bdel, P.t[b]));
+        const float* yb = P.y + b * d;
+        const float* vb = P.v + b * d;
+        if (P.kind == MSGM_SDE_SGM) {
+          q = sb * vb[k];
+        } else if (P.kind == MSGM_SDE_MSGM_SPARSE) {
+          // q_k = c sqrt(beta) (v_k y_{k+1} - v_{k+1} y_k): entries (i=k,j=k+1,k):+c and (i=k+1,j=k,k):-c (SDEs.py:375-380)
+          const int kn = (k + 1 == d) ? 0 : k + 1;
+          q = SQRT_HALF * sb * (vb[k] * yb[kn] - vb[kn] * yb[k]);
+        } else {
+          float acc = 0.0f;
+          for (int i = 0; i < d; ++i) {
+            float u = 0.0f;
+            for (int j = 0; j < d; ++j) u = fmaf(__ldg(P.G + (i * d + j) * d + k), yb[j], u);
+            acc = fmaf(vb[i], u, acc);
+          }
+          q = sb * acc;
+        }
+        P.Q[b * DP32 + k] = q;
+      }
+      sQ[k * TS + si] = q;
+    }
+    __syncthreads();
+    // ---- per-sample loss ------------------------------------------------------------------------------------------------
     if (tid < TS) {
       const long long b = b0 + tid;
       if (b < P.B) {
-        const float s = P.t[b];
-        const float bt = beta_of(P.bmin, P.bdel, s), sb = sqrtf(bt);
+        const float bt = beta_of(P.bmin, P.bdel, P.t[b]);
         float loss = 0.0f;
         for (int k = 0; k < d; ++k) {
           const float a = sOut[k * TR + 2 * tid], ad = sOut[k * TR + 2 * tid + 1];
-          float q;
           if (P.kind == MSGM_SDE_SGM) {
             const float vk = P.v[b * d + k];
-            q = sb * vk;
             loss = fmaf(0.5f * bt, vk * vk, loss);
-          } else if (P.kind == MSGM_SDE_MSGM_SPARSE) {
-            // q_k = c sqrt(beta) (v_k y_{k+1} - v_{k+1} y_k): entries (i=k,j=k+1,k):+c and (i=k+1,j=k,k):-c (SDEs.py:375-380)
-            const int kn = (k + 1 == d) ? 0 : k + 1;
-            q = SQRT_HALF * sb * (P.v[b * d + k] * P.y[b * d + kn] - P.v[b * d + kn] * P.y[b * d + k]);
-          } else {
-            float acc = 0.0f;
-            for (int i = 0; i < d; ++i) {
-              float u = 0.0f;
-              for (int j = 0; j < d; ++j) u = fmaf(__ldg(P.G + (i * d + j) * d + k), P.y[b * d + j], u);
-              acc = fmaf(P.v[b * d + i], u, acc);
-            }
-            q = sb * acc;
           }
-          P.Q[b * DP32 + k] = q;
-          loss = fmaf(q, ad, loss);
+          loss = fmaf(sQ[k * TS + tid], ad, loss);
           loss = fmaf(0.5f * a, a, loss);
         }
         P.loss[b] = loss;
@@ -295,41 +324,73 @@ __global__ void __launch_bounds__(SSM_THREADS, 1) ssm_backward_kernel(const __gr
     __syncthreads();
 
     for (int l = 2; l >= 0; --l) {
+      // this layer's pre-activations: issued before the product below so that their latency hides behind it
+      float4 zq[2][2], zdq[2][2];
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh)
+#pragma unroll
+        for (int si = 0; si < 2; ++si) {
+          const long long gr = 2 * b0 + 4 * pg + 2 * si;
+          const int f0 = ng * 4 + 64 * jh;
+          if (gr < 2 * P.B) {
+            zq[jh][si] = __ldg(reinterpret_cast<const float4*>(P.Z[l] + gr * HID + f0));
+            zdq[jh][si] = __ldg(reinterpret_cast<const float4*>(P.Z[l] + (gr + 1) * HID + f0));
+          } else {
+            zq[jh][si] = zdq[jh][si] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
       // hbar tile (rows: hbar, hdotbar) = Cot_{l+1} W_{l+1}
       float acc[4][8];
       if (l == 2) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int f = ng * 4 + (j & 3) + 64 * (j >> 2);
-            float s = 0.0f;
-            for (int c = 0; c < d; ++c) s = fmaf(sC4[c * TR + 4 * pg + i], sW4[c * HID + f], s);
-            acc[i][j] = s;
-          }
+          for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+        for (int c = 0; c < d; ++c) {
+          const float4 c4 = *reinterpret_cast<const float4*>(sC4 + c * TR + 4 * pg);
+          const float4 w0 = *reinterpret_cast<const float4*>(sW4 + c * HID + ng * 4);
+          const float4 w1 = *reinterpret_cast<const float4*>(sW4 + c * HID + 64 + ng * 4);
+          const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(cv[i], wv[j], acc[i][j]);
+        }
       } else {
         gemm_tile<false>(sW + (l == 1 ? 0 : HID * HID), HID, sCot, HID, ng, pg, acc);
         __syncthreads();  // sCot is overwritten below
       }
       // zbar = hbar phi'(z) + hdotbar phi''(z) zdot ;  zdotbar = hdotbar phi'(z)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int f = ng * 4 + (j & 3) + 64 * (j >> 2);
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int jh = 0; jh < 2; ++jh) {  // two quads of 4 contiguous features: 16-byte global loads and stores
+        const int f0 = ng * 4 + 64 * jh;
+        float o[4][4] = {};
 #pragma unroll
         for (int si = 0; si < 2; ++si) {
           const long long gr = 2 * b0 + 4 * pg + 2 * si;
           if (gr < 2 * P.B) {
-            const float z = P.Z[l][gr * HID + f], zd = P.Z[l][(gr + 1) * HID + f];
-            const SwishD sw = swish_derivs(z);
-            const float hb = acc[2 * si][j], hdb = acc[2 * si + 1][j];
-            o[2 * si] = fmaf(hb, sw.d1, hdb * sw.d2 * zd);
-            o[2 * si + 1] = hdb * sw.d1;
-            P.C[l][gr * HID + f] = o[2 * si];
-            P.C[l][(gr + 1) * HID + f] = o[2 * si + 1];
+            const float4 z4 = zq[jh][si], zd4 = zdq[jh][si];
+            const float* zp = &z4.x; const float* zdp = &zd4.x;
+            float4 c4, cd4;
+            float* cp = &c4.x; float* cdp = &cd4.x;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const SwishD sw = swish_derivs(zp[q]);
+              const float hb = acc[2 * si][4 * jh + q], hdb = acc[2 * si + 1][4 * jh + q];
+              cp[q] = fmaf(hb, sw.d1, hdb * sw.d2 * zdp[q]);
+              cdp[q] = hdb * sw.d1;
+              o[q][2 * si] = cp[q];
+              o[q][2 * si + 1] = cdp[q];
+            }
+            *reinterpret_cast<float4*>(P.C[l] + gr * HID + f0) = c4;
+            *reinterpret_cast<float4*>(P.C[l] + (gr + 1) * HID + f0) = cd4;
           }
         }
-        *reinterpret_cast<float4*>(sCot + f * TR + (((pg ^ (f >> 2)) & 15) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(sCot + (f0 + q) * TR + (((pg ^ ((f0 + q) >> 2)) & 15) << 2)) =
+              make_float4(o[q][0], o[q][1], o[q][2], o[q][3]);
       }
       __syncthreads();
     }

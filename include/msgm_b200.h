@@ -33,6 +33,8 @@ typedef enum {
 } msgm_status;
 
 typedef enum { MSGM_SDE_SGM = 0, MSGM_SDE_MSGM_DENSE = 1, MSGM_SDE_MSGM_SPARSE = 2 } msgm_sde_kind;
+/* Hutchinson probe distributions of sample_v (SDEs.py:514-536): 'rademacher', 'normal'/'gaussian', 'uniform' (sphere) */
+typedef enum { MSGM_V_RADEMACHER = 0, MSGM_V_GAUSSIAN = 1, MSGM_V_SPHERE = 2 } msgm_vtype;
 typedef enum { MSGM_SCHEME_EM = 0, MSGM_SCHEME_HEUN = 1, MSGM_SCHEME_RK4 = 2 } msgm_scheme;
 typedef enum {
   MSGM_PREC_FP32 = 0, /* CUDA-core fp32 everywhere: the parity mode (reference is fp32 end to end) */
@@ -118,6 +120,16 @@ int msgm_noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, 
                        const float* ts /* (N+1,) grid linspace(0,1,N+1)*T as the caller computed it, or NULL */,
                        const float* noise, const float* noise_single, uint64_t seed, uint64_t particle_offset, int64_t B,
                        void* stream);
+
+/* Training prologue in ONE launch.  Replaces PluginReverseSDE.sample_txy + sample_t + sample_v (SDEs.py:648-693,
+ * 514-536) and the forward noising they call: for every row draws t ~ U(0,T) floored at t_epsilon, the probe v, and
+ * y_t | x (MSGM: the simulation of msgm_noise_forward; SGM: the closed-form marginal of SDEs.py:134-146).
+ * x (B,d) in; t_out (B,), v_out (B,d), y_out (B,d) out; all device fp32.  Every draw is Philox keyed by
+ * (seed + *seed_offset_dev, sample_offset + row): seed_offset_dev (device uint64, may be NULL) lets a replayed CUDA
+ * graph see a fresh stream per iteration; sample_offset makes a batch sharded over ranks draw what one rank would. */
+int msgm_ssm_prepare(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* x, float* t_out, float* v_out, float* y_out,
+                     int32_t num_steps_forward, const float* ts, float t_epsilon, int32_t vtype, uint64_t seed,
+                     const uint64_t* seed_offset_dev, uint64_t sample_offset, int64_t B, void* stream);
 
 /* Stand-alone score-net forward a(y, s) -> (B,d) for NN.MLP.forward (NN.py:108-120); s is (B,). */
 int msgm_mlp_forward(msgm_ctx* ctx, const msgm_mlp_desc* mlp, const float* y, const float* s, float* out,

@@ -384,6 +384,9 @@ def sample_v(shape, device, vtype='rademacher'):
     return None  # the reference builds an Exception without raising it (SDEs.py:535-536)
 
 
+_VTYPES = {"rademacher": 0, "normal": 1, "gaussian": 1, "uniform": 2}  # msgm_vtype
+
+
 class PluginReverseSDE(torch.nn.Module):
     """Reverse-time SDE from a base SDE and a score net ``a`` (reference SDEs.py:538-729).
 
@@ -437,17 +440,41 @@ class PluginReverseSDE(torch.nn.Module):
         """(t, x, y_t) with t ~ U(0,T) floored at t_epsilon (reference SDEs.py:648-693)."""
         if self.ssm_intT:
             raise NotImplementedError("ssm_intT=True raises NameError in the reference (SDEs.py:700); not built")
+        if getattr(self, "device_rng", False) and x.is_cuda and x.dim() == 2 and x.shape[1] <= 32 \
+                and self.vtype in _VTYPES and isinstance(self.base_sde, (MSGMsde, SGMsde)):
+            t_, y, _ = self._prepare(x, with_v=False)
+            return t_, x, y
         with torch.no_grad():
             t_ = self.sample_t(x)
-            if getattr(self, "device_rng", False) and isinstance(self.base_sde, MSGMsde) and x.shape[1] <= 32:
-                # every draw from the CUDA generator, no host round trip: what train.GraphedSsmStep records
-                n = self.base_sde.num_steps_forward
-                y = self.base_sde.sample_scheme(t_, x, keep_all_samples=False,
-                                                noise=torch.randn(n, *x.shape, device=x.device),
-                                                _single=torch.randn(*x.shape, device=x.device))
-            else:
-                y = self.base_sde.sample(t_, x)
+            y = self.base_sde.sample(t_, x)
         return t_, x, y
+
+    def _prepare(self, x, with_v=True):
+        """(t, y_t, v) from ONE launch (msgm_ssm_prepare): every draw is in-kernel Philox keyed by (seed + device
+        counter, global row), so the call neither touches the host generator nor synchronises -- the path that
+        ``device_rng = True`` selects and that train.GraphedSsmStep records.  ``_rng`` = (seed, counter tensor or None,
+        row offset) is set by the trainer; without it each call draws a fresh seed from the host generator."""
+        import ctypes as C
+        base, dev = self.base_sde, x.device
+        B, d = x.shape
+        xc = _lib.f32c(x, dev)
+        t_ = torch.empty(B, 1, device=dev, dtype=torch.float32)
+        v = torch.empty(B, d, device=dev, dtype=torch.float32)
+        y = torch.empty(B, d, device=dev, dtype=torch.float32)
+        seed, counter, offset = getattr(self, "_rng", None) or (int(torch.randint(0, 2 ** 62, (1,)).item()), None, 0)
+        sd, keep = base.desc(dev)
+        sd.dim = d  # SGMsde has no dim of its own
+        n_tot = int(base.num_steps_forward)
+        T_host = _lib.host_float(base, "T")
+        grid = getattr(base, "_fwd_grid", None)
+        if grid is None or grid[0] != (n_tot, T_host, str(dev)):
+            base._fwd_grid = ((n_tot, T_host, str(dev)), (torch.linspace(0, 1, n_tot + 1) * T_host).to(dev))
+        _lib.check(_lib.lib().msgm_ssm_prepare(
+            _lib.ctx(dev), C.byref(sd), _lib.ptr(xc), _lib.ptr(t_), _lib.ptr(v), _lib.ptr(y), n_tot,
+            _lib.ptr(base._fwd_grid[1]), float(base.t_epsilon), _VTYPES[self.vtype], seed, _lib.ptr(counter), int(offset), B,
+            _lib.stream_ptr(dev)))
+        self._last_v = v if with_v else None
+        return t_, y, v
 
     def sample_t(self, x):
         shape = [x.size(0), ] + [1 for _ in range(x.ndim - 1)]

@@ -54,7 +54,7 @@ _ctx = {}
 
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
-           "msgm_sample_mlp", "msgm_noise_forward", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
+           "msgm_sample_mlp", "msgm_noise_forward", "msgm_ssm_prepare", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward",
            "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums",
            "msgm_conv1d", "msgm_emb_fold", "msgm_convt1d_k4s2", "msgm_embed_mlp", "msgm_normalize_log_radius",
@@ -107,6 +107,9 @@ def lib() -> C.CDLL:
                 L.msgm_vort_post.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p]
                 L.msgm_noise_forward.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
+                L.msgm_ssm_prepare.argtypes = [C.c_void_p, C.POINTER(SdeDesc)] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p,
+                                               C.c_float, C.c_int32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int64,
+                                               C.c_void_p]
                 L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]

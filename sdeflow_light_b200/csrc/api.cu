@@ -17,6 +17,8 @@ int sample_mlp_fp32(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const
                     cudaStream_t, const float* t_noise = nullptr, const float* noise_single = nullptr);
 int noise_forward(msgm_ctx*, const msgm_sde_desc*, const float*, float*, int, const float*, const float*, const float*,
                   uint64_t, uint64_t, int64_t, cudaStream_t);
+int ssm_prepare(msgm_ctx*, const msgm_sde_desc*, const float*, float*, float*, float*, int, const float*, float, int, uint64_t,
+                const uint64_t*, uint64_t, int64_t, cudaStream_t);
 int sample_mlp_tc(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const msgm_sample_args*, float*, int64_t,
                   cudaStream_t);
 int mlp_forward_fp32(msgm_ctx*, const msgm_mlp_desc*, const float*, const float*, float*, int64_t, cudaStream_t);
@@ -388,6 +390,25 @@ int msgm_noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, 
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return noise_forward(ctx, sde, t, y_inout, num_steps_forward, ts, noise, noise_single, seed, particle_offset, B,
                        (cudaStream_t)stream);
+}
+
+int msgm_ssm_prepare(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* x, float* t_out, float* v_out, float* y_out,
+                     int32_t num_steps_forward, const float* ts, float t_epsilon, int32_t vtype, uint64_t seed,
+                     const uint64_t* seed_offset_dev, uint64_t sample_offset, int64_t B, void* stream) {
+  if (!ctx || !sde || !x || !t_out || !v_out || !y_out) return invalid("msgm_ssm_prepare: NULL argument");
+  if (sde->dim < 1 || sde->dim > MSGM_MAX_DIM_MLP) {
+    set_error("msgm_ssm_prepare: dim must be in [1,32]");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (sde->kind != MSGM_SDE_SGM && sde->kind != MSGM_SDE_MSGM_DENSE && sde->kind != MSGM_SDE_MSGM_SPARSE)
+    return invalid("msgm_ssm_prepare: unknown sde kind");
+  if (sde->kind == MSGM_SDE_MSGM_DENSE && !sde->G) return invalid("dense MSGM needs G");
+  if (vtype < MSGM_V_RADEMACHER || vtype > MSGM_V_SPHERE) return invalid("msgm_ssm_prepare: unknown vtype");
+  if (num_steps_forward < 1) return invalid("num_steps_forward < 1");
+  if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return ssm_prepare(ctx, sde, x, t_out, v_out, y_out, num_steps_forward, ts, t_epsilon, vtype, seed, seed_offset_dev,
+                     sample_offset, B, (cudaStream_t)stream);
 }
 
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n) {

@@ -31,7 +31,16 @@ struct NoiseParams {
   unsigned long long seed, poff;
   float* x;                   // (B,d) in/out
   long long B;
+  // fused training prologue (msgm_ssm_prepare): draw t and the probe v in the same launch, read x from x_in
+  const float* x_in;          // (B,d) clean samples, or NULL = x holds them
+  float* t_out;               // (B) drawn noise times, or NULL = t_noise given
+  float* v_out;               // (B,d) Hutchinson probe, or NULL
+  int vtype;                  // MSGM_V_*
+  float t_eps;
+  const unsigned long long* seed_off;  // device counter added to the seed (CUDA-graph replays), or NULL
 };
+
+constexpr uint32_t STREAM_T = 0xFFFF0010u, STREAM_V = 0xFFFF0011u, STREAM_SGM = 0xFFFF0012u;
 
 template <int DP>
 struct GLayout {
@@ -55,17 +64,62 @@ __global__ void __launch_bounds__(128) noise_forward_kernel(const __grid_constan
     __syncthreads();
   }
   const unsigned full = 0xffffffffu;
+  const unsigned long long seed = P.seed + (P.seed_off ? *P.seed_off : 0ull);
   const long long ngroups = (P.B + PPB - 1) / PPB;
   for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const long long gp = grp * PPB + tid / DP;
     const bool live = gp < P.B;
     const bool mine = live && i < d;
-    float x = mine ? P.x[gp * d + i] : 0.0f;
+    float x = mine ? (P.x_in ? __ldg(P.x_in + gp * d + i) : P.x[gp * d + i]) : 0.0f;
     float y = x, ks = 0.0f;
+
+    // noise time: given, or t ~ U(0,T) floored at t_epsilon (PluginReverseSDE.sample_t, SDEs.py:684-693)
+    float tk = 0.0f;
+    if (P.t_out) {
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)(P.poff + gp), (uint32_t)((P.poff + gp) >> 32), STREAM_T, 0u),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      tk = u01(r.x) * P.Tsde;
+      tk = tk <= P.t_eps ? P.t_eps : tk;
+      if (live && i == 0) P.t_out[gp] = tk;
+    } else if (live) {
+      tk = __ldg(P.t_noise + gp);
+    }
+    // Hutchinson probe (sample_v, SDEs.py:514-536)
+    if (P.v_out) {
+      const unsigned long long pid = P.poff + (unsigned long long)gp;
+      float vi;
+      if (P.vtype == MSGM_V_RADEMACHER) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), STREAM_V, (uint32_t)(i >> 2)),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const int q = i & 3;
+        const uint32_t w = q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w));
+        vi = (w >> 31) ? 1.0f : -1.0f;
+      } else {
+        const float4 z = philox_normal4(seed, pid, STREAM_V, (uint32_t)(i >> 2));
+        const int q = i & 3;
+        vi = q == 0 ? z.x : (q == 1 ? z.y : (q == 2 ? z.z : z.w));
+        if (P.vtype == MSGM_V_SPHERE) {  // X / |X| (randu_on_sphere, SDEs.py:520-526)
+          float n2 = i < d ? vi * vi : 0.0f;
+#pragma unroll
+          for (int o = DP / 2; o > 0; o >>= 1) n2 += __shfl_xor_sync(full, n2, o, DP);
+          vi = vi / sqrtf(n2);
+        }
+      }
+      if (mine) P.v_out[gp * d + i] = vi;
+    }
+    if (KIND == MSGM_SDE_SGM) {
+      // closed-form VP marginal (SDE.sample_Song_et_al, SDEs.py:134-146): y = mean_weight(t) x + sqrt(var(t)) eps
+      const float4 z = philox_normal4(seed, P.poff + (unsigned long long)gp, STREAM_SGM, (uint32_t)(i >> 2));
+      const int q = i & 3;
+      const float eps = q == 0 ? z.x : (q == 1 ? z.y : (q == 2 ? z.z : z.w));
+      const float e1 = expf(-0.25f * tk * tk * P.bdel - 0.5f * tk * P.bmin);
+      const float var = 1.0f - expf(-0.5f * tk * tk * P.bdel - tk * P.bmin);
+      if (mine) P.x[gp * d + i] = fmaf(eps, sqrtf(var), e1 * x);
+      continue;
+    }
 
     // row schedule (SDEs.py:86-118)
     float delta = P.delta, delta_half = P.delta_half, sqrt_delta = P.sqrt_delta;
-    const float tk = live ? __ldg(P.t_noise + gp) : 0.0f;
     const int nk = tk >= P.Tsde ? P.N : (int)truncf(__fdiv_rn(__fmul_rn((float)P.N, tk), P.Tsde));
     const bool single = nk == 0;
     const int my_steps = single ? 1 : nk;
@@ -90,7 +144,7 @@ __global__ void __launch_bounds__(128) noise_forward_kernel(const __grid_constan
         } else if (P.noise && !single) {
           xi = live ? __ldg(P.noise + ((long long)step * P.B + gp) * d + i) : 0.0f;
         } else {
-          const float4 z = philox_normal4(P.seed, P.poff + (unsigned long long)gp, single ? 0xFFFF0002u : (uint32_t)step,
+          const float4 z = philox_normal4(seed, P.poff + (unsigned long long)gp, single ? 0xFFFF0002u : (uint32_t)step,
                                           (uint32_t)(i >> 2));
           const int q = i & 3;
           xi = q == 0 ? z.x : (q == 1 ? z.y : (q == 2 ? z.z : z.w));
@@ -174,13 +228,11 @@ static int launch_noise(msgm_ctx* ctx, const NoiseParams& P, cudaStream_t stream
 template <int DP>
 static int launch_noise_kind(msgm_ctx* ctx, int kind, const NoiseParams& P, cudaStream_t stream) {
   if (kind == MSGM_SDE_MSGM_DENSE) return launch_noise<DP, MSGM_SDE_MSGM_DENSE>(ctx, P, stream);
+  if (kind == MSGM_SDE_SGM) return launch_noise<DP, MSGM_SDE_SGM>(ctx, P, stream);
   return launch_noise<DP, MSGM_SDE_MSGM_SPARSE>(ctx, P, stream);
 }
 
-int noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, float* y_inout, int num_steps, const float* ts,
-                  const float* noise, const float* noise_single, uint64_t seed, uint64_t poff, int64_t B,
-                  cudaStream_t stream) {
-  NoiseParams P{};
+static int run_noise(msgm_ctx* ctx, const msgm_sde_desc* sde, NoiseParams& P, int num_steps, cudaStream_t stream) {
   const int d = sde->dim;
   P.d = d;
   P.N = num_steps;
@@ -193,14 +245,6 @@ int noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, float
   P.delta_half = (float)(delta / 2.0);
   P.sqrt_delta = (float)std::sqrt(delta);
   P.G = sde->G;
-  P.ts = ts;
-  P.t_noise = t;
-  P.noise = noise;
-  P.noise_single = noise_single;
-  P.seed = seed;
-  P.poff = poff;
-  P.x = y_inout;
-  P.B = B;
   const int DP = d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32;
   switch (DP) {
     case 2: return launch_noise_kind<2>(ctx, sde->kind, P, stream);
@@ -209,6 +253,40 @@ int noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, float
     case 16: return launch_noise_kind<16>(ctx, sde->kind, P, stream);
     default: return launch_noise_kind<32>(ctx, sde->kind, P, stream);
   }
+}
+
+int noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, float* y_inout, int num_steps, const float* ts,
+                  const float* noise, const float* noise_single, uint64_t seed, uint64_t poff, int64_t B,
+                  cudaStream_t stream) {
+  NoiseParams P{};
+  P.ts = ts;
+  P.t_noise = t;
+  P.noise = noise;
+  P.noise_single = noise_single;
+  P.seed = seed;
+  P.poff = poff;
+  P.x = y_inout;
+  P.B = B;
+  return run_noise(ctx, sde, P, num_steps, stream);
+}
+
+// Training prologue in one launch: t ~ U(0,T) floored at t_epsilon, the Hutchinson probe v, and y_t | x.
+int ssm_prepare(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* x, float* t_out, float* v_out, float* y_out,
+                int num_steps, const float* ts, float t_eps, int vtype, uint64_t seed, const uint64_t* seed_off,
+                uint64_t poff, int64_t B, cudaStream_t stream) {
+  NoiseParams P{};
+  P.ts = ts;
+  P.seed = seed;
+  P.seed_off = reinterpret_cast<const unsigned long long*>(seed_off);
+  P.poff = poff;
+  P.x_in = x;
+  P.x = y_out;
+  P.t_out = t_out;
+  P.v_out = v_out;
+  P.vtype = vtype;
+  P.t_eps = t_eps;
+  P.B = B;
+  return run_noise(ctx, sde, P, num_steps, stream);
 }
 
 }  // namespace msgm

@@ -56,6 +56,28 @@ class _SsmMlp(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+def fused_loss_and_grads(gen, t, y, v, gout, grad_flat):
+    """Per-sample loss (B,) AND the parameter gradient of ``sum_b gout_b loss_b`` written straight into ``grad_flat``
+    (torch parameter order of the MLP): the forward and backward kernels back to back, without an autograd graph.
+    What train.GraphedSsmStep records for MLP score nets."""
+    dev = y.device
+    base, net = gen.base_sde, gen.a
+    B = y.shape[0]
+    sd, keep = base.desc(dev)
+    sd.dim = y.shape[1]
+    md, k2 = net.desc(dev)
+    yc, vc, tc = _lib.f32c(y, dev), _lib.f32c(v, dev), _lib.f32c(t.reshape(-1), dev)
+    loss = torch.empty(B, device=dev, dtype=torch.float32)
+    scratch = torch.empty(int(_lib.lib().msgm_ssm_scratch_bytes(B)) // 4, device=dev, dtype=torch.float32)
+    h = _lib.ctx(dev)
+    _lib.check(_lib.lib().msgm_ssm_mlp_forward(h, C.byref(sd), C.byref(md), _lib.ptr(yc), _lib.ptr(vc), _lib.ptr(tc),
+                                               _lib.ptr(loss), _lib.ptr(scratch), B, _lib.stream_ptr(dev)))
+    _lib.check(_lib.lib().msgm_ssm_mlp_backward(h, C.byref(sd), C.byref(md), _lib.ptr(yc), _lib.ptr(vc), _lib.ptr(tc),
+                                                _lib.ptr(gout), _lib.ptr(scratch), _lib.ptr(grad_flat), B,
+                                                _lib.stream_ptr(dev)))
+    return loss
+
+
 def _ssm_loss_autograd(gen, t_, y, v):
     """SSM loss for score nets without a fused kernel (U-Nets): the reference's recipe (SDEs.py:616-646) -- a VJP through
     the net with create_graph -- on GPU tensors, with the drift written in its cancelled form mu_to_div = g.a (+ beta y/2
@@ -95,5 +117,10 @@ def ssm_loss(gen, t_, x, y, v=None):
 
 
 def ssm(gen, x):
+    if getattr(gen, "device_rng", False) and x.is_cuda and x.dim() == 2 and x.shape[1] <= 32:
+        from . import SDEs
+        if gen.vtype in SDEs._VTYPES and isinstance(gen.base_sde, (SDEs.MSGMsde, SDEs.SGMsde)):
+            t_, y, v = gen._prepare(x)  # t, y_t and the probe from one launch
+            return ssm_loss(gen, t_, x, y, v)
     t_, x, y = gen.sample_txy(x)
     return ssm_loss(gen, t_, x, y)

@@ -36,7 +36,7 @@ class _SsmModule(torch.nn.Module):
 
 class GraphedSsmStep:
     def __init__(self, gen, batch_shape, lr: float = 1e-3, optimizer: torch.optim.Optimizer | None = None,
-                 warmup: int = 3, group=None):
+                 warmup: int = 3, group=None, seed: int | None = None):
         dev = torch.device(gen.deviceReverseSDE)
         if dev.type != "cuda":
             raise RuntimeError("sdeflow_light_b200 runs on CUDA only (no CPU fallback)")
@@ -61,6 +61,19 @@ class GraphedSsmStep:
             o += p.numel()
         self._grads = [p.grad for p in self.params]
         self.launches_per_iter = 0
+        # Device-side random streams: a fixed seed plus a device counter bumped inside the graph, so every replay draws
+        # fresh t / noise / v; the row offset makes a batch sharded over ranks draw what a single rank would.
+        self._iter = torch.zeros(1, device=dev, dtype=torch.int64)
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._old_rng = getattr(gen, "_rng", None)
+        gen._rng = (int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed), self._iter,
+                    rank * int(batch_shape[0]))
+        # MLP score nets: forward and backward kernels back to back, gradients written straight into the flat buffer
+        from . import NN, SDEs
+        self._direct = (isinstance(gen.a, NN.MLP) and gen.a.fused_ok() and len(batch_shape) == 2 and batch_shape[1] <= 32
+                        and gen.vtype in SDEs._VTYPES and isinstance(gen.base_sde, (SDEs.MSGMsde, SDEs.SGMsde))
+                        and all(n.startswith("a.main.") for n in self._names))
+        self._gout = torch.full((int(batch_shape[0]),), 1.0 / int(batch_shape[0]), device=dev)
 
         gen.train()
         was = getattr(gen, "device_rng", False)
@@ -104,10 +117,19 @@ class GraphedSsmStep:
                         old = saved_s.get(id(q), {}).get(k)
                         v.copy_(old) if old is not None else v.zero_()
         self.x.zero_()
+        self._iter.zero_()
         gen.device_rng = was
+        gen._rng = self._old_rng  # the graphs have the trainer's stream baked in; eager calls keep their own
 
     # -- the recorded part of the iteration ---------------------------------------------------------------------
     def _fwd_bwd(self):
+        if self._direct:
+            from . import ssm_fused
+            t_, y, v = self.gen._prepare(self.x)
+            loss = ssm_fused.fused_loss_and_grads(self.gen, t_, y, v, self._gout, self.flat)
+            torch.mean(loss, dim=0, out=self.loss)
+            self._iter.add_(1)
+            return
         # The loss runs on fresh leaves aliasing the parameters, and autograd.grad + one multi-tensor copy replaces
         # .backward(): a parameter's AccumulateGrad node remembers the stream it was first used on, and one kept alive
         # by an earlier eager iteration (a retained loss, a live optimizer) would tie this capture to the default stream.
@@ -117,6 +139,7 @@ class GraphedSsmStep:
         grads = torch.autograd.grad(loss, leaves)
         torch._foreach_copy_(self._grads, list(grads))
         self.loss.copy_(loss.detach())
+        self._iter.add_(1)
 
     def set_lr(self, lr: float):
         """Change the learning rate seen by the recorded Adam update (in place, on the device)."""

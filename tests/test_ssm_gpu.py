@@ -110,8 +110,8 @@ def test_ssm_end_to_end_trains():
 
 
 def test_graphed_train_step_matches_eager_and_trains():
-    """train.GraphedSsmStep replays the reference loop (MSGM_higherDim.py:803-809) as one CUDA graph: (1) with the
-    CUDA generator reseeded identically, a replay produces the same loss as the eager iteration;
+    """train.GraphedSsmStep replays the reference loop (MSGM_higherDim.py:803-809) as one CUDA graph: (1) on the same
+    Philox stream a replay produces the same loss and parameter gradient as the eager autograd iteration;
     (2) successive replays draw fresh t / noise / v; (3) training through replays reduces the held-out loss."""
     from sdeflow_light_b200.train import GraphedSsmStep
     d = 2
@@ -136,19 +136,23 @@ def test_graphed_train_step_matches_eager_and_trains():
         if make == "msgm":  # G is random: share it so both replicas integrate the same SDE
             gen_e.base_sde.G, gen_e.base_sde.L_G = gen_g.base_sde.G, gen_g.base_sde.L_G
         gen_e.load_state_dict(gen_g.state_dict())
-        step = GraphedSsmStep(gen_g, (256, d), lr=0.0)          # lr = 0 during warm-up: parameters stay equal
+        step = GraphedSsmStep(gen_g, (256, d), lr=0.0, seed=123)
         step.set_lr(2e-3)
         opt_e = torch.optim.Adam(gen_e.parameters(), lr=2e-3)
         gen_e.train()
         gen_e.device_rng = True
+        gen_e._rng = (123, torch.zeros(1, device=DEV, dtype=torch.int64), 0)  # the trainer's stream at iteration 0
         x = data[:256]
-        torch.cuda.manual_seed(7)
         l_g = float(step(x))
-        torch.cuda.manual_seed(7)
+        g_graph = torch.cat([p.grad.reshape(-1) for p in gen_g.a.parameters()]).clone()
         opt_e.zero_grad()
         l = gen_e.ssm(x).mean()
         l.backward()
         l_e = float(l.detach())
+        g_eager = torch.cat([p.grad.reshape(-1) for p in gen_e.a.parameters()])
+        gerr = float((g_graph - g_eager).abs().max() / g_eager.abs().max())
+        Bd.report(test=f"graphed-vs-eager-grad-{make}", max_rel=gerr)
+        assert gerr <= 1e-4, (make, gerr)
         Bd.report(test=f"graphed-vs-eager-{make}", loss_graph=l_g, loss_eager=l_e)
         assert abs(l_g - l_e) <= 1e-5 + 1e-4 * abs(l_e), (make, l_g, l_e)  # observed: msgm identical, sgm 1.6e-5 rel
         # (2) fresh randomness per replay
@@ -168,3 +172,53 @@ def test_graphed_train_step_matches_eager_and_trains():
         Bd.report(test=f"graphed-train-{make}", eval_loss_before=before, eval_loss_after=after,
                   own_launches_per_iter=step.launches_per_iter)
         assert after < before - 0.005, (make, before, after)
+
+
+@pytest.mark.parametrize("kind,d", [("msgm_dense", 2), ("msgm_dense", 8), ("msgm_dense", 19), ("msgm_sparse", 11),
+                                    ("sgm", 5)])
+def test_ssm_prepare_kernel(kind, d):
+    """msgm_ssm_prepare (t, v, y_t in one launch; SDEs.py:648-693, 514-536): t ~ U(0,T) floored at t_epsilon, v in
+    {-1,+1}, and y_t identical to msgm_noise_forward run with the drawn t on the same Philox stream."""
+    import ctypes as C
+    from sdeflow_light_b200 import _lib
+    torch.manual_seed(3)
+    B = 20000
+    T = Bd.T_param(1.0)
+    if kind == "sgm":
+        base = P.SGMsde(beta_min=0.1, beta_max=20., T=T, t_epsilon=0.05, num_steps_forward=16, device=DEV)
+        base.dim = d
+        net = P.MLP(d).to(DEV)
+    else:
+        base = P.MSGMsde(torch.randn(64, d), beta_min=0.1, beta_max=20., T=T, t_epsilon=0.05,
+                         denseTensor=(kind == "msgm_dense"), norm_map="log", num_steps_forward=16, device=DEV,
+                         estim_cst_norm_dens_r_T=False)
+        net = P.MLP(d, premodule="NormalizeLogRadius").to(DEV)
+    gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
+    gen.device_rng = True
+    gen._rng = (99, None, 0)
+    x = torch.randn(B, d, device=DEV)
+    t, y, v = gen._prepare(x)
+    t = t.reshape(-1)
+    assert float(t.min()) >= 0.05 - 1e-7 and float(t.max()) <= 1.0
+    frac_floor = float((t == 0.05).float().mean())
+    assert abs(frac_floor - 0.05) < 0.01 and abs(float(t.mean()) - (0.5 + 0.05 ** 2 / 2)) < 0.01
+    assert bool(((v == 1) | (v == -1)).all()) and abs(float(v.mean())) < 0.02
+    assert abs(float((v[:, 0] * v[:, -1]).mean())) < 0.03 or d == 1
+    assert bool(torch.isfinite(y).all())
+    if kind != "sgm":
+        y2 = x.clone()
+        sd, keep = base.desc(torch.device(DEV))
+        _lib.check(_lib.lib().msgm_noise_forward(_lib.ctx(torch.device(DEV)), C.byref(sd), _lib.ptr(t.contiguous()),
+                                                 _lib.ptr(y2), 16, _lib.ptr(base._fwd_grid[1]), None, None, 99, 0, B,
+                                                 _lib.stream_ptr(torch.device(DEV))))
+        assert float((y - y2).abs().max()) == 0.0
+    else:  # closed form: E[y | x, t] = mean_weight(t) x, so the residual is N(0, var(t))
+        mw, var = base.mean_weight(t.reshape(-1, 1)), base.var(t.reshape(-1, 1))
+        z = (y - mw * x) / var.sqrt()
+        assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02
+    # sharding invariance: rows [B/2, B) drawn with a row offset equal the second half of the full draw
+    gen._rng = (99, None, B // 2)
+    t2, y2h, v2 = gen._prepare(x[B // 2:])
+    assert float((t2.reshape(-1) - t[B // 2:]).abs().max()) == 0.0 and float((v2 - v[B // 2:]).abs().max()) == 0.0
+    assert float((y2h - y[B // 2:]).abs().max()) == 0.0
+    Bd.report(test=f"ssm-prepare-{kind}-d{d}", t_floor_frac=frac_floor, v_mean=float(v.mean()))

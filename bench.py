@@ -213,6 +213,7 @@ def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev, gr
 def run_reference(args, rank):
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun sets OMP_NUM_THREADS=1; this arm may use every host core
     sde, mlp = build_problem(args.dim)
     B, n = 50_000, 4
     times = []
@@ -365,7 +366,11 @@ def main():
                          "flop_per_launch": fl, "kernel_ms": kms},
         }
         line["train"] = train
-        if not args.no_cpu_baseline:
+        if world > 1:  # the CPU baselines are timed at N = 1 only (torchrun also pins every rank to one host thread)
+            line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": None, "kind": "port",
+                                    "sample": "timed at N=1 only"}
+        elif not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
             train["cpu_baseline"] = {"value": None if args.no_train else time_cpu_train(sde, mlp, data_host, 256, 10), "unit": "samples/s",
                                      "cores": torch.get_num_threads(), "kind": "port",
                                      "sample": "batch 256, 10 iterations after 1 warm-up (oracle port, torch CPU fp32)"}

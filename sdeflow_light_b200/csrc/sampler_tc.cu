@@ -815,8 +815,8 @@ int sample_mlp_tc(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* 
     set_error("f16tc precision: the forward adapter / per-row horizons have no net and run in fp32 mode");
     return MSGM_ERR_UNSUPPORTED;
   }
-  if (d > 16 || (sde->kind == MSGM_SDE_MSGM_DENSE && d > 8)) {
-    set_error("f16tc precision is built for d <= 8 (dense MSGM) or d <= 16 (SGM / sparse MSGM); use fp32");
+  if (d > 16) {
+    set_error("f16tc precision is built for d <= 16; use fp32");
     return MSGM_ERR_UNSUPPORTED;
   }
   TcParams P{};

@@ -158,6 +158,8 @@ TC_CASES = [
     ("msgm_dense", 4, True, "heun", 0.25, True, 130, 16),
     ("msgm_dense", 8, True, "rk4", 0.0, True, 257, 12),
     ("msgm_dense", 5, False, "em", 0.5, True, 77, 16),
+    ("msgm_dense", 16, True, "rk4", 0.0, True, 200, 8),
+    ("msgm_dense", 11, True, "heun", 0.25, True, 130, 8),
     ("msgm_sparse", 2, True, "rk4", 0.0, True, 100, 16),
     ("msgm_sparse", 16, True, "rk4", 0.0, True, 129, 8),
     ("msgm_sparse", 7, True, "em", 0.3, True, 100, 16),

@@ -176,6 +176,12 @@ int msgm_latent_sample(msgm_ctx* ctx, const float* rT_sorted, int32_t n_r, int32
 int msgm_mmd_sums(msgm_ctx* ctx, const float* x, int64_t N, const float* y, int64_t M, int32_t d, double* sums_out,
                   void* stream);
 
+/* Log density of a 1-D Gaussian kernel density estimate at m query points: what MSGMsde.log_latent_pdf and the
+ * normalising-constant estimate of the constructor ask sklearn's KernelDensity.score_samples for (SDEs.py:240,261,509;
+ * kernel='gaussian', exact sum).  samples (n,), queries (m,), out (m,): device fp32. */
+int msgm_kde_logpdf(msgm_ctx* ctx, const float* samples, int32_t n, float bandwidth, const float* queries, float* out,
+                    int32_t m, void* stream);
+
 /* ---- 1-D U-Net score net layers (NNUnet1D.py:13-179), fp32, NCL layout -----------------------------------------------
  * One msgm_conv1d call = nn.Conv1d (+ optional exact GELU) over the channel concatenation [x1, x2, emb] WITHOUT building
  * it: x2 (decoder skip) may be NULL; the Cemb embedding channels, constant along the signal, enter through the folded

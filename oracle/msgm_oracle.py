@@ -493,6 +493,35 @@ def compute_mmd(x, y):
     return rbf_kernel_mean(x, x) + rbf_kernel_mean(y, y) - 2 * rbf_kernel_mean(x, y)
 
 
+def kde_logpdf(samples, bandwidth: float, queries):
+    """log density of the 1-D Gaussian KDE of ``samples`` at ``queries``: what the reference asks
+    sklearn.neighbors.KernelDensity(kernel='gaussian', bandwidth=h).fit(r_T).score_samples(r) for (SDEs.py:240,261,509;
+    scikit-learn is a dependency of the reference, its gaussian kernel is exp(-u^2/2)/(h sqrt(2 pi)), exact sum with the
+    default rtol=atol=0).  float64 logsumexp, returned as fp32 like the reference's torch.tensor(...).to(float32)."""
+    import numpy as np
+    s = np.asarray(samples, dtype=np.float64).reshape(1, -1)
+    q = np.asarray(queries, dtype=np.float64).reshape(-1, 1)
+    e = -0.5 * ((q - s) / bandwidth) ** 2
+    m = e.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(e - m).sum(axis=1))
+    return torch.from_numpy((lse - np.log(s.shape[1] * bandwidth * np.sqrt(2.0 * np.pi))).astype("float32"))
+
+
+def kde_log_normaliser(samples, bandwidth: float):
+    """cst_log_dens of MSGMsde.__init__ (SDEs.py:255-265): log of the rectangle-rule integral of the KDE over 1000
+    points spanning [min r_T, max r_T]."""
+    r = torch.as_tensor(samples, dtype=torch.float32).reshape(-1)
+    grid = torch.linspace(float(r.min()), float(r.max()), 1000)
+    dens = torch.exp(kde_logpdf(r, bandwidth, grid))
+    return torch.log(dens.sum() * (grid[1] - grid[0]))
+
+
+def log_latent_pdf(sde, yT, bandwidth: float, cst_log_dens):
+    """MSGMsde.log_latent_pdf (SDEs.py:503-509): KDE log-density of |y_T| minus the normalising constant."""
+    r = torch.linalg.norm(yT, dim=1)
+    return kde_logpdf(sde.r_T, bandwidth, r) - cst_log_dens
+
+
 # ----------------------------------------------------------------------------------------------------------
 # synthetic data of the reference driver (data.py:702-778); numpy/sklearn RNG like the reference
 # ----------------------------------------------------------------------------------------------------------

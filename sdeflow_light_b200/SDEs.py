@@ -229,19 +229,34 @@ class MSGMsde(SDE):
             self.name_SDE += "logNorm"
         self.cst_log_dens = 0
         if estim_cst_norm_dens_r_T or plot_validate:
-            rr = self.r_T.reshape(-1, 1).cpu()
-            grid = torch.linspace(float(rr.min()), float(rr.max()), 1000).reshape(1000, 1)
-            dens = torch.exp(torch.tensor(self.kde.score_samples(grid)).to(torch.float32))
-            self.cst_log_dens = torch.log(torch.sum(dens, dim=0) * (grid[1, 0] - grid[0, 0])).to(self.device)
+            # log of the rectangle-rule integral of the KDE over 1000 points spanning the radii (SDEs.py:255-265)
+            grid = torch.linspace(float(self.r_T.min()), float(self.r_T.max()), 1000, device=self.r_T.device)
+            dens = torch.exp(self._kde_logpdf(grid))
+            self.cst_log_dens = torch.log(torch.sum(dens, dim=0) * (grid[1] - grid[0])).to(self.device)
         gc.collect()
 
     @property
     def kde(self):
+        """sklearn KernelDensity object like the reference's attribute (SDEs.py:240), fitted lazily for callers that
+        want the estimator itself; the package's own density evaluations run on the GPU (``_kde_logpdf``)."""
         if self._kde is None:
             from sklearn.neighbors import KernelDensity
             self._kde = KernelDensity(kernel=self._kernel, bandwidth=self._bandwidth).fit(
                 self.r_T.reshape(-1, 1).detach().cpu())
         return self._kde
+
+    def _kde_logpdf(self, r):
+        """log KDE density of the radii at ``r`` (msgm_kde_logpdf: exact Gaussian-kernel sum, one CTA per query) --
+        replaces ``kde.score_samples`` (SDEs.py:261,509)."""
+        if self._kernel != "gaussian":
+            raise NotImplementedError(f"kernel '{self._kernel}': only the reference's default 'gaussian' is built")
+        dev = r.device
+        rT = _lib.f32c(self.r_T.reshape(-1), dev)
+        q = _lib.f32c(r.reshape(-1), dev)
+        out = torch.empty_like(q)
+        _lib.check(_lib.lib().msgm_kde_logpdf(_lib.ctx(dev), _lib.ptr(rT), rT.numel(), float(self._bandwidth), _lib.ptr(q),
+                                              _lib.ptr(out), q.numel(), _lib.stream_ptr(dev)))
+        return out
 
     def _kind(self):
         return _lib.SDE_MSGM_SPARSE if self.sparseTensor else _lib.SDE_MSGM_DENSE
@@ -340,8 +355,8 @@ class MSGMsde(SDE):
         return r_x * randu_on_sphere((x.shape[0], self.dim), device=self.device)
 
     def log_latent_pdf(self, yT):
-        r = torch.linalg.norm(yT.detach(), dim=1).reshape(-1, 1)
-        return torch.tensor(self.kde.score_samples(r.cpu())).to(torch.float32).to(self.device) - self.cst_log_dens
+        r = torch.linalg.norm(yT.detach().to(self.device), dim=1)
+        return self._kde_logpdf(r) - self.cst_log_dens
 
 
 def _latent(sde, num_samples, d, r_sorted, log_map, seed, particle_offset, U=None, Z=None):

@@ -37,6 +37,7 @@ int philox_normal(msgm_ctx*, float*, int, int64_t, float, uint64_t, uint64_t, ui
 int latent_sample(msgm_ctx*, const float*, int, int, int, const float*, const float*, float*, int, int64_t, uint64_t,
                   uint64_t, cudaStream_t);
 int mmd_sums(msgm_ctx*, const float*, int64_t, const float*, int64_t, int, double*, cudaStream_t);
+int kde_logpdf(msgm_ctx*, const float*, int, float, const float*, float*, int, cudaStream_t);
 
 int conv1d(msgm_ctx*, const msgm_conv1d_desc*, cudaStream_t);
 int emb_fold(msgm_ctx*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -260,6 +261,15 @@ int msgm_mmd_sums(msgm_ctx* ctx, const float* x, int64_t N, const float* y, int6
   if (!ctx || !x || !y || !sums_out || d < 1 || N < 1 || M < 1) return invalid("msgm_mmd_sums: bad argument");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return mmd_sums(ctx, x, N, y, M, d, sums_out, (cudaStream_t)stream);
+}
+
+int msgm_kde_logpdf(msgm_ctx* ctx, const float* samples, int32_t n, float bandwidth, const float* queries, float* out,
+                    int32_t m, void* stream) {
+  if (!ctx || !samples || !queries || !out || n < 1 || m < 0 || !(bandwidth > 0.0f))
+    return invalid("msgm_kde_logpdf: bad argument");
+  if (m == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return kde_logpdf(ctx, samples, n, bandwidth, queries, out, m, (cudaStream_t)stream);
 }
 
 int msgm_conv1d(msgm_ctx* ctx, const msgm_conv1d_desc* D, void* stream) {

@@ -8,6 +8,8 @@
 //                       broadcast (800 MB at N = M = 1e4, d = 2).
 #include <algorithm>
 
+#include <cmath>
+
 #include "msgm_common.cuh"
 
 namespace msgm {
@@ -126,6 +128,53 @@ int latent_sample(msgm_ctx* ctx, const float* rT_sorted, int n_r, int log_map, i
   const long long warps = std::min<long long>(B, (long long)ctx->num_sms * 64);
   const int grid = (int)((warps * 32 + 255) / 256);
   latent_sample_kernel<<<grid, 256, 0, stream>>>(rT_sorted, n_r, log_map, msgm, U, Z, out, d, B, seed, poff);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+// ---- 1-D Gaussian kernel density, log pdf at the query points (sklearn KernelDensity.score_samples, exact sum) -------
+// out_q = logsumexp_i( -((q - s_i)/h)^2 / 2 ) - log(n h sqrt(2 pi)): one CTA per query, per-thread online logsumexp
+// over a strided slice of the samples, then a block-level combine.
+__global__ void __launch_bounds__(256) kde_logpdf_kernel(const float* __restrict__ samples, int n, float inv_h,
+                                                         float log_norm, const float* __restrict__ queries,
+                                                         float* __restrict__ out, int m) {
+  __shared__ float sM[8], sS[8];
+  for (int q = blockIdx.x; q < m; q += gridDim.x) {
+    const float x = queries[q];
+    float mx = -INFINITY, sum = 0.0f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const float u = (x - __ldg(samples + i)) * inv_h;
+      const float e = -0.5f * u * u;
+      if (e > mx) { sum = sum * expf(mx - e) + 1.0f; mx = e; }
+      else sum += expf(e - mx);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, mx, o), s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mm = fmaxf(mx, m2);
+      sum = (mx == -INFINITY ? 0.0f : sum * expf(mx - mm)) + (m2 == -INFINITY ? 0.0f : s2 * expf(m2 - mm));
+      mx = mm;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sM[threadIdx.x >> 5] = mx; sS[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float mm = sM[0], ss = sS[0];
+      for (int w = 1; w < 8; ++w) {
+        const float m2 = sM[w], s2 = sS[w], mn = fmaxf(mm, m2);
+        ss = (mm == -INFINITY ? 0.0f : ss * expf(mm - mn)) + (m2 == -INFINITY ? 0.0f : s2 * expf(m2 - mn));
+        mm = mn;
+      }
+      out[q] = mm + logf(ss) - log_norm;
+    }
+  }
+}
+
+int kde_logpdf(msgm_ctx* ctx, const float* samples, int n, float bandwidth, const float* queries, float* out, int m,
+               cudaStream_t stream) {
+  const float log_norm = (float)(std::log((double)n) + std::log((double)bandwidth) + 0.5 * std::log(2.0 * 3.14159265358979323846));
+  kde_logpdf_kernel<<<std::min(m, ctx->num_sms * 8), 256, 0, stream>>>(samples, n, 1.0f / bandwidth, log_norm, queries, out, m);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

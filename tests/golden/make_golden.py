@@ -141,6 +141,33 @@ def misc_case(ref):
           x0=x0.numpy(), mmd_a=a.numpy(), mmd_b=b.numpy(), mmd=np.float32(mmd))
 
 
+def elbo_case(ref):
+    """ELBO pieces (NN.py:123-128, SDEs.py:495-509,708-721): the KDE log-density of the radii with its normalising
+    constant (sklearn on the reference side), and the reference's ELBO mean over a large test set."""
+    torch.manual_seed(61)
+    x_init = torch.randn(3000, 2) * torch.tensor([1.5, 0.7])
+    T = ref_live.T_param(1.0)
+    base = ref.SDEs.MSGMsde(x_init, beta_min=0.1, beta_max=20.0, t_epsilon=1e-3, T=T, num_steps_forward=16,
+                            device="cpu", estim_cst_norm_dens_r_T=True, norm_sampler="ecdf", norm_map="log",
+                            denseTensor=True, plot_validate=False)
+    net = ref.NN.MLP(input_dim=2, index_dim=1, hidden_dim=128, premodule="NormalizeLogRadius")
+    gen = ref.SDEs.PluginReverseSDE(base, net, T, vtype="rademacher", debias=False, ssm_intT=False,
+                                    deviceReverseSDE="cpu")
+    yT = torch.randn(300, 2) * 2.0
+    logpdf = base.log_latent_pdf(yT)
+    x_test = torch.randn(4096, 2) * torch.tensor([1.5, 0.7])
+    torch.manual_seed(62)
+    gen.eval()
+    with torch.enable_grad():
+        elbo = gen.elbo_random_t_slice(x_test).detach()
+    arrays = dict(x_init=x_init.numpy(), yT=yT.numpy(), logpdf=logpdf.numpy(), x_test=x_test.numpy(),
+                  cst_log_dens=np.float32(base.cst_log_dens), bandwidth=np.float32(base.kde.bandwidth),
+                  elbo_mean=np.float32(elbo.mean()), elbo_std=np.float32(elbo.std()), **_sde_arrays(base),
+                  **_net_arrays(net))
+    _save("misc_elbo", dict(kind="msgm_dense", dim=2, premodule=True, beta_min=0.1, beta_max=20.0, T=1.0,
+                            t_epsilon=1e-3, num_steps_forward=16, norm_map="log"), **arrays)
+
+
 def unet1d_case(ref, name, kind, L, B, N, seed, pre="NormalizeLogRadius"):
     """UNet1D score net (NNUnet1D.py) on 1-D signals of length L: forward, RK4 reverse sampling, SSM loss + gradients."""
     torch.manual_seed(seed)
@@ -238,6 +265,9 @@ def unet2d_case(ref, name, S, B, N, seed, pre="NormalizeLogRadius", order="F"):
 
 def main():
     ref = ref_live.load()
+    if "--elbo-only" in sys.argv:
+        elbo_case(ref)
+        return
     if "--unet2d-only" in sys.argv:
         unet2d_case(ref, "w01_unet2d_sparse_16x16", 16, 4, 2, 51)
         return
@@ -265,6 +295,7 @@ def main():
     ssm_case(ref, "t03_ssm_sparse_d8", "msgm_sparse", 8, P, 24, 23)
     ssm_case(ref, "t04_ssm_msgm_d16", "msgm_dense", 16, P, 16, 24)
     misc_case(ref)
+    elbo_case(ref)
     unet1d_case(ref, "u01_unet1d_sparse_L64", "msgm_sparse", 64, 6, 4, 41)
     unet1d_case(ref, "u02_unet1d_sgm_L48", "sgm", 48, 5, 3, 42, pre=None)
     unet2d_case(ref, "w01_unet2d_sparse_16x16", 16, 4, 2, 51)

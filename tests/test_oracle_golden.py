@@ -67,3 +67,15 @@ def test_noise_forward_replay():
                                  noise=arr["singles"][j][None, None])[0]
             j += 1
     assert float((cap - arr["y"]).abs().max()) <= TOL
+
+
+def test_kde_log_density_fixture():
+    """The oracle's exact Gaussian-kernel sum against the reference's sklearn KernelDensity.score_samples and its
+    normalising constant (SDEs.py:240,255-265,503-509)."""
+    meta, arr = G.load("misc_elbo")
+    sde, _ = G.oracle_objects(meta, arr)
+    h, cst = float(arr["bandwidth"]), float(arr["cst_log_dens"])
+    assert abs(h - 0.1 * float(torch.std(arr["r_T"]))) <= 1e-7
+    assert abs(float(O.kde_log_normaliser(arr["r_T"], h)) - cst) <= 2e-6
+    got = O.log_latent_pdf(sde, arr["yT"], h, cst)
+    assert float((got - arr["logpdf"]).abs().max()) <= 2e-5 * (1 + float(arr["logpdf"].abs().max()))

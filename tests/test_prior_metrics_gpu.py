@@ -57,3 +57,40 @@ def test_mmd_matches_reference_and_oracle():
         assert abs(got - ref) < 2e-6
     big = torch.randn(20_000, 2, device=DEV)  # the reference would need 2 x 3.2 GB broadcasts here
     assert abs(float(QC.compute_mmd(big, big))) < 1e-6
+
+
+def test_kde_log_latent_pdf_and_elbo():
+    """MSGMsde.log_latent_pdf / cst_log_dens on the GPU KDE kernel against the reference's sklearn values
+    (SDEs.py:240,255-265,503-509), and NN.evaluate (ELBO, NN.py:123-128) against the reference's mean on the same
+    test set (a Monte-Carlo estimate: agreement within 5 standard errors)."""
+    meta, arr = G.load("misc_elbo")
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(arr["x_init"], beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=True, norm_map="log",
+                     num_steps_forward=16, device=DEV, estim_cst_norm_dens_r_T=True)
+    assert abs(base._bandwidth - float(arr["bandwidth"])) < 1e-7
+    assert float((base.r_T.cpu() - arr["r_T"]).abs().max()) < 1e-6
+    cst = float(base.cst_log_dens)
+    lp = base.log_latent_pdf(arr["yT"].to(DEV)).cpu()
+    err = float((lp - arr["logpdf"]).abs().max())
+    Bd.report(test="kde-logpdf", max_abs=err, ref_max=float(arr["logpdf"].abs().max()), cst=cst, cst_ref=float(arr["cst_log_dens"]))
+    assert abs(cst - float(arr["cst_log_dens"])) < 5e-6
+    assert err < 2e-5 * (1 + float(arr["logpdf"].abs().max()))
+    # oracle on fresh queries, including far tails (log-sum-exp must not underflow)
+    q = torch.cat([torch.randn(500, 2) * 3, torch.tensor([[1e-4, 0.0], [40.0, 40.0]])])
+    ref = O.log_latent_pdf(G.oracle_objects(meta, arr)[0], q, float(arr["bandwidth"]), float(arr["cst_log_dens"]))
+    got = base.log_latent_pdf(q.to(DEV)).cpu()
+    assert bool(torch.isfinite(got).all()) and float(((got - ref).abs() / (1 + ref.abs())).max()) < 2e-5
+    # ELBO through the package's kernels
+    base.G, base.L_G = arr["G"].to(DEV), arr["L_G"].to(DEV)
+    net = P.MLP(2, premodule="NormalizeLogRadius").to(DEV)
+    with torch.no_grad():
+        for i, l in enumerate(net.linears()):
+            l.weight.copy_(arr[f"W{i}"])
+            l.bias.copy_(arr[f"b{i}"])
+    gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
+    torch.manual_seed(5)
+    mean, stderr = P.NN.evaluate(gen, arr["x_test"].to(DEV))
+    ref_se = float(arr["elbo_std"]) / 4096 ** 0.5
+    Bd.report(test="elbo-evaluate", mean=float(mean), stderr=float(stderr), ref_mean=float(arr["elbo_mean"]), ref_stderr=ref_se)
+    assert abs(float(mean) - float(arr["elbo_mean"])) < 5 * (ref_se ** 2 + float(stderr) ** 2) ** 0.5
+    assert 0.5 < float(stderr) / ref_se < 2.0

@@ -329,7 +329,13 @@ class MSGMsde(SDE):
         if self.norm_sampler == "ecdf":
             r_gen = torch.quantile(self.r_T, U).reshape(num_samples, 1)
         else:
-            r_gen = torch.from_numpy(self.kde.sample(num_samples)).to(torch.float32).to(self.device)
+            # a draw from the Gaussian KDE = a random radius sample + N(0, h^2), on the device (the reference's
+            # kde.sample branch raises NameError at SDEs.py:444; same law, no host round trip)
+            if self._kernel != "gaussian":
+                raise NotImplementedError(f"kernel '{self._kernel}': only the reference's default 'gaussian' is built")
+            idx = torch.randint(0, self.r_T.numel(), (num_samples,), device=self.device)
+            r_gen = (self.r_T.reshape(-1)[idx] + self._bandwidth * torch.randn(num_samples, device=self.device)
+                     ).reshape(num_samples, 1)
             if self.norm_map != "log":
                 r_gen = r_gen.clamp_min(0.)
         if self.norm_map == "log":
@@ -339,7 +345,7 @@ class MSGMsde(SDE):
     def latent_sample(self, num_samples, n, *, seed=None, particle_offset=0, U=None, Z=None):
         """x_0 = r s with r from the empirical radius law and s uniform on the sphere (reference SDEs.py:438-493): one
         fused kernel (sorted radius table, in-kernel Philox keyed by the global particle index).  ``U`` / ``Z`` inject the
-        reference's uniform / normal draws.  The KDE radius sampler keeps the reference's sklearn path."""
+        reference's uniform / normal draws."""
         if self.norm_sampler != "ecdf":
             return self.gen_radial_distribution(num_samples) * randu_on_sphere((num_samples, self.dim), device=self.device)
         return _latent(self, num_samples, self.dim, self._sorted_radii(), self.norm_map == "log", seed, particle_offset, U, Z)

@@ -215,6 +215,22 @@ typedef struct {
   int32_t B, C1, C2, Cout, K, stride, up, Hs, Ws, G, prologue;
 } msgm_conv2d_desc;
 int msgm_conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* desc, void* stream);
+/* Tensor-core form of msgm_conv2d (tcgen05, fp16 x 3 split operands, fp32 accumulate: fp32-level parity): 3x3 (padding 1)
+ * or 1x1, stride 1|2, C1 % 16 == 0, (C1 + C2) % 16 == 0, Cout % 32 == 0.  `wimg` is the packed weight image written by
+ * msgm_conv2d_tc_pack (msgm_conv2d_tc_pack_bytes bytes; pack once per weight tensor).  `ss` (B, C1 + C2, 2) is the
+ * GroupNorm of the input folded into a per-(sample, channel) scale / shift by msgm_gn_scale_shift (NULL: no norm);
+ * prologue 1 = normalise, 2 = normalise + SiLU, applied while the input tile is staged. */
+typedef struct {
+  const float* x1; const float* x2; const void* wimg; const float* bias; const float* ebias; const float* res;
+  const float* ss; float* out;
+  int32_t B, C1, C2, Cout, K, stride, up, Hs, Ws, prologue;
+} msgm_conv2d_tc_desc;
+int msgm_conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* desc, void* stream);
+int64_t msgm_conv2d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K);
+int msgm_conv2d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, int32_t K, void* wimg, void* stream);
+/* ss[b, c] = (rstd gamma_c, beta_c - mean rstd gamma_c) with the GroupNorm32 statistics of [x1, x2] (eps 1e-5). */
+int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,
+                        int32_t B, const float* gamma, const float* beta, float* ss, void* stream);
 /* GroupNorm32 statistics (model/nn_utils.py:39-41,107-114): stats (B,G,2) = mean, 1/sqrt(var + 1e-5) of [x1, x2]. */
 int msgm_gn_stats(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G, int32_t B,
                   float* stats, void* stream);

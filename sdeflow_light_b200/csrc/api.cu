@@ -48,6 +48,10 @@ int normalize_log_radius(msgm_ctx*, const float*, float*, float*, int, int, cuda
 
 int gn_stats(msgm_ctx*, const float*, int, const float*, int, int, int, int, float*, cudaStream_t);
 int conv2d(msgm_ctx*, const msgm_conv2d_desc*, cudaStream_t);
+int conv2d_tc(msgm_ctx*, const msgm_conv2d_tc_desc*, cudaStream_t);
+size_t conv2d_tc_pack_bytes(int, int, int);
+int conv2d_tc_pack(msgm_ctx*, const float*, int, int, int, void*, cudaStream_t);
+int gn_scale_shift(msgm_ctx*, const float*, int, const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int emb_proj(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int sincos_embed_mlp(msgm_ctx*, const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
                      int, cudaStream_t);
@@ -334,6 +338,44 @@ int msgm_conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* D, void* stream) {
   if (D->B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return conv2d(ctx, D, (cudaStream_t)stream);
+}
+
+static bool conv2d_tc_shape_ok(int Cout, int Cin, int C1, int K) {
+  return (K == 1 || K == 3) && Cout >= 32 && Cout % 32 == 0 && Cin >= 16 && Cin % 16 == 0 && C1 % 16 == 0;
+}
+
+int msgm_conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* D, void* stream) {
+  if (!ctx || !D || !D->x1 || !D->wimg || !D->out) return invalid("msgm_conv2d_tc: NULL argument");
+  const int Cin = D->C1 + (D->x2 ? D->C2 : 0);
+  if (!conv2d_tc_shape_ok(D->Cout, Cin, D->C1, D->K) || D->stride < 1 || D->stride > 2 || (D->up != 1 && D->up != 2) ||
+      D->Hs < 1 || D->Ws < 1 || D->B < 0 || (D->stride == 2 && ((D->Hs * D->up) % 2 || (D->Ws * D->up) % 2 || D->K != 3)))
+    return invalid("msgm_conv2d_tc: unsupported shape (k in {1,3}, Cin % 16 == 0, C1 % 16 == 0, Cout % 32 == 0, stride <= 2)");
+  if (D->prologue && !D->ss) return invalid("msgm_conv2d_tc: prologue without a scale/shift table");
+  if (D->B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv2d_tc(ctx, D, (cudaStream_t)stream);
+}
+
+int64_t msgm_conv2d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K) {
+  if (!conv2d_tc_shape_ok(Cout, Cin, 0, K)) return -1;
+  return (int64_t)conv2d_tc_pack_bytes(Cout, Cin, K);
+}
+
+int msgm_conv2d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, int32_t K, void* wimg, void* stream) {
+  if (!ctx || !W || !wimg) return invalid("msgm_conv2d_tc_pack: NULL argument");
+  if (!conv2d_tc_shape_ok(Cout, Cin, 0, K)) return invalid("msgm_conv2d_tc_pack: unsupported shape");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv2d_tc_pack(ctx, W, Cout, Cin, K, wimg, (cudaStream_t)stream);
+}
+
+int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,
+                        int32_t B, const float* gamma, const float* beta, float* ss, void* stream) {
+  if (!ctx || !x1 || !gamma || !beta || !ss || C1 < 1 || G < 1 || HW < 1 || B < 0) return invalid("msgm_gn_scale_shift: bad argument");
+  const int C = C1 + (x2 ? C2 : 0);
+  if (C % G || C / G > 256) return invalid("msgm_gn_scale_shift: channels not divisible by groups");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return gn_scale_shift(ctx, x1, C1, x2, C2, HW, G, B, gamma, beta, ss, (cudaStream_t)stream);
 }
 
 int msgm_gn_stats(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G, int32_t B,

@@ -1,0 +1,365 @@
+// 2-D U-Net convolutions on tcgen05 (model/unet.py:40-250: ResBlock / AttentionBlock / Upsample / Downsample convs).
+//
+// The conv is evaluated as a "shift GEMM" over a zero-padded LINEAR index space.  Every image is laid out with its
+// padding ring, (Hp, Wp) = (Hi + 2 PAD, Wi + 2 PAD), and all images are stacked: p = (b Hp + r) Wp + c.  For an interior
+// position p the 3x3 tap (ky, kx) reads position p + (ky-1) Wp + (kx-1) of the same image, so
+//     D[p, co] = sum_tap sum_ci A[p + off_tap, ci] W[co, ci, tap]
+// is nine GEMMs whose A operands are the SAME staged tile read at nine start addresses: in the canonical no-swizzle
+// K-major core-matrix layout with SBO = 128 B a row is 16 bytes, so a tap shift is a 16-byte multiple added to the
+// descriptor's start address.  No im2col copy exists anywhere.  Positions on the padding ring produce garbage rows that
+// the epilogue skips (efficiency Hi Wi / (Hp Wp): 0.89 at 32x32).
+//
+//   * CTA = MB x 128 consecutive positions x NOUT output channels; accumulators (MB x NOUT fp32 columns) in TMEM;
+//   * K loop over chunks of 16 input channels, double-buffered: 8 stager warps read the chunk's halo tile from global
+//     memory (NCHW fp32, the concat [x1, x2] in place, nearest x2 upsampling folded into the index), apply the
+//     GroupNorm scale/shift (+ SiLU) ON THE FLY, split each value into fp16 hi + lo and write the four planes
+//     [hi|lo][8-channel k-chunk][position][8] to shared memory; the chunk's packed weights (hi + lo, every tap) arrive by
+//     one TMA bulk copy; a ninth warp issues MB x taps x 3 tcgen05.mma (Ahi Whi + Alo Whi + Ahi Wlo: the fp16 x 3
+//     split keeps ~22 mantissa bits, i.e. fp32-level parity with the reference, at tensor-pipe speed) and commits to
+//     the buffer's "empty" mbarrier;
+//   * epilogue: tcgen05.ld, + bias[co] + ebias[b, co] (ResBlock embedding term) + residual, NCHW stores (lanes =
+//     consecutive positions -> coalesced); stride 2 (Downsample) keeps every second row / column.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "msgm_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace msgm {
+
+struct ConvTcParams {
+  const float* x1; int C1;
+  const float* x2; int C2;
+  const unsigned char* wimg;  // packed by conv2d_tc_pack_kernel: [ntile][chunk][tap][hi|lo][kc][NOUT][8] fp16
+  const float* bias;          // (Cout) or NULL
+  const float* ebias;         // (B, Cout) or NULL
+  const float* res;           // (B, Cout, Ho, Wo) or NULL
+  const float* ss;            // (B, Cin, 2) GroupNorm scale / shift or NULL
+  float* out;
+  int silu;                   // apply SiLU after the affine normalisation
+  int B, Cout, stride, up, Hs, Ws;  // (Hs, Ws): stored input size; the conv sees (Hs up, Ws up)
+  int Hi, Wi, Hp, Wp, Ho, Wo;
+  int halo, SL, MB, NC;       // halo = PAD (Wp + 1); SL = 128 MB + 2 halo staged positions; NC = Cin / 16 chunks
+  long long total;            // B Hp Wp
+  int tmem_cols;
+  int* flags;
+};
+
+__device__ __forceinline__ float silu_acc(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+constexpr int CTC_STAGERS = 256;
+
+template <int NOUT, int KS>
+__global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __grid_constant__ ConvTcParams P) {
+  constexpr int NT = KS * KS, PAD = KS / 2;
+  constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;  // bytes of packed weights per 16-channel chunk
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  // carve: [barriers 128 B][A stage 0][A stage 1][W stage 0][W stage 1], 128-byte aligned
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);  // [2]
+  uint64_t* bar_empty = bar_full + 2;                      // [2]
+  uint64_t* bar_done = bar_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 5);
+  const int PS = P.SL * 16;                                // plane stride (bytes)
+  const int ASTAGE = 4 * PS;
+  unsigned char* sA = smem + 128;
+  unsigned char* sW = sA + 2 * ASTAGE;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long p0 = (long long)blockIdx.x * (128 * P.MB);
+  const int co0 = blockIdx.y * NOUT;
+  const int HpWp = P.Hp * P.Wp;
+  const int Cin = P.C1 + P.C2;
+  const int HWs = P.Hs * P.Ws;
+
+  if (tid == CTC_STAGERS) {
+    mbar_init(bar_full + 0, CTC_STAGERS + 1);
+    mbar_init(bar_full + 1, CTC_STAGERS + 1);
+    mbar_init(bar_empty + 0, 1);
+    mbar_init(bar_empty + 1, 1);
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == CTC_STAGERS / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == CTC_STAGERS / 32) {
+    // ================================================ MMA issuer ==================================================
+    const uint32_t idesc = umma_idesc_f16(128, NOUT);
+    bool ok = true;
+    for (int k = 0; k < P.NC && ok; ++k) {
+      const int buf = k & 1;
+      ok = mbar_wait(bar_full + buf, (uint32_t)((k >> 1) & 1), P.flags);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA + buf * ASTAGE);
+      const uint32_t w_base = smem_u32(sW + buf * WSTAGE);
+      for (int mb = 0; mb < P.MB; ++mb) {
+        const uint32_t dcol = tbase + (uint32_t)(mb * NOUT);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int toff = KS == 3 ? (t / 3 - 1) * P.Wp + (t % 3 - 1) : 0;
+          const uint32_t a_hi = a_base + (uint32_t)((mb * 128 + P.halo + toff) * 16);
+          const uint32_t a_lo = a_hi + 2u * (uint32_t)PS;
+          const uint32_t w_hi = w_base + (uint32_t)(t * 4 * NOUT * 16);
+          const uint32_t w_lo = w_hi + 2u * NOUT * 16;
+          const uint64_t dAh = umma_desc(a_hi, PS, 128), dAl = umma_desc(a_lo, PS, 128);
+          const uint64_t dWh = umma_desc(w_hi, NOUT * 16, 128), dWl = umma_desc(w_lo, NOUT * 16, 128);
+          umma_ss(dcol, dAh, dWh, idesc, (k > 0 || t > 0) ? 1u : 0u, 0);
+          umma_ss(dcol, dAl, dWh, idesc, 1u, 0);
+          umma_ss(dcol, dAh, dWl, idesc, 1u, 0);
+        }
+      }
+      umma_commit(bar_empty + buf, 0);
+    }
+    umma_commit(bar_done, 0);
+    __syncwarp();
+  } else {
+    // ================================================== stagers ===================================================
+    bool ok = true;
+    for (int k = 0; k < P.NC && ok; ++k) {
+      const int buf = k & 1;
+      if (k >= 2) {
+        ok = mbar_wait(bar_empty + buf, (uint32_t)(((k >> 1) - 1) & 1), P.flags);
+        tc_fence_after();
+      }
+      unsigned char* wdst = sW + buf * WSTAGE;
+      if (tid == 0) {
+        mbar_expect_tx(bar_full + buf, (uint32_t)WSTAGE);
+        tma_bulk_g2s(wdst, P.wimg + ((size_t)blockIdx.y * P.NC + k) * WSTAGE, (uint32_t)WSTAGE, bar_full + buf);
+      }
+      unsigned char* adst = sA + buf * ASTAGE;
+      for (int e = tid; e < 2 * P.SL; e += CTC_STAGERS) {
+        const int kc = e >= P.SL ? 1 : 0, s = e - kc * P.SL;
+        const long long q = p0 - P.halo + s;
+        uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
+        if (q >= 0 && q < P.total) {
+          const int b = (int)(q / HpWp), rem = (int)(q - (long long)b * HpWp);
+          const int r = rem / P.Wp - PAD, c = rem % P.Wp - PAD;
+          if (r >= 0 && r < P.Hi && c >= 0 && c < P.Wi) {
+            const int ch0 = k * 16 + kc * 8;  // 8 consecutive input channels; a chunk never straddles x1 | x2 (C1 % 16 == 0)
+            const float* src = ch0 < P.C1 ? P.x1 + ((size_t)b * P.C1 + ch0) * HWs : P.x2 + ((size_t)b * P.C2 + (ch0 - P.C1)) * HWs;
+            src += (r / P.up) * P.Ws + (c / P.up);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (size_t)j * HWs);
+            if (P.ss) {
+              const float4* ssp = reinterpret_cast<const float4*>(P.ss + ((size_t)b * Cin + ch0) * 2);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 a = __ldg(ssp + j);
+                v[2 * j] = fmaf(v[2 * j], a.x, a.y);
+                v[2 * j + 1] = fmaf(v[2 * j + 1], a.z, a.w);
+              }
+              if (P.silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = silu_acc(v[j]);
+              }
+            }
+            split2_f16(v[0], v[1], hi4.x, lo4.x);
+            split2_f16(v[2], v[3], hi4.y, lo4.y);
+            split2_f16(v[4], v[5], hi4.z, lo4.z);
+            split2_f16(v[6], v[7], hi4.w, lo4.w);
+          }
+        }
+        *reinterpret_cast<uint4*>(adst + kc * PS + s * 16) = hi4;
+        *reinterpret_cast<uint4*>(adst + (2 + kc) * PS + s * 16) = lo4;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_full + buf);
+    }
+
+    // ================================================== epilogue ==================================================
+    ok = ok && mbar_wait(bar_done, 0, P.flags);
+    tc_fence_after();
+    const int q4 = warp & 3, half = warp >> 2;
+    constexpr int NH = NOUT / 2;
+    const int HWo = P.Ho * P.Wo;
+    for (int mb = 0; mb < P.MB; ++mb) {
+      const long long p = p0 + mb * 128 + q4 * 32 + lane;
+      bool valid = ok && p < P.total;
+      int b = 0, oy = 0, ox = 0;
+      if (valid) {
+        b = (int)(p / HpWp);
+        const int rem = (int)(p - (long long)b * HpWp);
+        const int r = rem / P.Wp - PAD, c = rem % P.Wp - PAD;
+        valid = r >= 0 && r < P.Hi && c >= 0 && c < P.Wi;
+        if (P.stride == 2) {
+          valid = valid && !(r & 1) && !(c & 1);
+          oy = r >> 1; ox = c >> 1;
+        } else {
+          oy = r; ox = c;
+        }
+      }
+      const uint32_t taddr = tbase + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mb * NOUT + half * NH);
+#pragma unroll 1
+      for (int cc = 0; cc < NH; cc += 16) {
+        uint32_t rr[16];
+        TMEM_LD16(taddr + cc, rr);
+        tc_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = co0 + half * NH + cc + j;
+            float v = __uint_as_float(rr[j]);
+            if (P.bias) v += __ldg(P.bias + co);
+            if (P.ebias) v += __ldg(P.ebias + (size_t)b * P.Cout + co);
+            const size_t o = ((size_t)b * P.Cout + co) * HWo + oy * P.Wo + ox;
+            if (P.res) v += __ldg(P.res + o);
+            P.out[o] = v;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == CTC_STAGERS / 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(P.tmem_cols));
+}
+
+// ---- weight packing: (Cout, Cin, K, K) fp32 -> [ntile][chunk][tap][hi|lo][kc][NOUT][8] fp16 ---------------------------
+__global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int Cin, int KK, int NOUT, __half* __restrict__ img,
+                                      long long nel) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  const int j = (int)(e % 8);
+  long long r = e / 8;
+  const int n = (int)(r % NOUT); r /= NOUT;
+  const int kc = (int)(r % 2); r /= 2;
+  const int hl = (int)(r % 2); r /= 2;
+  const int t = (int)(r % KK); r /= KK;
+  const int NC = Cin / 16;
+  const int k = (int)(r % NC);
+  const int nt = (int)(r / NC);
+  const int co = nt * NOUT + n, ci = k * 16 + kc * 8 + j;
+  const float v = W[((size_t)co * Cin + ci) * KK + t];
+  const __half hi = __float2half_rn(v);
+  img[e] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+}
+
+// ---- GroupNorm as a per-(sample, channel) affine map: ss[b, c] = (rstd gamma_c, beta_c - mean rstd gamma_c) -------------
+// (GroupNorm32, model/nn_utils.py:39-41,107-114; statistics over channels [g cpg, (g+1) cpg) x HW of the concat [x1, x2])
+__global__ void __launch_bounds__(256) gn_scale_shift_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
+                                                             int C2, int HW, int G, float eps, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ ss) {
+  __shared__ float rs[8], rq[8], mr[2];
+  const int b = blockIdx.x / G, g = blockIdx.x % G, C = C1 + C2, cpg = C / G, tid = threadIdx.x;
+  const int n = cpg * HW;
+  float s = 0.0f, q = 0.0f;
+  for (int e = tid; e < n; e += 256) {
+    const int c = g * cpg + e / HW, p = e % HW;
+    const float v = c < C1 ? x1[((size_t)b * C1 + c) * HW + p] : x2[((size_t)b * C2 + (c - C1)) * HW + p];
+    s += v;
+    q = fmaf(v, v, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((tid & 31) == 0) { rs[tid >> 5] = s; rq[tid >> 5] = q; }
+  __syncthreads();
+  if (tid == 0) {
+    float ts = 0.0f, tq = 0.0f;
+    for (int w = 0; w < 8; ++w) { ts += rs[w]; tq += rq[w]; }
+    const float mean = ts / n, var = fmaxf(tq / n - mean * mean, 0.0f);
+    mr[0] = mean;
+    mr[1] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  if (tid < cpg) {
+    const int c = g * cpg + tid;
+    const float sc = mr[1] * gamma[c];
+    ss[((size_t)b * C + c) * 2] = sc;
+    ss[((size_t)b * C + c) * 2 + 1] = fmaf(-mr[0], sc, beta[c]);
+  }
+}
+
+// ---- host dispatch ---------------------------------------------------------------------------------------------------
+int conv2d_tc_nout(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32); }
+
+size_t conv2d_tc_pack_bytes(int Cout, int Cin, int K) { return (size_t)Cout * Cin * K * K * 2 * 2; }
+
+int conv2d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cin, int K, void* img, cudaStream_t stream) {
+  const long long nel = (long long)Cout * Cin * K * K * 2;
+  conv2d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cin, K * K, conv2d_tc_nout(Cout),
+                                                                          reinterpret_cast<__half*>(img), nel);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int gn_scale_shift(msgm_ctx* ctx, const float* x1, int C1, const float* x2, int C2, int HW, int G, int B, const float* gamma,
+                   const float* beta, float* ss, cudaStream_t stream) {
+  if (B == 0) return MSGM_OK;
+  gn_scale_shift_kernel<<<B * G, 256, 0, stream>>>(x1, C1, x2, x2 ? C2 : 0, HW, G, 1e-5f, gamma, beta, ss);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+template <int NOUT, int KS>
+static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
+  constexpr int NT = KS * KS;
+  constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;
+  // M blocks per CTA: as many as TMEM (512 columns) and shared memory allow while still giving every SM a tile
+  const long long nblk = (P.total + 127) / 128;
+  int MB = 4;
+  while (MB > 1 && ((nblk + MB - 1) / MB) * (P.Cout / NOUT) < ctx->num_sms) MB >>= 1;
+  size_t smem = 0;
+  for (;; MB >>= 1) {
+    P.MB = MB;
+    P.SL = 128 * MB + 2 * P.halo;
+    smem = 128 + 128 + 2 * (size_t)(4 * P.SL * 16) + 2 * (size_t)WSTAGE;
+    if (smem <= 227 * 1024 || MB == 1) break;
+  }
+  if (smem > 227 * 1024) {
+    set_error("msgm_conv2d_tc: tile does not fit shared memory (image too wide)");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  int cols = 32;
+  while (cols < MB * NOUT) cols <<= 1;
+  P.tmem_cols = cols;
+  auto kern = conv2d_tc_kernel<NOUT, KS>;
+  MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((nblk + MB - 1) / MB), (unsigned)(P.Cout / NOUT));
+  kern<<<grid, CTC_STAGERS + 32, smem, stream>>>(P);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* D, cudaStream_t stream) {
+  if (D->B == 0) return MSGM_OK;
+  ConvTcParams P{};
+  P.x1 = D->x1; P.C1 = D->C1; P.x2 = D->x2; P.C2 = D->x2 ? D->C2 : 0;
+  P.wimg = reinterpret_cast<const unsigned char*>(D->wimg);
+  P.bias = D->bias; P.ebias = D->ebias; P.res = D->res; P.ss = D->ss; P.out = D->out;
+  P.silu = D->prologue == 2;
+  P.B = D->B; P.Cout = D->Cout; P.stride = D->stride; P.up = D->up; P.Hs = D->Hs; P.Ws = D->Ws;
+  const int pad = D->K / 2;
+  P.Hi = D->Hs * D->up; P.Wi = D->Ws * D->up;
+  P.Hp = P.Hi + 2 * pad; P.Wp = P.Wi + 2 * pad;
+  P.Ho = (P.Hi + 2 * pad - D->K) / D->stride + 1;
+  P.Wo = (P.Wi + 2 * pad - D->K) / D->stride + 1;
+  P.halo = pad * (P.Wp + 1);
+  P.NC = (P.C1 + P.C2) / 16;
+  P.total = (long long)D->B * P.Hp * P.Wp;
+  P.flags = reinterpret_cast<int*>(ctx->ws);
+  const int nout = conv2d_tc_nout(D->Cout);
+  if (D->K == 3) {
+    if (nout == 128) return launch_conv_tc<128, 3>(ctx, P, stream);
+    if (nout == 64) return launch_conv_tc<64, 3>(ctx, P, stream);
+    return launch_conv_tc<32, 3>(ctx, P, stream);
+  }
+  if (nout == 128) return launch_conv_tc<128, 1>(ctx, P, stream);
+  if (nout == 64) return launch_conv_tc<64, 1>(ctx, P, stream);
+  return launch_conv_tc<32, 1>(ctx, P, stream);
+}
+
+}  // namespace msgm

@@ -223,6 +223,8 @@ class UNetModel(nn.Module):
         Cout, K = W.shape[0], W.shape[-1]
         bias = None if conv.bias is None else _lib.f32c(conv.bias, dev)
         stride = conv.stride[0]
+        if self.conv_mode == "tc" and _tc_shape_ok(Cout, C1, C2, K, stride, Hs * up, Ws * up):
+            return self._k_conv_tc(dev, conv, W, bias, x1, x2, gn, silu, ebias, res, up, stride)
         stats = gamma = beta = None
         G = 0
         if gn is not None:
@@ -238,6 +240,37 @@ class UNetModel(nn.Module):
         d = _lib.Conv2dDesc(p(x1), p(x2), p(W), p(bias), p(ebias), p(res), p(stats), p(gamma), p(beta), p(out), B, C1, C2,
                             Cout, K, stride, up, Hs, Ws, G, 0 if gn is None else (2 if silu else 1))
         _lib.check(L.msgm_conv2d(h, C.byref(d), _lib.stream_ptr(dev)))
+        return out
+
+    conv_mode = "tc"  # "tc": tcgen05 split-fp16 implicit GEMM where the shape allows; "fp32": CUDA-core kernels only
+
+    def _k_conv_tc(self, dev, conv, W, bias, x1, x2, gn, silu, ebias, res, up, stride):
+        """Tensor-core conv (csrc/conv2d_tc.cu): packed weights cached per weight version, GroupNorm folded to scale/shift."""
+        h, L = _lib.ctx(dev), _lib.lib()
+        B, C1, Hs, Ws = x1.shape
+        C2 = 0 if x2 is None else x2.shape[1]
+        Cout, K = W.shape[0], W.shape[-1]
+        cache = self.__dict__.setdefault("_tc_wimg", {})
+        key = (W.data_ptr(), conv.weight._version, tuple(W.shape), dev.index)
+        ent = cache.get(W.data_ptr())
+        if ent is None or ent[0] != key:
+            nbytes = L.msgm_conv2d_tc_pack_bytes(Cout, C1 + C2, K)
+            img = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            _lib.check(L.msgm_conv2d_tc_pack(h, _lib.ptr(W), Cout, C1 + C2, K, _lib.ptr(img), _lib.stream_ptr(dev)))
+            ent = cache[W.data_ptr()] = (key, img)
+        ss = None
+        if gn is not None:
+            ss = torch.empty((B, C1 + C2, 2), device=dev, dtype=torch.float32)
+            _lib.check(L.msgm_gn_scale_shift(h, _lib.ptr(x1), C1, _lib.ptr(x2), C2, Hs * Ws, gn.num_groups, B,
+                                             _lib.ptr(_lib.f32c(gn.weight, dev)), _lib.ptr(_lib.f32c(gn.bias, dev)),
+                                             _lib.ptr(ss), _lib.stream_ptr(dev)))
+        pad = K // 2
+        Ho, Wo = (Hs * up + 2 * pad - K) // stride + 1, (Ws * up + 2 * pad - K) // stride + 1
+        out = torch.empty((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
+        p = lambda t_: None if t_ is None else t_.data_ptr()  # noqa: E731
+        d = _lib.Conv2dTcDesc(p(x1), p(x2), p(ent[1]), p(bias), p(ebias), p(res), p(ss), p(out), B, C1, C2, Cout, K, stride,
+                              up, Hs, Ws, 0 if gn is None else (2 if silu else 1))
+        _lib.check(L.msgm_conv2d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
         return out
 
     def _k_resblock(self, dev, blk, x1, x2, emb):
@@ -295,6 +328,12 @@ class UNetModel(nn.Module):
         for blk in self.output_blocks:
             cur = self._k_sequential(dev, blk, cur, skips.pop(), emb)
         return self._k_conv(dev, self.out[2], cur, gn=self.out[0])
+
+
+def _tc_shape_ok(Cout, C1, C2, K, stride, Hi, Wi):
+    if K not in (1, 3) or Cout % 32 or (C1 + C2) % 16 or C1 % 16:
+        return False
+    return stride == 1 or (stride == 2 and K == 3 and Hi % 2 == 0 and Wi % 2 == 0)
 
 
 class _Conv1x1View:

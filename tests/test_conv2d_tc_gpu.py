@@ -1,0 +1,116 @@
+"""GPU parity of the tcgen05 convolution (csrc/conv2d_tc.cu) that carries the 2-D U-Net's 3x3 / 1x1 convs
+(model/unet.py:40-250 in the reference): every fused feature (GroupNorm + SiLU prologue, channel concat, nearest x2
+upsampling, stride 2, bias + embedding term + residual) against the same layer evaluated by torch in float64.
+The operands are split fp16 hi + lo (three tensor-core products), so the stated tolerance is fp32-level: 2e-5 relative
+to max|ref| (observed ~1e-6)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from sdeflow_light_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run_tc(x1, x2, W, bias, ebias, res, gn, silu, up, stride):
+    dev = torch.device(DEV)
+    h, L = _lib.ctx(dev), _lib.lib()
+    B, C1, Hs, Ws = x1.shape
+    C2 = 0 if x2 is None else x2.shape[1]
+    Cout, K = W.shape[0], W.shape[-1]
+    nbytes = L.msgm_conv2d_tc_pack_bytes(Cout, C1 + C2, K)
+    assert nbytes == Cout * (C1 + C2) * K * K * 4
+    img = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    _lib.check(L.msgm_conv2d_tc_pack(h, _lib.ptr(W), Cout, C1 + C2, K, _lib.ptr(img), _lib.stream_ptr(dev)))
+    ss = None
+    if gn is not None:
+        G, gamma, beta = gn
+        ss = torch.empty((B, C1 + C2, 2), device=dev, dtype=torch.float32)
+        _lib.check(L.msgm_gn_scale_shift(h, _lib.ptr(x1), C1, _lib.ptr(x2), C2, Hs * Ws, G, B, _lib.ptr(gamma),
+                                         _lib.ptr(beta), _lib.ptr(ss), _lib.stream_ptr(dev)))
+    pad = K // 2
+    Ho, Wo = (Hs * up + 2 * pad - K) // stride + 1, (Ws * up + 2 * pad - K) // stride + 1
+    out = torch.full((B, Cout, Ho, Wo), float("nan"), device=dev, dtype=torch.float32)
+    p = lambda t_: None if t_ is None else t_.data_ptr()  # noqa: E731
+    d = _lib.Conv2dTcDesc(p(x1), p(x2), p(img), p(bias), p(ebias), p(res), p(ss), p(out), B, C1, C2, Cout, K, stride, up,
+                          Hs, Ws, 0 if gn is None else (2 if silu else 1))
+    _lib.check(L.msgm_conv2d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    flag = C.c_int32(0)
+    _lib.check(L.msgm_debug_flags(h, C.byref(flag)))
+    assert flag.value == 0, "a tcgen05 wait timed out"
+    return out
+
+
+def _ref(x1, x2, W, bias, ebias, res, gn, silu, up, stride):
+    x = x1 if x2 is None else torch.cat([x1, x2], 1)
+    x = x.double()
+    if gn is not None:
+        G, gamma, beta = gn
+        x = F.group_norm(x, G, gamma.double(), beta.double(), eps=1e-5)
+        if silu:
+            x = x * torch.sigmoid(x)
+    if up == 2:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    y = F.conv2d(x, W.double(), None if bias is None else bias.double(), stride=stride, padding=W.shape[-1] // 2)
+    if ebias is not None:
+        y = y + ebias.double()[:, :, None, None]
+    if res is not None:
+        y = y + res.double()
+    return y
+
+
+CASES = [
+    # B, C1, C2, Cout, K, H, W, up, stride, gn(0 none,1 norm,2 norm+silu), bias, ebias, res
+    (3, 32, 0, 32, 3, 32, 32, 1, 1, 2, 1, 1, 0),     # ResBlock in_layers at 32x32
+    (2, 64, 32, 64, 3, 16, 16, 1, 1, 2, 1, 1, 0),    # decoder ResBlock over the concat [h, skip]
+    (2, 128, 128, 128, 3, 8, 8, 1, 1, 2, 1, 0, 1),   # widest contraction (256 -> 128), residual epilogue
+    (5, 64, 0, 192, 1, 16, 16, 1, 1, 1, 1, 0, 0),    # attention qkv: GroupNorm without SiLU, 1x1, 3 N tiles
+    (4, 128, 0, 128, 1, 8, 8, 1, 1, 0, 1, 0, 1),     # attention proj_out + residual
+    (3, 64, 32, 64, 1, 16, 16, 1, 1, 0, 1, 0, 0),    # ResBlock 1x1 skip over a concat
+    (2, 64, 0, 64, 3, 8, 8, 2, 1, 0, 1, 0, 0),       # Upsample: nearest x2 folded into the staging
+    (3, 32, 0, 32, 3, 32, 32, 1, 2, 0, 1, 0, 0),     # Downsample: stride 2
+    (1, 16, 0, 32, 3, 5, 7, 1, 1, 2, 0, 0, 0),       # ragged: odd sizes, one 16-channel chunk, no bias
+    (130, 32, 0, 64, 3, 8, 8, 1, 1, 2, 1, 1, 1),     # many images per tile, every epilogue term
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv2d_tc_matches_float64(case):
+    B, C1, C2, Cout, K, H, W_, up, stride, gnm, hb, he, hr = case
+    torch.manual_seed(B * 1000 + Cout + K)
+    dev = DEV
+    x1 = torch.randn(B, C1, H, W_, device=dev) * 1.7 + 0.3
+    x2 = torch.randn(B, C2, H, W_, device=dev) * 0.6 if C2 else None
+    Wt = torch.randn(Cout, C1 + C2, K, K, device=dev) / ((C1 + C2) * K * K) ** 0.5
+    bias = torch.randn(Cout, device=dev) if hb else None
+    ebias = torch.randn(B, Cout, device=dev) if he else None
+    gn = None
+    if gnm:
+        G = min(32, C1 + C2)
+        gn = (G, torch.rand(C1 + C2, device=dev) + 0.5, torch.randn(C1 + C2, device=dev) * 0.2)
+    pad = K // 2
+    Ho, Wo = (H * up + 2 * pad - K) // stride + 1, (W_ * up + 2 * pad - K) // stride + 1
+    res = torch.randn(B, Cout, Ho, Wo, device=dev) if hr else None
+    got = _run_tc(x1, x2, Wt, bias, ebias, res, gn, gnm == 2, up, stride)
+    ref = _ref(x1, x2, Wt, bias, ebias, res, gn, gnm == 2, up, stride)
+    assert got.shape == ref.shape
+    assert torch.isfinite(got).all(), "positions left unwritten"
+    err = float((got.double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-5, f"conv2d_tc rel err {err:.3e}"
+
+
+def test_conv2d_tc_rejects_unsupported_shapes():
+    dev = torch.device(DEV)
+    L = _lib.lib()
+    assert L.msgm_conv2d_tc_pack_bytes(33, 32, 3) == -1     # Cout % 32
+    assert L.msgm_conv2d_tc_pack_bytes(32, 24, 3) == -1     # Cin % 16
+    assert L.msgm_conv2d_tc_pack_bytes(32, 32, 5) == -1     # kernel size
+    x = torch.zeros(1, 32, 4, 4, device=dev)
+    d = _lib.Conv2dTcDesc(x.data_ptr(), None, x.data_ptr(), None, None, None, None, x.data_ptr(), 1, 32, 0, 32, 3, 3, 1, 4,
+                          4, 0)
+    with pytest.raises(ValueError):
+        _lib.check(L.msgm_conv2d_tc(_lib.ctx(dev), C.byref(d), _lib.stream_ptr(dev)))

@@ -242,6 +242,10 @@ int msgm_sincos_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const 
                           float* out, int32_t B, int32_t dim, int32_t E, int32_t accumulate, void* stream);
 /* QKVAttention, single head: qkv (B,3C,T) -> out (B,C,T) = v softmax(q^T k / sqrt(C))^T (model/unet.py:236-250). */
 int msgm_attention(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32_t C, int32_t T, void* stream);
+/* Tensor-core form of msgm_attention (tcgen05, fp16 x 3 split operands: fp32-level parity) for C in {32,64,96,128},
+ * T in {64,128,192,256} within the shared-memory budget; msgm_attention_tc_supported says whether a shape is covered. */
+int msgm_attention_tc_supported(int32_t C, int32_t T);
+int msgm_attention_tc(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32_t C, int32_t T, void* stream);
 /* VorticityUNet wrapper: flat (B,H*W) -> image (B,1,H,W) / 5 [after x/(|x|+eps)*sqrt(d) when pre] and back (x5). */
 int msgm_vort_pre(msgm_ctx* ctx, const float* x, float* img, float* lognorm, int32_t B, int32_t H, int32_t W, int32_t forder,
                   int32_t pre, void* stream);

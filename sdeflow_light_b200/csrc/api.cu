@@ -56,6 +56,8 @@ int emb_proj(msgm_ctx*, const float*, const float*, const float*, float*, int, i
 int sincos_embed_mlp(msgm_ctx*, const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
                      int, cudaStream_t);
 int attention(msgm_ctx*, const float*, float*, int, int, int, cudaStream_t);
+bool attention_tc_ok(int, int);
+int attention_tc(msgm_ctx*, const float*, float*, int, int, int, cudaStream_t);
 int vort_pre(msgm_ctx*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
 int vort_post(msgm_ctx*, const float*, float*, int, int, int, int, cudaStream_t);
 
@@ -389,7 +391,7 @@ int msgm_gn_stats(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, i
 
 int msgm_emb_proj(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int32_t E, int32_t Cout,
                   int32_t B, void* stream) {
-  if (!ctx || !emb || !W || !bias || !out || E < 1 || Cout < 1 || B < 0) return invalid("msgm_emb_proj: bad argument");
+  if (!ctx || !emb || !W || !bias || !out || E < 1 || E > 8192 || Cout < 1 || B < 0) return invalid("msgm_emb_proj: bad argument");
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return emb_proj(ctx, emb, W, bias, out, E, Cout, B, (cudaStream_t)stream);
@@ -402,6 +404,19 @@ int msgm_sincos_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const 
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return sincos_embed_mlp(ctx, t, W1, b1, W2, b2, out, B, dim, E, accumulate, (cudaStream_t)stream);
+}
+
+int msgm_attention_tc_supported(int32_t C, int32_t T) { return attention_tc_ok(C, T) ? 1 : 0; }
+
+int msgm_attention_tc(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32_t C, int32_t T, void* stream) {
+  if (!ctx || !qkv || !out || B < 0) return invalid("msgm_attention_tc: bad argument");
+  if (!attention_tc_ok(C, T)) {
+    set_error("msgm_attention_tc: shape not covered (C % 32 == 0, C <= 128, T % 64 == 0, T <= 256); use msgm_attention");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return attention_tc(ctx, qkv, out, B, C, T, (cudaStream_t)stream);
 }
 
 int msgm_attention(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32_t C, int32_t T, void* stream) {

@@ -247,36 +247,42 @@ __global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int
 
 // ---- GroupNorm as a per-(sample, channel) affine map: ss[b, c] = (rstd gamma_c, beta_c - mean rstd gamma_c) -------------
 // (GroupNorm32, model/nn_utils.py:39-41,107-114; statistics over channels [g cpg, (g+1) cpg) x HW of the concat [x1, x2])
+// One warp per (sample, group): 16-byte loads when HW % 4 == 0, shuffle reduction, no block barrier.
 __global__ void __launch_bounds__(256) gn_scale_shift_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
-                                                             int C2, int HW, int G, float eps, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float* __restrict__ ss) {
-  __shared__ float rs[8], rq[8], mr[2];
-  const int b = blockIdx.x / G, g = blockIdx.x % G, C = C1 + C2, cpg = C / G, tid = threadIdx.x;
-  const int n = cpg * HW;
+                                                             int C2, int HW, int G, int BG, float eps,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ ss) {
+  const int wg = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wg >= BG) return;
+  const int b = wg / G, g = wg % G, C = C1 + C2, cpg = C / G;
   float s = 0.0f, q = 0.0f;
-  for (int e = tid; e < n; e += 256) {
-    const int c = g * cpg + e / HW, p = e % HW;
-    const float v = c < C1 ? x1[((size_t)b * C1 + c) * HW + p] : x2[((size_t)b * C2 + (c - C1)) * HW + p];
-    s += v;
-    q = fmaf(v, v, q);
+  for (int ci = 0; ci < cpg; ++ci) {
+    const int c = g * cpg + ci;
+    const float* src = c < C1 ? x1 + ((size_t)b * C1 + c) * HW : x2 + ((size_t)b * C2 + (c - C1)) * HW;
+    if ((HW & 3) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int e = lane; e < HW / 4; e += 32) {
+        const float4 v = __ldg(s4 + e);
+        s += (v.x + v.y) + (v.z + v.w);
+        q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
+      }
+    } else {
+      for (int e = lane; e < HW; e += 32) {
+        const float v = __ldg(src + e);
+        s += v;
+        q = fmaf(v, v, q);
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-  if ((tid & 31) == 0) { rs[tid >> 5] = s; rq[tid >> 5] = q; }
-  __syncthreads();
-  if (tid == 0) {
-    float ts = 0.0f, tq = 0.0f;
-    for (int w = 0; w < 8; ++w) { ts += rs[w]; tq += rq[w]; }
-    const float mean = ts / n, var = fmaxf(tq / n - mean * mean, 0.0f);
-    mr[0] = mean;
-    mr[1] = rsqrtf(var + eps);
-  }
-  __syncthreads();
-  if (tid < cpg) {
-    const int c = g * cpg + tid;
-    const float sc = mr[1] * gamma[c];
+  const float n = (float)cpg * (float)HW;
+  const float mean = s / n, var = fmaxf(q / n - mean * mean, 0.0f), rstd = rsqrtf(var + eps);
+  for (int ci = lane; ci < cpg; ci += 32) {
+    const int c = g * cpg + ci;
+    const float sc = rstd * gamma[c];
     ss[((size_t)b * C + c) * 2] = sc;
-    ss[((size_t)b * C + c) * 2 + 1] = fmaf(-mr[0], sc, beta[c]);
+    ss[((size_t)b * C + c) * 2 + 1] = fmaf(-mean, sc, beta[c]);
   }
 }
 
@@ -297,7 +303,7 @@ int conv2d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cin, int K, void
 int gn_scale_shift(msgm_ctx* ctx, const float* x1, int C1, const float* x2, int C2, int HW, int G, int B, const float* gamma,
                    const float* beta, float* ss, cudaStream_t stream) {
   if (B == 0) return MSGM_OK;
-  gn_scale_shift_kernel<<<B * G, 256, 0, stream>>>(x1, C1, x2, x2 ? C2 : 0, HW, G, 1e-5f, gamma, beta, ss);
+  gn_scale_shift_kernel<<<(B * G + 7) / 8, 256, 0, stream>>>(x1, C1, x2, x2 ? C2 : 0, HW, G, B * G, 1e-5f, gamma, beta, ss);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

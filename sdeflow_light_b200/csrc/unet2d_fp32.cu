@@ -159,16 +159,101 @@ __global__ void __launch_bounds__(256) conv2d_kernel(const __grid_constant__ Con
   }
 }
 
+// ---- degenerate shapes of the same conv: one input channel (the U-Net's first conv) / one output channel (its last) ------
+// Cin = 1, 3x3, stride 1: thread = one output position, all Cout channels (weights + bias in shared memory); stores are
+// coalesced per channel.  HBM-bound on the (B, Cout, H, W) output.
+__global__ void __launch_bounds__(256) conv2d_cin1_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int Cout,
+                                                          int H, int Wd, long long npos) {
+  extern __shared__ float swb[];  // [Cout][9] + [Cout]
+  for (int e = threadIdx.x; e < Cout * 9; e += 256) swb[e] = W[e];
+  for (int e = threadIdx.x; e < Cout; e += 256) swb[Cout * 9 + e] = bias ? bias[e] : 0.0f;
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= npos) return;
+  const int HW = H * Wd, b = (int)(p / HW), rem = (int)(p % HW), y = rem / Wd, xx = rem % Wd;
+  float in[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int iy = y + ky - 1, ix = xx + kx - 1;
+      in[ky * 3 + kx] = (iy >= 0 && iy < H && ix >= 0 && ix < Wd) ? __ldg(x + (size_t)b * HW + iy * Wd + ix) : 0.0f;
+    }
+  float* o = out + (size_t)b * Cout * HW + rem;
+  for (int co = 0; co < Cout; ++co) {
+    float a = swb[Cout * 9 + co];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a = fmaf(swb[co * 9 + k], in[k], a);
+    o[(size_t)co * HW] = a;
+  }
+}
+
+// Cout = 1, 3x3, stride 1, GroupNorm(+SiLU) prologue: CTA = one sample x a band of rows; per input channel the
+// normalised (+SiLU) band with its zero ring is staged once in shared memory and every thread accumulates its 9 taps.
+// HBM-bound on the (B, Cin, H, W) input.
+__global__ void __launch_bounds__(256) conv2d_cout1_kernel(const __grid_constant__ Conv2dParams P, int TR) {
+  extern __shared__ float sband[];  // [2][(TR + 2) * (Wi + 2)]
+  const int Hi = P.Hs, Wi = P.Ws, wc = Wi + 2, bandsz = (TR + 2) * wc;
+  const int b = blockIdx.y, y0 = blockIdx.x * TR, tid = threadIdx.x;
+  const int ry = tid / Wi, xx = tid % Wi;
+  const bool active = ry < TR && y0 + ry < Hi;
+  const int Cin = P.C1, cpg = P.G > 0 ? Cin / P.G : 1, HW = Hi * Wi;
+  float acc = P.bias ? P.bias[0] : 0.0f;
+  for (int c = 0; c < Cin; ++c) {
+    float* sb = sband + (c & 1) * bandsz;
+    float mean = 0.f, rstd = 1.f, ga = 1.f, be = 0.f;
+    if (P.prologue) {
+      mean = P.stats[((size_t)b * P.G + c / cpg) * 2];
+      rstd = P.stats[((size_t)b * P.G + c / cpg) * 2 + 1];
+      ga = P.gamma[c];
+      be = P.beta[c];
+    }
+    const float* src = P.x1 + ((size_t)b * Cin + c) * HW;
+    for (int e = tid; e < bandsz; e += 256) {
+      const int iy = y0 + e / wc - 1, ix = e % wc - 1;
+      float v = 0.0f;
+      if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) {
+        v = __ldg(src + iy * Wi + ix);
+        if (P.prologue) {
+          v = fmaf((v - mean) * rstd, ga, be);
+          if (P.prologue == 2) v = siluf(v);
+        }
+      }
+      sb[e] = v;
+    }
+    __syncthreads();  // double-buffered band: one barrier per channel
+    if (active) {
+      const float* w = P.W + c * 9;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc = fmaf(__ldg(w + ky * 3 + kx), sb[(ry + ky) * wc + xx + kx], acc);
+    }
+  }
+  if (active) {
+    const size_t o = (size_t)b * HW + (y0 + ry) * Wi + xx;
+    if (P.ebias) acc += P.ebias[b];
+    if (P.res) acc += P.res[o];
+    P.out[o] = acc;
+  }
+}
+
 // out[b,co] = bias[co] + sum_i W[co,i] silu(emb[b,i])   (ResBlock.emb_layers, model/unet.py:146-152)
-__global__ void __launch_bounds__(128) emb_proj_kernel(const float* __restrict__ emb, const float* __restrict__ W,
+__global__ void __launch_bounds__(256) emb_proj_kernel(const float* __restrict__ emb, const float* __restrict__ W,
                                                        const float* __restrict__ bias, float* __restrict__ out, int E,
                                                        int Cout, int B) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * Cout) return;
-  const int co = idx % Cout, b = idx / Cout;
-  float s = bias[co];
-  for (int i = 0; i < E; ++i) s = fmaf(W[(size_t)co * E + i], siluf(emb[(size_t)b * E + i]), s);
-  out[idx] = s;
+  extern __shared__ float se_[];  // silu(emb[b, :])
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < E; i += 256) se_[i] = siluf(emb[(size_t)b * E + i]);
+  __syncthreads();
+  for (int co = warp; co < Cout; co += 8) {  // one warp per output row: coalesced reads of W[co, :]
+    float s = 0.0f;
+    for (int i = lane; i < E; i += 32) s = fmaf(__ldg(W + (size_t)co * E + i), se_[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[(size_t)b * Cout + co] = s + bias[co];
+  }
 }
 
 // out (B,E) (+)= W2 silu(W1 sincos(t) + b1) + b2 ; sincos(t) = [cos(t w_k), sin(t w_k)], w_k = 1e4^(-k/half), dim = 2 half
@@ -349,6 +434,23 @@ int conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* D, cudaStream_t stream) {
     set_error("msgm_conv2d: output width must be a multiple of 4");
     return MSGM_ERR_UNSUPPORTED;
   }
+  if (D->K == 3 && D->stride == 1 && D->up == 1 && P.C2 == 0 && P.C1 == 1 && !D->prologue && !D->ebias && !D->res &&
+      D->Cout <= 512) {
+    const long long npos = (long long)D->B * P.Ho * P.Wo;
+    conv2d_cin1_kernel<<<(unsigned)((npos + 255) / 256), 256, sizeof(float) * 10 * D->Cout, stream>>>(
+        P.x1, P.W, P.bias, P.out, D->Cout, P.Hs, P.Ws, npos);
+    ctx->launches += 1;
+    MSGM_CUDA_TRY(cudaGetLastError());
+    return MSGM_OK;
+  }
+  if (D->K == 3 && D->stride == 1 && D->up == 1 && P.C2 == 0 && D->Cout == 1 && P.Ws <= 256) {
+    const int TR = std::max(1, std::min(256 / P.Ws, 8));
+    const size_t smem = sizeof(float) * 2 * (TR + 2) * (P.Ws + 2);
+    conv2d_cout1_kernel<<<dim3((P.Hs + TR - 1) / TR, D->B), 256, smem, stream>>>(P, TR);
+    ctx->launches += 1;
+    MSGM_CUDA_TRY(cudaGetLastError());
+    return MSGM_OK;
+  }
   const bool wide = D->Cout >= 64;  // 64 output channels per CTA (8 per thread) when there are that many
   dim3 grid((P.Ho * P.Wo + C2_P - 1) / C2_P, (D->Cout + (wide ? 64 : 32) - 1) / (wide ? 64 : 32), D->B);
   if (D->K == 3 && D->stride == 1) {
@@ -372,7 +474,7 @@ int conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* D, cudaStream_t stream) {
 
 int emb_proj(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int E, int Cout, int B,
              cudaStream_t stream) {
-  emb_proj_kernel<<<(B * Cout + 127) / 128, 128, 0, stream>>>(emb, W, bias, out, E, Cout, B);
+  emb_proj_kernel<<<B, 256, sizeof(float) * E, stream>>>(emb, W, bias, out, E, Cout, B);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

@@ -292,7 +292,8 @@ class UNetModel(nn.Module):
         B, Cc, Hh, Ww = x.shape
         qkv = self._k_conv(dev, _as2d(blk.qkv), x, gn=blk.norm, silu=False)
         att = torch.empty((B, Cc, Hh, Ww), device=dev, dtype=torch.float32)
-        _lib.check(L.msgm_attention(h, _lib.ptr(qkv), _lib.ptr(att), B, Cc, Hh * Ww, _lib.stream_ptr(dev)))
+        fn = L.msgm_attention_tc if self.conv_mode == "tc" and L.msgm_attention_tc_supported(Cc, Hh * Ww) else L.msgm_attention
+        _lib.check(fn(h, _lib.ptr(qkv), _lib.ptr(att), B, Cc, Hh * Ww, _lib.stream_ptr(dev)))
         return self._k_conv(dev, _as2d(blk.proj_out), att, res=x)
 
     def _k_sequential(self, dev, seq, x1, x2, emb):

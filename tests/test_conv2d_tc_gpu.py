@@ -114,3 +114,25 @@ def test_conv2d_tc_rejects_unsupported_shapes():
                           4, 0)
     with pytest.raises(ValueError):
         _lib.check(L.msgm_conv2d_tc(_lib.ctx(dev), C.byref(d), _lib.stream_ptr(dev)))
+
+
+@pytest.mark.parametrize("B,Cc,T", [(5, 64, 256), (3, 128, 64), (2, 32, 128), (2, 96, 192)])
+def test_attention_tc_matches_float64(B, Cc, T):
+    """QKVAttention (model/unet.py:236-250) on the tensor pipe vs float64: softmax((q s)^T (k s)) v, s = C^-1/4."""
+    dev = torch.device(DEV)
+    h, L = _lib.ctx(dev), _lib.lib()
+    assert L.msgm_attention_tc_supported(Cc, T) == 1
+    torch.manual_seed(T + Cc)
+    qkv = torch.randn(B, 3 * Cc, T, device=dev) * 1.5
+    out = torch.full((B, Cc, T), float("nan"), device=dev)
+    _lib.check(L.msgm_attention_tc(h, _lib.ptr(qkv), _lib.ptr(out), B, Cc, T, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    flag = C.c_int32(0)
+    _lib.check(L.msgm_debug_flags(h, C.byref(flag)))
+    assert flag.value == 0
+    q, k, v = qkv.double().split(Cc, dim=1)
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q, k) / Cc ** 0.5, dim=-1)
+    ref = torch.einsum("bts,bcs->bct", w, v)
+    err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
+    assert torch.isfinite(out).all() and err < 2e-5, f"attention_tc rel err {err:.3e}"
+    assert L.msgm_attention_tc_supported(128, 512) == 0 and L.msgm_attention_tc_supported(40, 64) == 0

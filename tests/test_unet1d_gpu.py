@@ -189,3 +189,25 @@ def test_unet2d_kernel_path_matches_module_path(S, B, pre, order):
     err = _rel(got, ref.cpu())
     Bd.report(test=f"unet2d-kernels-{S}x{S}", rel=err)
     assert got.shape == (B, S * S) and err < 5e-5
+
+
+def test_unet2d_cuda_graph_replay_tracks_weight_updates():
+    """The graphed forward (one CUDA graph per batch size) must equal the eager launch sequence bit for bit, and an
+    in-place weight update (an optimiser step between two sampling runs) must invalidate the captured graph and the
+    cached tensor-core weight images."""
+    net = _build_unet2d(16, "NormalizeLogRadius", "F", 5).to(DEV)
+    torch.manual_seed(1)
+    x, t = torch.randn(6, 256, device=DEV), torch.rand(6, device=DEV)
+    with torch.no_grad():
+        net.cuda_graph = True
+        g1 = net(x, t)
+        g1b = net(x * 0.5, t)             # replay with new inputs
+        net.cuda_graph = False
+        e1, e1b = net(x, t), net(x * 0.5, t)
+        assert torch.equal(g1, e1) and torch.equal(g1b, e1b)
+        net.core.input_blocks[1][0].in_layers[2].weight.mul_(1.5)   # a tensor-core conv weight
+        net.core.out[2].bias.add_(0.25)
+        e2 = net(x, t)
+        net.cuda_graph = True
+        g2 = net(x, t)
+        assert torch.equal(g2, e2) and not torch.equal(g2, g1)

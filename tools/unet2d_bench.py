@@ -36,9 +36,14 @@ def timeit(fn, reps=5):
 
 with torch.no_grad():
     net.core.conv_mode = "fp32"
+    net.cuda_graph = False
     ms_f, n_f = timeit(lambda: net(x, t))
     y_f = net(x, t)
     net.core.conv_mode = "tc"
+    net.cuda_graph = False
+    ms_e, n_e = timeit(lambda: net(x, t))
+    print(f"tc kernels, eager launches: {ms_e:.2f} ms ({n_e:.0f} launches)")
+    net.cuda_graph = True
     ms_k, n_k = timeit(lambda: net(x, t))
     y_k = net(x, t)
     print(f"tc vs fp32 kernels: rel diff {float((y_k - y_f).abs().max() / y_f.abs().max()):.2e}; fp32 CUDA-core kernels "

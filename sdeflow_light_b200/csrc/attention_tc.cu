@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
   unsigned char* sP = sQ;                                // P chunks reuse the Q | K space once S is complete
   const int npbuf = min(3, (2 * QB + 2 * KB) / ATC_PBUF);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // broadcast form: the role branches are provably warp-uniform
   const int b = blockIdx.y, t0 = blockIdx.x * 128;
   const float* q = P.qkv + (size_t)b * 3 * C * T;
   const float* k = q + (size_t)C * T;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = *tmem_slot;
+  const uint32_t tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // ---- S = Q^T K --------------------------------------------------------------------------------------------------------
   if (warp == 0) {

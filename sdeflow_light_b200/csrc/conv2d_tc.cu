@@ -50,7 +50,10 @@ __device__ __forceinline__ float silu_acc(float v) { return __fdividef(v, 1.0f +
 
 constexpr int CTC_STAGERS = 256;
 
-template <int NOUT, int KS>
+// CONST_BASE: the dynamic shared memory block starts at shared-window address 1024 (probed by the host, verified
+// here), so every MMA descriptor is computed from kernel parameters and constants only and ptxas keeps it in uniform
+// registers -- no per-MMA R2UR / vote sequences on the issue path.
+template <int NOUT, int KS, bool CONST_BASE>
 __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __grid_constant__ ConvTcParams P) {
   constexpr int NT = KS * KS, PAD = KS / 2;
   constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;  // bytes of packed weights per 16-channel chunk
@@ -66,7 +69,8 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
   unsigned char* sA = smem + 128;
   unsigned char* sW = sA + 2 * ASTAGE;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // broadcast form: lets ptxas treat the role branch as warp-uniform
   const long long p0 = (long long)blockIdx.x * (128 * P.MB);
   const int co0 = blockIdx.y * NOUT;
   const int HpWp = P.Hp * P.Wp;
@@ -88,35 +92,41 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = *tmem_slot;
+  const uint32_t tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == CTC_STAGERS / 32) {
     // ================================================ MMA issuer ==================================================
+    // Everything on the issue path is warp-uniform by construction (kernel parameters, constants, vote results).
     const uint32_t idesc = umma_idesc_f16(128, NOUT);
-    bool ok = true;
-    for (int k = 0; k < P.NC && ok; ++k) {
-      const int buf = k & 1;
-      ok = mbar_wait(bar_full + buf, (uint32_t)((k >> 1) & 1), P.flags);
-      tc_fence_after();
-      const uint32_t a_base = smem_u32(sA + buf * ASTAGE);
-      const uint32_t w_base = smem_u32(sW + buf * WSTAGE);
-      for (int mb = 0; mb < P.MB; ++mb) {
-        const uint32_t dcol = tbase + (uint32_t)(mb * NOUT);
+    const uint32_t sbase = CONST_BASE ? 1024u : smem_u32(smem);
+    if (sbase != smem_u32(smem)) {
+      if (lane == 0) atomicExch(P.flags, 2);
+    } else {
+      const uint32_t a_base0 = sbase + 128u, w_base0 = a_base0 + 2u * (uint32_t)ASTAGE;
+      for (int k = 0; k < P.NC; ++k) {
+        const int buf = k & 1;
+        if (!__all_sync(0xffffffffu, mbar_wait(bar_full + buf, (uint32_t)((k >> 1) & 1), P.flags))) break;
+        tc_fence_after();
+        const uint32_t a_base = a_base0 + (uint32_t)(buf * ASTAGE);
+        const uint32_t w_base = w_base0 + (uint32_t)(buf * WSTAGE);
+        for (int mb = 0; mb < P.MB; ++mb) {
+          const uint32_t dcol = tbase + (uint32_t)(mb * NOUT);
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const int toff = KS == 3 ? (t / 3 - 1) * P.Wp + (t % 3 - 1) : 0;
-          const uint32_t a_hi = a_base + (uint32_t)((mb * 128 + P.halo + toff) * 16);
-          const uint32_t a_lo = a_hi + 2u * (uint32_t)PS;
-          const uint32_t w_hi = w_base + (uint32_t)(t * 4 * NOUT * 16);
-          const uint32_t w_lo = w_hi + 2u * NOUT * 16;
-          const uint64_t dAh = umma_desc(a_hi, PS, 128), dAl = umma_desc(a_lo, PS, 128);
-          const uint64_t dWh = umma_desc(w_hi, NOUT * 16, 128), dWl = umma_desc(w_lo, NOUT * 16, 128);
-          umma_ss(dcol, dAh, dWh, idesc, (k > 0 || t > 0) ? 1u : 0u, 0);
-          umma_ss(dcol, dAl, dWh, idesc, 1u, 0);
-          umma_ss(dcol, dAh, dWl, idesc, 1u, 0);
+          for (int t = 0; t < NT; ++t) {
+            const int toff = KS == 3 ? (t / 3 - 1) * P.Wp + (t % 3 - 1) : 0;
+            const uint32_t a_hi = a_base + (uint32_t)((mb * 128 + P.halo + toff) * 16);
+            const uint32_t a_lo = a_hi + 2u * (uint32_t)PS;
+            const uint32_t w_hi = w_base + (uint32_t)(t * 4 * NOUT * 16);
+            const uint32_t w_lo = w_hi + 2u * NOUT * 16;
+            const uint64_t dAh = umma_desc(a_hi, PS, 128), dAl = umma_desc(a_lo, PS, 128);
+            const uint64_t dWh = umma_desc(w_hi, NOUT * 16, 128), dWl = umma_desc(w_lo, NOUT * 16, 128);
+            umma_ss(dcol, dAh, dWh, idesc, (k > 0 || t > 0) ? 1u : 0u, 0);
+            umma_ss(dcol, dAl, dWh, idesc, 1u, 0);
+            umma_ss(dcol, dAh, dWl, idesc, 1u, 0);
+          }
         }
+        umma_commit(bar_empty + buf, 0);
       }
-      umma_commit(bar_empty + buf, 0);
     }
     umma_commit(bar_done, 0);
     __syncwarp();
@@ -331,7 +341,10 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
   int cols = 32;
   while (cols < MB * NOUT) cols <<= 1;
   P.tmem_cols = cols;
-  auto kern = conv2d_tc_kernel<NOUT, KS>;
+  uint32_t sb = 0;
+  int rc = dyn_smem_base(ctx, stream, &sb);
+  if (rc) return rc;
+  auto kern = sb == 1024u ? conv2d_tc_kernel<NOUT, KS, true> : conv2d_tc_kernel<NOUT, KS, false>;
   MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((nblk + MB - 1) / MB), (unsigned)(P.Cout / NOUT));
   kern<<<grid, CTC_STAGERS + 32, smem, stream>>>(P);

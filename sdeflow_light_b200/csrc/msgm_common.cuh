@@ -22,6 +22,11 @@ int cuda_fail(cudaError_t e, const char* what);
 
 }  // namespace msgm
 
+struct msgm_ctx;
+namespace msgm {
+int dyn_smem_base(msgm_ctx* ctx, cudaStream_t stream, uint32_t* out);  // sampler_tc.cu
+}
+
 struct msgm_ctx {
   int device;
   int num_sms;

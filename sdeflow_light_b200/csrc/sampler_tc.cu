@@ -638,6 +638,25 @@ __global__ void smem_base_probe(uint32_t* out) {
   if (threadIdx.x == 0) *out = smem_u32(probe_smem);
 }
 
+// Shared-window address at which the dynamic shared memory block of a kernel WITHOUT static __shared__ data starts
+// (1024 on sm_100 with this driver).  Probed once per process (one tiny launch + stream sync: call it outside graph
+// capture first); the tensor-core kernels take it as a compile-time constant when it is 1024, so that every MMA
+// descriptor lives in uniform registers.
+int dyn_smem_base(msgm_ctx* ctx, cudaStream_t stream, uint32_t* out) {
+  static uint32_t cached = 0xFFFFFFFFu;
+  if (cached == 0xFFFFFFFFu) {
+    uint32_t* dptr = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ctx->ws) + 8);
+    smem_base_probe<<<1, 32, 1024, stream>>>(dptr);
+    MSGM_CUDA_TRY(cudaGetLastError());
+    uint32_t h = 0;
+    MSGM_CUDA_TRY(cudaMemcpyAsync(&h, dptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    MSGM_CUDA_TRY(cudaStreamSynchronize(stream));
+    cached = h;
+  }
+  *out = cached;
+  return MSGM_OK;
+}
+
 // ---- host dispatch ---------------------------------------------------------------------------------------------------
 static int ensure_ws(msgm_ctx* ctx, size_t need) {
   if (ctx->ws_bytes >= need) return MSGM_OK;
@@ -662,16 +681,9 @@ static int launch_tc(msgm_ctx* ctx, const msgm_mlp_desc* m, TcParams& P, cudaStr
                                                                 (KIND == MSGM_SDE_MSGM_DENSE && L::TCG) ? P.G : nullptr, img);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
-  static uint32_t smem_base_cached = 0xFFFFFFFFu;
-  if (smem_base_cached == 0xFFFFFFFFu) {  // once per process: where does a dynamic-smem-only kernel's block start?
-    uint32_t* dptr = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(ctx->ws) + 8);
-    smem_base_probe<<<1, 32, 1024, stream>>>(dptr);
-    MSGM_CUDA_TRY(cudaGetLastError());
-    uint32_t h = 0;
-    MSGM_CUDA_TRY(cudaMemcpyAsync(&h, dptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    MSGM_CUDA_TRY(cudaStreamSynchronize(stream));
-    smem_base_cached = h;
-  }
+  uint32_t smem_base_cached = 0;
+  rc = dyn_smem_base(ctx, stream, &smem_base_cached);
+  if (rc) return rc;
   P.smem_base = smem_base_cached;
   auto kern = smem_base_cached == 1024u ? sample_tc_kernel<DP, KIND, true> : sample_tc_kernel<DP, KIND, false>;
   MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES));

@@ -228,6 +228,19 @@ typedef struct {
 int msgm_conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* desc, void* stream);
 int64_t msgm_conv2d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K);
 int msgm_conv2d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, int32_t K, void* wimg, void* stream);
+/* Tensor-core form of msgm_conv1d for the 1-D U-Net (NNUnet1D.py:13-33,81-102): nn.Conv1d k3 (stride 1, padding 1),
+ * k4 (stride 2, padding 1: the down-sampling conv, evaluated at every position and kept at the even ones) or k1, over
+ * the concat [x1, x2]; (C1 + C2) % 16 == 0, C1 % 16 == 0, Cout % 32 == 0.  W (Cout, Cw, K) may carry Cw - (C1 + C2)
+ * trailing embedding channels: they are not packed, their contribution comes in as the folded table E (B, Cout, K) of
+ * msgm_emb_fold and is added per tap where that tap reads inside the signal.  gelu = 1 applies the exact GELU. */
+typedef struct {
+  const float* x1; const float* x2; const void* wimg; const float* bias; const float* E; float* out;
+  int32_t B, C1, C2, Cout, K, stride, Lin, gelu;
+} msgm_conv1d_tc_desc;
+int msgm_conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* desc, void* stream);
+int64_t msgm_conv1d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K);
+int msgm_conv1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw, int32_t Cin, int32_t K, void* wimg,
+                        void* stream);
 /* ss[b, c] = (rstd gamma_c, beta_c - mean rstd gamma_c) with the GroupNorm32 statistics of [x1, x2] (eps 1e-5). */
 int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,
                         int32_t B, const float* gamma, const float* beta, float* ss, void* stream);

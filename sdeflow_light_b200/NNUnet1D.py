@@ -74,6 +74,8 @@ class UNet1D(nn.Module):
             return self._forward(x, t)
 
     # ---- hand-written kernel path (inference) -------------------------------------------------------------------
+    conv_mode = "tc"  # "tc": k3 / k4s2 convs on tcgen05 (split fp16 x3, fp32-level parity); "fp32": CUDA-core kernels only
+
     def _conv(self, h, dev, conv, x1, x2=None, emb=None, gelu=False):
         L = _lib.lib()
         B, C1, Lin = x1.shape
@@ -89,6 +91,22 @@ class UNet1D(nn.Module):
             _lib.check(L.msgm_emb_fold(h, _lib.ptr(W), _lib.ptr(emb), _lib.ptr(E), Cw, C1 + C2, Cemb, Cout, K, B,
                                        _lib.stream_ptr(dev)))
         out = torch.empty((B, Cout, Lout), device=dev, dtype=torch.float32)
+        Cin = C1 + C2
+        if (self.conv_mode == "tc" and Cout % 32 == 0 and Cin % 16 == 0 and C1 % 16 == 0 and Cin > 0 and
+                ((K == 3 and stride == 1 and pad == 1) or (K == 4 and stride == 2 and pad == 1 and Lin >= 2) or
+                 (K == 1 and stride == 1 and pad == 0))):
+            cache = self.__dict__.setdefault("_tc_wimg", {})
+            key = (conv.weight._version, tuple(W.shape), dev.index)
+            ent = cache.get(W.data_ptr())
+            if ent is None or ent[0] != key:
+                img = torch.empty(L.msgm_conv1d_tc_pack_bytes(Cout, Cin, K), device=dev, dtype=torch.uint8)
+                _lib.check(L.msgm_conv1d_tc_pack(h, _lib.ptr(W), Cout, Cw, Cin, K, _lib.ptr(img), _lib.stream_ptr(dev)))
+                ent = cache[W.data_ptr()] = (key, img)
+            d = _lib.Conv1dTcDesc(x1.data_ptr(), None if x2 is None else x2.data_ptr(), ent[1].data_ptr(), bias.data_ptr(),
+                                  None if E is None else E.data_ptr(), out.data_ptr(), B, C1, C2, Cout, K, stride, Lin,
+                                  int(gelu))
+            _lib.check(L.msgm_conv1d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
+            return out
         d = _lib.Conv1dDesc(x1.data_ptr(), None if x2 is None else x2.data_ptr(), W.data_ptr(), bias.data_ptr(),
                             None if E is None else E.data_ptr(), out.data_ptr(), B, C1, C2, Cemb, Cout, K, stride, pad,
                             Lin, Lout, int(gelu))

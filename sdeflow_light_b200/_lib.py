@@ -53,6 +53,11 @@ class Conv2dTcDesc(C.Structure):
                [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "stride", "up", "Hs", "Ws", "prologue")]
 
 
+class Conv1dTcDesc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x1", "x2", "wimg", "bias", "E", "out")] + \
+               [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "stride", "Lin", "gelu")]
+
+
 _lib = None
 _lock = threading.Lock()
 _ctx = {}
@@ -65,7 +70,8 @@ SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy",
            "msgm_conv1d", "msgm_emb_fold", "msgm_convt1d_k4s2", "msgm_embed_mlp", "msgm_normalize_log_radius",
            "msgm_conv2d", "msgm_gn_stats", "msgm_emb_proj", "msgm_sincos_embed_mlp", "msgm_attention", "msgm_vort_pre",
            "msgm_vort_post", "msgm_conv2d_tc", "msgm_conv2d_tc_pack_bytes", "msgm_conv2d_tc_pack", "msgm_gn_scale_shift",
-           "msgm_attention_tc_supported", "msgm_attention_tc"]
+           "msgm_attention_tc_supported", "msgm_attention_tc", "msgm_conv1d_tc", "msgm_conv1d_tc_pack_bytes",
+           "msgm_conv1d_tc_pack"]
 
 
 def lib() -> C.CDLL:
@@ -109,6 +115,10 @@ def lib() -> C.CDLL:
                 L.msgm_conv2d_tc_pack_bytes.restype = C.c_int64
                 L.msgm_conv2d_tc_pack_bytes.argtypes = [C.c_int32] * 3
                 L.msgm_conv2d_tc_pack.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_void_p] * 2
+                L.msgm_conv1d_tc.argtypes = [C.c_void_p, C.POINTER(Conv1dTcDesc), C.c_void_p]
+                L.msgm_conv1d_tc_pack_bytes.restype = C.c_int64
+                L.msgm_conv1d_tc_pack_bytes.argtypes = [C.c_int32] * 3
+                L.msgm_conv1d_tc_pack.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2
                 L.msgm_gn_scale_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + \
                     [C.c_void_p] * 4
                 L.msgm_gn_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2

@@ -50,7 +50,8 @@ int gn_stats(msgm_ctx*, const float*, int, const float*, int, int, int, int, flo
 int conv2d(msgm_ctx*, const msgm_conv2d_desc*, cudaStream_t);
 int conv2d_tc(msgm_ctx*, const msgm_conv2d_tc_desc*, cudaStream_t);
 size_t conv2d_tc_pack_bytes(int, int, int);
-int conv2d_tc_pack(msgm_ctx*, const float*, int, int, int, void*, cudaStream_t);
+int conv2d_tc_pack(msgm_ctx*, const float*, int, int, int, int, void*, cudaStream_t);
+int conv1d_tc(msgm_ctx*, const msgm_conv1d_tc_desc*, cudaStream_t);
 int gn_scale_shift(msgm_ctx*, const float*, int, const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int emb_proj(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int sincos_embed_mlp(msgm_ctx*, const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
@@ -360,14 +361,42 @@ int msgm_conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* D, void* stream) {
 
 int64_t msgm_conv2d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K) {
   if (!conv2d_tc_shape_ok(Cout, Cin, 0, K)) return -1;
-  return (int64_t)conv2d_tc_pack_bytes(Cout, Cin, K);
+  return (int64_t)conv2d_tc_pack_bytes(Cout, Cin, K * K);
 }
 
 int msgm_conv2d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, int32_t K, void* wimg, void* stream) {
   if (!ctx || !W || !wimg) return invalid("msgm_conv2d_tc_pack: NULL argument");
   if (!conv2d_tc_shape_ok(Cout, Cin, 0, K)) return invalid("msgm_conv2d_tc_pack: unsupported shape");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
-  return conv2d_tc_pack(ctx, W, Cout, Cin, K, wimg, (cudaStream_t)stream);
+  return conv2d_tc_pack(ctx, W, Cout, Cin, Cin, K * K, wimg, (cudaStream_t)stream);
+}
+
+static bool conv1d_tc_shape_ok(int Cout, int Cin, int C1, int K) {
+  return (K == 1 || K == 3 || K == 4) && Cout >= 32 && Cout % 32 == 0 && Cin >= 16 && Cin % 16 == 0 && C1 % 16 == 0;
+}
+
+int msgm_conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* D, void* stream) {
+  if (!ctx || !D || !D->x1 || !D->wimg || !D->out) return invalid("msgm_conv1d_tc: NULL argument");
+  const int Cin = D->C1 + (D->x2 ? D->C2 : 0);
+  if (!conv1d_tc_shape_ok(D->Cout, Cin, D->C1, D->K) || D->Lin < 1 || D->B < 0 ||
+      !((D->K == 4 && D->stride == 2 && D->Lin >= 2) || (D->K != 4 && D->stride == 1)))
+    return invalid("msgm_conv1d_tc: unsupported shape (k3/k1 stride 1 or k4 stride 2, Cin % 16 == 0, C1 % 16 == 0, Cout % 32 == 0)");
+  if (D->B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv1d_tc(ctx, D, (cudaStream_t)stream);
+}
+
+int64_t msgm_conv1d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K) {
+  if (!conv1d_tc_shape_ok(Cout, Cin, 0, K)) return -1;
+  return (int64_t)conv2d_tc_pack_bytes(Cout, Cin, K);
+}
+
+int msgm_conv1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw, int32_t Cin, int32_t K, void* wimg,
+                        void* stream) {
+  if (!ctx || !W || !wimg) return invalid("msgm_conv1d_tc_pack: NULL argument");
+  if (!conv1d_tc_shape_ok(Cout, Cin, 0, K) || Cw < Cin) return invalid("msgm_conv1d_tc_pack: unsupported shape");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv2d_tc_pack(ctx, W, Cout, Cw, Cin, K, wimg, (cudaStream_t)stream);
 }
 
 int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,

@@ -36,11 +36,13 @@ struct ConvTcParams {
   const float* ebias;         // (B, Cout) or NULL
   const float* res;           // (B, Cout, Ho, Wo) or NULL
   const float* ss;            // (B, Cin, 2) GroupNorm scale / shift or NULL
+  const float* etab;          // 1-D only: (B, Cout, NT) folded embedding channels per tap (NNUnet1D.py:156-175) or NULL
   float* out;
   int silu;                   // apply SiLU after the affine normalisation
+  int gelu;                   // 1-D only: exact GELU in the epilogue (ConvBlock1D, NNUnet1D.py:13-33)
   int B, Cout, stride, up, Hs, Ws;  // (Hs, Ws): stored input size; the conv sees (Hs up, Ws up)
   int Hi, Wi, Hp, Wp, Ho, Wo;
-  int halo, SL, MB, NC;       // halo = PAD (Wp + 1); SL = 128 MB + 2 halo staged positions; NC = Cin / 16 chunks
+  int halo, SL, MB, NC;       // halo = PADH Wp + PADR; SL = 128 MB + 2 halo staged positions; NC = Cin / 16 chunks
   long long total;            // B Hp Wp
   int tmem_cols;
   int* flags;
@@ -53,9 +55,17 @@ constexpr int CTC_STAGERS = 256;
 // CONST_BASE: the dynamic shared memory block starts at shared-window address 1024 (probed by the host, verified
 // here), so every MMA descriptor is computed from kernel parameters and constants only and ptxas keeps it in uniform
 // registers -- no per-MMA R2UR / vote sequences on the issue path.
-template <int NOUT, int KS, bool CONST_BASE>
+// NT = taps: 9 (3x3, padding 1), 1 (1x1), 3 (1-D k3 p1), 4 (1-D k4 p1, used with stride 2: taps at -1..+2).
+template <int NT>
+struct TapGeom {
+  static constexpr int PADH = NT == 9 ? 1 : 0;
+  static constexpr int PADL = NT == 1 ? 0 : 1;
+  static constexpr int PADR = NT == 4 ? 2 : PADL;
+};
+
+template <int NOUT, int NT, bool CONST_BASE>
 __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __grid_constant__ ConvTcParams P) {
-  constexpr int NT = KS * KS, PAD = KS / 2;
+  constexpr int PADH = TapGeom<NT>::PADH, PADL = TapGeom<NT>::PADL;
   constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;  // bytes of packed weights per 16-channel chunk
   extern __shared__ __align__(128) unsigned char smem_dyn[];
   // carve: [barriers 128 B][A stage 0][A stage 1][W stage 0][W stage 1], 128-byte aligned
@@ -113,7 +123,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
           const uint32_t dcol = tbase + (uint32_t)(mb * NOUT);
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
-            const int toff = KS == 3 ? (t / 3 - 1) * P.Wp + (t % 3 - 1) : 0;
+            const int toff = NT == 9 ? (t / 3 - 1) * P.Wp + (t % 3 - 1) : (NT == 1 ? 0 : t - 1);
             const uint32_t a_hi = a_base + (uint32_t)((mb * 128 + P.halo + toff) * 16);
             const uint32_t a_lo = a_hi + 2u * (uint32_t)PS;
             const uint32_t w_hi = w_base + (uint32_t)(t * 4 * NOUT * 16);
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
         uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
         if (q >= 0 && q < P.total) {
           const int b = (int)(q / HpWp), rem = (int)(q - (long long)b * HpWp);
-          const int r = rem / P.Wp - PAD, c = rem % P.Wp - PAD;
+          const int r = rem / P.Wp - PADH, c = rem % P.Wp - PADL;
           if (r >= 0 && r < P.Hi && c >= 0 && c < P.Wi) {
             const int ch0 = k * 16 + kc * 8;  // 8 consecutive input channels; a chunk never straddles x1 | x2 (C1 % 16 == 0)
             const float* src = ch0 < P.C1 ? P.x1 + ((size_t)b * P.C1 + ch0) * HWs : P.x2 + ((size_t)b * P.C2 + (ch0 - P.C1)) * HWs;
@@ -194,15 +204,17 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
     for (int mb = 0; mb < P.MB; ++mb) {
       const long long p = p0 + mb * 128 + q4 * 32 + lane;
       bool valid = ok && p < P.total;
-      int b = 0, oy = 0, ox = 0;
+      int b = 0, oy = 0, ox = 0, ccol = 0;
       if (valid) {
         b = (int)(p / HpWp);
         const int rem = (int)(p - (long long)b * HpWp);
-        const int r = rem / P.Wp - PAD, c = rem % P.Wp - PAD;
+        const int r = rem / P.Wp - PADH, c = rem % P.Wp - PADL;
         valid = r >= 0 && r < P.Hi && c >= 0 && c < P.Wi;
+        ccol = c;
         if (P.stride == 2) {
           valid = valid && !(r & 1) && !(c & 1);
           oy = r >> 1; ox = c >> 1;
+          valid = valid && oy < P.Ho && ox < P.Wo;
         } else {
           oy = r; ox = c;
         }
@@ -222,6 +234,15 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
             if (P.ebias) v += __ldg(P.ebias + (size_t)b * P.Cout + co);
             const size_t o = ((size_t)b * P.Cout + co) * HWo + oy * P.Wo + ox;
             if (P.res) v += __ldg(P.res + o);
+            if constexpr (NT == 3 || NT == 4) {
+              if (P.etab) {  // embedding channels are constant along the signal: a tap contributes where it reads inside it
+                const float* et = P.etab + ((size_t)b * P.Cout + co) * NT;
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                  if (ccol + t - 1 >= 0 && ccol + t - 1 < P.Wi) v += __ldg(et + t);
+              }
+              if (P.gelu) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+            }
             P.out[o] = v;
           }
         }
@@ -236,8 +257,8 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
 }
 
 // ---- weight packing: (Cout, Cin, K, K) fp32 -> [ntile][chunk][tap][hi|lo][kc][NOUT][8] fp16 ---------------------------
-__global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int Cin, int KK, int NOUT, __half* __restrict__ img,
-                                      long long nel) {
+__global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int Cw, int Cin, int KK, int NOUT,
+                                      __half* __restrict__ img, long long nel) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nel) return;
   const int j = (int)(e % 8);
@@ -250,7 +271,7 @@ __global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int
   const int k = (int)(r % NC);
   const int nt = (int)(r / NC);
   const int co = nt * NOUT + n, ci = k * 16 + kc * 8 + j;
-  const float v = W[((size_t)co * Cin + ci) * KK + t];
+  const float v = W[((size_t)co * Cw + ci) * KK + t];  // Cw >= Cin: the weight tensor may carry extra (folded) input channels
   const __half hi = __float2half_rn(v);
   img[e] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
 }
@@ -299,11 +320,12 @@ __global__ void __launch_bounds__(256) gn_scale_shift_kernel(const float* __rest
 // ---- host dispatch ---------------------------------------------------------------------------------------------------
 int conv2d_tc_nout(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32); }
 
-size_t conv2d_tc_pack_bytes(int Cout, int Cin, int K) { return (size_t)Cout * Cin * K * K * 2 * 2; }
+size_t conv2d_tc_pack_bytes(int Cout, int Cin, int KK) { return (size_t)Cout * Cin * KK * 2 * 2; }
 
-int conv2d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cin, int K, void* img, cudaStream_t stream) {
-  const long long nel = (long long)Cout * Cin * K * K * 2;
-  conv2d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cin, K * K, conv2d_tc_nout(Cout),
+// W is (Cout, Cw, taps) with the first Cin input channels packed (Cw > Cin: trailing channels are handled elsewhere).
+int conv2d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cw, int Cin, int KK, void* img, cudaStream_t stream) {
+  const long long nel = (long long)Cout * Cin * KK * 2;
+  conv2d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cw, Cin, KK, conv2d_tc_nout(Cout),
                                                                           reinterpret_cast<__half*>(img), nel);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
@@ -319,10 +341,13 @@ int gn_scale_shift(msgm_ctx* ctx, const float* x1, int C1, const float* x2, int 
   return MSGM_OK;
 }
 
-template <int NOUT, int KS>
+template <int NOUT, int NT>
 static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
-  constexpr int NT = KS * KS;
   constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;
+  P.Hp = P.Hi + 2 * TapGeom<NT>::PADH;
+  P.Wp = P.Wi + TapGeom<NT>::PADL + TapGeom<NT>::PADR;
+  P.halo = TapGeom<NT>::PADH * P.Wp + TapGeom<NT>::PADR;
+  P.total = (long long)P.B * P.Hp * P.Wp;
   // M blocks per CTA: as many as TMEM (512 columns) and shared memory allow while still giving every SM a tile
   const long long nblk = (P.total + 127) / 128;
   int MB = 4;
@@ -335,7 +360,7 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
     if (smem <= 227 * 1024 || MB == 1) break;
   }
   if (smem > 227 * 1024) {
-    set_error("msgm_conv2d_tc: tile does not fit shared memory (image too wide)");
+    set_error("msgm_conv_tc: tile does not fit shared memory (image too wide)");
     return MSGM_ERR_UNSUPPORTED;
   }
   int cols = 32;
@@ -344,13 +369,21 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
   uint32_t sb = 0;
   int rc = dyn_smem_base(ctx, stream, &sb);
   if (rc) return rc;
-  auto kern = sb == 1024u ? conv2d_tc_kernel<NOUT, KS, true> : conv2d_tc_kernel<NOUT, KS, false>;
+  auto kern = sb == 1024u ? conv2d_tc_kernel<NOUT, NT, true> : conv2d_tc_kernel<NOUT, NT, false>;
   MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((nblk + MB - 1) / MB), (unsigned)(P.Cout / NOUT));
   kern<<<grid, CTC_STAGERS + 32, smem, stream>>>(P);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;
+}
+
+template <int NT>
+static int launch_conv_tc_n(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
+  const int nout = conv2d_tc_nout(P.Cout);
+  if (nout == 128) return launch_conv_tc<128, NT>(ctx, P, stream);
+  if (nout == 64) return launch_conv_tc<64, NT>(ctx, P, stream);
+  return launch_conv_tc<32, NT>(ctx, P, stream);
 }
 
 int conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* D, cudaStream_t stream) {
@@ -363,22 +396,29 @@ int conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* D, cudaStream_t stream) 
   P.B = D->B; P.Cout = D->Cout; P.stride = D->stride; P.up = D->up; P.Hs = D->Hs; P.Ws = D->Ws;
   const int pad = D->K / 2;
   P.Hi = D->Hs * D->up; P.Wi = D->Ws * D->up;
-  P.Hp = P.Hi + 2 * pad; P.Wp = P.Wi + 2 * pad;
   P.Ho = (P.Hi + 2 * pad - D->K) / D->stride + 1;
   P.Wo = (P.Wi + 2 * pad - D->K) / D->stride + 1;
-  P.halo = pad * (P.Wp + 1);
   P.NC = (P.C1 + P.C2) / 16;
-  P.total = (long long)D->B * P.Hp * P.Wp;
   P.flags = reinterpret_cast<int*>(ctx->ws);
-  const int nout = conv2d_tc_nout(D->Cout);
-  if (D->K == 3) {
-    if (nout == 128) return launch_conv_tc<128, 3>(ctx, P, stream);
-    if (nout == 64) return launch_conv_tc<64, 3>(ctx, P, stream);
-    return launch_conv_tc<32, 3>(ctx, P, stream);
-  }
-  if (nout == 128) return launch_conv_tc<128, 1>(ctx, P, stream);
-  if (nout == 64) return launch_conv_tc<64, 1>(ctx, P, stream);
-  return launch_conv_tc<32, 1>(ctx, P, stream);
+  return D->K == 3 ? launch_conv_tc_n<9>(ctx, P, stream) : launch_conv_tc_n<1>(ctx, P, stream);
+}
+
+// nn.Conv1d k3 (stride 1) / k4 (stride 2) / k1, padding 1 (0 for k1), as the H = 1 case of the same kernel
+int conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* D, cudaStream_t stream) {
+  if (D->B == 0) return MSGM_OK;
+  ConvTcParams P{};
+  P.x1 = D->x1; P.C1 = D->C1; P.x2 = D->x2; P.C2 = D->x2 ? D->C2 : 0;
+  P.wimg = reinterpret_cast<const unsigned char*>(D->wimg);
+  P.bias = D->bias; P.etab = D->E; P.out = D->out; P.gelu = D->gelu;
+  P.B = D->B; P.Cout = D->Cout; P.stride = D->stride; P.up = 1; P.Hs = 1; P.Ws = D->Lin;
+  P.Hi = 1; P.Wi = D->Lin; P.Ho = 1;
+  const int pad = D->K == 1 ? 0 : 1;
+  P.Wo = (D->Lin + 2 * pad - D->K) / D->stride + 1;
+  P.NC = (P.C1 + P.C2) / 16;
+  P.flags = reinterpret_cast<int*>(ctx->ws);
+  if (D->K == 3) return launch_conv_tc_n<3>(ctx, P, stream);
+  if (D->K == 4) return launch_conv_tc_n<4>(ctx, P, stream);
+  return launch_conv_tc_n<1>(ctx, P, stream);
 }
 
 }  // namespace msgm

@@ -136,3 +136,51 @@ def test_attention_tc_matches_float64(B, Cc, T):
     err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
     assert torch.isfinite(out).all() and err < 2e-5, f"attention_tc rel err {err:.3e}"
     assert L.msgm_attention_tc_supported(128, 512) == 0 and L.msgm_attention_tc_supported(40, 64) == 0
+
+
+# ---- 1-D form (NNUnet1D.py: ConvBlock1D k3 convs, the k4 stride-2 down convs, folded embedding channels, GELU) ----------
+CASES_1D = [
+    # B, C1, C2, Cemb, Cout, K, stride, L, gelu
+    (3, 32, 0, 0, 32, 3, 1, 1000, 1),      # ConvBlock1D second conv
+    (2, 32, 32, 128, 32, 3, 1, 1000, 1),   # decoder block over [up, skip] + 128 folded embedding channels
+    (4, 128, 128, 128, 128, 3, 1, 125, 1),  # widest decoder contraction, odd length
+    (3, 64, 0, 0, 64, 4, 2, 500, 0),       # down-sampling conv
+    (3, 128, 0, 0, 128, 4, 2, 125, 0),     # down-sampling conv, odd length
+    (2, 16, 0, 8, 32, 3, 1, 7, 1),         # ragged: shorter than one tile, embedding table at both borders
+    (2, 32, 0, 0, 64, 1, 1, 300, 0),       # pointwise
+]
+
+
+@pytest.mark.parametrize("case", CASES_1D)
+def test_conv1d_tc_matches_float64(case):
+    B, C1, C2, Cemb, Cout, K, stride, Lin, gelu = case
+    dev = torch.device(DEV)
+    h, L = _lib.ctx(dev), _lib.lib()
+    torch.manual_seed(Lin + Cout + K)
+    x1 = torch.randn(B, C1, Lin, device=dev) * 1.3
+    x2 = torch.randn(B, C2, Lin, device=dev) if C2 else None
+    emb = torch.randn(B, Cemb, device=dev) if Cemb else None
+    Cw = C1 + C2 + Cemb
+    W = torch.randn(Cout, Cw, K, device=dev) / (Cw * K) ** 0.5
+    bias = torch.randn(Cout, device=dev)
+    pad = 0 if K == 1 else 1
+    Lout = (Lin + 2 * pad - K) // stride + 1
+    E = None
+    if Cemb:
+        E = torch.empty((B, Cout, K), device=dev)
+        _lib.check(L.msgm_emb_fold(h, _lib.ptr(W), _lib.ptr(emb), _lib.ptr(E), Cw, C1 + C2, Cemb, Cout, K, B,
+                                   _lib.stream_ptr(dev)))
+    img = torch.empty(L.msgm_conv1d_tc_pack_bytes(Cout, C1 + C2, K), device=dev, dtype=torch.uint8)
+    _lib.check(L.msgm_conv1d_tc_pack(h, _lib.ptr(W), Cout, Cw, C1 + C2, K, _lib.ptr(img), _lib.stream_ptr(dev)))
+    out = torch.full((B, Cout, Lout), float("nan"), device=dev)
+    d = _lib.Conv1dTcDesc(x1.data_ptr(), None if x2 is None else x2.data_ptr(), img.data_ptr(), bias.data_ptr(),
+                          None if E is None else E.data_ptr(), out.data_ptr(), B, C1, C2, Cout, K, stride, Lin, gelu)
+    _lib.check(L.msgm_conv1d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    feats = [x1] + ([x2] if C2 else []) + ([emb[:, :, None].expand(-1, -1, Lin)] if Cemb else [])
+    ref = F.conv1d(torch.cat(feats, 1).double(), W.double(), bias.double(), stride=stride, padding=pad)
+    if gelu:
+        ref = F.gelu(ref)
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-5, f"conv1d_tc rel err {err:.3e}"

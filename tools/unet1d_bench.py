@@ -30,7 +30,14 @@ def timeit(fn, reps=10):
 
 
 with torch.no_grad():
+    net.conv_mode = "fp32"
+    ms_f, n_f = timeit(lambda: net(x, t))
+    y_f = net(x, t)
+    net.conv_mode = "tc"
     ms_k, n_k = timeit(lambda: net(x, t))
+    y_k = net(x, t)
+    print(f"tc vs fp32 kernels: rel diff {float((y_k - y_f).abs().max() / y_f.abs().max()):.2e}; fp32 CUDA-core kernels "
+          f"{ms_f:.2f} ms ({n_f:.0f} launches)")
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         ms_t, _ = timeit(lambda: net._forward(x, t))
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):

@@ -241,6 +241,12 @@ int msgm_conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* desc, void* stream)
 int64_t msgm_conv1d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K);
 int msgm_conv1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw, int32_t Cin, int32_t K, void* wimg,
                         void* stream);
+/* Tensor-core form of msgm_convt1d_k4s2: the transposed conv is a 3-tap conv with 2 Cout output columns (even | odd
+ * outputs).  Cin % 16 == 0, Cout % 16 == 0.  W (Cin, Cout, 4) is packed by msgm_convt1d_tc_pack into 24 Cin Cout bytes.
+ * `out` (B, Cout, Lout >= 2 Lin) must be zero-filled by the caller when Lout > 2 Lin (the reference's right padding). */
+int msgm_convt1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, void* wimg, void* stream);
+int msgm_convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bias, float* out, int32_t B, int32_t Cin,
+                    int32_t Cout, int32_t Lin, int32_t Lout, void* stream);
 /* ss[b, c] = (rstd gamma_c, beta_c - mean rstd gamma_c) with the GroupNorm32 statistics of [x1, x2] (eps 1e-5). */
 int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,
                         int32_t B, const float* gamma, const float* beta, float* ss, void* stream);

@@ -152,9 +152,23 @@ class UNet1D(nn.Module):
             skip = skips.pop()
             Bc, Cin, Lin = cur.shape
             W, bias = _lib.f32c(up.weight, dev), _lib.f32c(up.bias, dev)
-            upo = torch.empty((Bc, W.shape[1], skip.shape[-1]), device=dev, dtype=torch.float32)
-            _lib.check(L.msgm_convt1d_k4s2(h, _lib.ptr(cur), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(upo), Bc, Cin, W.shape[1],
-                                           Lin, skip.shape[-1], _lib.stream_ptr(dev)))
+            Cup, Lup = W.shape[1], skip.shape[-1]
+            if self.conv_mode == "tc" and Cin % 16 == 0 and Cup % 16 == 0 and Lup >= 2 * Lin:
+                cache = self.__dict__.setdefault("_tc_wimg", {})
+                key = (up.weight._version, tuple(W.shape), dev.index)
+                ent = cache.get(W.data_ptr())
+                if ent is None or ent[0] != key:
+                    img = torch.empty(24 * Cin * Cup, device=dev, dtype=torch.uint8)
+                    _lib.check(L.msgm_convt1d_tc_pack(h, _lib.ptr(W), Cup, Cin, _lib.ptr(img), _lib.stream_ptr(dev)))
+                    ent = cache[W.data_ptr()] = (key, img)
+                alloc = torch.zeros if Lup > 2 * Lin else torch.empty
+                upo = alloc((Bc, Cup, Lup), device=dev, dtype=torch.float32)
+                _lib.check(L.msgm_convt1d_tc(h, _lib.ptr(cur), _lib.ptr(ent[1]), _lib.ptr(bias), _lib.ptr(upo), Bc, Cin, Cup,
+                                             Lin, Lup, _lib.stream_ptr(dev)))
+            else:
+                upo = torch.empty((Bc, Cup, Lup), device=dev, dtype=torch.float32)
+                _lib.check(L.msgm_convt1d_k4s2(h, _lib.ptr(cur), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(upo), Bc, Cin, Cup,
+                                               Lin, Lup, _lib.stream_ptr(dev)))
             cur = self._block(h, dev, block, upo, skip, emb)
         out = self._conv(h, dev, self.final, cur)
         return out.squeeze(1)

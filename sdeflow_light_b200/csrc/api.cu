@@ -52,6 +52,8 @@ int conv2d_tc(msgm_ctx*, const msgm_conv2d_tc_desc*, cudaStream_t);
 size_t conv2d_tc_pack_bytes(int, int, int);
 int conv2d_tc_pack(msgm_ctx*, const float*, int, int, int, int, void*, cudaStream_t);
 int conv1d_tc(msgm_ctx*, const msgm_conv1d_tc_desc*, cudaStream_t);
+int convt1d_tc_pack(msgm_ctx*, const float*, int, int, void*, cudaStream_t);
+int convt1d_tc(msgm_ctx*, const float*, const void*, const float*, float*, int, int, int, int, int, cudaStream_t);
 int gn_scale_shift(msgm_ctx*, const float*, int, const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int emb_proj(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int sincos_embed_mlp(msgm_ctx*, const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
@@ -397,6 +399,22 @@ int msgm_conv1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw,
   if (!conv1d_tc_shape_ok(Cout, Cin, 0, K) || Cw < Cin) return invalid("msgm_conv1d_tc_pack: unsupported shape");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return conv2d_tc_pack(ctx, W, Cout, Cw, Cin, K, wimg, (cudaStream_t)stream);
+}
+
+int msgm_convt1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, void* wimg, void* stream) {
+  if (!ctx || !W || !wimg) return invalid("msgm_convt1d_tc_pack: NULL argument");
+  if (Cout < 16 || Cout % 16 || Cin < 16 || Cin % 16) return invalid("msgm_convt1d_tc_pack: Cin % 16 == 0 and Cout % 16 == 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return convt1d_tc_pack(ctx, W, Cout, Cin, wimg, (cudaStream_t)stream);
+}
+
+int msgm_convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bias, float* out, int32_t B, int32_t Cin,
+                    int32_t Cout, int32_t Lin, int32_t Lout, void* stream) {
+  if (!ctx || !x || !wimg || !out || B < 0 || Lin < 1 || Lout < 2 * Lin) return invalid("msgm_convt1d_tc: bad argument");
+  if (Cout < 16 || Cout % 16 || Cin < 16 || Cin % 16) return invalid("msgm_convt1d_tc: Cin % 16 == 0 and Cout % 16 == 0");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return convt1d_tc(ctx, x, wimg, bias, out, B, Cin, Cout, Lin, Lout, (cudaStream_t)stream);
 }
 
 int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,

@@ -40,6 +40,8 @@ struct ConvTcParams {
   float* out;
   int silu;                   // apply SiLU after the affine normalisation
   int gelu;                   // 1-D only: exact GELU in the epilogue (ConvBlock1D, NNUnet1D.py:13-33)
+  int convt;                  // 1-D only: transposed conv k4 s2 p1 as a 3-tap conv with 2 x convt output columns
+                              // (n = parity * convt + co -> out[b, co, 2 c + parity]); convt = real Cout, else 0
   int B, Cout, stride, up, Hs, Ws;  // (Hs, Ws): stored input size; the conv sees (Hs up, Ws up)
   int Hi, Wi, Hp, Wp, Ho, Wo;
   int halo, SL, MB, NC;       // halo = PADH Wp + PADR; SL = 128 MB + 2 halo staged positions; NC = Cin / 16 chunks
@@ -228,8 +230,17 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = co0 + half * NH + cc + j;
+            int co = co0 + half * NH + cc + j;
             float v = __uint_as_float(rr[j]);
+            if constexpr (NT == 3) {
+              if (P.convt) {  // ConvTranspose1d: even / odd outputs are the two halves of the N dimension
+                const int par = co >= P.convt ? 1 : 0;
+                co -= par * P.convt;
+                if (P.bias) v += __ldg(P.bias + co);
+                P.out[((size_t)b * P.convt + co) * P.Wo + 2 * ccol + par] = v;
+                continue;
+              }
+            }
             if (P.bias) v += __ldg(P.bias + co);
             if (P.ebias) v += __ldg(P.ebias + (size_t)b * P.Cout + co);
             const size_t o = ((size_t)b * P.Cout + co) * HWo + oy * P.Wo + ox;
@@ -272,6 +283,28 @@ __global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int
   const int nt = (int)(r / NC);
   const int co = nt * NOUT + n, ci = k * 16 + kc * 8 + j;
   const float v = W[((size_t)co * Cw + ci) * KK + t];  // Cw >= Cin: the weight tensor may carry extra (folded) input channels
+  const __half hi = __float2half_rn(v);
+  img[e] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
+}
+
+// ConvTranspose1d(Cin, Cout, k4, s2, p1), W (Cin, Cout, 4): out[2m] = x[m] W1 + x[m-1] W3, out[2m+1] = x[m+1] W0 + x[m] W2
+// -> a 3-tap conv (offsets -1, 0, +1) with 2 Cout output columns n = parity Cout + co; one third of the image is zeros.
+__global__ void convt1d_tc_pack_kernel(const float* __restrict__ W, int Cout, int Cin, int NOUT, __half* __restrict__ img,
+                                       long long nel) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nel) return;
+  const int j = (int)(e % 8);
+  long long r = e / 8;
+  const int n = (int)(r % NOUT); r /= NOUT;
+  const int kc = (int)(r % 2); r /= 2;
+  const int hl = (int)(r % 2); r /= 2;
+  const int t = (int)(r % 3); r /= 3;
+  const int NC = Cin / 16;
+  const int k = (int)(r % NC);
+  const int nt = (int)(r / NC);
+  const int nn = nt * NOUT + n, par = nn >= Cout ? 1 : 0, co = nn - par * Cout, ci = k * 16 + kc * 8 + j;
+  const int wk = par == 0 ? (t == 0 ? 3 : (t == 1 ? 1 : -1)) : (t == 0 ? -1 : (t == 1 ? 2 : 0));
+  const float v = wk >= 0 ? W[((size_t)ci * Cout + co) * 4 + wk] : 0.0f;
   const __half hi = __float2half_rn(v);
   img[e] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
 }
@@ -419,6 +452,30 @@ int conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* D, cudaStream_t stream) 
   if (D->K == 3) return launch_conv_tc_n<3>(ctx, P, stream);
   if (D->K == 4) return launch_conv_tc_n<4>(ctx, P, stream);
   return launch_conv_tc_n<1>(ctx, P, stream);
+}
+
+int convt1d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cin, void* img, cudaStream_t stream) {
+  const long long nel = (long long)2 * Cout * Cin * 3 * 2;
+  convt1d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cin, conv2d_tc_nout(2 * Cout),
+                                                                           reinterpret_cast<__half*>(img), nel);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+// out (B, Cout, Lout) must be zero beyond 2 Lin (the reference right-pads with zeros, NNUnet1D.py:165-169)
+int convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bias, float* out, int B, int Cin, int Cout,
+               int Lin, int Lout, cudaStream_t stream) {
+  if (B == 0) return MSGM_OK;
+  ConvTcParams P{};
+  P.x1 = x; P.C1 = Cin;
+  P.wimg = reinterpret_cast<const unsigned char*>(wimg);
+  P.bias = bias; P.out = out; P.convt = Cout;
+  P.B = B; P.Cout = 2 * Cout; P.stride = 1; P.up = 1; P.Hs = 1; P.Ws = Lin;
+  P.Hi = 1; P.Wi = Lin; P.Ho = 1; P.Wo = Lout;
+  P.NC = Cin / 16;
+  P.flags = reinterpret_cast<int*>(ctx->ws);
+  return launch_conv_tc_n<3>(ctx, P, stream);
 }
 
 }  // namespace msgm

@@ -184,3 +184,26 @@ def test_conv1d_tc_matches_float64(case):
     assert out.shape == ref.shape and torch.isfinite(out).all()
     err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
     assert err < 2e-5, f"conv1d_tc rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("B,Cin,Cout,Lin,Lout", [(3, 128, 128, 125, 250), (2, 128, 64, 250, 500), (4, 64, 32, 62, 125),
+                                                 (2, 16, 16, 3, 7)])
+def test_convt1d_tc_matches_float64(B, Cin, Cout, Lin, Lout):
+    """nn.ConvTranspose1d(k4, s2, p1) + right zero padding (NNUnet1D.py:98,165-169) as a 3-tap tensor-core conv."""
+    dev = torch.device(DEV)
+    h, L = _lib.ctx(dev), _lib.lib()
+    torch.manual_seed(Lin + Cout)
+    x = torch.randn(B, Cin, Lin, device=dev)
+    W = torch.randn(Cin, Cout, 4, device=dev) / (Cin * 2) ** 0.5
+    bias = torch.randn(Cout, device=dev)
+    img = torch.empty(24 * Cin * Cout, device=dev, dtype=torch.uint8)
+    _lib.check(L.msgm_convt1d_tc_pack(h, _lib.ptr(W), Cout, Cin, _lib.ptr(img), _lib.stream_ptr(dev)))
+    out = torch.zeros((B, Cout, Lout), device=dev)
+    out[:, :, :2 * Lin] = float("nan")
+    _lib.check(L.msgm_convt1d_tc(h, _lib.ptr(x), _lib.ptr(img), _lib.ptr(bias), _lib.ptr(out), B, Cin, Cout, Lin, Lout,
+                                 _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    ref = F.pad(F.conv_transpose1d(x.double(), W.double(), bias.double(), stride=2, padding=1), (0, Lout - 2 * Lin))
+    assert torch.isfinite(out).all()
+    err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-5, f"convt1d_tc rel err {err:.3e}"

@@ -46,6 +46,7 @@ struct ConvTcParams {
   int Hi, Wi, Hp, Wp, Ho, Wo;
   int halo, SL, MB, NC;       // halo = PADH Wp + PADR; SL = 128 MB + 2 halo staged positions; NC = Cin / 16 chunks
   long long total;            // B Hp Wp
+  uint32_t mul_img, shr_img, mul_row, shr_row;  // magic numbers: n / (Hp Wp) and n / Wp for n < 2^31
   int tmem_cols;
   int* flags;
 };
@@ -53,6 +54,11 @@ struct ConvTcParams {
 __device__ __forceinline__ float silu_acc(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 constexpr int CTC_STAGERS = 256;
+
+// n / d for n < 2^31 with the precomputed (mul, shr) of find_divisor below (d == 1: mul = 0)
+__device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr) {
+  return mul ? (int)(__umulhi((uint32_t)n, mul) >> shr) : n;
+}
 
 // CONST_BASE: the dynamic shared memory block starts at shared-window address 1024 (probed by the host, verified
 // here), so every MMA descriptor is computed from kernel parameters and constants only and ptxas keeps it in uniform
@@ -66,7 +72,7 @@ struct TapGeom {
 };
 
 template <int NOUT, int NT, bool CONST_BASE>
-__global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __grid_constant__ ConvTcParams P) {
+__global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_tc_kernel(const __grid_constant__ ConvTcParams P) {
   constexpr int PADH = TapGeom<NT>::PADH, PADL = TapGeom<NT>::PADL;
   constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;  // bytes of packed weights per 16-channel chunk
   extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -157,41 +163,69 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
         tma_bulk_g2s(wdst, P.wimg + ((size_t)blockIdx.y * P.NC + k) * WSTAGE, (uint32_t)WSTAGE, bar_full + buf);
       }
       unsigned char* adst = sA + buf * ASTAGE;
-      for (int e = tid; e < 2 * P.SL; e += CTC_STAGERS) {
-        const int kc = e >= P.SL ? 1 : 0, s = e - kc * P.SL;
-        const long long q = p0 - P.halo + s;
-        uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
-        if (q >= 0 && q < P.total) {
-          const int b = (int)(q / HpWp), rem = (int)(q - (long long)b * HpWp);
-          const int r = rem / P.Wp - PADH, c = rem % P.Wp - PADL;
-          if (r >= 0 && r < P.Hi && c >= 0 && c < P.Wi) {
-            const int ch0 = k * 16 + kc * 8;  // 8 consecutive input channels; a chunk never straddles x1 | x2 (C1 % 16 == 0)
-            const float* src = ch0 < P.C1 ? P.x1 + ((size_t)b * P.C1 + ch0) * HWs : P.x2 + ((size_t)b * P.C2 + (ch0 - P.C1)) * HWs;
-            src += (r / P.up) * P.Ws + (c / P.up);
-            float v[8];
+      // 16 input channels of this chunk come from x1 or from x2 (C1 % 16 == 0): one base pointer + per-sample stride
+      const int ch0 = k * 16;
+      const bool from1 = ch0 < P.C1;
+      const float* xb = from1 ? P.x1 + (size_t)ch0 * HWs : P.x2 + (size_t)(ch0 - P.C1) * HWs;
+      const size_t bstride = (size_t)(from1 ? P.C1 : P.C2) * HWs;
+      const int nitem = 2 * P.SL, upsh = P.up == 2 ? 1 : 0;
+      // ILP items (position x 8-channel k-chunk) per iteration: 8 ILP independent global loads in flight per thread
+      // (the narrow variant keeps one item: it lives on 3 CTAs per SM instead)
+      constexpr int ILP = NOUT == 32 ? 1 : 2;
+      for (int e0 = tid; e0 < nitem; e0 += ILP * CTC_STAGERS) {
+        float v[ILP][8];
+        int bb[ILP], kc[ILP], sp[ILP];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (size_t)j * HWs);
+        for (int u = 0; u < ILP; ++u) {
+          const int e = e0 + u * CTC_STAGERS;
+          bb[u] = -1;
+          if (e < nitem) {
+            kc[u] = e >= P.SL ? 1 : 0;
+            sp[u] = e - kc[u] * P.SL;
+            const long long q = p0 - P.halo + sp[u];
+            int off = 0;
+            if (q >= 0 && q < P.total) {
+              const int qi = (int)q, bq = fast_div(qi, P.mul_img, P.shr_img), rem = qi - bq * HpWp;
+              const int rr = fast_div(rem, P.mul_row, P.shr_row), r = rr - PADH, c = rem - rr * P.Wp - PADL;
+              if (r >= 0 && r < P.Hi && c >= 0 && c < P.Wi) {
+                bb[u] = bq;
+                off = (r >> upsh) * P.Ws + (c >> upsh);
+              }
+            }
+            if (bb[u] >= 0) {
+              const float* src = xb + (size_t)bb[u] * bstride + (size_t)(kc[u] * 8) * HWs + off;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[u][j] = __ldg(src + (size_t)j * HWs);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+          const int e = e0 + u * CTC_STAGERS;
+          if (e >= nitem) break;
+          uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
+          if (bb[u] >= 0) {
             if (P.ss) {
-              const float4* ssp = reinterpret_cast<const float4*>(P.ss + ((size_t)b * Cin + ch0) * 2);
+              const float4* ssp = reinterpret_cast<const float4*>(P.ss + ((size_t)bb[u] * Cin + ch0 + kc[u] * 8) * 2);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 a = __ldg(ssp + j);
-                v[2 * j] = fmaf(v[2 * j], a.x, a.y);
-                v[2 * j + 1] = fmaf(v[2 * j + 1], a.z, a.w);
+                v[u][2 * j] = fmaf(v[u][2 * j], a.x, a.y);
+                v[u][2 * j + 1] = fmaf(v[u][2 * j + 1], a.z, a.w);
               }
               if (P.silu) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = silu_acc(v[j]);
+                for (int j = 0; j < 8; ++j) v[u][j] = silu_acc(v[u][j]);
               }
             }
-            split2_f16(v[0], v[1], hi4.x, lo4.x);
-            split2_f16(v[2], v[3], hi4.y, lo4.y);
-            split2_f16(v[4], v[5], hi4.z, lo4.z);
-            split2_f16(v[6], v[7], hi4.w, lo4.w);
+            split2_f16(v[u][0], v[u][1], hi4.x, lo4.x);
+            split2_f16(v[u][2], v[u][3], hi4.y, lo4.y);
+            split2_f16(v[u][4], v[u][5], hi4.z, lo4.z);
+            split2_f16(v[u][6], v[u][7], hi4.w, lo4.w);
           }
+          *reinterpret_cast<uint4*>(adst + kc[u] * PS + sp[u] * 16) = hi4;
+          *reinterpret_cast<uint4*>(adst + (2 + kc[u]) * PS + sp[u] * 16) = lo4;
         }
-        *reinterpret_cast<uint4*>(adst + kc * PS + s * 16) = hi4;
-        *reinterpret_cast<uint4*>(adst + (2 + kc) * PS + s * 16) = lo4;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_full + buf);
@@ -208,9 +242,9 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
       bool valid = ok && p < P.total;
       int b = 0, oy = 0, ox = 0, ccol = 0;
       if (valid) {
-        b = (int)(p / HpWp);
-        const int rem = (int)(p - (long long)b * HpWp);
-        const int r = rem / P.Wp - PADH, c = rem % P.Wp - PADL;
+        b = fast_div((int)p, P.mul_img, P.shr_img);
+        const int rem = (int)p - b * HpWp;
+        const int rr = fast_div(rem, P.mul_row, P.shr_row), r = rr - PADH, c = rem - rr * P.Wp - PADL;
         valid = r >= 0 && r < P.Hi && c >= 0 && c < P.Wi;
         ccol = c;
         if (P.stride == 2) {
@@ -374,6 +408,16 @@ int gn_scale_shift(msgm_ctx* ctx, const float* x1, int C1, const float* x2, int 
   return MSGM_OK;
 }
 
+// CUTLASS-style magic division: n / d == umulhi(n, mul) >> shr for 0 <= n < 2^31
+static void find_divisor(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  if (d <= 1) { *mul = 0; *shr = 0; return; }
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  const uint32_t p = 31 + l;
+  *mul = (uint32_t)(((1ull << p) + d - 1) / d);
+  *shr = p - 32;
+}
+
 template <int NOUT, int NT>
 static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
   constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;
@@ -381,6 +425,12 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
   P.Wp = P.Wi + TapGeom<NT>::PADL + TapGeom<NT>::PADR;
   P.halo = TapGeom<NT>::PADH * P.Wp + TapGeom<NT>::PADR;
   P.total = (long long)P.B * P.Hp * P.Wp;
+  find_divisor((uint32_t)(P.Hp * P.Wp), &P.mul_img, &P.shr_img);
+  find_divisor((uint32_t)P.Wp, &P.mul_row, &P.shr_row);
+  if (P.total >= (1LL << 31) - 4096) {
+    set_error("msgm_conv_tc: more than 2^31 padded positions in one call; split the batch");
+    return MSGM_ERR_UNSUPPORTED;
+  }
   // M blocks per CTA: as many as TMEM (512 columns) and shared memory allow while still giving every SM a tile
   const long long nblk = (P.total + 127) / 128;
   int MB = 4;

@@ -210,6 +210,50 @@ def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev, gr
     return world * batch * iters / (ms / 1e3), ms / iters, n_launch, float(loss.detach())
 
 
+def time_unet_forward(P, dev):
+    """Score-net forward throughput of BASELINE configs 3 and 4 (one net evaluation = one Runge-Kutta stage of the generic
+    sampler): this repo's kernel path (tcgen05 convs / attention, split fp16 x3 = fp32-level parity) next to torch's fp32
+    library path on the same module and weights."""
+    out = {"metric": "score_net_forward_samples_per_sec", "unit": "samples/s", "precision": "fp16x3 split (fp32-level parity)",
+           "runs": []}
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    torch.manual_seed(0)
+    nets = [("unet1d_L1000_base32", P.UNet1D(1000, premodule="NormalizeLogRadius").to(dev), 256, 1000, 0.445),
+            ("vorticity_unet2d_32x32_base32", P.VorticityUNet(32, (1, 2, 4), 2, premodule="NormalizeLogRadius", in_space=32,
+                                                              attention_resolutions=(2, 4), flatten_order="F").to(dev), 128,
+             1024, 1.204)]
+    with torch.no_grad():
+        for name, net, B, d, gflop in nets:
+            for p_ in net.parameters():  # the reference zero-initialises some convs: give them weights so that work is real
+                if p_.dim() > 1 and float(p_.abs().sum()) == 0.0:
+                    p_.normal_(0, 0.02)
+            x, t = torch.randn(B, d, device=dev), torch.rand(B, device=dev)
+            ms = timeit(lambda: net(x, t), 10)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                ms_t = timeit(lambda: net._forward(x, t), 5)
+                ref = net._forward(x, t)
+                torch.backends.cuda.matmul.allow_tf32 = prev
+            err = float((net(x, t) - ref).abs().max() / ref.abs().max())
+            out["runs"].append({"net": name, "batch": B, "ms_per_forward": ms, "value": B / ms * 1e3,
+                                "algorithmic_tflops": gflop * B / ms, "torch_fp32_ms": ms_t,
+                                "rel_diff_vs_torch_fp32": err})
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -253,6 +297,7 @@ def main():
     ap.add_argument("--precision", default="f16tc", choices=["fp32", "f16tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the SSM training leg (profiling runs)")
+    ap.add_argument("--no-unet", action="store_true", help="skip the U-Net score-net forward leg (configs 3 and 4)")
     ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU (default 2^20)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -366,6 +411,11 @@ def main():
                          "flop_per_launch": fl, "kernel_ms": kms},
         }
         line["train"] = train
+        if world == 1 and not args.no_unet:
+            try:
+                line["unet"] = time_unet_forward(P, dev)
+            except Exception as exc:  # a secondary leg must never cost the headline line
+                line["unet"] = {"error": f"{type(exc).__name__}: {exc}"}
         if world > 1:  # the CPU baselines are timed at N = 1 only (torchrun also pins every rank to one host thread)
             line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": None, "kind": "port",
                                     "sample": "timed at N=1 only"}

@@ -224,6 +224,7 @@ typedef struct {
   const float* x1; const float* x2; const void* wimg; const float* bias; const float* ebias; const float* res;
   const float* ss; float* out;
   int32_t B, C1, C2, Cout, K, stride, up, Hs, Ws, prologue;
+  int32_t fast; /* 0: three split products (fp32-level parity); 1: one fp16 product, ~1e-3 relative (sampling only) */
 } msgm_conv2d_tc_desc;
 int msgm_conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* desc, void* stream);
 int64_t msgm_conv2d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K);
@@ -236,6 +237,7 @@ int msgm_conv2d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin
 typedef struct {
   const float* x1; const float* x2; const void* wimg; const float* bias; const float* E; float* out;
   int32_t B, C1, C2, Cout, K, stride, Lin, gelu;
+  int32_t fast; /* as in msgm_conv2d_tc_desc */
 } msgm_conv1d_tc_desc;
 int msgm_conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* desc, void* stream);
 int64_t msgm_conv1d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K);
@@ -246,7 +248,7 @@ int msgm_conv1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw,
  * `out` (B, Cout, Lout >= 2 Lin) must be zero-filled by the caller when Lout > 2 Lin (the reference's right padding). */
 int msgm_convt1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, void* wimg, void* stream);
 int msgm_convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bias, float* out, int32_t B, int32_t Cin,
-                    int32_t Cout, int32_t Lin, int32_t Lout, void* stream);
+                    int32_t Cout, int32_t Lin, int32_t Lout, int32_t fast, void* stream);
 /* ss[b, c] = (rstd gamma_c, beta_c - mean rstd gamma_c) with the GroupNorm32 statistics of [x1, x2] (eps 1e-5). */
 int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,
                         int32_t B, const float* gamma, const float* beta, float* ss, void* stream);

@@ -50,12 +50,12 @@ class Conv2dDesc(C.Structure):
 
 class Conv2dTcDesc(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x1", "x2", "wimg", "bias", "ebias", "res", "ss", "out")] + \
-               [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "stride", "up", "Hs", "Ws", "prologue")]
+               [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "stride", "up", "Hs", "Ws", "prologue", "fast")]
 
 
 class Conv1dTcDesc(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x1", "x2", "wimg", "bias", "E", "out")] + \
-               [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "stride", "Lin", "gelu")]
+               [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "stride", "Lin", "gelu", "fast")]
 
 
 _lib = None
@@ -120,7 +120,7 @@ def lib() -> C.CDLL:
                 L.msgm_conv1d_tc_pack_bytes.argtypes = [C.c_int32] * 3
                 L.msgm_conv1d_tc_pack.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2
                 L.msgm_convt1d_tc_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
-                L.msgm_convt1d_tc.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]
+                L.msgm_convt1d_tc.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 6 + [C.c_void_p]
                 L.msgm_gn_scale_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + \
                     [C.c_void_p] * 4
                 L.msgm_gn_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2

@@ -53,7 +53,7 @@ size_t conv2d_tc_pack_bytes(int, int, int);
 int conv2d_tc_pack(msgm_ctx*, const float*, int, int, int, int, void*, cudaStream_t);
 int conv1d_tc(msgm_ctx*, const msgm_conv1d_tc_desc*, cudaStream_t);
 int convt1d_tc_pack(msgm_ctx*, const float*, int, int, void*, cudaStream_t);
-int convt1d_tc(msgm_ctx*, const float*, const void*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int convt1d_tc(msgm_ctx*, const float*, const void*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int gn_scale_shift(msgm_ctx*, const float*, int, const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int emb_proj(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int sincos_embed_mlp(msgm_ctx*, const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
@@ -409,12 +409,12 @@ int msgm_convt1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Ci
 }
 
 int msgm_convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bias, float* out, int32_t B, int32_t Cin,
-                    int32_t Cout, int32_t Lin, int32_t Lout, void* stream) {
+                    int32_t Cout, int32_t Lin, int32_t Lout, int32_t fast, void* stream) {
   if (!ctx || !x || !wimg || !out || B < 0 || Lin < 1 || Lout < 2 * Lin) return invalid("msgm_convt1d_tc: bad argument");
   if (Cout < 16 || Cout % 16 || Cin < 16 || Cin % 16) return invalid("msgm_convt1d_tc: Cin % 16 == 0 and Cout % 16 == 0");
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
-  return convt1d_tc(ctx, x, wimg, bias, out, B, Cin, Cout, Lin, Lout, (cudaStream_t)stream);
+  return convt1d_tc(ctx, x, wimg, bias, out, B, Cin, Cout, Lin, Lout, fast, (cudaStream_t)stream);
 }
 
 int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,

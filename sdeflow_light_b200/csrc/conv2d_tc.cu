@@ -31,7 +31,7 @@ namespace msgm {
 struct ConvTcParams {
   const float* x1; int C1;
   const float* x2; int C2;
-  const unsigned char* wimg;  // packed by conv2d_tc_pack_kernel: [ntile][chunk][tap][hi|lo][kc][NOUT][8] fp16
+  const unsigned char* wimg;  // packed by conv2d_tc_pack_kernel: [ntile][chunk][hi|lo][tap][kc][NOUT][8] fp16
   const float* bias;          // (Cout) or NULL
   const float* ebias;         // (B, Cout) or NULL
   const float* res;           // (B, Cout, Ho, Wo) or NULL
@@ -48,6 +48,7 @@ struct ConvTcParams {
   long long total;            // B Hp Wp
   uint32_t mul_img, shr_img, mul_row, shr_row;  // magic numbers: n / (Hp Wp) and n / Wp for n < 2^31
   int tmem_cols;
+  int fast;                   // 1: single fp16 product (hi planes only; ~1e-3 relative), 0: three split products (fp32-level)
   int* flags;
 };
 
@@ -74,7 +75,8 @@ struct TapGeom {
 template <int NOUT, int NT, bool CONST_BASE>
 __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_tc_kernel(const __grid_constant__ ConvTcParams P) {
   constexpr int PADH = TapGeom<NT>::PADH, PADL = TapGeom<NT>::PADL;
-  constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;  // bytes of packed weights per 16-channel chunk
+  constexpr int WCHUNK = NT * 2 * 2 * NOUT * 16;  // bytes of packed weights per 16-channel chunk: [hi|lo][tap][kc][NOUT][8]
+  const int WSTAGE = P.fast ? WCHUNK / 2 : WCHUNK;  // the single-product mode copies the hi half only
   extern __shared__ __align__(128) unsigned char smem_dyn[];
   // carve: [barriers 128 B][A stage 0][A stage 1][W stage 0][W stage 1], 128-byte aligned
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
   uint64_t* bar_done = bar_full + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 5);
   const int PS = P.SL * 16;                                // plane stride (bytes)
-  const int ASTAGE = 4 * PS;
+  const int ASTAGE = (P.fast ? 2 : 4) * PS;        // planes [hi|lo][k-chunk]; no lo planes in the single-product mode
   unsigned char* sA = smem + 128;
   unsigned char* sW = sA + 2 * ASTAGE;
 
@@ -134,13 +136,15 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
             const int toff = NT == 9 ? (t / 3 - 1) * P.Wp + (t % 3 - 1) : (NT == 1 ? 0 : t - 1);
             const uint32_t a_hi = a_base + (uint32_t)((mb * 128 + P.halo + toff) * 16);
             const uint32_t a_lo = a_hi + 2u * (uint32_t)PS;
-            const uint32_t w_hi = w_base + (uint32_t)(t * 4 * NOUT * 16);
-            const uint32_t w_lo = w_hi + 2u * NOUT * 16;
+            const uint32_t w_hi = w_base + (uint32_t)(t * 2 * NOUT * 16);
+            const uint32_t w_lo = w_hi + (uint32_t)(NT * 2 * NOUT * 16);
             const uint64_t dAh = umma_desc(a_hi, PS, 128), dAl = umma_desc(a_lo, PS, 128);
             const uint64_t dWh = umma_desc(w_hi, NOUT * 16, 128), dWl = umma_desc(w_lo, NOUT * 16, 128);
             umma_ss(dcol, dAh, dWh, idesc, (k > 0 || t > 0) ? 1u : 0u, 0);
-            umma_ss(dcol, dAl, dWh, idesc, 1u, 0);
-            umma_ss(dcol, dAh, dWl, idesc, 1u, 0);
+            if (!P.fast) {
+              umma_ss(dcol, dAl, dWh, idesc, 1u, 0);
+              umma_ss(dcol, dAh, dWl, idesc, 1u, 0);
+            }
           }
         }
         umma_commit(bar_empty + buf, 0);
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
       unsigned char* wdst = sW + buf * WSTAGE;
       if (tid == 0) {
         mbar_expect_tx(bar_full + buf, (uint32_t)WSTAGE);
-        tma_bulk_g2s(wdst, P.wimg + ((size_t)blockIdx.y * P.NC + k) * WSTAGE, (uint32_t)WSTAGE, bar_full + buf);
+        tma_bulk_g2s(wdst, P.wimg + ((size_t)blockIdx.y * P.NC + k) * WCHUNK, (uint32_t)WSTAGE, bar_full + buf);
       }
       unsigned char* adst = sA + buf * ASTAGE;
       // 16 input channels of this chunk come from x1 or from x2 (C1 % 16 == 0): one base pointer + per-sample stride
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
             split2_f16(v[u][6], v[u][7], hi4.w, lo4.w);
           }
           *reinterpret_cast<uint4*>(adst + kc[u] * PS + sp[u] * 16) = hi4;
-          *reinterpret_cast<uint4*>(adst + (2 + kc[u]) * PS + sp[u] * 16) = lo4;
+          if (!P.fast) *reinterpret_cast<uint4*>(adst + (2 + kc[u]) * PS + sp[u] * 16) = lo4;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(P.tmem_cols));
 }
 
-// ---- weight packing: (Cout, Cin, K, K) fp32 -> [ntile][chunk][tap][hi|lo][kc][NOUT][8] fp16 ---------------------------
+// ---- weight packing: (Cout, Cin, K, K) fp32 -> [ntile][chunk][hi|lo][tap][kc][NOUT][8] fp16 ---------------------------
 __global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int Cw, int Cin, int KK, int NOUT,
                                       __half* __restrict__ img, long long nel) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,8 +314,8 @@ __global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int
   long long r = e / 8;
   const int n = (int)(r % NOUT); r /= NOUT;
   const int kc = (int)(r % 2); r /= 2;
-  const int hl = (int)(r % 2); r /= 2;
   const int t = (int)(r % KK); r /= KK;
+  const int hl = (int)(r % 2); r /= 2;
   const int NC = Cin / 16;
   const int k = (int)(r % NC);
   const int nt = (int)(r / NC);
@@ -331,8 +335,8 @@ __global__ void convt1d_tc_pack_kernel(const float* __restrict__ W, int Cout, in
   long long r = e / 8;
   const int n = (int)(r % NOUT); r /= NOUT;
   const int kc = (int)(r % 2); r /= 2;
-  const int hl = (int)(r % 2); r /= 2;
   const int t = (int)(r % 3); r /= 3;
+  const int hl = (int)(r % 2); r /= 2;
   const int NC = Cin / 16;
   const int k = (int)(r % NC);
   const int nt = (int)(r / NC);
@@ -420,7 +424,8 @@ static void find_divisor(uint32_t d, uint32_t* mul, uint32_t* shr) {
 
 template <int NOUT, int NT>
 static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
-  constexpr int WSTAGE = NT * 2 * 2 * NOUT * 16;
+  const int WSTAGE = NT * (P.fast ? 1 : 2) * 2 * NOUT * 16;
+  const int nplane = P.fast ? 2 : 4;
   P.Hp = P.Hi + 2 * TapGeom<NT>::PADH;
   P.Wp = P.Wi + TapGeom<NT>::PADL + TapGeom<NT>::PADR;
   P.halo = TapGeom<NT>::PADH * P.Wp + TapGeom<NT>::PADR;
@@ -439,7 +444,7 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
   for (;; MB >>= 1) {
     P.MB = MB;
     P.SL = 128 * MB + 2 * P.halo;
-    smem = 128 + 128 + 2 * (size_t)(4 * P.SL * 16) + 2 * (size_t)WSTAGE;
+    smem = 128 + 128 + 2 * (size_t)(nplane * P.SL * 16) + 2 * (size_t)WSTAGE;
     if (smem <= 227 * 1024 || MB == 1) break;
   }
   if (smem > 227 * 1024) {
@@ -476,6 +481,7 @@ int conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* D, cudaStream_t stream) 
   P.wimg = reinterpret_cast<const unsigned char*>(D->wimg);
   P.bias = D->bias; P.ebias = D->ebias; P.res = D->res; P.ss = D->ss; P.out = D->out;
   P.silu = D->prologue == 2;
+  P.fast = D->fast ? 1 : 0;
   P.B = D->B; P.Cout = D->Cout; P.stride = D->stride; P.up = D->up; P.Hs = D->Hs; P.Ws = D->Ws;
   const int pad = D->K / 2;
   P.Hi = D->Hs * D->up; P.Wi = D->Ws * D->up;
@@ -493,6 +499,7 @@ int conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* D, cudaStream_t stream) 
   P.x1 = D->x1; P.C1 = D->C1; P.x2 = D->x2; P.C2 = D->x2 ? D->C2 : 0;
   P.wimg = reinterpret_cast<const unsigned char*>(D->wimg);
   P.bias = D->bias; P.etab = D->E; P.out = D->out; P.gelu = D->gelu;
+  P.fast = D->fast ? 1 : 0;
   P.B = D->B; P.Cout = D->Cout; P.stride = D->stride; P.up = 1; P.Hs = 1; P.Ws = D->Lin;
   P.Hi = 1; P.Wi = D->Lin; P.Ho = 1;
   const int pad = D->K == 1 ? 0 : 1;
@@ -515,12 +522,12 @@ int convt1d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cin, void* img,
 
 // out (B, Cout, Lout) must be zero beyond 2 Lin (the reference right-pads with zeros, NNUnet1D.py:165-169)
 int convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bias, float* out, int B, int Cin, int Cout,
-               int Lin, int Lout, cudaStream_t stream) {
+               int Lin, int Lout, int fast, cudaStream_t stream) {
   if (B == 0) return MSGM_OK;
   ConvTcParams P{};
   P.x1 = x; P.C1 = Cin;
   P.wimg = reinterpret_cast<const unsigned char*>(wimg);
-  P.bias = bias; P.out = out; P.convt = Cout;
+  P.bias = bias; P.out = out; P.convt = Cout; P.fast = fast ? 1 : 0;
   P.B = B; P.Cout = 2 * Cout; P.stride = 1; P.up = 1; P.Hs = 1; P.Ws = Lin;
   P.Hi = 1; P.Wi = Lin; P.Ho = 1; P.Wo = Lout;
   P.NC = Cin / 16;

@@ -223,7 +223,7 @@ class UNetModel(nn.Module):
         Cout, K = W.shape[0], W.shape[-1]
         bias = None if conv.bias is None else _lib.f32c(conv.bias, dev)
         stride = conv.stride[0]
-        if self.conv_mode == "tc" and _tc_shape_ok(Cout, C1, C2, K, stride, Hs * up, Ws * up):
+        if self.conv_mode in ("tc", "tc16") and _tc_shape_ok(Cout, C1, C2, K, stride, Hs * up, Ws * up):
             return self._k_conv_tc(dev, conv, W, bias, x1, x2, gn, silu, ebias, res, up, stride)
         stats = gamma = beta = None
         G = 0
@@ -242,7 +242,9 @@ class UNetModel(nn.Module):
         _lib.check(L.msgm_conv2d(h, C.byref(d), _lib.stream_ptr(dev)))
         return out
 
-    conv_mode = "tc"  # "tc": tcgen05 split-fp16 implicit GEMM where the shape allows; "fp32": CUDA-core kernels only
+    # "tc": tcgen05 implicit GEMM with split fp16 x3 operands (fp32-level parity) where the shape allows; "tc16": the same
+    # with ONE fp16 product (3x fewer MMAs, ~1e-3 relative: sampling only); "fp32": CUDA-core kernels only
+    conv_mode = "tc"
 
     def _k_conv_tc(self, dev, conv, W, bias, x1, x2, gn, silu, ebias, res, up, stride):
         """Tensor-core conv (csrc/conv2d_tc.cu): packed weights cached per weight version, GroupNorm folded to scale/shift."""
@@ -269,7 +271,7 @@ class UNetModel(nn.Module):
         out = torch.empty((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
         p = lambda t_: None if t_ is None else t_.data_ptr()  # noqa: E731
         d = _lib.Conv2dTcDesc(p(x1), p(x2), p(ent[1]), p(bias), p(ebias), p(res), p(ss), p(out), B, C1, C2, Cout, K, stride,
-                              up, Hs, Ws, 0 if gn is None else (2 if silu else 1))
+                              up, Hs, Ws, 0 if gn is None else (2 if silu else 1), int(self.conv_mode == "tc16"))
         _lib.check(L.msgm_conv2d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
         return out
 
@@ -292,7 +294,7 @@ class UNetModel(nn.Module):
         B, Cc, Hh, Ww = x.shape
         qkv = self._k_conv(dev, _as2d(blk.qkv), x, gn=blk.norm, silu=False)
         att = torch.empty((B, Cc, Hh, Ww), device=dev, dtype=torch.float32)
-        fn = L.msgm_attention_tc if self.conv_mode == "tc" and L.msgm_attention_tc_supported(Cc, Hh * Ww) else L.msgm_attention
+        fn = L.msgm_attention_tc if self.conv_mode in ("tc", "tc16") and L.msgm_attention_tc_supported(Cc, Hh * Ww) else L.msgm_attention
         _lib.check(fn(h, _lib.ptr(qkv), _lib.ptr(att), B, Cc, Hh * Ww, _lib.stream_ptr(dev)))
         return self._k_conv(dev, _as2d(blk.proj_out), att, res=x)
 

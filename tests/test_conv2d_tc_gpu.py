@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _run_tc(x1, x2, W, bias, ebias, res, gn, silu, up, stride):
+def _run_tc(x1, x2, W, bias, ebias, res, gn, silu, up, stride, fast=0):
     dev = torch.device(DEV)
     h, L = _lib.ctx(dev), _lib.lib()
     B, C1, Hs, Ws = x1.shape
@@ -36,7 +36,7 @@ def _run_tc(x1, x2, W, bias, ebias, res, gn, silu, up, stride):
     out = torch.full((B, Cout, Ho, Wo), float("nan"), device=dev, dtype=torch.float32)
     p = lambda t_: None if t_ is None else t_.data_ptr()  # noqa: E731
     d = _lib.Conv2dTcDesc(p(x1), p(x2), p(img), p(bias), p(ebias), p(res), p(ss), p(out), B, C1, C2, Cout, K, stride, up,
-                          Hs, Ws, 0 if gn is None else (2 if silu else 1))
+                          Hs, Ws, 0 if gn is None else (2 if silu else 1), fast)
     _lib.check(L.msgm_conv2d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     flag = C.c_int32(0)
@@ -78,8 +78,11 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("fast", [0, 1])
 @pytest.mark.parametrize("case", CASES)
-def test_conv2d_tc_matches_float64(case):
+def test_conv2d_tc_matches_float64(case, fast):
+    """fast = 0: three split fp16 products, tolerance 2e-5 (fp32 level).  fast = 1 (`conv_mode="tc16"`): one fp16 product,
+    stated tolerance 3e-3 relative to max|ref| (fp16 operand rounding 2^-11 per factor; observed ~5e-4)."""
     B, C1, C2, Cout, K, H, W_, up, stride, gnm, hb, he, hr = case
     torch.manual_seed(B * 1000 + Cout + K)
     dev = DEV
@@ -95,12 +98,12 @@ def test_conv2d_tc_matches_float64(case):
     pad = K // 2
     Ho, Wo = (H * up + 2 * pad - K) // stride + 1, (W_ * up + 2 * pad - K) // stride + 1
     res = torch.randn(B, Cout, Ho, Wo, device=dev) if hr else None
-    got = _run_tc(x1, x2, Wt, bias, ebias, res, gn, gnm == 2, up, stride)
+    got = _run_tc(x1, x2, Wt, bias, ebias, res, gn, gnm == 2, up, stride, fast)
     ref = _ref(x1, x2, Wt, bias, ebias, res, gn, gnm == 2, up, stride)
     assert got.shape == ref.shape
     assert torch.isfinite(got).all(), "positions left unwritten"
     err = float((got.double() - ref).abs().max()) / float(ref.abs().max())
-    assert err < 2e-5, f"conv2d_tc rel err {err:.3e}"
+    assert err < (3e-3 if fast else 2e-5), f"conv2d_tc rel err {err:.3e}"
 
 
 def test_conv2d_tc_rejects_unsupported_shapes():
@@ -151,8 +154,9 @@ CASES_1D = [
 ]
 
 
+@pytest.mark.parametrize("fast", [0, 1])
 @pytest.mark.parametrize("case", CASES_1D)
-def test_conv1d_tc_matches_float64(case):
+def test_conv1d_tc_matches_float64(case, fast):
     B, C1, C2, Cemb, Cout, K, stride, Lin, gelu = case
     dev = torch.device(DEV)
     h, L = _lib.ctx(dev), _lib.lib()
@@ -174,7 +178,7 @@ def test_conv1d_tc_matches_float64(case):
     _lib.check(L.msgm_conv1d_tc_pack(h, _lib.ptr(W), Cout, Cw, C1 + C2, K, _lib.ptr(img), _lib.stream_ptr(dev)))
     out = torch.full((B, Cout, Lout), float("nan"), device=dev)
     d = _lib.Conv1dTcDesc(x1.data_ptr(), None if x2 is None else x2.data_ptr(), img.data_ptr(), bias.data_ptr(),
-                          None if E is None else E.data_ptr(), out.data_ptr(), B, C1, C2, Cout, K, stride, Lin, gelu)
+                          None if E is None else E.data_ptr(), out.data_ptr(), B, C1, C2, Cout, K, stride, Lin, gelu, fast)
     _lib.check(L.msgm_conv1d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     feats = [x1] + ([x2] if C2 else []) + ([emb[:, :, None].expand(-1, -1, Lin)] if Cemb else [])
@@ -183,12 +187,13 @@ def test_conv1d_tc_matches_float64(case):
         ref = F.gelu(ref)
     assert out.shape == ref.shape and torch.isfinite(out).all()
     err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
-    assert err < 2e-5, f"conv1d_tc rel err {err:.3e}"
+    assert err < (3e-3 if fast else 2e-5), f"conv1d_tc rel err {err:.3e}"
 
 
 @pytest.mark.parametrize("B,Cin,Cout,Lin,Lout", [(3, 128, 128, 125, 250), (2, 128, 64, 250, 500), (4, 64, 32, 62, 125),
                                                  (2, 16, 16, 3, 7)])
-def test_convt1d_tc_matches_float64(B, Cin, Cout, Lin, Lout):
+@pytest.mark.parametrize("fast", [0, 1])
+def test_convt1d_tc_matches_float64(B, Cin, Cout, Lin, Lout, fast):
     """nn.ConvTranspose1d(k4, s2, p1) + right zero padding (NNUnet1D.py:98,165-169) as a 3-tap tensor-core conv."""
     dev = torch.device(DEV)
     h, L = _lib.ctx(dev), _lib.lib()
@@ -201,9 +206,9 @@ def test_convt1d_tc_matches_float64(B, Cin, Cout, Lin, Lout):
     out = torch.zeros((B, Cout, Lout), device=dev)
     out[:, :, :2 * Lin] = float("nan")
     _lib.check(L.msgm_convt1d_tc(h, _lib.ptr(x), _lib.ptr(img), _lib.ptr(bias), _lib.ptr(out), B, Cin, Cout, Lin, Lout,
-                                 _lib.stream_ptr(dev)))
+                                 fast, _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     ref = F.pad(F.conv_transpose1d(x.double(), W.double(), bias.double(), stride=2, padding=1), (0, Lout - 2 * Lin))
     assert torch.isfinite(out).all()
     err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
-    assert err < 2e-5, f"convt1d_tc rel err {err:.3e}"
+    assert err < (3e-3 if fast else 2e-5), f"convt1d_tc rel err {err:.3e}"

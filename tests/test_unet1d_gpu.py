@@ -211,3 +211,26 @@ def test_unet2d_cuda_graph_replay_tracks_weight_updates():
         net.cuda_graph = True
         g2 = net(x, t)
         assert torch.equal(g2, e2) and not torch.equal(g2, g1)
+
+
+@pytest.mark.parametrize("which", ["unet1d", "unet2d"])
+def test_unet_single_product_mode_tolerance(which):
+    """`conv_mode="tc16"` (one fp16 tensor-core product per contraction instead of three split products; sampling only):
+    stated tolerance 1e-2 relative to max|ref| of one forward vs the fp32-level path (observed ~1e-3)."""
+    torch.manual_seed(3)
+    if which == "unet1d":
+        net = P.UNet1D(1000, premodule="NormalizeLogRadius").to(DEV)
+        x, t, core = torch.randn(8, 1000, device=DEV) * 1.3, torch.rand(8, device=DEV), None
+    else:
+        net = _build_unet2d(32, "NormalizeLogRadius", "F", 77).to(DEV)
+        x, t, core = torch.randn(8, 1024, device=DEV) * 2.0, torch.rand(8, device=DEV), net.core
+    holder = net if core is None else core
+    with torch.no_grad():
+        holder.conv_mode = "tc"
+        ref = net(x, t)
+        holder.conv_mode = "tc16"
+        got = net(x, t)
+        holder.conv_mode = "tc"
+    err = _rel(got, ref.cpu())
+    Bd.report(test=f"{which}-tc16", rel=err)
+    assert 0.0 < err < 1e-2

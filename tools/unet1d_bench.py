@@ -36,6 +36,10 @@ with torch.no_grad():
     net.conv_mode = "tc"
     ms_k, n_k = timeit(lambda: net(x, t))
     y_k = net(x, t)
+    net.conv_mode = "tc16"
+    ms_16, _ = timeit(lambda: net(x, t))
+    print(f"tc16 (single fp16 product) kernels: {ms_16:.2f} ms; rel diff vs tc {float((net(x, t) - y_k).abs().max() / y_k.abs().max()):.2e}")
+    net.conv_mode = "tc"
     print(f"tc vs fp32 kernels: rel diff {float((y_k - y_f).abs().max() / y_f.abs().max()):.2e}; fp32 CUDA-core kernels "
           f"{ms_f:.2f} ms ({n_f:.0f} launches)")
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):

@@ -294,7 +294,7 @@ int msgm_conv1d(msgm_ctx* ctx, const msgm_conv1d_desc* D, void* stream) {
 
 int msgm_emb_fold(msgm_ctx* ctx, const float* W, const float* emb, float* E, int32_t Cw, int32_t Coff, int32_t Cemb,
                   int32_t Cout, int32_t K, int32_t B, void* stream) {
-  if (!ctx || !W || !emb || !E || Cemb < 1 || Cout < 1 || K < 1 || B < 0) return invalid("msgm_emb_fold: bad argument");
+  if (!ctx || !W || !emb || !E || Cemb < 1 || Cemb > 1024 || Cout < 1 || K < 1 || B < 0) return invalid("msgm_emb_fold: bad argument");
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return emb_fold(ctx, W, emb, E, Cw, Coff, Cemb, Cout, K, B, (cudaStream_t)stream);

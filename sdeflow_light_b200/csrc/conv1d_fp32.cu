@@ -100,16 +100,83 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const __grid_constant__ Con
   }
 }
 
+// ---- degenerate shapes: ONE real input channel (the U-Net's first conv) / ONE output channel (its final 1x1 conv) -------
+// Both are HBM-bound on the (B, 32, L) tensor they write / read; thread = one position, coalesced along the signal.
+// First conv: k3, stride 1, padding 1, C1 = 1 (+ folded embedding table E, bias, GELU), Cout <= 128.
+__global__ void __launch_bounds__(256) conv1d_cin1_kernel(const __grid_constant__ Conv1dParams P, long long npos) {
+  extern __shared__ float swb1[];  // [Cout][3] weights of the real channel + [Cout] bias
+  for (int e = threadIdx.x; e < P.Cout * 3; e += 256) swb1[e] = P.W[(size_t)(e / 3) * P.Cw * 3 + e % 3];
+  for (int e = threadIdx.x; e < P.Cout; e += 256) swb1[P.Cout * 3 + e] = P.bias ? P.bias[e] : 0.0f;
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= npos) return;
+  const int b = (int)(p / P.Lout), l = (int)(p % P.Lout);
+  const float* x = P.x1 + (size_t)b * P.Lin;
+  const bool hasl = l > 0, hasr = l + 1 < P.Lin;
+  const float xm = hasl ? __ldg(x + l - 1) : 0.0f, x0 = __ldg(x + l), xp = hasr ? __ldg(x + l + 1) : 0.0f;
+  float* o = P.out + (size_t)b * P.Cout * P.Lout + l;
+  for (int co = 0; co < P.Cout; ++co) {
+    float a = swb1[P.Cout * 3 + co];
+    a = fmaf(swb1[co * 3], xm, a);
+    a = fmaf(swb1[co * 3 + 1], x0, a);
+    a = fmaf(swb1[co * 3 + 2], xp, a);
+    if (P.E) {  // constant embedding channels: a tap contributes where it reads inside the signal
+      const float* e = P.E + ((size_t)b * P.Cout + co) * 3;
+      a += __ldg(e + 1);
+      if (hasl) a += __ldg(e);
+      if (hasr) a += __ldg(e + 2);
+    }
+    o[(size_t)co * P.Lout] = P.gelu ? gelu_erf(a) : a;
+  }
+}
+
+// Final conv: k1, stride 1, Cout = 1 over [x1, x2]
+__global__ void __launch_bounds__(256) conv1d_cout1_k1_kernel(const __grid_constant__ Conv1dParams P, long long npos) {
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= npos) return;
+  const int b = (int)(p / P.Lout), l = (int)(p % P.Lout);
+  float a = P.bias ? P.bias[0] : 0.0f;
+  const float* x = P.x1 + (size_t)b * P.C1 * P.Lin + l;
+  for (int c = 0; c < P.C1; ++c) a = fmaf(__ldg(P.W + c), __ldg(x + (size_t)c * P.Lin), a);
+  if (P.C2) {
+    const float* y = P.x2 + (size_t)b * P.C2 * P.Lin + l;
+    for (int c = 0; c < P.C2; ++c) a = fmaf(__ldg(P.W + P.C1 + c), __ldg(y + (size_t)c * P.Lin), a);
+  }
+  if (P.E) a += __ldg(P.E + b);
+  P.out[p] = P.gelu ? gelu_erf(a) : a;
+}
+
 // E[b,co,k] = sum_ci W[co, Coff + ci, k] * emb[b,ci]
-__global__ void __launch_bounds__(128) emb_fold_kernel(const float* __restrict__ W, const float* __restrict__ emb,
+// CTA = 8 samples (their embeddings in shared memory), warp = one output channel at a time: the lanes walk the contiguous
+// (ci, k) run W[co, Coff.., :] once (coalesced) and accumulate the 8 x K partial sums, then one shuffle reduction each.
+constexpr int EF_S = 8;
+__global__ void __launch_bounds__(256) emb_fold_kernel(const float* __restrict__ W, const float* __restrict__ emb,
                                                        float* __restrict__ E, int Cw, int Coff, int Cemb, int Cout, int K,
                                                        int B) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (b, co, k)
-  if (idx >= B * Cout * K) return;
-  const int k = idx % K, co = (idx / K) % Cout, b = idx / (K * Cout);
-  float s = 0.0f;
-  for (int ci = 0; ci < Cemb; ++ci) s = fmaf(W[((size_t)co * Cw + Coff + ci) * K + k], emb[(size_t)b * Cemb + ci], s);
-  E[idx] = s;
+  extern __shared__ float semb[];  // [EF_S][Cemb]
+  const int b0 = blockIdx.x * EF_S, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < EF_S * Cemb; e += 256) semb[e] = b0 + e / Cemb < B ? emb[(size_t)b0 * Cemb + e] : 0.0f;
+  __syncthreads();
+  const int run = Cemb * K;
+  for (int co = blockIdx.y * 8 + warp; co < Cout; co += 8 * gridDim.y) {
+    const float* w = W + ((size_t)co * Cw + Coff) * K;
+    for (int k = 0; k < K; ++k) {
+      float acc[EF_S] = {};
+      for (int ci = lane; ci < Cemb; ci += 32) {
+        const float wv = __ldg(w + ci * K + k);
+#pragma unroll
+        for (int sidx = 0; sidx < EF_S; ++sidx) acc[sidx] = fmaf(wv, semb[sidx * Cemb + ci], acc[sidx]);
+      }
+#pragma unroll
+      for (int sidx = 0; sidx < EF_S; ++sidx) {
+        float v = acc[sidx];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && b0 + sidx < B) E[((size_t)(b0 + sidx) * Cout + co) * K + k] = v;
+      }
+    }
+  }
+  (void)run;
 }
 
 // ConvTranspose1d(k=4, s=2, p=1): out[b,co,l] = bias[co] + sum_ci sum_{k: (l+1-k) even, 0 <= (l+1-k)/2 < Lin} W[ci,co,k] x[b,ci,(l+1-k)/2]
@@ -201,6 +268,19 @@ int conv1d(msgm_ctx* ctx, const msgm_conv1d_desc* D, cudaStream_t stream) {
   P.W = D->W; P.bias = D->bias; P.E = D->E; P.out = D->out;
   P.Cw = D->C1 + P.C2 + D->Cemb;
   P.Cout = D->Cout; P.K = D->K; P.stride = D->stride; P.pad = D->pad; P.Lin = D->Lin; P.Lout = D->Lout; P.gelu = D->gelu;
+  const long long npos = (long long)D->B * D->Lout;
+  if (D->K == 3 && D->stride == 1 && D->pad == 1 && P.C1 == 1 && P.C2 == 0 && D->Cout <= 128) {
+    conv1d_cin1_kernel<<<(unsigned)((npos + 255) / 256), 256, sizeof(float) * 4 * D->Cout, stream>>>(P, npos);
+    ctx->launches += 1;
+    MSGM_CUDA_TRY(cudaGetLastError());
+    return MSGM_OK;
+  }
+  if (D->K == 1 && D->stride == 1 && D->pad == 0 && D->Cout == 1 && D->Cemb == 0) {
+    conv1d_cout1_k1_kernel<<<(unsigned)((npos + 255) / 256), 256, 0, stream>>>(P, npos);
+    ctx->launches += 1;
+    MSGM_CUDA_TRY(cudaGetLastError());
+    return MSGM_OK;
+  }
   dim3 grid((D->Lout + CT_L - 1) / CT_L, (D->Cout + CT_CO - 1) / CT_CO, D->B);
   conv1d_kernel<<<grid, 256, 0, stream>>>(P);
   ctx->launches += 1;
@@ -210,8 +290,9 @@ int conv1d(msgm_ctx* ctx, const msgm_conv1d_desc* D, cudaStream_t stream) {
 
 int emb_fold(msgm_ctx* ctx, const float* W, const float* emb, float* E, int Cw, int Coff, int Cemb, int Cout, int K, int B,
              cudaStream_t stream) {
-  const int n = B * Cout * K;
-  emb_fold_kernel<<<(n + 127) / 128, 128, 0, stream>>>(W, emb, E, Cw, Coff, Cemb, Cout, K, B);
+  const int gy = std::max(1, std::min((Cout + 7) / 8, 4));
+  emb_fold_kernel<<<dim3((B + EF_S - 1) / EF_S, gy), 256, sizeof(float) * EF_S * Cemb, stream>>>(W, emb, E, Cw, Coff, Cemb, Cout,
+                                                                                             K, B);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

@@ -37,6 +37,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.SampleArgs) == 32 + 8 * 8
     assert ctypes.sizeof(_lib.Conv1dDesc) == 6 * 8 + 11 * 4 + 4   # 11 int32 + tail padding to 8
     assert ctypes.sizeof(_lib.Conv2dDesc) == 10 * 8 + 11 * 4 + 4
+    assert ctypes.sizeof(_lib.Conv2dTcDesc) == 8 * 8 + 11 * 4 + 4   # ... prologue, fast
+    assert ctypes.sizeof(_lib.Conv1dTcDesc) == 6 * 8 + 9 * 4 + 4    # ... gelu, fast
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
@@ -106,3 +108,22 @@ def test_coefficient_methods_agree_with_oracle_on_cpu_tensors():
         assert torch.allclose(base.f(s, y), O.coef_f(sde, s, y))
         assert torch.allclose(base.div_Sigma(s, y), O.coef_div_sigma(sde, s, y))
         assert torch.allclose(base.g(s, y, sparse=not dense), O.coef_g(sde, s, y, sparse=not dense))
+
+
+def test_tensor_core_layer_shape_queries_need_no_gpu():
+    """The shape / size queries of the tensor-core layer entry points are pure host functions: which layers of the
+    reference's U-Nets (NNUnet1D.py:81-102, model/unet.py:40-250) the tcgen05 path takes, and the packed-weight sizes."""
+    L = _lib.lib()
+    # 2-D: (Cout, Cin, K) -> bytes = Cout Cin K^2 x (hi + lo) x 2 B
+    assert L.msgm_conv2d_tc_pack_bytes(128, 256, 3) == 128 * 256 * 9 * 4
+    assert L.msgm_conv2d_tc_pack_bytes(192, 64, 1) == 192 * 64 * 4
+    assert L.msgm_conv2d_tc_pack_bytes(1, 32, 3) == -1 and L.msgm_conv2d_tc_pack_bytes(32, 1, 3) == -1  # first / last conv
+    assert L.msgm_conv1d_tc_pack_bytes(64, 64, 4) == 64 * 64 * 4 * 4
+    assert L.msgm_conv1d_tc_pack_bytes(32, 32, 5) == -1
+    # attention: the reference's two shapes (C=64, T=256) and (C=128, T=64) are covered; larger ones fall back
+    assert L.msgm_attention_tc_supported(64, 256) == 1 and L.msgm_attention_tc_supported(128, 64) == 1
+    assert L.msgm_attention_tc_supported(128, 256) == 0 and L.msgm_attention_tc_supported(64, 1024) == 0
+    from sdeflow_light_b200.model.unet import _tc_shape_ok
+    assert _tc_shape_ok(64, 64, 32, 3, 1, 16, 16) and _tc_shape_ok(32, 32, 0, 3, 2, 32, 32)
+    assert not _tc_shape_ok(32, 1, 0, 3, 1, 32, 32) and not _tc_shape_ok(1, 32, 0, 3, 1, 32, 32)
+    assert not _tc_shape_ok(32, 32, 0, 3, 2, 31, 32) and not _tc_shape_ok(64, 40, 24, 1, 1, 8, 8)

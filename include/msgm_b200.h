@@ -258,6 +258,11 @@ int msgm_gn_stats(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, i
 /* out (B,Cout) = Linear(SiLU(emb)) : ResBlock.emb_layers. */
 int msgm_emb_proj(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int32_t E, int32_t Cout,
                   int32_t B, void* stream);
+/* Every ResBlock's emb_layers of one forward in one launch: W (Ctot,E) / bias (Ctot) are the blocks' Linear layers stacked
+ * along the output dimension, seg_start[0..nseg] (host array, nseg <= 64) the row offsets of the blocks; block i's result
+ * is the contiguous (B, len_i) matrix at out + B * seg_start[i] (the `ebias` operand of that block's conv). */
+int msgm_emb_proj_multi(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int32_t E,
+                        int32_t Ctot, int32_t B, int32_t nseg, const int32_t* seg_start, void* stream);
 /* out (B,E) (+)= Linear(E,E)(SiLU(Linear(dim,E)(timestep_embedding(t, dim)))) : time_embed / scale_embed. */
 int msgm_sincos_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float* b1, const float* W2, const float* b2,
                           float* out, int32_t B, int32_t dim, int32_t E, int32_t accumulate, void* stream);

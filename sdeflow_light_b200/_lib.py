@@ -71,7 +71,7 @@ SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy",
            "msgm_conv2d", "msgm_gn_stats", "msgm_emb_proj", "msgm_sincos_embed_mlp", "msgm_attention", "msgm_vort_pre",
            "msgm_vort_post", "msgm_conv2d_tc", "msgm_conv2d_tc_pack_bytes", "msgm_conv2d_tc_pack", "msgm_gn_scale_shift",
            "msgm_attention_tc_supported", "msgm_attention_tc", "msgm_conv1d_tc", "msgm_conv1d_tc_pack_bytes",
-           "msgm_conv1d_tc_pack", "msgm_convt1d_tc_pack", "msgm_convt1d_tc"]
+           "msgm_conv1d_tc_pack", "msgm_convt1d_tc_pack", "msgm_convt1d_tc", "msgm_emb_proj_multi"]
 
 
 def lib() -> C.CDLL:
@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
                 L.msgm_conv1d_tc_pack.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2
                 L.msgm_convt1d_tc_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
                 L.msgm_convt1d_tc.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 6 + [C.c_void_p]
+                L.msgm_emb_proj_multi.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.POINTER(C.c_int32), C.c_void_p]
                 L.msgm_gn_scale_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + \
                     [C.c_void_p] * 4
                 L.msgm_gn_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 2

@@ -60,6 +60,7 @@ int sincos_embed_mlp(msgm_ctx*, const float*, const float*, const float*, const 
                      int, cudaStream_t);
 int attention(msgm_ctx*, const float*, float*, int, int, int, cudaStream_t);
 bool attention_tc_ok(int, int);
+int emb_proj_multi(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, int, const int*, cudaStream_t);
 int attention_tc(msgm_ctx*, const float*, float*, int, int, int, cudaStream_t);
 int vort_pre(msgm_ctx*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
 int vort_post(msgm_ctx*, const float*, float*, int, int, int, int, cudaStream_t);
@@ -442,6 +443,18 @@ int msgm_emb_proj(msgm_ctx* ctx, const float* emb, const float* W, const float* 
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return emb_proj(ctx, emb, W, bias, out, E, Cout, B, (cudaStream_t)stream);
+}
+
+int msgm_emb_proj_multi(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int32_t E,
+                        int32_t Ctot, int32_t B, int32_t nseg, const int32_t* seg_start, void* stream) {
+  if (!ctx || !emb || !W || !bias || !out || !seg_start || E < 1 || E > 8192 || Ctot < 1 || B < 0 || nseg < 1 || nseg > 64)
+    return invalid("msgm_emb_proj_multi: bad argument");
+  if (seg_start[0] != 0 || seg_start[nseg] != Ctot) return invalid("msgm_emb_proj_multi: segments must cover [0, Ctot)");
+  for (int i = 0; i < nseg; ++i)
+    if (seg_start[i + 1] <= seg_start[i]) return invalid("msgm_emb_proj_multi: segment offsets must increase");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return emb_proj_multi(ctx, emb, W, bias, out, E, Ctot, B, nseg, seg_start, (cudaStream_t)stream);
 }
 
 int msgm_sincos_embed_mlp(msgm_ctx* ctx, const float* t, const float* W1, const float* b1, const float* W2, const float* b2,

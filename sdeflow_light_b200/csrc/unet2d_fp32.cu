@@ -256,6 +256,31 @@ __global__ void __launch_bounds__(256) emb_proj_kernel(const float* __restrict__
   }
 }
 
+// All ResBlocks' embedding projections of one forward in ONE launch: W (Ctot, E) / bias (Ctot) are the blocks' Linear
+// layers stacked along the output dimension; segment i = rows [seg[i], seg[i+1]) is written as its own contiguous
+// (B, len_i) matrix at out + B * seg[i], which is what the conv epilogue of that block reads as ebias.
+struct EmbSegs { int n; int start[65]; };
+__global__ void __launch_bounds__(256) emb_proj_multi_kernel(const float* __restrict__ emb, const float* __restrict__ W,
+                                                             const float* __restrict__ bias, float* __restrict__ out, int E,
+                                                             int Ctot, int B, const __grid_constant__ EmbSegs S) {
+  extern __shared__ float se_[];  // silu(emb[b, :])
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < E; i += 256) se_[i] = siluf(emb[(size_t)b * E + i]);
+  __syncthreads();
+  for (int co = blockIdx.y * 8 + warp; co < Ctot; co += 8 * gridDim.y) {
+    float s = 0.0f;
+    for (int i = lane; i < E; i += 32) s = fmaf(__ldg(W + (size_t)co * E + i), se_[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      int sg = 0;
+      while (sg + 1 < S.n && co >= S.start[sg + 1]) ++sg;
+      const int s0 = S.start[sg], len = S.start[sg + 1] - s0;
+      out[(size_t)B * s0 + (size_t)b * len + (co - s0)] = s + bias[co];
+    }
+  }
+}
+
 // out (B,E) (+)= W2 silu(W1 sincos(t) + b1) + b2 ; sincos(t) = [cos(t w_k), sin(t w_k)], w_k = 1e4^(-k/half), dim = 2 half
 // (timestep_embedding model/nn_utils.py:130-148 + time_embed / scale_embed model/unet.py:338-342, NNUnet.py:88-106)
 __global__ void __launch_bounds__(256) sincos_embed_mlp_kernel(const float* __restrict__ t, const float* __restrict__ W1,
@@ -475,6 +500,17 @@ int conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* D, cudaStream_t stream) {
 int emb_proj(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int E, int Cout, int B,
              cudaStream_t stream) {
   emb_proj_kernel<<<B, 256, sizeof(float) * E, stream>>>(emb, W, bias, out, E, Cout, B);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int emb_proj_multi(msgm_ctx* ctx, const float* emb, const float* W, const float* bias, float* out, int E, int Ctot, int B,
+                   int nseg, const int* seg_start, cudaStream_t stream) {
+  EmbSegs S{};
+  S.n = nseg;
+  for (int i = 0; i <= nseg; ++i) S.start[i] = seg_start[i];
+  emb_proj_multi_kernel<<<dim3(B, 4), 256, sizeof(float) * E, stream>>>(emb, W, bias, out, E, Ctot, B, S);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

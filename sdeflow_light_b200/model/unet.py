@@ -275,13 +275,41 @@ class UNetModel(nn.Module):
         _lib.check(L.msgm_conv2d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
         return out
 
+    def _k_all_emb_proj(self, dev, emb):
+        """Linear(SiLU(emb)) of every ResBlock in one launch (stacked weights cached per weight version)."""
+        h, L = _lib.ctx(dev), _lib.lib()
+        blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+        if not blocks or len(blocks) > 64 or emb.shape[1] > 8192:
+            return None
+        lins = [b_.emb_layers[1] for b_ in blocks]
+        ver = tuple((l.weight._version, l.bias._version, l.weight.data_ptr()) for l in lins) + (dev.index,)
+        ent = self.__dict__.get("_emb_stack")
+        if ent is None or ent[0] != ver:
+            Wc = torch.cat([_lib.f32c(l.weight, dev) for l in lins], 0).contiguous()
+            bc = torch.cat([_lib.f32c(l.bias, dev) for l in lins], 0).contiguous()
+            starts = [0]
+            for l in lins:
+                starts.append(starts[-1] + l.weight.shape[0])
+            ent = self.__dict__["_emb_stack"] = (ver, Wc, bc, starts, (C.c_int32 * len(starts))(*starts))
+        _, Wc, bc, starts, cstarts = ent
+        B, E = emb.shape
+        out = torch.empty(B * starts[-1], device=dev, dtype=torch.float32)
+        _lib.check(L.msgm_emb_proj_multi(h, _lib.ptr(emb), _lib.ptr(Wc), _lib.ptr(bc), _lib.ptr(out), E, starts[-1], B,
+                                         len(lins), cstarts, _lib.stream_ptr(dev)))
+        return {id(b_): out[B * starts[i]:B * starts[i + 1]].view(B, -1) for i, b_ in enumerate(blocks)}
+
     def _k_resblock(self, dev, blk, x1, x2, emb):
         h, L = _lib.ctx(dev), _lib.lib()
         B, E = emb.shape
         lin = blk.emb_layers[1]
-        eb = torch.empty((B, blk.out_channels), device=dev, dtype=torch.float32)
-        _lib.check(L.msgm_emb_proj(h, _lib.ptr(emb), _lib.ptr(_lib.f32c(lin.weight, dev)), _lib.ptr(_lib.f32c(lin.bias, dev)),
-                                   _lib.ptr(eb), E, blk.out_channels, B, _lib.stream_ptr(dev)))
+        pre = self.__dict__.get("_emb_cur")
+        if pre is not None and id(blk) in pre:
+            eb = pre[id(blk)]
+        else:
+            eb = torch.empty((B, blk.out_channels), device=dev, dtype=torch.float32)
+            _lib.check(L.msgm_emb_proj(h, _lib.ptr(emb), _lib.ptr(_lib.f32c(lin.weight, dev)),
+                                       _lib.ptr(_lib.f32c(lin.bias, dev)), _lib.ptr(eb), E, blk.out_channels, B,
+                                       _lib.stream_ptr(dev)))
         h1 = self._k_conv(dev, blk.in_layers[2], x1, x2, gn=blk.in_layers[0], ebias=eb)
         if isinstance(blk.skip_connection, nn.Identity):
             skip = x1  # channels unchanged: the block input is a single tensor
@@ -324,13 +352,16 @@ class UNetModel(nn.Module):
         if self.num_heads != 1 or not self.conv_resample:
             raise NotImplementedError("kernel path is built for the driver's configuration (1 head, learned resampling)")
         skips, cur = [], _lib.f32c(x, dev)
+        self.__dict__["_emb_cur"] = self._k_all_emb_proj(dev, emb)
         for blk in self.input_blocks:
             cur = self._k_sequential(dev, blk, cur, None, emb)
             skips.append(cur)
         cur = self._k_sequential(dev, self.middle_block, cur, None, emb)
         for blk in self.output_blocks:
             cur = self._k_sequential(dev, blk, cur, skips.pop(), emb)
-        return self._k_conv(dev, self.out[2], cur, gn=self.out[0])
+        out = self._k_conv(dev, self.out[2], cur, gn=self.out[0])
+        self.__dict__["_emb_cur"] = None
+        return out
 
 
 def _tc_shape_ok(Cout, C1, C2, K, stride, Hi, Wi):

@@ -268,7 +268,7 @@ def run_reference(args, rank):
     ms = 1e3 * sum(times) / len(times)
     value = B * n / (ms / 1e3)
     sample = f"{B} particles x {n} RK4 steps per bench step (same net/SDE as the GPU arm)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "reverse_sde_particle_steps_per_sec", "value": value,
         "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -276,7 +276,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
                          "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 def workload_config(args, where):
@@ -285,6 +285,28 @@ def workload_config(args, where):
             "lmbd": 0.0, "norm_correction": True, "precision": args.precision if where == "gpu" else "fp32",
             "l2_policy": "working set is on-chip (weights in smem, state in registers); x_0/x_N (2 x 4*B*d bytes) "
                          "streamed once per call; a 256 MB buffer is rewritten between timed calls to flush L2"}
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else written to fd 1 during the run (NCCL's version banner, library
+    warnings) is routed to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -300,6 +322,7 @@ def main():
     ap.add_argument("--no-unet", action="store_true", help="skip the U-Net score-net forward leg (configs 3 and 4)")
     ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU (default 2^20)")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -429,7 +452,7 @@ def main():
                                     "kind": "port",
                                     "sample": "50000 particles x 4 RK4 steps, best of 3, same net/SDE (oracle port of "
                                               "the reference's op sequence, torch CPU fp32)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

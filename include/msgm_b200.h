@@ -99,8 +99,9 @@ int msgm_create(msgm_ctx** out, int device);
 int msgm_destroy(msgm_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t msgm_launch_count(const msgm_ctx* ctx);
-/* Debug: synchronises the device and returns the kernel-side flag word (bit 0: a bounded mbarrier wait inside
- * the tensor-core sampler timed out).  Used by the tests; 0 in a healthy run. */
+/* Debug: synchronises the device and returns the kernel-side flag word (1: a bounded mbarrier wait inside a
+ * tensor-core kernel -- sampler, conv, attention -- timed out; 2: shared-memory / TMEM base assumption violated).
+ * Read-and-clear.  Used by the tests; 0 in a healthy run. */
 int msgm_debug_flags(msgm_ctx* ctx, int32_t* out_host);
 /* Debug: cycle counters of the tensor-core sampler (CTA 0), filled only while the environment variable
  * MSGM_TC_PROF is set; n <= 24.  [0..7] owner thread, [8..15] MMA thread, [16..23] helper thread. */

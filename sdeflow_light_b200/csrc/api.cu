@@ -130,6 +130,9 @@ int msgm_debug_flags(msgm_ctx* ctx, int32_t* out_host) {
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   MSGM_CUDA_TRY(cudaDeviceSynchronize());
   MSGM_CUDA_TRY(cudaMemcpy(out_host, ctx->ws, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  // read-and-clear: the conv / attention kernels do not reset the word per launch (the sampler does), so a timeout seen
+  // once must not make every later bounded wait bail out early
+  if (*out_host != 0) MSGM_CUDA_TRY(cudaMemset(ctx->ws, 0, sizeof(int32_t)));
   return MSGM_OK;
 }
 

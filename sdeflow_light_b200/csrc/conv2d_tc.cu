@@ -155,6 +155,31 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
   } else {
     // ================================================== stagers ===================================================
     bool ok = true;
+    // The items a thread stages (position x 8-channel k-chunk) are the same for every 16-channel chunk: decode them once
+    // per tile.  it_b = sample index (-1: padding ring / outside, -2: no such item), it_o = element offset of the item's
+    // first channel inside the chunk's 16 stored channel planes, it_s = k-chunk << 30 | staged position.
+    constexpr int NI_MAX = 6;  // 6 x 256 items = 768 staged positions (the host guarantees SL <= 768)
+    const int nitem = 2 * P.SL, upsh = P.up == 2 ? 1 : 0;
+    int it_b[NI_MAX], it_o[NI_MAX], it_s[NI_MAX];
+#pragma unroll
+    for (int i = 0; i < NI_MAX; ++i) {
+      const int e = tid + i * CTC_STAGERS;
+      it_b[i] = -2; it_o[i] = 0; it_s[i] = 0;
+      if (e < nitem) {
+        const int kc = e >= P.SL ? 1 : 0, sp = e - kc * P.SL;
+        it_s[i] = (kc << 30) | sp;
+        it_b[i] = -1;
+        const long long q = p0 - P.halo + sp;
+        if (q >= 0 && q < P.total) {
+          const int qi = (int)q, bq = fast_div(qi, P.mul_img, P.shr_img), rem = qi - bq * HpWp;
+          const int rr = fast_div(rem, P.mul_row, P.shr_row), r = rr - PADH, c = rem - rr * P.Wp - PADL;
+          if (r >= 0 && r < P.Hi && c >= 0 && c < P.Wi) {
+            it_b[i] = bq;
+            it_o[i] = kc * 8 * HWs + (r >> upsh) * P.Ws + (c >> upsh);
+          }
+        }
+      }
+    }
     for (int k = 0; k < P.NC && ok; ++k) {
       const int buf = k & 1;
       if (k >= 2) {
@@ -172,45 +197,29 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
       const bool from1 = ch0 < P.C1;
       const float* xb = from1 ? P.x1 + (size_t)ch0 * HWs : P.x2 + (size_t)(ch0 - P.C1) * HWs;
       const size_t bstride = (size_t)(from1 ? P.C1 : P.C2) * HWs;
-      const int nitem = 2 * P.SL, upsh = P.up == 2 ? 1 : 0;
-      // ILP items (position x 8-channel k-chunk) per iteration: 8 ILP independent global loads in flight per thread
-      // (the narrow variant keeps one item: it lives on 3 CTAs per SM instead)
+      // ILP items (position x 8-channel k-chunk) per step: 8 ILP independent global loads in flight per thread (the narrow
+      // variant keeps one item: it lives on 3 CTAs per SM instead)
       constexpr int ILP = NOUT == 32 ? 1 : 2;
-      for (int e0 = tid; e0 < nitem; e0 += ILP * CTC_STAGERS) {
+#pragma unroll
+      for (int i0 = 0; i0 < NI_MAX; i0 += ILP) {
+        if (tid + i0 * CTC_STAGERS >= nitem) break;
         float v[ILP][8];
-        int bb[ILP], kc[ILP], sp[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
-          const int e = e0 + u * CTC_STAGERS;
-          bb[u] = -1;
-          if (e < nitem) {
-            kc[u] = e >= P.SL ? 1 : 0;
-            sp[u] = e - kc[u] * P.SL;
-            const long long q = p0 - P.halo + sp[u];
-            int off = 0;
-            if (q >= 0 && q < P.total) {
-              const int qi = (int)q, bq = fast_div(qi, P.mul_img, P.shr_img), rem = qi - bq * HpWp;
-              const int rr = fast_div(rem, P.mul_row, P.shr_row), r = rr - PADH, c = rem - rr * P.Wp - PADL;
-              if (r >= 0 && r < P.Hi && c >= 0 && c < P.Wi) {
-                bb[u] = bq;
-                off = (r >> upsh) * P.Ws + (c >> upsh);
-              }
-            }
-            if (bb[u] >= 0) {
-              const float* src = xb + (size_t)bb[u] * bstride + (size_t)(kc[u] * 8) * HWs + off;
+          if (i0 + u < NI_MAX && it_b[i0 + u] >= 0) {
+            const float* src = xb + (size_t)it_b[i0 + u] * bstride + it_o[i0 + u];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[u][j] = __ldg(src + (size_t)j * HWs);
-            }
+            for (int j = 0; j < 8; ++j) v[u][j] = __ldg(src + (size_t)j * HWs);
           }
         }
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
-          const int e = e0 + u * CTC_STAGERS;
-          if (e >= nitem) break;
+          if (i0 + u >= NI_MAX || it_b[i0 + u] == -2) break;
+          const int bcur = it_b[i0 + u], kcc = it_s[i0 + u] >> 30, spp = it_s[i0 + u] & 0x3fffffff;
           uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
-          if (bb[u] >= 0) {
+          if (bcur >= 0) {
             if (P.ss) {
-              const float4* ssp = reinterpret_cast<const float4*>(P.ss + ((size_t)bb[u] * Cin + ch0 + kc[u] * 8) * 2);
+              const float4* ssp = reinterpret_cast<const float4*>(P.ss + ((size_t)bcur * Cin + ch0 + kcc * 8) * 2);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 a = __ldg(ssp + j);
@@ -227,8 +236,8 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
             split2_f16(v[u][4], v[u][5], hi4.z, lo4.z);
             split2_f16(v[u][6], v[u][7], hi4.w, lo4.w);
           }
-          *reinterpret_cast<uint4*>(adst + kc[u] * PS + sp[u] * 16) = hi4;
-          if (!P.fast) *reinterpret_cast<uint4*>(adst + (2 + kc[u]) * PS + sp[u] * 16) = lo4;
+          *reinterpret_cast<uint4*>(adst + kcc * PS + spp * 16) = hi4;
+          if (!P.fast) *reinterpret_cast<uint4*>(adst + (2 + kcc) * PS + spp * 16) = lo4;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -445,10 +454,10 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
     P.MB = MB;
     P.SL = 128 * MB + 2 * P.halo;
     smem = 128 + 128 + 2 * (size_t)(nplane * P.SL * 16) + 2 * (size_t)WSTAGE;
-    if (smem <= 227 * 1024 || MB == 1) break;
+    if ((smem <= 227 * 1024 && P.SL <= 768) || MB == 1) break;
   }
-  if (smem > 227 * 1024) {
-    set_error("msgm_conv_tc: tile does not fit shared memory (image too wide)");
+  if (smem > 227 * 1024 || P.SL > 768) {
+    set_error("msgm_conv_tc: tile does not fit shared memory / the stager's item table (image too wide)");
     return MSGM_ERR_UNSUPPORTED;
   }
   int cols = 32;

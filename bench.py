@@ -280,8 +280,8 @@ def run_reference(args, rank):
 
 
 def workload_config(args, where):
-    return {"workload": f"gaussmix_d{args.dim}_msgm_dense_mlp128_rk4_n{N_SDE_STEPS}_{args.particles}particles_per_gpu",
-            "dim": args.dim, "particles_per_gpu": args.particles, "sde_steps": N_SDE_STEPS, "scheme": "rk4",
+    return {"workload": f"gaussmix_d{args.dim}_msgm_dense_mlp128_rk4_n{args.sde_steps}_{args.particles}particles_per_gpu",
+            "dim": args.dim, "particles_per_gpu": args.particles, "sde_steps": args.sde_steps, "scheme": "rk4",
             "lmbd": 0.0, "norm_correction": True, "precision": args.precision if where == "gpu" else "fp32",
             "l2_policy": "working set is on-chip (weights in smem, state in registers); x_0/x_N (2 x 4*B*d bytes) "
                          "streamed once per call; a 256 MB buffer is rewritten between timed calls to flush L2"}
@@ -320,6 +320,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the SSM training leg (profiling runs)")
     ap.add_argument("--no-unet", action="store_true", help="skip the U-Net score-net forward leg (configs 3 and 4)")
+    ap.add_argument("--sde-steps", type=int, default=N_SDE_STEPS, help="reverse-SDE steps per sampler call (default 128; "
+                    "BASELINE config 5 uses 1000)")
     ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU (default 2^20)")
     args = ap.parse_args()
     _claim_stdout()
@@ -343,7 +345,7 @@ def main():
 
     sde, mlp = build_problem(args.dim)
     P, gen = package_objects(sde, mlp, dev)
-    B, N = args.particles, N_SDE_STEPS
+    B, N = args.particles, args.sde_steps
     torch.manual_seed(1234 + rank)
     x0_host = (torch.randn(B, args.dim) * 1.5).pin_memory()
     x0_dev = x0_host.to(dev)
@@ -431,7 +433,14 @@ def main():
                          "traffic": load_traffic(workload_config(args, "gpu")["workload"], args.precision),
                          "algorithmic_bytes": 8 * args.dim * B, "peak_source": peaks["src"],
                          "kernel": "sample_fp32_kernel" if args.precision == "fp32" else "sample_tc_kernel",
-                         "flop_per_launch": fl, "kernel_ms": kms},
+                         "flop_per_launch": fl, "kernel_ms": kms,
+                         # the unit that actually binds the tcgen05 sampler: one MUFU.TANH per hidden activation
+                         # (3 x 128 per net evaluation, 4 evaluations per RK4 step) at 16 / clk / SM (profiles/README.md)
+                         "binding_unit": None if args.precision == "fp32" else {
+                             "pipe": "xu (MUFU)", "ops_per_particle_step": 4 * 384,
+                             "achieved_ops_per_s": 4 * 384 * B * N / (kms / 1e3),
+                             "peak_ops_per_s": 148 * 16 * 1.965e9,
+                             "frac": 4 * 384 * B * N / (kms / 1e3) / (148 * 16 * 1.965e9)}},
         }
         line["train"] = train
         if world == 1 and not args.no_unet:

@@ -83,6 +83,7 @@ class VorticityUNet(nn.Module):
                 torch.backends.cuda.matmul.allow_tf32 = prev
 
     cuda_graph = True  # replay the ~150 launches of one forward as one CUDA graph per (batch size, weight version)
+    max_batch = 1024   # larger batches are evaluated in chunks of this many samples (one graph per chunk size)
 
     @torch.no_grad()
     def _forward_kernels(self, x, t):
@@ -98,6 +99,9 @@ class VorticityUNet(nn.Module):
         tt = _lib.f32c(t, dev)
         if tt.numel() == 1 and B != 1:
             tt = tt.expand(B).contiguous()
+        if B > self.max_batch:  # bound the activation working set (29.5 MB of fp32 activations per 32x32 sample)
+            return torch.cat([self._forward_kernels(xs[i:i + self.max_batch], tt[i:i + self.max_batch])
+                              for i in range(0, B, self.max_batch)], 0)
         if not self.cuda_graph or B == 0 or torch.cuda.is_current_stream_capturing():
             return self._forward_kernels_eager(xs, tt)
         plist = self.__dict__.get("_plist")

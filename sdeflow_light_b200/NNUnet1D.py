@@ -77,6 +77,7 @@ class UNet1D(nn.Module):
     # "tc": convs on tcgen05 with split fp16 x3 operands (fp32-level parity); "tc16": one fp16 product (~1e-3 relative,
     # sampling only); "fp32": CUDA-core kernels only
     conv_mode = "tc"
+    max_batch = 4096  # larger batches are evaluated in chunks of this many samples
 
     def _conv(self, h, dev, conv, x1, x2=None, emb=None, gelu=False):
         L = _lib.lib()
@@ -135,6 +136,9 @@ class UNet1D(nn.Module):
         tt = _lib.f32c(t.reshape(-1), dev)
         if tt.numel() == 1 and B != 1:
             tt = tt.expand(B).contiguous()
+        if B > self.max_batch:  # bound the activation working set (~10 MB of fp32 activations per L = 1000 sample)
+            return torch.cat([self._forward_kernels(xs[i:i + self.max_batch], tt[i:i + self.max_batch])
+                              for i in range(0, B, self.max_batch)], 0)
         E = self.time_mlp[2].weight.shape[0]
         emb = torch.empty((B, E), device=dev, dtype=torch.float32)
         self._embed(h, dev, self.time_mlp, tt, emb, False)

@@ -234,3 +234,23 @@ def test_unet_single_product_mode_tolerance(which):
     err = _rel(got, ref.cpu())
     Bd.report(test=f"{which}-tc16", rel=err)
     assert 0.0 < err < 1e-2
+
+
+@pytest.mark.parametrize("which", ["unet1d", "unet2d"])
+def test_unet_chunked_large_batch_equals_single_pass(which):
+    """Batches above `max_batch` are evaluated in chunks (bounded activation working set): same rows, bit for bit."""
+    torch.manual_seed(11)
+    if which == "unet1d":
+        net = P.UNet1D(125, premodule="NormalizeLogRadius").to(DEV)
+        x, t = torch.randn(37, 125, device=DEV), torch.rand(37, device=DEV)
+    else:
+        net = _build_unet2d(16, "NormalizeLogRadius", "F", 9).to(DEV)
+        x, t = torch.randn(37, 256, device=DEV), torch.rand(37, device=DEV)
+    with torch.no_grad():
+        full = net(x, t)
+        net.max_batch = 16
+        chunked = net(x, t)
+        one_t = net(x, t[:1])      # a single time for the whole batch, as the samplers pass it
+        net.max_batch = 4096
+        one_t_full = net(x, t[:1])
+    assert chunked.shape == full.shape and torch.equal(chunked, full) and torch.equal(one_t, one_t_full)

@@ -20,21 +20,28 @@ from tests import _build as Bd
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-FIX = os.path.join(os.path.dirname(__file__), "golden", "x01_experiment_swissroll_msgm.npz")
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def test_reduced_default_experiment_matches_reference():
-    arr = {k: torch.from_numpy(np.asarray(v)) for k, v in np.load(FIX).items()}
+@pytest.mark.parametrize("kind", ["msgm", "sgm"])  # the driver runs both: MSGMs = [0, 1] (MSGM_higherDim.py:154-157)
+def test_reduced_default_experiment_matches_reference(kind):
+    fix = "x01_experiment_swissroll_msgm.npz" if kind == "msgm" else "x02_experiment_swissroll_sgm.npz"
+    arr = {k: torch.from_numpy(np.asarray(v)) for k, v in np.load(os.path.join(GOLD, fix)).items()}
+    msgm = kind == "msgm"
     K = int(arr["meta_K"])
     np.random.seed(0)
     x_init, xtest = O.swiss_roll(20000), O.swiss_roll(10000)
     assert abs(float(x_init.double().sum()) - float(arr["xinit_sum"])) < 1e-6, "training data differ from the fixture's"
     assert abs(float(xtest.double().sum()) - float(arr["xtest_sum"])) < 1e-6
     T = Bd.T_param(1.0)
-    base = P.MSGMsde(x_init, beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=True, norm_sampler="ecdf",
-                     norm_map="log", num_steps_forward=16, device=DEV, estim_cst_norm_dens_r_T=False)
-    base.G, base.L_G = arr["G"].to(DEV), arr["L_G"].to(DEV)
-    net = P.MLP(2, premodule="NormalizeLogRadius")
+    if msgm:
+        base = P.MSGMsde(x_init, beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=True, norm_sampler="ecdf",
+                         norm_map="log", num_steps_forward=16, device=DEV, estim_cst_norm_dens_r_T=False)
+        base.G, base.L_G = arr["G"].to(DEV), arr["L_G"].to(DEV)
+    else:
+        base = P.SGMsde(beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, num_steps_forward=16, device=DEV)
+        base.dim = 2
+    net = P.MLP(2, premodule="NormalizeLogRadius" if msgm else None)
     net.load_state_dict({k[4:]: v for k, v in arr.items() if k.startswith("sd0.")})
     gen = P.PluginReverseSDE(base, net.to(DEV), T, deviceReverseSDE=DEV).to(DEV)
     opt = torch.optim.Adam(gen.parameters(), lr=1e-3)
@@ -56,13 +63,13 @@ def test_reduced_default_experiment_matches_reference():
     for prec in ("fp32", "f16tc"):
         torch.manual_seed(5)
         x0 = gen.latent_sample(10000, 2)
-        xs = P.rk4_stratonovich_sampler(gen, x0, 128, lmbd=0.0, keep_all_samples=False, norm_correction=True, precision=prec,
+        xs = P.rk4_stratonovich_sampler(gen, x0, 128, lmbd=0.0, keep_all_samples=False, norm_correction=msgm, precision=prec,
                                         seed=17)
         assert torch.isfinite(xs).all()
         mmd = float(QC.compute_mmd(xs[:4000].to(DEV), xt))
         mean, cov = xs.mean(0), torch.cov(xs.T)
         rq = torch.quantile(xs.norm(dim=1), torch.tensor([0.1, 0.5, 0.9]))
-        Bd.report(test=f"experiment-{prec}", K=K, mmd=mmd, ref_mmd=[float(v) for v in ref_mmd],
+        Bd.report(test=f"experiment-{kind}-{prec}", K=K, mmd=mmd, ref_mmd=[float(v) for v in ref_mmd],
                   mean=[float(v) for v in mean], cov=[float(v) for v in cov.flatten()])
         # generated samples are as close to the data as the reference's (MMD of two data halves = the noise floor)
         assert mmd < float(ref_mmd.max()) + 3 * float(spread(ref_mmd)) + 2e-3

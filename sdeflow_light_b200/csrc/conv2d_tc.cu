@@ -445,21 +445,34 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
     set_error("msgm_conv_tc: more than 2^31 padded positions in one call; split the batch");
     return MSGM_ERR_UNSUPPORTED;
   }
-  // M blocks per CTA: as many as TMEM (512 columns) and shared memory allow while still giving every SM a tile
+  // M blocks (128 positions) per CTA, 1..4 (TMEM: MB x NOUT <= 512 columns): the choice that minimises
+  // waves x (MB + 1.5 blocks of per-tile overhead), e.g. 324 blocks on 148 SMs run as one wave of 108 three-block tiles rather than
+  // two waves of two-block tiles.  A wave holds num_sms x (CTAs that fit one SM's shared memory / register file).
   const long long nblk = (P.total + 127) / 128;
-  int MB = 4;
-  while (MB > 1 && ((nblk + MB - 1) / MB) * (P.Cout / NOUT) < ctx->num_sms) MB >>= 1;
+  const int reg_limit = NOUT == 32 ? 3 : 2;
+  int MB = 0;
   size_t smem = 0;
-  for (;; MB >>= 1) {
-    P.MB = MB;
-    P.SL = 128 * MB + 2 * P.halo;
-    smem = 128 + 128 + 2 * (size_t)(nplane * P.SL * 16) + 2 * (size_t)WSTAGE;
-    if ((smem <= 227 * 1024 && P.SL <= 768) || MB == 1) break;
+  double best = 1e300;
+  for (int mb = 1; mb <= 4; ++mb) {
+    const int SL = 128 * mb + 2 * P.halo;
+    const size_t sm = 128 + 128 + 2 * (size_t)(nplane * SL * 16) + 2 * (size_t)WSTAGE;
+    if (sm > 227 * 1024 || SL > 768) continue;
+    const long long tiles = ((nblk + mb - 1) / mb) * (P.Cout / NOUT);
+    const int occ = (int)std::max<size_t>(1, std::min<size_t>(reg_limit, (size_t)(228 * 1024) / (sm + 1024)));
+    const long long slots = (long long)ctx->num_sms * occ;
+    // few waves: whole waves count (the tail wave costs a full tile time); many waves: CTAs drift apart and the
+    // scheduler fills the gaps, so the fractional count is the better model
+    const double wexact = (double)tiles / (double)slots;
+    const double waves = wexact >= 4.0 ? wexact : (double)((tiles + slots - 1) / slots);
+    const double cost = waves * (mb + 1.5);  // 1.5 blocks: halo staging (2 halo / 128), pipeline fill, prologue, epilogue
+    if (cost <= best) { best = cost; MB = mb; smem = sm; }
   }
-  if (smem > 227 * 1024 || P.SL > 768) {
+  if (MB == 0) {
     set_error("msgm_conv_tc: tile does not fit shared memory / the stager's item table (image too wide)");
     return MSGM_ERR_UNSUPPORTED;
   }
+  P.MB = MB;
+  P.SL = 128 * MB + 2 * P.halo;
   int cols = 32;
   while (cols < MB * NOUT) cols <<= 1;
   P.tmem_cols = cols;

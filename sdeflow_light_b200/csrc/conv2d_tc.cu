@@ -398,7 +398,8 @@ __global__ void __launch_bounds__(256) gn_scale_shift_kernel(const float* __rest
 }
 
 // ---- host dispatch ---------------------------------------------------------------------------------------------------
-int conv2d_tc_nout(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32); }
+// output-channel tile: 192 serves the attention qkv convs (Cout = 3 C = 192 / 384) with one / two tiles instead of three
+int conv2d_tc_nout(int Cout) { return Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32)); }
 
 size_t conv2d_tc_pack_bytes(int Cout, int Cin, int KK) { return (size_t)Cout * Cin * KK * 2 * 2; }
 
@@ -456,7 +457,7 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
   for (int mb = 1; mb <= 4; ++mb) {
     const int SL = 128 * mb + 2 * P.halo;
     const size_t sm = 128 + 128 + 2 * (size_t)(nplane * SL * 16) + 2 * (size_t)WSTAGE;
-    if (sm > 227 * 1024 || SL > 768) continue;
+    if (sm > 227 * 1024 || SL > 768 || mb * NOUT > 512) continue;  // shared memory, item table, TMEM columns
     const long long tiles = ((nblk + mb - 1) / mb) * (P.Cout / NOUT);
     const int occ = (int)std::max<size_t>(1, std::min<size_t>(reg_limit, (size_t)(228 * 1024) / (sm + 1024)));
     const long long slots = (long long)ctx->num_sms * occ;
@@ -491,6 +492,7 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
 template <int NT>
 static int launch_conv_tc_n(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
   const int nout = conv2d_tc_nout(P.Cout);
+  if (nout == 192) return launch_conv_tc<192, NT>(ctx, P, stream);
   if (nout == 128) return launch_conv_tc<128, NT>(ctx, P, stream);
   if (nout == 64) return launch_conv_tc<64, NT>(ctx, P, stream);
   return launch_conv_tc<32, NT>(ctx, P, stream);

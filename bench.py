@@ -66,43 +66,60 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    The sampler is started well before the region (nvidia-smi needs up to a second to enumerate an 8-GPU box) and every
+    row is stamped on arrival; `begin()` / `end()` bracket the timed region and `summary()` reports the rows inside it
+    (or, for a region shorter than the sampling period, the rows closest to it -- `samples_in_region` says which)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
-
-    def __enter__(self):
+    def __init__(self, index: int, enabled: bool = True):
+        self.rows, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
+        if not enabled:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
-        return self
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc:
+            time.sleep(0.12)  # let the last in-region sample arrive
             self.proc.terminate()
             self.t.join(timeout=2)
+            self.proc = None
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        if not sm:
+        rows = [(ts, r) for ts, r in self.rows if r and r[0].isdigit()]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        inside = [r for ts, r in rows if self.t0 is not None and self.t0 <= ts <= (self.t1 or ts) + 0.06]
+        n_in = len(inside)
+        if not inside:  # region shorter than the sampling period: the samples nearest to it
+            mid = 0.5 * ((self.t0 or rows[-1][0]) + (self.t1 or rows[-1][0]))
+            inside = [r for _, r in sorted(rows, key=lambda e: abs(e[0] - mid))[:3]]
+        sm = sorted(int(r[0]) for r in inside)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in inside)]
+        mx = [int(r[1]) for r in inside if len(r) > 1 and r[1].isdigit()]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_region": n_in}
 
 
 def build_problem(d: int, seed: int = 0):
@@ -361,6 +378,7 @@ def main():
     def one_call(seed):
         return P.rk4_stratonovich_sampler(gen, x0_dev, N, seed=seed, device_out=True, **kw)
 
+    clk = ClockSampler(local, enabled=(rank == 0))  # started before the warm-up so that it is sampling by the timed region
     for i in range(args.warmup):
         one_call(i)
     barrier()
@@ -368,14 +386,16 @@ def main():
     # ---- device-resident timing (value, roofline) ----------------------------------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = P._lib.launch_count(dev)
-    with ClockSampler(local) as clk:
-        barrier()
-        for i in range(args.steps):
-            flush.fill_(float(i))
-            ev[i][0].record()
-            one_call(100 + i)
-            ev[i][1].record()
-        barrier()
+    barrier()
+    clk.begin()
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        one_call(100 + i)
+        ev[i][1].record()
+    barrier()
+    clk.end()
+    clk.stop()
     launches = P._lib.launch_count(dev) - launches0
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     t_dev = torch.tensor([sum(kern_ms)], device=dev, dtype=torch.float64)

@@ -73,7 +73,7 @@ struct TapGeom {
 };
 
 template <int NOUT, int NT, bool CONST_BASE>
-__global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_tc_kernel(const __grid_constant__ ConvTcParams P) {
+__global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __grid_constant__ ConvTcParams P) {
   constexpr int PADH = TapGeom<NT>::PADH, PADL = TapGeom<NT>::PADL;
   constexpr int WCHUNK = NT * 2 * 2 * NOUT * 16;  // bytes of packed weights per 16-channel chunk: [hi|lo][tap][kc][NOUT][8]
   const int WSTAGE = P.fast ? WCHUNK / 2 : WCHUNK;  // the single-product mode copies the hi half only
@@ -197,9 +197,8 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, NOUT == 32 ? 3 : 2) conv2d_t
       const bool from1 = ch0 < P.C1;
       const float* xb = from1 ? P.x1 + (size_t)ch0 * HWs : P.x2 + (size_t)(ch0 - P.C1) * HWs;
       const size_t bstride = (size_t)(from1 ? P.C1 : P.C2) * HWs;
-      // ILP items (position x 8-channel k-chunk) per step: 8 ILP independent global loads in flight per thread (the narrow
-      // variant keeps one item: it lives on 3 CTAs per SM instead)
-      constexpr int ILP = NOUT == 32 ? 1 : 2;
+      // ILP items (position x 8-channel k-chunk) per step: 8 ILP independent global loads in flight per thread
+      constexpr int ILP = 2;
 #pragma unroll
       for (int i0 = 0; i0 < NI_MAX; i0 += ILP) {
         if (tid + i0 * CTC_STAGERS >= nitem) break;
@@ -450,7 +449,7 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
   // waves x (MB + 1.5 blocks of per-tile overhead), e.g. 324 blocks on 148 SMs run as one wave of 108 three-block tiles rather than
   // two waves of two-block tiles.  A wave holds num_sms x (CTAs that fit one SM's shared memory / register file).
   const long long nblk = (P.total + 127) / 128;
-  const int reg_limit = NOUT == 32 ? 3 : 2;
+  const int reg_limit = 2;
   int MB = 0;
   size_t smem = 0;
   double best = 1e300;

@@ -115,6 +115,7 @@ int msgm_sample_mlp(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc
 /* Forward noising for training, whole batch in ONE launch.  Replaces SDE.sample_scheme / MSGMsde.sample
  * (SDEs.py:78-122,434-436): row k is integrated (RK4-Stratonovich, forward SDE, no radius correction) for
  * n_k = trunc(N t_k / T) steps of size T/N and stops there; a row with n_k == 0 takes one step of size t_k instead.
+ * Dense tensor: d <= 32; sparse tensor: d <= 4096 (one CTA per row: the U-Net configurations, NNUnet1D / NNUnet sizes).
  * t (B,) device; y_inout (B,d) holds x on entry and y_t on exit.  noise (N,B,d) / noise_single (B,d) inject the normals
  * of the common grid / of the one-step rows; NULL = in-kernel Philox keyed by (seed, particle_offset + row). */
 int msgm_noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, float* y_inout, int32_t num_steps_forward,

@@ -78,13 +78,16 @@ class SDE(torch.nn.Module):
         return d, []
 
     # ---- forward noising by simulation (reference SDEs.py:78-132) ------------------------------------------------
+    fused_noising = True  # large sparse states: one launch for the whole forward noising (False: per-stage kernels)
+
     @torch.no_grad()
     def sample_scheme(self, t, y0, keep_all_samples, return_noise=False, *, noise=None, noise_rows=None,
                       _single=None):
         """y_t | y_0: the state after trunc(N_fwd t/T) RK4 steps; rows with 0 steps take ONE step of size t.
 
         ONE launch (msgm_noise_forward) replaces the reference's batch sampler call plus its per-row Python loop of
-        one-sample sampler calls; states with d > 32 use the per-stage kernels in two passes.  ``noise`` (N_fwd,B,d) and
+        one-sample sampler calls, for the dense tensor up to d = 32 and for the sparse tensor up to d = 4096 (the U-Net
+        configurations); ``fused_noising = False`` selects the per-stage kernels in two passes instead (N_fwd x 5 launches).  ``noise`` (N_fwd,B,d) and
         ``noise_rows`` (n_zero_step_rows,d) inject the standard normals the reference would have drawn (parity tests).
         (The reference's 'warning : t >= T' print is dropped: it would cost a host synchronisation per call.)
         """
@@ -95,7 +98,8 @@ class SDE(torch.nn.Module):
         t = t.to(dev)
         y0 = y0.to(dev)
         d = y0.shape[1]
-        if d <= 32:
+        if d <= 32 or (getattr(self, "sparseTensor", False) and d <= 4096 and self.fused_noising):
+            # one launch: the lanes-per-particle kernel (d <= 32) or the one-CTA-per-row kernel (sparse tensor, d <= 4096)
             import ctypes as C
             handle = _lib.ctx(dev)
             y = _lib.f32c(y0, dev).clone()
@@ -408,6 +412,11 @@ def sample_v(shape, device, vtype='rademacher'):
 _VTYPES = {"rademacher": 0, "normal": 1, "gaussian": 1, "uniform": 2}  # msgm_vtype
 
 
+def _prepare_dim_ok(base, d):
+    """msgm_ssm_prepare covers d <= 32 (any SDE) and d <= 4096 for the sparse tensor / the additive SDE."""
+    return d <= 32 or (d <= 4096 and (isinstance(base, SGMsde) or getattr(base, "sparseTensor", False)))
+
+
 class PluginReverseSDE(torch.nn.Module):
     """Reverse-time SDE from a base SDE and a score net ``a`` (reference SDEs.py:538-729).
 
@@ -461,7 +470,7 @@ class PluginReverseSDE(torch.nn.Module):
         """(t, x, y_t) with t ~ U(0,T) floored at t_epsilon (reference SDEs.py:648-693)."""
         if self.ssm_intT:
             raise NotImplementedError("ssm_intT=True raises NameError in the reference (SDEs.py:700); not built")
-        if getattr(self, "device_rng", False) and x.is_cuda and x.dim() == 2 and x.shape[1] <= 32 \
+        if getattr(self, "device_rng", False) and x.is_cuda and x.dim() == 2 and _prepare_dim_ok(self.base_sde, x.shape[1]) \
                 and self.vtype in _VTYPES and isinstance(self.base_sde, (MSGMsde, SGMsde)):
             t_, y, _ = self._prepare(x, with_v=False)
             return t_, x, y

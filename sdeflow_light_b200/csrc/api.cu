@@ -510,8 +510,8 @@ int msgm_noise_forward(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* t, 
   if (!ctx || !sde || !t || !y_inout) return invalid("msgm_noise_forward: NULL argument");
   if (sde->kind != MSGM_SDE_MSGM_DENSE && sde->kind != MSGM_SDE_MSGM_SPARSE)
     return invalid("msgm_noise_forward: the additive SDE has a closed-form marginal (SDEs.py:134-146)");
-  if (sde->dim < 1 || sde->dim > MSGM_MAX_DIM_MLP) {
-    set_error("msgm_noise_forward: dim must be in [1,32] (larger states go through msgm_stage_update)");
+  if (sde->dim < 1 || sde->dim > 4096 || (sde->dim > MSGM_MAX_DIM_MLP && sde->kind == MSGM_SDE_MSGM_DENSE)) {
+    set_error("msgm_noise_forward: dim must be in [1,32] for the dense tensor, [1,4096] for the sparse tensor / SGM");
     return MSGM_ERR_UNSUPPORTED;
   }
   if (sde->kind == MSGM_SDE_MSGM_DENSE && (!sde->G || !sde->L_G)) return invalid("dense MSGM needs G and L_G");
@@ -526,8 +526,8 @@ int msgm_ssm_prepare(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* x, fl
                      int32_t num_steps_forward, const float* ts, float t_epsilon, int32_t vtype, uint64_t seed,
                      const uint64_t* seed_offset_dev, uint64_t sample_offset, int64_t B, void* stream) {
   if (!ctx || !sde || !x || !t_out || !v_out || !y_out) return invalid("msgm_ssm_prepare: NULL argument");
-  if (sde->dim < 1 || sde->dim > MSGM_MAX_DIM_MLP) {
-    set_error("msgm_ssm_prepare: dim must be in [1,32]");
+  if (sde->dim < 1 || sde->dim > 4096 || (sde->dim > MSGM_MAX_DIM_MLP && sde->kind == MSGM_SDE_MSGM_DENSE)) {
+    set_error("msgm_ssm_prepare: dim must be in [1,32] for the dense tensor, [1,4096] for the sparse tensor / SGM");
     return MSGM_ERR_UNSUPPORTED;
   }
   if (sde->kind != MSGM_SDE_SGM && sde->kind != MSGM_SDE_MSGM_DENSE && sde->kind != MSGM_SDE_MSGM_SPARSE)

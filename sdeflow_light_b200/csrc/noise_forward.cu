@@ -211,6 +211,201 @@ __global__ void __launch_bounds__(128) noise_forward_kernel(const __grid_constan
   }
 }
 
+// ---- large states (U-Net configs: d = 1000 / 1024, sparse cyclic tensor or SGM), d <= 4096 ----------------------------------
+// One CTA per row, thread = groups of 4 consecutive components (one Philox4x32 call = their four normals), state x / y /
+// running RK sum / dW in registers for all steps.  The cyclic 3-point stencil needs y_{c+1}, y_{c-1} and dW_{c-1}: inside a
+// group they are registers, across groups they come from a double-buffered copy of y in shared memory (one barrier per
+// stage).  This replaces N_fwd x (4 stage launches + 1 noise launch) = 640 launches per training iteration at N_fwd = 128.
+constexpr int NB_THREADS = 256, NB_MAXG = 4;  // 256 threads x 4 groups x 4 components = 4096
+
+__device__ __forceinline__ float nb_block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  v = l < NB_THREADS / 32 ? red[l] : 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(NB_THREADS) noise_forward_big_kernel(const __grid_constant__ NoiseParams P) {
+  extern __shared__ __align__(16) float sbig[];  // [2][d] stage inputs y, [d] dW
+  __shared__ float red[NB_THREADS / 32];
+  const int d = P.d, tid = threadIdx.x;
+  float* sy = sbig;
+  float* sdw = sbig + 2 * d;
+  const unsigned long long seed = P.seed + (P.seed_off ? *P.seed_off : 0ull);
+  for (long long gp = blockIdx.x; gp < P.B; gp += gridDim.x) {
+    const unsigned long long pid = P.poff + (unsigned long long)gp;
+    float x[NB_MAXG][4], y[NB_MAXG][4], ks[NB_MAXG][4], dw[NB_MAXG][4];
+#pragma unroll
+    for (int e = 0; e < NB_MAXG; ++e)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = 4 * (tid + e * NB_THREADS) + k;
+        x[e][k] = c < d ? (P.x_in ? __ldg(P.x_in + gp * d + c) : P.x[gp * d + c]) : 0.0f;
+        y[e][k] = x[e][k];
+        ks[e][k] = 0.0f;
+        dw[e][k] = 0.0f;
+      }
+    // noise time: given, or t ~ U(0,T) floored at t_epsilon (PluginReverseSDE.sample_t, SDEs.py:684-693)
+    float tk;
+    if (P.t_out) {
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), STREAM_T, 0u),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      tk = u01(r.x) * P.Tsde;
+      tk = tk <= P.t_eps ? P.t_eps : tk;
+      if (tid == 0) P.t_out[gp] = tk;
+    } else {
+      tk = __ldg(P.t_noise + gp);
+    }
+    // Hutchinson probe (sample_v, SDEs.py:514-536)
+    if (P.v_out) {
+      float vv[NB_MAXG][4], n2 = 0.0f;
+#pragma unroll
+      for (int e = 0; e < NB_MAXG; ++e) {
+        const int g = tid + e * NB_THREADS;
+        if (4 * g >= d) continue;
+        if (P.vtype == MSGM_V_RADEMACHER) {
+          const uint4 r = philox4x32_10(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), STREAM_V, (uint32_t)g),
+                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+          vv[e][0] = (r.x >> 31) ? 1.0f : -1.0f; vv[e][1] = (r.y >> 31) ? 1.0f : -1.0f;
+          vv[e][2] = (r.z >> 31) ? 1.0f : -1.0f; vv[e][3] = (r.w >> 31) ? 1.0f : -1.0f;
+        } else {
+          const float4 z = philox_normal4(seed, pid, STREAM_V, (uint32_t)g);
+          vv[e][0] = z.x; vv[e][1] = z.y; vv[e][2] = z.z; vv[e][3] = z.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (4 * g + k < d) n2 = fmaf(vv[e][k], vv[e][k], n2);
+      }
+      float sc = 1.0f;
+      if (P.vtype == MSGM_V_SPHERE) sc = rsqrtf(nb_block_sum(n2, red));  // X / |X| (randu_on_sphere, SDEs.py:520-526)
+#pragma unroll
+      for (int e = 0; e < NB_MAXG; ++e)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * (tid + e * NB_THREADS) + k;
+          if (c < d) P.v_out[gp * d + c] = vv[e][k] * sc;
+        }
+    }
+    if (KIND == MSGM_SDE_SGM) {
+      // closed-form VP marginal (SDE.sample_Song_et_al, SDEs.py:134-146): y = mean_weight(t) x + sqrt(var(t)) eps
+      const float e1 = expf(-0.25f * tk * tk * P.bdel - 0.5f * tk * P.bmin);
+      const float sd = sqrtf(1.0f - expf(-0.5f * tk * tk * P.bdel - tk * P.bmin));
+#pragma unroll
+      for (int e = 0; e < NB_MAXG; ++e) {
+        const int g = tid + e * NB_THREADS;
+        if (4 * g >= d) continue;
+        const float4 z = philox_normal4(seed, pid, STREAM_SGM, (uint32_t)g);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (4 * g + k < d) P.x[gp * d + 4 * g + k] = fmaf(zz[k], sd, e1 * x[e][k]);
+      }
+      continue;
+    }
+
+    // row schedule (SDEs.py:86-118): n_k steps of the common grid, or one step of size t_k
+    float delta = P.delta, delta_half = P.delta_half, sqrt_delta = P.sqrt_delta;
+    const int nk = tk >= P.Tsde ? P.N : (int)truncf(__fdiv_rn(__fmul_rn((float)P.N, tk), P.Tsde));
+    const bool single = nk == 0;
+    const int my_steps = single ? 1 : nk;
+    if (single) {
+      delta = tk;
+      delta_half = (float)((double)tk * 0.5);
+      sqrt_delta = (float)sqrt((double)tk);
+    }
+    int buf = 0;
+    __syncthreads();  // the previous row's last reads of sy / sdw are done
+    for (int step = 0; step < my_steps; ++step) {
+      const float tcur = single ? 0.0f : (P.ts ? __ldg(P.ts + step) : __fmul_rn((float)step, delta));
+#pragma unroll
+      for (int e = 0; e < NB_MAXG; ++e) {
+        const int g = tid + e * NB_THREADS;
+        if (4 * g >= d) continue;
+        float z4[4];
+        if (single && P.noise_single) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) z4[k] = 4 * g + k < d ? __ldg(P.noise_single + gp * d + 4 * g + k) : 0.0f;
+        } else if (P.noise && !single) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) z4[k] = 4 * g + k < d ? __ldg(P.noise + ((long long)step * P.B + gp) * d + 4 * g + k) : 0.0f;
+        } else {
+          const float4 z = philox_normal4(seed, pid, single ? 0xFFFF0002u : (uint32_t)step, (uint32_t)g);
+          z4[0] = z.x; z4[1] = z.y; z4[2] = z.z; z4[3] = z.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          dw[e][k] = sqrt_delta * z4[k];
+          if (4 * g + k < d) {
+            sdw[4 * g + k] = dw[e][k];
+            sy[buf * d + 4 * g + k] = y[e][k];
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        float tst = tcur;
+        if (st > 0) tst = st < 3 ? __fadd_rn(tcur, delta_half) : __fadd_rn(tcur, delta);
+        const float sb = sqrtf(beta_of(P.bmin, P.bdel, tst));
+        const float* yin = sy + buf * d;
+        float* yout = sy + (buf ^ 1) * d;
+#pragma unroll
+        for (int e = 0; e < NB_MAXG; ++e) {
+          const int g = tid + e * NB_THREADS;
+          if (4 * g >= d) continue;
+          float ynew[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = 4 * g + k;
+            ynew[k] = 0.0f;
+            if (c >= d) continue;
+            // cyclic stencil of SDEs.py:369-399: K_c = sqrt(beta / 2) (y_{c+1} dW_c - y_{c-1} dW_{c-1})
+            const float yn = (k < 3 && c + 1 < d) ? y[e][k + 1] : yin[c + 1 == d ? 0 : c + 1];
+            const float yp = k > 0 ? y[e][k - 1] : yin[c == 0 ? d - 1 : c - 1];
+            const float wp = k > 0 ? dw[e][k - 1] : sdw[c == 0 ? d - 1 : c - 1];
+            const float K = (SQRT_HALF * (sb * yn)) * dw[e][k] + (-SQRT_HALF * (sb * yp)) * wp;
+            if (st == 0) { ks[e][k] = K; ynew[k] = x[e][k] + K / 2.0f; }
+            else if (st == 1) { ks[e][k] = ks[e][k] + 2.0f * K; ynew[k] = x[e][k] + K / 2.0f; }
+            else if (st == 2) { ks[e][k] = ks[e][k] + 2.0f * K; ynew[k] = x[e][k] + K; }
+            else { x[e][k] = x[e][k] + (ks[e][k] + K) / 6.0f; ynew[k] = x[e][k]; }
+            yout[c] = ynew[k];
+          }
+          // the registers take the next stage input only after the whole group was evaluated with the old one
+#pragma unroll
+          for (int k = 0; k < 4; ++k) y[e][k] = ynew[k];
+        }
+        buf ^= 1;
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < NB_MAXG; ++e)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = 4 * (tid + e * NB_THREADS) + k;
+        if (c < d) P.x[gp * d + c] = x[e][k];
+      }
+  }
+}
+
+template <int KIND>
+static int launch_noise_big(msgm_ctx* ctx, const NoiseParams& P, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * 3 * (size_t)P.d;
+  auto kern = noise_forward_big_kernel<KIND>;
+  if (smem > 48 * 1024) MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(int)std::min<long long>(P.B, (long long)ctx->num_sms * 8), NB_THREADS, smem, stream>>>(P);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
 template <int DP, int KIND>
 static int launch_noise(msgm_ctx* ctx, const NoiseParams& P, cudaStream_t stream) {
   auto kern = noise_forward_kernel<DP, KIND>;
@@ -245,6 +440,12 @@ static int run_noise(msgm_ctx* ctx, const msgm_sde_desc* sde, NoiseParams& P, in
   P.delta_half = (float)(delta / 2.0);
   P.sqrt_delta = (float)std::sqrt(delta);
   P.G = sde->G;
+  if (d > 32) {  // U-Net sized states: the one-CTA-per-row kernel (sparse multiplicative SDE or SGM)
+    if (sde->kind == MSGM_SDE_MSGM_SPARSE) return launch_noise_big<MSGM_SDE_MSGM_SPARSE>(ctx, P, stream);
+    if (sde->kind == MSGM_SDE_SGM) return launch_noise_big<MSGM_SDE_SGM>(ctx, P, stream);
+    set_error("forward noising of a dense tensor is built for d <= 32 (O(d^3) per step)");
+    return MSGM_ERR_UNSUPPORTED;
+  }
   const int DP = d <= 2 ? 2 : d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32;
   switch (DP) {
     case 2: return launch_noise_kind<2>(ctx, sde->kind, P, stream);

@@ -254,3 +254,57 @@ def test_unet_chunked_large_batch_equals_single_pass(which):
         net.max_batch = 4096
         one_t_full = net(x, t[:1])
     assert chunked.shape == full.shape and torch.equal(chunked, full) and torch.equal(one_t, one_t_full)
+
+
+@pytest.mark.parametrize("d", [1000, 1024, 130, 37])
+def test_fused_noising_of_large_sparse_states_matches_stage_kernels(d):
+    """Training-time forward noising (SDE.sample_scheme, reference SDEs.py:78-122) of U-Net sized states: the one-launch
+    kernel (one CTA per row, all N_fwd steps) against the per-stage kernels on the same injected normals, including a row
+    that takes the single short step (n_k = 0), a row at t = T and dimensions that are not multiples of 4."""
+    torch.manual_seed(d)
+    B, N = 24, 16
+    data = torch.randn(200, d) * 1.2
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(data, beta_min=0.8, beta_max=160., T=T, t_epsilon=8e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=N, device=DEV, estim_cst_norm_dens_r_T=False)
+    x = data[:B].to(DEV)
+    t = torch.rand(B, 1, device=DEV)
+    t[0], t[1], t[2] = 1e-3, 1.0, 0.4 / N
+    n_int = torch.trunc(N * t / 1.0).int().reshape(-1)
+    noise = torch.randn(N, B, d, device=DEV)
+    noise_rows = torch.randn(int((n_int == 0).sum()), d, device=DEV)
+    base.fused_noising = True
+    l0 = P._lib.launch_count(DEV)
+    y_fused = base.sample_scheme(t, x, keep_all_samples=False, noise=noise, noise_rows=noise_rows)
+    n_fused = P._lib.launch_count(DEV) - l0
+    base.fused_noising = False
+    y_stage = base.sample_scheme(t, x, keep_all_samples=False, noise=noise, noise_rows=noise_rows)
+    err = float((y_fused - y_stage).abs().max()) / float(y_stage.abs().max())
+    Bd.report(test=f"fused-noising-d{d}", rel=err, launches=int(n_fused))
+    assert n_fused == 1 and err < 2e-5
+    # in-kernel Philox (the production path): the multiplicative noise keeps the radius up to the RK4 error -- checked on
+    # a milder schedule (beta <= 20, 64 steps); with beta_max = 160 and 16 steps RK4 itself diverges, in every implementation
+    mild = P.MSGMsde(data, beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=64, device=DEV, estim_cst_norm_dens_r_T=False)
+    y = mild.sample_scheme(t, x, keep_all_samples=False)
+    assert torch.isfinite(y).all()
+    assert float(((y.norm(dim=1) - x.norm(dim=1)).abs() / x.norm(dim=1)).max()) < 0.05
+
+
+def test_unet_training_prologue_in_one_launch():
+    """device_rng: t, the Hutchinson probe and y_t of a U-Net sized batch come from ONE launch (msgm_ssm_prepare)."""
+    torch.manual_seed(0)
+    d, B = 1000, 32
+    data = torch.randn(100, d)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(data, beta_min=0.1, beta_max=20., T=T, t_epsilon=8e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=64, device=DEV, estim_cst_norm_dens_r_T=False)
+    gen = P.PluginReverseSDE(base, P.UNet1D(d, premodule="NormalizeLogRadius").to(DEV), T, deviceReverseSDE=DEV).to(DEV)
+    gen.device_rng = True
+    x = data[:B].to(DEV)
+    l0 = P._lib.launch_count(DEV)
+    t_, xx, y = gen.sample_txy(x)
+    assert P._lib.launch_count(DEV) - l0 == 1
+    assert t_.shape == (B, 1) and y.shape == (B, d) and torch.isfinite(y).all()
+    assert float(t_.min()) >= 8e-3 - 1e-9 and float(t_.max()) <= 1.0
+    assert float(((y.norm(dim=1) - x.norm(dim=1)).abs() / x.norm(dim=1)).max()) < 0.05

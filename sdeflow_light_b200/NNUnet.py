@@ -149,7 +149,7 @@ class VorticityUNet(nn.Module):
         log_norm = None
         if self.pre is not None:
             x, log_norm = self.pre(x)
-            x = x * torch.sqrt(torch.tensor(x.shape[-1], dtype=log_norm.dtype, device=log_norm.device))
+            x = x * float(torch.sqrt(torch.tensor(float(x.shape[-1]))))  # fp32 sqrt(d) as in the reference, without a device copy (CUDA-graph safe)
         flat = x.dim() == 2
         if flat:
             img = flat_to_img(x, self.in_space, self.in_space, order=self.flatten_order)

@@ -184,7 +184,7 @@ class UNet1D(nn.Module):
         emb = self.time_mlp(t.view(-1, 1))
         if self.premodule is not None:
             h, log_norm = self.premodule(h)
-            h = h * torch.sqrt(torch.tensor(h.shape[-1], dtype=log_norm.dtype, device=log_norm.device))
+            h = h * float(torch.sqrt(torch.tensor(float(h.shape[-1]))))  # fp32 sqrt(d) as in the reference, without a device copy (CUDA-graph safe)
             emb = emb + self.scale_embed(log_norm.view(log_norm.shape[0], -1).to(emb.dtype))
         emb = emb.unsqueeze(-1)
 

@@ -45,10 +45,17 @@ def zero_module(m):
     return m
 
 
+_FREQS = {}
+
+
 def timestep_embedding(timesteps, dim, max_period=10000):
     """[cos(t w_k), sin(t w_k)], w_k = max_period^(-k/half) (reference model/nn_utils.py:130-148)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
+    key = (half, max_period, str(timesteps.device))
+    freqs = _FREQS.get(key)
+    if freqs is None:  # computed on the host exactly like the reference, copied once (no H2D per call: CUDA-graph safe)
+        freqs = _FREQS[key] = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(
+            timesteps.device)
     ang = timesteps[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
     return torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1) if dim % 2 else emb

@@ -117,9 +117,10 @@ def ssm_loss(gen, t_, x, y, v=None):
 
 
 def ssm(gen, x):
-    if getattr(gen, "device_rng", False) and x.is_cuda and x.dim() == 2 and x.shape[1] <= 32:
+    if getattr(gen, "device_rng", False) and x.is_cuda and x.dim() == 2:
         from . import SDEs
-        if gen.vtype in SDEs._VTYPES and isinstance(gen.base_sde, (SDEs.MSGMsde, SDEs.SGMsde)):
+        if gen.vtype in SDEs._VTYPES and isinstance(gen.base_sde, (SDEs.MSGMsde, SDEs.SGMsde)) \
+                and SDEs._prepare_dim_ok(gen.base_sde, x.shape[1]):
             t_, y, v = gen._prepare(x)  # t, y_t and the probe from one launch
             return ssm_loss(gen, t_, x, y, v)
     t_, x, y = gen.sample_txy(x)

@@ -212,3 +212,56 @@ def test_convt1d_tc_matches_float64(B, Cin, Cout, Lin, Lout, fast):
     assert torch.isfinite(out).all()
     err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
     assert err < (3e-3 if fast else 2e-5), f"convt1d_tc rel err {err:.3e}"
+
+
+def test_tensor_core_kernels_write_inside_their_outputs():
+    """Guard bands: every tensor-core kernel writes its output view and nothing around it (ragged shapes, where tiles hang
+    over the end of the position space)."""
+    dev = torch.device(DEV)
+    h, L = _lib.ctx(dev), _lib.lib()
+    torch.manual_seed(0)
+    PAD, CAN = 4096, 12345.0
+
+    def banded(shape):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        buf = torch.full((n + 2 * PAD,), CAN, device=dev)
+        return buf, buf[PAD:PAD + n].view(shape)
+
+    def intact(buf, n):
+        return bool((buf[:PAD] == CAN).all()) and bool((buf[PAD + n:] == CAN).all())
+
+    # 2-D conv, odd sizes, one sample
+    B, Cin, Cout, H, W_ = 3, 16, 32, 5, 7
+    x = torch.randn(B, Cin, H, W_, device=dev)
+    Wt = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.1
+    img = torch.empty(L.msgm_conv2d_tc_pack_bytes(Cout, Cin, 3), device=dev, dtype=torch.uint8)
+    _lib.check(L.msgm_conv2d_tc_pack(h, _lib.ptr(Wt), Cout, Cin, 3, _lib.ptr(img), _lib.stream_ptr(dev)))
+    buf, out = banded((B, Cout, H, W_))
+    d = _lib.Conv2dTcDesc(x.data_ptr(), None, img.data_ptr(), None, None, None, None, out.data_ptr(), B, Cin, 0, Cout, 3, 1, 1,
+                          H, W_, 0, 0)
+    _lib.check(L.msgm_conv2d_tc(h, C.byref(d), _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), Wt.double(), padding=1)
+    assert intact(buf, out.numel()) and float((out.double() - ref).abs().max()) < 1e-4
+    # transposed 1-D conv with right padding
+    Bc, Ci, Co, Lin, Lout = 2, 16, 16, 9, 21
+    xt = torch.randn(Bc, Ci, Lin, device=dev)
+    Wc = torch.randn(Ci, Co, 4, device=dev) * 0.2
+    bias = torch.randn(Co, device=dev)
+    imgt = torch.empty(24 * Ci * Co, device=dev, dtype=torch.uint8)
+    _lib.check(L.msgm_convt1d_tc_pack(h, _lib.ptr(Wc), Co, Ci, _lib.ptr(imgt), _lib.stream_ptr(dev)))
+    buf, out = banded((Bc, Co, Lout))
+    out.zero_()
+    _lib.check(L.msgm_convt1d_tc(h, _lib.ptr(xt), _lib.ptr(imgt), _lib.ptr(bias), _lib.ptr(out), Bc, Ci, Co, Lin, Lout, 0,
+                                 _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    ref = F.pad(F.conv_transpose1d(xt.double(), Wc.double(), bias.double(), stride=2, padding=1), (0, Lout - 2 * Lin))
+    assert intact(buf, out.numel()) and float((out.double() - ref).abs().max()) < 1e-4
+    # attention, T = 64 (half of the 128-query tile is padding)
+    qkv = torch.randn(3, 192, 64, device=dev)
+    buf, out = banded((3, 64, 64))
+    _lib.check(L.msgm_attention_tc(h, _lib.ptr(qkv), _lib.ptr(out), 3, 64, 64, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert intact(buf, out.numel()) and torch.isfinite(out).all()

@@ -336,3 +336,27 @@ def test_graphed_unet_train_iteration(which):
     assert all(l == l and abs(l) < 1e6 for l in losses) and len(set(losses)) > 1   # finite, fresh draws per replay
     moved = sum(float((p.detach() - q).abs().sum()) for p, q in zip((p for p in gen.parameters() if p.requires_grad), p0))
     assert moved > 0.0
+
+
+def test_fused_noising_writes_inside_its_output():
+    """Guard bands around y for the one-CTA-per-row noising kernel at a dimension that is not a multiple of 4."""
+    import ctypes as C
+    from sdeflow_light_b200 import _lib
+    torch.manual_seed(2)
+    d, B, N = 1001, 5, 8
+    data = torch.randn(64, d)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(data, beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=N, device=DEV, estim_cst_norm_dens_r_T=False)
+    dev = torch.device(DEV)
+    PAD, CAN = 4096, 777.0
+    buf = torch.full((B * d + 2 * PAD,), CAN, device=dev)
+    y = buf[PAD:PAD + B * d].view(B, d)
+    y.copy_(data[:B])
+    t = torch.rand(B, device=dev)
+    sd, keep = base.desc(dev)
+    ts = (torch.linspace(0, 1, N + 1) * 1.0).to(dev)
+    _lib.check(_lib.lib().msgm_noise_forward(_lib.ctx(dev), C.byref(sd), _lib.ptr(t), _lib.ptr(y), N, _lib.ptr(ts), None, None,
+                                             11, 0, B, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert bool((buf[:PAD] == CAN).all()) and bool((buf[PAD + B * d:] == CAN).all()) and torch.isfinite(y).all()

@@ -18,6 +18,21 @@ from .NN import NormalizeLogRadius, evaluate  # noqa: F401
 scale_image = 5
 
 
+def set_library_precision(tf32: bool):
+    """Precision of torch's library convolutions / matmuls on the autograd (training) path of the U-Nets.
+
+    The backward and double-backward convolutions run when the USER calls ``loss.backward()``, outside any context this
+    module could open, and torch's default lets cuDNN use TF32 there (10-bit mantissa: gradients 3e-4 off an fp32
+    run).  The reference is fp32 end to end, so the training forward sets the process-wide switches to fp32 -- a
+    deliberate, documented side effect -- unless the net opts in with ``train_tf32 = True`` (what the reference itself
+    would silently get on a GPU)."""
+    tf32 = bool(tf32)
+    if torch.backends.cudnn.allow_tf32 != tf32:
+        torch.backends.cudnn.allow_tf32 = tf32
+    if torch.backends.cuda.matmul.allow_tf32 != tf32:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def flat_to_img(x, H, W, order="C"):
     B, d = x.shape
     assert d == H * W, f"Expected d={H*W}, got {d}"
@@ -74,14 +89,11 @@ class VorticityUNet(nn.Module):
         needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if not needs_graph and x.dim() == 2:
             return self._forward_kernels(x, t.view(-1))
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):  # the reference is fp32 end to end
-            prev = torch.backends.cuda.matmul.allow_tf32
-            torch.backends.cuda.matmul.allow_tf32 = False
-            try:
-                return self._forward(x, t.view(-1))
-            finally:
-                torch.backends.cuda.matmul.allow_tf32 = prev
+        # autograd (training) path through torch's library layers
+        set_library_precision(self.train_tf32)
+        return self._forward(x, t.view(-1))
 
+    train_tf32 = False  # TF32 tensor cores for the library convs of the autograd (training) path; off = fp32 parity
     cuda_graph = True  # replay the ~150 launches of one forward as one CUDA graph per (batch size, weight version)
     max_batch = 1024   # larger batches are evaluated in chunks of this many samples (one graph per chunk size)
 

@@ -69,15 +69,18 @@ class UNet1D(nn.Module):
         needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if not needs_graph:
             return self._forward_kernels(x, t)
-        # autograd path: the reference is fp32 end to end, keep cuDNN from silently using TF32 for the convolutions
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            return self._forward(x, t)
+        # autograd path: the reference is fp32 end to end, keep cuDNN from silently using TF32 for the convolutions of the
+        # forward AND of the backward / double backward the caller triggers later (process-wide switch, see NNUnet)
+        from .NNUnet import set_library_precision
+        set_library_precision(self.train_tf32)
+        return self._forward(x, t)
 
     # ---- hand-written kernel path (inference) -------------------------------------------------------------------
     # "tc": convs on tcgen05 with split fp16 x3 operands (fp32-level parity); "tc16": one fp16 product (~1e-3 relative,
     # sampling only); "fp32": CUDA-core kernels only
     conv_mode = "tc"
     max_batch = 4096  # larger batches are evaluated in chunks of this many samples
+    train_tf32 = False  # TF32 for the library convs of the autograd (training) path; off = fp32 parity with the reference
 
     def _conv(self, h, dev, conv, x1, x2=None, emb=None, gelu=False):
         L = _lib.lib()

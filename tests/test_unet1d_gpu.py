@@ -1,6 +1,7 @@
 """GPU parity of the 1-D U-Net score path (BASELINE config 3) against golden fixtures of the reference: the UNet1D
 forward, RK4 reverse sampling with the sparse multiplicative SDE through the hand-written per-stage update kernels, and
-the SSM loss + gradients.  fp32 tolerances: 2e-4 + 2e-4 max|ref| (cuDNN convolutions vs the reference's CPU convolutions).
+the SSM loss + gradients.  fp32 tolerances: 2e-5 relative to max|ref| (tensor-core split-precision forward kernels and
+cuDNN fp32 autograd vs the reference's CPU convolutions).
 """
 import pytest
 import torch
@@ -47,7 +48,8 @@ def test_unet1d_forward_sampler_ssm(name):
     loss.mean().backward()
     e_g = max(_rel(p.grad, arr["grad." + k]) for k, p in net.named_parameters())
     Bd.report(test=name, fwd_rel=e_f, sampler_rel=e_s, loss_rel=e_l, grad_rel=e_g)
-    assert e_f < 2e-4 and e_s < 2e-4 and e_l < 2e-4 and e_g < 1e-3
+    # observed 2e-7 .. 1e-6 everywhere (the backward runs in fp32 too: NNUnet.set_library_precision); 2e-5 leaves a 20x margin
+    assert e_f < 2e-5 and e_s < 2e-5 and e_l < 2e-5 and e_g < 2e-5
 
 
 @pytest.mark.parametrize("kind,d,scheme,lmbd,nc", [("msgm_sparse", 1000, "rk4", 0.0, True), ("msgm_sparse", 257, "heun", 0.3, True),
@@ -132,7 +134,8 @@ def test_unet2d_forward_sampler_ssm(name):
     Bd.report(test=name, fwd_rel=e_f, sampler_rel=e_s, loss_rel=e_l, gradnorm_rel=e_g, gradhead_rel=e_h)
     # a 40-layer random-weight net amplifies the cuDNN-vs-CPU summation-order difference of one forward (~5e-6) through
     # 8 chained evaluations (sampler) and through the double backward (loss / gradients)
-    assert e_f < 5e-5 and e_s < 1e-3 and e_l < 2e-3 and e_g < 5e-3 and e_h < 5e-3
+    # (observed: forward 7e-6, sampler 3e-4, loss 3e-6, gradients 2e-6 / 6e-6 with the fp32 backward)
+    assert e_f < 5e-5 and e_s < 1e-3 and e_l < 1e-4 and e_g < 1e-4 and e_h < 2e-4
 
 
 def test_unet2d_full_size_runs():

@@ -374,6 +374,8 @@ class UNetModel(nn.Module):
 def _tc_shape_ok(Cout, C1, C2, K, stride, Hi, Wi):
     if K not in (1, 3) or Cout % 32 or (C1 + C2) % 16 or C1 % 16:
         return False
+    if K == 3 and 128 + 2 * (Wi + 3) > 768:  # one 128-position block plus its halo must fit the stager's item table
+        return False
     return stride == 1 or (stride == 2 and K == 3 and Hi % 2 == 0 and Wi % 2 == 0)
 
 

@@ -268,6 +268,26 @@ def time_unet_forward(P, dev):
             out["runs"].append({"net": name, "batch": B, "ms_per_forward": ms, "value": B / ms * 1e3,
                                 "algorithmic_tflops": gflop * B / ms, "torch_fp32_ms": ms_t,
                                 "rel_diff_vs_torch_fp32": err})
+    # one SSM training iteration of the same nets (sparse multiplicative SDE; one-launch noising, forward-mode loss through
+    # torch's fp32 library layers, Adam), replayed as CUDA graphs by train.GraphedSsmStep
+    from sdeflow_light_b200.train import GraphedSsmStep
+    for (name, net, _, d, _), (Bt, nfwd) in zip(nets, ((64, 16), (32, 128))):
+        try:
+            data = torch.randn(512, d)
+            T = torch.nn.Parameter(torch.FloatTensor([1.0]), requires_grad=False)
+            base = P.MSGMsde(data, beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                             num_steps_forward=nfwd, device=dev, estim_cst_norm_dens_r_T=False)
+            gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=dev).to(dev)
+            step = GraphedSsmStep(gen, (Bt, d), lr=1e-4)
+            xs = data[:Bt].to(dev)
+            ms = timeit(lambda: step(xs), 10)
+            entry = {"train_batch": Bt, "num_steps_forward": nfwd, "train_ms_per_iter": ms,
+                     "train_samples_per_sec": Bt / ms * 1e3, "train_loss": float(step.loss)}
+        except Exception as exc:
+            entry = {"train_error": f"{type(exc).__name__}: {exc}"}
+        for r in out["runs"]:
+            if r["net"] == name:
+                r.update(entry)
     return out
 
 

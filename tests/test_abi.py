@@ -127,3 +127,29 @@ def test_tensor_core_layer_shape_queries_need_no_gpu():
     assert _tc_shape_ok(64, 64, 32, 3, 1, 16, 16) and _tc_shape_ok(32, 32, 0, 3, 2, 32, 32)
     assert not _tc_shape_ok(32, 1, 0, 3, 1, 32, 32) and not _tc_shape_ok(1, 32, 0, 3, 1, 32, 32)
     assert not _tc_shape_ok(32, 32, 0, 3, 2, 31, 32) and not _tc_shape_ok(64, 40, 24, 1, 1, 8, 8)
+
+
+def test_training_path_host_policies():
+    """Host-side policies of the U-Net training path: which states the one-launch prologue covers, and the process-wide
+    library precision switch (fp32 unless a net opts into TF32)."""
+    from sdeflow_light_b200 import SDEs
+    from sdeflow_light_b200.NNUnet import set_library_precision
+    T = torch.nn.Parameter(torch.FloatTensor([1.0]), requires_grad=False)
+    sgm = P.SGMsde(T=T, device="cpu")
+
+    class _Sparse:
+        sparseTensor = True
+
+    class _Dense:
+        sparseTensor = False
+
+    assert SDEs._prepare_dim_ok(sgm, 2) and SDEs._prepare_dim_ok(sgm, 1024) and not SDEs._prepare_dim_ok(sgm, 5000)
+    assert SDEs._prepare_dim_ok(_Sparse(), 1000) and SDEs._prepare_dim_ok(_Dense(), 32) and not SDEs._prepare_dim_ok(_Dense(), 33)
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        set_library_precision(False)
+        assert not torch.backends.cudnn.allow_tf32 and not torch.backends.cuda.matmul.allow_tf32
+        set_library_precision(True)
+        assert torch.backends.cudnn.allow_tf32 and torch.backends.cuda.matmul.allow_tf32
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev

@@ -99,10 +99,14 @@ int msgm_create(msgm_ctx** out, int device);
 int msgm_destroy(msgm_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t msgm_launch_count(const msgm_ctx* ctx);
-/* Debug: synchronises the device and returns the kernel-side flag word (1: a bounded mbarrier wait inside a
- * tensor-core kernel -- sampler, conv, attention -- timed out; 2: shared-memory / TMEM base assumption violated).
- * Read-and-clear.  Used by the tests; 0 in a healthy run. */
+/* Error word of the tensor-core kernels (sampler, conv, attention): 1 = a bounded mbarrier wait timed out and the
+ * launch gave up (its output is undefined), 2 = shared-memory / TMEM base assumption violated; 0 in a healthy run.  The
+ * kernels write the word into mapped pinned host memory, so msgm_async_error reads it WITHOUT synchronising: it reports
+ * whatever has been raised by launches that already ran (the Python shims call it on entry and after every device->host
+ * copy and raise RuntimeError).  msgm_debug_flags synchronises the device first.  Both are read-and-clear.
+ * (The reference has no counterpart: a CUDA fault in its ATen ops surfaces as a RuntimeError of the next call.) */
 int msgm_debug_flags(msgm_ctx* ctx, int32_t* out_host);
+int msgm_async_error(msgm_ctx* ctx, int32_t* out_host);
 /* Debug: cycle counters of the tensor-core sampler (CTA 0), filled only while the environment variable
  * MSGM_TC_PROF is set; n <= 24.  [0..7] owner thread, [8..15] MMA thread, [16..23] helper thread. */
 int msgm_debug_counters(msgm_ctx* ctx, int64_t* out_host, int n);

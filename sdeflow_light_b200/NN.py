@@ -17,15 +17,33 @@ import torch.nn as nn
 from . import _lib
 
 
-def save_checkpoint(path, gen_sde, optim, iteration):
-    """Same dictionary layout as the reference (NN.py:13-22) so checkpoints load both ways."""
-    torch.save({"iteration": iteration, "model": gen_sde.state_dict(), "optimizer": optim.state_dict(),
-                "torch_rng": torch.get_rng_state().cpu(), "numpy_rng": np.random.get_state(),
-                "python_rng": random.getstate()}, path)
+_SDE_TENSORS = ("G", "L_G", "r_T", "G_I", "G_J", "G_K", "G_V")
 
 
-def load_checkpoint(path, gen_sde, optim, device):
-    """NN.py:24-42."""
+def save_checkpoint(path, gen_sde, optim, iteration, *, trainer=None, persist_sde=True):
+    """Same dictionary layout as the reference (NN.py:13-22) so checkpoints load both ways.
+
+    Two extra keys the reference's loader ignores (it reads its six keys by name): ``msgm_sde`` holds the base SDE's
+    tensors that ``state_dict()`` does not -- the random skew-symmetric ``G`` (drawn from the global RNG at construction,
+    SDEs.py:315-321), ``L_G``, the radius table ``r_T`` or the sparse ``G_I/G_J/G_K/G_V`` -- so that a resumed multiplicative
+    SDE is well defined; ``msgm_trainer_rng`` holds the Philox seed / iteration counter of a
+    ``train.GraphedSsmStep`` so that a resumed run continues its random stream."""
+    ck = {"iteration": iteration, "model": gen_sde.state_dict(), "optimizer": optim.state_dict(),
+          "torch_rng": torch.get_rng_state().cpu(), "numpy_rng": np.random.get_state(),
+          "python_rng": random.getstate()}
+    base = getattr(gen_sde, "base_sde", None)
+    if persist_sde and base is not None:
+        extra = {n: getattr(base, n).detach().cpu() for n in _SDE_TENSORS if torch.is_tensor(getattr(base, n, None))}
+        if extra:
+            ck["msgm_sde"] = extra
+    if trainer is not None:
+        ck["msgm_trainer_rng"] = trainer.rng_state()
+    torch.save(ck, path)
+
+
+def load_checkpoint(path, gen_sde, optim, device, *, trainer=None):
+    """NN.py:24-42; additionally restores the ``msgm_sde`` / ``msgm_trainer_rng`` extras when the file has them (a file
+    written by the reference has neither and loads exactly as in the reference)."""
     ck = torch.load(path, map_location=device, weights_only=False)
     gen_sde.load_state_dict(ck["model"])
     optim.load_state_dict(ck["optimizer"])
@@ -33,6 +51,13 @@ def load_checkpoint(path, gen_sde, optim, device):
     torch.set_rng_state((rng if rng.dtype == torch.uint8 else rng.to(torch.uint8)).cpu())
     np.random.set_state(ck["numpy_rng"])
     random.setstate(ck["python_rng"])
+    base = getattr(gen_sde, "base_sde", None)
+    if base is not None and "msgm_sde" in ck:
+        for n, t in ck["msgm_sde"].items():
+            setattr(base, n, t.to(base.device))
+        base.__dict__.pop("_rT_sorted", None)  # derived caches
+    if trainer is not None and "msgm_trainer_rng" in ck:
+        trainer.load_rng_state(ck["msgm_trainer_rng"])
     print(f"Resuming from iteration {ck['iteration'] + 1}")
     return ck["iteration"]
 

@@ -106,6 +106,8 @@ class VorticityUNet(nn.Module):
         changes the version key and triggers a re-capture (which also re-packs the tensor-core weight images)."""
         from . import _lib
         dev = x.device
+        if not torch.cuda.is_current_stream_capturing():
+            _lib.check_async(dev)  # an earlier tensor-core launch that gave up surfaces here (no synchronisation)
         B = x.shape[0]
         xs = _lib.f32c(x, dev)
         tt = _lib.f32c(t, dev)
@@ -119,7 +121,7 @@ class VorticityUNet(nn.Module):
         plist = self.__dict__.get("_plist")
         if plist is None:
             plist = self.__dict__["_plist"] = list(self.parameters())
-        ver = hash(tuple((p_._version, p_.data_ptr()) for p_ in plist))
+        ver = hash(tuple((p_._version, p_.data_ptr()) for p_ in plist) + (_lib.weight_epoch(),))
         cache = self.__dict__.setdefault("_graphs", {})
         key = (B, dev.index, self.core.conv_mode)
         ent = cache.get(key)

@@ -102,7 +102,7 @@ class UNet1D(nn.Module):
                 ((K == 3 and stride == 1 and pad == 1) or (K == 4 and stride == 2 and pad == 1 and Lin >= 2) or
                  (K == 1 and stride == 1 and pad == 0))):
             cache = self.__dict__.setdefault("_tc_wimg", {})
-            key = (conv.weight._version, tuple(W.shape), dev.index)
+            key = (conv.weight._version, _lib.weight_epoch(), tuple(W.shape), dev.index)
             ent = cache.get(W.data_ptr())
             if ent is None or ent[0] != key:
                 img = torch.empty(L.msgm_conv1d_tc_pack_bytes(Cout, Cin, K), device=dev, dtype=torch.uint8)
@@ -134,6 +134,8 @@ class UNet1D(nn.Module):
     def _forward_kernels(self, x, t):
         dev = x.device
         h, L = _lib.ctx(dev), _lib.lib()
+        if not torch.cuda.is_current_stream_capturing():
+            _lib.check_async(dev)  # an earlier tensor-core launch that gave up surfaces here (no synchronisation)
         xs = _lib.f32c(x.reshape(x.shape[0], -1), dev)
         B, Lsig = xs.shape
         tt = _lib.f32c(t.reshape(-1), dev)
@@ -164,7 +166,7 @@ class UNet1D(nn.Module):
             Cup, Lup = W.shape[1], skip.shape[-1]
             if self.conv_mode in ("tc", "tc16") and Cin % 16 == 0 and Cup % 16 == 0 and Lup >= 2 * Lin:
                 cache = self.__dict__.setdefault("_tc_wimg", {})
-                key = (up.weight._version, tuple(W.shape), dev.index)
+                key = (up.weight._version, _lib.weight_epoch(), tuple(W.shape), dev.index)
                 ent = cache.get(W.data_ptr())
                 if ent is None or ent[0] != key:
                     img = torch.empty(24 * Cin * Cup, device=dev, dtype=torch.uint8)

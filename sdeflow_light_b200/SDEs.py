@@ -105,6 +105,7 @@ class SDE(torch.nn.Module):
             y = _lib.f32c(y0, dev).clone()
             tt = _lib.f32c(t.reshape(-1), dev)
             sd, keep = self.desc(dev)
+            sd.dim = d  # SGMsde has no dim of its own
             if noise is not None:
                 noise = _lib.f32c(noise, dev)
             single = None if _single is None else _lib.f32c(_single, dev)  # (B,d): row k's draw if it takes 0 steps

@@ -12,7 +12,9 @@ import threading
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmsgm_b200.so")
+# MSGM_LIB_VARIANT=<name> loads libmsgm_b200_<name>.so instead (kernel A/B experiments, tools/tc_variants.py)
+LIB_PATH = os.path.join(HERE, "libmsgm_b200" + ("_" + os.environ["MSGM_LIB_VARIANT"] if os.environ.get("MSGM_LIB_VARIANT")
+                                                else "") + ".so")
 
 SDE_SGM, SDE_MSGM_DENSE, SDE_MSGM_SPARSE = 0, 1, 2
 SCHEME_EM, SCHEME_HEUN, SCHEME_RK4 = 0, 1, 2
@@ -63,7 +65,7 @@ _lock = threading.Lock()
 _ctx = {}
 
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
-SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count",
+SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count", "msgm_async_error",
            "msgm_sample_mlp", "msgm_noise_forward", "msgm_ssm_prepare", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward",
            "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums", "msgm_kde_logpdf",
@@ -90,6 +92,7 @@ def lib() -> C.CDLL:
                 L.msgm_destroy.argtypes = [C.c_void_p]
                 L.msgm_launch_count.argtypes = [C.c_void_p]
                 L.msgm_debug_flags.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+                L.msgm_async_error.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
                 L.msgm_ssm_scratch_bytes.restype = C.c_uint64
                 L.msgm_ssm_scratch_bytes.argtypes = [C.c_int64]
                 L.msgm_ssm_mlp_forward.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc)] + [C.c_void_p] * 5 + \
@@ -174,6 +177,21 @@ def ctx(device) -> C.c_void_p:
     return _ctx[idx]
 
 
+# Weight epoch: parameters updated INSIDE a replayed CUDA graph (train.GraphedSsmStep) do not bump ``Tensor._version``,
+# so every cache derived from weights (packed tensor-core images, stacked embedding weights, captured inference graphs)
+# also keys on this counter, which the trainer bumps after each replay.
+_weight_epoch = 0
+
+
+def weight_epoch() -> int:
+    return _weight_epoch
+
+
+def bump_weight_epoch() -> None:
+    global _weight_epoch
+    _weight_epoch += 1
+
+
 def launch_count(device=None) -> int:
     if device is None:
         return sum(int(lib().msgm_launch_count(h)) for h in _ctx.values())
@@ -184,6 +202,22 @@ def debug_flags(device) -> int:
     out = C.c_int32(0)
     check(lib().msgm_debug_flags(ctx(device), C.byref(out)))
     return int(out.value)
+
+
+_ASYNC_MSG = {1: "a bounded mbarrier wait inside a tensor-core kernel timed out (the launch gave up; its output is "
+                   "undefined)", 2: "tensor-core kernel: shared-memory / TMEM base assumption violated"}
+
+
+def check_async(device=None) -> None:
+    """Raise if a tensor-core kernel that has already run reported an error (no synchronisation: msgm_async_error reads a
+    mapped host word).  Called by the shims on entry and after device->host copies, so a timed-out launch surfaces as a
+    RuntimeError instead of silently wrong numbers."""
+    handles = _ctx.values() if device is None else [ctx(device)]
+    for h in handles:
+        out = C.c_int32(0)
+        check(lib().msgm_async_error(h, C.byref(out)))
+        if out.value:
+            raise RuntimeError("libmsgm_b200: " + _ASYNC_MSG.get(int(out.value), f"kernel error code {out.value}"))
 
 
 def debug_counters(device):

@@ -103,11 +103,22 @@ int msgm_create(msgm_ctx** out, int device) {
   c->launches = 0;
   c->ws = nullptr;
   c->ws_bytes = 0;
+  c->host_flag = nullptr;
+  c->host_flag_dev = nullptr;
+  c->launch_seq = 0;
   // fixed device workspace: [0,256) debug flags, [256,256K) packed fp16 weight image, [256K,512K) padded G
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaMalloc(&c->ws, 1 << 19);
   if (e == cudaSuccess) e = cudaMemset(c->ws, 0, 1 << 19);
+  // error word of the tensor-core kernels: mapped pinned host memory, written by the device, polled by the host
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->host_flag), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e == cudaSuccess) {
+    *c->host_flag = 0;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->host_flag_dev), c->host_flag, 0);
+  }
   if (e != cudaSuccess) {
+    if (c->ws) cudaFree(c->ws);
+    if (c->host_flag) cudaFreeHost(c->host_flag);
     delete c;
     return cuda_fail(e, "msgm_create workspace");
   }
@@ -119,6 +130,7 @@ int msgm_create(msgm_ctx** out, int device) {
 int msgm_destroy(msgm_ctx* ctx) {
   if (!ctx) return MSGM_OK;
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->host_flag) cudaFreeHost(ctx->host_flag);
   delete ctx;
   return MSGM_OK;
 }
@@ -129,10 +141,14 @@ int msgm_debug_flags(msgm_ctx* ctx, int32_t* out_host) {
   if (!ctx || !out_host) return invalid("msgm_debug_flags: NULL argument");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   MSGM_CUDA_TRY(cudaDeviceSynchronize());
-  MSGM_CUDA_TRY(cudaMemcpy(out_host, ctx->ws, sizeof(int32_t), cudaMemcpyDeviceToHost));
-  // read-and-clear: the conv / attention kernels do not reset the word per launch (the sampler does), so a timeout seen
-  // once must not make every later bounded wait bail out early
-  if (*out_host != 0) MSGM_CUDA_TRY(cudaMemset(ctx->ws, 0, sizeof(int32_t)));
+  return msgm_async_error(ctx, out_host);
+}
+
+int msgm_async_error(msgm_ctx* ctx, int32_t* out_host) {
+  if (!ctx || !out_host) return invalid("msgm_async_error: NULL argument");
+  volatile int* f = ctx->host_flag;
+  *out_host = *f;
+  if (*out_host != 0) *f = 0;  // read-and-clear
   return MSGM_OK;
 }
 

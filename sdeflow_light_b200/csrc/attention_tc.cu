@@ -22,7 +22,7 @@ struct AttnTcParams {
   float* out;
   int C, T;
   float scale2;
-  int* flags;
+  TcFlags flags;
 };
 
 constexpr int ATC_THREADS = 256;
@@ -210,7 +210,7 @@ bool attention_tc_ok(int C, int T) {
 }
 
 int attention_tc(msgm_ctx* ctx, const float* qkv, float* out, int B, int C, int T, cudaStream_t stream) {
-  AttnTcParams P{qkv, out, C, T, 1.0f / sqrtf((float)C), reinterpret_cast<int*>(ctx->ws)};
+  AttnTcParams P{qkv, out, C, T, 1.0f / sqrtf((float)C), next_tc_flags(ctx)};
   const size_t smem = 128 + 128 + 4 * (size_t)C * (128 + 2 * T);
   MSGM_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_tc_kernel<<<dim3((T + 127) / 128, B), ATC_THREADS, smem, stream>>>(P);

@@ -49,7 +49,7 @@ struct ConvTcParams {
   uint32_t mul_img, shr_img, mul_row, shr_row;  // magic numbers: n / (Hp Wp) and n / Wp for n < 2^31
   int tmem_cols;
   int fast;                   // 1: single fp16 product (hi planes only; ~1e-3 relative), 0: three split products (fp32-level)
-  int* flags;
+  TcFlags flags;
 };
 
 __device__ __forceinline__ float silu_acc(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
     const uint32_t idesc = umma_idesc_f16(128, NOUT);
     const uint32_t sbase = CONST_BASE ? 1024u : smem_u32(smem);
     if (sbase != smem_u32(smem)) {
-      if (lane == 0) atomicExch(P.flags, 2);
+      if (lane == 0) tc_raise(P.flags, 2);
     } else {
       const uint32_t a_base0 = sbase + 128u, w_base0 = a_base0 + 2u * (uint32_t)ASTAGE;
       for (int k = 0; k < P.NC; ++k) {
@@ -511,7 +511,7 @@ int conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* D, cudaStream_t stream) 
   P.Ho = (P.Hi + 2 * pad - D->K) / D->stride + 1;
   P.Wo = (P.Wi + 2 * pad - D->K) / D->stride + 1;
   P.NC = (P.C1 + P.C2) / 16;
-  P.flags = reinterpret_cast<int*>(ctx->ws);
+  P.flags = next_tc_flags(ctx);
   return D->K == 3 ? launch_conv_tc_n<9>(ctx, P, stream) : launch_conv_tc_n<1>(ctx, P, stream);
 }
 
@@ -528,7 +528,7 @@ int conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* D, cudaStream_t stream) 
   const int pad = D->K == 1 ? 0 : 1;
   P.Wo = (D->Lin + 2 * pad - D->K) / D->stride + 1;
   P.NC = (P.C1 + P.C2) / 16;
-  P.flags = reinterpret_cast<int*>(ctx->ws);
+  P.flags = next_tc_flags(ctx);
   if (D->K == 3) return launch_conv_tc_n<3>(ctx, P, stream);
   if (D->K == 4) return launch_conv_tc_n<4>(ctx, P, stream);
   return launch_conv_tc_n<1>(ctx, P, stream);
@@ -554,7 +554,7 @@ int convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bia
   P.B = B; P.Cout = 2 * Cout; P.stride = 1; P.up = 1; P.Hs = 1; P.Ws = Lin;
   P.Hi = 1; P.Wi = Lin; P.Ho = 1; P.Wo = Lout;
   P.NC = Cin / 16;
-  P.flags = reinterpret_cast<int*>(ctx->ws);
+  P.flags = next_tc_flags(ctx);
   return launch_conv_tc_n<3>(ctx, P, stream);
 }
 

@@ -33,6 +33,9 @@ struct msgm_ctx {
   int64_t launches;
   void* ws;          // device workspace (packed fp16 weights for the tensor-core path, ...)
   size_t ws_bytes;
+  int* host_flag;      // mapped pinned host word: error code raised by a tensor-core kernel (tc_ptx.cuh, TcFlags)
+  int* host_flag_dev;  // its device alias
+  int launch_seq;      // ids of the tensor-core launches (1, 2, ...)
 };
 
 namespace msgm {

@@ -30,6 +30,25 @@
 #include "msgm_common.cuh"
 #include "tc_ptx.cuh"
 
+// Scheduling options of the tensor-core sampler (compile-time; see the "XU arbitration" notes in the kernel):
+//   MSGM_TC_XULOCK    one activation epilogue at a time per SM sub-partition (FCFS ticket lock on its MUFU pipe)
+//   MSGM_TC_STAGGER   the static MMA schedule runs slot s  s*NLAYER/NSLOT layers behind slot 0
+//   MSGM_TC_PREFETCH  the epilogue loads the next 32 accumulator columns while it works on the current ones
+#ifndef MSGM_TC_XULOCK
+#define MSGM_TC_XULOCK 0
+#endif
+#ifndef MSGM_TC_STAGGER
+#define MSGM_TC_STAGGER 0
+#endif
+#ifndef MSGM_TC_PREFETCH
+#define MSGM_TC_PREFETCH 0
+#endif
+//   MSGM_TC_POLY_PAIRS  of the 16 column pairs of every 32-column accumulator chunk, how many evaluate Swish on the FMA
+//                       pipe (packed-half polynomial, swish_poly_h2) instead of the MUFU pipe (tanh.approx)
+#ifndef MSGM_TC_POLY_PAIRS
+#define MSGM_TC_POLY_PAIRS 0
+#endif
+
 namespace msgm {
 
 constexpr int TM = 128;            // particles per tile (= UMMA M = TMEM lanes)
@@ -55,7 +74,8 @@ struct TcLayout {
   static constexpr int oLG = oG + 4 * DP * DP * DP;            // fp32 [DP][DP]
   static constexpr int oW4f = oLG + 4 * DP * DP;               // fp32 [128][DP] + b4[DP]: CUDA-core output layer
   static constexpr int oBar = ((oW4f + 4 * (128 * DP + DP) + 15) / 16) * 16;  // 1 + 2*NSLOT mbarriers + tmem slot
-  static constexpr int oA = oBar + 128;                        // NSLOT activation tiles
+  static constexpr int oXu = oBar + 128;                       // XU ticket locks: 4 x 4 ring mbarriers + 4 counters
+  static constexpr int oA = oBar + 384;                        // NSLOT activation tiles
   static constexpr bool L4_CC = DP <= 4;                       // output layer on CUDA cores
   static constexpr int NSLOT = DP <= 4 ? 4 : 3;                // tiles in flight per CTA (registers / smem bound)
   static constexpr int THREADS = 128 * NSLOT + 32;             // 4 particle warps per slot + 1 MMA issuer warp
@@ -82,7 +102,7 @@ struct TcParams {
   float* keep_out;
   float* x;
   long long B;
-  int* flags;  // [0] = wait timeout seen
+  TcFlags flags;
   long long* prof;  // NULL or 24 cycle counters (see Prof)
   uint32_t smem_base;  // shared-window address of the dynamic smem block, as a launch-uniform value (see smem_base_probe)
 };
@@ -108,34 +128,137 @@ __device__ __forceinline__ void store_a_chunks(unsigned char* sA, int row, int f
     *reinterpret_cast<uint4*>(base + (first_chunk + i) * 2048) = make_uint4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
 }
 
-// Activation epilogue of one hidden layer for one particle row: D (128 fp32 cols, = z/2) -> Swish -> either packed
-// fp16 into the slot's smem A tile, or (ACC_OUT) straight into the 128->d output layer a_c += W4[n][c] s_n.
+// ---- XU arbitration ------------------------------------------------------------------------------------------------
+// The activation epilogues are MUFU-bound (one tanh per activation, 16 / clk / SM) and every SM sub-partition hosts one
+// warp of every slot.  Left to the warp scheduler, the slots' epilogues share the sub-partition's MUFU pipe fairly, finish
+// together, and then all wait for their next MMA at the same time: the pipe idles for a full MMA round trip per layer
+// (measured round 1: XU 73 % busy at d = 8).  A FCFS ticket lock per sub-partition lets ONE epilogue run at full rate
+// while the other slots' MMAs are in flight, which staggers the slots instead.  Ticket t waits on ring[t % 4] (phase
+// parity (t / 4) & 1); releasing ticket t arrives on ring[(t + 1) % 4]; at most NSLOT <= 4 tickets are outstanding.
+struct XuLock {
+  uint64_t* ring;      // this sub-partition's 4 mbarriers (count 1; ring[0] pre-arrived at setup)
+  uint32_t* next;      // this sub-partition's ticket counter
+  uint32_t ticket;
+  __device__ __forceinline__ bool acquire(int lane, const TcFlags& flags) {
+#if MSGM_TC_XULOCK
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(next, 1u);
+    ticket = __shfl_sync(0xffffffffu, t, 0);
+    return mbar_wait(ring + (ticket & 3u), (ticket >> 2) & 1u, flags);
+#else
+    return true;
+#endif
+  }
+  __device__ __forceinline__ void release(int lane) {
+#if MSGM_TC_XULOCK
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ring + ((ticket + 1u) & 3u));
+#endif
+  }
+};
+
+#define TMEM_WAIT_LD_FENCE32(r)                                                                                      \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                     \
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),      \
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), \
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),          \
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),          \
+                 "+r"(r[30]), "+r"(r[31])                                                                            \
+               :                                                                                                    \
+               : "memory")
+
+// Swish of two pre-activations on the FMA pipe, in packed half precision (no MUFU):
+//   z sigmoid(z) = h + h tanh(h) = 2 max(h, 0) - e(|h|),  h = z/2,  e(u) = u (1 - tanh u)
+// e is a bump (max 0.28 at u = 0.64, < 1.2e-3 beyond u = 4.5) evaluated as a degree-9 polynomial in x = 2 min(|h|, U) / U - 1
+// by Horner in fp16 (coefficients O(1) in this basis).  tools/swish_poly_fit.py derives the constants and checks every
+// fp16 input: max |err| 2.7e-3 (at |h| = 4, where the fp16 spacing of the result is 7.8e-3), at most 1.3e-3 above the
+// rounding of the exact value, mean 3.5e-4 for |h| < 4 -- the same order as the fp16 operand rounding of the next layer.
+// One MUFU op costs 8 issue cycles of a sub-partition's XU pipe; this costs ~8 FMA/ALU-pipe instructions per activation,
+// which run beside the tanh stream of the other columns.
+__device__ __forceinline__ uint32_t swish_poly_h2(float h0, float h1) {
+  constexpr uint32_t C[10] = {0x2A5D2A5Du, 0xB177B177u, 0x34013401u, 0xB28EB28Eu, 0x30433043u,
+                              0x30A530A5u, 0xB927B927u, 0x37383738u, 0x32C132C1u, 0xB30DB30Du};
+  auto H2 = [](uint32_t b) { return *reinterpret_cast<const __half2*>(&b); };
+  const __half2 hh = __floats2half2_rn(h0, h1);
+  const __half2 u = __hmin2(__habs2(hh), H2(0x44804480u));                  // min(|h|, 4.5)
+  const __half2 x = __hfma2(u, H2(0x371C371Cu), H2(0xBC00BC00u));           // 2u/U - 1
+  __half2 p = H2(C[9]);
+#pragma unroll
+  for (int k = 8; k >= 0; --k) p = __hfma2(p, x, H2(C[k]));
+  const __half2 r = __hmax2(hh, H2(0u));
+  const __half2 s = __hfma2(r, H2(0x40004000u), __hneg2(p));                // 2 max(h,0) - e
+  return *reinterpret_cast<const uint32_t*>(&s);
+}
+
+// 32 accumulator columns (= z/2) of one particle row -> Swish -> either packed fp16 into the slot's smem A tile (k-chunks
+// 4c..4c+3), or (ACC_OUT) straight into the 128->d output layer a_e += W4[n][e] s_n.
 template <int DP, bool ACC_OUT>
-__device__ __forceinline__ void swish_epilogue(uint32_t taddr, unsigned char* sA, int row, const float* __restrict__ sW4f,
-                                               float* a) {
+__device__ __forceinline__ void swish_chunk(const uint32_t* r, int c, unsigned char* sA, int row,
+                                            const float* __restrict__ sW4f, float* a) {
+  uint32_t q[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float h0 = __uint_as_float(r[2 * j]), h1 = __uint_as_float(r[2 * j + 1]);
+    float s0, s1;
+    if (j >= 16 - MSGM_TC_POLY_PAIRS) {  // FMA-pipe branch (compile-time choice of columns)
+      q[j] = swish_poly_h2(h0, h1);
+      if constexpr (ACC_OUT) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&q[j]));
+        s0 = f.x;
+        s1 = f.y;
+      } else {
+        continue;
+      }
+    } else {
+      s0 = fmaf(h0, tanh_fast(h0), h0);  // z sigmoid(z) with z = 2h   (NN.py:52-53)
+      s1 = fmaf(h1, tanh_fast(h1), h1);
+    }
+    if constexpr (ACC_OUT) {
+      const int n = c * 32 + 2 * j;
+#pragma unroll
+      for (int e = 0; e < DP; ++e) {
+        a[e] = fmaf(sW4f[n * DP + e], s0, a[e]);
+        a[e] = fmaf(sW4f[(n + 1) * DP + e], s1, a[e]);
+      }
+    } else {
+      q[j] = pack_f16x2(s0, s1);
+    }
+  }
+  if constexpr (!ACC_OUT) store_a_chunks(sA, row, 4 * c, q);
+}
+
+// Activation epilogue of one hidden layer for one particle row: D (128 fp32 cols) -> Swish -> next operand / output layer.
+// The sub-partition's XU lock is taken after the first TMEM load is in flight and dropped once the last tanh is issued.
+template <int DP, bool ACC_OUT>
+__device__ __forceinline__ bool swish_epilogue(uint32_t taddr, unsigned char* sA, int row, const float* __restrict__ sW4f,
+                                               float* a, XuLock& xu, int lane, const TcFlags& flags) {
+#if MSGM_TC_PREFETCH
+  uint32_t ra[32], rb[32];
+  TMEM_LD32(taddr, ra);
+  const bool ok = xu.acquire(lane, flags);
+  TMEM_WAIT_LD_FENCE32(ra);
+  TMEM_LD32(taddr + 32, rb);
+  swish_chunk<DP, ACC_OUT>(ra, 0, sA, row, sW4f, a);
+  TMEM_WAIT_LD_FENCE32(rb);
+  TMEM_LD32(taddr + 64, ra);
+  swish_chunk<DP, ACC_OUT>(rb, 1, sA, row, sW4f, a);
+  TMEM_WAIT_LD_FENCE32(ra);
+  TMEM_LD32(taddr + 96, rb);
+  swish_chunk<DP, ACC_OUT>(ra, 2, sA, row, sW4f, a);
+  TMEM_WAIT_LD_FENCE32(rb);
+  swish_chunk<DP, ACC_OUT>(rb, 3, sA, row, sW4f, a);
+#else
+  const bool ok = xu.acquire(lane, flags);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    uint32_t r[32], q[16];
+    uint32_t r[32];
     TMEM_LD32(taddr + c * 32, r);
     tc_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float h0 = __uint_as_float(r[2 * j]), h1 = __uint_as_float(r[2 * j + 1]);
-      const float s0 = fmaf(h0, tanh_fast(h0), h0);  // z sigmoid(z) with z = 2h   (NN.py:52-53)
-      const float s1 = fmaf(h1, tanh_fast(h1), h1);
-      if constexpr (ACC_OUT) {
-        const int n = c * 32 + 2 * j;
-#pragma unroll
-        for (int e = 0; e < DP; ++e) {
-          a[e] = fmaf(sW4f[n * DP + e], s0, a[e]);
-          a[e] = fmaf(sW4f[(n + 1) * DP + e], s1, a[e]);
-        }
-      } else {
-        q[j] = pack_f16x2(s0, s1);
-      }
-    }
-    if constexpr (!ACC_OUT) store_a_chunks(sA, row, 4 * c, q);
+    swish_chunk<DP, ACC_OUT>(r, c, sA, row, sW4f, a);
   }
+#endif
+  xu.release(lane);
+  return ok;
 }
 
 // CONST_BASE: the dynamic shared memory block starts at shared-window address 1024 (verified at run time), which turns
@@ -153,6 +276,8 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
   uint64_t* bar_a = bar_w + 1;          // [NSLOT] operand of the slot's next layer is in smem, D consumed
   uint64_t* bar_d = bar_a + NSLOT;      // [NSLOT] the slot's accumulator is complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + NSLOT);
+  uint64_t* xu_ring = reinterpret_cast<uint64_t*>(smem + L::oXu);          // [4 sub-partitions][4]
+  uint32_t* xu_next = reinterpret_cast<uint32_t*>(smem + L::oXu + 128);    // [4]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = P.d;
@@ -167,7 +292,12 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
       mbar_init(bar_a + sl, 128);
       mbar_init(bar_d + sl, 1);
     }
+    for (int q = 0; q < 4; ++q) {
+      for (int i = 0; i < 4; ++i) mbar_init(xu_ring + 4 * q + i, 1);
+      xu_next[q] = 0u;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int q = 0; q < 4; ++q) mbar_arrive(xu_ring + 4 * q);  // ticket 0 of every sub-partition may go
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -225,7 +355,7 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
     const uint32_t sbase = CONST_BASE ? 1024u : P.smem_base;
     bool ok = mbar_wait(bar_w, 0, P.flags);
     if (tbase != 0u || sbase != smem_u32(smem)) {
-      if (lane == 0) atomicExch(P.flags, 2);
+      if (lane == 0) tc_raise(P.flags, 2);
       ok = false;
     }
     const uint32_t idesc_h = umma_idesc_f16(128, 128), idesc_o = umma_idesc_f16(128, 16);
@@ -245,32 +375,37 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
     // fixed order costs nothing, while the issue code stays free of data-dependent branches: the warp is converged at
     // every tcgen05.mma, descriptors are launch-uniform, and ptxas feeds them from uniform registers (measured with
     // tools/tc_probe.cu: 74 clk per MMA issued this way vs 96-113 from a single-lane branch).
-    long long iters[NSLOT];
-    long long max_iters = 0;
+    // With MSGM_TC_STAGGER slot s runs OFF(s) = s * NLAYER / NSLOT layers behind slot 0, so that the long MUFU-free part
+    // of one slot's stage (output layer round trip, SDE update, layer-1 round trip) falls on the other slots' epilogues.
+    long long nlay[NSLOT];   // layers this slot issues in total
+    long long kend = 0;      // global schedule length
 #pragma unroll
     for (int sl = 0; sl < NSLOT; ++sl) {
       const long long first = (long long)blockIdx.x * NSLOT + sl;
       const long long nt = first < ntiles ? (ntiles - first + tstride - 1) / tstride : 0;
-      iters[sl] = nt * P.N * nstage;
-      max_iters = iters[sl] > max_iters ? iters[sl] : max_iters;
+      nlay[sl] = nt * P.N * nstage * NLAYER;
+      const long long e = nlay[sl] + (MSGM_TC_STAGGER ? (sl * NLAYER) / NSLOT : 0);
+      kend = e > kend ? e : kend;
     }
-    uint32_t par = 0;  // all slot barriers flip once per layer, in lock step with this loop
-    for (long long it = 0; it < max_iters && ok; ++it) {
+    for (long long it = 0; it * NLAYER < kend && ok; ++it) {
 #pragma unroll
       for (int layer = 0; layer < NLAYER; ++layer) {
 #pragma unroll
         for (int sl = 0; sl < NSLOT; ++sl) {
-          if (it < iters[sl] && ok) {
-            ok = mbar_wait(bar_a + sl, par, P.flags);
+          const int off = MSGM_TC_STAGGER ? (sl * NLAYER) / NSLOT : 0;          // compile-time after unrolling
+          const int lay = ((layer - off) % NLAYER + NLAYER) % NLAYER;            // which layer of the net this is
+          const long long n = it * NLAYER + layer - off;                         // layers of this slot issued so far
+          if (n >= 0 && n < nlay[sl] && ok) {
+            ok = mbar_wait(bar_a + sl, (uint32_t)(n & 1), P.flags);
             tc_fence_after();
             pf.tick(0);  // waiting for an operand
             const uint32_t dcol = tb + 128 * sl;
             const uint64_t a_desc = umma_desc(sbase + L::oA + sl * A_BYTES, 2048, 128);
-            if (layer == 0) {  // layer 1: K1/16 slices, bias rides in the padding of the last one
+            if (lay == 0) {  // layer 1: K1/16 slices, bias rides in the padding of the last one
 #pragma unroll
               for (int s = 0; s < K1 / 16; ++s) umma_ss(dcol, a_desc + s * 256, w1_desc + s * 256, idesc_h, s > 0, lead);
-            } else if (layer < 3) {  // layers 2, 3: ones-slice (bias) + 8 slices
-              const uint64_t w_desc = layer == 1 ? w2_desc : w3_desc;
+            } else if (lay < 3) {  // layers 2, 3: ones-slice (bias) + 8 slices
+              const uint64_t w_desc = lay == 1 ? w2_desc : w3_desc;
               umma_ss(dcol, ones_desc, w_desc, idesc_h, 0, lead);
 #pragma unroll
               for (int s = 0; s < 8; ++s) umma_ss(dcol, a_desc + s * 256, w_desc + (s + 1) * 256, idesc_h, 1, lead);
@@ -288,7 +423,6 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
             pf.tick(1);  // issue
           }
         }
-        par ^= 1;
       }
     }
     __syncwarp();
@@ -308,6 +442,7 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
     const float c_a = delta * (1.0f - 0.5f * lm);
     uint32_t pd = 0;
     bool ok = true;
+    XuLock xu{xu_ring + 4 * (warp & 3), xu_next + (warp & 3), 0u};
     Prof pf{(P.prof && blockIdx.x == 0 && tid == 0) ? P.prof : nullptr, 0};
     pf.start();
 
@@ -413,24 +548,24 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
           float a[DP];
 #pragma unroll
           for (int c = 0; c < DP; ++c) a[c] = L4_CC ? sW4f[128 * DP + c] : 0.0f;
+          // One copy of the 128-activation epilogue in the instruction stream wherever possible: the kernel is ~100 KB
+          // of SASS and the warps of a CTA sit in different phases, so code size shows up as instruction-fetch stalls.
 #pragma unroll 1
-          for (int l = 0; l < 2; ++l) {
+          for (int l = 0; l < (L4_CC ? 2 : 3); ++l) {
             ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
             pf.tick(1);  // wait for the accumulator
-            swish_epilogue<DP, false>(taddr, sA, row, sW4f, a);
+            ok = swish_epilogue<DP, false>(taddr, sA, row, sW4f, a, xu, lane, P.flags) && ok;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             mbar_arrive(my_a);
             pf.tick(2);  // epilogue
           }
-          ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
-          pf.tick(1);
-          swish_epilogue<DP, L4_CC>(taddr, sA, row, sW4f, a);
-          pf.tick(2);
-          if (!L4_CC) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tc_fence_before();
-            mbar_arrive(my_a);
+          if constexpr (L4_CC) {  // third hidden layer: activations go straight into the CUDA-core output layer
+            ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
+            pf.tick(1);
+            ok = swish_epilogue<DP, true>(taddr, sA, row, sW4f, a, xu, lane, P.flags) && ok;
+            pf.tick(2);
+          } else {
             ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
             uint32_t r[16];
             TMEM_LD16(taddr, r);
@@ -667,14 +802,16 @@ static int ensure_ws(msgm_ctx* ctx, size_t need) {
 template <int DP, int KIND>
 static int launch_tc(msgm_ctx* ctx, const msgm_mlp_desc* m, TcParams& P, cudaStream_t stream) {
   using L = TcLayout<DP>;
-  const size_t need = 256 + (size_t)L::IMG_BYTES;
-  int rc = ensure_ws(ctx, need);
+  int rc = ensure_ws(ctx, 256);
   if (rc) return rc;
-  P.flags = reinterpret_cast<int*>(ctx->ws);
+  P.flags = next_tc_flags(ctx);
   P.prof = std::getenv("MSGM_TC_PROF") ? reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(ctx->ws) + 64) : nullptr;
-  unsigned char* img = reinterpret_cast<unsigned char*>(ctx->ws) + 256;
+  if (P.prof) MSGM_CUDA_TRY(cudaMemsetAsync(P.prof, 0, 192, stream));
+  // The packed fp16 weight image is a stream-ordered allocation of THIS call (freed behind the sampler kernel), so calls
+  // on different streams of one context -- different nets, different dimensions -- never share it.
+  unsigned char* img = nullptr;
+  MSGM_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&img), (size_t)L::IMG_BYTES, stream));
   P.img = img;
-  MSGM_CUDA_TRY(cudaMemsetAsync(ctx->ws, 0, 256, stream));
   const int nel = L::IMG_BYTES / 2;
   pack_mlp_tc_kernel<DP><<<(nel + 255) / 256, 256, 0, stream>>>(P.d, P.pre, m->W[0], m->b[0], m->W[1], m->b[1], m->W[2],
                                                                 m->b[2], m->W[3], m->b[3],
@@ -692,6 +829,7 @@ static int launch_tc(msgm_ctx* ctx, const msgm_mlp_desc* m, TcParams& P, cudaStr
   kern<<<grid, L::THREADS, L::SMEM_BYTES, stream>>>(P);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
+  MSGM_CUDA_TRY(cudaFreeAsync(img, stream));
   return MSGM_OK;
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include "msgm_common.cuh"
+
 namespace msgm {
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
@@ -27,17 +29,38 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: returns false (and raises the debug flag) instead of hanging if the partner never arrives.
-// Normal waits last microseconds; the limit is ~0.2 s, and a raised flag makes every other waiter bail out at once.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* flags) {
+// Error reporting of the tensor-core kernels.  `abort` is a device word holding the id of the launch that gave up (so a
+// stale value from an earlier launch never makes a later one bail out, and nothing has to be cleared per launch);
+// `sticky` is a word in mapped pinned HOST memory that receives the error code: the host reads it at its next API call
+// without synchronising (msgm_async_error) and raises.  Codes: 1 = a bounded mbarrier wait timed out, 2 = shared-memory /
+// TMEM base assumption violated.
+struct TcFlags {
+  int* abort;
+  volatile int* sticky;
+  int id;
+};
+// Host side: the flags of the next tensor-core launch of this context.
+inline TcFlags next_tc_flags(msgm_ctx* ctx) {
+  ctx->launch_seq = ctx->launch_seq == 0x7fffffff ? 1 : ctx->launch_seq + 1;
+  return TcFlags{reinterpret_cast<int*>(ctx->ws), ctx->host_flag_dev, ctx->launch_seq};
+}
+__device__ __forceinline__ void tc_raise(const TcFlags& f, int code) {
+  atomicExch(f.abort, f.id);
+  *f.sticky = code;
+  __threadfence_system();
+}
+// Bounded wait: returns false (and raises the error) instead of hanging if the partner never arrives.
+// Normal waits last microseconds; the limit is ~0.2 s, and a raised abort word makes every other waiter of the same launch
+// bail out at once.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, const TcFlags& f) {
   if (mbar_try(bar, parity)) return true;
   const long long t0 = clock64();
   int spins = 0;
   while (clock64() - t0 < 400000000LL) {
     if (mbar_try(bar, parity)) return true;
-    if ((++spins & 255) == 0 && *reinterpret_cast<volatile int*>(flags) != 0) return false;
+    if ((++spins & 255) == 0 && *reinterpret_cast<volatile int*>(f.abort) == f.id) return false;
   }
-  atomicExch(flags, 1);
+  tc_raise(f, 1);
   return false;
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

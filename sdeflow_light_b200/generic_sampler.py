@@ -24,6 +24,7 @@ def run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, incl
     base, net, fwd = _describe(sde)
     device = sde.T.device
     handle, L = _lib.ctx(device), _lib.lib()
+    _lib.check_async(device)
     stream = _lib.stream_ptr(device)
     B, d = x_0.size(0), x_0.size(1)
     sd, keep_alive = base.desc(device)
@@ -80,6 +81,10 @@ def run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, incl
             traj[i + (1 if include_t0 else 0)].copy_(x)
         elif keep_step is not None:
             m = keep_step == (i + (1 if include_t0 else 0))
-            keep_out[m] = x[m]
+            torch.where(m[:, None], x, keep_out, out=keep_out)  # no nonzero(): no host sync inside the loop
     out = traj if keep_all_samples else (keep_out if samplesToKeep is not None else x)
-    return out if device_out else out.to("cpu")
+    if device_out:
+        return out
+    out = out.to("cpu")
+    _lib.check_async(device)  # the copy synchronised: every conv / attention launch of this call has reported by now
+    return out

@@ -260,7 +260,7 @@ class UNetModel(nn.Module):
         C2 = 0 if x2 is None else x2.shape[1]
         Cout, K = W.shape[0], W.shape[-1]
         cache = self.__dict__.setdefault("_tc_wimg", {})
-        key = (W.data_ptr(), conv.weight._version, tuple(W.shape), dev.index)
+        key = (W.data_ptr(), conv.weight._version, _lib.weight_epoch(), tuple(W.shape), dev.index)
         ent = cache.get(W.data_ptr())
         if ent is None or ent[0] != key:
             nbytes = L.msgm_conv2d_tc_pack_bytes(Cout, C1 + C2, K)
@@ -289,7 +289,7 @@ class UNetModel(nn.Module):
         if not blocks or len(blocks) > 64 or emb.shape[1] > 8192:
             return None
         lins = [b_.emb_layers[1] for b_ in blocks]
-        ver = tuple((l.weight._version, l.bias._version, l.weight.data_ptr()) for l in lins) + (dev.index,)
+        ver = tuple((l.weight._version, l.bias._version, l.weight.data_ptr()) for l in lins) + (dev.index, _lib.weight_epoch())
         ent = self.__dict__.get("_emb_stack")
         if ent is None or ent[0] != ver:
             Wc = torch.cat([_lib.f32c(l.weight, dev) for l in lins], 0).contiguous()

@@ -54,6 +54,7 @@ def _run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, inc
     base, net, fwd = _describe(sde)
     device = sde.T.device
     handle = _lib.ctx(device)  # RuntimeError on CPU: there is no CPU fallback
+    _lib.check_async(device)   # a tensor-core launch that gave up earlier surfaces here (no synchronisation)
     B, d = x_0.size(0), x_0.size(1)
     T_run = _lib.host_float(sde, "T") if (not torch.is_tensor(T_) and T_ == -1) else T_.item()
     if keep_all_samples is False and samplesToKeep is not None and len(samplesToKeep) != B:
@@ -69,6 +70,7 @@ def _run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, inc
         out = x.new_zeros((n_out, 0, d)) if keep_all_samples else x
         return out if device_out else out.to("cpu")
     sd, keep_alive = base.desc(device)
+    sd.dim = d  # SGMsde, like the reference's, has no `dim` attribute: the state width is the batch's
     a = _lib.SampleArgs()
     a.scheme, a.num_steps, a.lmbd = scheme, int(num_steps), float(lmbd)
     a.norm_correction, a.include_t0, a.forward_only = int(bool(norm_correction)), int(bool(include_t0)), int(fwd)
@@ -105,7 +107,11 @@ def _run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, inc
     _lib.check(_lib.lib().msgm_sample_mlp(handle, C.byref(sd), md, C.byref(a), _lib.ptr(x), B,
                                           _lib.stream_ptr(device)))
     out = traj if keep_all_samples else (keep_out if samplesToKeep is not None else x)
-    return out if device_out else out.to("cpu")  # reference samplers always return CPU tensors (:99,172,269)
+    if device_out:
+        return out
+    out = out.to("cpu")  # reference samplers always return CPU tensors (:99,172,269)
+    _lib.check_async(device)  # the copy synchronised: this call's own kernel has reported by now
+    return out
 
 
 @torch.no_grad()

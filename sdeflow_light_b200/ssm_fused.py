@@ -23,6 +23,7 @@ class _SsmMlp(torch.autograd.Function):
         base, net = gen.base_sde, gen.a
         B = y.shape[0]
         sd, keep = base.desc(dev)
+        sd.dim = y.shape[1]  # SGMsde has no dim of its own
         md, k2 = net.desc(dev)
         yc, vc, tc = _lib.f32c(y, dev), _lib.f32c(v, dev), _lib.f32c(t.reshape(-1), dev)
         loss = torch.empty(B, device=dev, dtype=torch.float32)
@@ -41,6 +42,7 @@ class _SsmMlp(torch.autograd.Function):
         gen = ctx.gen
         base, net = gen.base_sde, gen.a
         sd, keep = base.desc(dev)
+        sd.dim = yc.shape[1]
         md, k2 = net.desc(dev)
         n = sum(int(torch.Size(s).numel()) for s in ctx.shapes)
         flat = torch.empty(n, device=dev, dtype=torch.float32)

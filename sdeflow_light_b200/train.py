@@ -66,8 +66,9 @@ class GraphedSsmStep:
         self._iter = torch.zeros(1, device=dev, dtype=torch.int64)
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._old_rng = getattr(gen, "_rng", None)
-        gen._rng = (int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed), self._iter,
-                    rank * int(batch_shape[0]))
+        self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
+        self._row_offset = rank * int(batch_shape[0])
+        gen._rng = (self._seed, self._iter, self._row_offset)
         # MLP score nets: forward and backward kernels back to back, gradients written straight into the flat buffer
         from . import NN, SDEs
         self._direct = (isinstance(gen.a, NN.MLP) and gen.a.fused_ok() and len(batch_shape) == 2 and batch_shape[1] <= 32
@@ -141,6 +142,18 @@ class GraphedSsmStep:
         self.loss.copy_(loss.detach())
         self._iter.add_(1)
 
+    # -- resumable random stream ---------------------------------------------------------------------------------
+    def rng_state(self) -> dict:
+        """Philox seed and device iteration counter of the recorded draws (t, noise, v).  Store it next to the model
+        checkpoint (``NN.save_checkpoint(..., trainer=step)``): a run resumed with ``load_rng_state`` continues the random
+        stream instead of repeating it from iteration 0."""
+        return {"seed": int(self._seed), "iter": int(self._iter.item()), "row_offset": int(self._row_offset)}
+
+    def load_rng_state(self, state: dict) -> None:
+        if int(state["seed"]) != int(self._seed):
+            raise ValueError("the Philox seed is baked into the recorded graphs: build GraphedSsmStep(seed=state['seed'])")
+        self._iter.fill_(int(state["iter"]))
+
     def set_lr(self, lr: float):
         """Change the learning rate seen by the recorded Adam update (in place, on the device)."""
         for g in self.opt.param_groups:
@@ -160,4 +173,7 @@ class GraphedSsmStep:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat /= self.world  # Adam reads the averaged gradient through the .grad views
             self.g_opt.replay()
+        # the replayed Adam wrote the parameters without bumping Tensor._version: invalidate every weight-derived cache
+        # (packed tensor-core images, captured inference graphs) so that the next sample / evaluate sees live weights
+        _lib.bump_weight_epoch()
         return self.loss

@@ -27,7 +27,6 @@ def base_from(meta, arr, device, n_fwd=None):
               num_steps_forward=n_fwd or meta.get("num_steps_forward", 16), device=device)
     if kind == "sgm":
         base = P.SGMsde(**kw)
-        base.dim = d
     else:
         base = P.MSGMsde(torch.randn(8, d), denseTensor=(kind == "msgm_dense"), norm_sampler="ecdf", norm_map="log",
                          estim_cst_norm_dens_r_T=False, **kw)

@@ -48,7 +48,6 @@ def test_no_cpu_fallback():
     assert rc == _lib.ERR_NO_DEVICE and b"no CPU fallback" in _lib.lib().msgm_last_error()
     T = torch.nn.Parameter(torch.FloatTensor([1.0]), requires_grad=False)
     base = P.SGMsde(T=T, device="cpu")
-    base.dim = 2
     gen = P.PluginReverseSDE(base, P.MLP(2), T)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         P.rk4_stratonovich_sampler(gen, torch.zeros(4, 2), 2)

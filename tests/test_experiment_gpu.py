@@ -40,7 +40,6 @@ def test_reduced_default_experiment_matches_reference(kind):
         base.G, base.L_G = arr["G"].to(DEV), arr["L_G"].to(DEV)
     else:
         base = P.SGMsde(beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, num_steps_forward=16, device=DEV)
-        base.dim = 2
     net = P.MLP(2, premodule="NormalizeLogRadius" if msgm else None)
     net.load_state_dict({k[4:]: v for k, v in arr.items() if k.startswith("sd0.")})
     gen = P.PluginReverseSDE(base, net.to(DEV), T, deviceReverseSDE=DEV).to(DEV)

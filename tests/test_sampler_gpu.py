@@ -126,7 +126,6 @@ def test_philox_noise_is_standard_normal():
     """Forward SGM with beta -> sqrt(beta) dW only: one EM step of the forward SDE exposes the in-kernel normals."""
     d, B = 4, 400_000
     base = P.SGMsde(beta_min=1.0, beta_max=1.0, T=Bd.T_param(1.0), device=DEV)
-    base.dim = d
     fwd = P.forward_SDE(base, base.T.to(DEV))
     x = P.euler_maruyama_sampler(fwd, torch.zeros(B, d, device=DEV), 1, keep_all_samples=False, seed=7,
                                  device_out=True)  # x = sqrt(beta) sqrt(delta) xi = xi

@@ -86,7 +86,6 @@ def test_ssm_end_to_end_trains():
             net = P.MLP(d, premodule="NormalizeLogRadius").to(DEV)
         else:
             base = P.SGMsde(beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, num_steps_forward=16, device=DEV)
-            base.dim = d
             net = P.MLP(d).to(DEV)
         gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
         opt = torch.optim.Adam(gen.parameters(), lr=2e-3)
@@ -128,7 +127,6 @@ def test_graphed_train_step_matches_eager_and_trains():
                 net = P.MLP(d, premodule="NormalizeLogRadius").to(DEV)
             else:
                 base = P.SGMsde(beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, num_steps_forward=16, device=DEV)
-                base.dim = d
                 net = P.MLP(d).to(DEV)
             return P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
 
@@ -186,7 +184,6 @@ def test_ssm_prepare_kernel(kind, d):
     T = Bd.T_param(1.0)
     if kind == "sgm":
         base = P.SGMsde(beta_min=0.1, beta_max=20., T=T, t_epsilon=0.05, num_steps_forward=16, device=DEV)
-        base.dim = d
         net = P.MLP(d).to(DEV)
     else:
         base = P.MSGMsde(torch.randn(64, d), beta_min=0.1, beta_max=20., T=T, t_epsilon=0.05,

@@ -17,7 +17,6 @@ DEV = "cuda:0"
 
 def _unet_gen(meta, arr):
     base, T = Bd.base_from(meta, arr, DEV)
-    base.dim = meta["dim"]
     net = P.UNet1D(input_dim=meta["dim"], base_channels=meta["base_channels"], channel_mults=(1, 2, 4), num_res_blocks=2,
                    premodule="NormalizeLogRadius" if meta["premodule"] else None, emb_dim=meta["emb_dim"])
     sd = {k[3:]: v for k, v in arr.items() if k.startswith("sd.")}
@@ -108,7 +107,6 @@ def _build_unet2d(S, pre, order, seed):
 def test_unet2d_forward_sampler_ssm(name):
     meta, arr = G.load(name)
     base, T = Bd.base_from(meta, arr, DEV)
-    base.dim = meta["dim"]
     net = _build_unet2d(meta["in_space"], "NormalizeLogRadius" if meta["premodule"] else None, meta["flatten_order"],
                         meta["seed"])
     assert [k for k, _ in net.named_parameters()] == meta["param_names"]  # the reference's checkpoint keys
@@ -214,6 +212,42 @@ def test_unet2d_cuda_graph_replay_tracks_weight_updates():
         net.cuda_graph = True
         g2 = net(x, t)
         assert torch.equal(g2, e2) and not torch.equal(g2, g1)
+
+
+@pytest.mark.parametrize("which", ["unet1d", "unet2d"])
+def test_inference_caches_follow_graph_replayed_training(which):
+    """Adam inside a replayed CUDA graph (train.GraphedSsmStep) does not bump Tensor._version.  The packed tensor-core
+    weight images and the captured inference graph must still be refreshed: infer, train a few replayed iterations, infer
+    again, and compare with the torch-module forward on the live weights."""
+    from sdeflow_light_b200.train import GraphedSsmStep
+    torch.manual_seed(11)
+    if which == "unet1d":
+        d, Bt = 64, 8
+        net = P.UNet1D(d, premodule="NormalizeLogRadius").to(DEV)
+    else:
+        d, Bt = 256, 4
+        net = _build_unet2d(16, "NormalizeLogRadius", "F", 5).to(DEV)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(torch.randn(64, d), beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=4, device=DEV, estim_cst_norm_dens_r_T=False)
+    gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
+    x, t = torch.randn(6, d, device=DEV), torch.rand(6, device=DEV)
+    gen.eval()
+    with torch.no_grad():
+        before = net(x, t).clone()
+    step = GraphedSsmStep(gen, (Bt, d), lr=1e-2)
+    xs = torch.randn(Bt, d, device=DEV)
+    for _ in range(3):
+        step(xs)
+    gen.eval()
+    with torch.no_grad():
+        after = net(x, t)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            ref = net._forward(x, t)
+    assert not torch.allclose(after, before, atol=1e-6), "training did not move the net: the test proves nothing"
+    err = _rel(after, ref.cpu())
+    Bd.report(test="inference_after_graph_training", which=which, rel=err)
+    assert err < 2e-5, err
 
 
 @pytest.mark.parametrize("which", ["unet1d", "unet2d"])

@@ -2,20 +2,26 @@
 """Headline benchmark: reverse-SDE sampling throughput (particle-steps/s) of the MSGM hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dim D] [--precision P]
+                    [--particles B] [--sde-steps N]
 
-Workload (BASELINE.json configs[1]): synthetic higher-dimensional Gaussian-mixture data, MLP score net
-(NN.py, hidden 128, NormalizeLogRadius), dense multiplicative SDE, 2^20 particles per GPU, RK4-Stratonovich with
-128 reverse steps, lambda = 0, radius correction on, final state only (keep_all_samples=False).  One bench "step"
-is one full sampler call over the batch.  Weights are random-init (no checkpoints offline), data synthetic.
+Workload (default = BASELINE.json configs[4], the configuration the metric's 1/2/4/8-GPU sweep is quoted on; it fits one
+GPU): MLP score net (NN.py, hidden 128, NormalizeLogRadius) on synthetic higher-dimensional Gaussian-mixture data (d = 8),
+dense multiplicative SDE, 10^7 particles per GPU, RK4-Stratonovich with 1000 reverse steps, lambda = 0, radius correction
+on, final state only (keep_all_samples=False).  One bench "step" is one full sampler call over the batch.  Weights are
+random-init (no checkpoints offline), data synthetic.  BASELINE.json configs[1] (2^20 particles x 128 steps) is timed in
+the same run and reported under ``config2``; ``--particles 1048576 --sde-steps 128`` makes it the headline instead.
 
 * ``value``      whole-job particle-steps/s with x_0 already resident in HBM (kernel launch -> completion).
 * ``e2e``        the same through the public API ``rk4_stratonovich_sampler`` with HOST buffers: pinned x_0 H2D
-                 and the final states D2H are inside the timed region.
+                 and the final states D2H are inside the timed region.  ``e2e_stock``: the unmodified drop-in call
+                 (CPU tensor in, CPU tensor out) as the reference driver issues it (MSGM_higherDim.py:903-906).
 * ``roofline``   tensor-pipe roofline of the sampler kernel: algorithmic FLOP / CUDA-event duration vs the
-                 measured cuBLAS bf16 peak in MEASURED_PEAKS.json (sustained figure: the kernel runs for >100 ms).
-* ``cpu_baseline`` the CPU oracle port of the reference (oracle/msgm_oracle.py, same ATen op sequence as the
-                 reference) timed on this host on a bounded sample of the same workload.
-* ``--impl reference`` times that CPU port alone, on the same config, as the reference arm.
+                 measured cuBLAS bf16 peak in MEASURED_PEAKS.json (sustained figure: the kernel runs for seconds).
+* ``fp32_parity`` throughput of the fp32 parity mode (``precision="fp32"``, CUDA cores, reference arithmetic) on a bounded
+                 sample of the same workload, next to the f16 tensor-core headline.
+* ``cpu_baseline`` the reference's own CPU implementation (baseline/_ref when present, else the oracle port, which
+                 issues the same ATen op sequence) timed on this host on a bounded sample of the same workload.
+* ``--impl reference`` times that CPU path alone, on the same config, as the reference arm.
 
 Multi-GPU: launched by torchrun, one rank per GPU; particles are sharded (weak scaling, B per GPU fixed), no
 data-path collective; Philox noise is keyed by the global particle index.
@@ -35,8 +41,9 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_SDE_STEPS = 128
-PARTICLES_PER_GPU = 1 << 20
+N_SDE_STEPS = 1000               # BASELINE.json configs[4]
+PARTICLES_PER_GPU = 10_000_000
+CFG2_STEPS, CFG2_PARTICLES = 128, 1 << 20   # BASELINE.json configs[1]
 STAGES = {"em": 1, "heun": 2, "rk4": 4}
 
 
@@ -48,12 +55,13 @@ def flop_per_particle_step(d: int, pre: int, dense: bool, scheme: str = "rk4") -
 
 def load_traffic(workload: str, precision: str):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this exact workload."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.isfile(p):
-        ent = json.load(open(p)).get(f"{workload}/{precision}")
-        if ent:
-            return ent["traffic_bytes"]
-    return None
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.isfile(p):
+            ent = json.load(open(p)).get(f"{workload}/{precision}")
+            if ent:
+                return ent["traffic_bytes"]
+    return None  # no capture of this exact workload: say so rather than quote another one's bytes
 
 
 def load_peaks():
@@ -122,64 +130,117 @@ class ClockSampler:
                 "samples": len(sm), "samples_in_region": n_in}
 
 
-def build_problem(d: int, seed: int = 0):
-    """Synthetic config-2 problem, identical on every rank (CPU tensors): data -> r_T, dense G, MLP weights."""
-    from oracle import msgm_oracle as O  # data + init helpers only; the measured GPU path never calls the oracle
-    torch.manual_seed(seed)
-    data = O.gaussian_mixture(100_000, d, seed=seed)
-    sde = O.make_msgm(data, dense=True, num_steps_forward=16)
-    mlp = O.init_mlp(d, True, seed=seed, scale=6.0)
-    return sde, mlp
+def build_problem(d: int, seed: int = 0) -> dict:
+    """Synthetic config-2/5 problem, identical on every rank (CPU tensors): Gaussian-mixture data (means 3 randn(K,d), shared
+    correlation A = randn(d,d) as the reference's Gaussian(correlation=True), data.py:751-778), the log-radius table, a
+    dense skew-symmetric G scaled to tr(L_G) = -d/2 (SDEs.py:315-341) and nn.Linear-style random weights with the output
+    layer widened x6 so that the untrained net produces an O(1) drift."""
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(d, d, generator=g)
+    mu = 3.0 * torch.randn(8, d, generator=g)
+    c = torch.randint(0, 8, (100_000,), generator=g)
+    data = (torch.randn(100_000, d, generator=g) @ A.T) * 0.3 + mu[c]
+    F = torch.stack([torch.randn(d, d, generator=g) for _ in range(d)], dim=2)
+    G = 0.5 * (F - F.transpose(0, 1))
+    G = torch.sqrt(-0.5 * d / torch.trace(0.5 * torch.einsum("ijk,jmk->im", G, G))) * G
+    sizes = [d + 2, 128, 128, 128, d]
+    W, b = [], []
+    for l in range(4):
+        k = 1.0 / sizes[l] ** 0.5
+        W.append((torch.rand(sizes[l + 1], sizes[l], generator=g) * 2 - 1) * k * (6.0 if l == 3 else 1.0))
+        b.append((torch.rand(sizes[l + 1], generator=g) * 2 - 1) * k * (6.0 if l == 3 else 1.0))
+    return dict(dim=d, data=data, G=G, L_G=0.5 * torch.einsum("ijk,jmk->im", G, G),
+                r_T=torch.log(torch.linalg.norm(data, dim=1) + 1e-6), W=W, b=b, beta_min=0.1, beta_max=20.0, T=1.0,
+                t_epsilon=1e-3, num_steps_forward=16)
 
 
-def package_objects(sde, mlp, device):
+def package_objects(prob, device):
     import sdeflow_light_b200 as P
-    T = torch.nn.Parameter(torch.FloatTensor([sde.T]), requires_grad=False)
-    base = P.MSGMsde(torch.randn(8, sde.dim), beta_min=sde.beta_min, beta_max=sde.beta_max, T=T,
-                     t_epsilon=sde.t_epsilon, denseTensor=True, norm_sampler="ecdf", norm_map="log",
-                     num_steps_forward=sde.num_steps_forward, device=device, estim_cst_norm_dens_r_T=False)
-    base.G, base.L_G, base.r_T = sde.G.to(device), sde.L_G.to(device), sde.r_T.to(device)
-    net = P.MLP(input_dim=sde.dim, premodule="NormalizeLogRadius")
+    d = prob["dim"]
+    T = torch.nn.Parameter(torch.FloatTensor([prob["T"]]), requires_grad=False)
+    base = P.MSGMsde(torch.randn(8, d), beta_min=prob["beta_min"], beta_max=prob["beta_max"], T=T,
+                     t_epsilon=prob["t_epsilon"], denseTensor=True, norm_sampler="ecdf", norm_map="log",
+                     num_steps_forward=prob["num_steps_forward"], device=device, estim_cst_norm_dens_r_T=False)
+    base.G, base.L_G, base.r_T = prob["G"].to(device), prob["L_G"].to(device), prob["r_T"].to(device)
+    net = P.MLP(input_dim=d, premodule="NormalizeLogRadius")
     with torch.no_grad():
         for i, l in enumerate(net.linears()):
-            l.weight.copy_(mlp.W[i])
-            l.bias.copy_(mlp.b[i])
+            l.weight.copy_(prob["W"][i])
+            l.bias.copy_(prob["b"][i])
     gen = P.PluginReverseSDE(base, net.to(device), T, deviceReverseSDE=device).to(device)
     return P, gen
 
 
-def time_cpu_port(sde, mlp, B: int, n_steps: int, reps: int):
-    """particle-steps/s of the CPU oracle port (reference op sequence) with all host threads."""
-    from oracle import msgm_oracle as O
-    rev = O.OReverse(sde, mlp)
-    torch.manual_seed(1)
-    x0 = O.latent_sample(sde, B)
-    best = float("inf")
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        O.integrate(rev, x0, n_steps, "rk4", 0.0, keep_all_samples=False, norm_correction=True)
-        best = min(best, time.perf_counter() - t0)
-    return B * n_steps / best, best
+# ---- CPU legs (cpu_baseline, --impl reference): the only places that touch oracle/ or baseline/_ref ----------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
-def time_cpu_train(sde, mlp, data, batch: int, iters: int):
-    """samples/s of the reference's train step on the CPU port: ssm -> mean -> backward -> Adam (MSGM_higherDim.py:803-809)."""
-    from oracle import msgm_oracle as O
-    params = [p.clone().requires_grad_(True) for p in mlp.parameters()]
-    net = O.OMlp(params[0::2], params[1::2], mlp.premodule, mlp.input_dim)
-    rev = O.OReverse(sde, net)
-    opt = torch.optim.Adam(params, lr=1e-3)
-    torch.manual_seed(2)
-    t0 = None
-    for it in range(iters + 1):
-        if it == 1:
+def cpu_objects(prob):
+    """(kind, sampler callable, train-step factory) of the reference's CPU path on this problem: the UNMODIFIED reference
+    from baseline/_ref when it travelled with the repo (plot / IO modules stubbed), else the oracle port."""
+    d = prob["dim"]
+    if os.path.isfile(os.path.join(REF_DIR, "SDEs.py")):
+        os.environ["MSGM_REFERENCE_ROOT"] = REF_DIR
+        from oracle import ref_live
+        ref = ref_live.load()
+        base, gen, net = ref_live.build(ref, "msgm_dense", d, prob["data"][:4096], "NormalizeLogRadius",
+                                        beta_min=prob["beta_min"], beta_max=prob["beta_max"], t_eps=prob["t_epsilon"],
+                                        n_fwd=prob["num_steps_forward"], T0=prob["T"])
+        base.G, base.L_G, base.r_T = prob["G"], prob["L_G"], prob["r_T"]
+        with torch.no_grad():
+            lin = [m for m in net.main if isinstance(m, torch.nn.Linear)]
+            for i, l in enumerate(lin):
+                l.weight.copy_(prob["W"][i])
+                l.bias.copy_(prob["b"][i])
+
+        def sample(B, n):
+            x0 = base.latent_sample(B, d)
             t0 = time.perf_counter()
-        opt.zero_grad()
-        x = data[torch.randint(0, data.shape[0], (batch,))]
-        loss, _ = O.ssm(rev, x)
-        loss.mean().backward()
-        opt.step()
-    return batch * iters / (time.perf_counter() - t0)
+            ref.sde_scheme.rk4_stratonovich_sampler(gen, x0, num_steps=n, lmbd=0., keep_all_samples=False,
+                                                    norm_correction=True)
+            return time.perf_counter() - t0
+
+        def train(batch, iters):
+            opt = torch.optim.Adam(gen.parameters(), lr=1e-3)
+            gen.train()
+            t0 = None
+            for it in range(iters + 1):
+                if it == 1:
+                    t0 = time.perf_counter()
+                opt.zero_grad()
+                x = prob["data"][torch.randint(0, prob["data"].shape[0], (batch,))]
+                gen.ssm(x).mean().backward()
+                opt.step()
+            return batch * iters / (time.perf_counter() - t0)
+
+        return "reference", sample, train
+    from oracle import msgm_oracle as O
+    sde = O.OSde("msgm_dense", d, prob["beta_min"], prob["beta_max"], prob["T"], prob["t_epsilon"],
+                 prob["num_steps_forward"], G=prob["G"], L_G=prob["L_G"], r_T=prob["r_T"], norm_map="log")
+    mlp = O.OMlp(prob["W"], prob["b"], True, d)
+
+    def sample(B, n):
+        x0 = O.latent_sample(sde, B)
+        t0 = time.perf_counter()
+        O.integrate(O.OReverse(sde, mlp), x0, n, "rk4", 0.0, keep_all_samples=False, norm_correction=True)
+        return time.perf_counter() - t0
+
+    def train(batch, iters):
+        params = [p.clone().requires_grad_(True) for p in mlp.parameters()]
+        rev = O.OReverse(sde, O.OMlp(params[0::2], params[1::2], True, d))
+        opt = torch.optim.Adam(params, lr=1e-3)
+        t0 = None
+        for it in range(iters + 1):
+            if it == 1:
+                t0 = time.perf_counter()
+            opt.zero_grad()
+            x = prob["data"][torch.randint(0, prob["data"].shape[0], (batch,))]
+            loss, _ = O.ssm(rev, x)
+            loss.mean().backward()
+            opt.step()
+        return batch * iters / (time.perf_counter() - t0)
+
+    return "port", sample, train
 
 
 def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev, graphed: bool = False):
@@ -291,33 +352,45 @@ def time_unet_forward(P, dev):
     return out
 
 
+def cpu_sample_size(args):
+    """Bounded sample of the workload for the CPU legs: ~10-30 s of CPU work per measurement."""
+    return 50_000, 4
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun sets OMP_NUM_THREADS=1; this arm may use every host core
-    sde, mlp = build_problem(args.dim)
-    B, n = 50_000, 4
+    prob = build_problem(args.dim)
+    kind, sample, _ = cpu_objects(prob)
+    B, n = cpu_sample_size(args)
     times = []
     for i in range(args.warmup + args.steps):
-        v, t = time_cpu_port(sde, mlp, B, n, 1)
+        t = sample(B, n)
         if i >= args.warmup:
             times.append(t)
     ms = 1e3 * sum(times) / len(times)
     value = B * n / (ms / 1e3)
-    sample = f"{B} particles x {n} RK4 steps per bench step (same net/SDE as the GPU arm)"
+    what = "the unmodified reference (baseline/_ref, sde_scheme.rk4_stratonovich_sampler, torch CPU fp32)" \
+        if kind == "reference" else "oracle port of the reference's op sequence (torch CPU fp32)"
     emit({
         "impl": "reference", "metric": "reverse_sde_particle_steps_per_sec", "value": value,
         "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, "cpu"),
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
-                         "kind": "port", "sample": sample},
+                         "kind": kind,
+                         "sample": f"{B} particles x {n} RK4 steps per bench step, same net/SDE as the GPU arm; {what}"},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
 
 
+def workload_name(dim, steps, particles):
+    return f"gaussmix_d{dim}_msgm_dense_mlp128_rk4_n{steps}_{particles}particles_per_gpu"
+
+
 def workload_config(args, where):
-    return {"workload": f"gaussmix_d{args.dim}_msgm_dense_mlp128_rk4_n{args.sde_steps}_{args.particles}particles_per_gpu",
+    return {"workload": workload_name(args.dim, args.sde_steps, args.particles),
             "dim": args.dim, "particles_per_gpu": args.particles, "sde_steps": args.sde_steps, "scheme": "rk4",
             "lmbd": 0.0, "norm_correction": True, "precision": args.precision if where == "gpu" else "fp32",
             "l2_policy": "working set is on-chip (weights in smem, state in registers); x_0/x_N (2 x 4*B*d bytes) "
@@ -357,9 +430,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the SSM training leg (profiling runs)")
     ap.add_argument("--no-unet", action="store_true", help="skip the U-Net score-net forward leg (configs 3 and 4)")
-    ap.add_argument("--sde-steps", type=int, default=N_SDE_STEPS, help="reverse-SDE steps per sampler call (default 128; "
-                    "BASELINE config 5 uses 1000)")
-    ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU (default 2^20)")
+    ap.add_argument("--no-extra", action="store_true", help="skip config 2 / fp32 parity / per-dimension side measurements")
+    ap.add_argument("--sde-steps", type=int, default=N_SDE_STEPS, help="reverse-SDE steps per sampler call (default 1000 = "
+                    "BASELINE config 5; config 2 uses 128)")
+    ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU (default 10^7 = BASELINE "
+                    "config 5; config 2 uses 2^20)")
     args = ap.parse_args()
     _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -380,8 +455,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    sde, mlp = build_problem(args.dim)
-    P, gen = package_objects(sde, mlp, dev)
+    prob = build_problem(args.dim)
+    P, gen = package_objects(prob, dev)
     B, N = args.particles, args.sde_steps
     torch.manual_seed(1234 + rank)
     x0_host = (torch.randn(B, args.dim) * 1.5).pin_memory()
@@ -397,6 +472,22 @@ def main():
 
     def one_call(seed):
         return P.rk4_stratonovich_sampler(gen, x0_dev, N, seed=seed, device_out=True, **kw)
+
+    def time_calls(fn, reps, warm):
+        """mean CUDA-event milliseconds of `reps` calls after `warm` untimed ones (secondary measurements)."""
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        ms = []
+        for i in range(reps):
+            flush.fill_(float(i))
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            fn(50 + i)
+            b_.record()
+            torch.cuda.synchronize(dev)
+            ms.append(a_.elapsed_time(b_))
+        return sum(ms) / len(ms)
 
     clk = ClockSampler(local, enabled=(rank == 0))  # started before the warm-up so that it is sampling by the timed region
     for i in range(args.warmup):
@@ -423,6 +514,7 @@ def main():
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     total_ms = float(t_dev.item())
     value = world * B * N * args.steps / (total_ms / 1e3)
+    P._lib.check_async(dev)
 
     # ---- end-to-end through the public API with host buffers -------------------------------------------------
     # Every step copies its input from pinned host memory and its result back to pinned host memory inside the timed
@@ -467,14 +559,64 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * B * N * args.steps / (float(t_e2e.item()) / 1e3)
     assert all(bool(torch.isfinite(o).all()) for o in out_host[:min(2, args.steps)])
+    del out_host, xbuf
+
+    # ---- the stock drop-in call: CPU tensor in, CPU tensor out, nothing but the reference's own arguments ---------------
+    # (a) as the reference driver issues it (MSGM_higherDim.py:903-906): 10^4 particles, 128 steps, every step kept;
+    # (b) a 2^20-particle batch, final state only.  Wall clock around the blocking call (it returns a host tensor).
+    stock = []
+    if rank == 0:
+        for nb, ns, keep in ((10_000, 128, True), (1 << 20, 128, False)):
+            xc = torch.randn(nb, args.dim) * 1.5
+            best = float("inf")
+            for _ in range(3):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                out = P.rk4_stratonovich_sampler(gen, xc, ns, lmbd=0., keep_all_samples=keep, include_t0=keep,
+                                                 norm_correction=True, precision=args.precision)
+                best = min(best, time.perf_counter() - t0)
+            assert out.device.type == "cpu" and bool(torch.isfinite(out).all())
+            stock.append({"particles": nb, "sde_steps": ns, "keep_all_samples": keep, "include_t0": keep,
+                          "seconds": best, "value": nb * ns / best, "unit": "particle-steps/s",
+                          "h2d_bytes": xc.numel() * 4, "d2h_bytes": out.numel() * 4})
+
+    # ---- the other named configuration, the fp32 parity mode and the other dimensions, same run ----------------------------
+    def sampler_rate(d_, nb, ns, prec, reps=2):
+        pr = prob if d_ == args.dim else build_problem(d_)
+        g_ = gen if d_ == args.dim else package_objects(pr, dev)[1]
+        xs = torch.randn(nb, d_, device=dev) * 1.5
+        ms_ = time_calls(lambda sd: P.rk4_stratonovich_sampler(
+            g_, xs, ns, seed=sd, device_out=True, lmbd=0.0, keep_all_samples=False, norm_correction=True, precision=prec),
+            reps, 1)
+        return nb * ns / (ms_ / 1e3), ms_
+
+    peaks = load_peaks()
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        v2, ms2 = sampler_rate(args.dim, CFG2_PARTICLES, CFG2_STEPS, args.precision, reps=3)
+        extra["config2"] = {"workload": workload_name(args.dim, CFG2_STEPS, CFG2_PARTICLES), "value": v2,
+                            "unit": "particle-steps/s", "ms_per_call": ms2, "precision": args.precision,
+                            "roofline_frac": v2 * flop_per_particle_step(args.dim, 1, True) / 1e12 / peaks["tflops"]}
+        nb32 = 1 << 17
+        v32, ms32 = sampler_rate(args.dim, nb32, 128, "fp32")
+        extra["fp32_parity"] = {"precision": "fp32", "kernel": "sample_fp32_kernel", "value": v32,
+                                "unit": "particle-steps/s", "ms_per_call": ms32,
+                                "sample": f"{nb32} particles x 128 RK4 steps, same net/SDE (fp32 CUDA-core parity mode: "
+                                          "states within 5e-5 + 5e-5 |x| of the reference)",
+                                "fp32_fma_frac": v32 * flop_per_particle_step(args.dim, 1, True) / 1e12 / 72.0}
+        by_dim = []
+        for d_ in (2, 4, 8, 16):
+            vd, msd = sampler_rate(d_, CFG2_PARTICLES, CFG2_STEPS, "f16tc")
+            by_dim.append({"dim": d_, "value": vd, "ms_per_call": msd,
+                           "roofline_frac": vd * flop_per_particle_step(d_, 1, True) / 1e12 / peaks["tflops"]})
+        extra["by_dim_f16tc_2p20_x128"] = by_dim
 
     # ---- secondary metric of BASELINE.json: score-matching train samples/s (SSM is the reference's live loss) -----
-    from oracle import msgm_oracle as O
-    data_host = O.gaussian_mixture(100_000, args.dim, seed=0)
+    data_host = prob["data"]
     data_dev = data_host.to(dev)
     gen.train()
     train = {"metric": "ssm_train_samples_per_sec", "unit": "samples/s", "precision": "fp32",
-             "step": "gen.ssm(x).mean().backward(); flat-grad all-reduce (N>1); torch.optim.Adam.step()", "runs": []}
+             "step": "gen.ssm(x).mean().backward(); flat-grad all-reduce (N>1); Adam step", "runs": []}
     for batch, graphed in (() if args.no_train else ((256, False), (256, True), (16384, False), (16384, True))):
         v_, ms_, launches_, loss_ = time_gpu_train(P, gen, data_dev, batch, 100 if graphed else 20, world, dev, graphed)
         train["runs"].append({"batch_per_gpu": batch, "mode": "cuda_graph" if graphed else "eager", "value": v_,
@@ -482,7 +624,6 @@ def main():
     train["value"] = max((r["value"] for r in train["runs"]), default=None)
 
     if rank == 0:
-        peaks = load_peaks()
         fl = flop_per_particle_step(args.dim, 1, True) * B * N  # per launch
         kms = sum(kern_ms) / len(kern_ms)
         achieved = fl / (kms / 1e3) / 1e12
@@ -493,6 +634,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, "gpu"),
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": B * args.dim * 4,
                     "d2h_bytes_per_step": B * args.dim * 4},
+            "e2e_stock": stock,
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
@@ -502,13 +644,15 @@ def main():
                          "kernel": "sample_fp32_kernel" if args.precision == "fp32" else "sample_tc_kernel",
                          "flop_per_launch": fl, "kernel_ms": kms,
                          # the unit that actually binds the tcgen05 sampler: one MUFU.TANH per hidden activation
-                         # (3 x 128 per net evaluation, 4 evaluations per RK4 step) at 16 / clk / SM (profiles/README.md)
+                         # (3 x 128 per net evaluation, 4 evaluations per RK4 step) at 16 / clk / SM; measured XU-pipe
+                         # utilisation in profiles/ncu_raw_sample_tc_d*_r02_baseline_pipes.csv
                          "binding_unit": None if args.precision == "fp32" else {
                              "pipe": "xu (MUFU)", "ops_per_particle_step": 4 * 384,
                              "achieved_ops_per_s": 4 * 384 * B * N / (kms / 1e3),
                              "peak_ops_per_s": 148 * 16 * 1.965e9,
                              "frac": 4 * 384 * B * N / (kms / 1e3) / (148 * 16 * 1.965e9)}},
         }
+        line.update(extra)
         line["train"] = train
         if world == 1 and not args.no_unet:
             try:
@@ -520,14 +664,17 @@ def main():
                                     "sample": "timed at N=1 only"}
         elif not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            train["cpu_baseline"] = {"value": None if args.no_train else time_cpu_train(sde, mlp, data_host, 256, 10), "unit": "samples/s",
-                                     "cores": torch.get_num_threads(), "kind": "port",
-                                     "sample": "batch 256, 10 iterations after 1 warm-up (oracle port, torch CPU fp32)"}
-            v, t = time_cpu_port(sde, mlp, 50_000, 4, 3)
-            line["cpu_baseline"] = {"value": v, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
-                                    "kind": "port",
-                                    "sample": "50000 particles x 4 RK4 steps, best of 3, same net/SDE (oracle port of "
-                                              "the reference's op sequence, torch CPU fp32)"}
+            kind, cpu_sample, cpu_train = cpu_objects(prob)
+            what = "unmodified reference from baseline/_ref" if kind == "reference" else "oracle port of the reference's op sequence"
+            train["cpu_baseline"] = {"value": None if args.no_train else cpu_train(256, 10), "unit": "samples/s",
+                                     "cores": torch.get_num_threads(), "kind": kind,
+                                     "sample": f"batch 256, 10 iterations after 1 warm-up ({what}, torch CPU fp32)"}
+            nb, ns = cpu_sample_size(args)
+            best = min(cpu_sample(nb, ns) for _ in range(3))
+            line["cpu_baseline"] = {"value": nb * ns / best, "unit": "particle-steps/s", "cores": torch.get_num_threads(),
+                                    "kind": kind,
+                                    "sample": f"{nb} particles x {ns} RK4 steps, best of 3, same net/SDE ({what}, "
+                                              "torch CPU fp32)"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -199,3 +199,64 @@ def test_tc_matches_fp32_statistics():
     assert float(err.mean()) < 5e-3
     assert float((a.mean(0) - b.mean(0)).abs().max()) < 2e-3
     assert float((torch.cov(a.T) - torch.cov(b.T)).abs().max()) < 5e-3
+
+
+def _bench_problem(d):
+    """The bench's own synthetic problem (bench.build_problem) as (oracle OSde, OMlp, package gen)."""
+    import bench
+    prob = bench.build_problem(d)
+    sde = O.OSde("msgm_dense", d, prob["beta_min"], prob["beta_max"], prob["T"], prob["t_epsilon"],
+                 prob["num_steps_forward"], G=prob["G"], L_G=prob["L_G"], r_T=prob["r_T"], norm_map="log")
+    mlp = O.OMlp(prob["W"], prob["b"], True, d)
+    return sde, mlp, bench.package_objects(prob, DEV)[1]
+
+
+@pytest.mark.parametrize("d", [8, 2])
+def test_tc_headline_configuration_against_oracle(d):
+    """The bench's headline configuration itself -- its weights, G and data, dense multiplicative SDE, RK4, 128 reverse
+    steps, lambda = 0, radius correction -- on 4096 particles with injected noise: EVERY one of the 128 states of the
+    tcgen05 (f16tc) path against the CPU oracle at the stated f16tc tolerance, and the fp32 parity mode at its own."""
+    sde, mlp, gen = _bench_problem(d)
+    torch.manual_seed(77)
+    B, N = 4096, 128
+    x0 = torch.randn(B, d) * 1.5
+    noise = torch.randn(N, B, d)
+    ref = O.integrate(O.OReverse(sde, mlp), x0, N, "rk4", 0.0, True, None, True, None, True, noise=noise)
+    for prec, atol, rtol in (("f16tc", TC_ATOL, TC_RTOL), ("fp32", 5e-5, 5e-5)):
+        out = P.rk4_stratonovich_sampler(gen, x0.to(DEV), N, lmbd=0.0, keep_all_samples=True, include_t0=True,
+                                         norm_correction=True, noise=noise, precision=prec)
+        assert P._lib.debug_flags(DEV) == 0
+        assert tuple(out.shape) == (N + 1, B, d)
+        _close(f"headline-d{d}-N128-{prec}", out, ref, atol, rtol)
+        # the error must not grow into the tolerance over the 128 steps: last state on its own
+        _close(f"headline-d{d}-N128-{prec}-final", out[-1], ref[-1], atol, rtol)
+
+
+def test_tc_vs_fp32_at_bench_size():
+    """2^20 particles x 128 RK4 steps, in-kernel Philox (the bench's config 2): the f16tc and fp32 kernels draw the same
+    noise, so particles agree one by one within the f16tc tolerance, and the ensembles agree in mean, covariance, radius
+    (pinned by norm_correction) and MMD."""
+    from sdeflow_light_b200 import quantitative_comparison as Q
+    d, B, N = 8, 1 << 20, 128
+    _, _, gen = _bench_problem(d)
+    torch.manual_seed(5)
+    x0 = (torch.randn(B, d) * 1.5).to(DEV)
+    kw = dict(keep_all_samples=False, norm_correction=True, seed=2024, device_out=True)
+    b = P.rk4_stratonovich_sampler(gen, x0, N, precision="f16tc", **kw)
+    a = P.rk4_stratonovich_sampler(gen, x0, N, precision="fp32", **kw)
+    assert P._lib.debug_flags(DEV) == 0
+    err = (a - b).abs()
+    tol = TC_ATOL + TC_RTOL * a.abs().max(dim=1, keepdim=True)[0]
+    frac_out = float((err > tol).float().mean())
+    Bd.report(test="tc-vs-fp32-2p20-N128", max_abs=float(err.max()), mean_abs=float(err.mean()),
+              ref_max=float(a.abs().max()), frac_outside_tol=frac_out)
+    assert frac_out < 1e-4, frac_out          # chaotic outliers only (none observed)
+    assert float(err.mean()) < 5e-4
+    assert float((a.mean(0) - b.mean(0)).abs().max()) < 1e-3
+    assert float((torch.cov(a.T) - torch.cov(b.T)).abs().max()) < 2e-3
+    assert float(((b.norm(dim=1) - x0.norm(dim=1)).abs() / x0.norm(dim=1)).max()) < 1e-5
+    idx = torch.randperm(B, device=DEV)[:20000]
+    mmd_ab = float(Q.compute_mmd(a[idx], b[idx]))
+    mmd_aa = float(Q.compute_mmd(a[idx], a[torch.randperm(B, device=DEV)[:20000]]))
+    Bd.report(test="tc-vs-fp32-2p20-N128-mmd", mmd_tc_vs_fp32=mmd_ab, mmd_fp32_vs_fp32_resample=mmd_aa)
+    assert mmd_ab < 1e-5 and mmd_ab < mmd_aa

@@ -11,8 +11,8 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 prec = sys.argv[4] if len(sys.argv) > 4 else "f16tc"
 dev = torch.device("cuda", 0)
-sde, mlp = bench.build_problem(d)
-P, gen = bench.package_objects(sde, mlp, dev)
+prob = bench.build_problem(d)
+P, gen = bench.package_objects(prob, dev)
 torch.manual_seed(1)
 x0 = (torch.randn(B, d) * 1.5).to(dev)
 for i in range(2):

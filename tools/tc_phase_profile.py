@@ -10,8 +10,8 @@ import bench  # noqa: E402
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 N = 32
 B = 148 * (4 if d <= 4 else 3) * 128  # one tile per slot
-sde, mlp = bench.build_problem(d)
-P, gen = bench.package_objects(sde, mlp, torch.device("cuda", 0))
+prob = bench.build_problem(d)
+P, gen = bench.package_objects(prob, torch.device("cuda", 0))
 x0 = (torch.randn(B, d) * 1.5).cuda()
 for _ in range(2):
     P.rk4_stratonovich_sampler(gen, x0, N, keep_all_samples=False, norm_correction=True, precision="f16tc", seed=1,

@@ -14,8 +14,8 @@ import bench  # noqa: E402
 dims = [int(a) for a in sys.argv[1:]] or [2, 8]
 dev = torch.device("cuda", 0)
 for d in dims:
-    sde, mlp = bench.build_problem(d)
-    P, gen = bench.package_objects(sde, mlp, dev)
+    prob = bench.build_problem(d)
+    P, gen = bench.package_objects(prob, dev)
     B, N = 1 << 20, 128
     torch.manual_seed(1)
     x0 = (torch.randn(B, d) * 1.5).to(dev)

@@ -11,8 +11,8 @@ from sdeflow_light_b200.train import GraphedSsmStep  # noqa: E402
 
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda", 0)
-sde, mlp = bench.build_problem(d)
-P, gen = bench.package_objects(sde, mlp, dev)
+prob = bench.build_problem(d)
+P, gen = bench.package_objects(prob, dev)
 data = O.gaussian_mixture(100_000, d, seed=0).to(dev)
 opt = torch.optim.Adam(gen.parameters(), lr=1e-3, fused=True)
 gen.train()

@@ -182,6 +182,32 @@ int msgm_latent_sample(msgm_ctx* ctx, const float* rT_sorted, int32_t n_r, int32
 int msgm_mmd_sums(msgm_ctx* ctx, const float* x, int64_t N, const float* y, int64_t M, int32_t d, double* sums_out,
                   void* stream);
 
+/* Sample-quality metrics of the reference's evaluation step, on device-resident particles.
+ * msgm_row_norm_stats: norms_out[b] = |x_b * scale| (scale_opt: (d,) per-dimension factor or NULL;
+ *   own_plotting.py:646-653,729-736) and minpos_max_out = {smallest positive norm, largest norm} (two floats), the span of
+ *   the shared radius grid (_compute_common_R_grid, own_plotting.py:616-632).
+ * msgm_survival_counts: counts_out[g] = #{b : norms[b] > R_grid[g]} for an ascending float64 grid (n_grid <= 4096), i.e.
+ *   norms.size - searchsorted(sort(norms), R_grid, side='right') of _empirical_survival_from_norms (own_plotting.py:635-640);
+ *   scratch: 8 (n_grid + 1) bytes of device memory.  The tail exponent of _tail_fit_loglog (own_plotting.py:656-700) needs
+ *   no sort either: R_g >= the (n-k-1)-th order statistic  <=>  counts[g] <= k.
+ * msgm_moments: colsum_out (d doubles) = sum_b x_b, gram_out (d x d doubles, upper 32x32 tiles filled) = sum_b x_b x_b^T:
+ *   mean, torch.cov, torch.var and the energy mean|x|^2 of preprocessing() (own_plotting.py:339-394). */
+int msgm_row_norm_stats(msgm_ctx* ctx, const float* x, const float* scale_opt, float* norms_out, float* minpos_max_out,
+                        int32_t d, int64_t n, void* stream);
+int msgm_survival_counts(msgm_ctx* ctx, const float* norms, int64_t n, const double* R_grid, int32_t n_grid,
+                         int64_t* counts_out, void* scratch, void* stream);
+int msgm_moments(msgm_ctx* ctx, const float* x, int64_t n, int32_t d, double* colsum_out, double* gram_out, void* stream);
+
+/* Adam update (torch.optim.Adam(lr) as the reference driver builds it, MSGM_higherDim.py:792: betas (0.9, 0.999),
+ * eps 1e-8, no weight decay) over the trainer's flat gradient buffer in one launch.  seg_table: device array of n_tensors
+ * {float* param; int64 begin} records (16 bytes each, ascending begin) mapping flat ranges to the parameter tensors;
+ * exp_avg / exp_avg_sq: flat moment buffers (total floats); lr_dev, step_dev: device scalars (the kernel uses step+1 and
+ * stores it back), so the launch replays inside a CUDA graph; grad_scale multiplies the gradient (1/world after a summed
+ * all-reduce). */
+int msgm_adam_step(msgm_ctx* ctx, const void* seg_table, int32_t n_tensors, int64_t total, const float* grad_flat,
+                   float* exp_avg, float* exp_avg_sq, const float* lr_dev, int64_t* step_dev, float beta1, float beta2,
+                   float eps, float grad_scale, void* stream);
+
 /* Log density of a 1-D Gaussian kernel density estimate at m query points: what MSGMsde.log_latent_pdf and the
  * normalising-constant estimate of the constructor ask sklearn's KernelDensity.score_samples for (SDEs.py:240,261,509;
  * kernel='gaussian', exact sum).  samples (n,), queries (m,), out (m,): device fp32. */

@@ -65,7 +65,7 @@ _lock = threading.Lock()
 _ctx = {}
 
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
-SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count", "msgm_async_error",
+SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count", "msgm_async_error", "msgm_row_norm_stats", "msgm_survival_counts", "msgm_moments", "msgm_adam_step",
            "msgm_sample_mlp", "msgm_noise_forward", "msgm_ssm_prepare", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward",
            "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums", "msgm_kde_logpdf",
@@ -142,6 +142,12 @@ def lib() -> C.CDLL:
                                                C.c_void_p]
                 L.msgm_kde_logpdf.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
                                               C.c_void_p]
+                L.msgm_row_norm_stats.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p]
+                L.msgm_survival_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p]
+                L.msgm_moments.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+                L.msgm_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 5 + \
+                    [C.c_float] * 4 + [C.c_void_p]
                 L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]

@@ -39,6 +39,12 @@ int latent_sample(msgm_ctx*, const float*, int, int, int, const float*, const fl
 int mmd_sums(msgm_ctx*, const float*, int64_t, const float*, int64_t, int, double*, cudaStream_t);
 int kde_logpdf(msgm_ctx*, const float*, int, float, const float*, float*, int, cudaStream_t);
 
+int row_norm_stats(msgm_ctx*, const float*, const float*, float*, float*, int, int64_t, cudaStream_t);
+int survival_counts(msgm_ctx*, const float*, int64_t, const double*, int, int64_t*, void*, cudaStream_t);
+int moments(msgm_ctx*, const float*, int64_t, int, double*, double*, cudaStream_t);
+int adam_step(msgm_ctx*, const void*, int, int64_t, const float*, float*, float*, const float*, int64_t*, float, float, float,
+              float, cudaStream_t);
+
 int conv1d(msgm_ctx*, const msgm_conv1d_desc*, cudaStream_t);
 int emb_fold(msgm_ctx*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int convt1d(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
@@ -290,6 +296,37 @@ int msgm_mmd_sums(msgm_ctx* ctx, const float* x, int64_t N, const float* y, int6
   if (!ctx || !x || !y || !sums_out || d < 1 || N < 1 || M < 1) return invalid("msgm_mmd_sums: bad argument");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return mmd_sums(ctx, x, N, y, M, d, sums_out, (cudaStream_t)stream);
+}
+
+int msgm_row_norm_stats(msgm_ctx* ctx, const float* x, const float* scale_opt, float* norms_out, float* minpos_max_out,
+                        int32_t d, int64_t n, void* stream) {
+  if (!ctx || !x || !norms_out || !minpos_max_out || d < 1 || n < 1) return invalid("msgm_row_norm_stats: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return row_norm_stats(ctx, x, scale_opt, norms_out, minpos_max_out, d, n, (cudaStream_t)stream);
+}
+
+int msgm_survival_counts(msgm_ctx* ctx, const float* norms, int64_t n, const double* R_grid, int32_t n_grid,
+                         int64_t* counts_out, void* scratch, void* stream) {
+  if (!ctx || !norms || !R_grid || !counts_out || !scratch || n < 1 || n_grid < 1)
+    return invalid("msgm_survival_counts: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return survival_counts(ctx, norms, n, R_grid, n_grid, counts_out, scratch, (cudaStream_t)stream);
+}
+
+int msgm_moments(msgm_ctx* ctx, const float* x, int64_t n, int32_t d, double* colsum_out, double* gram_out, void* stream) {
+  if (!ctx || !x || !colsum_out || !gram_out || n < 1 || d < 1) return invalid("msgm_moments: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return moments(ctx, x, n, d, colsum_out, gram_out, (cudaStream_t)stream);
+}
+
+int msgm_adam_step(msgm_ctx* ctx, const void* seg_table, int32_t n_tensors, int64_t total, const float* grad_flat,
+                   float* exp_avg, float* exp_avg_sq, const float* lr_dev, int64_t* step_dev, float beta1, float beta2,
+                   float eps, float grad_scale, void* stream) {
+  if (!ctx || !seg_table || !grad_flat || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || n_tensors < 1 || total < 1)
+    return invalid("msgm_adam_step: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return adam_step(ctx, seg_table, n_tensors, total, grad_flat, exp_avg, exp_avg_sq, lr_dev, step_dev, beta1, beta2, eps,
+                   grad_scale, (cudaStream_t)stream);
 }
 
 int msgm_kde_logpdf(msgm_ctx* ctx, const float* samples, int32_t n, float bandwidth, const float* queries, float* out,

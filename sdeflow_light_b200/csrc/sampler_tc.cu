@@ -45,6 +45,10 @@
 #endif
 //   MSGM_TC_POLY_PAIRS  of the 16 column pairs of every 32-column accumulator chunk, how many evaluate Swish on the FMA
 //                       pipe (packed-half polynomial, swish_poly_h2) instead of the MUFU pipe (tanh.approx)
+//   MSGM_TC_MERGE_EPI   d > 4: all three hidden-layer epilogues share one copy of the code (smaller kernel image)
+#ifndef MSGM_TC_MERGE_EPI
+#define MSGM_TC_MERGE_EPI 1
+#endif
 #ifndef MSGM_TC_POLY_PAIRS
 #define MSGM_TC_POLY_PAIRS 0
 #endif
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
           // One copy of the 128-activation epilogue in the instruction stream wherever possible: the kernel is ~100 KB
           // of SASS and the warps of a CTA sit in different phases, so code size shows up as instruction-fetch stalls.
 #pragma unroll 1
-          for (int l = 0; l < (L4_CC ? 2 : 3); ++l) {
+          for (int l = 0; l < ((L4_CC || !MSGM_TC_MERGE_EPI) ? 2 : 3); ++l) {
             ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
             pf.tick(1);  // wait for the accumulator
             ok = swish_epilogue<DP, false>(taddr, sA, row, sW4f, a, xu, lane, P.flags) && ok;
@@ -566,6 +570,15 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
             ok = swish_epilogue<DP, true>(taddr, sA, row, sW4f, a, xu, lane, P.flags) && ok;
             pf.tick(2);
           } else {
+#if !MSGM_TC_MERGE_EPI
+            ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
+            pf.tick(1);
+            ok = swish_epilogue<DP, false>(taddr, sA, row, sW4f, a, xu, lane, P.flags) && ok;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(my_a);
+            pf.tick(2);
+#endif
             ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
             uint32_t r[16];
             TMEM_LD16(taddr, r);

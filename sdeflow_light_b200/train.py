@@ -36,7 +36,7 @@ class _SsmModule(torch.nn.Module):
 
 class GraphedSsmStep:
     def __init__(self, gen, batch_shape, lr: float = 1e-3, optimizer: torch.optim.Optimizer | None = None,
-                 warmup: int = 3, group=None, seed: int | None = None):
+                 warmup: int = 3, group=None, seed: int | None = None, graph_allreduce: bool = True):
         dev = torch.device(gen.deviceReverseSDE)
         if dev.type != "cuda":
             raise RuntimeError("sdeflow_light_b200 runs on CUDA only (no CPU fallback)")
@@ -44,12 +44,14 @@ class GraphedSsmStep:
         self._names = [n for n, p in gen.named_parameters() if p.requires_grad]
         self.params = [p for n, p in gen.named_parameters() if p.requires_grad]
         self._mod = _SsmModule(gen)
-        # lr lives in a device tensor so that schedulers can change it between replays (set_lr)
-        self.opt = optimizer if optimizer is not None else torch.optim.Adam(
-            self.params, lr=torch.tensor(float(lr), device=dev), fused=True, capturable=True)
-        for g in self.opt.param_groups:
-            if not g.get("capturable", False):
-                raise ValueError("the optimizer must be built with capturable=True to be replayed inside a CUDA graph")
+        # Default optimiser: the reference driver's Adam(lr) (MSGM_higherDim.py:792) as ONE launch over the flat gradient
+        # buffer (msgm_adam_step; lr and the update counter are device scalars, so schedulers can change lr between replays
+        # with set_lr).  A caller-supplied torch optimiser (capturable=True) is recorded instead when given.
+        self.opt = optimizer
+        if optimizer is not None:
+            for g in self.opt.param_groups:
+                if not g.get("capturable", False):
+                    raise ValueError("the optimizer must be built with capturable=True to be replayed inside a CUDA graph")
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.x = torch.zeros(*batch_shape, device=dev, dtype=torch.float32)
         self.loss = torch.zeros((), device=dev, dtype=torch.float32)
@@ -60,6 +62,17 @@ class GraphedSsmStep:
             p.grad = self.flat[o:o + p.numel()].view_as(p)
             o += p.numel()
         self._grads = [p.grad for p in self.params]
+        if self.opt is None:
+            self.lr = torch.tensor(float(lr), device=dev, dtype=torch.float32)
+            self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+            self.adam_step = torch.zeros(1, device=dev, dtype=torch.int64)
+            tab, o = torch.zeros(len(self.params), 2, dtype=torch.int64), 0
+            for i, p in enumerate(self.params):
+                if not (p.is_contiguous() and p.dtype == torch.float32):
+                    raise ValueError("msgm_adam_step needs contiguous fp32 parameters")
+                tab[i, 0], tab[i, 1] = p.data_ptr(), o
+                o += p.numel()
+            self._seg_table = tab.to(dev)
         self.launches_per_iter = 0
         # Device-side random streams: a fixed seed plus a device counter bumped inside the graph, so every replay draws
         # fresh t / noise / v; the row offset makes a batch sharded over ranks draw what a single rank would.
@@ -82,47 +95,69 @@ class GraphedSsmStep:
         # Warm-up runs real iterations (allocator pools, lazy module loads, optimizer state creation) on stand-in data:
         # snapshot parameters and optimizer state, and put them back -- in place, the graphs hold the addresses.
         saved_p = [p.detach().clone() for p in self.params]
-        saved_s = {id(q): {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
-                   for q, st in self.opt.state.items()}
+        saved_s = {} if self.opt is None else {id(q): {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
+                                               for q, st in self.opt.state.items()}
         self.x.normal_()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
-                self._fwd_bwd()
-                if self.world > 1:
-                    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-                    self.flat /= self.world
-                self.opt.step()
+                self._iteration()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
 
+        # ONE graph per iteration: prologue, forward, backward, [NCCL all-reduce of the flat gradient -- NCCL collectives are
+        # capturable --], Adam.  `graph_allreduce = False` keeps the collective between two graphs (fwd/bwd | all-reduce |
+        # Adam), the round-1 arrangement, for process groups that cannot be captured.
         l0 = _lib.launch_count(dev)
-        self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
-            self._fwd_bwd()
-            if self.world == 1:
-                self.opt.step()
-        self.g_opt = None
-        if self.world > 1:  # the collective stays outside the graphs: fwd/bwd graph -> all-reduce -> Adam graph
+        self.g_fb, self.g_opt = torch.cuda.CUDAGraph(), None
+        if self.world == 1 or graph_allreduce:
+            with torch.cuda.graph(self.g_fb):
+                self._iteration()
+        else:
+            with torch.cuda.graph(self.g_fb):
+                self._fwd_bwd()
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt):
-                self.opt.step()
+                self._opt_step()
         self.launches_per_iter = _lib.launch_count(dev) - l0
         with torch.no_grad():
             for p, q in zip(self.params, saved_p):
                 p.copy_(q)
-            for q, st in self.opt.state.items():
-                for k, v in st.items():
-                    if torch.is_tensor(v):
-                        old = saved_s.get(id(q), {}).get(k)
-                        v.copy_(old) if old is not None else v.zero_()
+            if self.opt is None:
+                self.exp_avg.zero_()
+                self.exp_avg_sq.zero_()
+                self.adam_step.zero_()
+            else:
+                for q, st in self.opt.state.items():
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            old = saved_s.get(id(q), {}).get(k)
+                            v.copy_(old) if old is not None else v.zero_()
         self.x.zero_()
         self._iter.zero_()
         gen.device_rng = was
         gen._rng = self._old_rng  # the graphs have the trainer's stream baked in; eager calls keep their own
 
     # -- the recorded part of the iteration ---------------------------------------------------------------------
+    def _iteration(self):
+        self._fwd_bwd()
+        if self.world > 1:  # summed over ranks; the 1/world is folded into the Adam kernel's gradient scale
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self._opt_step()
+
+    def _opt_step(self):
+        if self.opt is None:
+            import ctypes as C  # noqa: F401
+            _lib.check(_lib.lib().msgm_adam_step(
+                _lib.ctx(self.dev), _lib.ptr(self._seg_table), len(self.params), self.flat.numel(), _lib.ptr(self.flat),
+                _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), _lib.ptr(self.lr), _lib.ptr(self.adam_step), 0.9, 0.999,
+                1e-8, 1.0 / self.world, _lib.stream_ptr(self.dev)))
+        else:
+            if self.world > 1:
+                self.flat /= self.world
+            self.opt.step()
+
     def _fwd_bwd(self):
         if self._direct:
             from . import ssm_fused
@@ -142,6 +177,40 @@ class GraphedSsmStep:
         self.loss.copy_(loss.detach())
         self._iter.add_(1)
 
+    # -- optimiser state in torch.optim.Adam's layout (what NN.save_checkpoint / the reference's loader expect) ---------
+    def state_dict(self) -> dict:
+        """``torch.optim.Adam(...).state_dict()``-compatible view of the optimiser state, so that
+        ``NN.save_checkpoint(path, gen, step, it)`` writes a file the reference's ``load_checkpoint`` reads into its own
+        ``torch.optim.Adam`` (NN.py:24-27)."""
+        if self.opt is not None:
+            return self.opt.state_dict()
+        state, o = {}, 0
+        t = self.adam_step.detach().to(torch.float32).reshape(()).cpu()
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            state[i] = {"step": t.clone(), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+            o += n
+        group = {"lr": float(self.lr.item()), "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if self.opt is not None:
+            return self.opt.load_state_dict(sd)
+        o, steps = 0, []
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                n, st = p.numel(), sd["state"].get(i)
+                if st is not None:
+                    self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.append(int(float(st["step"])))
+                o += n
+            self.adam_step.fill_(max(steps) if steps else 0)
+            self.lr.fill_(float(sd["param_groups"][0]["lr"]))
+
     # -- resumable random stream ---------------------------------------------------------------------------------
     def rng_state(self) -> dict:
         """Philox seed and device iteration counter of the recorded draws (t, noise, v).  Store it next to the model
@@ -156,6 +225,9 @@ class GraphedSsmStep:
 
     def set_lr(self, lr: float):
         """Change the learning rate seen by the recorded Adam update (in place, on the device)."""
+        if self.opt is None:
+            self.lr.fill_(float(lr))
+            return
         for g in self.opt.param_groups:
             if isinstance(g["lr"], torch.Tensor):
                 g["lr"].fill_(float(lr))
@@ -171,7 +243,6 @@ class GraphedSsmStep:
         self.g_fb.replay()
         if self.g_opt is not None:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat /= self.world  # Adam reads the averaged gradient through the .grad views
             self.g_opt.replay()
         # the replayed Adam wrote the parameters without bumping Tensor._version: invalidate every weight-derived cache
         # (packed tensor-core images, captured inference graphs) so that the next sample / evaluate sees live weights

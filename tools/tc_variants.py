@@ -16,7 +16,7 @@ dev = torch.device("cuda", 0)
 for d in dims:
     prob = bench.build_problem(d)
     P, gen = bench.package_objects(prob, dev)
-    B, N = 1 << 20, 128
+    B, N = int(os.environ.get("TCV_B", 1 << 20)), int(os.environ.get("TCV_N", 128))
     torch.manual_seed(1)
     x0 = (torch.randn(B, d) * 1.5).to(dev)
     kw = dict(lmbd=0.0, keep_all_samples=False, norm_correction=True, device_out=True)

@@ -489,6 +489,37 @@ def main():
             ms.append(a_.elapsed_time(b_))
         return sum(ms) / len(ms)
 
+    # ---- the other named configuration, the fp32 parity mode and the other dimensions, same run (taken first: seconds of work) ----
+    def sampler_rate(d_, nb, ns, prec, reps=2):
+        pr = prob if d_ == args.dim else build_problem(d_)
+        g_ = gen if d_ == args.dim else package_objects(pr, dev)[1]
+        xs = torch.randn(nb, d_, device=dev) * 1.5
+        ms_ = time_calls(lambda sd: P.rk4_stratonovich_sampler(
+            g_, xs, ns, seed=sd, device_out=True, lmbd=0.0, keep_all_samples=False, norm_correction=True, precision=prec),
+            reps, 1)
+        return nb * ns / (ms_ / 1e3), ms_
+
+    peaks = load_peaks()
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        v2, ms2 = sampler_rate(args.dim, CFG2_PARTICLES, CFG2_STEPS, args.precision, reps=3)
+        extra["config2"] = {"workload": workload_name(args.dim, CFG2_STEPS, CFG2_PARTICLES), "value": v2,
+                            "unit": "particle-steps/s", "ms_per_call": ms2, "precision": args.precision,
+                            "roofline_frac": v2 * flop_per_particle_step(args.dim, 1, True) / 1e12 / peaks["tflops"]}
+        nb32 = 1 << 17
+        v32, ms32 = sampler_rate(args.dim, nb32, 128, "fp32")
+        extra["fp32_parity"] = {"precision": "fp32", "kernel": "sample_fp32_kernel", "value": v32,
+                                "unit": "particle-steps/s", "ms_per_call": ms32,
+                                "sample": f"{nb32} particles x 128 RK4 steps, same net/SDE (fp32 CUDA-core parity mode: "
+                                          "states within 5e-5 + 5e-5 |x| of the reference)",
+                                "fp32_fma_frac": v32 * flop_per_particle_step(args.dim, 1, True) / 1e12 / 72.0}
+        by_dim = []
+        for d_ in (2, 4, 8, 16):
+            vd, msd = sampler_rate(d_, CFG2_PARTICLES, CFG2_STEPS, "f16tc")
+            by_dim.append({"dim": d_, "value": vd, "ms_per_call": msd,
+                           "roofline_frac": vd * flop_per_particle_step(d_, 1, True) / 1e12 / peaks["tflops"]})
+        extra["by_dim_f16tc_2p20_x128"] = by_dim
+
     clk = ClockSampler(local, enabled=(rank == 0))  # started before the warm-up so that it is sampling by the timed region
     for i in range(args.warmup):
         one_call(i)
@@ -579,37 +610,6 @@ def main():
             stock.append({"particles": nb, "sde_steps": ns, "keep_all_samples": keep, "include_t0": keep,
                           "seconds": best, "value": nb * ns / best, "unit": "particle-steps/s",
                           "h2d_bytes": xc.numel() * 4, "d2h_bytes": out.numel() * 4})
-
-    # ---- the other named configuration, the fp32 parity mode and the other dimensions, same run ----------------------------
-    def sampler_rate(d_, nb, ns, prec, reps=2):
-        pr = prob if d_ == args.dim else build_problem(d_)
-        g_ = gen if d_ == args.dim else package_objects(pr, dev)[1]
-        xs = torch.randn(nb, d_, device=dev) * 1.5
-        ms_ = time_calls(lambda sd: P.rk4_stratonovich_sampler(
-            g_, xs, ns, seed=sd, device_out=True, lmbd=0.0, keep_all_samples=False, norm_correction=True, precision=prec),
-            reps, 1)
-        return nb * ns / (ms_ / 1e3), ms_
-
-    peaks = load_peaks()
-    extra = {}
-    if rank == 0 and not args.no_extra:
-        v2, ms2 = sampler_rate(args.dim, CFG2_PARTICLES, CFG2_STEPS, args.precision, reps=3)
-        extra["config2"] = {"workload": workload_name(args.dim, CFG2_STEPS, CFG2_PARTICLES), "value": v2,
-                            "unit": "particle-steps/s", "ms_per_call": ms2, "precision": args.precision,
-                            "roofline_frac": v2 * flop_per_particle_step(args.dim, 1, True) / 1e12 / peaks["tflops"]}
-        nb32 = 1 << 17
-        v32, ms32 = sampler_rate(args.dim, nb32, 128, "fp32")
-        extra["fp32_parity"] = {"precision": "fp32", "kernel": "sample_fp32_kernel", "value": v32,
-                                "unit": "particle-steps/s", "ms_per_call": ms32,
-                                "sample": f"{nb32} particles x 128 RK4 steps, same net/SDE (fp32 CUDA-core parity mode: "
-                                          "states within 5e-5 + 5e-5 |x| of the reference)",
-                                "fp32_fma_frac": v32 * flop_per_particle_step(args.dim, 1, True) / 1e12 / 72.0}
-        by_dim = []
-        for d_ in (2, 4, 8, 16):
-            vd, msd = sampler_rate(d_, CFG2_PARTICLES, CFG2_STEPS, "f16tc")
-            by_dim.append({"dim": d_, "value": vd, "ms_per_call": msd,
-                           "roofline_frac": vd * flop_per_particle_step(d_, 1, True) / 1e12 / peaks["tflops"]})
-        extra["by_dim_f16tc_2p20_x128"] = by_dim
 
     # ---- secondary metric of BASELINE.json: score-matching train samples/s (SSM is the reference's live loss) -----
     data_host = prob["data"]

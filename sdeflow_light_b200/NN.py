@@ -54,7 +54,12 @@ def load_checkpoint(path, gen_sde, optim, device, *, trainer=None):
     base = getattr(gen_sde, "base_sde", None)
     if base is not None and "msgm_sde" in ck:
         for n, t in ck["msgm_sde"].items():
-            setattr(base, n, t.to(base.device))
+            cur = getattr(base, n, None)
+            if torch.is_tensor(cur) and cur.shape == t.shape and cur.dtype == t.dtype:
+                with torch.no_grad():
+                    cur.copy_(t)  # in place: captured CUDA graphs (train.GraphedSsmStep) hold these addresses
+            else:
+                setattr(base, n, t.to(base.device))
         base.__dict__.pop("_rT_sorted", None)  # derived caches
     if trainer is not None and "msgm_trainer_rng" in ck:
         trainer.load_rng_state(ck["msgm_trainer_rng"])

@@ -184,25 +184,30 @@ class GraphedSsmStep:
         ``torch.optim.Adam`` (NN.py:24-27)."""
         if self.opt is not None:
             return self.opt.state_dict()
+        # torch indexes the state by position in the list the optimiser was built from; the reference builds its Adam from
+        # gen_sde.parameters() (MSGM_higherDim.py:792), which also holds the two frozen horizons T (no state entries)
+        allp = list(self.gen.parameters())
+        pos = {id(p): i for i, p in enumerate(allp)}
         state, o = {}, 0
         t = self.adam_step.detach().to(torch.float32).reshape(()).cpu()
-        for i, p in enumerate(self.params):
+        for p in self.params:
             n = p.numel()
-            state[i] = {"step": t.clone(), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
-                        "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+            state[pos[id(p)]] = {"step": t.clone(), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                                 "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
             o += n
         group = {"lr": float(self.lr.item()), "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
-                 "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+                 "decoupled_weight_decay": False, "params": list(range(len(allp)))}
         return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd: dict) -> None:
         if self.opt is not None:
             return self.opt.load_state_dict(sd)
+        pos = {id(p): i for i, p in enumerate(self.gen.parameters())}
         o, steps = 0, []
         with torch.no_grad():
-            for i, p in enumerate(self.params):
-                n, st = p.numel(), sd["state"].get(i)
+            for p in self.params:
+                n, st = p.numel(), sd["state"].get(pos[id(p)])
                 if st is not None:
                     self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
                     self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))

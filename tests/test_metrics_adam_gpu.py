@@ -154,4 +154,4 @@ def test_trainer_state_dict_is_torch_adam_compatible(tmp_path):
     l1, l2 = float(step(x)), float(step2(x))
     assert l1 == l2
     for p, q in zip(gen.a.parameters(), gen2.a.parameters()):
-        assert torch.equal(p, q)
+        assert float((p - q).abs().max()) < 1e-6  # the weight-gradient reduction uses atomics: last-bit differences

@@ -156,6 +156,19 @@ int msgm_ssm_mlp_backward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_ml
                           const float* v, const float* t, const float* grad_out, void* scratch, float* grad_flat,
                           int64_t B, void* stream);
 
+/* The same training step on tcgen05 tensor cores (fp16 operands, fp32 accumulation), ONE launch for loss + activation
+ * backward + every weight gradient (csrc/ssm_tc.cu): loss_out[b] as msgm_ssm_mlp_forward, grad_flat_out = gradient of
+ * sum_b grad_out[b] loss[b] in torch parameter order as msgm_ssm_mlp_backward.  d <= 16.  scratch: device memory of
+ * msgm_ssm_tc_scratch_bytes(ctx, d, premodule, B) bytes (per-CTA partial gradients, summed by a second small launch).
+ * cot_scale: a power of two that brings grad_out to O(1) (B for the 1/B of a batch mean): the cotangents are fp16
+ * tensor-core operands; the scale is applied inside the kernel and removed from the result.
+ * Stated tolerance vs the fp32 kernels / the reference: loss 2e-3 of max|loss|, gradients 3e-3 of max|g| per tensor.
+ * Replaces PluginReverseSDE.ssm + loss.backward() (SDEs.py:607-646; MSGM_higherDim.py:803-809). */
+uint64_t msgm_ssm_tc_scratch_bytes(const msgm_ctx* ctx, int32_t d, int32_t premodule, int64_t B);
+int msgm_ssm_mlp_fwd_bwd_tc(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const float* y,
+                            const float* v, const float* t, const float* grad_out, float* loss_out, float* grad_flat_out,
+                            void* scratch, float cot_scale, int64_t B, void* stream);
+
 /* Per-stage SDE update for score nets that are not fused into the sampler (U-Nets, d up to 4096; SGM and sparse MSGM).
  * One call per Runge-Kutta stage replaces EMstep + PluginReverseSDE.{mu_Strato,sigma} + the stage bookkeeping
  * (sde_scheme.py:18-40,223-255; SDEs.py:556-588).  `a` is the score-net output at (stage input, s); x (B,d) is the state

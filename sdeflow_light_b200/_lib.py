@@ -67,7 +67,8 @@ _ctx = {}
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count", "msgm_async_error", "msgm_row_norm_stats", "msgm_survival_counts", "msgm_moments", "msgm_adam_step",
            "msgm_sample_mlp", "msgm_noise_forward", "msgm_ssm_prepare", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
-           "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward",
+           "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward", "msgm_ssm_tc_scratch_bytes",
+           "msgm_ssm_mlp_fwd_bwd_tc",
            "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums", "msgm_kde_logpdf",
            "msgm_conv1d", "msgm_emb_fold", "msgm_convt1d_k4s2", "msgm_embed_mlp", "msgm_normalize_log_radius",
            "msgm_conv2d", "msgm_gn_stats", "msgm_emb_proj", "msgm_sincos_embed_mlp", "msgm_attention", "msgm_vort_pre",
@@ -99,6 +100,10 @@ def lib() -> C.CDLL:
                     [C.c_int64, C.c_void_p]
                 L.msgm_ssm_mlp_backward.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc)] + [C.c_void_p] * 6 + \
                     [C.c_int64, C.c_void_p]
+                L.msgm_ssm_tc_scratch_bytes.restype = C.c_uint64
+                L.msgm_ssm_tc_scratch_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]
+                L.msgm_ssm_mlp_fwd_bwd_tc.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc)] + [C.c_void_p] * 7 + \
+                    [C.c_float, C.c_int64, C.c_void_p]
                 L.msgm_stage_update.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.c_int32, C.c_int32, C.c_float, C.c_int32,
                                                 C.c_int32, C.c_float, C.c_float] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
                 L.msgm_row_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]

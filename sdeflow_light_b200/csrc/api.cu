@@ -29,6 +29,10 @@ int ssm_forward(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const flo
 int ssm_backward(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const float*, const float*, const float*,
                  const float*, float*, float*, int64_t, cudaStream_t);
 
+int ssm_tc_grid(const msgm_ctx*, long long);
+int ssm_fwd_bwd_tc(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const float*, const float*, const float*,
+                   const float*, float*, float*, float*, float, int64_t, cudaStream_t);
+
 int stage_update(msgm_ctx*, const msgm_sde_desc*, int, int, float, int, int, float, float, const float*, const float*,
                  const float*, float*, float*, float*, int64_t, cudaStream_t);
 int row_norm(msgm_ctx*, const float*, float*, int, int64_t, cudaStream_t);
@@ -241,6 +245,26 @@ int msgm_ssm_mlp_backward(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_ml
   if (!y || !v || !t || !grad_out || !scratch) return invalid("msgm_ssm_mlp_backward: NULL buffer");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return ssm_backward(ctx, sde, mlp, y, v, t, grad_out, (float*)scratch, grad_flat, B, (cudaStream_t)stream);
+}
+
+uint64_t msgm_ssm_tc_scratch_bytes(const msgm_ctx* ctx, int32_t d, int32_t premodule, int64_t B) {
+  if (!ctx || d < 1) return 0;
+  const uint64_t nparam = 128ull * (d + 1 + (premodule ? 1 : 0)) + 128 + 2 * (128 * 128 + 128) + 128ull * d + d;
+  return sizeof(float) * ((nparam + 3) & ~3ull) * (uint64_t)ssm_tc_grid(ctx, B < 1 ? 1 : B);
+}
+
+int msgm_ssm_mlp_fwd_bwd_tc(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_mlp_desc* mlp, const float* y,
+                            const float* v, const float* t, const float* grad_out, float* loss_out, float* grad_flat,
+                            void* scratch, float cot_scale, int64_t B, void* stream) {
+  int rc = check_ssm(ctx, sde, mlp, B);
+  if (rc) return rc;
+  if (!loss_out || !grad_flat) return invalid("msgm_ssm_mlp_fwd_bwd_tc: NULL buffer");
+  if (B == 0) return MSGM_OK;
+  if (!y || !v || !t || !grad_out || !scratch) return invalid("msgm_ssm_mlp_fwd_bwd_tc: NULL buffer");
+  if (!(cot_scale > 0.0f)) return invalid("msgm_ssm_mlp_fwd_bwd_tc: cot_scale must be positive");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return ssm_fwd_bwd_tc(ctx, sde, mlp, y, v, t, grad_out, loss_out, grad_flat, (float*)scratch, cot_scale, B,
+                        (cudaStream_t)stream);
 }
 
 int msgm_stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,

@@ -9,6 +9,7 @@ the hand-derived backward kernels, so ``torch.optim.Adam(gen.parameters())`` tra
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import torch
 
@@ -58,10 +59,17 @@ class _SsmMlp(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+def tc_ok(gen, d) -> bool:
+    """``gen.ssm_precision == "f16tc"`` and the tensor-core SSM kernel covers this problem (csrc/ssm_tc.cu: d <= 16)."""
+    return getattr(gen, "ssm_precision", "fp32") == "f16tc" and d <= 16
+
+
 def fused_loss_and_grads(gen, t, y, v, gout, grad_flat):
     """Per-sample loss (B,) AND the parameter gradient of ``sum_b gout_b loss_b`` written straight into ``grad_flat``
-    (torch parameter order of the MLP): the forward and backward kernels back to back, without an autograd graph.
-    What train.GraphedSsmStep records for MLP score nets."""
+    (torch parameter order of the MLP), without an autograd graph: what train.GraphedSsmStep records for MLP score nets.
+    ``gen.ssm_precision = "fp32"`` (default, reference arithmetic): the forward and backward kernels back to back;
+    ``"f16tc"``: ONE tcgen05 launch for loss, backward and weight gradients (+ the partial-sum launch), stated tolerance in
+    include/msgm_b200.h."""
     dev = y.device
     base, net = gen.base_sde, gen.a
     B = y.shape[0]
@@ -70,6 +78,15 @@ def fused_loss_and_grads(gen, t, y, v, gout, grad_flat):
     md, k2 = net.desc(dev)
     yc, vc, tc = _lib.f32c(y, dev), _lib.f32c(v, dev), _lib.f32c(t.reshape(-1), dev)
     loss = torch.empty(B, device=dev, dtype=torch.float32)
+    if tc_ok(gen, y.shape[1]):
+        h, L = _lib.ctx(dev), _lib.lib()
+        nbytes = int(L.msgm_ssm_tc_scratch_bytes(h, int(sd.dim), int(md.premodule), B))
+        part = torch.empty(nbytes // 4, device=dev, dtype=torch.float32)
+        _lib.check(L.msgm_ssm_mlp_fwd_bwd_tc(h, C.byref(sd), C.byref(md), _lib.ptr(yc), _lib.ptr(vc), _lib.ptr(tc),
+                                             _lib.ptr(_lib.f32c(gout, dev)), _lib.ptr(loss), _lib.ptr(grad_flat),
+                                             _lib.ptr(part), float(2 ** round(math.log2(max(B, 1)))), B,
+                                             _lib.stream_ptr(dev)))
+        return loss
     scratch = torch.empty(int(_lib.lib().msgm_ssm_scratch_bytes(B)) // 4, device=dev, dtype=torch.float32)
     h = _lib.ctx(dev)
     _lib.check(_lib.lib().msgm_ssm_mlp_forward(h, C.byref(sd), C.byref(md), _lib.ptr(yc), _lib.ptr(vc), _lib.ptr(tc),
@@ -78,6 +95,32 @@ def fused_loss_and_grads(gen, t, y, v, gout, grad_flat):
                                                 _lib.ptr(gout), _lib.ptr(scratch), _lib.ptr(grad_flat), B,
                                                 _lib.stream_ptr(dev)))
     return loss
+
+
+class _SsmMlpTc(torch.autograd.Function):
+    """Eager-mode wrapper of the fused tensor-core step: the kernel needs the upstream gradient up front, so ``forward``
+    runs it for the loss and ``backward`` runs it again with the real ``gout`` (the graphed trainer calls
+    ``fused_loss_and_grads`` directly, once per iteration)."""
+
+    @staticmethod
+    def forward(ctx, gen, t, y, v, *params):
+        n = sum(p.numel() for p in params)
+        scratch_grad = torch.empty(n, device=y.device, dtype=torch.float32)
+        ctx.gen, ctx.saved, ctx.shapes = gen, (t, y, v), [p.shape for p in params]
+        return fused_loss_and_grads(gen, t, y, v, torch.zeros(y.shape[0], device=y.device), scratch_grad)
+
+    @staticmethod
+    def backward(ctx, gout):
+        t, y, v = ctx.saved
+        n = sum(int(torch.Size(s).numel()) for s in ctx.shapes)
+        flat = torch.empty(n, device=y.device, dtype=torch.float32)
+        fused_loss_and_grads(ctx.gen, t, y, v, gout, flat)
+        grads, o = [], 0
+        for s in ctx.shapes:
+            k = int(torch.Size(s).numel())
+            grads.append(flat[o:o + k].view(s))
+            o += k
+        return (None, None, None, None, *grads)
 
 
 def _mu_and_a(gen, t_, y):
@@ -135,6 +178,8 @@ def ssm_loss(gen, t_, x, y, v=None):
     if not (isinstance(net, NN.MLP) and net.fused_ok()):
         return _ssm_loss_autograd(gen, t_.to(y), y, v)
     params = [p for l in net.linears() for p in (l.weight, l.bias)]
+    if tc_ok(gen, y.shape[1]):
+        return _SsmMlpTc.apply(gen, t_, y.detach(), v, *params)
     return _SsmMlp.apply(gen, t_, y.detach(), v, *params)
 
 

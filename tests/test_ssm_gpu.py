@@ -219,3 +219,84 @@ def test_ssm_prepare_kernel(kind, d):
     assert float((t2.reshape(-1) - t[B // 2:]).abs().max()) == 0.0 and float((v2 - v[B // 2:]).abs().max()) == 0.0
     assert float((y2h - y[B // 2:]).abs().max()) == 0.0
     Bd.report(test=f"ssm-prepare-{kind}-d{d}", t_floor_frac=frac_floor, v_mean=float(v.mean()))
+
+
+# ---- tensor-core SSM step (csrc/ssm_tc.cu): fp16 operands / fp32 accumulation, one launch for loss + backward + wgrad ----------
+# Stated tolerance of this mode: loss 2e-3 of max|loss|, gradients 3e-3 of max|grad| per parameter tensor.
+STC_LTOL, STC_GTOL = 2e-3, 3e-3  # observed: loss <= 9e-4, gradients <= 8e-4
+
+
+@pytest.mark.parametrize("name", [n for n in G.names("t") if "d32" not in n])
+def test_golden_ssm_tensor_core(name):
+    """The reference's own loss / gradient fixtures (autograd double backward) against the tcgen05 step."""
+    meta, arr = G.load(name)
+    if meta["dim"] > 16:
+        pytest.skip("f16tc SSM step covers d <= 16")
+    _, _, gen = Bd.gen_from(meta, arr, DEV)
+    gen.ssm_precision = "f16tc"
+    grads = [arr[k] for i in range(4) for k in (f"gW{i}", f"gb{i}")]
+    _check(name + "-f16tc", gen, arr["t"], arr["x"], arr["y"], arr["v"], arr["loss"], grads, STC_LTOL, STC_GTOL)
+    assert P._lib.debug_flags(DEV) == 0
+
+
+@pytest.mark.parametrize("kind,d,pre,B", [("msgm_dense", 8, True, 64), ("msgm_dense", 8, True, 1000),
+                                          ("msgm_dense", 3, True, 257), ("msgm_dense", 16, True, 333),
+                                          ("msgm_sparse", 5, False, 100), ("msgm_sparse", 12, True, 129),
+                                          ("sgm", 7, False, 64), ("sgm", 16, False, 4100), ("msgm_dense", 2, True, 20000)])
+def test_ssm_tensor_core_against_oracle(kind, d, pre, B):
+    """Ragged batches (partial tiles, several tiles per CTA), every SDE kind, both layer-1 widths."""
+    torch.manual_seed(700 + d)
+    sde = O.make_sgm(d) if kind == "sgm" else O.make_msgm(torch.randn(256, d) * 1.5, dense=(kind == "msgm_dense"))
+    mlp = O.init_mlp(d, pre, seed=d, scale=3.0)
+    for p in mlp.parameters():
+        p.requires_grad_(True)
+    t = torch.rand(B, 1).clamp_min(1e-3)
+    y = (torch.randn(B, d) * 1.4).requires_grad_()
+    v = O.sample_rademacher((B, d))
+    loss = O.ssm_loss(O.OReverse(sde, mlp), t, y, v)
+    grads = torch.autograd.grad(loss.mean(), mlp.parameters())
+    for p in mlp.parameters():
+        p.requires_grad_(False)
+    _, _, gen = Bd.from_oracle(sde, mlp, DEV)
+    gen.ssm_precision = "f16tc"
+    _check(f"ssm-tc-oracle-{kind}-d{d}-B{B}", gen, t, y.detach(), y.detach(), v, loss.detach(), [g.detach() for g in grads],
+           STC_LTOL, STC_GTOL)
+    assert P._lib.debug_flags(DEV) == 0
+
+
+def test_ssm_tensor_core_graphed_training_tracks_fp32():
+    """train.GraphedSsmStep with ssm_precision = "f16tc": the whole iteration (prologue, fused tensor-core step, partial
+    sum, Adam) replays as one graph and, on the same seeds and Philox streams, follows the fp32 mode's training trajectory;
+    the loss on a fixed held-out (t, y, v) goes down."""
+    from sdeflow_light_b200.train import GraphedSsmStep
+    d = 2
+    data = O.swiss_roll(8192).to(DEV)
+    T = Bd.T_param(1.0)
+    hist, evals = {}, {}
+    for prec in ("fp32", "f16tc"):
+        torch.manual_seed(4)
+        base = P.MSGMsde(data.cpu(), beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=True, norm_map="log",
+                         num_steps_forward=16, device=DEV, estim_cst_norm_dens_r_T=False)
+        gen = P.PluginReverseSDE(base, P.MLP(d, premodule="NormalizeLogRadius").to(DEV), T, deviceReverseSDE=DEV).to(DEV)
+        if prec == "f16tc":  # same random G and initial weights as the fp32 run
+            gen.base_sde.G.copy_(G0)
+            gen.base_sde.L_G.copy_(LG0)
+            gen.load_state_dict(sd0)
+        else:
+            G0, LG0, sd0 = gen.base_sde.G.clone(), gen.base_sde.L_G.clone(), {k: v.clone() for k, v in gen.state_dict().items()}
+        gen.ssm_precision = prec
+        gen.device_rng = True
+        gen._rng = (5, None, 0)
+        with torch.no_grad():
+            te, ye, ve = gen._prepare(data[:2048])
+            before = float(gen.ssm_loss(te, data[:2048], ye, ve).mean())
+        step = GraphedSsmStep(gen, (512, d), lr=2e-3, seed=77)
+        torch.manual_seed(9)
+        hist[prec] = [float(step(data[torch.randint(0, data.shape[0], (512,), device=DEV)])) for _ in range(200)]
+        with torch.no_grad():
+            evals[prec] = (before, float(gen.ssm_loss(te, data[:2048], ye, ve).mean()))
+    dmax = max(abs(a - b) for a, b in zip(hist["fp32"], hist["f16tc"]))
+    Bd.report(test="ssm-tc-graphed-training", max_loss_diff=dmax, eval_fp32=evals["fp32"], eval_f16tc=evals["f16tc"])
+    assert P._lib.debug_flags(DEV) == 0
+    assert dmax < 5e-3, dmax
+    assert evals["f16tc"][1] < evals["f16tc"][0] - 0.005 and abs(evals["f16tc"][1] - evals["fp32"][1]) < 5e-3

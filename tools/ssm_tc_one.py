@@ -1,0 +1,27 @@
+"""A few eager SSM training iterations for the ncu launch list: python tools/ssm_tc_one.py [batch] [precision] [dim]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import bench  # noqa: E402
+from sdeflow_light_b200 import ssm_fused  # noqa: E402
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+prec = sys.argv[2] if len(sys.argv) > 2 else "f16tc"
+d = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+dev = torch.device("cuda", 0)
+prob = bench.build_problem(d)
+P, gen = bench.package_objects(prob, dev)
+gen.ssm_precision = prec
+gen.train()
+gen.device_rng = True
+x = prob["data"][:batch].to(dev) if batch <= 100000 else None
+n = sum(p.numel() for p in gen.a.parameters())
+flat = torch.zeros(n, device=dev)
+gout = torch.full((batch,), 1.0 / batch, device=dev)
+for _ in range(4):
+    t_, y, v = gen._prepare(x)
+    loss = ssm_fused.fused_loss_and_grads(gen, t_, y, v, gout, flat)
+torch.cuda.synchronize()
+print("ok", float(loss.mean()), float(flat.abs().max()), P._lib.debug_flags(dev))

@@ -33,6 +33,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "msgm_common.cuh"
 #include "tc_ptx.cuh"
@@ -58,7 +59,8 @@ struct StcLayout {
   static constexpr int oW4f = oBias + 4 * (256 + DP);  // fp32 [DP][128]          W4 for the CUDA-core data gradient
   static constexpr int oX = oW4f + 4 * DP * 128;       // fp32 [128 rows][DP]     output cotangents in fp32
   static constexpr int oDb = oX + 4 * 128 * DP;        // fp32 db2[128] db3[128] db4[DP]  (accumulated over the CTA's tiles)
-  static constexpr int oG = oDb + 4 * (256 + DP);      // fp32 dense G [d][d][d] (d <= 16)
+  static constexpr int oQ = oDb + 4 * (256 + DP);      // fp32 [128 rows][DP]     second half of the q partial sums
+  static constexpr int oG = oQ + 4 * 128 * DP;         // fp32 dense G [d][d][d] (d <= 16)
   static constexpr int oBar = oG + 4 * 16 * 16 * 16;
   static constexpr int SMEM = oBar + 64;
 };
@@ -80,6 +82,7 @@ struct StcParams {
                         // fp16 tensor-core operands, and gout = 1/B of a batch mean would put them in the subnormal range
   long long B;
   TcFlags flags;
+  long long* prof;  // NULL, or 24 cycle counters of CTA 0 / thread 0 (MSGM_TC_PROF; msgm_debug_counters)
 };
 
 constexpr uint32_t IDESC_A_MN = 1u << 15, IDESC_B_MN = 1u << 16;  // "transposed" (MN-major) operand bits
@@ -99,6 +102,35 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
+// sum over the 16 lanes of equal parity of 16 per-lane values: returns sum_lanes v[pair_col(lane)]   (15 shuffles)
+__device__ __forceinline__ float warp_pair_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 2; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off / 2; ++i) {
+      const float send = up ? v[i] : v[i + off / 2];
+      const float keep = up ? v[i + off / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// The two rows of a sample (primal row in the even lane, tangent row in the odd lane) need each other's values in every
+// epilogue.  Instead of both lanes evaluating sigmoid / phi' / phi'' of all 32 columns of a chunk, each lane takes 16 columns
+// for BOTH rows: the even lane columns 0..15, the odd lane columns 16..31 (16 shuffles instead of 32, half the MUFU work).
+// p[j] / t[j] = primal-row / tangent-row value of this lane's column j.
+__device__ __forceinline__ void pair_split(const uint32_t (&mine)[32], bool primal, float (&p)[16], float (&t)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float lo = __uint_as_float(mine[j]), hi = __uint_as_float(mine[16 + j]);
+    const float recv = __shfl_xor_sync(0xffffffffu, primal ? hi : lo, 1);
+    p[j] = primal ? lo : recv;
+    t[j] = primal ? recv : hi;
+  }
+}
+
 // 8 fp32 -> one 16-byte store of 8 fp16 at (row, 8-column chunk) of a [chunk][128 rows][8] tile
 __device__ __forceinline__ void store_chunk(unsigned char* tile, int row, int chunk, const float* x) {
   *reinterpret_cast<uint4*>(tile + chunk * 2048 + row * 16) =
@@ -114,6 +146,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
   float* sX = reinterpret_cast<float*>(smem + L::oX);
   float* sDb = reinterpret_cast<float*>(smem + L::oDb);
   float* sG = reinterpret_cast<float*>(smem + L::oG);
+  float* sQ = reinterpret_cast<float*>(smem + L::oQ);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::oBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -180,6 +213,16 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
   const uint32_t sbase = smem_u32(smem);
   uint32_t par = 0;
   bool ok = true;
+  long long* prof = (P.prof && blockIdx.x == 0 && tid == 0) ? P.prof : nullptr;
+  long long tprev = prof ? clock64() : 0;
+  auto tick = [&](int slot) {
+    if (prof) {
+      const long long now = clock64();
+      prof[slot] += now - tprev;
+      tprev = now;
+    }
+  };
+  tick(17);  // setup
 
   // K-major [chunk][rows][8] tile with `rows` rows: the two 8-column chunks of a K=16 slice are rows*16 bytes apart
   auto kdesc = [&](int off, int slice, int rows) { return umma_desc(sbase + off + slice * rows * 32, rows * 16, 128); };
@@ -199,58 +242,61 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
   constexpr uint32_t ID_H = umma_idesc_f16(128, 128), ID_O = umma_idesc_f16(128, 16), ID_1 = umma_idesc_f16(128, K1);
   constexpr uint32_t D1 = 0, D2 = 128, D3 = 256, WK = 384;  // TMEM column bases
 
+  const int rowP = row & ~1, rowT = row | 1;  // the sample's primal / tangent tile rows
   // Forward epilogue of hidden layer l (1..3): (z; zdot) in TMEM -> (h; hdot) = (phi(z); phi'(z) zdot) as fp16 rows of `dst`.
   auto fwd_epilogue = [&](uint32_t dcol, const float* bias, int dst) {
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      const int col0 = 64 * half + 32 * c;
+      const int col0 = 64 * half + 32 * c, cb = col0 + (primal ? 0 : 16);
       uint32_t r[32];
       TMEM_LD32(tlane + dcol + col0, r);
       tc_wait_ld();
-      float o[32];
+      float z[16], zd[16];
+      pair_split(r, primal, z, zd);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float mine = __uint_as_float(r[j]) + ((bias != nullptr && primal) ? bias[col0 + j] : 0.0f);
-        const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-        const float z = primal ? mine : other, zd = primal ? other : mine;
-        const float sg = fmaf(0.5f, tanh_fast(0.5f * z), 0.5f);  // sigmoid(z), one MUFU op
-        o[j] = primal ? z * sg : sg * fmaf(z, 1.0f - sg, 1.0f) * zd;
+      for (int j = 0; j < 16; ++j) {
+        const float zz = z[j] + (bias != nullptr ? bias[cb + j] : 0.0f);
+        const float sg = fmaf(0.5f, tanh_fast(0.5f * zz), 0.5f);  // sigmoid(z), one MUFU op
+        z[j] = zz * sg;
+        zd[j] = sg * fmaf(zz, 1.0f - sg, 1.0f) * zd[j];
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) store_chunk(smem + dst, row, (col0 >> 3) + q, o + 8 * q);
+      store_chunk(smem + dst, rowP, cb >> 3, z);
+      store_chunk(smem + dst, rowP, (cb >> 3) + 1, z + 8);
+      store_chunk(smem + dst, rowT, cb >> 3, zd);
+      store_chunk(smem + dst, rowT, (cb >> 3) + 1, zd + 8);
     }
   };
-  // Backward epilogue of hidden layer l: hbar / hdotbar (this row's entry, from `hb`) and (z; zdot) -> cotangents
-  //   zbar = hbar phi'(z) + hdotbar phi''(z) zdot (primal rows),  zdotbar = hdotbar phi'(z) (tangent rows)
-  // written as fp16 rows of `dst`; the bias gradient sum over primal rows of zbar goes to db (shared-memory accumulator).
-  auto bwd_epilogue = [&](uint32_t dcol, const float* bias, int dst, float* db, auto&& hb_of) {
+  // Backward epilogue of hidden layer l: (hbar; hdotbar) of this lane's 16 columns (from `hb_pair`) and (z; zdot) ->
+  //   zbar = hbar phi'(z) + hdotbar phi''(z) zdot (primal row),  zdotbar = hdotbar phi'(z) (tangent row)
+  // written as fp16 rows of `dst`; the bias gradient sum over the primal rows of zbar goes to db (shared-memory accumulator).
+  auto bwd_epilogue = [&](uint32_t dcol, const float* bias, int dst, float* db, auto&& hb_pair) {
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      const int col0 = 64 * half + 32 * c;
-      uint32_t r[32];
-      TMEM_LD32(tlane + dcol + col0, r);
-      tc_wait_ld();
-      float hb[32];
-      hb_of(col0, hb);
-      float o[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float mine = __uint_as_float(r[j]) + ((bias != nullptr && primal) ? bias[col0 + j] : 0.0f);
-        const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-        const float hbo = __shfl_xor_sync(0xffffffffu, hb[j], 1);
-        const float z = primal ? mine : other, zd = primal ? other : mine;
-        const float sg = fmaf(0.5f, tanh_fast(0.5f * z), 0.5f);
-        const float d1 = sg * fmaf(z, 1.0f - sg, 1.0f);
-        const float d2 = sg * (1.0f - sg) * fmaf(z, 1.0f - 2.0f * sg, 2.0f);
-        o[j] = primal ? fmaf(hb[j], d1, hbo * d2 * zd) : hb[j] * d1;
+      const int col0 = 64 * half + 32 * c, cb = col0 + (primal ? 0 : 16);
+      float z[16], zd[16], hp[16], ht[16];
+      {
+        uint32_t r[32];
+        TMEM_LD32(tlane + dcol + col0, r);
+        tc_wait_ld();
+        pair_split(r, primal, z, zd);
       }
+      hb_pair(col0, cb, hp, ht);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) store_chunk(smem + dst, row, (col0 >> 3) + q, o + 8 * q);
+      for (int j = 0; j < 16; ++j) {
+        const float zz = z[j] + (bias != nullptr ? bias[cb + j] : 0.0f);
+        const float sg = fmaf(0.5f, tanh_fast(0.5f * zz), 0.5f);
+        const float d1 = sg * fmaf(zz, 1.0f - sg, 1.0f);
+        const float d2 = sg * (1.0f - sg) * fmaf(zz, 1.0f - 2.0f * sg, 2.0f);
+        z[j] = fmaf(hp[j], d1, ht[j] * d2 * zd[j]);
+        zd[j] = ht[j] * d1;
+      }
+      store_chunk(smem + dst, rowP, cb >> 3, z);
+      store_chunk(smem + dst, rowP, (cb >> 3) + 1, z + 8);
+      store_chunk(smem + dst, rowT, cb >> 3, zd);
+      store_chunk(smem + dst, rowT, (cb >> 3) + 1, zd + 8);
       if (db != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = primal ? o[j] : 0.0f;
-        const float s = warp_transpose_sum(o, lane);
-        atomicAdd(db + col0 + lane, s);
+        const float sum = warp_pair_sum16(z, lane);  // over this warp's 16 samples, column cb + bits(4..1) of the lane
+        atomicAdd(db + cb + (((lane >> 4) & 1) << 3 | ((lane >> 3) & 1) << 2 | ((lane >> 2) & 1) << 1 | ((lane >> 1) & 1)), sum);
       }
     }
   };
@@ -262,14 +308,14 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
       uint32_t r[32];
       TMEM_LD32(tlane + dcol + col0, r);
       tc_wait_ld();
-      float4* dst = reinterpret_cast<float4*>(part + goff + row * 128 + col0);
+      // fire-and-forget 16-byte reductions into this CTA's private slice (no read latency, no contention)
+      float* dst = part + goff + row * 128 + col0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 g = dst[q];
-        g.x += __uint_as_float(r[4 * q]); g.y += __uint_as_float(r[4 * q + 1]);
-        g.z += __uint_as_float(r[4 * q + 2]); g.w += __uint_as_float(r[4 * q + 3]);
-        dst[q] = g;
-      }
+      for (int q = 0; q < 8; ++q)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(r[4 * q])),
+                     "f"(__uint_as_float(r[4 * q + 1])), "f"(__uint_as_float(r[4 * q + 2])),
+                     "f"(__uint_as_float(r[4 * q + 3]))
+                     : "memory");
     }
   };
 
@@ -281,7 +327,9 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
     float gout = 0.0f, half_bv2 = 0.0f;
 
     // ---- layer-1 operand: (u; udot) of the premodule (NN.py:64-70) and q ----------------------------------------------------
-    if (half == 0) {
+    // The four threads of a sample (primal / tangent lane x two column halves) all load y and v; the half-0 pair writes the
+    // layer-1 operand; the d^3 contraction of q is split four ways (i by column half, j by lane parity).
+    {
       float yv[DP], vv[DP];
       float r2 = 0.0f, ydotv = 0.0f, v2 = 0.0f;
 #pragma unroll
@@ -296,30 +344,31 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
       gout = live ? P.gout[b] * P.cot_scale : 0.0f;
       const float bt = beta_of(P.bmin, P.bdel, s), sb = sqrtf(bt);
       if (KIND == MSGM_SDE_SGM) half_bv2 = 0.5f * bt * v2;
-      float x[K1];
+      if (half == 0) {
+        float x[K1];
 #pragma unroll
-      for (int k = 0; k < K1; ++k) x[k] = 0.0f;
-      if (P.pre) {
-        const float r = sqrtf(r2), rn = r + 1e-6f, rdot = ydotv / r;
+        for (int k = 0; k < K1; ++k) x[k] = 0.0f;
+        if (P.pre) {
+          const float r = sqrtf(r2), rn = r + 1e-6f, rdot = ydotv / r;
 #pragma unroll
-        for (int c = 0; c < DP; ++c)
-          if (c < d) x[c] = primal ? yv[c] / rn : vv[c] / rn - yv[c] * rdot / (rn * rn);
-        // runtime column d: written through a select chain so that x[] stays in registers
+          for (int c = 0; c < DP; ++c)
+            if (c < d) x[c] = primal ? yv[c] / rn : vv[c] / rn - yv[c] * rdot / (rn * rn);
 #pragma unroll
-        for (int k = 0; k < K1; ++k)
-          if (k == d) x[k] = primal ? logf(rn) : rdot / rn;
-      } else {
+          for (int k = 0; k < K1; ++k)  // runtime column d through a select chain: x[] stays in registers
+            if (k == d) x[k] = primal ? logf(rn) : rdot / rn;
+        } else {
 #pragma unroll
-        for (int c = 0; c < DP; ++c)
-          if (c < d) x[c] = primal ? yv[c] : vv[c];
+          for (int c = 0; c < DP; ++c)
+            if (c < d) x[c] = primal ? yv[c] : vv[c];
+        }
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+          if (k == d + P.pre) x[k] = primal ? s : 0.0f;           // time input
+          if (k == d + P.pre + 1) x[k] = primal ? 1.0f : 0.0f;    // ones column: the bias b1 rides on the tensor pipe
+        }
+#pragma unroll
+        for (int ch = 0; ch < K1 / 8; ++ch) store_chunk(smem + L::oIn0, row, ch, x + 8 * ch);
       }
-#pragma unroll
-      for (int k = 0; k < K1; ++k) {
-        if (k == d + P.pre) x[k] = primal ? s : 0.0f;           // time input
-        if (k == d + P.pre + 1) x[k] = primal ? 1.0f : 0.0f;    // ones column: the bias b1 rides on the tensor pipe
-      }
-#pragma unroll
-      for (int ch = 0; ch < K1 / 8; ++ch) store_chunk(smem + L::oIn0, row, ch, x + 8 * ch);
       // q_k: MSGM dense sqrt(beta) sum_ij v_i G_ijk y_j; sparse c sqrt(beta) (v_k y_{k+1} - v_{k+1} y_k); SGM sqrt(beta) v_k
 #pragma unroll
       for (int k = 0; k < DP; ++k) q[k] = 0.0f;
@@ -339,24 +388,34 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
           q[k] = k < d ? SQRT_HALF * sb * (vv[k] * yn - vn * yv[k]) : 0.0f;
         }
       } else {
-        for (int i = 0; i < d; ++i) {
-          float vi = 0.0f;
+        const int jpar = primal ? 0 : 1;
 #pragma unroll
-          for (int e = 0; e < DP; ++e) vi = (e == i) ? vv[e] : vi;
-          for (int j = 0; j < d; ++j) {
-            float yj = 0.0f;
+        for (int i2 = 0; i2 < DP / 2; ++i2) {
 #pragma unroll
-            for (int e = 0; e < DP; ++e) yj = (e == j) ? yv[e] : yj;
-            const float w = sb * vi * yj;
-            const float* g = sG + (i * d + j) * d;
+          for (int j2 = 0; j2 < DP / 2; ++j2) {
+            // i = 2 i2 + half, j = 2 j2 + jpar: compile-time register picks, two selects instead of a DP-way chain
+            const float vi = half ? vv[2 * i2 + 1] : vv[2 * i2];
+            const float yj = jpar ? yv[2 * j2 + 1] : yv[2 * j2];
+            const int i = 2 * i2 + half, j = 2 * j2 + jpar;
+            if (i < d && j < d) {
+              const float w = sb * vi * yj;
+              const float* g = sG + (i * d + j) * d;
 #pragma unroll
-            for (int k = 0; k < DP; ++k)
-              if (k < d) q[k] = fmaf(w, g[k], q[k]);
+              for (int k = 0; k < DP; ++k)
+                if (k < d) q[k] = fmaf(w, g[k], q[k]);
+            }
           }
+        }
+#pragma unroll
+        for (int k = 0; k < DP; ++k) q[k] += __shfl_xor_sync(0xffffffffu, q[k], 1);  // the two j halves
+        if (half == 1) {
+#pragma unroll
+          for (int k = 0; k < DP; ++k) sQ[row * DP + k] = q[k];  // the other i half: added by the half-0 thread in the loss phase
         }
       }
     }
     publish();
+    tick(0);
 
     // ---- forward: three hidden layers and the output layer ---------------------------------------------------------------
     if (warp == 0) {
@@ -365,36 +424,47 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
       umma_commit(bar, 0);
     }
     wait_mma();
+    tick(1);
     fwd_epilogue(D1, nullptr, L::oIn1);
     publish();
+    tick(2);
     if (warp == 0) {
 #pragma unroll
       for (int s = 0; s < 8; ++s) umma_ss(tbase + D2, kdesc(L::oIn1, s, 128), kdesc(L::oW2, s, 128), ID_H, s > 0, 0);
       umma_commit(bar, 0);
     }
     wait_mma();
+    tick(3);
     fwd_epilogue(D2, sB2, L::oIn2);
     publish();
+    tick(4);
     if (warp == 0) {
 #pragma unroll
       for (int s = 0; s < 8; ++s) umma_ss(tbase + D3, kdesc(L::oIn2, s, 128), kdesc(L::oW3, s, 128), ID_H, s > 0, 0);
       umma_commit(bar, 0);
     }
     wait_mma();
+    tick(5);
     fwd_epilogue(D3, sB2 + 128, L::oIn3);
     publish();
+    tick(6);
     if (warp == 0) {
 #pragma unroll
       for (int s = 0; s < 8; ++s) umma_ss(tbase + WK, kdesc(L::oIn3, s, 128), kdesc(L::oW4, s, 16), ID_O, s > 0, 0);
       umma_commit(bar, 0);
     }
     wait_mma();
+    tick(7);
 
     // ---- loss and output cotangents: abar = gout a (primal rows), adotbar = gout q (tangent rows) ------------------------------
     if (half == 0) {
       uint32_t r[16];
       TMEM_LD16(tlane + WK, r);
       tc_wait_ld();
+      if (KIND == MSGM_SDE_MSGM_DENSE) {
+#pragma unroll
+        for (int k = 0; k < DP; ++k) q[k] += sQ[row * DP + k];
+      }
       float lp = 0.0f, x[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
@@ -404,7 +474,11 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
           lp = primal ? fmaf(0.5f * a, a, lp) : fmaf(q[c], a, lp);
           x[c] = gout * (primal ? a : q[c]);
           sX[row * DP + c] = x[c];
-          if (primal && c < d) atomicAdd(sDb + 256 + c, x[c]);
+          // bias gradient of the output layer: sum of abar over the warp's primal rows, one shared-memory atomic per warp
+          float sabar = primal ? x[c] : 0.0f;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) sabar += __shfl_xor_sync(0xffffffffu, sabar, off);
+          if (lane == 0 && c < d) atomicAdd(sDb + 256 + c, sabar);
         } else {
           x[c] = 0.0f;
         }
@@ -415,6 +489,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
       store_chunk(smem + L::oC4, row, 1, x + 8);
     }
     publish();
+    tick(8);
 
     // ---- backward -----------------------------------------------------------------------------------------------------------
     // layer 4 weight gradient, transposed: gW4^T [in 128][out 16] = H3^T Cot4 (both MN-major, K = rows)
@@ -425,38 +500,46 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
       umma_commit(bar, 0);
     }
     wait_mma();
+    tick(9);
     if (half == 0) {  // row = input feature of W4
       uint32_t r[16];
       TMEM_LD16(tlane + WK, r);
       tc_wait_ld();
 #pragma unroll
       for (int o = 0; o < 16; ++o)
-        if (o < d) part[gW4 + o * 128 + row] += __uint_as_float(r[o]);
+        if (o < d) atomicAdd(part + gW4 + o * 128 + row, __uint_as_float(r[o]));  // result unused: a fire-and-forget RED
     }
-    {  // layer 3: hbar = Cot4 W4 on the CUDA cores (K = d is tiny), cotangents into the tile of H3
-      float cot[DP];
+    {  // layer 3: (hbar; hdotbar) = Cot4 W4 on the CUDA cores (K = d is tiny), cotangents into the tile of H3
+      float cp[DP], ct[DP];
 #pragma unroll
-      for (int c = 0; c < DP; ++c) cot[c] = sX[row * DP + c];
-      bwd_epilogue(D3, sB2 + 128, L::oIn3, sDb + 128, [&](int col0, float (&hb)[32]) {
+      for (int c = 0; c < DP; ++c) {
+        cp[c] = sX[rowP * DP + c];
+        ct[c] = sX[rowT * DP + c];
+      }
+      bwd_epilogue(D3, sB2 + 128, L::oIn3, sDb + 128, [&](int, int cb, float (&hp)[16], float (&ht)[16]) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) hb[j] = 0.0f;
+        for (int j = 0; j < 16; ++j) hp[j] = ht[j] = 0.0f;
         for (int o = 0; o < d; ++o) {
-          float co = 0.0f;
+          float a = 0.0f, bq = 0.0f;
 #pragma unroll
-          for (int e = 0; e < DP; ++e) co = (e == o) ? cot[e] : co;
-          const float4* w = reinterpret_cast<const float4*>(sW4f + o * 128 + col0);
+          for (int e = 0; e < DP; ++e) {
+            a = (e == o) ? cp[e] : a;
+            bq = (e == o) ? ct[e] : bq;
+          }
+          const float4* w = reinterpret_cast<const float4*>(sW4f + o * 128 + cb);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
+          for (int j4 = 0; j4 < 4; ++j4) {
             const float4 ww = w[j4];
-            hb[4 * j4] = fmaf(co, ww.x, hb[4 * j4]);
-            hb[4 * j4 + 1] = fmaf(co, ww.y, hb[4 * j4 + 1]);
-            hb[4 * j4 + 2] = fmaf(co, ww.z, hb[4 * j4 + 2]);
-            hb[4 * j4 + 3] = fmaf(co, ww.w, hb[4 * j4 + 3]);
+            hp[4 * j4] = fmaf(a, ww.x, hp[4 * j4]);         ht[4 * j4] = fmaf(bq, ww.x, ht[4 * j4]);
+            hp[4 * j4 + 1] = fmaf(a, ww.y, hp[4 * j4 + 1]); ht[4 * j4 + 1] = fmaf(bq, ww.y, ht[4 * j4 + 1]);
+            hp[4 * j4 + 2] = fmaf(a, ww.z, hp[4 * j4 + 2]); ht[4 * j4 + 2] = fmaf(bq, ww.z, ht[4 * j4 + 2]);
+            hp[4 * j4 + 3] = fmaf(a, ww.w, hp[4 * j4 + 3]); ht[4 * j4 + 3] = fmaf(bq, ww.w, ht[4 * j4 + 3]);
           }
         }
       });
     }
     publish();
+    tick(10);
     for (int l = 3; l >= 2; --l) {
       // gW_l = Cot_l^T H_{l-1} into layer l's own (dead) TMEM columns; Hbar_{l-1} = Cot_l W_l into the working columns
       const int cotT = l == 3 ? L::oIn3 : L::oIn2, inT = l == 3 ? L::oIn2 : L::oIn1, wT = l == 3 ? L::oW3 : L::oW2;
@@ -470,17 +553,19 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
         umma_commit(bar, 0);
       }
       wait_mma();
+      tick(l == 3 ? 11 : 13);
       flush_tile(dl, l == 3 ? gW3 : gW2);
-      auto hb_tmem = [&](int col0, float (&hb)[32]) {
+      tick(l == 3 ? 18 : 19);
+      auto hb_tmem = [&](int col0, int, float (&hp)[16], float (&ht)[16]) {
         uint32_t r[32];
         TMEM_LD32(tlane + WK + col0, r);
         tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) hb[j] = __uint_as_float(r[j]);
+        pair_split(r, primal, hp, ht);
       };
       if (l == 3) bwd_epilogue(D2, sB2, L::oIn2, sDb, hb_tmem);
       else bwd_epilogue(D1, nullptr, L::oIn1, nullptr, hb_tmem);  // b1 is inside D1; its gradient comes out of gW1's ones column
       publish();
+      tick(l == 3 ? 12 : 14);
     }
     // layer 1: gW1 [out 128][K1] = Cot1^T (u; udot); column K1ref is the bias gradient
     if (warp == 0) {
@@ -490,6 +575,7 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
       umma_commit(bar, 0);
     }
     wait_mma();
+    tick(15);
     if (half == 0) {
 #pragma unroll
       for (int c = 0; c < K1 / 16; ++c) {
@@ -499,14 +585,15 @@ __global__ void __launch_bounds__(STC_THREADS, 1) ssm_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int k = 16 * c + j;
-          if (k < K1ref) part[gW1 + row * K1ref + k] += __uint_as_float(r[j]);
-          else if (k == K1ref) part[gb1 + row] += __uint_as_float(r[j]);
+          if (k < K1ref) atomicAdd(part + gW1 + row * K1ref + k, __uint_as_float(r[j]));
+          else if (k == K1ref) atomicAdd(part + gb1 + row, __uint_as_float(r[j]));
         }
       }
     }
     tc_fence_before();
     __syncthreads();  // every TMEM read of this tile is done before the next tile's products overwrite the columns
     tc_fence_after();
+    tick(16);
   }
 
   // ---- bias gradients of layers 2-4 accumulated in shared memory over the CTA's tiles ---------------------------------------------
@@ -539,6 +626,8 @@ static int launch_stc(msgm_ctx* ctx, StcParams& P, float* grad_flat, cudaStream_
   MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
   const int grid = ssm_tc_grid(ctx, P.B);
   P.flags = next_tc_flags(ctx);
+  P.prof = std::getenv("MSGM_TC_PROF") ? reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(ctx->ws) + 64) : nullptr;
+  if (P.prof) MSGM_CUDA_TRY(cudaMemsetAsync(P.prof, 0, 192, stream));
   kern<<<grid, STC_THREADS, L::SMEM, stream>>>(P);
   ssm_tc_reduce_kernel<<<(P.nparam + 255) / 256, 256, 0, stream>>>(P.part, grid, P.nparam, P.pstride, 1.0f / P.cot_scale, grad_flat);
   ctx->launches += 2;

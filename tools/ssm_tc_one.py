@@ -25,3 +25,12 @@ for _ in range(4):
     loss = ssm_fused.fused_loss_and_grads(gen, t_, y, v, gout, flat)
 torch.cuda.synchronize()
 print("ok", float(loss.mean()), float(flat.abs().max()), P._lib.debug_flags(dev))
+if os.environ.get("MSGM_TC_PROF"):
+    c = P._lib.debug_counters(dev)
+    ntile = max(1, -(-batch // 64) // 148 + (1 if (-(-batch // 64)) % 148 else 0)) if batch > 64 * 148 else 1
+    names = ["prologue", "F1 mma", "F1 epi", "F2 mma", "F2 epi", "F3 mma", "F3 epi", "F4 mma", "loss epi", "gW4 mma",
+             "B3 epi(+dgrad4)", "B3 mma", "B2 epi", "B2 mma", "B1 epi", "gW1 mma", "gW1 flush", "setup", "flush gW3", "flush gW2"]
+    print("cycles of CTA 0 thread 0 (whole launch; CTA 0 ran", ntile, "tiles):")
+    for n_, v_ in zip(names, c):
+        print(f"  {n_:18s} {v_:10d}")
+    print("  total", sum(c[:20]))

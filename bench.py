@@ -287,6 +287,8 @@ def time_gpu_train(P, gen, data_dev, batch: int, iters: int, world: int, dev, gr
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax.item())
     n_launch = gstep.launches_per_iter if graphed else (P._lib.launch_count(dev) - l0) / iters
+    if graphed:
+        gstep.close()  # collective teardown of the peer-memory all-reduce buffers (no-op on one GPU)
     return world * batch * iters / (ms / 1e3), ms / iters, n_launch, float(loss.detach())
 
 

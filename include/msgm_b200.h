@@ -221,6 +221,28 @@ int msgm_adam_step(msgm_ctx* ctx, const void* seg_table, int32_t n_tensors, int6
                    float* exp_avg, float* exp_avg_sq, const float* lr_dev, int64_t* step_dev, float beta1, float beta2,
                    float eps, float grad_scale, void* stream);
 
+/* Gradient all-reduce fused with the Adam update over NVLink peer memory (csrc/p2p.cu; one node, one process per GPU):
+ * what `dist.all_reduce(flat); flat /= world; optim.step()` does in a data-parallel run of the reference's loop
+ * (MSGM_higherDim.py:803-809), as two launches without a collective-library call.  Every rank pushes its flat gradient into
+ * a receive slot of every rank, raises a sequence flag there, and each rank's Adam kernel waits for the world's flags, sums
+ * the slots in rank order (bit-identical on all ranks) and updates.
+ *   msgm_p2p_create   allocates this rank's receive buffer (cudaMalloc) for gradients of up to nfloats floats and writes its
+ *                     64-byte CUDA IPC handle to handle_out; the caller all-gathers the handles (torch.distributed);
+ *   msgm_p2p_connect  all_handles: world x 64 bytes in rank order; opens the peers' buffers;
+ *   msgm_p2p_disconnect / msgm_p2p_destroy  teardown: every rank closes its peer mappings, the ranks synchronise, then
+ *                     each frees its own buffer (freeing memory a peer still maps can block);
+ *   msgm_p2p_allreduce_adam  arguments as msgm_adam_step (grad_scale is 1/world); grad_flat must be readable up to the
+ *                     next multiple of 4 floats.  Stream-ordered and CUDA-graph capturable; every rank must issue the same
+ *                     sequence of calls.  A peer that never arrives raises error code 3 (msgm_async_error) after ~2 s. */
+typedef struct msgm_p2p msgm_p2p;
+int msgm_p2p_create(msgm_ctx* ctx, int64_t nfloats, int32_t world, int32_t rank, msgm_p2p** out, unsigned char* handle_out);
+int msgm_p2p_connect(msgm_ctx* ctx, msgm_p2p* h, const unsigned char* all_handles);
+int msgm_p2p_disconnect(msgm_p2p* h);  /* closes the peers' buffers; call on every rank, then synchronise the ranks, then destroy */
+int msgm_p2p_destroy(msgm_p2p* h);
+int msgm_p2p_allreduce_adam(msgm_ctx* ctx, msgm_p2p* h, const void* seg_table, int32_t n_tensors, int64_t total,
+                            const float* grad_flat, float* exp_avg, float* exp_avg_sq, const float* lr_dev, int64_t* step_dev,
+                            float beta1, float beta2, float eps, void* stream);
+
 /* Log density of a 1-D Gaussian kernel density estimate at m query points: what MSGMsde.log_latent_pdf and the
  * normalising-constant estimate of the constructor ask sklearn's KernelDensity.score_samples for (SDEs.py:240,261,509;
  * kernel='gaussian', exact sum).  samples (n,), queries (m,), out (m,): device fp32. */

@@ -65,7 +65,8 @@ _lock = threading.Lock()
 _ctx = {}
 
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
-SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count", "msgm_async_error", "msgm_row_norm_stats", "msgm_survival_counts", "msgm_moments", "msgm_adam_step",
+SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count", "msgm_async_error", "msgm_row_norm_stats", "msgm_survival_counts", "msgm_moments", "msgm_adam_step", "msgm_p2p_create", "msgm_p2p_connect", "msgm_p2p_disconnect", "msgm_p2p_destroy",
+           "msgm_p2p_allreduce_adam",
            "msgm_sample_mlp", "msgm_noise_forward", "msgm_ssm_prepare", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward", "msgm_ssm_tc_scratch_bytes",
            "msgm_ssm_mlp_fwd_bwd_tc",
@@ -153,6 +154,12 @@ def lib() -> C.CDLL:
                 L.msgm_moments.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
                 L.msgm_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 5 + \
                     [C.c_float] * 4 + [C.c_void_p]
+                L.msgm_p2p_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_char_p]
+                L.msgm_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+                L.msgm_p2p_destroy.argtypes = [C.c_void_p]
+                L.msgm_p2p_disconnect.argtypes = [C.c_void_p]
+                L.msgm_p2p_allreduce_adam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64] + \
+                    [C.c_void_p] * 5 + [C.c_float] * 3 + [C.c_void_p]
                 L.msgm_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
                 L.msgm_sample_mlp.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.POINTER(MlpDesc),
                                               C.POINTER(SampleArgs), C.c_void_p, C.c_int64, C.c_void_p]
@@ -215,7 +222,7 @@ def debug_flags(device) -> int:
     return int(out.value)
 
 
-_ASYNC_MSG = {1: "a bounded mbarrier wait inside a tensor-core kernel timed out (the launch gave up; its output is "
+_ASYNC_MSG = {3: "p2p gradient all-reduce: a peer rank never delivered its gradient (timeout)", 1: "a bounded mbarrier wait inside a tensor-core kernel timed out (the launch gave up; its output is "
                    "undefined)", 2: "tensor-core kernel: shared-memory / TMEM base assumption violated"}
 
 

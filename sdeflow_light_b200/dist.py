@@ -42,3 +42,42 @@ def allreduce_grads_(params, average: bool = True, group=None):
         n = p.grad.numel()
         p.grad.copy_(flat[o:o + n].view_as(p.grad))
         o += n
+
+
+class P2PAllreduceAdam:
+    """Handle of the peer-memory all-reduce + Adam (csrc/p2p.cu) for one flat gradient of ``nfloats`` floats: allocates this
+    rank's receive buffer, exchanges the CUDA IPC handles over ``torch.distributed`` and opens the peers' buffers.  All ranks
+    of the group must live on one node (NVLink / PCIe peer access); construction raises otherwise and the caller keeps the
+    NCCL path."""
+
+    def __init__(self, device, nfloats: int, group=None):
+        import ctypes as C
+        from . import _lib
+        self.world, self.rank, self._group = dist.get_world_size(group), dist.get_rank(group), group
+        self.dev = torch.device(device)
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        _lib.check(_lib.lib().msgm_p2p_create(_lib.ctx(self.dev), int(nfloats), self.world, self.rank, C.byref(self._h), buf))
+        mine = torch.tensor(list(buf.raw), dtype=torch.uint8, device=self.dev)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=group)
+        blob = bytes(torch.cat(allh).cpu().tolist())
+        _lib.check(_lib.lib().msgm_p2p_connect(_lib.ctx(self.dev), self._h, blob))
+        dist.barrier(group)  # nobody pushes before every rank has opened every buffer
+
+    def step(self, seg_table, n_tensors, total, grad_flat, exp_avg, exp_avg_sq, lr, adam_step):
+        from . import _lib
+        _lib.check(_lib.lib().msgm_p2p_allreduce_adam(
+            _lib.ctx(self.dev), self._h, _lib.ptr(seg_table), n_tensors, total, _lib.ptr(grad_flat), _lib.ptr(exp_avg),
+            _lib.ptr(exp_avg_sq), _lib.ptr(lr), _lib.ptr(adam_step), 0.9, 0.999, 1e-8, _lib.stream_ptr(self.dev)))
+
+    def close(self):
+        """Collective teardown: every rank unmaps its peers' buffers, the ranks meet, then each frees its own."""
+        from . import _lib
+        if self._h:
+            torch.cuda.synchronize(self.dev)
+            _lib.lib().msgm_p2p_disconnect(self._h)
+            if dist.is_initialized():
+                dist.barrier(self._group)
+            _lib.lib().msgm_p2p_destroy(self._h)
+            self._h = None

@@ -36,7 +36,8 @@ class _SsmModule(torch.nn.Module):
 
 class GraphedSsmStep:
     def __init__(self, gen, batch_shape, lr: float = 1e-3, optimizer: torch.optim.Optimizer | None = None,
-                 warmup: int = 3, group=None, seed: int | None = None, graph_allreduce: bool = True):
+                 warmup: int = 3, group=None, seed: int | None = None, graph_allreduce: bool = True,
+                 p2p: bool | None = None):
         dev = torch.device(gen.deviceReverseSDE)
         if dev.type != "cuda":
             raise RuntimeError("sdeflow_light_b200 runs on CUDA only (no CPU fallback)")
@@ -56,7 +57,9 @@ class GraphedSsmStep:
         self.x = torch.zeros(*batch_shape, device=dev, dtype=torch.float32)
         self.loss = torch.zeros((), device=dev, dtype=torch.float32)
         # every .grad is a view into ONE flat buffer: the all-reduce needs no gather/scatter, Adam reads it in place
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev)
+        n_flat = sum(p.numel() for p in self.params)
+        self._flat_storage = torch.zeros((n_flat + 3) // 4 * 4, device=dev)  # padded: the peer push moves 16-byte words
+        self.flat = self._flat_storage[:n_flat]
         o = 0
         for p in self.params:
             p.grad = self.flat[o:o + p.numel()].view_as(p)
@@ -73,6 +76,18 @@ class GraphedSsmStep:
                 tab[i, 0], tab[i, 1] = p.data_ptr(), o
                 o += p.numel()
             self._seg_table = tab.to(dev)
+        # Several ranks on one node: the gradient all-reduce is fused with Adam over NVLink peer memory (csrc/p2p.cu) unless
+        # p2p=False / MSGM_NO_P2P=1 or the peers' buffers cannot be opened (then: NCCL all-reduce inside the graph).
+        self.p2p = None
+        import os
+        if self.world > 1 and self.opt is None and (p2p if p2p is not None else os.environ.get("MSGM_NO_P2P") != "1"):
+            try:
+                from .dist import P2PAllreduceAdam
+                self.p2p = P2PAllreduceAdam(dev, n_flat, group)
+            except (RuntimeError, ValueError) as exc:
+                if p2p:
+                    raise
+                self.p2p_error = str(exc)
         self.launches_per_iter = 0
         # Device-side random streams: a fixed seed plus a device counter bumped inside the graph, so every replay draws
         # fresh t / noise / v; the row offset makes a batch sharded over ranks draw what a single rank would.
@@ -142,6 +157,10 @@ class GraphedSsmStep:
     # -- the recorded part of the iteration ---------------------------------------------------------------------
     def _iteration(self):
         self._fwd_bwd()
+        if self.p2p is not None:  # push to the peers + wait / sum / Adam: two launches, no collective call
+            self.p2p.step(self._seg_table, len(self.params), self.flat.numel(), self.flat, self.exp_avg, self.exp_avg_sq,
+                          self.lr, self.adam_step)
+            return
         if self.world > 1:  # summed over ranks; the 1/world is folded into the Adam kernel's gradient scale
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self._opt_step()
@@ -176,6 +195,12 @@ class GraphedSsmStep:
         torch._foreach_copy_(self._grads, list(grads))
         self.loss.copy_(loss.detach())
         self._iter.add_(1)
+
+    def close(self):
+        """Release the peer-memory all-reduce buffers (collective: call on every rank before the process group goes away)."""
+        if self.p2p is not None:
+            self.p2p.close()
+            self.p2p = None
 
     # -- optimiser state in torch.optim.Adam's layout (what NN.save_checkpoint / the reference's loader expect) ---------
     def state_dict(self) -> dict:

@@ -221,6 +221,48 @@ int msgm_adam_step(msgm_ctx* ctx, const void* seg_table, int32_t n_tensors, int6
                    float* exp_avg, float* exp_avg_sq, const float* lr_dev, int64_t* step_dev, float beta1, float beta2,
                    float eps, float grad_scale, void* stream);
 
+/* ---- U-Net score nets: building blocks of the hand-written training path (csrc/unet_train.cu) ---------------------------------
+ * The SSM loss of a U-Net (PluginReverseSDE.ssm_loss, SDEs.py:616-646, over NNUnet1D.py:110-179 / model/unet.py:101-250) is
+ * evaluated in forward mode: every activation is a PAIR stacked along the batch axis, samples [0,B) primal, [B,2B) tangent.
+ * Convolutions / Linear layers are linear, so the inference entry points above (msgm_conv1d[_tc], msgm_conv2d_tc, ...) run
+ * them on the 2B-sample tensors (and, with flipped / transposed weights, their data gradients); these are the remaining ops.
+ * They replace what torch autograd + cuDNN did for the reference (F.gelu / SiLU and their double backward, conv weight
+ * gradients, nn.Linear, NormalizeLogRadius NN.py:56-70) on this path.
+ *   msgm_pair_act       act 0 = exact GELU, 1 = SiLU.  grad_h NULL: out = (phi(z); phi'(z) zdot).  grad_h given: out =
+ *                       (hbar phi' + hdotbar phi'' zdot; hdotbar phi').  z, out, grad_h: 2 * half_elems floats.
+ *   msgm_amax / msgm_pow2_scale  max|x| into a device float; y = x * 2^k with k such that max|x| lands at 2^target_exp
+ *                       (inverse: 2^-k).  Brackets the tensor-core data-gradient convs: deep-layer cotangents (~1e-7) sit in
+ *                       the fp16 subnormal range where the hi/lo operand split of msgm_conv*_tc would lose its bits.
+ *   msgm_rows_bias_add  x[n][c][p] += bias[c] for n < nrows (bias acts on the primal half only).
+ *   msgm_channel_sums   out[c] += sum_{n < nrows, p} x[n][c][p] (bias gradients).
+ *   msgm_tap_sums_1d    E[n][co][k] = sum of cot[n][co][p] over the output positions p whose tap k lands inside [0, Lin): the
+ *                       cotangent of the folded embedding table of msgm_emb_fold.
+ *   msgm_conv_wgrad     gW[co][coff + ci][ky][kx] += sum_{n,oy,ox} cot[n][co][oy][ox] in[n][ci][oy s + ky - pad][ox s + kx - pad]
+ *                       (in = channel concat [in1, in2], optionally nearest-upsampled x2; 1-D: Hi = Ho = KH = 1), all N samples.
+ *   msgm_gemm_f32       C = [C +] op(A) op(B) (row-major, fp32): the nn.Linear layers of the embedding MLPs and table folds.
+ *   msgm_premodule_pair xn (2B,d) = scale * (x / (|x| + 1e-6); its tangent along v), logn (2B) = (log(|x| + 1e-6); tangent).
+ *   msgm_sparse_ssm_loss  gout NULL: out[b] = q . adot + |a|^2/2 (+ beta |v|^2/2, SGM) from the net output pair a_pair
+ *                       (2B,d), q from the cyclic sparse tensor (SDEs.py:369-399) or sqrt(beta) v (SGM); gout given: out =
+ *                       the output cotangent pair (gout a; gout q), (2B,d). */
+int msgm_pair_act(msgm_ctx* ctx, const float* z, const float* grad_h_or_null, float* out, int64_t half_elems, int32_t act,
+                  void* stream);
+int msgm_amax(msgm_ctx* ctx, const float* x, int64_t n, float* amax_out, void* stream);
+int msgm_pow2_scale(msgm_ctx* ctx, const float* x, float* y, int64_t n, const float* amax_dev, int32_t target_exp,
+                    int32_t inverse, void* stream);
+int msgm_rows_bias_add(msgm_ctx* ctx, float* x, const float* bias, int64_t nrows, int32_t C, int64_t P, void* stream);
+int msgm_channel_sums(msgm_ctx* ctx, const float* x, float* out_accumulate, int64_t nrows, int32_t C, int64_t P, void* stream);
+int msgm_tap_sums_1d(msgm_ctx* ctx, const float* cot, float* E, int64_t N, int32_t Cout, int32_t K, int32_t stride, int32_t pad,
+                     int32_t Lin, int32_t Lout, void* stream);
+int msgm_conv_wgrad(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate, int32_t N,
+                    int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff, int32_t KH, int32_t KW, int32_t stride,
+                    int32_t pad, int32_t up, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, void* stream);
+int msgm_gemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t lda,
+                  int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b, int32_t accumulate, void* stream);
+int msgm_premodule_pair(msgm_ctx* ctx, const float* x, const float* v, float* xn_pair, float* logn_pair, int64_t B, int32_t d,
+                        float scale, void* stream);
+int msgm_sparse_ssm_loss(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* a_pair, const float* y, const float* v,
+                         const float* t, const float* gout_or_null, float* out, int64_t B, void* stream);
+
 /* Gradient all-reduce fused with the Adam update over NVLink peer memory (csrc/p2p.cu; one node, one process per GPU):
  * what `dist.all_reduce(flat); flat /= world; optim.step()` does in a data-parallel run of the reference's loop
  * (MSGM_higherDim.py:803-809), as two launches without a collective-library call.  Every rank pushes its flat gradient into

@@ -1,0 +1,477 @@
+// Building blocks of the hand-written score-matching TRAINING path of the U-Net score nets (NNUnet1D.py:110-179,
+// NNUnet.py / model/unet.py:101-250 under PluginReverseSDE.ssm_loss, SDEs.py:616-646).
+//
+// The loss needs the net output a(y) and its directional derivative adot = (da/dy) v.  Every activation of the training path
+// is therefore a PAIR stacked along the batch axis: samples [0,B) hold the primal, samples [B,2B) the tangent (forward
+// mode).  Linear layers (convolutions, Linear) act on both halves alike, so the inference kernels (tensor-core convs) run
+// them unchanged on the 2B-sample tensor; this file holds what inference does not have:
+//   pair_act_fwd / pair_act_bwd   (h; hdot) = (phi(z); phi'(z) zdot) and its backward
+//                                 (zbar; zdotbar) = (hbar phi' + hdotbar phi'' zdot; hdotbar phi'), phi = exact GELU or SiLU
+//   rows_bias_add                 bias on the primal half only
+//   conv_wgrad                    gW[co][ci][ky][kx] = sum_{n,oy,ox} cot[n][co][oy][ox] in[n][ci][oy s + ky - p][ox s + kx - p]
+//                                 over all 2B samples (1-D: H = 1), register-tiled fp32 with atomics across row slices
+//   channel_sums                  bias gradient: sum of cot over the primal half and all positions
+//   tap_sums_1d                   cotangent of the folded embedding table of the 1-D U-Net (NNUnet1D.py:156,162,175): per tap
+//                                 the sum of cot over the output positions whose tap lands inside the signal
+//   gemm_f32                      small dense products of the embedding MLPs and table folds (C = op(A) op(B) [+ C])
+//   premodule_pair                NormalizeLogRadius (NN.py:56-70) and its tangent, x sqrt(d) as the U-Nets apply it
+//   sparse_ssm_loss / _cot        loss_b = q . adot + |a|^2/2 (+ beta |v|^2/2, SGM) with q from the cyclic sparse tensor
+//                                 (SDEs.py:369-399) and the output cotangent pair (gout a; gout q)
+#include <algorithm>
+
+#include "msgm_common.cuh"
+
+namespace msgm {
+
+// ---- activations -----------------------------------------------------------------------------------------------------------
+struct ActD {
+  float h, d1, d2;
+};
+__device__ __forceinline__ ActD act_derivs(float z, int act) {
+  ActD r;
+  if (act == 0) {  // exact GELU: z Phi(z)
+    const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * z * z);
+    r.h = z * cdf;
+    r.d1 = cdf + z * pdf;
+    r.d2 = pdf * (2.0f - z * z);
+  } else {  // SiLU
+    const float sg = 1.0f / (1.0f + expf(-z));
+    r.h = z * sg;
+    r.d1 = sg * (1.0f + z * (1.0f - sg));
+    r.d2 = sg * (1.0f - sg) * (2.0f + z * (1.0f - 2.0f * sg));
+  }
+  return r;
+}
+
+// z: (2B, n) flattened per sample; first half primal, second half tangent
+__global__ void __launch_bounds__(256) pair_act_fwd_kernel(const float* __restrict__ z, float* __restrict__ h, long long half,
+                                                           int act) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < half; i += stride) {
+    const ActD a = act_derivs(z[i], act);
+    h[i] = a.h;
+    h[half + i] = a.d1 * z[half + i];
+  }
+}
+
+__global__ void __launch_bounds__(256) pair_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gh,
+                                                           float* __restrict__ gz, long long half, int act) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < half; i += stride) {
+    const ActD a = act_derivs(z[i], act);
+    const float hb = gh[i], hdb = gh[half + i];
+    gz[i] = fmaf(hb, a.d1, hdb * a.d2 * z[half + i]);
+    gz[half + i] = hdb * a.d1;
+  }
+}
+
+// Range scaling around the tensor-core data-gradient convs.  The tcgen05 convs split every fp32 operand into fp16 hi + lo; the
+// cotangents of the deep layers are ~1e-7 and smaller, i.e. inside / below the fp16 subnormal range, where the split loses its
+// bits.  amax_kernel finds max|x| (non-negative float bits are ordered as integers), pow2_scale_kernel multiplies by the power
+// of two that brings max|x| to 2^target (or by its inverse), so the conv sees O(1e4) values and nothing is rounded by the
+// scaling itself.
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ out) {
+  float m = 0.0f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f && isfinite(m)) atomicMax(out, __float_as_uint(m));
+}
+
+__device__ __forceinline__ float pow2_factor(const unsigned int* amax_bits, int target_exp, int inverse) {
+  const float m = __uint_as_float(*amax_bits);
+  if (!(m > 0.0f)) return 1.0f;
+  int e;
+  frexpf(m, &e);  // m = f 2^e, f in [0.5, 1)
+  const int k = max(-120, min(120, target_exp - e));
+  return ldexpf(1.0f, inverse ? -k : k);
+}
+
+__global__ void __launch_bounds__(256) pow2_scale_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                                                         const unsigned int* __restrict__ amax_bits, int target_exp, int inverse) {
+  const float f = pow2_factor(amax_bits, target_exp, inverse);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) y[i] = x[i] * f;
+}
+
+// x: (N, C, P): x[n][c][p] += bias[c] for n < nrows
+__global__ void __launch_bounds__(256) rows_bias_add_kernel(float* __restrict__ x, const float* __restrict__ bias, long long nrows,
+                                                            int C, long long P) {
+  const long long total = nrows * C * P, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) x[i] += bias[(i / P) % C];
+}
+
+// out[c] = sum_{n < nrows, p} x[n][c][p]
+__global__ void __launch_bounds__(256) channel_sums_kernel(const float* __restrict__ x, float* __restrict__ out, long long nrows,
+                                                           int C, long long P) {
+  const int c = blockIdx.x;
+  float s = 0.0f;
+  for (long long n = blockIdx.y; n < nrows; n += gridDim.y)
+    for (long long p = threadIdx.x; p < P; p += blockDim.x) s += x[(n * C + c) * P + p];
+  __shared__ float red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out + c, red[0]);
+}
+
+// E[n][co][k] = sum over output positions p with 0 <= p*stride + k - pad < Lin of cot[n][co][p]     (1-D)
+__global__ void __launch_bounds__(128) tap_sums_1d_kernel(const float* __restrict__ cot, float* __restrict__ E, int K, int stride,
+                                                          int pad, int Lin, int Lout) {
+  const long long nc = blockIdx.x;  // n * Cout + co
+  const float* row = cot + nc * Lout;
+  float s = 0.0f;
+  for (int p = threadIdx.x; p < Lout; p += blockDim.x) s += row[p];
+  __shared__ float red[128];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < K) {  // total minus the positions whose tap k falls outside [0, Lin)
+    const int k = threadIdx.x;
+    float t = red[0];
+    for (int p = 0; p < Lout && p * stride + k - pad < 0; ++p) t -= row[p];
+    for (int p = Lout - 1; p >= 0 && p * stride + k - pad >= Lin; --p) t -= row[p];
+    E[nc * K + k] = t;
+  }
+}
+
+// ---- weight gradient of a convolution ------------------------------------------------------------------------------------
+struct WgradConvParams {
+  const float* cot;   // (N, Cout, Ho, Wo)
+  const float* in1;   // (N, C1, Hi, Wi)
+  const float* in2;   // (N, C2, Hi, Wi) or NULL: channel concat [in1, in2]
+  float* gW;          // (Cout, Cw, KH, KW): channels [coff, coff + C1 + C2) of the weight's input axis are written
+  int N, Cout, C1, C2, Cw, coff, KH, KW, stride, pad_h, pad_w, up;  // up = 2: the conv reads the nearest-upsampled input
+  int Hi, Wi, Ho, Wo;
+  long long pos_per_slice;  // output positions (n, oy, ox) per z-slice
+};
+
+// grid: x = 64x64 tile of (co, ci), y = tap, z = slice of the positions.  256 threads, 4x4 outputs each.
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__ WgradConvParams P) {
+  const int Cin = P.C1 + P.C2;
+  const int tiles_ci = (Cin + 63) / 64;
+  const int tm = (blockIdx.x / tiles_ci) * 64, tn = (blockIdx.x % tiles_ci) * 64;
+  const int ky = blockIdx.y / P.KW, kx = blockIdx.y % P.KW;
+  __shared__ float sC[32][65];
+  __shared__ float sI[32][65];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  const long long npos = (long long)P.N * P.Ho * P.Wo;
+  const long long p_begin = (long long)blockIdx.z * P.pos_per_slice, p_end = min(npos, p_begin + P.pos_per_slice);
+  const int Hu = P.Hi * P.up, Wu = P.Wi * P.up;  // extent the conv sees
+  for (long long p0 = p_begin; p0 < p_end; p0 += 32) {
+    // 32 positions x 64 channels of both operands; a warp walks 32 consecutive positions of one channel (coalesced)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = tid + 256 * q, ch = e >> 5, pp = e & 31;
+      const long long p = p0 + pp;
+      float c = 0.0f, x = 0.0f;
+      if (p < p_end) {
+        const int ox = (int)(p % P.Wo), oy = (int)((p / P.Wo) % P.Ho);
+        const long long n = p / ((long long)P.Wo * P.Ho);
+        if (tm + ch < P.Cout) c = __ldg(P.cot + ((n * P.Cout + tm + ch) * P.Ho + oy) * P.Wo + ox);
+        const int iy = oy * P.stride + ky - P.pad_h, ix = ox * P.stride + kx - P.pad_w;
+        const int ci = tn + ch;
+        if (ci < Cin && iy >= 0 && iy < Hu && ix >= 0 && ix < Wu) {
+          const int sy = iy / P.up, sx = ix / P.up;
+          x = ci < P.C1 ? __ldg(P.in1 + ((n * P.C1 + ci) * P.Hi + sy) * P.Wi + sx)
+                        : __ldg(P.in2 + ((n * P.C2 + ci - P.C1) * P.Hi + sy) * P.Wi + sx);
+        }
+      }
+      sC[pp][ch] = c;
+      sI[pp][ch] = x;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pp = 0; pp < 32; ++pp) {
+      float c4[4], x4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { c4[i] = sC[pp][ty * 4 + i]; x4[i] = sI[pp][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(c4[i], x4[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = tm + ty * 4 + i, ci = tn + tx * 4 + j;
+      if (co < P.Cout && ci < Cin)
+        atomicAdd(P.gW + (((size_t)co * P.Cw + P.coff + ci) * P.KH + ky) * P.KW + kx, acc[i][j]);
+    }
+}
+
+// ---- small dense product: C (M x N, ldc) = [C +] op(A) op(B), op = identity or transpose ---------------------------------------
+// A is (M x K) [lda] or, transposed, stored (K x M); B is (K x N) [ldb] or, transposed, stored (N x K).
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Cm,
+                                                       int M, int N, int K, int lda, int ldb, int ldc, int ta, int tb, int accumulate) {
+  __shared__ float sA[16][65], sB[16][65];
+  const int tm = blockIdx.y * 64, tn = blockIdx.x * 64, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + 256 * q;
+      {  // A tile: 16 k x 64 m
+        const int kk = ta ? (e >> 6) : (e & 15), mm = ta ? (e & 63) : (e >> 4);
+        const int k = k0 + kk, m = tm + mm;
+        sA[kk][mm] = (k < K && m < M) ? __ldg(ta ? A + (size_t)k * lda + m : A + (size_t)m * lda + k) : 0.0f;
+      }
+      {  // B tile: 16 k x 64 n
+        const int kk = tb ? (e & 15) : (e >> 6), nn = tb ? (e >> 4) : (e & 63);
+        const int k = k0 + kk, n = tn + nn;
+        sB[kk][nn] = (k < K && n < N) ? __ldg(tb ? B + (size_t)n * ldb + k : B + (size_t)k * ldb + n) : 0.0f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a4[4], b4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a4[i] = sA[kk][ty * 4 + i]; b4[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = tm + ty * 4 + i, n = tn + tx * 4 + j;
+      if (m < M && n < N) {
+        float* c = Cm + (size_t)m * ldc + n;
+        *c = accumulate ? *c + acc[i][j] : acc[i][j];
+      }
+    }
+}
+
+// ---- premodule: NormalizeLogRadius (NN.py:56-70) and its tangent, times `scale` (the U-Nets multiply by sqrt(d)) ------------------
+// x, v: (B, d) -> xn: (2B, d), logn: (2B): one warp per sample
+__global__ void __launch_bounds__(256) premodule_pair_kernel(const float* __restrict__ x, const float* __restrict__ v,
+                                                             float* __restrict__ xn, float* __restrict__ logn, long long B, int d,
+                                                             float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long b = w0; b < B; b += nw) {
+    float r2 = 0.0f, xv = 0.0f;
+    for (int c = lane; c < d; c += 32) {
+      const float xc = x[b * d + c];
+      r2 = fmaf(xc, xc, r2);
+      xv = fmaf(xc, v[b * d + c], xv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      xv += __shfl_xor_sync(0xffffffffu, xv, o);
+    }
+    const float r = sqrtf(r2), rn = r + 1e-6f, rdot = xv / r;
+    for (int c = lane; c < d; c += 32) {
+      const float xc = x[b * d + c], vc = v[b * d + c];
+      xn[b * d + c] = scale * (xc / rn);
+      xn[(B + b) * d + c] = scale * (vc / rn - xc * rdot / (rn * rn));
+    }
+    if (lane == 0) {
+      logn[b] = logf(rn);
+      logn[B + b] = rdot / rn;
+    }
+  }
+}
+
+// ---- loss and output cotangents for the sparse multiplicative SDE / the additive SDE (state width d up to 4096) ------------------
+// a: (2B, d) net output pair.  q_k = c sqrt(beta) (v_k y_{k+1} - v_{k+1} y_k) (cyclic) or sqrt(beta) v_k (SGM).
+__device__ __forceinline__ float ssm_q(int kind, float sb, const float* y, const float* v, int k, int d) {
+  if (kind == MSGM_SDE_SGM) return sb * v[k];
+  const int kn = (k + 1 == d) ? 0 : k + 1;
+  return SQRT_HALF * sb * (v[k] * y[kn] - v[kn] * y[k]);
+}
+
+__global__ void __launch_bounds__(256) sparse_ssm_loss_kernel(const float* __restrict__ a, const float* __restrict__ y,
+                                                              const float* __restrict__ v, const float* __restrict__ t,
+                                                              float* __restrict__ loss, long long B, int d, int kind, float bmin,
+                                                              float bdel) {
+  const long long b = blockIdx.x;
+  const float bt = beta_of(bmin, bdel, t[b]), sb = sqrtf(bt);
+  float s = 0.0f;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const float ak = a[b * d + k], adk = a[(B + b) * d + k];
+    s = fmaf(ssm_q(kind, sb, y + b * d, v + b * d, k, d), adk, s);
+    s = fmaf(0.5f * ak, ak, s);
+    if (kind == MSGM_SDE_SGM) s = fmaf(0.5f * bt, v[b * d + k] * v[b * d + k], s);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[b] = red[0];
+}
+
+__global__ void __launch_bounds__(256) sparse_ssm_cot_kernel(const float* __restrict__ a, const float* __restrict__ y,
+                                                             const float* __restrict__ v, const float* __restrict__ t,
+                                                             const float* __restrict__ gout, float* __restrict__ cot, long long B,
+                                                             int d, int kind, float bmin, float bdel) {
+  const long long b = blockIdx.x;
+  const float sb = sqrtf(beta_of(bmin, bdel, t[b])), g = gout[b];
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    cot[b * d + k] = g * a[b * d + k];
+    cot[(B + b) * d + k] = g * ssm_q(kind, sb, y + b * d, v + b * d, k, d);
+  }
+}
+
+}  // namespace msgm
+
+using namespace msgm;
+
+static int ut_invalid(const char* m) {
+  set_error(m);
+  return MSGM_ERR_INVALID;
+}
+static int ut_grid(const msgm_ctx* ctx, long long n) { return (int)std::min<long long>((n + 255) / 256, (long long)ctx->num_sms * 8); }
+
+extern "C" {
+
+int msgm_pair_act(msgm_ctx* ctx, const float* z, const float* grad_h_or_null, float* out, int64_t half_elems, int32_t act,
+                  void* stream) {
+  if (!ctx || !z || !out || half_elems < 0 || (act != 0 && act != 1)) return ut_invalid("msgm_pair_act: bad argument");
+  if (half_elems == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (grad_h_or_null)
+    pair_act_bwd_kernel<<<ut_grid(ctx, half_elems), 256, 0, (cudaStream_t)stream>>>(z, grad_h_or_null, out, half_elems, act);
+  else
+    pair_act_fwd_kernel<<<ut_grid(ctx, half_elems), 256, 0, (cudaStream_t)stream>>>(z, out, half_elems, act);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_amax(msgm_ctx* ctx, const float* x, int64_t n, float* amax_out, void* stream) {
+  if (!ctx || !x || !amax_out || n < 1) return ut_invalid("msgm_amax: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  MSGM_CUDA_TRY(cudaMemsetAsync(amax_out, 0, sizeof(float), (cudaStream_t)stream));
+  amax_kernel<<<ut_grid(ctx, n), 256, 0, (cudaStream_t)stream>>>(x, n, reinterpret_cast<unsigned int*>(amax_out));
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_pow2_scale(msgm_ctx* ctx, const float* x, float* y, int64_t n, const float* amax_dev, int32_t target_exp,
+                    int32_t inverse, void* stream) {
+  if (!ctx || !x || !y || !amax_dev || n < 1) return ut_invalid("msgm_pow2_scale: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  pow2_scale_kernel<<<ut_grid(ctx, n), 256, 0, (cudaStream_t)stream>>>(x, y, n, reinterpret_cast<const unsigned int*>(amax_dev),
+                                                                      target_exp, inverse);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_rows_bias_add(msgm_ctx* ctx, float* x, const float* bias, int64_t nrows, int32_t C, int64_t P, void* stream) {
+  if (!ctx || !x || !bias || nrows < 0 || C < 1 || P < 1) return ut_invalid("msgm_rows_bias_add: bad argument");
+  if (nrows == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  rows_bias_add_kernel<<<ut_grid(ctx, nrows * C * P), 256, 0, (cudaStream_t)stream>>>(x, bias, nrows, C, P);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_channel_sums(msgm_ctx* ctx, const float* x, float* out_accumulate, int64_t nrows, int32_t C, int64_t P, void* stream) {
+  if (!ctx || !x || !out_accumulate || nrows < 1 || C < 1 || P < 1) return ut_invalid("msgm_channel_sums: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  const int gy = (int)std::min<long long>(nrows, std::max(1, ctx->num_sms * 4 / C));
+  channel_sums_kernel<<<dim3(C, gy), 256, 0, (cudaStream_t)stream>>>(x, out_accumulate, nrows, C, P);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_tap_sums_1d(msgm_ctx* ctx, const float* cot, float* E, int64_t N, int32_t Cout, int32_t K, int32_t stride, int32_t pad,
+                     int32_t Lin, int32_t Lout, void* stream) {
+  if (!ctx || !cot || !E || N < 1 || Cout < 1 || K < 1 || K > 128 || Lout < 1) return ut_invalid("msgm_tap_sums_1d: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  tap_sums_1d_kernel<<<(unsigned)(N * Cout), 128, 0, (cudaStream_t)stream>>>(cot, E, K, stride, pad, Lin, Lout);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_conv_wgrad(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate, int32_t N,
+                    int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff, int32_t KH, int32_t KW, int32_t stride,
+                    int32_t pad, int32_t up, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, void* stream) {
+  if (!ctx || !cot || !in1 || !gW_accumulate || N < 1 || Cout < 1 || C1 < 1 || C2 < 0 || (C2 > 0 && !in2) || coff < 0 ||
+      coff + C1 + C2 > Cw || KH < 1 || KW < 1 || KH * KW > 64 || stride < 1 || (up != 1 && up != 2))
+    return ut_invalid("msgm_conv_wgrad: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  // 1-D convolutions come in as Hi = Ho = KH = 1: no padding along that axis
+  WgradConvParams P{cot, in1, in2, gW_accumulate, N, Cout, C1, C2, Cw, coff, KH, KW, stride, KH == 1 ? 0 : pad, pad, up, Hi, Wi, Ho, Wo, 0};
+  const long long npos = (long long)N * Ho * Wo;
+  const int tiles = ((Cout + 63) / 64) * ((C1 + C2 + 63) / 64) * KH * KW;
+  long long slices = std::max<long long>(1, std::min<long long>((npos + 255) / 256, (long long)ctx->num_sms * 4 / std::max(1, tiles) + 1));
+  slices = std::min<long long>(slices, 65535);
+  P.pos_per_slice = ((npos + slices - 1) / slices + 31) / 32 * 32;
+  const int nslice = (int)((npos + P.pos_per_slice - 1) / P.pos_per_slice);
+  conv_wgrad_kernel<<<dim3(((Cout + 63) / 64) * ((C1 + C2 + 63) / 64), KH * KW, nslice), 256, 0, (cudaStream_t)stream>>>(P);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_gemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* Cm, int32_t M, int32_t N, int32_t K, int32_t lda,
+                  int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b, int32_t accumulate, void* stream) {
+  if (!ctx || !A || !B || !Cm || M < 1 || N < 1 || K < 1) return ut_invalid("msgm_gemm_f32: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, B, Cm, M, N, K, lda, ldb, ldc, trans_a,
+                                                                                         trans_b, accumulate);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_premodule_pair(msgm_ctx* ctx, const float* x, const float* v, float* xn_pair, float* logn_pair, int64_t B, int32_t d,
+                        float scale, void* stream) {
+  if (!ctx || !x || !v || !xn_pair || !logn_pair || B < 1 || d < 1) return ut_invalid("msgm_premodule_pair: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  premodule_pair_kernel<<<(int)std::min<long long>((B + 7) / 8, (long long)ctx->num_sms * 8), 256, 0, (cudaStream_t)stream>>>(
+      x, v, xn_pair, logn_pair, B, d, scale);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_sparse_ssm_loss(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* a_pair, const float* y, const float* v,
+                         const float* t, const float* gout_or_null, float* out, int64_t B, void* stream) {
+  if (!ctx || !sde || !a_pair || !y || !v || !t || !out || B < 1 || sde->dim < 1)
+    return ut_invalid("msgm_sparse_ssm_loss: bad argument");
+  if (sde->kind != MSGM_SDE_SGM && sde->kind != MSGM_SDE_MSGM_SPARSE) {
+    set_error("msgm_sparse_ssm_loss: built for the additive SDE and the sparse multiplicative SDE");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (gout_or_null)
+    sparse_ssm_cot_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(a_pair, y, v, t, gout_or_null, out, B, sde->dim, sde->kind,
+                                                                         sde->beta_min, sde->beta_delta);
+  else
+    sparse_ssm_loss_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(a_pair, y, v, t, out, B, sde->dim, sde->kind, sde->beta_min,
+                                                                          sde->beta_delta);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+}  // extern "C"

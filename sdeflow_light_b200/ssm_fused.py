@@ -176,6 +176,9 @@ def ssm_loss(gen, t_, x, y, v=None):
             raise ValueError(f"vtype {gen.vtype} not supported")
     v = v.to(y)
     if not (isinstance(net, NN.MLP) and net.fused_ok()):
+        from . import unet_train
+        if unet_train.supported(gen, y):  # U-Nets: hand-written forward-mode kernels, torch.autograd only as the tape
+            return unet_train.ssm_loss(gen, t_.to(y), y, v)
         return _ssm_loss_autograd(gen, t_.to(y), y, v)
     params = [p for l in net.linears() for p in (l.weight, l.bias)]
     if tc_ok(gen, y.shape[1]):

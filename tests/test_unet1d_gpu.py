@@ -397,3 +397,35 @@ def test_fused_noising_writes_inside_its_output():
                                              11, 0, B, _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     assert bool((buf[:PAD] == CAN).all()) and bool((buf[PAD + B * d:] == CAN).all()) and torch.isfinite(y).all()
+
+
+def test_unet1d_handwritten_training_matches_library_autograd():
+    """The hand-written forward-mode training path (unet_train.py: tcgen05 convs on primal/tangent pairs, csrc/unet_train.cu for
+    everything else; torch.autograd as the tape only) against torch's own autograd through the library layers, at the full
+    configuration-3 size (L = 1000), with cuDNN switched off for the hand-written run: loss and every parameter gradient."""
+    torch.manual_seed(21)
+    d, B = 1000, 6
+    net = P.UNet1D(d, premodule="NormalizeLogRadius").to(DEV)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(torch.randn(64, d), beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=4, device=DEV, estim_cst_norm_dens_r_T=False)
+    gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
+    gen.train()
+    y = (torch.randn(B, d) * 1.3).to(DEV)
+    v = (torch.rand(B, d).ge(0.5).float() * 2 - 1).to(DEV)
+    t = (torch.rand(B, 1) * 0.9 + 0.05).to(DEV)
+    gen.unet_train_kernels = False
+    gen.zero_grad()
+    l_ref = gen.ssm_loss(t, y, y, v)
+    l_ref.mean().backward()
+    g_ref = {k: p.grad.clone() for k, p in net.named_parameters()}
+    gen.unet_train_kernels = True
+    gen.zero_grad()
+    with torch.backends.cudnn.flags(enabled=False):
+        l_own = gen.ssm_loss(t, y, y, v)
+        l_own.mean().backward()
+    e_l = _rel(l_own.detach(), l_ref.detach().cpu())
+    worst = max((_rel(p.grad, g_ref[k].cpu()), k) for k, p in net.named_parameters())
+    Bd.report(test="unet1d-handwritten-train-L1000", loss_rel=e_l, grad_rel=worst[0], worst_param=worst[1])
+    assert e_l < 1e-4, e_l
+    assert worst[0] < 5e-4, worst

@@ -1,5 +1,6 @@
-"""SSM training iteration of the U-Net score nets (BASELINE configs 3 and 4): eager loop vs train.GraphedSsmStep, library
-backward in fp32 (default, reference parity) and with the opt-in TF32 policy (`net.train_tf32 = True`)."""
+"""SSM training iteration of the U-Net score nets (BASELINE configs 3 and 4): eager loop vs train.GraphedSsmStep, on the
+hand-written kernel path (sdeflow_light_b200/unet_train.py, where it covers the net) and on the library path (torch autograd
+through cuDNN: fp32 = reference parity, and the opt-in TF32 policy `net.train_tf32 = True`)."""
 import os
 import sys
 import time
@@ -11,7 +12,8 @@ from sdeflow_light_b200.train import GraphedSsmStep  # noqa: E402
 
 dev = torch.device("cuda", 0)
 for which, d, B, nfwd in (("unet1d", 1000, 64, 16), ("unet2d", 1024, 32, 128)):
-    for tf32 in (False, True):
+    for mode in ("kernels", "library-fp32", "library-tf32"):
+        tf32 = mode == "library-tf32"
         torch.manual_seed(0)
         data = torch.randn(512, d)
         T = torch.nn.Parameter(torch.FloatTensor([1.0]), requires_grad=False)
@@ -22,6 +24,11 @@ for which, d, B, nfwd in (("unet1d", 1000, 64, 16), ("unet2d", 1024, 32, 128)):
                                flatten_order="F")).to(dev)
         net.train_tf32 = tf32
         gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=dev).to(dev)
+        gen.unet_train_kernels = mode == "kernels"
+        from sdeflow_light_b200 import unet_train
+        if mode == "kernels" and not unet_train.supported(gen, data[:B].to(dev)):
+            print(f"{which}: hand-written training path not built for this net", flush=True)
+            continue
         xs = data[:B].to(dev)
         opt = torch.optim.Adam(gen.parameters(), lr=1e-4)
         gen.train()
@@ -48,5 +55,5 @@ for which, d, B, nfwd in (("unet1d", 1000, 64, 16), ("unet2d", 1024, 32, 128)):
             step(xs)
         torch.cuda.synchronize()
         ms_g = (time.time() - t0) / 10 * 1e3
-        print(f"{which} d={d} batch={B} N_fwd={nfwd} library precision={'tf32' if tf32 else 'fp32'}: eager {ms_e:.1f} ms/iter, "
+        print(f"{which} d={d} batch={B} N_fwd={nfwd} path={mode}: eager {ms_e:.1f} ms/iter, "
               f"graphed {ms_g:.1f} ms/iter ({B / ms_g * 1e3:.0f} samples/s)", flush=True)

@@ -244,6 +244,24 @@ int msgm_adam_step(msgm_ctx* ctx, const void* seg_table, int32_t n_tensors, int6
  *   msgm_sparse_ssm_loss  gout NULL: out[b] = q . adot + |a|^2/2 (+ beta |v|^2/2, SGM) from the net output pair a_pair
  *                       (2B,d), q from the cyclic sparse tensor (SDEs.py:369-399) or sqrt(beta) v (SGM); gout given: out =
  *                       the output cotangent pair (gout a; gout q), (2B,d). */
+/*   msgm_bgemm_f32     msgm_gemm_f32 over `batch` problems (pointer strides) with a scalar factor: the products of
+ *                       QKVAttention (model/unet.py:236-250) on a pair and of its backward.
+ *   msgm_gn_pair        GroupNorm32 (model/nn_utils.py:39-46,107-114) on a pair x (2B,C,HW): grad_y NULL: out = (y; ydot),
+ *                       stats (B,G,4) written; grad_y given: out = cotangents of (x; xdot), ggamma / gbeta accumulated.
+ *   msgm_softmax_pair   A NULL: out1 = softmax(S) rows, out2 = Pdot = P (Sdot - sum P Sdot); A given (first argument = P):
+ *                       out1 = Sbar, out2 = Sdotbar from the direct cotangents A = dL/dP, Pdotbar = dL/dPdot.
+ *   msgm_sincos_pair    timestep_embedding (model/nn_utils.py:130-148) of a pair of scalars (value; tangent) -> (2B, dim).
+ *   msgm_resample2      mode 0: zero-stuffing to twice the size (adjoint of a stride-2 conv's sub-sampling); mode 1: 2x2 block
+ *                       sums (adjoint of the nearest-neighbour upsampling of Upsample, model/unet.py:40-60). */
+int msgm_bgemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t lda,
+                   int32_t ldb, int32_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c, int32_t batch, int32_t trans_a,
+                   int32_t trans_b, float alpha, int32_t accumulate, void* stream);
+int msgm_gn_pair(msgm_ctx* ctx, const float* x, const float* gamma, const float* beta, float* stats, const float* grad_y_or_null,
+                 float* out, float* ggamma, float* gbeta, int32_t B, int32_t C, int32_t G, int32_t HW, void* stream);
+int msgm_softmax_pair(msgm_ctx* ctx, const float* S_or_P, const float* Sdot, const float* A_or_null, const float* Pdotbar_or_null,
+                      float* out1, float* out2, int64_t nrows, int32_t T, void* stream);
+int msgm_sincos_pair(msgm_ctx* ctx, const float* val_pair, float* emb_pair, int32_t B, int32_t dim, void* stream);
+int msgm_resample2(msgm_ctx* ctx, const float* x, float* out, int64_t NC, int32_t H, int32_t W, int32_t mode, void* stream);
 int msgm_pair_act(msgm_ctx* ctx, const float* z, const float* grad_h_or_null, float* out, int64_t half_elems, int32_t act,
                   void* stream);
 int msgm_amax(msgm_ctx* ctx, const float* x, int64_t n, float* amax_out, void* stream);

@@ -398,14 +398,18 @@ __global__ void __launch_bounds__(256) gn_scale_shift_kernel(const float* __rest
 
 // ---- host dispatch ---------------------------------------------------------------------------------------------------
 // output-channel tile: 192 serves the attention qkv convs (Cout = 3 C = 192 / 384) with one / two tiles instead of three
-int conv2d_tc_nout(int Cout) { return Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32)); }
+// output-channel tile: 192 only where two weight stages of that width fit shared memory (up to 4 taps: 1x1 and the 1-D convs);
+// a 3x3 conv with 192 k output channels (data gradients of the 192-input decoder convs) runs as 128- or 64-wide tiles
+int conv2d_tc_nout(int Cout, int taps) {
+  return (Cout % 192 == 0 && taps <= 4) ? 192 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));
+}
 
 size_t conv2d_tc_pack_bytes(int Cout, int Cin, int KK) { return (size_t)Cout * Cin * KK * 2 * 2; }
 
 // W is (Cout, Cw, taps) with the first Cin input channels packed (Cw > Cin: trailing channels are handled elsewhere).
 int conv2d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cw, int Cin, int KK, void* img, cudaStream_t stream) {
   const long long nel = (long long)Cout * Cin * KK * 2;
-  conv2d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cw, Cin, KK, conv2d_tc_nout(Cout),
+  conv2d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cw, Cin, KK, conv2d_tc_nout(Cout, KK),
                                                                           reinterpret_cast<__half*>(img), nel);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
@@ -490,7 +494,7 @@ static int launch_conv_tc(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
 
 template <int NT>
 static int launch_conv_tc_n(msgm_ctx* ctx, ConvTcParams& P, cudaStream_t stream) {
-  const int nout = conv2d_tc_nout(P.Cout);
+  const int nout = conv2d_tc_nout(P.Cout, NT);
   if (nout == 192) return launch_conv_tc<192, NT>(ctx, P, stream);
   if (nout == 128) return launch_conv_tc<128, NT>(ctx, P, stream);
   if (nout == 64) return launch_conv_tc<64, NT>(ctx, P, stream);
@@ -536,7 +540,7 @@ int conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* D, cudaStream_t stream) 
 
 int convt1d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cin, void* img, cudaStream_t stream) {
   const long long nel = (long long)2 * Cout * Cin * 3 * 2;
-  convt1d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cin, conv2d_tc_nout(2 * Cout),
+  convt1d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cin, conv2d_tc_nout(2 * Cout, 3),
                                                                            reinterpret_cast<__half*>(img), nel);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());

@@ -215,8 +215,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
 // ---- small dense product: C (M x N, ldc) = [C +] op(A) op(B), op = identity or transpose ---------------------------------------
 // A is (M x K) [lda] or, transposed, stored (K x M); B is (K x N) [ldb] or, transposed, stored (N x K).
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Cm,
-                                                       int M, int N, int K, int lda, int ldb, int ldc, int ta, int tb, int accumulate) {
+                                                       int M, int N, int K, int lda, int ldb, int ldc, int ta, int tb, int accumulate,
+                                                       long long sa, long long sb, long long sc, float alpha) {
   __shared__ float sA[16][65], sB[16][65];
+  A += blockIdx.z * sa;  // batched: one product per blockIdx.z
+  B += blockIdx.z * sb;
+  Cm += blockIdx.z * sc;
   const int tm = blockIdx.y * 64, tn = blockIdx.x * 64, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   float acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += 16) {
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       const int m = tm + ty * 4 + i, n = tn + tx * 4 + j;
       if (m < M && n < N) {
         float* c = Cm + (size_t)m * ldc + n;
-        *c = accumulate ? *c + acc[i][j] : acc[i][j];
+        *c = accumulate ? fmaf(alpha, acc[i][j], *c) : alpha * acc[i][j];
       }
     }
 }
@@ -331,6 +335,195 @@ __global__ void __launch_bounds__(256) sparse_ssm_cot_kernel(const float* __rest
   for (int k = threadIdx.x; k < d; k += blockDim.x) {
     cot[b * d + k] = g * a[b * d + k];
     cot[(B + b) * d + k] = g * ssm_q(kind, sb, y + b * d, v + b * d, k, d);
+  }
+}
+
+
+// ---- GroupNorm on a pair (model/nn_utils.py:39-46,107-114) ----------------------------------------------------------------------
+// Primal: xh = (x - mu) r, y = gamma xh + beta.  Tangent: ydot = gamma r (u - c xh), u = xdot - mean(xdot), c = mean(xh xdot).
+// x: (2B, C, HW).  One CTA per (sample, group).  stats: (B, G, 4) = mu, r, mean(xdot), c.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.0f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) gn_pair_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ y,
+                                                          float* __restrict__ stats, int B, int C, int G, int HW, float eps) {
+  __shared__ float red[8];
+  const int b = blockIdx.x / G, g = blockIdx.x % G, cg = C / G, n = cg * HW;
+  const float* xp = x + ((size_t)b * C + g * cg) * HW;
+  const float* xt = x + ((size_t)(B + b) * C + g * cg) * HW;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { s1 += xp[i]; s2 += xt[i]; }
+  const float mu = block_sum(s1, red) / n, m1 = block_sum(s2, red) / n;
+  float v = 0.f, cc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = xp[i] - mu;
+    v = fmaf(d, d, v);
+    cc = fmaf(d, xt[i], cc);
+  }
+  const float var = block_sum(v, red) / n, r = rsqrtf(var + eps);
+  const float c = block_sum(cc, red) / n * r;  // mean(xh xdot)
+  if (threadIdx.x == 0) {
+    float* st = stats + ((size_t)b * G + g) * 4;
+    st[0] = mu; st[1] = r; st[2] = m1; st[3] = c;
+  }
+  float* yp = y + ((size_t)b * C + g * cg) * HW;
+  float* yt = y + ((size_t)(B + b) * C + g * cg) * HW;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ch = g * cg + i / HW;
+    const float xh = (xp[i] - mu) * r, ga = gamma[ch];
+    yp[i] = fmaf(ga, xh, beta[ch]);
+    yt[i] = ga * r * (xt[i] - m1 - c * xh);
+  }
+}
+
+// gy: (2B, C, HW) cotangents of (y; ydot) -> gx: cotangents of (x; xdot); ggamma / gbeta accumulated with atomics
+__global__ void __launch_bounds__(256) gn_pair_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ stats, const float* __restrict__ gy,
+                                                          float* __restrict__ gx, float* __restrict__ ggamma,
+                                                          float* __restrict__ gbeta, int B, int C, int G, int HW) {
+  __shared__ float red[8];
+  const int b = blockIdx.x / G, g = blockIdx.x % G, cg = C / G, n = cg * HW;
+  const size_t op = ((size_t)b * C + g * cg) * HW, ot = ((size_t)(B + b) * C + g * cg) * HW;
+  const float* st = stats + ((size_t)b * G + g) * 4;
+  const float mu = st[0], r = st[1], m1 = st[2], c = st[3];
+  float sa = 0.f, sax = 0.f, sb = 0.f, sbx = 0.f, sbu = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float ga = gamma[g * cg + i / HW];
+    const float xh = (x[op + i] - mu) * r, u = x[ot + i] - m1;
+    const float a = ga * gy[op + i], bb = ga * gy[ot + i];
+    sa += a; sax = fmaf(a, xh, sax); sb += bb; sbx = fmaf(bb, xh, sbx); sbu = fmaf(bb, u, sbu);
+  }
+  const float ma = block_sum(sa, red) / n, max_ = block_sum(sax, red) / n, mb = block_sum(sb, red) / n;
+  const float qm = block_sum(sbx, red) / n, p = block_sum(sbu, red) / n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float ga = gamma[g * cg + i / HW];
+    const float xh = (x[op + i] - mu) * r, u = x[ot + i] - m1;
+    const float a = ga * gy[op + i], bb = ga * gy[ot + i];
+    gx[ot + i] = r * (bb - mb - xh * qm);
+    gx[op + i] = r * (a - ma - xh * max_) - r * r * (xh * (p - 3.0f * c * qm) + qm * u + c * (bb - mb));
+  }
+  // per-channel parameter gradients: gbeta_c = sum ybar, ggamma_c = sum (ybar xh + ydotbar xhdot), xhdot = r (u - c xh)
+  for (int ch = 0; ch < cg; ++ch) {
+    float sg = 0.f, sbeta = 0.f;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const int e = ch * HW + i;
+      const float xh = (x[op + e] - mu) * r, u = x[ot + e] - m1;
+      sg = fmaf(gy[op + e], xh, sg);
+      sg = fmaf(gy[ot + e], r * (u - c * xh), sg);
+      sbeta += gy[op + e];
+    }
+    const float tg = block_sum(sg, red), tb = block_sum(sbeta, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(ggamma + g * cg + ch, tg);
+      atomicAdd(gbeta + g * cg + ch, tb);
+    }
+  }
+}
+
+// ---- softmax on a pair of logit matrices (QKVAttention, model/unet.py:236-250) ------------------------------------------------------
+// rows: (nrows, T).  forward: P = softmax(S), Pdot = P (Sdot - sum_l P_l Sdot_l).  One warp per row.
+__global__ void __launch_bounds__(256) softmax_pair_fwd_kernel(const float* __restrict__ S, const float* __restrict__ Sd,
+                                                               float* __restrict__ Pm, float* __restrict__ Pd, long long nrows,
+                                                               int T) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const float* s = S + row * T;
+  const float* sd = Sd + row * T;
+  float m = -INFINITY;
+  for (int j = lane; j < T; j += 32) m = fmaxf(m, s[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float z = 0.f, d = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float e = expf(s[j] - m);
+    z += e;
+    d = fmaf(e, sd[j], d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { z += __shfl_xor_sync(0xffffffffu, z, o); d += __shfl_xor_sync(0xffffffffu, d, o); }
+  const float iz = 1.0f / z;
+  d *= iz;
+  for (int j = lane; j < T; j += 32) {
+    const float pj = expf(s[j] - m) * iz;
+    Pm[row * T + j] = pj;
+    Pd[row * T + j] = pj * (sd[j] - d);
+  }
+}
+
+// backward: given P, Sdot and the direct cotangents A = dL/dP, Pdb = dL/dPdot:
+//   d = sum P Sdot, e = sum Pdb P, Pbar = A + Pdb (Sdot - d) - e Sdot, Sdotbar = P (Pdb - e), Sbar = P (Pbar - sum P Pbar)
+__global__ void __launch_bounds__(256) softmax_pair_bwd_kernel(const float* __restrict__ Pm, const float* __restrict__ Sd,
+                                                               const float* __restrict__ A, const float* __restrict__ Pdb,
+                                                               float* __restrict__ Sb, float* __restrict__ Sdb, long long nrows,
+                                                               int T) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const float* p = Pm + row * T;
+  const float* sd = Sd + row * T;
+  const float* a = A + row * T;
+  const float* pdb = Pdb + row * T;
+  float d = 0.f, e = 0.f;
+  for (int j = lane; j < T; j += 32) { d = fmaf(p[j], sd[j], d); e = fmaf(pdb[j], p[j], e); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { d += __shfl_xor_sync(0xffffffffu, d, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
+  float w = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float pb = a[j] + pdb[j] * (sd[j] - d) - e * sd[j];
+    w = fmaf(p[j], pb, w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+  for (int j = lane; j < T; j += 32) {
+    const float pb = a[j] + pdb[j] * (sd[j] - d) - e * sd[j];
+    Sb[row * T + j] = p[j] * (pb - w);
+    Sdb[row * T + j] = p[j] * (pdb[j] - e);
+  }
+}
+
+// ---- sinusoidal embedding of a pair of scalars (model/nn_utils.py:130-148): [cos(x w_k), sin(x w_k)] and its tangent --------------
+__global__ void sincos_pair_kernel(const float* __restrict__ val, float* __restrict__ emb, int B, int dim) {
+  const int half = dim / 2;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B * half; e += gridDim.x * blockDim.x) {
+    const int b = e / half, k = e % half;
+    const float w = expf(-logf(10000.0f) * (float)k / (float)half);
+    const float ang = val[b] * w, xd = val[B + b] * w;
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    emb[(size_t)b * dim + k] = cs;
+    emb[(size_t)b * dim + half + k] = sn;
+    emb[(size_t)(B + b) * dim + k] = -sn * xd;
+    emb[(size_t)(B + b) * dim + half + k] = cs * xd;
+  }
+}
+
+// ---- x2 resampling adjoints ------------------------------------------------------------------------------------------------------
+// mode 0: out (NC, 2H, 2W): x at the even positions, zeros elsewhere (adjoint of taking every second position: stride-2 conv)
+// mode 1: out (NC, H, W): sums of the 2x2 blocks of x (NC, 2H, 2W) (adjoint of nearest-neighbour upsampling)
+__global__ void __launch_bounds__(256) resample2_kernel(const float* __restrict__ x, float* __restrict__ out, long long NC, int H,
+                                                        int W, int mode) {
+  const long long total = mode == 0 ? NC * 4 * H * W : NC * H * W, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    if (mode == 0) {
+      const int ox = (int)(i % (2 * W)), oy = (int)((i / (2 * W)) % (2 * H));
+      const long long nc = i / (4LL * H * W);
+      out[i] = ((ox | oy) & 1) ? 0.0f : x[(nc * H + (oy >> 1)) * W + (ox >> 1)];
+    } else {
+      const int ox = (int)(i % W), oy = (int)((i / W) % H);
+      const long long nc = i / ((long long)H * W);
+      const float* s = x + (nc * 2 * H + 2 * oy) * 2 * W + 2 * ox;
+      out[i] = s[0] + s[1] + s[2 * W] + s[2 * W + 1];
+    }
   }
 }
 
@@ -437,7 +630,7 @@ int msgm_gemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* Cm, int3
   if (!ctx || !A || !B || !Cm || M < 1 || N < 1 || K < 1) return ut_invalid("msgm_gemm_f32: bad argument");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, B, Cm, M, N, K, lda, ldb, ldc, trans_a,
-                                                                                         trans_b, accumulate);
+                                                                                         trans_b, accumulate, 0, 0, 0, 1.0f);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;
@@ -469,6 +662,69 @@ int msgm_sparse_ssm_loss(msgm_ctx* ctx, const msgm_sde_desc* sde, const float* a
   else
     sparse_ssm_loss_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(a_pair, y, v, t, out, B, sde->dim, sde->kind, sde->beta_min,
                                                                           sde->beta_delta);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_bgemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* Cm, int32_t M, int32_t N, int32_t K, int32_t lda,
+                   int32_t ldb, int32_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c, int32_t batch, int32_t trans_a,
+                   int32_t trans_b, float alpha, int32_t accumulate, void* stream) {
+  if (!ctx || !A || !B || !Cm || M < 1 || N < 1 || K < 1 || batch < 1 || batch > 65535) return ut_invalid("msgm_bgemm_f32: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64, batch), 256, 0, (cudaStream_t)stream>>>(
+      A, B, Cm, M, N, K, lda, ldb, ldc, trans_a, trans_b, accumulate, stride_a, stride_b, stride_c, alpha);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_gn_pair(msgm_ctx* ctx, const float* x, const float* gamma, const float* beta, float* stats, const float* grad_y_or_null,
+                 float* out, float* ggamma, float* gbeta, int32_t B, int32_t C, int32_t G, int32_t HW, void* stream) {
+  if (!ctx || !x || !gamma || !stats || !out || B < 1 || C < 1 || G < 1 || C % G || HW < 1) return ut_invalid("msgm_gn_pair: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (grad_y_or_null) {
+    if (!ggamma || !gbeta) return ut_invalid("msgm_gn_pair: backward needs ggamma / gbeta");
+    gn_pair_bwd_kernel<<<B * G, 256, 0, (cudaStream_t)stream>>>(x, gamma, stats, grad_y_or_null, out, ggamma, gbeta, B, C, G, HW);
+  } else {
+    if (!beta) return ut_invalid("msgm_gn_pair: forward needs beta");
+    gn_pair_fwd_kernel<<<B * G, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, out, stats, B, C, G, HW, 1e-5f);
+  }
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_softmax_pair(msgm_ctx* ctx, const float* S_or_P, const float* Sdot, const float* A_or_null, const float* Pdotbar_or_null,
+                      float* out1, float* out2, int64_t nrows, int32_t T, void* stream) {
+  if (!ctx || !S_or_P || !Sdot || !out1 || !out2 || nrows < 1 || T < 1) return ut_invalid("msgm_softmax_pair: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  const unsigned blocks = (unsigned)((nrows * 32 + 255) / 256);
+  if (A_or_null) {
+    if (!Pdotbar_or_null) return ut_invalid("msgm_softmax_pair: backward needs both cotangents");
+    softmax_pair_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(S_or_P, Sdot, A_or_null, Pdotbar_or_null, out1, out2, nrows, T);
+  } else {
+    softmax_pair_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(S_or_P, Sdot, out1, out2, nrows, T);
+  }
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_sincos_pair(msgm_ctx* ctx, const float* val_pair, float* emb_pair, int32_t B, int32_t dim, void* stream) {
+  if (!ctx || !val_pair || !emb_pair || B < 1 || dim < 2 || dim % 2) return ut_invalid("msgm_sincos_pair: bad argument (even dim)");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  sincos_pair_kernel<<<(B * dim / 2 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(val_pair, emb_pair, B, dim);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_resample2(msgm_ctx* ctx, const float* x, float* out, int64_t NC, int32_t H, int32_t W, int32_t mode, void* stream) {
+  if (!ctx || !x || !out || NC < 1 || H < 1 || W < 1 || (mode != 0 && mode != 1)) return ut_invalid("msgm_resample2: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  const long long total = mode == 0 ? NC * 4 * H * W : NC * H * W;
+  resample2_kernel<<<ut_grid(ctx, total), 256, 0, (cudaStream_t)stream>>>(x, out, NC, H, W, mode);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

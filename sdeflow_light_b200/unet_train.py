@@ -361,6 +361,10 @@ def supported(gen, y) -> bool:
     if isinstance(net, NNUnet1D.UNet1D):
         L, n = y.shape[1], len(net.downs)
         return L % (1 << n) == 0 and net.input_dim == L
+    from . import NNUnet
+    if isinstance(net, NNUnet.VorticityUNet):
+        S, n = net.in_space, len(net.core.channel_mult) - 1
+        return y.shape[1] == S * S and S % (1 << n) == 0 and net.core.dropout == 0
     return False
 
 
@@ -368,4 +372,304 @@ def ssm_loss(gen, t_, y, v):
     from . import NNUnet1D
     if isinstance(gen.a, NNUnet1D.UNet1D):
         return unet1d_ssm_loss(gen, t_, y, v)
-    raise NotImplementedError
+    return unet2d_ssm_loss(gen, t_, y, v)
+
+
+# =====================================================================================================================
+# 2-D U-Net (NNUnet.VorticityUNet over model/unet.py UNetModel): GroupNorm, SiLU, 3x3 / 1x1 convs, attention, resampling
+# =====================================================================================================================
+def conv2d_raw(x, W, ebias, stride, up):
+    """out = conv2d(nearest-upsample^{up}(x), W, padding K//2, stride) + ebias[n, co]; no per-channel bias."""
+    from .model.unet import _tc_shape_ok
+    dev = x.device
+    h, L, st = _h(dev)
+    N, Cin, Hs, Ws = x.shape
+    Cout, K = W.shape[0], W.shape[-1]
+    pad = K // 2
+    Ho, Wo = (Hs * up + 2 * pad - K) // stride + 1, (Ws * up + 2 * pad - K) // stride + 1
+    out = torch.empty((N, Cout, Ho, Wo), device=dev, dtype=torch.float32)
+    p = lambda t_: None if t_ is None else t_.data_ptr()  # noqa: E731
+    if _tc_shape_ok(Cout, Cin, 0, K, stride, Hs * up, Ws * up):
+        img = torch.empty(L.msgm_conv2d_tc_pack_bytes(Cout, Cin, K), device=dev, dtype=torch.uint8)
+        _lib.check(L.msgm_conv2d_tc_pack(h, _lib.ptr(W), Cout, Cin, K, _lib.ptr(img), st))
+        d = _lib.Conv2dTcDesc(p(x), None, p(img), None, p(ebias), None, None, p(out), N, Cin, 0, Cout, K, stride, up, Hs, Ws, 0, 0)
+        _lib.check(L.msgm_conv2d_tc(h, C.byref(d), st))
+        return out
+    d = _lib.Conv2dDesc(p(x), None, p(W), None, p(ebias), None, None, None, None, p(out), N, Cin, 0, Cout, K, stride, up, Hs, Ws,
+                        0, 0)
+    _lib.check(L.msgm_conv2d(h, C.byref(d), st))
+    return out
+
+
+def resample2(x, mode):
+    h, L, st = _h(x.device)
+    N, Cc, H, W = x.shape
+    out = torch.empty((N, Cc, 2 * H, 2 * W) if mode == 0 else (N, Cc, H // 2, W // 2), device=x.device, dtype=torch.float32)
+    _lib.check(L.msgm_resample2(h, _lib.ptr(x), _lib.ptr(out), N * Cc, H if mode == 0 else H // 2, W if mode == 0 else W // 2,
+                                mode, st))
+    return out
+
+
+def sample_channel_sums(g):
+    """(N, C) sums of g (N, C, ...) over the positions."""
+    h, L, st = _h(g.device)
+    N, Cc = g.shape[:2]
+    P_ = g[0, 0].numel()
+    out = torch.empty((N, Cc), device=g.device, dtype=torch.float32)
+    _lib.check(L.msgm_tap_sums_1d(h, _lib.ptr(g), _lib.ptr(out), N, Cc, 1, 1, 0, P_, P_, st))
+    return out
+
+
+class Conv2dPair(torch.autograd.Function):
+    """conv_nd(2, ...) of model/unet.py on a pair: 3x3 (padding 1) or 1x1, stride 1 or 2, optionally on the nearest-upsampled
+    input (Upsample), plus a per-sample, per-channel term e (the ResBlock's embedding projection); bias on the primal half."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, e, stride, up):
+        x = x.contiguous()
+        N = x.shape[0]
+        Cout = W.shape[0]
+        eb = torch.zeros((N, Cout), device=x.device, dtype=torch.float32) if e is None else e.contiguous().clone()
+        if b is not None:
+            rows_bias_add(eb.view(N, Cout, 1), b, N // 2)
+        out = conv2d_raw(x, W, eb, stride, up)
+        ctx.save_for_backward(x, W)
+        ctx.cfg = (stride, up, b is not None, e is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        stride, up, has_b, has_e = ctx.cfg
+        g = g.contiguous()
+        N, Cin, Hs, Ws = x.shape
+        Cout, K = W.shape[0], W.shape[-1]
+        Ho, Wo = g.shape[-2:]
+        gx = None
+        if ctx.needs_input_grad[0]:
+            Wd = W.flip(2, 3).transpose(0, 1).contiguous()  # data gradient: the same conv, flipped taps, swapped channel roles
+            src = resample2(g, 0) if stride == 2 else g     # stride 2: cotangent back on the input grid (zeros in between)
+            gx = ranged(lambda t_: conv2d_raw(t_, Wd, None, 1, 1), src)
+            if up == 2:                                      # adjoint of the nearest-neighbour upsampling
+                gx = resample2(gx, 1)
+        gW = torch.zeros_like(W)
+        conv_wgrad(g, x, None, gW, 0, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo)
+        gb = channel_sums(g, N // 2) if has_b else None
+        ge = sample_channel_sums(g) if has_e else None
+        return gx, gW, gb, ge, None, None
+
+
+class GnPair(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, G):
+        x = x.contiguous()
+        h, L, st = _h(x.device)
+        N, Cc = x.shape[:2]
+        HW = x[0, 0].numel()
+        out = torch.empty_like(x)
+        stats = torch.empty((N // 2, G, 4), device=x.device, dtype=torch.float32)
+        _lib.check(L.msgm_gn_pair(h, _lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(stats), None, _lib.ptr(out), None,
+                                  None, N // 2, Cc, G, HW, st))
+        ctx.save_for_backward(x, gamma, stats)
+        ctx.G = G
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, stats = ctx.saved_tensors
+        g = g.contiguous()
+        h, L, st = _h(x.device)
+        N, Cc = x.shape[:2]
+        gx = torch.empty_like(x)
+        gg, gb = torch.zeros_like(gamma), torch.zeros_like(gamma)
+        _lib.check(L.msgm_gn_pair(h, _lib.ptr(x), _lib.ptr(gamma), None, _lib.ptr(stats), _lib.ptr(g), _lib.ptr(gx), _lib.ptr(gg),
+                                  _lib.ptr(gb), N // 2, Cc, ctx.G, x[0, 0].numel(), st))
+        return gx, gg, gb, None
+
+
+def _bgemm(dev, A, B, Cm, M, N, K, lda, ldb, ldc, sa, sb, sc, batch, ta=False, tb=False, alpha=1.0, acc=False):
+    h, L, st = _h(dev)
+    _lib.check(L.msgm_bgemm_f32(h, A, B, Cm, M, N, K, lda, ldb, ldc, sa, sb, sc, batch, int(ta), int(tb), float(alpha), int(acc), st))
+
+
+class AttnPair(torch.autograd.Function):
+    """QKVAttention (model/unet.py:236-250, one head) on a pair qkv (2B, 3C, T): S = s^2 q^T k, P = softmax(S), O = v P^T and
+    the tangents Sdot = s^2 (qdot^T k + q^T kdot), Pdot = P (Sdot - rowsum(P Sdot)), Odot = vdot P^T + v Pdot^T, as batched
+    fp32 products (msgm_bgemm_f32) and two row kernels (msgm_softmax_pair); the backward is the hand-derived adjoint."""
+
+    @staticmethod
+    def forward(ctx, qkv):
+        qkv = qkv.contiguous()
+        dev = qkv.device
+        N, C3, T = qkv.shape
+        B, Cc = N // 2, C3 // 3
+        s2 = 1.0 / math.sqrt(Cc)  # (C^-1/4)^2
+        f = 4  # bytes
+        base = qkv.data_ptr()
+        sq = C3 * T  # sample stride (floats)
+
+        def ptr(sample0, part):
+            return C.c_void_p(base + f * (sample0 * sq + part * Cc * T))
+
+        q, k, v, qd, kd, vd = ptr(0, 0), ptr(0, 1), ptr(0, 2), ptr(B, 0), ptr(B, 1), ptr(B, 2)
+        S = torch.empty((B, T, T), device=dev, dtype=torch.float32)
+        Sd = torch.empty_like(S)
+        _bgemm(dev, q, k, _lib.ptr(S), T, T, Cc, T, T, T, sq, sq, T * T, B, ta=True, alpha=s2)
+        _bgemm(dev, qd, k, _lib.ptr(Sd), T, T, Cc, T, T, T, sq, sq, T * T, B, ta=True, alpha=s2)
+        _bgemm(dev, q, kd, _lib.ptr(Sd), T, T, Cc, T, T, T, sq, sq, T * T, B, ta=True, alpha=s2, acc=True)
+        Pm, Pd = torch.empty_like(S), torch.empty_like(S)
+        h, L, st = _h(dev)
+        _lib.check(L.msgm_softmax_pair(h, _lib.ptr(S), _lib.ptr(Sd), None, None, _lib.ptr(Pm), _lib.ptr(Pd), B * T, T, st))
+        out = torch.empty((N, Cc, T), device=dev, dtype=torch.float32)
+        o, od = C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr() + f * B * Cc * T)
+        _bgemm(dev, v, _lib.ptr(Pm), o, Cc, T, T, T, T, T, sq, T * T, Cc * T, B, tb=True)
+        _bgemm(dev, vd, _lib.ptr(Pm), od, Cc, T, T, T, T, T, sq, T * T, Cc * T, B, tb=True)
+        _bgemm(dev, v, _lib.ptr(Pd), od, Cc, T, T, T, T, T, sq, T * T, Cc * T, B, tb=True, acc=True)
+        ctx.save_for_backward(qkv, Pm, Pd, Sd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, Pm, Pd, Sd = ctx.saved_tensors
+        g = g.contiguous()
+        dev = qkv.device
+        N, C3, T = qkv.shape
+        B, Cc = N // 2, C3 // 3
+        s2 = 1.0 / math.sqrt(Cc)
+        f, sq, so = 4, C3 * T, Cc * T
+        base = qkv.data_ptr()
+
+        def ptr(sample0, part):
+            return C.c_void_p(base + f * (sample0 * sq + part * Cc * T))
+
+        q, k, v, qd, kd, vd = ptr(0, 0), ptr(0, 1), ptr(0, 2), ptr(B, 0), ptr(B, 1), ptr(B, 2)
+        ob, odb = C.c_void_p(g.data_ptr()), C.c_void_p(g.data_ptr() + f * B * so)  # cotangents of O and Odot
+        A = torch.empty((B, T, T), device=dev, dtype=torch.float32)
+        Pdb = torch.empty_like(A)
+        _bgemm(dev, ob, v, _lib.ptr(A), T, T, Cc, T, T, T, so, sq, T * T, B, ta=True)
+        _bgemm(dev, odb, vd, _lib.ptr(A), T, T, Cc, T, T, T, so, sq, T * T, B, ta=True, acc=True)
+        _bgemm(dev, odb, v, _lib.ptr(Pdb), T, T, Cc, T, T, T, so, sq, T * T, B, ta=True)
+        Sb, Sdb = torch.empty_like(A), torch.empty_like(A)
+        h, L, st = _h(dev)
+        _lib.check(L.msgm_softmax_pair(h, _lib.ptr(Pm), _lib.ptr(Sd), _lib.ptr(A), _lib.ptr(Pdb), _lib.ptr(Sb), _lib.ptr(Sdb),
+                                       B * T, T, st))
+        gq = torch.empty_like(qkv)
+        gbase = gq.data_ptr()
+
+        def gptr(sample0, part):
+            return C.c_void_p(gbase + f * (sample0 * sq + part * Cc * T))
+
+        # vbar = Obar P + Odotbar Pdot ; vdotbar = Odotbar P
+        _bgemm(dev, ob, _lib.ptr(Pm), gptr(0, 2), Cc, T, T, T, T, T, so, T * T, sq, B)
+        _bgemm(dev, odb, _lib.ptr(Pd), gptr(0, 2), Cc, T, T, T, T, T, so, T * T, sq, B, acc=True)
+        _bgemm(dev, odb, _lib.ptr(Pm), gptr(B, 2), Cc, T, T, T, T, T, so, T * T, sq, B)
+        # qbar = s^2 (k Sbar^T + kdot Sdotbar^T) ; qdotbar = s^2 k Sdotbar^T
+        _bgemm(dev, k, _lib.ptr(Sb), gptr(0, 0), Cc, T, T, T, T, T, sq, T * T, sq, B, tb=True, alpha=s2)
+        _bgemm(dev, kd, _lib.ptr(Sdb), gptr(0, 0), Cc, T, T, T, T, T, sq, T * T, sq, B, tb=True, alpha=s2, acc=True)
+        _bgemm(dev, k, _lib.ptr(Sdb), gptr(B, 0), Cc, T, T, T, T, T, sq, T * T, sq, B, tb=True, alpha=s2)
+        # kbar = s^2 (q Sbar + qdot Sdotbar) ; kdotbar = s^2 q Sdotbar
+        _bgemm(dev, q, _lib.ptr(Sb), gptr(0, 1), Cc, T, T, T, T, T, sq, T * T, sq, B, alpha=s2)
+        _bgemm(dev, qd, _lib.ptr(Sdb), gptr(0, 1), Cc, T, T, T, T, T, sq, T * T, sq, B, alpha=s2, acc=True)
+        _bgemm(dev, q, _lib.ptr(Sdb), gptr(B, 1), Cc, T, T, T, T, T, sq, T * T, sq, B, alpha=s2)
+        return gq
+
+
+def _gn_silu(norm, x, silu=True):
+    y = GnPair.apply(x, norm.weight, norm.bias, norm.num_groups)
+    return PairAct.apply(y, SILU) if silu else y
+
+
+def _resblock_pair(blk, x, emb_act):
+    conv1, conv2 = blk.in_layers[2], blk.out_layers[3]
+    lin = blk.emb_layers[1]
+    e = LinearPair.apply(emb_act, lin.weight, lin.bias)                    # Linear(SiLU(emb)) on the pair
+    hdn = Conv2dPair.apply(_gn_silu(blk.in_layers[0], x), conv1.weight, conv1.bias, e, 1, 1)
+    hdn = Conv2dPair.apply(_gn_silu(blk.out_layers[0], hdn), conv2.weight, conv2.bias, None, 1, 1)
+    if isinstance(blk.skip_connection, torch.nn.Identity):
+        return x + hdn
+    sc = blk.skip_connection
+    return Conv2dPair.apply(x, sc.weight, sc.bias, None, 1, 1) + hdn
+
+
+def _attention_pair(blk, x):
+    N, Cc, Hh, Ww = x.shape
+    qkv = Conv2dPair.apply(_gn_silu(blk.norm, x, silu=False), blk.qkv.weight.unsqueeze(-1), blk.qkv.bias, None, 1, 1)
+    a = AttnPair.apply(qkv.view(N, 3 * Cc, Hh * Ww)).view(N, Cc, Hh, Ww)
+    return x + Conv2dPair.apply(a, blk.proj_out.weight.unsqueeze(-1), blk.proj_out.bias, None, 1, 1)
+
+
+def _run_layer_pair(layer, x, emb_act):
+    from .model import unet as U
+    if isinstance(layer, U.ResBlock):
+        return _resblock_pair(layer, x, emb_act)
+    if isinstance(layer, U.AttentionBlock):
+        return _attention_pair(layer, x)
+    if isinstance(layer, U.Upsample):
+        if not layer.use_conv or layer.odd_size:
+            raise NotImplementedError("hand-written U-Net training: Upsample without conv / odd sizes")
+        return Conv2dPair.apply(x, layer.conv.weight, layer.conv.bias, None, 1, 2)
+    if isinstance(layer, U.Downsample):
+        if not isinstance(layer.op, torch.nn.Conv2d):
+            raise NotImplementedError("hand-written U-Net training: Downsample without conv")
+        return Conv2dPair.apply(x, layer.op.weight, layer.op.bias, None, 2, 1)
+    if isinstance(layer, torch.nn.Conv2d):
+        return Conv2dPair.apply(x, layer.weight, layer.bias, None, layer.stride[0], 1)
+    raise NotImplementedError(f"hand-written U-Net training: layer {type(layer).__name__}")
+
+
+def _sincos_mlp_pair(mlp, val_pair, dim):
+    """time_embed / scale_embed (Linear, SiLU, Linear) of the sinusoidal embedding of a pair of scalars."""
+    dev = val_pair.device
+    h, L, st = _h(dev)
+    N = val_pair.numel()
+    emb = torch.empty((N, dim), device=dev, dtype=torch.float32)
+    _lib.check(L.msgm_sincos_pair(h, _lib.ptr(val_pair), _lib.ptr(emb), N // 2, dim, st))
+    l1, l2 = mlp[0], mlp[2]
+    return LinearPair.apply(PairAct.apply(LinearPair.apply(emb, l1.weight, l1.bias), SILU), l2.weight, l2.bias)
+
+
+def unet2d_pair_forward(net, y, v, s):
+    """(a; adot) of NNUnet.VorticityUNet at (y, s) along v: (2B, d).  Follows VorticityUNet._forward / UNetModel.run_blocks."""
+    from .NNUnet import scale_image
+    dev = y.device
+    h, L, st = _h(dev)
+    B, d = y.shape
+    S = net.in_space
+    core = net.core
+    s_pair = torch.cat([s.reshape(B), torch.zeros(B, device=dev)], 0).contiguous()
+    emb = _sincos_mlp_pair(core.time_embed, s_pair, core.model_channels)
+    if net.pre is not None:
+        x_pair = torch.empty((2 * B, d), device=dev, dtype=torch.float32)
+        logn = torch.empty(2 * B, device=dev, dtype=torch.float32)
+        _lib.check(L.msgm_premodule_pair(h, _lib.ptr(y), _lib.ptr(v), _lib.ptr(x_pair), _lib.ptr(logn), B, d,
+                                         float(torch.sqrt(torch.tensor(float(d)))) / scale_image, st))
+        emb = emb + _sincos_mlp_pair(core.scale_embed, logn, core.model_channels)
+    else:
+        x_pair = torch.cat([y, v], 0) / scale_image
+    img = x_pair.view(2 * B, 1, S, S) if net.flatten_order == "C" else x_pair.view(2 * B, 1, S, S).transpose(2, 3).contiguous()
+    emb_act = PairAct.apply(emb, SILU)  # every ResBlock starts its embedding branch with the same SiLU(emb)
+    skips, cur = [], img
+    for blk in core.input_blocks:
+        for layer in blk:
+            cur = _run_layer_pair(layer, cur, emb_act)
+        skips.append(cur)
+    for layer in core.middle_block:
+        cur = _run_layer_pair(layer, cur, emb_act)
+    for blk in core.output_blocks:
+        cur = torch.cat([cur, skips.pop()], dim=1)
+        for layer in blk:
+            cur = _run_layer_pair(layer, cur, emb_act)
+    oc = core.out[2]
+    out = Conv2dPair.apply(_gn_silu(core.out[0], cur), oc.weight, oc.bias, None, 1, 1) * float(scale_image)
+    return (out.reshape(2 * B, d) if net.flatten_order == "C" else out.transpose(2, 3).contiguous().view(2 * B, d))
+
+
+def unet2d_ssm_loss(gen, t_, y, v):
+    base, net = gen.base_sde, gen.a
+    dev = y.device
+    sd, keep = base.desc(dev)
+    sd.dim = y.shape[1]
+    yc, vc = _lib.f32c(y, dev), _lib.f32c(v, dev)
+    tc = _lib.f32c(t_.reshape(-1), dev)
+    a_pair = unet2d_pair_forward(net, yc, vc, tc)
+    return SparseSsmLoss.apply(a_pair, yc, vc, tc, sd)

@@ -429,3 +429,46 @@ def test_unet1d_handwritten_training_matches_library_autograd():
     Bd.report(test="unet1d-handwritten-train-L1000", loss_rel=e_l, grad_rel=worst[0], worst_param=worst[1])
     assert e_l < 1e-4, e_l
     assert worst[0] < 5e-4, worst
+
+
+@pytest.mark.parametrize("S,B,order", [(32, 3, "F"), (16, 4, "C")])
+def test_unet2d_handwritten_training_matches_library_autograd(S, B, order):
+    """The hand-written forward-mode training path of the 2-D U-Net (unet_train.py: tcgen05 convs on primal / tangent pairs and
+    for the data gradients, csrc/unet_train.cu for GroupNorm / attention / SiLU second-order terms, weight gradients, embeddings)
+    against torch's own autograd through the library layers, up to the full configuration-4 size (32x32), with cuDNN switched
+    off for the hand-written run: loss and every parameter gradient (relative to the largest gradient entry of the net)."""
+    torch.manual_seed(23)
+    d = S * S
+    net = _build_unet2d(S, "NormalizeLogRadius", order, 5).to(DEV)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(torch.randn(64, d), beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=4, device=DEV, estim_cst_norm_dens_r_T=False)
+    gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=DEV).to(DEV)
+    gen.train()
+    y = (torch.randn(B, d) * 1.3).to(DEV)
+    v = (torch.rand(B, d).ge(0.5).float() * 2 - 1).to(DEV)
+    t = (torch.rand(B, 1) * 0.9 + 0.05).to(DEV)
+    from sdeflow_light_b200 import unet_train
+    assert unet_train.supported(gen, y)
+    gen.unet_train_kernels = False
+    gen.zero_grad()
+    l_ref = gen.ssm_loss(t, y, y, v)
+    l_ref.mean().backward()
+    g_ref = {k: p.grad.clone() for k, p in net.named_parameters()}
+    gmax = max(float(g.abs().max()) for g in g_ref.values())
+    gen.unet_train_kernels = True
+    gen.zero_grad()
+    n0 = P._lib.launch_count(DEV)
+    with torch.backends.cudnn.flags(enabled=False):
+        l_own = gen.ssm_loss(t, y, y, v)
+        l_own.mean().backward()
+    launches = P._lib.launch_count(DEV) - n0
+    e_l = _rel(l_own.detach(), l_ref.detach().cpu())
+    # per tensor: relative to its own largest entry, floored at 1e-4 of the net's largest gradient entry (the bias in front of
+    # a GroupNorm has an exactly-zero gradient: both paths return rounding noise there)
+    worst = max((float((p.grad - g_ref[k]).abs().max()) / max(float(g_ref[k].abs().max()), 1e-4 * gmax), k)
+                for k, p in net.named_parameters())
+    Bd.report(test=f"unet2d-handwritten-train-{S}x{S}", loss_rel=e_l, grad_rel=worst[0], worst_param=worst[1], launches=launches)
+    assert launches > 500                      # the net ran on this repo's kernels
+    assert e_l < 2e-4, e_l
+    assert worst[0] < 1e-3, worst

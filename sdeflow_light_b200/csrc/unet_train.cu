@@ -143,6 +143,40 @@ __global__ void __launch_bounds__(128) tap_sums_1d_kernel(const float* __restric
   }
 }
 
+// ---- register-tiled fp32 products ------------------------------------------------------------------------------------------
+// Both the conv weight gradient and the small dense products below are C (TM x TN) += A^T B over a K range staged through
+// shared memory as sA[k][TM], sB[k][TN].  A thread owns 8 x 8 outputs: rows {4 rg .. 4 rg + 3} and {TM/2 + 4 rg ..}, columns
+// likewise, so that one k step is four 16-byte shared-memory loads (conflict-free: the lanes of a quarter warp read
+// consecutive 16-byte words or the same word) for 64 FMAs.  Row strides TM + 4 / TN + 4 keep the loads aligned and put
+// neighbouring k rows four banks apart.
+template <int TM, int TN>
+struct Tile {
+  static constexpr int NT = (TM / 8) * (TN / 8);  // thread tiles covering the C tile
+  static constexpr int SA = TM + 4, SB = TN + 4;
+};
+
+// k steps [k_first, k_end) in steps of k_step of the staged tiles
+template <int TM, int TN>
+__device__ __forceinline__ void tile_fma(const float* __restrict__ sA, const float* __restrict__ sB, int tt, int k_first, int k_end,
+                                         int k_step, float (&acc)[8][8]) {
+  using T = Tile<TM, TN>;
+  const int rg = tt % (TM / 8), cg = tt / (TM / 8);
+  for (int k = k_first; k < k_end; k += k_step) {
+    const float4 a0 = *reinterpret_cast<const float4*>(sA + k * T::SA + 4 * rg);
+    const float4 a1 = *reinterpret_cast<const float4*>(sA + k * T::SA + TM / 2 + 4 * rg);
+    const float4 b0 = *reinterpret_cast<const float4*>(sB + k * T::SB + 4 * cg);
+    const float4 b1 = *reinterpret_cast<const float4*>(sB + k * T::SB + TN / 2 + 4 * cg);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+template <int T_>
+__device__ __forceinline__ int tile_index(int g, int i) { return (i < 4 ? 0 : T_ / 2 - 4) + 4 * g + i; }  // row / column of output i
+
 // ---- weight gradient of a convolution ------------------------------------------------------------------------------------
 struct WgradConvParams {
   const float* cot;   // (N, Cout, Ho, Wo)
@@ -154,108 +188,170 @@ struct WgradConvParams {
   long long pos_per_slice;  // output positions (n, oy, ox) per z-slice
 };
 
-// grid: x = 64x64 tile of (co, ci), y = tap, z = slice of the positions.  256 threads, 4x4 outputs each.
+// grid: x = TM x TN tile of (co, ci), y = tap, z = slice of the positions.  256 threads = Tile::NT thread tiles x KG groups that
+// take every KG-th position of a staged chunk; partial sums meet in gW through atomics (as the slices do).
+// Staging: a warp instruction covers 8 consecutive positions of 4 channels (32-byte global segments; banks 4 pp + ch: no
+// shared-memory conflict), and a thread keeps its position for the whole chunk, so (n, oy, ox) is decomposed once per chunk.
+// The global loads of chunk i + 1 are issued into registers before the FMAs of chunk i (the small tiles are latency-bound).
+template <int TM, int TN>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__ WgradConvParams P) {
+  using T = Tile<TM, TN>;
+  // positions per staged chunk: more for the small tiles, whose chunks would otherwise be two k steps between two barriers
+  constexpr int KG = 256 / T::NT, KT = TM + TN <= 64 ? 128 : (TM + TN <= 128 ? 64 : 32), NJ = KT / 32;
   const int Cin = P.C1 + P.C2;
-  const int tiles_ci = (Cin + 63) / 64;
-  const int tm = (blockIdx.x / tiles_ci) * 64, tn = (blockIdx.x % tiles_ci) * 64;
+  const int tiles_ci = (Cin + TN - 1) / TN;
+  const int tm = (blockIdx.x / tiles_ci) * TM, tn = (blockIdx.x % tiles_ci) * TN;
   const int ky = blockIdx.y / P.KW, kx = blockIdx.y % P.KW;
-  __shared__ float sC[32][65];
-  __shared__ float sI[32][65];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[4][4] = {};
+  __shared__ __align__(16) float sC[KT * T::SA];
+  __shared__ __align__(16) float sI[KT * T::SB];
+  const int tid = threadIdx.x, tt = tid % T::NT, kg = tid / T::NT;
+  const int pp = (tid & 7) + 8 * ((tid >> 5) & 3), ch0 = ((tid >> 3) & 3) + 4 * (tid >> 7);  // staging role: position, first channel
+  float acc[8][8] = {};
   const long long npos = (long long)P.N * P.Ho * P.Wo;
   const long long p_begin = (long long)blockIdx.z * P.pos_per_slice, p_end = min(npos, p_begin + P.pos_per_slice);
   const int Hu = P.Hi * P.up, Wu = P.Wi * P.up;  // extent the conv sees
-  for (long long p0 = p_begin; p0 < p_end; p0 += 32) {
-    // 32 positions x 64 channels of both operands; a warp walks 32 consecutive positions of one channel (coalesced)
+  const long long HWo = (long long)P.Ho * P.Wo, HWi = (long long)P.Hi * P.Wi;
+  float rc[NJ][TM / 8], ri[NJ][TN / 8];
+  auto fetch = [&](long long p0) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int e = tid + 256 * q, ch = e >> 5, pp = e & 31;
-      const long long p = p0 + pp;
-      float c = 0.0f, x = 0.0f;
-      if (p < p_end) {
-        const int ox = (int)(p % P.Wo), oy = (int)((p / P.Wo) % P.Ho);
-        const long long n = p / ((long long)P.Wo * P.Ho);
-        if (tm + ch < P.Cout) c = __ldg(P.cot + ((n * P.Cout + tm + ch) * P.Ho + oy) * P.Wo + ox);
-        const int iy = oy * P.stride + ky - P.pad_h, ix = ox * P.stride + kx - P.pad_w;
-        const int ci = tn + ch;
-        if (ci < Cin && iy >= 0 && iy < Hu && ix >= 0 && ix < Wu) {
-          const int sy = iy / P.up, sx = ix / P.up;
-          x = ci < P.C1 ? __ldg(P.in1 + ((n * P.C1 + ci) * P.Hi + sy) * P.Wi + sx)
-                        : __ldg(P.in2 + ((n * P.C2 + ci - P.C1) * P.Hi + sy) * P.Wi + sx);
-        }
+    for (int j = 0; j < NJ; ++j) {
+      const long long p = p0 + pp + 32 * j;
+      const bool live = p < p_end;
+      long long n = 0;
+      int ox = 0, oy = 0;
+      if (live) {
+        n = p / HWo;
+        const int r = (int)(p - n * HWo);
+        oy = r / P.Wo;
+        ox = r - oy * P.Wo;
       }
-      sC[pp][ch] = c;
-      sI[pp][ch] = x;
+      const int iy = oy * P.stride + ky - P.pad_h, ix = ox * P.stride + kx - P.pad_w;
+      const bool inside = live && iy >= 0 && iy < Hu && ix >= 0 && ix < Wu;
+      const float* cp = P.cot + (n * P.Cout) * HWo + (long long)oy * P.Wo + ox;
+      const long long ioff = (long long)(iy / P.up) * P.Wi + ix / P.up;
+#pragma unroll
+      for (int q = 0; q < TM / 8; ++q) {  // cotangent tile: TM channels x KT positions
+        const int ch = ch0 + 8 * q;
+        rc[j][q] = (live && tm + ch < P.Cout) ? __ldg(cp + (long long)(tm + ch) * HWo) : 0.0f;
+      }
+#pragma unroll
+      for (int q = 0; q < TN / 8; ++q) {  // input tile at this tap: TN channels x KT positions
+        const int ci = tn + ch0 + 8 * q;
+        float x = 0.0f;
+        if (inside && ci < Cin)
+          x = ci < P.C1 ? __ldg(P.in1 + (n * P.C1 + ci) * HWi + ioff) : __ldg(P.in2 + (n * P.C2 + ci - P.C1) * HWi + ioff);
+        ri[j][q] = x;
+      }
+    }
+  };
+  if (p_begin < p_end) fetch(p_begin);
+  for (long long p0 = p_begin; p0 < p_end; p0 += KT) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+      for (int q = 0; q < TM / 8; ++q) sC[(pp + 32 * j) * T::SA + ch0 + 8 * q] = rc[j][q];
+#pragma unroll
+      for (int q = 0; q < TN / 8; ++q) sI[(pp + 32 * j) * T::SB + ch0 + 8 * q] = ri[j][q];
     }
     __syncthreads();
-#pragma unroll 8
-    for (int pp = 0; pp < 32; ++pp) {
-      float c4[4], x4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { c4[i] = sC[pp][ty * 4 + i]; x4[i] = sI[pp][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(c4[i], x4[j], acc[i][j]);
-    }
+    if (p0 + KT < p_end) fetch(p0 + KT);
+    tile_fma<TM, TN>(sC, sI, tt, kg, KT, KG, acc);
     __syncthreads();
   }
+  const int rg = tt % (TM / 8), cg = tt / (TM / 8);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = tm + ty * 4 + i, ci = tn + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int co = tm + tile_index<TM>(rg, i), ci = tn + tile_index<TN>(cg, j);
       if (co < P.Cout && ci < Cin)
         atomicAdd(P.gW + (((size_t)co * P.Cw + P.coff + ci) * P.KH + ky) * P.KW + kx, acc[i][j]);
     }
 }
 
-// ---- small dense product: C (M x N, ldc) = [C +] op(A) op(B), op = identity or transpose ---------------------------------------
-// A is (M x K) [lda] or, transposed, stored (K x M); B is (K x N) [ldb] or, transposed, stored (N x K).
-__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Cm,
-                                                       int M, int N, int K, int lda, int ldb, int ldc, int ta, int tb, int accumulate,
-                                                       long long sa, long long sb, long long sc, float alpha) {
-  __shared__ float sA[16][65], sB[16][65];
+// ---- small dense product: C (M x N, ldc) = [C +] alpha op(A) op(B), op = identity or transpose -----------------------------------
+// A is (M x K) [lda] or, transposed, stored (K x M); B is (K x N) [ldb] or, transposed, stored (N x K).  256 threads per
+// TM x TN tile = Tile::NT thread tiles x KG groups; group g takes every KG-th k of a staged chunk of 16 and the groups' partial
+// tiles are summed through shared memory (tree, log2 KG rounds) -- the attention products of the training path are many small
+// matrices, so the threads have to come from the K axis.  Batched over blockIdx.z.
+template <int TM, int TN>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                       float* __restrict__ Cm, int M, int N, int K, int lda, int ldb, int ldc,
+                                                       int ta, int tb, int accumulate, long long sa, long long sb, long long sc,
+                                                       float alpha) {
+  using T = Tile<TM, TN>;
+  constexpr int KT = 16, NT = T::NT, KG = 256 / NT;
+  constexpr int EA = KT * TM / 256, EB = KT * TN / 256;  // staged elements per thread
+  __shared__ __align__(16) float sA[KT * T::SA];
+  __shared__ __align__(16) float sB[KT * T::SB];
+  __shared__ float red[KG > 1 ? 64 * 128 : 1];
   A += blockIdx.z * sa;  // batched: one product per blockIdx.z
   B += blockIdx.z * sb;
   Cm += blockIdx.z * sc;
-  const int tm = blockIdx.y * 64, tn = blockIdx.x * 64, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  const int tm = blockIdx.y * TM, tn = blockIdx.x * TN, tid = threadIdx.x, tt = tid % NT, kg = tid / NT;
+  float acc[8][8] = {};
+  float ra[EA], rb[EB];
+  auto fetch = [&](int k0) {  // lanes run along the operand's contiguous axis
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < EA; ++q) {
       const int e = tid + 256 * q;
-      {  // A tile: 16 k x 64 m
-        const int kk = ta ? (e >> 6) : (e & 15), mm = ta ? (e & 63) : (e >> 4);
-        const int k = k0 + kk, m = tm + mm;
-        sA[kk][mm] = (k < K && m < M) ? __ldg(ta ? A + (size_t)k * lda + m : A + (size_t)m * lda + k) : 0.0f;
-      }
-      {  // B tile: 16 k x 64 n
-        const int kk = tb ? (e & 15) : (e >> 6), nn = tb ? (e >> 4) : (e & 63);
-        const int k = k0 + kk, n = tn + nn;
-        sB[kk][nn] = (k < K && n < N) ? __ldg(tb ? B + (size_t)n * ldb + k : B + (size_t)k * ldb + n) : 0.0f;
-      }
+      const int kk = ta ? e / TM : e % KT, mm = ta ? e % TM : e / KT;
+      const int k = k0 + kk, m = tm + mm;
+      ra[q] = (k < K && m < M) ? __ldg(ta ? A + (size_t)k * lda + m : A + (size_t)m * lda + k) : 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < EB; ++q) {
+      const int e = tid + 256 * q;
+      const int kk = tb ? e % KT : e / TN, nn = tb ? e / KT : e % TN;
+      const int k = k0 + kk, n = tn + nn;
+      rb[q] = (k < K && n < N) ? __ldg(tb ? B + (size_t)n * ldb + k : B + (size_t)k * ldb + n) : 0.0f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += KT) {
+#pragma unroll
+    for (int q = 0; q < EA; ++q) {
+      const int e = tid + 256 * q;
+      sA[(ta ? e / TM : e % KT) * T::SA + (ta ? e % TM : e / KT)] = ra[q];
+    }
+#pragma unroll
+    for (int q = 0; q < EB; ++q) {
+      const int e = tid + 256 * q;
+      sB[(tb ? e % KT : e / TN) * T::SB + (tb ? e / KT : e % TN)] = rb[q];
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a4[4], b4[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a4[i] = sA[kk][ty * 4 + i]; b4[i] = sB[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
-    }
+    if (k0 + KT < K) fetch(k0 + KT);
+    tile_fma<TM, TN>(sA, sB, tt, kg, KT, KG, acc);
     __syncthreads();
   }
+  if constexpr (KG > 1) {  // tree sum over the K groups: the upper half writes, the lower half adds
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int half = KG / 2; half >= 1; half >>= 1) {
+      if (kg >= half && kg < 2 * half) {
+        const int slot = (kg - half) * NT + tt;  // < 128
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int m = tm + ty * 4 + i, n = tn + tx * 4 + j;
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) red[(i * 8 + j) * 128 + slot] = acc[i][j];
+      }
+      __syncthreads();
+      if (kg < half) {
+        const int slot = kg * NT + tt;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] += red[(i * 8 + j) * 128 + slot];
+      }
+      __syncthreads();
+    }
+    if (kg != 0) return;
+  }
+  const int rg = tt % (TM / 8), cg = tt / (TM / 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int m = tm + tile_index<TM>(rg, i), n = tn + tile_index<TN>(cg, j);
       if (m < M && n < N) {
         float* c = Cm + (size_t)m * ldc + n;
         *c = accumulate ? fmaf(alpha, acc[i][j], *c) : alpha * acc[i][j];
@@ -527,6 +623,24 @@ __global__ void __launch_bounds__(256) resample2_kernel(const float* __restrict_
   }
 }
 
+// tile choice: the largest of 128 x 128, 64 x 64, 32 x 32 that still gives every SM two CTAs (or 32 x 32)
+static void launch_gemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* Cm, int M, int N, int K, int lda, int ldb, int ldc,
+                            long long sa, long long sb, long long sc, int batch, int ta, int tb, float alpha, int accumulate,
+                            cudaStream_t st) {
+  auto ctas = [&](int t) { return (long long)((M + t - 1) / t) * ((N + t - 1) / t) * batch; };
+  const long long want = 2LL * ctx->num_sms;
+  if (M > 64 && N > 64 && ctas(128) >= want) {
+    gemm_f32_kernel<128, 128><<<dim3((N + 127) / 128, (M + 127) / 128, batch), 256, 0, st>>>(
+        A, B, Cm, M, N, K, lda, ldb, ldc, ta, tb, accumulate, sa, sb, sc, alpha);
+  } else if (M > 32 && N > 32 && ctas(64) >= want) {
+    gemm_f32_kernel<64, 64><<<dim3((N + 63) / 64, (M + 63) / 64, batch), 256, 0, st>>>(
+        A, B, Cm, M, N, K, lda, ldb, ldc, ta, tb, accumulate, sa, sb, sc, alpha);
+  } else {
+    gemm_f32_kernel<32, 32><<<dim3((N + 31) / 32, (M + 31) / 32, batch), 256, 0, st>>>(
+        A, B, Cm, M, N, K, lda, ldb, ldc, ta, tb, accumulate, sa, sb, sc, alpha);
+  }
+}
+
 }  // namespace msgm
 
 using namespace msgm;
@@ -614,12 +728,22 @@ int msgm_conv_wgrad(msgm_ctx* ctx, const float* cot, const float* in1, const flo
   // 1-D convolutions come in as Hi = Ho = KH = 1: no padding along that axis
   WgradConvParams P{cot, in1, in2, gW_accumulate, N, Cout, C1, C2, Cw, coff, KH, KW, stride, KH == 1 ? 0 : pad, pad, up, Hi, Wi, Ho, Wo, 0};
   const long long npos = (long long)N * Ho * Wo;
-  const int tiles = ((Cout + 63) / 64) * ((C1 + C2 + 63) / 64) * KH * KW;
-  long long slices = std::max<long long>(1, std::min<long long>((npos + 255) / 256, (long long)ctx->num_sms * 4 / std::max(1, tiles) + 1));
+  const int Cin = C1 + C2;
+  const int TMs = Cout > 64 ? 128 : (Cout > 32 ? 64 : 32), TNs = Cin > 64 ? 128 : (Cin > 32 ? 64 : 32);
+  const int tiles = ((Cout + TMs - 1) / TMs) * ((Cin + TNs - 1) / TNs);
+  // position slices: about three CTAs per SM in total, at least 256 positions each
+  long long slices = std::max<long long>(1, std::min<long long>((npos + 255) / 256,
+                                                                (long long)ctx->num_sms * 3 / std::max(1, tiles * KH * KW) + 1));
   slices = std::min<long long>(slices, 65535);
-  P.pos_per_slice = ((npos + slices - 1) / slices + 31) / 32 * 32;
+  P.pos_per_slice = ((npos + slices - 1) / slices + 127) / 128 * 128;
   const int nslice = (int)((npos + P.pos_per_slice - 1) / P.pos_per_slice);
-  conv_wgrad_kernel<<<dim3(((Cout + 63) / 64) * ((C1 + C2 + 63) / 64), KH * KW, nslice), 256, 0, (cudaStream_t)stream>>>(P);
+  const dim3 grid(tiles, KH * KW, nslice);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MSGM_WGRAD(TM_, TN_) if (TMs == TM_ && TNs == TN_) conv_wgrad_kernel<TM_, TN_><<<grid, 256, 0, st>>>(P)
+  MSGM_WGRAD(128, 128); MSGM_WGRAD(128, 64); MSGM_WGRAD(128, 32);
+  MSGM_WGRAD(64, 128); MSGM_WGRAD(64, 64); MSGM_WGRAD(64, 32);
+  MSGM_WGRAD(32, 128); MSGM_WGRAD(32, 64); MSGM_WGRAD(32, 32);
+#undef MSGM_WGRAD
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;
@@ -629,8 +753,7 @@ int msgm_gemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* Cm, int3
                   int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b, int32_t accumulate, void* stream) {
   if (!ctx || !A || !B || !Cm || M < 1 || N < 1 || K < 1) return ut_invalid("msgm_gemm_f32: bad argument");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
-  gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, B, Cm, M, N, K, lda, ldb, ldc, trans_a,
-                                                                                         trans_b, accumulate, 0, 0, 0, 1.0f);
+  launch_gemm_f32(ctx, A, B, Cm, M, N, K, lda, ldb, ldc, 0, 0, 0, 1, trans_a, trans_b, 1.0f, accumulate, (cudaStream_t)stream);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;
@@ -672,8 +795,8 @@ int msgm_bgemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* Cm, int
                    int32_t trans_b, float alpha, int32_t accumulate, void* stream) {
   if (!ctx || !A || !B || !Cm || M < 1 || N < 1 || K < 1 || batch < 1 || batch > 65535) return ut_invalid("msgm_bgemm_f32: bad argument");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
-  gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64, batch), 256, 0, (cudaStream_t)stream>>>(
-      A, B, Cm, M, N, K, lda, ldb, ldc, trans_a, trans_b, accumulate, stride_a, stride_b, stride_c, alpha);
+  launch_gemm_f32(ctx, A, B, Cm, M, N, K, lda, ldb, ldc, stride_a, stride_b, stride_c, batch, trans_a, trans_b, alpha, accumulate,
+                  (cudaStream_t)stream);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

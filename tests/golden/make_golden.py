@@ -209,6 +209,54 @@ def unet1d_case(ref, name, kind, L, B, N, seed, pre="NormalizeLogRadius"):
     _save(name, meta, **arrays)
 
 
+def build_unet1d_full(module, L, pre, seed):
+    """Default-size UNet1D (base 32, embedding 128: BASELINE config 3) from a seed, for fixtures that do not store weights."""
+    torch.manual_seed(seed)
+    net = module.UNet1D(input_dim=L, premodule=pre)
+    with torch.no_grad():
+        net.final.weight.mul_(4.0)
+    return net
+
+
+def unet1d_full_case(ref, name, L, B, N, seed, pre="NormalizeLogRadius"):
+    """UNet1D at the full configuration-3 size (L = 1000, default widths) with the sparse multiplicative SDE: forward, RK4
+    reverse sampling, SSM loss and gradients.  Weights are reproduced from the seed (checksums stored); gradients are stored as
+    per-tensor norms and leading entries."""
+    net = build_unet1d_full(ref.NNUnet1D, L, pre, seed)
+    torch.manual_seed(seed + 1)
+    sig = torch.sin(torch.linspace(0, 6.28, L)[None] * torch.randint(1, 4, (64, 1)) + 6.28 * torch.rand(64, 1)) \
+        + 0.1 * torch.randn(64, L)
+    base, gen, _ = ref_live.build(ref, "msgm_sparse", L, sig, pre, net=net)
+    x0 = sig[:B].clone() + 0.3 * torch.randn(B, L)
+    s = torch.rand(B)
+    with torch.no_grad():
+        fwd = net(x0, s)
+    torch.manual_seed(seed + 2)
+    xs = ref.sde_scheme.rk4_stratonovich_sampler(gen, x0, N, lmbd=0., keep_all_samples=True, include_t0=True,
+                                                 norm_correction=True)
+    torch.manual_seed(seed + 2)
+    noise = torch.stack([torch.randn_like(x0) for _ in range(N)])
+    t_ = torch.rand(B, 1).clamp_min(1e-3)
+    y = (x0 + 0.2 * torch.randn(B, L)).requires_grad_()
+    state = torch.get_rng_state()
+    v = ref.SDEs.sample_rademacher(x0.shape, "cpu")
+    torch.set_rng_state(state)
+    gen.train()
+    loss = gen.ssm_loss(t_, x0, y)
+    gen.zero_grad()
+    loss.mean().backward()
+    arrays = dict(x0=x0.numpy(), s=s.numpy(), fwd=fwd.numpy(), noise=noise.numpy(), out=xs.numpy(), t=t_.numpy(),
+                  y=y.detach().numpy(), v=v.numpy(), loss=loss.detach().numpy(), **_sde_arrays(base))
+    arrays["wsum"] = np.array([float(p_.double().sum()) for p_ in net.state_dict().values()])
+    names = [k for k, _ in net.named_parameters()]
+    arrays["gradnorm"] = np.array([float(p_.grad.norm()) for _, p_ in net.named_parameters()], dtype=np.float32)
+    arrays["gradhead"] = np.stack([torch.nn.functional.pad(p_.grad.flatten()[:8], (0, max(0, 8 - p_.numel()))).numpy()
+                                   for _, p_ in net.named_parameters()])
+    meta = dict(kind="msgm_sparse", dim=L, premodule=pre is not None, scheme="rk4", num_steps=N, lmbd=0.0,
+                norm_correction=True, include_t0=True, beta_min=0.1, beta_max=20.0, T=1.0, seed=seed, param_names=names)
+    _save(name, meta, **arrays)
+
+
 def build_unet2d(module, S, pre, order, seed):
     """Seeded construction shared by the fixture writer (reference module) and the tests (drop-in module): the same
     constructor order consumes the global RNG identically, so the 4.04 M weights need not be stored."""
@@ -271,6 +319,10 @@ def main():
     if "--unet2d-only" in sys.argv:
         unet2d_case(ref, "w01_unet2d_sparse_16x16", 16, 4, 2, 51)
         return
+    if "--full-size-only" in sys.argv:  # BASELINE configs 3 and 4 at their full sizes, a few samples
+        unet1d_full_case(ref, "v01_unet1d_sparse_L1000", 1000, 3, 2, 61)
+        unet2d_case(ref, "w02_unet2d_sparse_32x32", 32, 2, 1, 71)
+        return
     if "--unet-only" in sys.argv:
         unet1d_case(ref, "u01_unet1d_sparse_L64", "msgm_sparse", 64, 6, 4, 41)
         unet1d_case(ref, "u02_unet1d_sgm_L48", "sgm", 48, 5, 3, 42, pre=None)
@@ -299,6 +351,8 @@ def main():
     unet1d_case(ref, "u01_unet1d_sparse_L64", "msgm_sparse", 64, 6, 4, 41)
     unet1d_case(ref, "u02_unet1d_sgm_L48", "sgm", 48, 5, 3, 42, pre=None)
     unet2d_case(ref, "w01_unet2d_sparse_16x16", 16, 4, 2, 51)
+    unet1d_full_case(ref, "v01_unet1d_sparse_L1000", 1000, 3, 2, 61)
+    unet2d_case(ref, "w02_unet2d_sparse_32x32", 32, 2, 1, 71)
 
 
 if __name__ == "__main__":

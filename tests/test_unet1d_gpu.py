@@ -51,6 +51,42 @@ def test_unet1d_forward_sampler_ssm(name):
     assert e_f < 2e-5 and e_s < 2e-5 and e_l < 2e-5 and e_g < 2e-5
 
 
+@pytest.mark.parametrize("name", G.names("v"))
+def test_unet1d_full_size_against_reference(name):
+    """BASELINE configuration 3 at its full size (L = 1000, default widths; fixture from the live reference, weights reproduced
+    from the seed and proven by checksums): forward, two RK4 reverse steps on injected noise, SSM loss and every gradient
+    tensor (norms + leading entries) on the hand-written kernels."""
+    meta, arr = G.load(name)
+    base, T = Bd.base_from(meta, arr, DEV)
+    torch.manual_seed(meta["seed"])
+    net = P.UNet1D(input_dim=meta["dim"], premodule="NormalizeLogRadius" if meta["premodule"] else None)
+    with torch.no_grad():
+        net.final.weight.mul_(4.0)
+    assert [k for k, _ in net.named_parameters()] == meta["param_names"]
+    wsum = torch.tensor([float(p.double().sum()) for p in net.state_dict().values()], dtype=torch.float64)
+    assert float((wsum - arr["wsum"]).abs().max()) < 1e-9, "seeded weights differ from the reference's"
+    gen = P.PluginReverseSDE(base, net.to(DEV), T, deviceReverseSDE=DEV).to(DEV)
+    with torch.no_grad():
+        fwd = net(arr["x0"].to(DEV), arr["s"].to(DEV))
+    e_f = _rel(fwd, arr["fwd"])
+    out = P.rk4_stratonovich_sampler(gen, arr["x0"].to(DEV), meta["num_steps"], lmbd=0., keep_all_samples=True,
+                                     include_t0=True, norm_correction=True, noise=arr["noise"])
+    e_s = _rel(out, arr["out"])
+    gen.train()
+    gen.zero_grad()
+    with torch.backends.cudnn.flags(enabled=False):  # the hand-written training path: no library convolution may run
+        loss = gen.ssm_loss(arr["t"].to(DEV), arr["x0"].to(DEV), arr["y"].to(DEV), arr["v"].to(DEV))
+        e_l = _rel(loss.detach(), arr["loss"])
+        loss.mean().backward()
+    gn = torch.tensor([float(p.grad.norm()) for _, p in net.named_parameters()])
+    gh = torch.stack([torch.nn.functional.pad(p.grad.flatten()[:8], (0, max(0, 8 - p.numel()))).cpu()
+                      for _, p in net.named_parameters()])
+    e_g = float((gn - arr["gradnorm"]).abs().max() / arr["gradnorm"].max())
+    e_h = float((gh - arr["gradhead"]).abs().max()) / float(arr["gradhead"].abs().max())
+    Bd.report(test=name, fwd_rel=e_f, sampler_rel=e_s, loss_rel=e_l, gradnorm_rel=e_g, gradhead_rel=e_h)
+    assert e_f < 2e-5 and e_s < 5e-5 and e_l < 5e-5 and e_g < 1e-4 and e_h < 2e-4
+
+
 @pytest.mark.parametrize("kind,d,scheme,lmbd,nc", [("msgm_sparse", 1000, "rk4", 0.0, True), ("msgm_sparse", 257, "heun", 0.3, True),
                                                    ("sgm", 1024, "em", 0.5, False), ("msgm_sparse", 40, "em", 0.5, False)])
 def test_stage_kernels_against_oracle(kind, d, scheme, lmbd, nc):
@@ -464,9 +500,9 @@ def test_unet2d_handwritten_training_matches_library_autograd(S, B, order):
         l_own.mean().backward()
     launches = P._lib.launch_count(DEV) - n0
     e_l = _rel(l_own.detach(), l_ref.detach().cpu())
-    # per tensor: relative to its own largest entry, floored at 1e-4 of the net's largest gradient entry (the bias in front of
+    # per tensor: relative to its own largest entry, floored at 1e-3 of the net's largest gradient entry (the bias in front of
     # a GroupNorm has an exactly-zero gradient: both paths return rounding noise there)
-    worst = max((float((p.grad - g_ref[k]).abs().max()) / max(float(g_ref[k].abs().max()), 1e-4 * gmax), k)
+    worst = max((float((p.grad - g_ref[k]).abs().max()) / max(float(g_ref[k].abs().max()), 1e-3 * gmax), k)
                 for k, p in net.named_parameters())
     Bd.report(test=f"unet2d-handwritten-train-{S}x{S}", loss_rel=e_l, grad_rel=worst[0], worst_param=worst[1], launches=launches)
     assert launches > 500                      # the net ran on this repo's kernels

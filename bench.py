@@ -333,21 +333,32 @@ def time_unet_forward(P, dev):
             out["runs"].append({"net": name, "batch": B, "ms_per_forward": ms, "value": B / ms * 1e3,
                                 "algorithmic_tflops": gflop * B / ms, "torch_fp32_ms": ms_t,
                                 "rel_diff_vs_torch_fp32": err})
-    # one SSM training iteration of the same nets (sparse multiplicative SDE; one-launch noising, forward-mode loss through
-    # torch's fp32 library layers, Adam), replayed as CUDA graphs by train.GraphedSsmStep
+    # (i) RK4 reverse sampling of BASELINE configs 3 / 4 through the drop-in sampler (sparse multiplicative SDE, norm correction,
+    # in-kernel Philox): one CUDA graph per step (4 net evaluations + 4 stage updates), against SURVEY 8d's tensor bounds;
+    # (ii) one SSM training iteration of the same nets on the hand-written training path (unet_train.py: forward-mode pairs on the
+    # tcgen05 convs, hand-derived backward), with the one-launch noising and Adam, replayed as CUDA graphs by train.GraphedSsmStep
+    from sdeflow_light_b200 import unet_train
     from sdeflow_light_b200.train import GraphedSsmStep
-    for (name, net, _, d, _), (Bt, nfwd) in zip(nets, ((64, 16), (32, 128))):
+    bounds = {"unet1d_L1000_base32": 7.8e5, "vorticity_unet2d_32x32_base32": 2.9e5}
+    for (name, net, Bs, d, _), (Bt, nfwd) in zip(nets, ((64, 16), (32, 128))):
         try:
             data = torch.randn(512, d)
             T = torch.nn.Parameter(torch.FloatTensor([1.0]), requires_grad=False)
             base = P.MSGMsde(data, beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
                              num_steps_forward=nfwd, device=dev, estim_cst_norm_dens_r_T=False)
             gen = P.PluginReverseSDE(base, net, T, deviceReverseSDE=dev).to(dev)
-            step = GraphedSsmStep(gen, (Bt, d), lr=1e-4)
+            x0, nst = gen.latent_sample(Bs, d), 16
+            ms_s = timeit(lambda: P.rk4_stratonovich_sampler(gen, x0, nst, keep_all_samples=False, norm_correction=True,
+                                                             seed=1, device_out=True), 3)
+            entry = {"sampling_batch": Bs, "sampling_steps": nst, "sampling_ms_per_call": ms_s,
+                     "sampling_particle_steps_per_sec": Bs * nst / ms_s * 1e3,
+                     "sampling_frac_of_tensor_bound": Bs * nst / ms_s * 1e3 / bounds[name]}
             xs = data[:Bt].to(dev)
+            entry["train_path"] = "hand-written kernels" if unet_train.supported(gen, xs) else "library autograd"
+            step = GraphedSsmStep(gen, (Bt, d), lr=1e-4)
             ms = timeit(lambda: step(xs), 10)
-            entry = {"train_batch": Bt, "num_steps_forward": nfwd, "train_ms_per_iter": ms,
-                     "train_samples_per_sec": Bt / ms * 1e3, "train_loss": float(step.loss)}
+            entry.update({"train_batch": Bt, "num_steps_forward": nfwd, "train_ms_per_iter": ms,
+                          "train_samples_per_sec": Bt / ms * 1e3, "train_loss": float(step.loss)})
         except Exception as exc:
             entry = {"train_error": f"{type(exc).__name__}: {exc}"}
         for r in out["runs"]:

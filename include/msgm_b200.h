@@ -177,6 +177,32 @@ int msgm_ssm_mlp_fwd_bwd_tc(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_
 int msgm_stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,
                       int32_t norm_correction, int32_t forward_only, float s, float delta, const float* a,
                       const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B, void* stream);
+/* Device-side step clock of the per-stage sampler.  With it every step-dependent value of the loop sde_scheme.py:223-255 is
+ * read from device memory, so ONE captured CUDA graph (noise draw, nstage net evaluations, nstage stage updates, clock advance)
+ * is replayed for all N steps instead of ~130 host launches per step: clock[0] = index i of the current step,
+ * s_table[i * nstage + st] = noise time of stage st of step i (N * nstage + 1 entries, the last one unused). */
+typedef struct msgm_step_clock {
+  const int32_t* clock;      /* device (1,) */
+  const float* s_table;      /* device (N * nstage + 1,) */
+  float* s_next;             /* device (B,) or NULL: receives, per row, the noise time of the NEXT net evaluation */
+  float* traj;               /* device (N + include_t0, B, d) or NULL: the new state lands at [clock + include_t0] (last stage) */
+  const int32_t* keep_step;  /* device (B,) per-row step to keep, with keep_out (samplesToKeep, sde_scheme.py:101-103,258-260) */
+  float* keep_out;           /* device (B, d) or NULL */
+  int32_t include_t0;
+  int32_t reserved;
+} msgm_step_clock;
+/* msgm_stage_update with the stage time taken from clk (stage input / output as above);
+ * msgm_philox_normal_clocked: out = scale * N(0,1) keyed by the clock's step, or scale * noise[clock] when injected noise
+ * (N,B,d) is given; also writes the time of the step's first net evaluation to clk->s_next;
+ * msgm_clock_advance: clock[0] += 1 (last node of the step graph). */
+int msgm_stage_update_clocked(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,
+                              int32_t norm_correction, int32_t forward_only, const msgm_step_clock* clk, float delta,
+                              const float* a, const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B,
+                              void* stream);
+int msgm_philox_normal_clocked(msgm_ctx* ctx, float* out, int32_t d, int64_t B, float scale, uint64_t seed,
+                               uint64_t particle_offset, const msgm_step_clock* clk, int32_t nstage,
+                               const float* noise_or_null, void* stream);
+int msgm_clock_advance(msgm_ctx* ctx, int32_t* clock, void* stream);
 /* r[b] = |x[b,:]|  (torch.norm(x_t, dim=1), sde_scheme.py:66,124,205). */
 int msgm_row_norm(msgm_ctx* ctx, const float* x, float* r, int32_t d, int64_t B, void* stream);
 /* out (B,d) = scale * N(0,1) with the samplers' Philox keying (seed, particle_offset + row, step). */

@@ -39,6 +39,11 @@ class SampleArgs(C.Structure):
                 ("keep_step", C.c_void_p), ("keep_out", C.c_void_p), ("T_rows", C.c_void_p)]
 
 
+class StepClock(C.Structure):
+    _fields_ = [("clock", C.c_void_p), ("s_table", C.c_void_p), ("s_next", C.c_void_p), ("traj", C.c_void_p),
+                ("keep_step", C.c_void_p), ("keep_out", C.c_void_p), ("include_t0", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Conv1dDesc(C.Structure):
     _fields_ = [("x1", C.c_void_p), ("x2", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("E", C.c_void_p),
                 ("out", C.c_void_p)] + [(n, C.c_int32) for n in ("B", "C1", "C2", "Cemb", "Cout", "K", "stride", "pad",
@@ -72,7 +77,8 @@ SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy",
            "msgm_sample_mlp", "msgm_noise_forward", "msgm_ssm_prepare", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward", "msgm_ssm_tc_scratch_bytes",
            "msgm_ssm_mlp_fwd_bwd_tc",
-           "msgm_stage_update", "msgm_row_norm", "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums", "msgm_kde_logpdf",
+           "msgm_stage_update", "msgm_stage_update_clocked", "msgm_philox_normal_clocked", "msgm_clock_advance", "msgm_row_norm",
+           "msgm_philox_normal", "msgm_latent_sample", "msgm_mmd_sums", "msgm_kde_logpdf",
            "msgm_conv1d", "msgm_emb_fold", "msgm_convt1d_k4s2", "msgm_embed_mlp", "msgm_normalize_log_radius",
            "msgm_conv2d", "msgm_gn_stats", "msgm_emb_proj", "msgm_sincos_embed_mlp", "msgm_attention", "msgm_vort_pre",
            "msgm_vort_post", "msgm_conv2d_tc", "msgm_conv2d_tc_pack_bytes", "msgm_conv2d_tc_pack", "msgm_gn_scale_shift",
@@ -109,6 +115,12 @@ def lib() -> C.CDLL:
                     [C.c_float, C.c_int64, C.c_void_p]
                 L.msgm_stage_update.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.c_int32, C.c_int32, C.c_float, C.c_int32,
                                                 C.c_int32, C.c_float, C.c_float] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
+                L.msgm_stage_update_clocked.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                                        C.c_int32, C.POINTER(StepClock), C.c_float] + [C.c_void_p] * 6 + \
+                    [C.c_int64, C.c_void_p]
+                L.msgm_philox_normal_clocked.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64,
+                                                         C.c_uint64, C.POINTER(StepClock), C.c_int32, C.c_void_p, C.c_void_p]
+                L.msgm_clock_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
                 L.msgm_row_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
                 L.msgm_philox_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64,
                                                  C.c_uint64, C.c_uint32, C.c_void_p]

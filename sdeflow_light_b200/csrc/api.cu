@@ -34,9 +34,11 @@ int ssm_fwd_bwd_tc(msgm_ctx*, const msgm_sde_desc*, const msgm_mlp_desc*, const 
                    const float*, float*, float*, float*, float, int64_t, cudaStream_t);
 
 int stage_update(msgm_ctx*, const msgm_sde_desc*, int, int, float, int, int, float, float, const float*, const float*,
-                 const float*, float*, float*, float*, int64_t, cudaStream_t);
+                 const float*, float*, float*, float*, int64_t, cudaStream_t, const msgm_step_clock*);
 int row_norm(msgm_ctx*, const float*, float*, int, int64_t, cudaStream_t);
-int philox_normal(msgm_ctx*, float*, int, int64_t, float, uint64_t, uint64_t, uint32_t, cudaStream_t);
+int philox_normal(msgm_ctx*, float*, int, int64_t, float, uint64_t, uint64_t, uint32_t, cudaStream_t, const msgm_step_clock*,
+                  const float*, int);
+int clock_advance(msgm_ctx*, int32_t*, cudaStream_t);
 
 int latent_sample(msgm_ctx*, const float*, int, int, int, const float*, const float*, float*, int, int64_t, uint64_t,
                   uint64_t, cudaStream_t);
@@ -267,9 +269,11 @@ int msgm_ssm_mlp_fwd_bwd_tc(msgm_ctx* ctx, const msgm_sde_desc* sde, const msgm_
                         (cudaStream_t)stream);
 }
 
-int msgm_stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,
-                      int32_t norm_correction, int32_t forward_only, float s, float delta, const float* a,
-                      const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B, void* stream) {
+static int stage_update_checked(const char* who, msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,
+                                int32_t norm_correction, int32_t forward_only, float s, float delta, const float* a,
+                                const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B, void* stream,
+                                const msgm_step_clock* clk) {
+  (void)who;
   if (!ctx || !sde || !dW || !x || !y || !ks) return invalid("msgm_stage_update: NULL argument");
   if (!forward_only && !a) return invalid("msgm_stage_update: score-net output missing");
   if (norm_correction && !r0) return invalid("msgm_stage_update: r0 missing");
@@ -284,10 +288,28 @@ int msgm_stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, i
   if (scheme < MSGM_SCHEME_EM || scheme > MSGM_SCHEME_RK4) return invalid("unknown scheme");
   const int nstage = scheme == MSGM_SCHEME_RK4 ? 4 : (scheme == MSGM_SCHEME_HEUN ? 2 : 1);
   if (stage < 0 || stage >= nstage) return invalid("stage out of range");
+  if (clk && (!clk->clock || !clk->s_table)) return invalid("msgm_stage_update_clocked: clock / s_table missing");
+  if (clk && clk->keep_out && !clk->keep_step) return invalid("msgm_stage_update_clocked: keep_step missing");
   if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return stage_update(ctx, sde, scheme, stage, lmbd, norm_correction, forward_only, s, delta, a, dW, r0, x, y, ks, B,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, clk);
+}
+
+int msgm_stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,
+                      int32_t norm_correction, int32_t forward_only, float s, float delta, const float* a,
+                      const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B, void* stream) {
+  return stage_update_checked("msgm_stage_update", ctx, sde, scheme, stage, lmbd, norm_correction, forward_only, s, delta, a, dW, r0,
+                              x, y, ks, B, stream, nullptr);
+}
+
+int msgm_stage_update_clocked(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t scheme, int32_t stage, float lmbd,
+                              int32_t norm_correction, int32_t forward_only, const msgm_step_clock* clk, float delta,
+                              const float* a, const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B,
+                              void* stream) {
+  if (!clk) return invalid("msgm_stage_update_clocked: clock missing");
+  return stage_update_checked("msgm_stage_update_clocked", ctx, sde, scheme, stage, lmbd, norm_correction, forward_only, 0.0f, delta,
+                              a, dW, r0, x, y, ks, B, stream, clk);
 }
 
 int msgm_row_norm(msgm_ctx* ctx, const float* x, float* r, int32_t d, int64_t B, void* stream) {
@@ -302,7 +324,23 @@ int msgm_philox_normal(msgm_ctx* ctx, float* out, int32_t d, int64_t B, float sc
   if (!ctx || !out || d < 1) return invalid("msgm_philox_normal: bad argument");
   if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
-  return philox_normal(ctx, out, d, B, scale, seed, particle_offset, step, (cudaStream_t)stream);
+  return philox_normal(ctx, out, d, B, scale, seed, particle_offset, step, (cudaStream_t)stream, nullptr, nullptr, 1);
+}
+
+int msgm_philox_normal_clocked(msgm_ctx* ctx, float* out, int32_t d, int64_t B, float scale, uint64_t seed,
+                               uint64_t particle_offset, const msgm_step_clock* clk, int32_t nstage,
+                               const float* noise_or_null, void* stream) {
+  if (!ctx || !out || d < 1 || !clk || !clk->clock || !clk->s_table || nstage < 1)
+    return invalid("msgm_philox_normal_clocked: bad argument");
+  if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return philox_normal(ctx, out, d, B, scale, seed, particle_offset, 0u, (cudaStream_t)stream, clk, noise_or_null, nstage);
+}
+
+int msgm_clock_advance(msgm_ctx* ctx, int32_t* clock, void* stream) {
+  if (!ctx || !clock) return invalid("msgm_clock_advance: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return clock_advance(ctx, clock, (cudaStream_t)stream);
 }
 
 int msgm_latent_sample(msgm_ctx* ctx, const float* rT_sorted, int32_t n_r, int32_t log_map, int32_t msgm, const float* U,

@@ -28,6 +28,14 @@ struct StageParams {
   float* y;        // (B,d) stage input (in) / next stage input (out); aliases x on stage 0
   float* ks;       // (B,d) running Runge-Kutta sum
   long long B;
+  // device-side step clock (msgm_step_clock): all NULL / 0 for the host-clocked call
+  const int* clock;
+  const float* s_tab;
+  float* s_next;
+  float* traj;
+  const int* keep_step;
+  float* keep_out;
+  int inc_t0;
 };
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -55,7 +63,9 @@ __global__ void __launch_bounds__(256) stage_update_kernel(const __grid_constant
   const bool last = P.stage == nstage - 1;
   const bool ito = P.scheme == MSGM_SCHEME_EM;
   const float lm = P.lmbd, delta = P.delta;
-  const float bt = beta_of(P.bmin, P.bdel, P.s), sb = sqrtf(bt);
+  const int step = P.clock ? *P.clock : 0;
+  const float s_cur = P.clock ? P.s_tab[step * nstage + P.stage] : P.s;
+  const float bt = beta_of(P.bmin, P.bdel, s_cur), sb = sqrtf(bt);
   const float c_a = P.fwd ? 0.0f : delta * (1.0f - 0.5f * lm);
   const float c_w = P.fwd ? 1.0f : sqrtf(1.0f - lm);
   const float c_f = P.fwd ? (ito ? 1.0f : 0.0f) : (ito ? (1.0f - 2.0f * lm) : -lm);
@@ -115,12 +125,20 @@ __global__ void __launch_bounds__(256) stage_update_kernel(const __grid_constant
     if (last) {
       float sc = 1.0f;
       if (P.nc) sc = P.r0[row] / sqrtf(block_sum(sq, red));
+      float* tr = P.traj ? P.traj + ((long long)(step + P.inc_t0) * P.B + row) * d : nullptr;
+      float* ko = (P.keep_step && P.keep_step[row] == step + P.inc_t0) ? P.keep_out + row * d : nullptr;
 #pragma unroll
       for (int e = 0; e < MAXE; ++e) {
         const int c = threadIdx.x + e * 256;
-        if (c < d) xr[c] = Kv[e] * sc;
+        if (c < d) {
+          const float xn = Kv[e] * sc;
+          xr[c] = xn;
+          if (tr) tr[c] = xn;
+          if (ko) ko[c] = xn;
+        }
       }
     }
+    if (P.s_next && threadIdx.x == 0) P.s_next[row] = P.s_tab[step * nstage + P.stage + 1];  // time of the next net evaluation
     __syncthreads();
   }
 }
@@ -139,24 +157,40 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__
 }
 
 // dW = scale * N(0,1), same Philox keying as the fused samplers: (seed, global particle, step, component block)
+// With a step clock the step index comes from device memory, injected noise (N,B,d) replaces Philox when given, and the
+// noise time of the step's first net evaluation is written per row (s_first).
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, int d, long long B, float scale,
-                                                            unsigned long long seed, unsigned long long poff, unsigned step) {
+                                                            unsigned long long seed, unsigned long long poff, unsigned step_host,
+                                                            const int* __restrict__ clock, const float* __restrict__ noise,
+                                                            const float* __restrict__ s_tab, float* __restrict__ s_first,
+                                                            int nstage) {
+  const unsigned step = clock ? (unsigned)*clock : step_host;
   const long long nblk = (long long)((d + 3) / 4);
   const long long total = B * nblk;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / nblk;
     const int blk = (int)(i % nblk);
-    const float4 z = philox_normal4(seed, poff + (unsigned long long)row, step, (unsigned)blk);
-    const float zz[4] = {z.x, z.y, z.z, z.w};
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noise) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (blk * 4 + c < d) zz[c] = noise[((long long)step * B + row) * d + blk * 4 + c];
+    } else {
+      const float4 z = philox_normal4(seed, poff + (unsigned long long)row, step, (unsigned)blk);
+      zz[0] = z.x; zz[1] = z.y; zz[2] = z.z; zz[3] = z.w;
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       if (blk * 4 + c < d) out[row * d + blk * 4 + c] = scale * zz[c];
+    if (s_first && blk == 0) s_first[row] = s_tab[step * nstage];
   }
 }
 
+__global__ void clock_advance_kernel(int* clock) { *clock += 1; }
+
 int stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int scheme, int stage, float lmbd, int nc, int fwd, float s,
                  float delta, const float* a, const float* dW, const float* r0, float* x, float* y, float* ks, int64_t B,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const msgm_step_clock* clk) {
   StageParams P{};
   P.kind = sde->kind;
   P.d = sde->dim;
@@ -170,6 +204,10 @@ int stage_update(msgm_ctx* ctx, const msgm_sde_desc* sde, int scheme, int stage,
   P.delta = delta;
   P.lmbd = lmbd;
   P.a = a; P.dW = dW; P.r0 = r0; P.x = x; P.y = y; P.ks = ks; P.B = B;
+  if (clk) {
+    P.clock = clk->clock; P.s_tab = clk->s_table; P.s_next = clk->s_next; P.traj = clk->traj;
+    P.keep_step = clk->keep_out ? clk->keep_step : nullptr; P.keep_out = clk->keep_out; P.inc_t0 = clk->include_t0;
+  }
   const int grid = (int)std::min<long long>(B, (long long)ctx->num_sms * 8);
   stage_update_kernel<<<grid, 256, 0, stream>>>(P);
   ctx->launches += 1;
@@ -185,10 +223,18 @@ int row_norm(msgm_ctx* ctx, const float* x, float* r, int d, int64_t B, cudaStre
 }
 
 int philox_normal(msgm_ctx* ctx, float* out, int d, int64_t B, float scale, uint64_t seed, uint64_t poff, uint32_t step,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const msgm_step_clock* clk, const float* noise, int nstage) {
   const long long total = B * ((d + 3) / 4);
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
-  philox_normal_kernel<<<grid, 256, 0, stream>>>(out, d, B, scale, seed, poff, step);
+  philox_normal_kernel<<<grid, 256, 0, stream>>>(out, d, B, scale, seed, poff, step, clk ? clk->clock : nullptr, noise,
+                                                 clk ? clk->s_table : nullptr, clk ? clk->s_next : nullptr, nstage);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int clock_advance(msgm_ctx* ctx, int32_t* clock, cudaStream_t stream) {
+  clock_advance_kernel<<<1, 1, 0, stream>>>(clock);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

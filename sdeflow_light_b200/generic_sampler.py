@@ -17,6 +17,55 @@ from . import _lib
 
 _NSTAGE = {_lib.SCHEME_EM: 1, _lib.SCHEME_HEUN: 2, _lib.SCHEME_RK4: 4}
 
+# One CUDA graph per STEP: calls with at least GRAPH_MIN_STEPS steps capture the launches of one whole step once (noise draw,
+# nstage net evaluations = ~130 kernels each for the U-Nets, nstage stage updates) and replay that graph num_steps times; the
+# step index and the stage times are read from device memory (msgm_step_clock), so the graph is step-independent.  Measured
+# on a B200 (tools/unet_sampling_bench.py, profiles/unet_sampling_bench_r02.txt): the eager loop is already GPU-bound (the
+# per-stage time IS the net forward, 0.5 ms at batch 16 and 0.98 ms at batch 256 for the 1-D U-Net), so the graph changes
+# throughput by less than the ~12 ms its capture costs per call; what it buys is a host thread that issues one launch per step
+# instead of ~520.  Hence the threshold: only long calls (the drivers' N = 1000) take this path.
+STEP_GRAPH = True
+GRAPH_MIN_STEPS = 256
+
+
+def _run_step_graph(handle, L, stream, device, sd, scheme, nstage, net, fwd, lmbd, norm_correction, delta, stage_time, num_steps,
+                    noise, seed, particle_offset, include_t0, x, y, ks, dW, r0, s_vec, traj, keep_step, keep_out):
+    f32 = np.float32
+    B, d = x.shape
+    s_tab = np.zeros(num_steps * nstage + 1, dtype=np.float32)
+    for i in range(num_steps):
+        for st in range(nstage):
+            s_tab[i * nstage + st] = stage_time(i, st)
+    s_dev = torch.from_numpy(s_tab).to(device)
+    clock = torch.zeros(1, device=device, dtype=torch.int32)
+    keep32 = None if keep_step is None else keep_step.to(torch.int32).contiguous()
+    clk = _lib.StepClock(clock.data_ptr(), s_dev.data_ptr(), s_vec.data_ptr(), None if traj is None else traj.data_ptr(),
+                         None if keep32 is None else keep32.data_ptr(), None if keep_out is None else keep_out.data_ptr(),
+                         int(bool(include_t0)), 0)
+
+    def step_body():
+        stream = _lib.stream_ptr(device)  # the capture runs on torch's capture stream, not on the caller's
+        _lib.check(L.msgm_philox_normal_clocked(handle, _lib.ptr(dW), d, B, float(f32(delta ** 0.5)), int(seed or 0),
+                                                int(particle_offset), C.byref(clk), nstage, _lib.ptr(noise), stream))
+        for st in range(nstage):
+            a = None
+            if not fwd:
+                a = _lib.f32c(net(x if st == 0 else y, s_vec), device).reshape(B, d)
+            _lib.check(L.msgm_stage_update_clocked(handle, C.byref(sd), scheme, st, float(lmbd), int(bool(norm_correction)),
+                                                   int(fwd), C.byref(clk), float(f32(delta)), _lib.ptr(a), _lib.ptr(dW),
+                                                   _lib.ptr(r0), _lib.ptr(x), _lib.ptr(y), _lib.ptr(ks), B, stream))
+        _lib.check(L.msgm_clock_advance(handle, _lib.ptr(clock), stream))
+
+    # the first step runs eagerly: it is step 0 of the result AND the warm-up that packs weight images / sets kernel
+    # attributes before the capture
+    step_body()
+    torch.cuda.synchronize(device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step_body()
+    for _ in range(1, num_steps):
+        graph.replay()
+
 
 def run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, include_t0, T_run, norm_correction, noise,
         seed, particle_offset, device_out):
@@ -59,29 +108,37 @@ def run(scheme, sde, x_0, num_steps, lmbd, keep_all_samples, samplesToKeep, incl
         keep_step = torch.as_tensor(samplesToKeep).reshape(-1).to(device)
         keep_out = torch.zeros((B, d), device=device, dtype=torch.float32)
     s_vec = torch.empty(B, device=device, dtype=torch.float32)
-    for i in range(num_steps):
-        if noise is not None:
-            torch.mul(noise[i], float(f32(delta ** 0.5)), out=dW)
-        else:
-            _lib.check(L.msgm_philox_normal(handle, _lib.ptr(dW), d, B, float(f32(delta ** 0.5)), int(seed),
-                                            int(particle_offset), i, stream))
-        for st in range(nstage):
-            t_s = ts[i]
-            if st > 0:
-                t_s = f32(t_s + f32(delta / 2)) if (nstage == 4 and st < 3) else f32(t_s + f32(delta))
-            s = float(t_s) if fwd else float(f32(T_sde - t_s))
-            a = None
-            if not fwd:
-                s_vec.fill_(s)
-                a = _lib.f32c(net(x if st == 0 else y, s_vec), device).reshape(B, d)
-            _lib.check(L.msgm_stage_update(handle, C.byref(sd), scheme, st, float(lmbd), int(bool(norm_correction)),
-                                           int(fwd), s, float(f32(delta)), _lib.ptr(a), _lib.ptr(dW), _lib.ptr(r0),
-                                           _lib.ptr(x), _lib.ptr(y), _lib.ptr(ks), B, stream))
-        if traj is not None:
-            traj[i + (1 if include_t0 else 0)].copy_(x)
-        elif keep_step is not None:
-            m = keep_step == (i + (1 if include_t0 else 0))
-            torch.where(m[:, None], x, keep_out, out=keep_out)  # no nonzero(): no host sync inside the loop
+
+    def stage_time(i, st):
+        t_s = ts[i]
+        if st > 0:
+            t_s = f32(t_s + f32(delta / 2)) if (nstage == 4 and st < 3) else f32(t_s + f32(delta))
+        return float(t_s) if fwd else float(f32(T_sde - t_s))
+
+    if STEP_GRAPH and num_steps >= GRAPH_MIN_STEPS and not torch.cuda.is_current_stream_capturing():
+        _run_step_graph(handle, L, stream, device, sd, scheme, nstage, net, fwd, lmbd, norm_correction, delta, stage_time,
+                        num_steps, noise, seed, particle_offset, include_t0, x, y, ks, dW, r0, s_vec, traj, keep_step, keep_out)
+    else:
+        for i in range(num_steps):
+            if noise is not None:
+                torch.mul(noise[i], float(f32(delta ** 0.5)), out=dW)
+            else:
+                _lib.check(L.msgm_philox_normal(handle, _lib.ptr(dW), d, B, float(f32(delta ** 0.5)), int(seed),
+                                                int(particle_offset), i, stream))
+            for st in range(nstage):
+                s = stage_time(i, st)
+                a = None
+                if not fwd:
+                    s_vec.fill_(s)
+                    a = _lib.f32c(net(x if st == 0 else y, s_vec), device).reshape(B, d)
+                _lib.check(L.msgm_stage_update(handle, C.byref(sd), scheme, st, float(lmbd), int(bool(norm_correction)),
+                                               int(fwd), s, float(f32(delta)), _lib.ptr(a), _lib.ptr(dW), _lib.ptr(r0),
+                                               _lib.ptr(x), _lib.ptr(y), _lib.ptr(ks), B, stream))
+            if traj is not None:
+                traj[i + (1 if include_t0 else 0)].copy_(x)
+            elif keep_step is not None:
+                m = keep_step == (i + (1 if include_t0 else 0))
+                torch.where(m[:, None], x, keep_out, out=keep_out)  # no nonzero(): no host sync inside the loop
     out = traj if keep_all_samples else (keep_out if samplesToKeep is not None else x)
     if device_out:
         return out

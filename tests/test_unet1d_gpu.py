@@ -508,3 +508,46 @@ def test_unet2d_handwritten_training_matches_library_autograd(S, B, order):
     assert launches > 500                      # the net ran on this repo's kernels
     assert e_l < 2e-4, e_l
     assert worst[0] < 1e-3, worst
+
+
+@pytest.mark.parametrize("which,mode", [("unet1d", "traj"), ("unet1d", "keep"), ("unet2d", "final"), ("fwd", "traj")])
+def test_step_graph_sampler_is_bit_identical_to_the_eager_loop(which, mode):
+    """generic_sampler: one captured CUDA graph per step (device-side step clock: step index, stage times, trajectory slot and
+    samplesToKeep rows all read from device memory) against the eager per-launch loop: same kernels, same order, so every
+    state must be bit-identical -- with in-kernel Philox and with injected noise."""
+    from sdeflow_light_b200 import generic_sampler as GS
+    torch.manual_seed(5)
+    N, B = 12, 7
+    if which == "unet2d":
+        d, net = 256, _build_unet2d(16, "NormalizeLogRadius", "F", 3)
+    else:
+        d, net = 120, P.UNet1D(120, premodule="NormalizeLogRadius")
+        with torch.no_grad():
+            net.final.weight.mul_(4.0)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(torch.randn(64, d), beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=N, device=DEV, estim_cst_norm_dens_r_T=False)
+    gen = P.PluginReverseSDE(base, net.to(DEV), T, deviceReverseSDE=DEV).to(DEV)
+    x0 = torch.randn(B, d).to(DEV)
+    kw = dict(lmbd=0., norm_correction=True, device_out=True)
+    if mode == "traj":
+        kw.update(keep_all_samples=True, include_t0=True)
+    elif mode == "keep":
+        kw.update(keep_all_samples=False, include_t0=True, samplesToKeep=torch.randint(1, N + 1, (B,)))
+    else:
+        kw.update(keep_all_samples=False)
+    sde = P.forward_SDE(base, T).to(DEV) if which == "fwd" else gen
+    for noise in (None, torch.randn(N, B, d)):
+        res = {}
+        for graphed in (False, True):
+            GS.STEP_GRAPH, old_min = graphed, GS.GRAPH_MIN_STEPS
+            GS.GRAPH_MIN_STEPS = 4
+            try:
+                l0 = P._lib.launch_count(DEV)
+                res[graphed] = P.rk4_stratonovich_sampler(sde, x0, N, seed=11, noise=noise, **kw).clone()
+                launches = P._lib.launch_count(DEV) - l0
+            finally:
+                GS.STEP_GRAPH, GS.GRAPH_MIN_STEPS = True, old_min
+        assert torch.isfinite(res[True]).all()
+        assert torch.equal(res[True], res[False]), float((res[True] - res[False]).abs().max())
+    Bd.report(test="step-graph-sampler", which=which, mode=mode, host_launches_graphed=launches)

@@ -52,6 +52,14 @@
 #ifndef MSGM_TC_POLY_PAIRS
 #define MSGM_TC_POLY_PAIRS 0
 #endif
+//   MSGM_TC_TCG8        d in 5..8: the dense G . y contraction as a split-precision MMA (1) or on the CUDA cores from the fp32
+//                       copy of G in shared memory (0); without the per-slot operand tiles a 4th slot fits shared memory
+#ifndef MSGM_TC_TCG8
+#define MSGM_TC_TCG8 1
+#endif
+#ifndef MSGM_TC_SLOT4
+#define MSGM_TC_SLOT4 1
+#endif
 
 namespace msgm {
 
@@ -69,19 +77,19 @@ struct TcLayout {
   static constexpr int oW2 = oW1 + W1_BYTES;
   static constexpr int oW3 = oW2 + WH_BYTES;
   static constexpr int oW4 = oW3 + WH_BYTES;
-  static constexpr bool TCG = DP == 8;                         // dense G . y on the tensor pipe (d in 5..8)
+  static constexpr bool TCG = DP == 8 && MSGM_TC_TCG8;         // dense G . y on the tensor pipe (d in 5..8)
   static constexpr int GI_BYTES = 4096;                        // fp16 [4][8][8][8]: rows n = i*8+k, k-index = split j
   static constexpr int oGI = oW4 + W4_BYTES;
   static constexpr int IMG_BYTES = oGI + GI_BYTES;             // what the pack kernel writes / TMA copies
   static constexpr int oOnes = IMG_BYTES;                      // fp16 [2][16][8][8]: A operand of the bias slices
   static constexpr int oG = oOnes + 4096;                      // fp32 [DP][DP][DP] (dense)
   static constexpr int oLG = oG + 4 * DP * DP * DP;            // fp32 [DP][DP]
-  static constexpr int oW4f = oLG + 4 * DP * DP;               // fp32 [128][DP] + b4[DP]: CUDA-core output layer
-  static constexpr int oBar = ((oW4f + 4 * (128 * DP + DP) + 15) / 16) * 16;  // 1 + 2*NSLOT mbarriers + tmem slot
+  static constexpr int oW4f = oLG + 4 * DP * DP;               // fp32 [128][DP] + b4[DP]: CUDA-core output layer (d <= 4 only)
+  static constexpr int oBar = ((oW4f + (DP <= 4 ? 4 * (128 * DP + DP) : 0) + 15) / 16) * 16;  // 1 + 2*NSLOT mbarriers + tmem slot
   static constexpr int oXu = oBar + 128;                       // XU ticket locks: 4 x 4 ring mbarriers + 4 counters
   static constexpr int oA = oBar + 384;                        // NSLOT activation tiles
   static constexpr bool L4_CC = DP <= 4;                       // output layer on CUDA cores
-  static constexpr int NSLOT = DP <= 4 ? 4 : 3;                // tiles in flight per CTA (registers / smem bound)
+  static constexpr int NSLOT = (DP <= 4 || (DP == 8 && !TCG && MSGM_TC_SLOT4)) ? 4 : 3;  // tiles in flight per CTA (registers / smem bound)
   static constexpr int THREADS = 128 * NSLOT + 32;             // 4 particle warps per slot + 1 MMA issuer warp
   static constexpr int AG_BYTES = 8192;                        // per slot: split y operand, fp16 [4][16][8][8]
   static constexpr int oAg = oA + NSLOT * A_BYTES;

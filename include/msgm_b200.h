@@ -288,6 +288,17 @@ int msgm_softmax_pair(msgm_ctx* ctx, const float* S_or_P, const float* Sdot, con
                       float* out1, float* out2, int64_t nrows, int32_t T, void* stream);
 int msgm_sincos_pair(msgm_ctx* ctx, const float* val_pair, float* emb_pair, int32_t B, int32_t dim, void* stream);
 int msgm_resample2(msgm_ctx* ctx, const float* x, float* out, int64_t NC, int32_t H, int32_t W, int32_t mode, void* stream);
+/* msgm_conv_wgrad on tcgen05 (csrc/conv_wgrad_tc.cu): the weight gradient as a product over positions with both operands read
+ * MN-major from the forward conv's staged tile layout, split fp16 x 3 (fp32-level parity), cotangent range-scaled by the power of
+ * two derived from amax (device word written by msgm_amax; NULL = no scaling).  Takes stride-1 convolutions with "same" padding:
+ * 3x3 (KH = KW = 3, pad 1), 1-D k3 (KH = 1, KW = 3, pad 1) and 1x1, channel counts % 16 == 0 (C1 % 16 == 0), up in {1, 2};
+ * msgm_conv_wgrad_tc_ok tells (1 / 0) whether a shape is taken; otherwise the call returns MSGM_ERR_UNSUPPORTED and the caller
+ * uses msgm_conv_wgrad.  (Hs, Ws) is the stored input size; cot is (N, Cout, Hs up, Ws up). */
+int msgm_conv_wgrad_tc_ok(int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
+                          int32_t up, int32_t Hs, int32_t Ws);
+int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate,
+                       const float* amax_or_null, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
+                       int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, void* stream);
 int msgm_pair_act(msgm_ctx* ctx, const float* z, const float* grad_h_or_null, float* out, int64_t half_elems, int32_t act,
                   void* stream);
 int msgm_amax(msgm_ctx* ctx, const float* x, int64_t n, float* amax_out, void* stream);

@@ -1,0 +1,342 @@
+// Weight gradient of the U-Net convolutions on tcgen05 (training path of NNUnet1D.py:110-179 / model/unet.py:101-250 under
+// PluginReverseSDE.ssm_loss, SDEs.py:616-646):
+//     gW[co][ci][ky][kx] = sum_{n,y,x} cot[n][co][y][x] in[n][ci][y + ky - 1][x + kx - 1]          (stride 1, "same" padding)
+// is a product over POSITIONS: D[co, (tap, ci)] = Cot^T In_tap with K = all positions of all 2B samples of the primal /
+// tangent pair.  Both tensors are NCHW, i.e. the contraction index is the contiguous one, and the staged tile layout of the
+// forward conv (conv2d_tc.cu: planes [8-channel chunk][position][8 channels], fp16 hi + lo) read MN-MAJOR is exactly that
+// product's operand layout (validated for ssm_tc.cu by tools/mn_probe.cu: LBO = 128 B between 8-position groups, SBO = plane
+// chunk stride between 8-channel groups).  As in the forward conv, all images live in one zero-padded LINEAR position space
+// p = (n Hp + r) Wp + c, so a tap is a shift of the input operand's start address by whole 16-byte rows and no im2col exists.
+//
+//   * CTA = 128 output channels (M, zero-padded) x NCI input channels (N) x the NTG taps of one kernel row (3x3: grid.y also
+//     enumerates the kernel rows, whose shift (ky - 1) Wp is folded into the staged input window, so its halo is one position)
+//     x a contiguous slice of the positions; accumulators NTG x NCI fp32 TMEM columns;
+//   * position chunks of 64 (4 K = 16 slices), double-buffered: 8 stager warps read cot and the input window from global
+//     memory (lanes = consecutive positions: coalesced), scale the cotangent by a power of two into the fp16 range (deep-layer
+//     cotangents are ~1e-7: the fp16 x 3 split would lose its low part in the subnormals), split to fp16 hi + lo and write the
+//     planes; a ninth warp issues 4 x NTG x 3 tcgen05.mma (hi hi + lo hi + hi lo: fp32-level parity) and commits;
+//   * epilogue: tcgen05.ld, unscale, red.global.add into gW (the position slices and the primal / tangent halves sum there).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "msgm_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace msgm {
+
+constexpr int WG_KT = 64;          // positions per staged chunk
+constexpr int WG_STAGERS = 256;
+constexpr uint32_t WG_IDESC_MN = (1u << 15) | (1u << 16);  // both operands MN-major ("transposed")
+
+struct WgradTcParams {
+  const float* cot;  // (N, Cout, H, W)
+  const float* x1;   // (N, C1, Hs, Ws)
+  const float* x2;   // (N, C2, Hs, Ws) or NULL: channel concat
+  float* gW;         // (Cout, Cw, KH, KW), accumulated; input channels [coff, coff + C1 + C2)
+  const unsigned int* amax_bits;  // max |cot| as float bits (msgm_amax) or NULL: no range scaling
+  int C1, C2, Cout, Cw, coff, KH, KW;
+  int N, H, W, Hs, Ws, upsh;  // the conv sees (H, W) = (Hs << upsh, Ws << upsh)
+  int Hp, Wp, padh, padw;
+  long long total;            // N Hp Wp padded positions
+  int nchunks, chunks_per_cta;
+  int NCI, NG;                // input-channel tile width; kernel rows enumerated by grid.y (3 for 3x3, else 1)
+  uint32_t mul_img, shr_img, mul_row, shr_row;
+  int tmem_cols;
+  TcFlags flags;
+};
+
+__device__ __forceinline__ int wg_div(int n, uint32_t mul, uint32_t shr) { return mul ? (int)(__umulhi((uint32_t)n, mul) >> shr) : n; }
+
+__device__ __forceinline__ float wg_pow2(const unsigned int* amax_bits, int target_exp) {
+  if (!amax_bits) return 1.0f;
+  const float m = __uint_as_float(*amax_bits);
+  if (!(m > 0.0f)) return 1.0f;
+  int e;
+  frexpf(m, &e);
+  return ldexpf(1.0f, max(-120, min(120, target_exp - e)));
+}
+
+template <int NTG, bool CONST_BASE>
+__global__ void __launch_bounds__(WG_STAGERS + 32, 1) conv_wgrad_tc_kernel(const __grid_constant__ WgradTcParams P) {
+  constexpr int KT = WG_KT, SLI = KT + (NTG == 3 ? 2 : 0);
+  constexpr int APLANE = 16 * KT * 16;  // 128 channels x KT positions, fp16
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem);  // [2]
+  uint64_t* bar_empty = bar_full + 2;                      // [2]
+  uint64_t* bar_done = bar_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 5);
+  const int BPLANE = (P.NCI / 8) * SLI * 16;
+  const int ASTAGE = 2 * APLANE, BSTAGE = 2 * BPLANE;
+  unsigned char* sA = smem + 128;
+  unsigned char* sB = sA + 2 * ASTAGE;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int g = blockIdx.y % P.NG, cit = blockIdx.y / P.NG;
+  const int co0 = blockIdx.z * 128, ci0 = cit * P.NCI;
+  const int Cin = P.C1 + P.C2;
+  const int first_chunk = blockIdx.x * P.chunks_per_cta;
+  const int my_chunks = min(P.chunks_per_cta, P.nchunks - first_chunk);
+  const int HpWp = P.Hp * P.Wp;
+
+  if (tid == WG_STAGERS) {
+    mbar_init(bar_full + 0, WG_STAGERS);
+    mbar_init(bar_full + 1, WG_STAGERS);
+    mbar_init(bar_empty + 0, 1);
+    mbar_init(bar_empty + 1, 1);
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_STAGERS / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // channel chunks the stagers never write (Cout < 128, input channels past Cin) must read as zeros
+  const int nch_a = min(16, (P.Cout - co0 + 7) / 8);
+  const int nch_b = min(P.NCI / 8, max(0, (Cin - ci0) / 8));
+  if (nch_a < 16 || nch_b < P.NCI / 8) {
+    uint4* z = reinterpret_cast<uint4*>(sA);
+    const int n16 = (2 * ASTAGE + 2 * BSTAGE) / 16;
+    for (int e = tid; e < n16; e += WG_STAGERS + 32) z[e] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == WG_STAGERS / 32) {
+    // ================================================ MMA issuer ==================================================
+    const uint32_t idesc = umma_idesc_f16(128, P.NCI) | WG_IDESC_MN;
+    const uint32_t sbase = CONST_BASE ? 1024u : smem_u32(smem);
+    if (sbase != smem_u32(smem)) {
+      if (lane == 0) tc_raise(P.flags, 2);
+    } else {
+      const uint32_t a_base0 = sbase + 128u, b_base0 = a_base0 + 2u * (uint32_t)ASTAGE;
+      for (int k = 0; k < my_chunks; ++k) {
+        const int buf = k & 1;
+        if (!__all_sync(0xffffffffu, mbar_wait(bar_full + buf, (uint32_t)((k >> 1) & 1), P.flags))) break;
+        tc_fence_after();
+        const uint32_t a_base = a_base0 + (uint32_t)(buf * ASTAGE), b_base = b_base0 + (uint32_t)(buf * BSTAGE);
+#pragma unroll
+        for (int s = 0; s < KT / 16; ++s) {
+          // MN-major descriptors: 8-position groups 128 B apart (LBO), 8-channel groups one plane chunk apart (SBO)
+          const uint64_t dAh = umma_desc(a_base + (uint32_t)(s * 256), 128, KT * 16);
+          const uint64_t dAl = umma_desc(a_base + (uint32_t)(APLANE + s * 256), 128, KT * 16);
+#pragma unroll
+          for (int t = 0; t < NTG; ++t) {
+            const uint32_t b_hi = b_base + (uint32_t)((t + 16 * s) * 16);
+            const uint64_t dBh = umma_desc(b_hi, 128, SLI * 16), dBl = umma_desc(b_hi + (uint32_t)BPLANE, 128, SLI * 16);
+            const uint32_t dcol = tbase + (uint32_t)(t * P.NCI);
+            umma_ss(dcol, dAh, dBh, idesc, (k > 0 || s > 0) ? 1u : 0u, 0);
+            umma_ss(dcol, dAl, dBh, idesc, 1u, 0);
+            umma_ss(dcol, dAh, dBl, idesc, 1u, 0);
+          }
+        }
+        umma_commit(bar_empty + buf, 0);
+      }
+    }
+    umma_commit(bar_done, 0);
+    __syncwarp();
+  } else {
+    // ================================================== stagers ===================================================
+    bool ok = true;
+    const float scale = wg_pow2(P.amax_bits, 12);
+    const long long HWo = (long long)P.H * P.W, HWs = (long long)P.Hs * P.Ws;
+    // the input window of this CTA's kernel row starts (ky - 1) Wp - 1 positions before the cotangent chunk
+    const int shift = (P.NG == 3 ? (g - 1) * P.Wp : 0) - (NTG == 3 ? 1 : 0);
+    for (int k = 0; k < my_chunks && ok; ++k) {
+      const int buf = k & 1;
+      if (k >= 2) {
+        ok = mbar_wait(bar_empty + buf, (uint32_t)(((k >> 1) - 1) & 1), P.flags);
+        tc_fence_after();
+      }
+      const long long pbase = (long long)(first_chunk + k) * KT;
+      unsigned char* adst = sA + buf * ASTAGE;
+      unsigned char* bdst = sB + buf * BSTAGE;
+      // ---- cotangent: nch_a channel chunks x KT positions ----
+      for (int e = tid; e < nch_a * KT; e += WG_STAGERS) {
+        const int row = e & (KT - 1), c = e / KT;
+        const long long q = pbase + row;
+        uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
+        if (q < P.total) {
+          const int qi = (int)q, n = wg_div(qi, P.mul_img, P.shr_img), rem = qi - n * HpWp;
+          const int rr = wg_div(rem, P.mul_row, P.shr_row), y = rr - P.padh, x = rem - rr * P.Wp - P.padw;
+          if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
+            const int ch = co0 + 8 * c;
+            const float* src = P.cot + ((long long)n * P.Cout + ch) * HWo + (long long)y * P.W + x;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (ch + j < P.Cout) ? __ldg(src + j * HWo) * scale : 0.0f;
+            split2_f16(v[0], v[1], hi4.x, lo4.x);
+            split2_f16(v[2], v[3], hi4.y, lo4.y);
+            split2_f16(v[4], v[5], hi4.z, lo4.z);
+            split2_f16(v[6], v[7], hi4.w, lo4.w);
+          }
+        }
+        *reinterpret_cast<uint4*>(adst + (c * KT + row) * 16) = hi4;
+        *reinterpret_cast<uint4*>(adst + APLANE + (c * KT + row) * 16) = lo4;
+      }
+      // ---- input window: nch_b channel chunks x SLI positions ----
+      for (int e = tid; e < nch_b * SLI; e += WG_STAGERS) {
+        const int c = e / SLI, row = e - c * SLI;
+        const long long q = pbase + shift + row;
+        uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
+        if (q >= 0 && q < P.total) {
+          const int qi = (int)q, n = wg_div(qi, P.mul_img, P.shr_img), rem = qi - n * HpWp;
+          const int rr = wg_div(rem, P.mul_row, P.shr_row), y = rr - P.padh, x = rem - rr * P.Wp - P.padw;
+          if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
+            const int ch = ci0 + 8 * c;  // C1 % 8 == 0: a chunk never straddles the concat
+            const long long off = (long long)(y >> P.upsh) * P.Ws + (x >> P.upsh);
+            const float* src = ch < P.C1 ? P.x1 + ((long long)n * P.C1 + ch) * HWs + off
+                                         : P.x2 + ((long long)n * P.C2 + ch - P.C1) * HWs + off;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j * HWs);
+            split2_f16(v[0], v[1], hi4.x, lo4.x);
+            split2_f16(v[2], v[3], hi4.y, lo4.y);
+            split2_f16(v[4], v[5], hi4.z, lo4.z);
+            split2_f16(v[6], v[7], hi4.w, lo4.w);
+          }
+        }
+        *reinterpret_cast<uint4*>(bdst + (c * SLI + row) * 16) = hi4;
+        *reinterpret_cast<uint4*>(bdst + BPLANE + (c * SLI + row) * 16) = lo4;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_full + buf);
+    }
+
+    // ================================================== epilogue ==================================================
+    ok = ok && mbar_wait(bar_done, 0, P.flags);
+    tc_fence_after();
+    if (warp < 4 && my_chunks > 0) {
+      const int co = co0 + warp * 32 + lane;
+      const float inv = 1.0f / scale;
+      const int ky = P.NG == 3 ? g : 0;
+#pragma unroll 1
+      for (int t = 0; t < NTG; ++t) {
+        const uint32_t taddr = tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * P.NCI);
+#pragma unroll 1
+        for (int cc = 0; cc < P.NCI; cc += 16) {
+          uint32_t rr[16];
+          TMEM_LD16(taddr + cc, rr);
+          tc_wait_ld();
+          if (ok && co < P.Cout) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ci = ci0 + cc + j;
+              if (ci < Cin)
+                atomicAdd(P.gW + (((size_t)co * P.Cw + P.coff + ci) * P.KH + ky) * P.KW + t, __uint_as_float(rr[j]) * inv);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WG_STAGERS / 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(P.tmem_cols));
+}
+
+static void wg_find_divisor(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  if (d <= 1) { *mul = 0; *shr = 0; return; }
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  const uint32_t p = 31 + l;
+  *mul = (uint32_t)(((1ull << p) + d - 1) / d);
+  *shr = p - 32;
+}
+
+// 1 when conv_wgrad_tc takes this convolution (the caller falls back to the CUDA-core kernel otherwise)
+int conv_wgrad_tc_supported(int Cout, int C1, int C2, int KH, int KW, int stride, int pad, int up, long long padded_positions) {
+  const int Cin = C1 + C2;
+  const bool shape = (KH == 3 && KW == 3 && pad == 1) || (KH == 1 && KW == 3 && pad == 1) || (KH == 1 && KW == 1 && pad == 0);
+  return shape && stride == 1 && (up == 1 || up == 2) && Cin % 16 == 0 && C1 % 16 == 0 && Cout >= 1 &&
+         padded_positions < (1LL << 31) - 4096;
+}
+
+int conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* x1, const float* x2, float* gW, const unsigned int* amax_bits,
+                  int N, int Cout, int C1, int C2, int Cw, int coff, int KH, int KW, int up, int Hs, int Ws, cudaStream_t stream) {
+  WgradTcParams P{};
+  P.cot = cot; P.x1 = x1; P.x2 = x2; P.gW = gW; P.amax_bits = amax_bits;
+  P.C1 = C1; P.C2 = x2 ? C2 : 0; P.Cout = Cout; P.Cw = Cw; P.coff = coff; P.KH = KH; P.KW = KW;
+  P.N = N; P.Hs = Hs; P.Ws = Ws; P.upsh = up == 2 ? 1 : 0; P.H = Hs * up; P.W = Ws * up;
+  P.padh = KH == 3 ? 1 : 0; P.padw = KW == 3 ? 1 : 0;
+  P.Hp = P.H + 2 * P.padh; P.Wp = P.W + 2 * P.padw;
+  P.total = (long long)N * P.Hp * P.Wp;
+  wg_find_divisor((uint32_t)(P.Hp * P.Wp), &P.mul_img, &P.shr_img);
+  wg_find_divisor((uint32_t)P.Wp, &P.mul_row, &P.shr_row);
+  const int Cin = P.C1 + P.C2, ntg = KW == 3 ? 3 : 1;
+  P.NG = KH == 3 ? 3 : 1;
+  // input-channel tile: as wide as the TMEM columns (ntg x NCI <= 512) and the channel count allow, a multiple of 16
+  int nci = std::min(128, Cin);
+  if (Cin > 128) {  // balance the tiles: 192 -> 2 x 96, 256 -> 2 x 128, 384 -> 3 x 128
+    const int tiles = (Cin + 127) / 128;
+    nci = ((Cin + tiles - 1) / tiles + 15) / 16 * 16;
+  }
+  P.NCI = nci;
+  const int ci_tiles = (Cin + nci - 1) / nci, co_tiles = (Cout + 127) / 128;
+  int cols = 32;
+  while (cols < ntg * nci) cols <<= 1;
+  P.tmem_cols = cols;
+  P.nchunks = (int)((P.total + WG_KT - 1) / WG_KT);
+  // position slices: about one CTA per SM over the whole grid, at least 8 chunks each (the flush of a CTA's accumulators is
+  // up to 128 x 384 atomics: it has to be amortised over enough positions)
+  const int other = P.NG * ci_tiles * co_tiles;
+  int slices = std::max(1, std::min(P.nchunks / 8 + 1, (ctx->num_sms + other - 1) / other));
+  P.chunks_per_cta = (P.nchunks + slices - 1) / slices;
+  slices = (P.nchunks + P.chunks_per_cta - 1) / P.chunks_per_cta;
+  P.flags = next_tc_flags(ctx);
+  const int sli = WG_KT + (ntg == 3 ? 2 : 0);
+  const size_t smem = 128 + 128 + 2 * (size_t)(2 * 16 * WG_KT * 16) + 2 * (size_t)(2 * (nci / 8) * sli * 16);
+  uint32_t sb = 0;
+  int rc = dyn_smem_base(ctx, stream, &sb);
+  if (rc) return rc;
+  const dim3 grid((unsigned)slices, (unsigned)(P.NG * ci_tiles), (unsigned)co_tiles);
+#define MSGM_WG_LAUNCH(NTG_)                                                                                               \
+  {                                                                                                                        \
+    auto kern = sb == 1024u ? conv_wgrad_tc_kernel<NTG_, true> : conv_wgrad_tc_kernel<NTG_, false>;                        \
+    MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+    kern<<<grid, WG_STAGERS + 32, smem, stream>>>(P);                                                                      \
+  }
+  if (ntg == 3) MSGM_WG_LAUNCH(3) else MSGM_WG_LAUNCH(1)
+#undef MSGM_WG_LAUNCH
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+}  // namespace msgm
+
+using namespace msgm;
+
+extern "C" {
+
+int msgm_conv_wgrad_tc_ok(int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
+                          int32_t up, int32_t Hs, int32_t Ws) {
+  const long long padded = (long long)N * (Hs * up + (KH == 3 ? 2 : 0)) * (Ws * up + (KW == 3 ? 2 : 0));
+  return conv_wgrad_tc_supported(Cout, C1, C2, KH, KW, stride, pad, up, padded);
+}
+
+int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate,
+                       const float* amax_or_null, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
+                       int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, void* stream) {
+  if (!ctx || !cot || !in1 || !gW_accumulate || N < 1 || Cout < 1 || C1 < 1 || C2 < 0 || (C2 > 0 && !in2) || coff < 0 ||
+      coff + C1 + C2 > Cw || Hs < 1 || Ws < 1) {
+    set_error("msgm_conv_wgrad_tc: bad argument");
+    return MSGM_ERR_INVALID;
+  }
+  if (!msgm_conv_wgrad_tc_ok(N, Cout, C1, C2, KH, KW, stride, pad, up, Hs, Ws)) {
+    set_error("msgm_conv_wgrad_tc: shape not taken by the tensor-core kernel (stride 1, 3x3 / 1x3 / 1x1, channels % 16)");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv_wgrad_tc(ctx, cot, in1, in2, gW_accumulate, reinterpret_cast<const unsigned int*>(amax_or_null), N, Cout, C1, C2, Cw,
+                       coff, KH, KW, up, Hs, Ws, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -111,12 +111,20 @@ def channel_sums(x, nrows):
     return out
 
 
-def ranged(conv, g):
-    """``conv(g)`` with g brought to max|g| = 2^12 first and the result scaled back (powers of two: exact).  The tensor-core
-    convs split operands into fp16 hi + lo; cotangents of the deep layers (~1e-7) would fall into the fp16 subnormal range."""
+def amax_of(g):
+    """Device word holding max|g| (float bits): the range scaling of the tensor-core data / weight gradient kernels."""
     h, L, st = _h(g.device)
     amax = torch.empty(1, device=g.device, dtype=torch.float32)
     _lib.check(L.msgm_amax(h, _lib.ptr(g), g.numel(), _lib.ptr(amax), st))
+    return amax
+
+
+def ranged(conv, g, amax=None):
+    """``conv(g)`` with g brought to max|g| = 2^12 first and the result scaled back (powers of two: exact).  The tensor-core
+    convs split operands into fp16 hi + lo; cotangents of the deep layers (~1e-7) would fall into the fp16 subnormal range."""
+    h, L, st = _h(g.device)
+    if amax is None:
+        amax = amax_of(g)
     gs = torch.empty_like(g)
     _lib.check(L.msgm_pow2_scale(h, _lib.ptr(g), _lib.ptr(gs), g.numel(), _lib.ptr(amax), 12, 0, st))
     out = conv(gs)
@@ -124,9 +132,19 @@ def ranged(conv, g):
     return out
 
 
-def conv_wgrad(cot, in1, in2, gW, coff, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo):
+WGRAD_TC = True  # weight gradients on tcgen05 (csrc/conv_wgrad_tc.cu) where the shape allows; False: fp32 CUDA-core kernel
+
+
+def conv_wgrad(cot, in1, in2, gW, coff, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, amax=None):
     h, L, st = _h(cot.device)
     C2 = 0 if in2 is None else in2.shape[1]
+    if WGRAD_TC and L.msgm_conv_wgrad_tc_ok(cot.shape[0], cot.shape[1], in1.shape[1], C2, KH, KW, stride, pad, up, Hi, Wi):
+        if amax is None:
+            amax = amax_of(cot)
+        _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), _lib.ptr(amax),
+                                        cot.shape[0], cot.shape[1], in1.shape[1], C2, gW.shape[1], coff, KH, KW, stride, pad, up,
+                                        Hi, Wi, st))
+        return
     _lib.check(L.msgm_conv_wgrad(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), cot.shape[0], cot.shape[1],
                                  in1.shape[1], C2, gW.shape[1], coff, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, st))
 
@@ -215,19 +233,20 @@ class Conv1dPair(torch.autograd.Function):
         Cin = C1 + C2
         Cout, Cw, K = W.shape
         gx1 = gx2 = gemb = None
+        amax = amax_of(g)
         if ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1]):
             if stride == 1:   # data gradient = the same conv with flipped taps and swapped channel roles
                 Wd = W[:, :Cin, :].flip(-1).transpose(0, 1).contiguous()
-                gx = ranged(lambda t_: conv1d_raw(t_, None, Wd, None, 1, K - 1 - pad), g)
+                gx = ranged(lambda t_: conv1d_raw(t_, None, Wd, None, 1, K - 1 - pad), g, amax)
             else:             # k4 s2 p1: data gradient = ConvTranspose1d(k4, s2, p1) with the weight read as (in = Cout, out = Cin)
                 if Lin != 2 * Lout:
                     raise NotImplementedError("hand-written U-Net training: odd signal length at a stride-2 conv")
                 Wt = W[:, :Cin, :].contiguous()
-                gx = ranged(lambda t_: convt1d_raw(t_, Wt, Lin), g)
+                gx = ranged(lambda t_: convt1d_raw(t_, Wt, Lin), g, amax)
             gx1 = gx[:, :C1]
             gx2 = gx[:, C1:] if x2 is not None else None
         gW = torch.zeros_like(W)
-        conv_wgrad(g, x1, x2, gW, 0, 1, K, stride, pad, 1, 1, Lin, 1, Lout)
+        conv_wgrad(g, x1, x2, gW, 0, 1, K, stride, pad, 1, 1, Lin, 1, Lout, amax)
         if emb is not None:
             Cemb = Cw - Cin
             Eb = torch.empty((N, Cout, K), device=dev, dtype=torch.float32)  # cotangent of the folded table
@@ -446,14 +465,15 @@ class Conv2dPair(torch.autograd.Function):
         Cout, K = W.shape[0], W.shape[-1]
         Ho, Wo = g.shape[-2:]
         gx = None
+        amax = amax_of(g)
         if ctx.needs_input_grad[0]:
             Wd = W.flip(2, 3).transpose(0, 1).contiguous()  # data gradient: the same conv, flipped taps, swapped channel roles
             src = resample2(g, 0) if stride == 2 else g     # stride 2: cotangent back on the input grid (zeros in between)
-            gx = ranged(lambda t_: conv2d_raw(t_, Wd, None, 1, 1), src)
+            gx = ranged(lambda t_: conv2d_raw(t_, Wd, None, 1, 1), src, amax)
             if up == 2:                                      # adjoint of the nearest-neighbour upsampling
                 gx = resample2(gx, 1)
         gW = torch.zeros_like(W)
-        conv_wgrad(g, x, None, gW, 0, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo)
+        conv_wgrad(g, x, None, gW, 0, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo, amax)
         gb = channel_sums(g, N // 2) if has_b else None
         ge = sample_channel_sums(g) if has_e else None
         return gx, gW, gb, ge, None, None

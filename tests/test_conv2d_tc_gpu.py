@@ -265,3 +265,51 @@ def test_tensor_core_kernels_write_inside_their_outputs():
     _lib.check(L.msgm_attention_tc(h, _lib.ptr(qkv), _lib.ptr(out), 3, 64, 64, _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     assert intact(buf, out.numel()) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("N,Cout,C1,C2,KH,KW,up,Hs,Ws,cscale", [
+    (6, 32, 32, 0, 3, 3, 1, 12, 12, 1.0),        # the 32-channel full-resolution layers (M padded from 32 to 128 channels)
+    (4, 64, 64, 32, 3, 3, 1, 8, 8, 1e-7),        # decoder concat; cotangents far below the fp16 range (range scaling)
+    (3, 128, 256, 0, 3, 3, 1, 8, 8, 3e-5),       # two input-channel tiles of 128
+    (5, 64, 64, 0, 3, 3, 2, 7, 5, 1.0),          # Upsample conv: the input is read through the nearest x2 index
+    (4, 192, 64, 0, 1, 1, 1, 16, 16, 1e-3),      # qkv 1x1 conv, two output-channel tiles
+    (3, 128, 128, 64, 1, 1, 1, 9, 9, 1.0),       # skip_connection 1x1 on a concat: 192 input channels -> 2 tiles of 96
+    (7, 64, 32, 32, 1, 3, 1, 1, 125, 1.0),       # 1-D k3 conv on a concat
+    (2, 1, 32, 0, 1, 1, 1, 1, 1000, 1e-6),       # 1-D final pointwise conv: one output channel
+    (64, 32, 32, 0, 3, 3, 1, 32, 32, 1.0),       # full config-4 size of one layer: 74 k padded positions, many slices
+])
+def test_conv_wgrad_tc_matches_float64(N, Cout, C1, C2, KH, KW, up, Hs, Ws, cscale):
+    """csrc/conv_wgrad_tc.cu: the conv weight gradient as a tcgen05 product over positions (both operands MN-major from the
+    staged tile layout, split fp16 x 3, power-of-two range scaling of the cotangent) against torch's float64 weight gradient;
+    the result is accumulated into gW at a channel offset, and entries outside the written block must stay untouched."""
+    torch.manual_seed(N * 1000 + Cout + C1 + KH)
+    dev = torch.device(DEV)
+    h, L = _lib.ctx(dev), _lib.lib()
+    Cin, pad = C1 + C2, KW // 2
+    assert L.msgm_conv_wgrad_tc_ok(N, Cout, C1, C2, KH, KW, 1, pad, up, Hs, Ws) == 1
+    x1 = torch.randn(N, C1, Hs, Ws)
+    x2 = torch.randn(N, C2, Hs, Ws) if C2 else None
+    cot = torch.randn(N, Cout, Hs * up, Ws * up) * cscale
+    xin = x1 if x2 is None else torch.cat([x1, x2], 1)
+    if up == 2:
+        xin = F.interpolate(xin, scale_factor=2, mode="nearest")
+    Wd = torch.zeros(Cout, Cin, KH, KW, dtype=torch.float64, requires_grad=True)
+    out = F.conv2d(xin.double(), Wd, padding=(KH // 2, KW // 2))
+    (out * cot.double()).sum().backward()
+    ref = Wd.grad
+    coff, Cw = 3, Cin + 5                       # written block inside a wider weight tensor (the 1-D U-Net's folded channels)
+    g0 = torch.randn(Cout, Cw, KH, KW) * float(ref.abs().max())  # what is already in the gradient buffer
+    gW = g0.clone().to(dev)
+    cd, x1d = cot.to(dev), x1.to(dev)
+    x2d = None if x2 is None else x2.to(dev)
+    amax = torch.empty(1, device=dev, dtype=torch.float32)
+    _lib.check(L.msgm_amax(h, _lib.ptr(cd), cd.numel(), _lib.ptr(amax), _lib.stream_ptr(dev)))
+    _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cd), _lib.ptr(x1d), _lib.ptr(x2d), _lib.ptr(gW), _lib.ptr(amax), N, Cout, C1, C2,
+                                    Cw, coff, KH, KW, 1, pad, up, Hs, Ws, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    _lib.check_async(dev)
+    got = gW.cpu()
+    err = float((got[:, coff:coff + Cin].double() - g0[:, coff:coff + Cin].double() - ref).abs().max() / ref.abs().max())
+    untouched = torch.equal(got[:, :coff], g0[:, :coff]) and torch.equal(got[:, coff + Cin:], g0[:, coff + Cin:])
+    assert untouched
+    assert err < 2e-5, err

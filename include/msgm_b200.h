@@ -279,6 +279,25 @@ int msgm_adam_step(msgm_ctx* ctx, const void* seg_table, int32_t n_tensors, int6
  *   msgm_sincos_pair    timestep_embedding (model/nn_utils.py:130-148) of a pair of scalars (value; tangent) -> (2B, dim).
  *   msgm_resample2      mode 0: zero-stuffing to twice the size (adjoint of a stride-2 conv's sub-sampling); mode 1: 2x2 block
  *                       sums (adjoint of the nearest-neighbour upsampling of Upsample, model/unet.py:40-60). */
+/* A group of small batched products of ONE shape in one launch: problem i computes, for every matrix b < batch,
+ *   C_i[b] = [C_i[b] +] alpha_i * sum_{s < nseg_i} op(A_i,s[b]) op(B_i,s[b])      (M x N, contraction length K)
+ * -- the attention of the U-Net training path (QKVAttention on primal / tangent pairs, model/unet.py:236-250, and its adjoint)
+ * is four such groups instead of 21 separate launches.  Problems of a group must not write overlapping outputs. */
+#define MSGM_GEMM_MAX_PROBLEMS 6
+typedef struct msgm_gemm_problem {
+  const float* A[2];
+  const float* B[2];
+  float* C;
+  int64_t stride_a[2], stride_b[2], stride_c;  /* element strides between the matrices of the batch */
+  int32_t lda[2], ldb[2], ldc;
+  int32_t trans_a[2], trans_b[2];              /* 1: stored transposed (A as K x M, B as N x K) */
+  int32_t nseg;                                /* 1 or 2 products summed */
+  int32_t accumulate;                          /* 1: add to C */
+  float alpha;
+  int32_t reserved;
+} msgm_gemm_problem;
+int msgm_gemm_group_f32(msgm_ctx* ctx, const msgm_gemm_problem* problems, int32_t n_problems, int32_t M, int32_t N, int32_t K,
+                        int32_t batch, void* stream);
 int msgm_bgemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t lda,
                    int32_t ldb, int32_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c, int32_t batch, int32_t trans_a,
                    int32_t trans_b, float alpha, int32_t accumulate, void* stream);

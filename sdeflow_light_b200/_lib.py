@@ -44,6 +44,13 @@ class StepClock(C.Structure):
                 ("keep_step", C.c_void_p), ("keep_out", C.c_void_p), ("include_t0", C.c_int32), ("reserved", C.c_int32)]
 
 
+class GemmProblem(C.Structure):
+    _fields_ = [("A", C.c_void_p * 2), ("B", C.c_void_p * 2), ("C", C.c_void_p), ("stride_a", C.c_int64 * 2),
+                ("stride_b", C.c_int64 * 2), ("stride_c", C.c_int64), ("lda", C.c_int32 * 2), ("ldb", C.c_int32 * 2),
+                ("ldc", C.c_int32), ("trans_a", C.c_int32 * 2), ("trans_b", C.c_int32 * 2), ("nseg", C.c_int32),
+                ("accumulate", C.c_int32), ("alpha", C.c_float), ("reserved", C.c_int32)]
+
+
 class Conv1dDesc(C.Structure):
     _fields_ = [("x1", C.c_void_p), ("x2", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("E", C.c_void_p),
                 ("out", C.c_void_p)] + [(n, C.c_int32) for n in ("B", "C1", "C2", "Cemb", "Cout", "K", "stride", "pad",
@@ -72,7 +79,7 @@ _ctx = {}
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count", "msgm_async_error", "msgm_row_norm_stats", "msgm_survival_counts", "msgm_moments", "msgm_adam_step", "msgm_p2p_create", "msgm_p2p_connect", "msgm_p2p_disconnect", "msgm_p2p_destroy",
            "msgm_p2p_allreduce_adam", "msgm_pair_act", "msgm_amax", "msgm_pow2_scale", "msgm_rows_bias_add", "msgm_channel_sums", "msgm_tap_sums_1d",
-           "msgm_conv_wgrad", "msgm_conv_wgrad_tc_ok", "msgm_conv_wgrad_tc", "msgm_gemm_f32", "msgm_premodule_pair", "msgm_sparse_ssm_loss", "msgm_bgemm_f32", "msgm_gn_pair", "msgm_softmax_pair",
+           "msgm_conv_wgrad", "msgm_conv_wgrad_tc_ok", "msgm_conv_wgrad_tc", "msgm_gemm_f32", "msgm_premodule_pair", "msgm_sparse_ssm_loss", "msgm_bgemm_f32", "msgm_gemm_group_f32", "msgm_gn_pair", "msgm_softmax_pair",
            "msgm_sincos_pair", "msgm_resample2",
            "msgm_sample_mlp", "msgm_noise_forward", "msgm_ssm_prepare", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
            "msgm_ssm_scratch_bytes", "msgm_ssm_mlp_forward", "msgm_ssm_mlp_backward", "msgm_ssm_tc_scratch_bytes",
@@ -188,6 +195,7 @@ def lib() -> C.CDLL:
                 L.msgm_sparse_ssm_loss.argtypes = [C.c_void_p, C.POINTER(SdeDesc)] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
                 L.msgm_bgemm_f32.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 6 + [C.c_int64] * 3 + [C.c_int32] * 3 + \
                     [C.c_float, C.c_int32, C.c_void_p]
+                L.msgm_gemm_group_f32.argtypes = [C.c_void_p, C.POINTER(GemmProblem)] + [C.c_int32] * 5 + [C.c_void_p]
                 L.msgm_gn_pair.argtypes = [C.c_void_p] * 9 + [C.c_int32] * 4 + [C.c_void_p]
                 L.msgm_softmax_pair.argtypes = [C.c_void_p] * 7 + [C.c_int64, C.c_int32, C.c_void_p]
                 L.msgm_sincos_pair.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 2 + [C.c_void_p]

@@ -156,53 +156,89 @@ __global__ void __launch_bounds__(WG_STAGERS + 32, 1) conv_wgrad_tc_kernel(const
       const long long pbase = (long long)(first_chunk + k) * KT;
       unsigned char* adst = sA + buf * ASTAGE;
       unsigned char* bdst = sB + buf * BSTAGE;
+      // Items = (8-channel chunk, position).  A thread's items of one chunk (<= ILP) are handled together: all their global
+      // loads are issued before the first is consumed (one round trip per chunk instead of one per item).
+      constexpr int ILP = 5;  // 16 x 66 items / 256 threads
       // ---- cotangent: nch_a channel chunks x KT positions ----
-      for (int e = tid; e < nch_a * KT; e += WG_STAGERS) {
-        const int row = e & (KT - 1), c = e / KT;
-        const long long q = pbase + row;
-        uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
-        if (q < P.total) {
-          const int qi = (int)q, n = wg_div(qi, P.mul_img, P.shr_img), rem = qi - n * HpWp;
-          const int rr = wg_div(rem, P.mul_row, P.shr_row), y = rr - P.padh, x = rem - rr * P.Wp - P.padw;
-          if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
-            const int ch = co0 + 8 * c;
-            const float* src = P.cot + ((long long)n * P.Cout + ch) * HWo + (long long)y * P.W + x;
-            float v[8];
+      {
+        float v[ILP][8];
+        int dst[ILP];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (ch + j < P.Cout) ? __ldg(src + j * HWo) * scale : 0.0f;
-            split2_f16(v[0], v[1], hi4.x, lo4.x);
-            split2_f16(v[2], v[3], hi4.y, lo4.y);
-            split2_f16(v[4], v[5], hi4.z, lo4.z);
-            split2_f16(v[6], v[7], hi4.w, lo4.w);
+        for (int u = 0; u < ILP; ++u) {
+          const int e = tid + u * WG_STAGERS;
+          dst[u] = -1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.0f;
+          if (u * WG_STAGERS < 16 * KT && e < nch_a * KT) {
+            const int row = e & (KT - 1), c = e / KT;
+            dst[u] = (c * KT + row) * 16;
+            const long long q = pbase + row;
+            if (q < P.total) {
+              const int qi = (int)q, n = wg_div(qi, P.mul_img, P.shr_img), rem = qi - n * HpWp;
+              const int rr = wg_div(rem, P.mul_row, P.shr_row), y = rr - P.padh, x = rem - rr * P.Wp - P.padw;
+              if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
+                const int ch = co0 + 8 * c;
+                const float* src = P.cot + ((long long)n * P.Cout + ch) * HWo + (long long)y * P.W + x;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (ch + j < P.Cout) v[u][j] = __ldg(src + j * HWo);
+              }
+            }
           }
         }
-        *reinterpret_cast<uint4*>(adst + (c * KT + row) * 16) = hi4;
-        *reinterpret_cast<uint4*>(adst + APLANE + (c * KT + row) * 16) = lo4;
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+          if (dst[u] >= 0) {
+            uint4 hi4, lo4;
+            split2_f16(v[u][0] * scale, v[u][1] * scale, hi4.x, lo4.x);
+            split2_f16(v[u][2] * scale, v[u][3] * scale, hi4.y, lo4.y);
+            split2_f16(v[u][4] * scale, v[u][5] * scale, hi4.z, lo4.z);
+            split2_f16(v[u][6] * scale, v[u][7] * scale, hi4.w, lo4.w);
+            *reinterpret_cast<uint4*>(adst + dst[u]) = hi4;
+            *reinterpret_cast<uint4*>(adst + APLANE + dst[u]) = lo4;
+          }
+        }
       }
       // ---- input window: nch_b channel chunks x SLI positions ----
-      for (int e = tid; e < nch_b * SLI; e += WG_STAGERS) {
-        const int c = e / SLI, row = e - c * SLI;
-        const long long q = pbase + shift + row;
-        uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
-        if (q >= 0 && q < P.total) {
-          const int qi = (int)q, n = wg_div(qi, P.mul_img, P.shr_img), rem = qi - n * HpWp;
-          const int rr = wg_div(rem, P.mul_row, P.shr_row), y = rr - P.padh, x = rem - rr * P.Wp - P.padw;
-          if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
-            const int ch = ci0 + 8 * c;  // C1 % 8 == 0: a chunk never straddles the concat
-            const long long off = (long long)(y >> P.upsh) * P.Ws + (x >> P.upsh);
-            const float* src = ch < P.C1 ? P.x1 + ((long long)n * P.C1 + ch) * HWs + off
-                                         : P.x2 + ((long long)n * P.C2 + ch - P.C1) * HWs + off;
-            float v[8];
+      {
+        float v[ILP][8];
+        int dst[ILP];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(src + j * HWs);
-            split2_f16(v[0], v[1], hi4.x, lo4.x);
-            split2_f16(v[2], v[3], hi4.y, lo4.y);
-            split2_f16(v[4], v[5], hi4.z, lo4.z);
-            split2_f16(v[6], v[7], hi4.w, lo4.w);
+        for (int u = 0; u < ILP; ++u) {
+          const int e = tid + u * WG_STAGERS;
+          dst[u] = -1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.0f;
+          if (e < nch_b * SLI) {
+            const int c = e / SLI, row = e - c * SLI;
+            dst[u] = (c * SLI + row) * 16;
+            const long long q = pbase + shift + row;
+            if (q >= 0 && q < P.total) {
+              const int qi = (int)q, n = wg_div(qi, P.mul_img, P.shr_img), rem = qi - n * HpWp;
+              const int rr = wg_div(rem, P.mul_row, P.shr_row), y = rr - P.padh, x = rem - rr * P.Wp - P.padw;
+              if (y >= 0 && y < P.H && x >= 0 && x < P.W) {
+                const int ch = ci0 + 8 * c;  // C1 % 8 == 0: a chunk never straddles the concat
+                const long long off = (long long)(y >> P.upsh) * P.Ws + (x >> P.upsh);
+                const float* src = ch < P.C1 ? P.x1 + ((long long)n * P.C1 + ch) * HWs + off
+                                             : P.x2 + ((long long)n * P.C2 + ch - P.C1) * HWs + off;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u][j] = __ldg(src + j * HWs);
+              }
+            }
           }
         }
-        *reinterpret_cast<uint4*>(bdst + (c * SLI + row) * 16) = hi4;
-        *reinterpret_cast<uint4*>(bdst + BPLANE + (c * SLI + row) * 16) = lo4;
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+          if (dst[u] >= 0) {
+            uint4 hi4, lo4;
+            split2_f16(v[u][0], v[u][1], hi4.x, lo4.x);
+            split2_f16(v[u][2], v[u][3], hi4.y, lo4.y);
+            split2_f16(v[u][4], v[u][5], hi4.z, lo4.z);
+            split2_f16(v[u][6], v[u][7], hi4.w, lo4.w);
+            *reinterpret_cast<uint4*>(bdst + dst[u]) = hi4;
+            *reinterpret_cast<uint4*>(bdst + BPLANE + dst[u]) = lo4;
+          }
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(bar_full + buf);

@@ -269,60 +269,69 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
     }
 }
 
-// ---- small dense product: C (M x N, ldc) = [C +] alpha op(A) op(B), op = identity or transpose -----------------------------------
-// A is (M x K) [lda] or, transposed, stored (K x M); B is (K x N) [ldb] or, transposed, stored (N x K).  256 threads per
-// TM x TN tile = Tile::NT thread tiles x KG groups; group g takes every KG-th k of a staged chunk of 16 and the groups' partial
-// tiles are summed through shared memory (tree, log2 KG rounds) -- the attention products of the training path are many small
-// matrices, so the threads have to come from the K axis.  Batched over blockIdx.z.
+// ---- small dense products: C (M x N, ldc) = [C +] alpha sum_s op(A_s) op(B_s), op = identity or transpose -----------------------
+// A_s is (M x K) [lda] or, transposed, stored (K x M); B_s is (K x N) [ldb] or, transposed, stored (N x K).  One launch carries a
+// GROUP of up to MSGM_GEMM_MAX_PROBLEMS problems of one shape, each the sum of up to two products (the attention of the training
+// path is 21 small batched products per block; its forward-mode pairs are sums such as Sdot = qdot^T k + q^T kdot), each
+// batched over `batch` matrices: blockIdx.z = problem * batch + matrix.  256 threads per TM x TN tile = Tile::NT thread tiles x
+// KG groups; group g takes every KG-th k of a staged chunk of 16 and the groups' partial tiles are summed through shared memory
+// (tree, log2 KG rounds) -- these are many small matrices, so the threads have to come from the K axis.
+struct GemmGroupParams {
+  msgm_gemm_problem prob[MSGM_GEMM_MAX_PROBLEMS];
+  int nprob, M, N, K, batch;
+};
+
 template <int TM, int TN>
-__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                       float* __restrict__ Cm, int M, int N, int K, int lda, int ldb, int ldc,
-                                                       int ta, int tb, int accumulate, long long sa, long long sb, long long sc,
-                                                       float alpha) {
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const __grid_constant__ GemmGroupParams G) {
   using T = Tile<TM, TN>;
   constexpr int KT = 16, NT = T::NT, KG = 256 / NT;
   constexpr int EA = KT * TM / 256, EB = KT * TN / 256;  // staged elements per thread
   __shared__ __align__(16) float sA[KT * T::SA];
   __shared__ __align__(16) float sB[KT * T::SB];
   __shared__ float red[KG > 1 ? 64 * 128 : 1];
-  A += blockIdx.z * sa;  // batched: one product per blockIdx.z
-  B += blockIdx.z * sb;
-  Cm += blockIdx.z * sc;
+  const msgm_gemm_problem& Q = G.prob[blockIdx.z / G.batch];
+  const long long bz = blockIdx.z % G.batch;
+  const int M = G.M, N = G.N, K = G.K;
   const int tm = blockIdx.y * TM, tn = blockIdx.x * TN, tid = threadIdx.x, tt = tid % NT, kg = tid / NT;
   float acc[8][8] = {};
-  float ra[EA], rb[EB];
-  auto fetch = [&](int k0) {  // lanes run along the operand's contiguous axis
+  for (int sgm = 0; sgm < Q.nseg; ++sgm) {
+    const float* __restrict__ A = Q.A[sgm] + bz * Q.stride_a[sgm];
+    const float* __restrict__ B = Q.B[sgm] + bz * Q.stride_b[sgm];
+    const int ta = Q.trans_a[sgm], tb = Q.trans_b[sgm], lda = Q.lda[sgm], ldb = Q.ldb[sgm];
+    float ra[EA], rb[EB];
+    auto fetch = [&](int k0) {  // lanes run along the operand's contiguous axis
 #pragma unroll
-    for (int q = 0; q < EA; ++q) {
-      const int e = tid + 256 * q;
-      const int kk = ta ? e / TM : e % KT, mm = ta ? e % TM : e / KT;
-      const int k = k0 + kk, m = tm + mm;
-      ra[q] = (k < K && m < M) ? __ldg(ta ? A + (size_t)k * lda + m : A + (size_t)m * lda + k) : 0.0f;
-    }
+      for (int q = 0; q < EA; ++q) {
+        const int e = tid + 256 * q;
+        const int kk = ta ? e / TM : e % KT, mm = ta ? e % TM : e / KT;
+        const int k = k0 + kk, m = tm + mm;
+        ra[q] = (k < K && m < M) ? __ldg(ta ? A + (size_t)k * lda + m : A + (size_t)m * lda + k) : 0.0f;
+      }
 #pragma unroll
-    for (int q = 0; q < EB; ++q) {
-      const int e = tid + 256 * q;
-      const int kk = tb ? e % KT : e / TN, nn = tb ? e / KT : e % TN;
-      const int k = k0 + kk, n = tn + nn;
-      rb[q] = (k < K && n < N) ? __ldg(tb ? B + (size_t)n * ldb + k : B + (size_t)k * ldb + n) : 0.0f;
-    }
-  };
-  fetch(0);
-  for (int k0 = 0; k0 < K; k0 += KT) {
+      for (int q = 0; q < EB; ++q) {
+        const int e = tid + 256 * q;
+        const int kk = tb ? e % KT : e / TN, nn = tb ? e / KT : e % TN;
+        const int k = k0 + kk, n = tn + nn;
+        rb[q] = (k < K && n < N) ? __ldg(tb ? B + (size_t)n * ldb + k : B + (size_t)k * ldb + n) : 0.0f;
+      }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += KT) {
 #pragma unroll
-    for (int q = 0; q < EA; ++q) {
-      const int e = tid + 256 * q;
-      sA[(ta ? e / TM : e % KT) * T::SA + (ta ? e % TM : e / KT)] = ra[q];
-    }
+      for (int q = 0; q < EA; ++q) {
+        const int e = tid + 256 * q;
+        sA[(ta ? e / TM : e % KT) * T::SA + (ta ? e % TM : e / KT)] = ra[q];
+      }
 #pragma unroll
-    for (int q = 0; q < EB; ++q) {
-      const int e = tid + 256 * q;
-      sB[(tb ? e % KT : e / TN) * T::SB + (tb ? e / KT : e % TN)] = rb[q];
+      for (int q = 0; q < EB; ++q) {
+        const int e = tid + 256 * q;
+        sB[(tb ? e % KT : e / TN) * T::SB + (tb ? e / KT : e % TN)] = rb[q];
+      }
+      __syncthreads();
+      if (k0 + KT < K) fetch(k0 + KT);
+      tile_fma<TM, TN>(sA, sB, tt, kg, KT, KG, acc);
+      __syncthreads();
     }
-    __syncthreads();
-    if (k0 + KT < K) fetch(k0 + KT);
-    tile_fma<TM, TN>(sA, sB, tt, kg, KT, KG, acc);
-    __syncthreads();
   }
   if constexpr (KG > 1) {  // tree sum over the K groups: the upper half writes, the lower half adds
 #pragma unroll
@@ -346,6 +355,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     }
     if (kg != 0) return;
   }
+  float* __restrict__ Cm = Q.C + bz * Q.stride_c;
   const int rg = tt % (TM / 8), cg = tt / (TM / 8);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -353,8 +363,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     for (int j = 0; j < 8; ++j) {
       const int m = tm + tile_index<TM>(rg, i), n = tn + tile_index<TN>(cg, j);
       if (m < M && n < N) {
-        float* c = Cm + (size_t)m * ldc + n;
-        *c = accumulate ? fmaf(alpha, acc[i][j], *c) : alpha * acc[i][j];
+        float* c = Cm + (size_t)m * Q.ldc + n;
+        *c = Q.accumulate ? fmaf(Q.alpha, acc[i][j], *c) : Q.alpha * acc[i][j];
       }
     }
 }
@@ -624,21 +634,30 @@ __global__ void __launch_bounds__(256) resample2_kernel(const float* __restrict_
 }
 
 // tile choice: the largest of 128 x 128, 64 x 64, 32 x 32 that still gives every SM two CTAs (or 32 x 32)
+static void launch_gemm_group(msgm_ctx* ctx, const GemmGroupParams& G, cudaStream_t st) {
+  const int M = G.M, N = G.N;
+  const long long nz = (long long)G.nprob * G.batch;
+  auto ctas = [&](int t) { return (long long)((M + t - 1) / t) * ((N + t - 1) / t) * nz; };
+  const long long want = 2LL * ctx->num_sms;
+  if (M > 64 && N > 64 && ctas(128) >= want) {
+    gemm_f32_kernel<128, 128><<<dim3((N + 127) / 128, (M + 127) / 128, (unsigned)nz), 256, 0, st>>>(G);
+  } else if (M > 32 && N > 32 && ctas(64) >= want) {
+    gemm_f32_kernel<64, 64><<<dim3((N + 63) / 64, (M + 63) / 64, (unsigned)nz), 256, 0, st>>>(G);
+  } else {
+    gemm_f32_kernel<32, 32><<<dim3((N + 31) / 32, (M + 31) / 32, (unsigned)nz), 256, 0, st>>>(G);
+  }
+}
+
 static void launch_gemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* Cm, int M, int N, int K, int lda, int ldb, int ldc,
                             long long sa, long long sb, long long sc, int batch, int ta, int tb, float alpha, int accumulate,
                             cudaStream_t st) {
-  auto ctas = [&](int t) { return (long long)((M + t - 1) / t) * ((N + t - 1) / t) * batch; };
-  const long long want = 2LL * ctx->num_sms;
-  if (M > 64 && N > 64 && ctas(128) >= want) {
-    gemm_f32_kernel<128, 128><<<dim3((N + 127) / 128, (M + 127) / 128, batch), 256, 0, st>>>(
-        A, B, Cm, M, N, K, lda, ldb, ldc, ta, tb, accumulate, sa, sb, sc, alpha);
-  } else if (M > 32 && N > 32 && ctas(64) >= want) {
-    gemm_f32_kernel<64, 64><<<dim3((N + 63) / 64, (M + 63) / 64, batch), 256, 0, st>>>(
-        A, B, Cm, M, N, K, lda, ldb, ldc, ta, tb, accumulate, sa, sb, sc, alpha);
-  } else {
-    gemm_f32_kernel<32, 32><<<dim3((N + 31) / 32, (M + 31) / 32, batch), 256, 0, st>>>(
-        A, B, Cm, M, N, K, lda, ldb, ldc, ta, tb, accumulate, sa, sb, sc, alpha);
-  }
+  GemmGroupParams G{};
+  G.nprob = 1; G.M = M; G.N = N; G.K = K; G.batch = batch;
+  msgm_gemm_problem& Q = G.prob[0];
+  Q.A[0] = A; Q.B[0] = B; Q.C = Cm; Q.nseg = 1;
+  Q.lda[0] = lda; Q.ldb[0] = ldb; Q.ldc = ldc; Q.trans_a[0] = ta; Q.trans_b[0] = tb;
+  Q.stride_a[0] = sa; Q.stride_b[0] = sb; Q.stride_c = sc; Q.alpha = alpha; Q.accumulate = accumulate;
+  launch_gemm_group(ctx, G, st);
 }
 
 }  // namespace msgm
@@ -797,6 +816,26 @@ int msgm_bgemm_f32(msgm_ctx* ctx, const float* A, const float* B, float* Cm, int
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   launch_gemm_f32(ctx, A, B, Cm, M, N, K, lda, ldb, ldc, stride_a, stride_b, stride_c, batch, trans_a, trans_b, alpha, accumulate,
                   (cudaStream_t)stream);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_gemm_group_f32(msgm_ctx* ctx, const msgm_gemm_problem* problems, int32_t n_problems, int32_t M, int32_t N, int32_t K,
+                        int32_t batch, void* stream) {
+  if (!ctx || !problems || n_problems < 1 || n_problems > MSGM_GEMM_MAX_PROBLEMS || M < 1 || N < 1 || K < 1 || batch < 1 ||
+      (long long)n_problems * batch > 65535)
+    return ut_invalid("msgm_gemm_group_f32: bad argument");
+  GemmGroupParams G{};
+  G.nprob = n_problems; G.M = M; G.N = N; G.K = K; G.batch = batch;
+  for (int i = 0; i < n_problems; ++i) {
+    const msgm_gemm_problem& Q = problems[i];
+    if (Q.nseg < 1 || Q.nseg > 2 || !Q.C || !Q.A[0] || !Q.B[0] || (Q.nseg == 2 && (!Q.A[1] || !Q.B[1])))
+      return ut_invalid("msgm_gemm_group_f32: bad problem descriptor");
+    G.prob[i] = Q;
+  }
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  launch_gemm_group(ctx, G, (cudaStream_t)stream);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

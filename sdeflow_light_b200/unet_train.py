@@ -507,15 +507,27 @@ class GnPair(torch.autograd.Function):
         return gx, gg, gb, None
 
 
-def _bgemm(dev, A, B, Cm, M, N, K, lda, ldb, ldc, sa, sb, sc, batch, ta=False, tb=False, alpha=1.0, acc=False):
+def _prob(segs, Cptr, ldc, sc, alpha=1.0):
+    """One problem of a product group: C = alpha * sum over segs of op(A) op(B); seg = (A, B, lda, ldb, sa, sb, ta, tb)."""
+    q = _lib.GemmProblem()
+    for i, (A, B, lda, ldb, sa, sb, ta, tb) in enumerate(segs):
+        q.A[i], q.B[i] = A, B
+        q.lda[i], q.ldb[i], q.stride_a[i], q.stride_b[i], q.trans_a[i], q.trans_b[i] = lda, ldb, sa, sb, int(ta), int(tb)
+    q.C, q.ldc, q.stride_c, q.nseg, q.alpha, q.accumulate = Cptr, ldc, sc, len(segs), float(alpha), 0
+    return q
+
+
+def _gemm_group(dev, probs, M, N, K, batch):
     h, L, st = _h(dev)
-    _lib.check(L.msgm_bgemm_f32(h, A, B, Cm, M, N, K, lda, ldb, ldc, sa, sb, sc, batch, int(ta), int(tb), float(alpha), int(acc), st))
+    arr = (_lib.GemmProblem * len(probs))(*probs)
+    _lib.check(L.msgm_gemm_group_f32(h, arr, len(probs), M, N, K, batch, st))
 
 
 class AttnPair(torch.autograd.Function):
     """QKVAttention (model/unet.py:236-250, one head) on a pair qkv (2B, 3C, T): S = s^2 q^T k, P = softmax(S), O = v P^T and
-    the tangents Sdot = s^2 (qdot^T k + q^T kdot), Pdot = P (Sdot - rowsum(P Sdot)), Odot = vdot P^T + v Pdot^T, as batched
-    fp32 products (msgm_bgemm_f32) and two row kernels (msgm_softmax_pair); the backward is the hand-derived adjoint."""
+    the tangents Sdot = s^2 (qdot^T k + q^T kdot), Pdot = P (Sdot - rowsum(P Sdot)), Odot = vdot P^T + v Pdot^T; the backward is
+    the hand-derived adjoint.  The 21 small batched products run as FOUR grouped launches (msgm_gemm_group_f32: problems of one
+    shape side by side, sums of two products inside one problem) around two row kernels (msgm_softmax_pair)."""
 
     @staticmethod
     def forward(ctx, qkv):
@@ -524,27 +536,24 @@ class AttnPair(torch.autograd.Function):
         N, C3, T = qkv.shape
         B, Cc = N // 2, C3 // 3
         s2 = 1.0 / math.sqrt(Cc)  # (C^-1/4)^2
-        f = 4  # bytes
+        f, sq, TT, so = 4, C3 * T, T * T, Cc * T  # bytes per float; sample strides (floats) of qkv, of a logit matrix, of the output
         base = qkv.data_ptr()
-        sq = C3 * T  # sample stride (floats)
 
         def ptr(sample0, part):
-            return C.c_void_p(base + f * (sample0 * sq + part * Cc * T))
+            return base + f * (sample0 * sq + part * Cc * T)
 
         q, k, v, qd, kd, vd = ptr(0, 0), ptr(0, 1), ptr(0, 2), ptr(B, 0), ptr(B, 1), ptr(B, 2)
         S = torch.empty((B, T, T), device=dev, dtype=torch.float32)
         Sd = torch.empty_like(S)
-        _bgemm(dev, q, k, _lib.ptr(S), T, T, Cc, T, T, T, sq, sq, T * T, B, ta=True, alpha=s2)
-        _bgemm(dev, qd, k, _lib.ptr(Sd), T, T, Cc, T, T, T, sq, sq, T * T, B, ta=True, alpha=s2)
-        _bgemm(dev, q, kd, _lib.ptr(Sd), T, T, Cc, T, T, T, sq, sq, T * T, B, ta=True, alpha=s2, acc=True)
+        _gemm_group(dev, [_prob([(q, k, T, T, sq, sq, 1, 0)], S.data_ptr(), T, TT, s2),
+                          _prob([(qd, k, T, T, sq, sq, 1, 0), (q, kd, T, T, sq, sq, 1, 0)], Sd.data_ptr(), T, TT, s2)], T, T, Cc, B)
         Pm, Pd = torch.empty_like(S), torch.empty_like(S)
         h, L, st = _h(dev)
         _lib.check(L.msgm_softmax_pair(h, _lib.ptr(S), _lib.ptr(Sd), None, None, _lib.ptr(Pm), _lib.ptr(Pd), B * T, T, st))
         out = torch.empty((N, Cc, T), device=dev, dtype=torch.float32)
-        o, od = C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr() + f * B * Cc * T)
-        _bgemm(dev, v, _lib.ptr(Pm), o, Cc, T, T, T, T, T, sq, T * T, Cc * T, B, tb=True)
-        _bgemm(dev, vd, _lib.ptr(Pm), od, Cc, T, T, T, T, T, sq, T * T, Cc * T, B, tb=True)
-        _bgemm(dev, v, _lib.ptr(Pd), od, Cc, T, T, T, T, T, sq, T * T, Cc * T, B, tb=True, acc=True)
+        o, od, P_, Pd_ = out.data_ptr(), out.data_ptr() + f * B * so, Pm.data_ptr(), Pd.data_ptr()
+        _gemm_group(dev, [_prob([(v, P_, T, T, sq, TT, 0, 1)], o, T, so),
+                          _prob([(vd, P_, T, T, sq, TT, 0, 1), (v, Pd_, T, T, sq, TT, 0, 1)], od, T, so)], Cc, T, T, B)
         ctx.save_for_backward(qkv, Pm, Pd, Sd)
         return out
 
@@ -556,19 +565,19 @@ class AttnPair(torch.autograd.Function):
         N, C3, T = qkv.shape
         B, Cc = N // 2, C3 // 3
         s2 = 1.0 / math.sqrt(Cc)
-        f, sq, so = 4, C3 * T, Cc * T
+        f, sq, so, TT = 4, C3 * T, Cc * T, T * T
         base = qkv.data_ptr()
 
         def ptr(sample0, part):
-            return C.c_void_p(base + f * (sample0 * sq + part * Cc * T))
+            return base + f * (sample0 * sq + part * Cc * T)
 
         q, k, v, qd, kd, vd = ptr(0, 0), ptr(0, 1), ptr(0, 2), ptr(B, 0), ptr(B, 1), ptr(B, 2)
-        ob, odb = C.c_void_p(g.data_ptr()), C.c_void_p(g.data_ptr() + f * B * so)  # cotangents of O and Odot
+        ob, odb = g.data_ptr(), g.data_ptr() + f * B * so  # cotangents of O and Odot
         A = torch.empty((B, T, T), device=dev, dtype=torch.float32)
         Pdb = torch.empty_like(A)
-        _bgemm(dev, ob, v, _lib.ptr(A), T, T, Cc, T, T, T, so, sq, T * T, B, ta=True)
-        _bgemm(dev, odb, vd, _lib.ptr(A), T, T, Cc, T, T, T, so, sq, T * T, B, ta=True, acc=True)
-        _bgemm(dev, odb, v, _lib.ptr(Pdb), T, T, Cc, T, T, T, so, sq, T * T, B, ta=True)
+        # direct cotangents of P and Pdot: A = Obar^T v + Odotbar^T vdot, Pdotbar = Odotbar^T v
+        _gemm_group(dev, [_prob([(ob, v, T, T, so, sq, 1, 0), (odb, vd, T, T, so, sq, 1, 0)], A.data_ptr(), T, TT),
+                          _prob([(odb, v, T, T, so, sq, 1, 0)], Pdb.data_ptr(), T, TT)], T, T, Cc, B)
         Sb, Sdb = torch.empty_like(A), torch.empty_like(A)
         h, L, st = _h(dev)
         _lib.check(L.msgm_softmax_pair(h, _lib.ptr(Pm), _lib.ptr(Sd), _lib.ptr(A), _lib.ptr(Pdb), _lib.ptr(Sb), _lib.ptr(Sdb),
@@ -577,20 +586,19 @@ class AttnPair(torch.autograd.Function):
         gbase = gq.data_ptr()
 
         def gptr(sample0, part):
-            return C.c_void_p(gbase + f * (sample0 * sq + part * Cc * T))
+            return gbase + f * (sample0 * sq + part * Cc * T)
 
-        # vbar = Obar P + Odotbar Pdot ; vdotbar = Odotbar P
-        _bgemm(dev, ob, _lib.ptr(Pm), gptr(0, 2), Cc, T, T, T, T, T, so, T * T, sq, B)
-        _bgemm(dev, odb, _lib.ptr(Pd), gptr(0, 2), Cc, T, T, T, T, T, so, T * T, sq, B, acc=True)
-        _bgemm(dev, odb, _lib.ptr(Pm), gptr(B, 2), Cc, T, T, T, T, T, so, T * T, sq, B)
-        # qbar = s^2 (k Sbar^T + kdot Sdotbar^T) ; qdotbar = s^2 k Sdotbar^T
-        _bgemm(dev, k, _lib.ptr(Sb), gptr(0, 0), Cc, T, T, T, T, T, sq, T * T, sq, B, tb=True, alpha=s2)
-        _bgemm(dev, kd, _lib.ptr(Sdb), gptr(0, 0), Cc, T, T, T, T, T, sq, T * T, sq, B, tb=True, alpha=s2, acc=True)
-        _bgemm(dev, k, _lib.ptr(Sdb), gptr(B, 0), Cc, T, T, T, T, T, sq, T * T, sq, B, tb=True, alpha=s2)
-        # kbar = s^2 (q Sbar + qdot Sdotbar) ; kdotbar = s^2 q Sdotbar
-        _bgemm(dev, q, _lib.ptr(Sb), gptr(0, 1), Cc, T, T, T, T, T, sq, T * T, sq, B, alpha=s2)
-        _bgemm(dev, qd, _lib.ptr(Sdb), gptr(0, 1), Cc, T, T, T, T, T, sq, T * T, sq, B, alpha=s2, acc=True)
-        _bgemm(dev, q, _lib.ptr(Sdb), gptr(B, 1), Cc, T, T, T, T, T, sq, T * T, sq, B, alpha=s2)
+        P_, Pd_, Sb_, Sdb_ = Pm.data_ptr(), Pd.data_ptr(), Sb.data_ptr(), Sdb.data_ptr()
+        _gemm_group(dev, [
+            # vbar = Obar P + Odotbar Pdot ; vdotbar = Odotbar P
+            _prob([(ob, P_, T, T, so, TT, 0, 0), (odb, Pd_, T, T, so, TT, 0, 0)], gptr(0, 2), T, sq),
+            _prob([(odb, P_, T, T, so, TT, 0, 0)], gptr(B, 2), T, sq),
+            # qbar = s^2 (k Sbar^T + kdot Sdotbar^T) ; qdotbar = s^2 k Sdotbar^T
+            _prob([(k, Sb_, T, T, sq, TT, 0, 1), (kd, Sdb_, T, T, sq, TT, 0, 1)], gptr(0, 0), T, sq, s2),
+            _prob([(k, Sdb_, T, T, sq, TT, 0, 1)], gptr(B, 0), T, sq, s2),
+            # kbar = s^2 (q Sbar + qdot Sdotbar) ; kdotbar = s^2 q Sdotbar
+            _prob([(q, Sb_, T, T, sq, TT, 0, 0), (qd, Sdb_, T, T, sq, TT, 0, 0)], gptr(0, 1), T, sq, s2),
+            _prob([(q, Sdb_, T, T, sq, TT, 0, 0)], gptr(B, 1), T, sq, s2)], Cc, T, T, B)
         return gq
 
 

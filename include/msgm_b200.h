@@ -307,16 +307,26 @@ int msgm_softmax_pair(msgm_ctx* ctx, const float* S_or_P, const float* Sdot, con
                       float* out1, float* out2, int64_t nrows, int32_t T, void* stream);
 int msgm_sincos_pair(msgm_ctx* ctx, const float* val_pair, float* emb_pair, int32_t B, int32_t dim, void* stream);
 int msgm_resample2(msgm_ctx* ctx, const float* x, float* out, int64_t NC, int32_t H, int32_t W, int32_t mode, void* stream);
+/* Range scaling of the NEXT msgm_conv2d_tc / msgm_conv1d_tc / msgm_convt1d_tc launch of this context (one-shot: the launch
+ * consumes it): the kernel stages its input times the power of two that brings amax (device word, max|input| as written by
+ * msgm_amax) to 2^12 and scales its accumulators back before bias / residual terms.  Used by the data gradients of the U-Net
+ * training path, whose cotangents (~1e-7 in the deep layers) would otherwise fall into the fp16 subnormal range of the split
+ * operands.  NULL clears a pending request. */
+int msgm_tc_range_scale(msgm_ctx* ctx, const float* amax_or_null);
 /* msgm_conv_wgrad on tcgen05 (csrc/conv_wgrad_tc.cu): the weight gradient as a product over positions with both operands read
  * MN-major from the forward conv's staged tile layout, split fp16 x 3 (fp32-level parity), cotangent range-scaled by the power of
  * two derived from amax (device word written by msgm_amax; NULL = no scaling).  Takes stride-1 convolutions with "same" padding:
  * 3x3 (KH = KW = 3, pad 1), 1-D k3 (KH = 1, KW = 3, pad 1) and 1x1, channel counts % 16 == 0 (C1 % 16 == 0), up in {1, 2};
  * msgm_conv_wgrad_tc_ok tells (1 / 0) whether a shape is taken; otherwise the call returns MSGM_ERR_UNSUPPORTED and the caller
- * uses msgm_conv_wgrad.  (Hs, Ws) is the stored input size; cot is (N, Cout, Hs up, Ws up). */
+ * uses msgm_conv_wgrad.  (Hs, Ws) is the stored input size; cot is (N, Cout, Hs up, Ws up).  scratch: device buffer of
+ * msgm_conv_wgrad_tc_scratch_bytes(...) bytes (Cin = C1 + C2) for the per-slice partial tiles, summed by a second launch in a
+ * fixed order (no atomics). */
 int msgm_conv_wgrad_tc_ok(int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
                           int32_t up, int32_t Hs, int32_t Ws);
+uint64_t msgm_conv_wgrad_tc_scratch_bytes(const msgm_ctx* ctx, int32_t N, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW,
+                                          int32_t up, int32_t Hs, int32_t Ws);
 int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate,
-                       const float* amax_or_null, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
+                       const float* amax_or_null, void* scratch, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
                        int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, void* stream);
 int msgm_pair_act(msgm_ctx* ctx, const float* z, const float* grad_h_or_null, float* out, int64_t half_elems, int32_t act,
                   void* stream);

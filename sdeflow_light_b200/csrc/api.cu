@@ -312,6 +312,12 @@ int msgm_stage_update_clocked(msgm_ctx* ctx, const msgm_sde_desc* sde, int32_t s
                               a, dW, r0, x, y, ks, B, stream, clk);
 }
 
+int msgm_tc_range_scale(msgm_ctx* ctx, const float* amax_or_null) {
+  if (!ctx) return invalid("msgm_tc_range_scale: NULL context");
+  ctx->tc_in_amax = reinterpret_cast<const unsigned int*>(amax_or_null);
+  return MSGM_OK;
+}
+
 int msgm_row_norm(msgm_ctx* ctx, const float* x, float* r, int32_t d, int64_t B, void* stream) {
   if (!ctx || !x || !r || d < 1) return invalid("msgm_row_norm: bad argument");
   if (B <= 0) return B == 0 ? MSGM_OK : invalid("B < 0");

@@ -49,12 +49,24 @@ struct ConvTcParams {
   uint32_t mul_img, shr_img, mul_row, shr_row;  // magic numbers: n / (Hp Wp) and n / Wp for n < 2^31
   int tmem_cols;
   int fast;                   // 1: single fp16 product (hi planes only; ~1e-3 relative), 0: three split products (fp32-level)
+  const unsigned int* in_amax;  // NULL or max|input| as float bits: the input is staged times 2^k (max -> 2^12) and the
+                              // accumulators are scaled back: data gradients of cotangents far below the fp16 range
   TcFlags flags;
 };
 
 __device__ __forceinline__ float silu_acc(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 constexpr int CTC_STAGERS = 256;
+
+// power of two that brings max|x| to 2^12 (exact scaling; 1 when no range word is given)
+__device__ __forceinline__ float ctc_range_scale(const unsigned int* amax_bits) {
+  if (!amax_bits) return 1.0f;
+  const float m = __uint_as_float(*amax_bits);
+  if (!(m > 0.0f)) return 1.0f;
+  int e;
+  frexpf(m, &e);
+  return ldexpf(1.0f, max(-120, min(120, 12 - e)));
+}
 
 // n / d for n < 2^31 with the precomputed (mul, shr) of find_divisor below (d == 1: mul = 0)
 __device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr) {
@@ -159,6 +171,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
     // per tile.  it_b = sample index (-1: padding ring / outside, -2: no such item), it_o = element offset of the item's
     // first channel inside the chunk's 16 stored channel planes, it_s = k-chunk << 30 | staged position.
     constexpr int NI_MAX = 6;  // 6 x 256 items = 768 staged positions (the host guarantees SL <= 768)
+    const float in_scale = ctc_range_scale(P.in_amax);
     const int nitem = 2 * P.SL, upsh = P.up == 2 ? 1 : 0;
     int it_b[NI_MAX], it_o[NI_MAX], it_s[NI_MAX];
 #pragma unroll
@@ -217,6 +230,10 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
           const int bcur = it_b[i0 + u], kcc = it_s[i0 + u] >> 30, spp = it_s[i0 + u] & 0x3fffffff;
           uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
           if (bcur >= 0) {
+            if (P.in_amax) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[u][j] *= in_scale;
+            }
             if (P.ss) {
               const float4* ssp = reinterpret_cast<const float4*>(P.ss + ((size_t)bcur * Cin + ch0 + kcc * 8) * 2);
 #pragma unroll
@@ -248,6 +265,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
     tc_fence_after();
     const int q4 = warp & 3, half = warp >> 2;
     constexpr int NH = NOUT / 2;
+    const float out_scale = 1.0f / in_scale;
     const int HWo = P.Ho * P.Wo;
     for (int mb = 0; mb < P.MB; ++mb) {
       const long long p = p0 + mb * 128 + q4 * 32 + lane;
@@ -278,6 +296,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
           for (int j = 0; j < 16; ++j) {
             int co = co0 + half * NH + cc + j;
             float v = __uint_as_float(rr[j]);
+            if (P.in_amax) v *= out_scale;
             if constexpr (NT == 3) {
               if (P.convt) {  // ConvTranspose1d: even / odd outputs are the two halves of the N dimension
                 const int par = co >= P.convt ? 1 : 0;
@@ -515,6 +534,8 @@ int conv2d_tc(msgm_ctx* ctx, const msgm_conv2d_tc_desc* D, cudaStream_t stream) 
   P.Ho = (P.Hi + 2 * pad - D->K) / D->stride + 1;
   P.Wo = (P.Wi + 2 * pad - D->K) / D->stride + 1;
   P.NC = (P.C1 + P.C2) / 16;
+  P.in_amax = ctx->tc_in_amax;
+  ctx->tc_in_amax = nullptr;
   P.flags = next_tc_flags(ctx);
   return D->K == 3 ? launch_conv_tc_n<9>(ctx, P, stream) : launch_conv_tc_n<1>(ctx, P, stream);
 }
@@ -532,6 +553,8 @@ int conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* D, cudaStream_t stream) 
   const int pad = D->K == 1 ? 0 : 1;
   P.Wo = (D->Lin + 2 * pad - D->K) / D->stride + 1;
   P.NC = (P.C1 + P.C2) / 16;
+  P.in_amax = ctx->tc_in_amax;
+  ctx->tc_in_amax = nullptr;
   P.flags = next_tc_flags(ctx);
   if (D->K == 3) return launch_conv_tc_n<3>(ctx, P, stream);
   if (D->K == 4) return launch_conv_tc_n<4>(ctx, P, stream);
@@ -558,6 +581,8 @@ int convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bia
   P.B = B; P.Cout = 2 * Cout; P.stride = 1; P.up = 1; P.Hs = 1; P.Ws = Lin;
   P.Hi = 1; P.Wi = Lin; P.Ho = 1; P.Wo = Lout;
   P.NC = Cin / 16;
+  P.in_amax = ctx->tc_in_amax;
+  ctx->tc_in_amax = nullptr;
   P.flags = next_tc_flags(ctx);
   return launch_conv_tc_n<3>(ctx, P, stream);
 }

@@ -15,7 +15,8 @@
 //     memory (lanes = consecutive positions: coalesced), scale the cotangent by a power of two into the fp16 range (deep-layer
 //     cotangents are ~1e-7: the fp16 x 3 split would lose its low part in the subnormals), split to fp16 hi + lo and write the
 //     planes; a ninth warp issues 4 x NTG x 3 tcgen05.mma (hi hi + lo hi + hi lo: fp32-level parity) and commits;
-//   * epilogue: tcgen05.ld, unscale, red.global.add into gW (the position slices and the primal / tangent halves sum there).
+//   * epilogue: tcgen05.ld, unscale, the CTA's partial tile goes to a scratch slice with coalesced plain stores (lane = output
+//     channel); wgrad_reduce_kernel sums the position slices into gW in a fixed order (no atomics: deterministic).
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -34,6 +35,7 @@ struct WgradTcParams {
   const float* x1;   // (N, C1, Hs, Ws)
   const float* x2;   // (N, C2, Hs, Ws) or NULL: channel concat
   float* gW;         // (Cout, Cw, KH, KW), accumulated; input channels [coff, coff + C1 + C2)
+  float* scratch;    // per-CTA partial tiles [cta][tap * NCI + ci][128 co] (plain coalesced stores; reduced by wgrad_reduce_kernel)
   const unsigned int* amax_bits;  // max |cot| as float bits (msgm_amax) or NULL: no range scaling
   int C1, C2, Cout, Cw, coff, KH, KW;
   int N, H, W, Hs, Ws, upsh;  // the conv sees (H, W) = (Hs << upsh, Ws << upsh)
@@ -247,27 +249,18 @@ __global__ void __launch_bounds__(WG_STAGERS + 32, 1) conv_wgrad_tc_kernel(const
     // ================================================== epilogue ==================================================
     ok = ok && mbar_wait(bar_done, 0, P.flags);
     tc_fence_after();
-    if (warp < 4 && my_chunks > 0) {
-      const int co = co0 + warp * 32 + lane;
+    if (warp < 4) {
+      // partial tile -> scratch: lane = output channel, so a warp store covers 128 contiguous bytes; no atomics, fixed order
       const float inv = 1.0f / scale;
-      const int ky = P.NG == 3 ? g : 0;
+      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      float* dst = P.scratch + cta * (size_t)(NTG * P.NCI) * 128 + warp * 32 + lane;
 #pragma unroll 1
-      for (int t = 0; t < NTG; ++t) {
-        const uint32_t taddr = tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * P.NCI);
-#pragma unroll 1
-        for (int cc = 0; cc < P.NCI; cc += 16) {
-          uint32_t rr[16];
-          TMEM_LD16(taddr + cc, rr);
-          tc_wait_ld();
-          if (ok && co < P.Cout) {
+      for (int cc = 0; cc < NTG * P.NCI; cc += 16) {
+        uint32_t rr[16];
+        TMEM_LD16(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, rr);
+        tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int ci = ci0 + cc + j;
-              if (ci < Cin)
-                atomicAdd(P.gW + (((size_t)co * P.Cw + P.coff + ci) * P.KH + ky) * P.KW + t, __uint_as_float(rr[j]) * inv);
-            }
-          }
-        }
+        for (int j = 0; j < 16; ++j) dst[(size_t)(cc + j) * 128] = (ok && my_chunks > 0) ? __uint_as_float(rr[j]) * inv : 0.0f;
       }
     }
   }
@@ -276,6 +269,25 @@ __global__ void __launch_bounds__(WG_STAGERS + 32, 1) conv_wgrad_tc_kernel(const
   __syncthreads();
   if (warp == WG_STAGERS / 32)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(P.tmem_cols));
+}
+
+// gW[co][coff + ci][ky][kx] += sum over the position slices of the partial tiles (threads run along co: coalesced reads)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ gW, int gx, int gy,
+                                                           int gz, int cols, int NCI, int NG, int Cout, int Cin, int Cw, int coff,
+                                                           int KH, int KW) {
+  const long long total = (long long)gz * gy * cols * 128;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i & 127);
+    long long r = i >> 7;
+    const int col = (int)(r % cols); r /= cols;
+    const int y = (int)(r % gy), z = (int)(r / gy);
+    const int co = z * 128 + row, g = y % NG, cit = y / NG, t = col / NCI, ci = cit * NCI + col % NCI;
+    if (co >= Cout || ci >= Cin) continue;
+    const float* src = scratch + (((size_t)z * gy + y) * gx) * (size_t)cols * 128 + (size_t)col * 128 + row;
+    float sum = 0.0f;
+    for (int x = 0; x < gx; ++x) sum += src[(size_t)x * cols * 128];
+    gW[(((size_t)co * Cw + coff + ci) * KH + (NG == 3 ? g : 0)) * KW + t] += sum;
+  }
 }
 
 static void wg_find_divisor(uint32_t d, uint32_t* mul, uint32_t* shr) {
@@ -295,10 +307,44 @@ int conv_wgrad_tc_supported(int Cout, int C1, int C2, int KH, int KW, int stride
          padded_positions < (1LL << 31) - 4096;
 }
 
+struct WgGeom {
+  int ntg, NG, nci, ci_tiles, co_tiles, nchunks, chunks_per_cta, slices, cols;
+};
+
+static WgGeom wg_geometry(const msgm_ctx* ctx, int N, int Cout, int Cin, int KH, int KW, int up, int Hs, int Ws) {
+  WgGeom g{};
+  g.ntg = KW == 3 ? 3 : 1;
+  g.NG = KH == 3 ? 3 : 1;
+  const long long total = (long long)N * (Hs * up + (KH == 3 ? 2 : 0)) * (Ws * up + (KW == 3 ? 2 : 0));
+  // input-channel tile: as wide as the TMEM columns (ntg x NCI <= 512) and the channel count allow, a multiple of 16
+  int nci = std::min(128, Cin);
+  if (Cin > 128) {  // balance the tiles: 192 -> 2 x 96, 256 -> 2 x 128, 384 -> 3 x 128
+    const int tiles = (Cin + 127) / 128;
+    nci = ((Cin + tiles - 1) / tiles + 15) / 16 * 16;
+  }
+  g.nci = nci;
+  g.ci_tiles = (Cin + nci - 1) / nci;
+  g.co_tiles = (Cout + 127) / 128;
+  g.cols = g.ntg * nci;
+  g.nchunks = (int)((total + WG_KT - 1) / WG_KT);
+  // position slices: about one CTA per SM over the whole grid, at least 4 chunks each
+  const int other = g.NG * g.ci_tiles * g.co_tiles;
+  int slices = std::max(1, std::min(g.nchunks / 4 + 1, (ctx->num_sms + other - 1) / other));
+  g.chunks_per_cta = (g.nchunks + slices - 1) / slices;
+  g.slices = (g.nchunks + g.chunks_per_cta - 1) / g.chunks_per_cta;
+  return g;
+}
+
+size_t conv_wgrad_tc_scratch_bytes(const msgm_ctx* ctx, int N, int Cout, int Cin, int KH, int KW, int up, int Hs, int Ws) {
+  const WgGeom g = wg_geometry(ctx, N, Cout, Cin, KH, KW, up, Hs, Ws);
+  return (size_t)g.slices * g.NG * g.ci_tiles * g.co_tiles * g.cols * 128 * sizeof(float);
+}
+
 int conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* x1, const float* x2, float* gW, const unsigned int* amax_bits,
-                  int N, int Cout, int C1, int C2, int Cw, int coff, int KH, int KW, int up, int Hs, int Ws, cudaStream_t stream) {
+                  float* scratch, int N, int Cout, int C1, int C2, int Cw, int coff, int KH, int KW, int up, int Hs, int Ws,
+                  cudaStream_t stream) {
   WgradTcParams P{};
-  P.cot = cot; P.x1 = x1; P.x2 = x2; P.gW = gW; P.amax_bits = amax_bits;
+  P.cot = cot; P.x1 = x1; P.x2 = x2; P.gW = gW; P.amax_bits = amax_bits; P.scratch = scratch;
   P.C1 = C1; P.C2 = x2 ? C2 : 0; P.Cout = Cout; P.Cw = Cw; P.coff = coff; P.KH = KH; P.KW = KW;
   P.N = N; P.Hs = Hs; P.Ws = Ws; P.upsh = up == 2 ? 1 : 0; P.H = Hs * up; P.W = Ws * up;
   P.padh = KH == 3 ? 1 : 0; P.padw = KW == 3 ? 1 : 0;
@@ -306,42 +352,32 @@ int conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* x1, const float*
   P.total = (long long)N * P.Hp * P.Wp;
   wg_find_divisor((uint32_t)(P.Hp * P.Wp), &P.mul_img, &P.shr_img);
   wg_find_divisor((uint32_t)P.Wp, &P.mul_row, &P.shr_row);
-  const int Cin = P.C1 + P.C2, ntg = KW == 3 ? 3 : 1;
-  P.NG = KH == 3 ? 3 : 1;
-  // input-channel tile: as wide as the TMEM columns (ntg x NCI <= 512) and the channel count allow, a multiple of 16
-  int nci = std::min(128, Cin);
-  if (Cin > 128) {  // balance the tiles: 192 -> 2 x 96, 256 -> 2 x 128, 384 -> 3 x 128
-    const int tiles = (Cin + 127) / 128;
-    nci = ((Cin + tiles - 1) / tiles + 15) / 16 * 16;
-  }
-  P.NCI = nci;
-  const int ci_tiles = (Cin + nci - 1) / nci, co_tiles = (Cout + 127) / 128;
+  const int Cin = P.C1 + P.C2;
+  const WgGeom g = wg_geometry(ctx, N, Cout, Cin, KH, KW, up, Hs, Ws);
+  P.NG = g.NG; P.NCI = g.nci; P.nchunks = g.nchunks; P.chunks_per_cta = g.chunks_per_cta;
   int cols = 32;
-  while (cols < ntg * nci) cols <<= 1;
+  while (cols < g.cols) cols <<= 1;
   P.tmem_cols = cols;
-  P.nchunks = (int)((P.total + WG_KT - 1) / WG_KT);
-  // position slices: about one CTA per SM over the whole grid, at least 8 chunks each (the flush of a CTA's accumulators is
-  // up to 128 x 384 atomics: it has to be amortised over enough positions)
-  const int other = P.NG * ci_tiles * co_tiles;
-  int slices = std::max(1, std::min(P.nchunks / 8 + 1, (ctx->num_sms + other - 1) / other));
-  P.chunks_per_cta = (P.nchunks + slices - 1) / slices;
-  slices = (P.nchunks + P.chunks_per_cta - 1) / P.chunks_per_cta;
   P.flags = next_tc_flags(ctx);
-  const int sli = WG_KT + (ntg == 3 ? 2 : 0);
-  const size_t smem = 128 + 128 + 2 * (size_t)(2 * 16 * WG_KT * 16) + 2 * (size_t)(2 * (nci / 8) * sli * 16);
+  const int sli = WG_KT + (g.ntg == 3 ? 2 : 0);
+  const size_t smem = 128 + 128 + 2 * (size_t)(2 * 16 * WG_KT * 16) + 2 * (size_t)(2 * (g.nci / 8) * sli * 16);
   uint32_t sb = 0;
   int rc = dyn_smem_base(ctx, stream, &sb);
   if (rc) return rc;
-  const dim3 grid((unsigned)slices, (unsigned)(P.NG * ci_tiles), (unsigned)co_tiles);
+  const dim3 grid((unsigned)g.slices, (unsigned)(g.NG * g.ci_tiles), (unsigned)g.co_tiles);
 #define MSGM_WG_LAUNCH(NTG_)                                                                                               \
   {                                                                                                                        \
     auto kern = sb == 1024u ? conv_wgrad_tc_kernel<NTG_, true> : conv_wgrad_tc_kernel<NTG_, false>;                        \
     MSGM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
     kern<<<grid, WG_STAGERS + 32, smem, stream>>>(P);                                                                      \
   }
-  if (ntg == 3) MSGM_WG_LAUNCH(3) else MSGM_WG_LAUNCH(1)
+  if (g.ntg == 3) MSGM_WG_LAUNCH(3) else MSGM_WG_LAUNCH(1)
 #undef MSGM_WG_LAUNCH
-  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  const long long nel = (long long)grid.z * grid.y * g.cols * 128;
+  wgrad_reduce_kernel<<<(unsigned)std::min<long long>((nel + 255) / 256, (long long)ctx->num_sms * 8), 256, 0, stream>>>(
+      scratch, gW, (int)grid.x, (int)grid.y, (int)grid.z, g.cols, g.nci, g.NG, Cout, Cin, Cw, coff, KH, KW);
+  ctx->launches += 2;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;
 }
@@ -358,11 +394,17 @@ int msgm_conv_wgrad_tc_ok(int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32
   return conv_wgrad_tc_supported(Cout, C1, C2, KH, KW, stride, pad, up, padded);
 }
 
+uint64_t msgm_conv_wgrad_tc_scratch_bytes(const msgm_ctx* ctx, int32_t N, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW,
+                                          int32_t up, int32_t Hs, int32_t Ws) {
+  if (!ctx || N < 1 || Cout < 1 || Cin < 1 || Hs < 1 || Ws < 1) return 0;
+  return conv_wgrad_tc_scratch_bytes(ctx, N, Cout, Cin, KH, KW, up, Hs, Ws);
+}
+
 int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate,
-                       const float* amax_or_null, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
+                       const float* amax_or_null, void* scratch, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
                        int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, void* stream) {
-  if (!ctx || !cot || !in1 || !gW_accumulate || N < 1 || Cout < 1 || C1 < 1 || C2 < 0 || (C2 > 0 && !in2) || coff < 0 ||
-      coff + C1 + C2 > Cw || Hs < 1 || Ws < 1) {
+  if (!ctx || !cot || !in1 || !gW_accumulate || !scratch || N < 1 || Cout < 1 || C1 < 1 || C2 < 0 || (C2 > 0 && !in2) ||
+      coff < 0 || coff + C1 + C2 > Cw || Hs < 1 || Ws < 1) {
     set_error("msgm_conv_wgrad_tc: bad argument");
     return MSGM_ERR_INVALID;
   }
@@ -371,8 +413,8 @@ int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const 
     return MSGM_ERR_UNSUPPORTED;
   }
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
-  return conv_wgrad_tc(ctx, cot, in1, in2, gW_accumulate, reinterpret_cast<const unsigned int*>(amax_or_null), N, Cout, C1, C2, Cw,
-                       coff, KH, KW, up, Hs, Ws, (cudaStream_t)stream);
+  return conv_wgrad_tc(ctx, cot, in1, in2, gW_accumulate, reinterpret_cast<const unsigned int*>(amax_or_null),
+                       reinterpret_cast<float*>(scratch), N, Cout, C1, C2, Cw, coff, KH, KW, up, Hs, Ws, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -36,6 +36,7 @@ struct msgm_ctx {
   int* host_flag;      // mapped pinned host word: error code raised by a tensor-core kernel (tc_ptx.cuh, TcFlags)
   int* host_flag_dev;  // its device alias
   int launch_seq;      // ids of the tensor-core launches (1, 2, ...)
+  const unsigned int* tc_in_amax;  // one-shot: range scaling of the NEXT tensor-core conv launch (msgm_tc_range_scale)
 };
 
 namespace msgm {

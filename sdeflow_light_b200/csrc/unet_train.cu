@@ -202,8 +202,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
   const int tiles_ci = (Cin + TN - 1) / TN;
   const int tm = (blockIdx.x / tiles_ci) * TM, tn = (blockIdx.x % tiles_ci) * TN;
   const int ky = blockIdx.y / P.KW, kx = blockIdx.y % P.KW;
-  __shared__ __align__(16) float sC[KT * T::SA];
-  __shared__ __align__(16) float sI[KT * T::SB];
+  __shared__ __align__(16) float tile[KT * (T::SA + T::SB)];  // >= 16 KB for every instantiation: reused by the K-group reduction
+  float* sC = tile;
+  float* sI = tile + KT * T::SA;
   const int tid = threadIdx.x, tt = tid % T::NT, kg = tid / T::NT;
   const int pp = (tid & 7) + 8 * ((tid >> 5) & 3), ch0 = ((tid >> 3) & 3) + 4 * (tid >> 7);  // staging role: position, first channel
   float acc[8][8] = {};
@@ -257,6 +258,32 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
     if (p0 + KT < p_end) fetch(p0 + KT);
     tile_fma<TM, TN>(sC, sI, tt, kg, KT, KG, acc);
     __syncthreads();
+  }
+  if constexpr (KG > 1) {  // sum the K groups' partial tiles in shared memory first: KG times fewer atomics on the same addresses
+    static_assert(KT * (T::SA + T::SB) >= 32 * 128, "reduction buffer");
+#pragma unroll
+    for (int half = KG / 2; half >= 1; half >>= 1) {
+#pragma unroll
+      for (int ih = 0; ih < 2; ++ih) {  // rows 0..3 and 4..7 of the thread tiles in turn (16 KB buffer)
+        if (kg >= half && kg < 2 * half) {
+          const int slot = (kg - half) * T::NT + tt;  // < 128
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tile[(i * 8 + j) * 128 + slot] = acc[4 * ih + i][j];
+        }
+        __syncthreads();
+        if (kg < half) {
+          const int slot = kg * T::NT + tt;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[4 * ih + i][j] += tile[(i * 8 + j) * 128 + slot];
+        }
+        __syncthreads();
+      }
+    }
+    if (kg != 0) return;
   }
   const int rg = tt % (TM / 8), cg = tt / (TM / 8);
 #pragma unroll

@@ -119,17 +119,21 @@ def amax_of(g):
     return amax
 
 
-def ranged(conv, g, amax=None):
-    """``conv(g)`` with g brought to max|g| = 2^12 first and the result scaled back (powers of two: exact).  The tensor-core
-    convs split operands into fp16 hi + lo; cotangents of the deep layers (~1e-7) would fall into the fp16 subnormal range."""
+def ranged(conv, g, amax=None, tc=True):
+    """``conv(g)`` evaluated on g times the power of two that brings max|g| to 2^12, result scaled back (exact).  The tensor-core
+    convs split operands into fp16 hi + lo; cotangents of the deep layers (~1e-7) would fall into the fp16 subnormal range.
+    tc=True: ``conv`` is ONE tensor-core conv launch, which scales while staging and unscales in its epilogue
+    (msgm_tc_range_scale, one-shot); otherwise (CUDA-core fall-back shapes: fp32, no scaling needed) the conv runs as is."""
     h, L, st = _h(g.device)
+    if not tc:
+        return conv(g)
     if amax is None:
         amax = amax_of(g)
-    gs = torch.empty_like(g)
-    _lib.check(L.msgm_pow2_scale(h, _lib.ptr(g), _lib.ptr(gs), g.numel(), _lib.ptr(amax), 12, 0, st))
-    out = conv(gs)
-    _lib.check(L.msgm_pow2_scale(h, _lib.ptr(out), _lib.ptr(out), out.numel(), _lib.ptr(amax), 12, 1, st))
-    return out
+    _lib.check(L.msgm_tc_range_scale(h, _lib.ptr(amax)))
+    try:
+        return conv(g)
+    finally:
+        _lib.check(L.msgm_tc_range_scale(h, None))
 
 
 WGRAD_TC = True  # weight gradients on tcgen05 (csrc/conv_wgrad_tc.cu) where the shape allows; False: fp32 CUDA-core kernel
@@ -141,8 +145,10 @@ def conv_wgrad(cot, in1, in2, gW, coff, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo,
     if WGRAD_TC and L.msgm_conv_wgrad_tc_ok(cot.shape[0], cot.shape[1], in1.shape[1], C2, KH, KW, stride, pad, up, Hi, Wi):
         if amax is None:
             amax = amax_of(cot)
+        nb = L.msgm_conv_wgrad_tc_scratch_bytes(h, cot.shape[0], cot.shape[1], in1.shape[1] + C2, KH, KW, up, Hi, Wi)
+        scratch = torch.empty(nb, device=cot.device, dtype=torch.uint8)
         _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), _lib.ptr(amax),
-                                        cot.shape[0], cot.shape[1], in1.shape[1], C2, gW.shape[1], coff, KH, KW, stride, pad, up,
+                                        _lib.ptr(scratch), cot.shape[0], cot.shape[1], in1.shape[1], C2, gW.shape[1], coff, KH, KW, stride, pad, up,
                                         Hi, Wi, st))
         return
     _lib.check(L.msgm_conv_wgrad(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), cot.shape[0], cot.shape[1],

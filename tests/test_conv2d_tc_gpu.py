@@ -304,8 +304,9 @@ def test_conv_wgrad_tc_matches_float64(N, Cout, C1, C2, KH, KW, up, Hs, Ws, csca
     x2d = None if x2 is None else x2.to(dev)
     amax = torch.empty(1, device=dev, dtype=torch.float32)
     _lib.check(L.msgm_amax(h, _lib.ptr(cd), cd.numel(), _lib.ptr(amax), _lib.stream_ptr(dev)))
-    _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cd), _lib.ptr(x1d), _lib.ptr(x2d), _lib.ptr(gW), _lib.ptr(amax), N, Cout, C1, C2,
-                                    Cw, coff, KH, KW, 1, pad, up, Hs, Ws, _lib.stream_ptr(dev)))
+    scratch = torch.empty(L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, Cin, KH, KW, up, Hs, Ws), device=dev, dtype=torch.uint8)
+    _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cd), _lib.ptr(x1d), _lib.ptr(x2d), _lib.ptr(gW), _lib.ptr(amax), _lib.ptr(scratch),
+                                    N, Cout, C1, C2, Cw, coff, KH, KW, 1, pad, up, Hs, Ws, _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     _lib.check_async(dev)
     got = gW.cpu()

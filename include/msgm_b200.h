@@ -320,14 +320,15 @@ int msgm_tc_range_scale(msgm_ctx* ctx, const float* amax_or_null);
  * msgm_conv_wgrad_tc_ok tells (1 / 0) whether a shape is taken; otherwise the call returns MSGM_ERR_UNSUPPORTED and the caller
  * uses msgm_conv_wgrad.  (Hs, Ws) is the stored input size; cot is (N, Cout, Hs up, Ws up).  scratch: device buffer of
  * msgm_conv_wgrad_tc_scratch_bytes(...) bytes (Cin = C1 + C2) for the per-slice partial tiles, summed by a second launch in a
- * fixed order (no atomics). */
+ * fixed order (no atomics); accumulate = 0 overwrites the addressed block of gW instead of adding to it. */
 int msgm_conv_wgrad_tc_ok(int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
                           int32_t up, int32_t Hs, int32_t Ws);
 uint64_t msgm_conv_wgrad_tc_scratch_bytes(const msgm_ctx* ctx, int32_t N, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW,
                                           int32_t up, int32_t Hs, int32_t Ws);
 int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate,
                        const float* amax_or_null, void* scratch, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
-                       int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, void* stream);
+                       int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, int32_t accumulate,
+                       void* stream);
 int msgm_pair_act(msgm_ctx* ctx, const float* z, const float* grad_h_or_null, float* out, int64_t half_elems, int32_t act,
                   void* stream);
 int msgm_amax(msgm_ctx* ctx, const float* x, int64_t n, float* amax_out, void* stream);

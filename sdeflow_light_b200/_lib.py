@@ -192,7 +192,7 @@ def lib() -> C.CDLL:
                 L.msgm_conv_wgrad_tc_ok.argtypes = [C.c_int32] * 11
                 L.msgm_conv_wgrad_tc_scratch_bytes.restype = C.c_uint64
                 L.msgm_conv_wgrad_tc_scratch_bytes.argtypes = [C.c_void_p] + [C.c_int32] * 8
-                L.msgm_conv_wgrad_tc.argtypes = [C.c_void_p] * 7 + [C.c_int32] * 13 + [C.c_void_p]
+                L.msgm_conv_wgrad_tc.argtypes = [C.c_void_p] * 7 + [C.c_int32] * 14 + [C.c_void_p]
                 L.msgm_gemm_f32.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 9 + [C.c_void_p]
                 L.msgm_premodule_pair.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]
                 L.msgm_sparse_ssm_loss.argtypes = [C.c_void_p, C.POINTER(SdeDesc)] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(WG_STAGERS + 32, 1) conv_wgrad_tc_kernel(const
 // gW[co][coff + ci][ky][kx] += sum over the position slices of the partial tiles (threads run along co: coalesced reads)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ gW, int gx, int gy,
                                                            int gz, int cols, int NCI, int NG, int Cout, int Cin, int Cw, int coff,
-                                                           int KH, int KW) {
+                                                           int KH, int KW, int accumulate) {
   const long long total = (long long)gz * gy * cols * 128;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(i & 127);
@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     const float* src = scratch + (((size_t)z * gy + y) * gx) * (size_t)cols * 128 + (size_t)col * 128 + row;
     float sum = 0.0f;
     for (int x = 0; x < gx; ++x) sum += src[(size_t)x * cols * 128];
-    gW[(((size_t)co * Cw + coff + ci) * KH + (NG == 3 ? g : 0)) * KW + t] += sum;
+    float* o = gW + (((size_t)co * Cw + coff + ci) * KH + (NG == 3 ? g : 0)) * KW + t;
+    *o = accumulate ? *o + sum : sum;
   }
 }
 
@@ -342,7 +343,7 @@ size_t conv_wgrad_tc_scratch_bytes(const msgm_ctx* ctx, int N, int Cout, int Cin
 
 int conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* x1, const float* x2, float* gW, const unsigned int* amax_bits,
                   float* scratch, int N, int Cout, int C1, int C2, int Cw, int coff, int KH, int KW, int up, int Hs, int Ws,
-                  cudaStream_t stream) {
+                  int accumulate, cudaStream_t stream) {
   WgradTcParams P{};
   P.cot = cot; P.x1 = x1; P.x2 = x2; P.gW = gW; P.amax_bits = amax_bits; P.scratch = scratch;
   P.C1 = C1; P.C2 = x2 ? C2 : 0; P.Cout = Cout; P.Cw = Cw; P.coff = coff; P.KH = KH; P.KW = KW;
@@ -376,7 +377,7 @@ int conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* x1, const float*
   MSGM_CUDA_TRY(cudaGetLastError());
   const long long nel = (long long)grid.z * grid.y * g.cols * 128;
   wgrad_reduce_kernel<<<(unsigned)std::min<long long>((nel + 255) / 256, (long long)ctx->num_sms * 8), 256, 0, stream>>>(
-      scratch, gW, (int)grid.x, (int)grid.y, (int)grid.z, g.cols, g.nci, g.NG, Cout, Cin, Cw, coff, KH, KW);
+      scratch, gW, (int)grid.x, (int)grid.y, (int)grid.z, g.cols, g.nci, g.NG, Cout, Cin, Cw, coff, KH, KW, accumulate);
   ctx->launches += 2;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;
@@ -402,7 +403,8 @@ uint64_t msgm_conv_wgrad_tc_scratch_bytes(const msgm_ctx* ctx, int32_t N, int32_
 
 int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate,
                        const float* amax_or_null, void* scratch, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
-                       int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, void* stream) {
+                       int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, int32_t accumulate,
+                       void* stream) {
   if (!ctx || !cot || !in1 || !gW_accumulate || !scratch || N < 1 || Cout < 1 || C1 < 1 || C2 < 0 || (C2 > 0 && !in2) ||
       coff < 0 || coff + C1 + C2 > Cw || Hs < 1 || Ws < 1) {
     set_error("msgm_conv_wgrad_tc: bad argument");
@@ -414,7 +416,7 @@ int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const 
   }
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return conv_wgrad_tc(ctx, cot, in1, in2, gW_accumulate, reinterpret_cast<const unsigned int*>(amax_or_null),
-                       reinterpret_cast<float*>(scratch), N, Cout, C1, C2, Cw, coff, KH, KW, up, Hs, Ws, (cudaStream_t)stream);
+                       reinterpret_cast<float*>(scratch), N, Cout, C1, C2, Cw, coff, KH, KW, up, Hs, Ws, accumulate, (cudaStream_t)stream);
 }
 
 }  // extern "C"

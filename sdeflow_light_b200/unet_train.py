@@ -139,20 +139,25 @@ def ranged(conv, g, amax=None, tc=True):
 WGRAD_TC = True  # weight gradients on tcgen05 (csrc/conv_wgrad_tc.cu) where the shape allows; False: fp32 CUDA-core kernel
 
 
-def conv_wgrad(cot, in1, in2, gW, coff, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, amax=None):
+def conv_wgrad(cot, in1, in2, Wshape, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, amax=None):
+    """Weight gradient (tensor of shape Wshape = (Cout, Cw, ...)) of a conv over the channels [0, C1 + C2) of its input axis; any
+    further input channels of the weight (the 1-D U-Net's folded embedding channels) are left for the caller to fill."""
     h, L, st = _h(cot.device)
-    C2 = 0 if in2 is None else in2.shape[1]
-    if WGRAD_TC and L.msgm_conv_wgrad_tc_ok(cot.shape[0], cot.shape[1], in1.shape[1], C2, KH, KW, stride, pad, up, Hi, Wi):
+    C1, C2 = in1.shape[1], 0 if in2 is None else in2.shape[1]
+    N, Cout, Cw = cot.shape[0], cot.shape[1], Wshape[1]
+    if WGRAD_TC and L.msgm_conv_wgrad_tc_ok(N, Cout, C1, C2, KH, KW, stride, pad, up, Hi, Wi):
         if amax is None:
             amax = amax_of(cot)
-        nb = L.msgm_conv_wgrad_tc_scratch_bytes(h, cot.shape[0], cot.shape[1], in1.shape[1] + C2, KH, KW, up, Hi, Wi)
+        gW = torch.empty(Wshape, device=cot.device, dtype=torch.float32)  # the kernel overwrites its block
+        nb = L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, C1 + C2, KH, KW, up, Hi, Wi)
         scratch = torch.empty(nb, device=cot.device, dtype=torch.uint8)
         _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), _lib.ptr(amax),
-                                        _lib.ptr(scratch), cot.shape[0], cot.shape[1], in1.shape[1], C2, gW.shape[1], coff, KH, KW, stride, pad, up,
-                                        Hi, Wi, st))
-        return
-    _lib.check(L.msgm_conv_wgrad(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), cot.shape[0], cot.shape[1],
-                                 in1.shape[1], C2, gW.shape[1], coff, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, st))
+                                        _lib.ptr(scratch), N, Cout, C1, C2, Cw, 0, KH, KW, stride, pad, up, Hi, Wi, 0, st))
+        return gW
+    gW = torch.zeros(Wshape, device=cot.device, dtype=torch.float32)
+    _lib.check(L.msgm_conv_wgrad(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), N, Cout, C1, C2, Cw, 0, KH, KW,
+                                 stride, pad, up, Hi, Wi, Ho, Wo, st))
+    return gW
 
 
 # ---- autograd Functions = tape entries; all arithmetic is in the kernels -------------------------------------------------------
@@ -251,8 +256,7 @@ class Conv1dPair(torch.autograd.Function):
                 gx = ranged(lambda t_: convt1d_raw(t_, Wt, Lin), g, amax)
             gx1 = gx[:, :C1]
             gx2 = gx[:, C1:] if x2 is not None else None
-        gW = torch.zeros_like(W)
-        conv_wgrad(g, x1, x2, gW, 0, 1, K, stride, pad, 1, 1, Lin, 1, Lout, amax)
+        gW = conv_wgrad(g, x1, x2, W.shape, 1, K, stride, pad, 1, 1, Lin, 1, Lout, amax)
         if emb is not None:
             Cemb = Cw - Cin
             Eb = torch.empty((N, Cout, K), device=dev, dtype=torch.float32)  # cotangent of the folded table
@@ -289,8 +293,8 @@ class ConvT1dPair(torch.autograd.Function):
         N, Cin, Lin = x.shape
         # data gradient: Conv1d(k4, s2, p1) with the weight read as (out = Cin, in = Cout), no flip
         gx = ranged(lambda t_: conv1d_raw(t_, None, W, None, 2, 1), g) if ctx.needs_input_grad[0] else None
-        gW = torch.zeros_like(W)  # gW[ci][co][k] = sum x[ci][p] g[co][2p - 1 + k]: a conv weight gradient with the roles swapped
-        conv_wgrad(x, g, None, gW, 0, 1, 4, 2, 1, 1, 1, ctx.Lout, 1, Lin)
+        # gW[ci][co][k] = sum x[ci][p] g[co][2p - 1 + k]: a conv weight gradient with the roles swapped
+        gW = conv_wgrad(x, g, None, W.shape, 1, 4, 2, 1, 1, 1, ctx.Lout, 1, Lin)
         gb = channel_sums(g, N // 2)
         return gx, gW, gb, None
 
@@ -478,8 +482,7 @@ class Conv2dPair(torch.autograd.Function):
             gx = ranged(lambda t_: conv2d_raw(t_, Wd, None, 1, 1), src, amax)
             if up == 2:                                      # adjoint of the nearest-neighbour upsampling
                 gx = resample2(gx, 1)
-        gW = torch.zeros_like(W)
-        conv_wgrad(g, x, None, gW, 0, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo, amax)
+        gW = conv_wgrad(g, x, None, W.shape, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo, amax)
         gb = channel_sums(g, N // 2) if has_b else None
         ge = sample_channel_sums(g) if has_e else None
         return gx, gW, gb, ge, None, None

@@ -306,7 +306,7 @@ def test_conv_wgrad_tc_matches_float64(N, Cout, C1, C2, KH, KW, up, Hs, Ws, csca
     _lib.check(L.msgm_amax(h, _lib.ptr(cd), cd.numel(), _lib.ptr(amax), _lib.stream_ptr(dev)))
     scratch = torch.empty(L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, Cin, KH, KW, up, Hs, Ws), device=dev, dtype=torch.uint8)
     _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cd), _lib.ptr(x1d), _lib.ptr(x2d), _lib.ptr(gW), _lib.ptr(amax), _lib.ptr(scratch),
-                                    N, Cout, C1, C2, Cw, coff, KH, KW, 1, pad, up, Hs, Ws, _lib.stream_ptr(dev)))
+                                    N, Cout, C1, C2, Cw, coff, KH, KW, 1, pad, up, Hs, Ws, 1, _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     _lib.check_async(dev)
     got = gW.cpu()

@@ -307,6 +307,13 @@ int msgm_softmax_pair(msgm_ctx* ctx, const float* S_or_P, const float* Sdot, con
                       float* out1, float* out2, int64_t nrows, int32_t T, void* stream);
 int msgm_sincos_pair(msgm_ctx* ctx, const float* val_pair, float* emb_pair, int32_t B, int32_t dim, void* stream);
 int msgm_resample2(msgm_ctx* ctx, const float* x, float* out, int64_t NC, int32_t H, int32_t W, int32_t mode, void* stream);
+/* Weight image of the DATA-GRADIENT conv of a stride-1 "same" convolution, packed straight from the forward weight W
+ * (Cout, Cw, taps), taps = 9 (3x3) / 3 (1-D k3) / 1, first Cin input channels used: the adjoint is the same conv with the channel
+ * roles swapped and the taps flipped, Wd[ci][co][taps-1-t] = W[co][ci][t], so the image has Cin output and Cout input channels and
+ * is consumed by msgm_conv2d_tc / msgm_conv1d_tc like any other (size: msgm_conv2d_tc_pack_bytes / msgm_conv1d_tc_pack_bytes of
+ * the swapped shape).  Replaces the transposed / flipped weight copy torch's convolution backward makes. */
+int msgm_conv_tc_pack_dgrad(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw, int32_t Cin, int32_t taps, void* wimg,
+                            void* stream);
 /* Range scaling of the NEXT msgm_conv2d_tc / msgm_conv1d_tc / msgm_convt1d_tc launch of this context (one-shot: the launch
  * consumes it): the kernel stages its input times the power of two that brings amax (device word, max|input| as written by
  * msgm_amax) to 2^12 and scales its accumulators back before bias / residual terms.  Used by the data gradients of the U-Net

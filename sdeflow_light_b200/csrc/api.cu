@@ -62,7 +62,7 @@ int gn_stats(msgm_ctx*, const float*, int, const float*, int, int, int, int, flo
 int conv2d(msgm_ctx*, const msgm_conv2d_desc*, cudaStream_t);
 int conv2d_tc(msgm_ctx*, const msgm_conv2d_tc_desc*, cudaStream_t);
 size_t conv2d_tc_pack_bytes(int, int, int);
-int conv2d_tc_pack(msgm_ctx*, const float*, int, int, int, int, void*, cudaStream_t);
+int conv2d_tc_pack(msgm_ctx*, const float*, int, int, int, int, void*, cudaStream_t, int dgrad = 0);
 int conv1d_tc(msgm_ctx*, const msgm_conv1d_tc_desc*, cudaStream_t);
 int convt1d_tc_pack(msgm_ctx*, const float*, int, int, void*, cudaStream_t);
 int convt1d_tc(msgm_ctx*, const float*, const void*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -524,6 +524,16 @@ int msgm_conv1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw,
   if (!conv1d_tc_shape_ok(Cout, Cin, 0, K) || Cw < Cin) return invalid("msgm_conv1d_tc_pack: unsupported shape");
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return conv2d_tc_pack(ctx, W, Cout, Cw, Cin, K, wimg, (cudaStream_t)stream);
+}
+
+int msgm_conv_tc_pack_dgrad(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw, int32_t Cin, int32_t taps, void* wimg,
+                            void* stream) {
+  if (!ctx || !W || !wimg) return invalid("msgm_conv_tc_pack_dgrad: NULL argument");
+  // the data-gradient conv has Cin output and Cout input channels
+  if (!(taps == 1 || taps == 3 || taps == 9) || Cin < 32 || Cin % 32 || Cout < 16 || Cout % 16 || Cw < Cin)
+    return invalid("msgm_conv_tc_pack_dgrad: unsupported shape (taps 1 / 3 / 9, Cin % 32 == 0, Cout % 16 == 0)");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv2d_tc_pack(ctx, W, Cin, Cw, Cout, taps, wimg, (cudaStream_t)stream, 1);
 }
 
 int msgm_convt1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, void* wimg, void* stream) {

@@ -333,8 +333,11 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
 }
 
 // ---- weight packing: (Cout, Cin, K, K) fp32 -> [ntile][chunk][hi|lo][tap][kc][NOUT][8] fp16 ---------------------------
+// dgrad = 1: W is the FORWARD conv's weight (Cin rows of the image come from its output axis): the image is the one of the
+// data-gradient conv, whose weight is W with the channel roles swapped and the taps flipped, Wd[ci_f][co_f][KK-1-t] -- so that
+// no transposed / flipped copy of the weight has to be made first.  Cw is always the row length of W's input axis.
 __global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int Cw, int Cin, int KK, int NOUT,
-                                      __half* __restrict__ img, long long nel) {
+                                      __half* __restrict__ img, long long nel, int dgrad) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nel) return;
   const int j = (int)(e % 8);
@@ -347,7 +350,8 @@ __global__ void conv2d_tc_pack_kernel(const float* __restrict__ W, int Cout, int
   const int k = (int)(r % NC);
   const int nt = (int)(r / NC);
   const int co = nt * NOUT + n, ci = k * 16 + kc * 8 + j;
-  const float v = W[((size_t)co * Cw + ci) * KK + t];  // Cw >= Cin: the weight tensor may carry extra (folded) input channels
+  // Cw >= Cin: the weight tensor may carry extra (folded) input channels
+  const float v = dgrad ? W[((size_t)ci * Cw + co) * KK + (KK - 1 - t)] : W[((size_t)co * Cw + ci) * KK + t];
   const __half hi = __float2half_rn(v);
   img[e] = hl ? __float2half_rn(v - __half2float(hi)) : hi;
 }
@@ -426,10 +430,10 @@ int conv2d_tc_nout(int Cout, int taps) {
 size_t conv2d_tc_pack_bytes(int Cout, int Cin, int KK) { return (size_t)Cout * Cin * KK * 2 * 2; }
 
 // W is (Cout, Cw, taps) with the first Cin input channels packed (Cw > Cin: trailing channels are handled elsewhere).
-int conv2d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cw, int Cin, int KK, void* img, cudaStream_t stream) {
+int conv2d_tc_pack(msgm_ctx* ctx, const float* W, int Cout, int Cw, int Cin, int KK, void* img, cudaStream_t stream, int dgrad) {
   const long long nel = (long long)Cout * Cin * KK * 2;
   conv2d_tc_pack_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, stream>>>(W, Cout, Cw, Cin, KK, conv2d_tc_nout(Cout, KK),
-                                                                          reinterpret_cast<__half*>(img), nel);
+                                                                          reinterpret_cast<__half*>(img), nel, dgrad);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

@@ -41,11 +41,28 @@ def _zeros(dev, n):
 
 
 # ---- raw kernel calls -------------------------------------------------------------------------------------------------------
-def conv1d_raw(x1, x2, W, E, stride, pad, fast=False):
-    """out = conv1d([x1, x2], W[:, :C1+C2]) (+ folded embedding table E), no bias.  W: (Cout, Cw, K), Cw >= C1 + C2."""
+def conv1d_raw(x1, x2, W, E, stride, pad, fast=False, dgrad=False):
+    """out = conv1d([x1, x2], W[:, :C1+C2]) (+ folded embedding table E), no bias.  W: (Cout, Cw, K), Cw >= C1 + C2.
+    dgrad=True: W is the weight of the FORWARD conv (stride 1, "same") and the call evaluates that conv's data gradient, i.e. the
+    conv with weight W[:, :C, :] transposed and flipped, on x1 (a cotangent, W.shape[0] channels) -> (N, C, L); C = number of
+    real (non-embedding) input channels is given as E (an int) in that case."""
     dev = x1.device
     h, L, st = _h(dev)
     N, C1, Lin = x1.shape
+    if dgrad:
+        Cf_out, Cw, K = W.shape
+        Cf_in = int(E)
+        out = torch.empty((N, Cf_in, Lin), device=dev, dtype=torch.float32)
+        zb = _zeros(dev, Cf_in)
+        if Cf_in % 32 == 0 and Cf_out % 16 == 0 and K in (1, 3) and pad == K // 2:
+            img = torch.empty(L.msgm_conv1d_tc_pack_bytes(Cf_in, Cf_out, K), device=dev, dtype=torch.uint8)
+            _lib.check(L.msgm_conv_tc_pack_dgrad(h, _lib.ptr(W), Cf_out, Cw, Cf_in, K, _lib.ptr(img), st))
+            d = _lib.Conv1dTcDesc(x1.data_ptr(), None, img.data_ptr(), zb.data_ptr(), None, out.data_ptr(), N, Cf_out, 0, Cf_in, K,
+                                  1, Lin, 0, int(fast))
+            _lib.check(L.msgm_conv1d_tc(h, C.byref(d), st))
+            return out
+        Wd = W[:, :Cf_in, :].flip(-1).transpose(0, 1).contiguous()
+        return conv1d_raw(x1, None, Wd, None, 1, K - 1 - pad, fast)
     C2 = 0 if x2 is None else x2.shape[1]
     Cout, Cw, K = W.shape
     Cin = C1 + C2
@@ -247,8 +264,7 @@ class Conv1dPair(torch.autograd.Function):
         amax = amax_of(g)
         if ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1]):
             if stride == 1:   # data gradient = the same conv with flipped taps and swapped channel roles
-                Wd = W[:, :Cin, :].flip(-1).transpose(0, 1).contiguous()
-                gx = ranged(lambda t_: conv1d_raw(t_, None, Wd, None, 1, K - 1 - pad), g, amax)
+                gx = ranged(lambda t_: conv1d_raw(t_, None, W, Cin, 1, pad, dgrad=True), g, amax)
             else:             # k4 s2 p1: data gradient = ConvTranspose1d(k4, s2, p1) with the weight read as (in = Cout, out = Cin)
                 if Lin != 2 * Lout:
                     raise NotImplementedError("hand-written U-Net training: odd signal length at a stride-2 conv")
@@ -407,17 +423,29 @@ def ssm_loss(gen, t_, y, v):
 # =====================================================================================================================
 # 2-D U-Net (NNUnet.VorticityUNet over model/unet.py UNetModel): GroupNorm, SiLU, 3x3 / 1x1 convs, attention, resampling
 # =====================================================================================================================
-def conv2d_raw(x, W, ebias, stride, up):
-    """out = conv2d(nearest-upsample^{up}(x), W, padding K//2, stride) + ebias[n, co]; no per-channel bias."""
+def conv2d_raw(x, W, ebias, stride, up, dgrad=False):
+    """out = conv2d(nearest-upsample^{up}(x), W, padding K//2, stride) + ebias[n, co]; no per-channel bias.
+    dgrad=True (stride 1, up 1): W is the weight of the FORWARD conv and the call evaluates that conv's data gradient on the
+    cotangent x, i.e. the conv with W transposed (channel roles) and flipped (taps), packed straight from W."""
     from .model.unet import _tc_shape_ok
     dev = x.device
     h, L, st = _h(dev)
     N, Cin, Hs, Ws = x.shape
+    p = lambda t_: None if t_ is None else t_.data_ptr()  # noqa: E731
+    if dgrad:
+        Cf_out, Cf_in, K = W.shape[0], W.shape[1], W.shape[-1]
+        if _tc_shape_ok(Cf_in, Cf_out, 0, K, 1, Hs, Ws):
+            out = torch.empty((N, Cf_in, Hs, Ws), device=dev, dtype=torch.float32)
+            img = torch.empty(L.msgm_conv2d_tc_pack_bytes(Cf_in, Cf_out, K), device=dev, dtype=torch.uint8)
+            _lib.check(L.msgm_conv_tc_pack_dgrad(h, _lib.ptr(W), Cf_out, Cf_in, Cf_in, K * K, _lib.ptr(img), st))
+            d = _lib.Conv2dTcDesc(p(x), None, p(img), None, None, None, None, p(out), N, Cf_out, 0, Cf_in, K, 1, 1, Hs, Ws, 0, 0)
+            _lib.check(L.msgm_conv2d_tc(h, C.byref(d), st))
+            return out
+        return conv2d_raw(x, W.flip(2, 3).transpose(0, 1).contiguous(), None, 1, 1)
     Cout, K = W.shape[0], W.shape[-1]
     pad = K // 2
     Ho, Wo = (Hs * up + 2 * pad - K) // stride + 1, (Ws * up + 2 * pad - K) // stride + 1
     out = torch.empty((N, Cout, Ho, Wo), device=dev, dtype=torch.float32)
-    p = lambda t_: None if t_ is None else t_.data_ptr()  # noqa: E731
     if _tc_shape_ok(Cout, Cin, 0, K, stride, Hs * up, Ws * up):
         img = torch.empty(L.msgm_conv2d_tc_pack_bytes(Cout, Cin, K), device=dev, dtype=torch.uint8)
         _lib.check(L.msgm_conv2d_tc_pack(h, _lib.ptr(W), Cout, Cin, K, _lib.ptr(img), st))
@@ -477,9 +505,9 @@ class Conv2dPair(torch.autograd.Function):
         gx = None
         amax = amax_of(g)
         if ctx.needs_input_grad[0]:
-            Wd = W.flip(2, 3).transpose(0, 1).contiguous()  # data gradient: the same conv, flipped taps, swapped channel roles
+            # data gradient: the same conv with flipped taps and swapped channel roles (image packed straight from W)
             src = resample2(g, 0) if stride == 2 else g     # stride 2: cotangent back on the input grid (zeros in between)
-            gx = ranged(lambda t_: conv2d_raw(t_, Wd, None, 1, 1), src, amax)
+            gx = ranged(lambda t_: conv2d_raw(t_, W, None, 1, 1, dgrad=True), src, amax)
             if up == 2:                                      # adjoint of the nearest-neighbour upsampling
                 gx = resample2(gx, 1)
         gW = conv_wgrad(g, x, None, W.shape, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo, amax)

@@ -60,6 +60,12 @@
 #ifndef MSGM_TC_SLOT4
 #define MSGM_TC_SLOT4 1
 #endif
+//   MSGM_TC_HELPERS     d > 4: every slot gets four HELPER warps that run the activation epilogue of accumulator columns 64..127
+//                       (nothing else: no particle state), so each sub-partition hosts two epilogue warps per slot instead of
+//                       one; registers are rebalanced with setmaxnreg (particle warp groups 120, helper warp groups 40)
+#ifndef MSGM_TC_HELPERS
+#define MSGM_TC_HELPERS 0
+#endif
 
 namespace msgm {
 
@@ -90,7 +96,9 @@ struct TcLayout {
   static constexpr int oA = oBar + 384;                        // NSLOT activation tiles
   static constexpr bool L4_CC = DP <= 4;                       // output layer on CUDA cores
   static constexpr int NSLOT = (DP <= 4 || (DP == 8 && !TCG && MSGM_TC_SLOT4)) ? 4 : 3;  // tiles in flight per CTA (registers / smem bound)
-  static constexpr int THREADS = 128 * NSLOT + 32;             // 4 particle warps per slot + 1 MMA issuer warp
+  static constexpr bool HELP = MSGM_TC_HELPERS && DP > 4;      // helper epilogue warps (see MSGM_TC_HELPERS)
+  static constexpr int PWARPS = 4 * NSLOT * (HELP ? 2 : 1);    // particle (+ helper) warps; the MMA issuer warp follows
+  static constexpr int THREADS = 32 * PWARPS + 32;             // 4 particle warps per slot (+ 4 helpers) + 1 MMA issuer warp
   static constexpr int AG_BYTES = 8192;                        // per slot: split y operand, fp16 [4][16][8][8]
   static constexpr int oAg = oA + NSLOT * A_BYTES;
   static constexpr int SMEM_BYTES = oAg + (TCG ? NSLOT * AG_BYTES : 0);
@@ -241,10 +249,11 @@ __device__ __forceinline__ void swish_chunk(const uint32_t* r, int c, unsigned c
 
 // Activation epilogue of one hidden layer for one particle row: D (128 fp32 cols) -> Swish -> next operand / output layer.
 // The sub-partition's XU lock is taken after the first TMEM load is in flight and dropped once the last tanh is issued.
-template <int DP, bool ACC_OUT>
+template <int DP, bool ACC_OUT, int C0 = 0, int C1 = 4>
 __device__ __forceinline__ bool swish_epilogue(uint32_t taddr, unsigned char* sA, int row, const float* __restrict__ sW4f,
                                                float* a, XuLock& xu, int lane, const TcFlags& flags) {
 #if MSGM_TC_PREFETCH
+  static_assert(C0 == 0 && C1 == 4, "prefetch variant covers the whole accumulator");
   uint32_t ra[32], rb[32];
   TMEM_LD32(taddr, ra);
   const bool ok = xu.acquire(lane, flags);
@@ -262,7 +271,7 @@ __device__ __forceinline__ bool swish_epilogue(uint32_t taddr, unsigned char* sA
 #else
   const bool ok = xu.acquire(lane, flags);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = C0; c < C1; ++c) {  // 32-column chunks [C0, C1) of the 128 accumulator columns
     uint32_t r[32];
     TMEM_LD32(taddr + c * 32, r);
     tc_wait_ld();
@@ -298,10 +307,11 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
   const long long tstride = (long long)gridDim.x * NSLOT;
 
   // ---- setup ----------------------------------------------------------------------------------------------------
-  if (tid == 128 * NSLOT) {
+  constexpr int ISSUER = L::PWARPS;  // warp index of the MMA issuer
+  if (tid == 32 * ISSUER) {
     mbar_init(bar_w, 1);
     for (int sl = 0; sl < NSLOT; ++sl) {
-      mbar_init(bar_a + sl, 128);
+      mbar_init(bar_a + sl, L::HELP ? 256 : 128);
       mbar_init(bar_d + sl, 1);
     }
     for (int q = 0; q < 4; ++q) {
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
-  if (tid == 128 * NSLOT) {  // weights: one TMA bulk copy per layer image, all landing on bar_w
+  if (tid == 32 * ISSUER) {  // weights: one TMA bulk copy per layer image, all landing on bar_w
     mbar_expect_tx(bar_w, (uint32_t)L::IMG_BYTES);
     tma_bulk_g2s(smem + L::oW1, P.img + L::oW1, L::W1_BYTES, bar_w);
     tma_bulk_g2s(smem + L::oW2, P.img + L::oW2, L::WH_BYTES, bar_w);
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
     tma_bulk_g2s(smem + L::oGI, P.img + L::oGI, L::GI_BYTES, bar_w);
   }
 
-  if (warp == 4 * NSLOT) {
+  if (warp == ISSUER) {
     // =========================================== MMA issuer ===================================================
     // The warp runs converged: it polls the slots' "operand ready" barriers round-robin, issues whatever layer is
     // ready (the tcgen05 instructions themselves are predicated on lane 0) and commits to that slot's accumulator
@@ -438,8 +448,40 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
       }
     }
     __syncwarp();
+  } else if (L::HELP && warp >= 4 * NSLOT) {
+    // ========================================= helper threads =================================================
+    // Same barrier protocol as the particle threads of the slot (four arrivals on bar_a and four waits on bar_d per stage),
+    // but the only work is the activation epilogue of accumulator columns 64..127 of the three hidden layers.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const int sl = (warp - 4 * NSLOT) >> 2;
+    const int row = tid & 127;
+    const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 128 * sl;
+    unsigned char* sA = smem + L::oA + sl * A_BYTES;
+    uint64_t* my_a = bar_a + sl;
+    uint64_t* my_d = bar_d + sl;
+    uint32_t pd = 0;
+    bool ok = true;
+    XuLock xu{xu_ring + 4 * (warp & 3), xu_next + (warp & 3), 0u};
+    float a_unused[1];
+    for (long long tile = (long long)blockIdx.x * NSLOT + sl; tile < ntiles && ok; tile += tstride) {
+      for (int step = 0; step < P.N && ok; ++step) {
+        for (int st = 0; st < nstage && ok; ++st) {
+          mbar_arrive(my_a);  // layer-1 operand: written by the particle threads only
+#pragma unroll 1
+          for (int l = 0; l < 3; ++l) {
+            ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
+            ok = swish_epilogue<DP, false, 2, 4>(taddr, sA, row, sW4f, a_unused, xu, lane, P.flags) && ok;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(my_a);
+          }
+          ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1;  // output layer: nothing to read, the phase is only tracked
+        }
+      }
+    }
   } else {
     // ======================================= particle threads ================================================
+    if constexpr (L::HELP) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int sl = warp >> 2;          // slot
     const int row = tid & 127;         // particle row in the tile == TMEM lane
     const uint32_t taddr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 128 * sl;
@@ -566,7 +608,7 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
           for (int l = 0; l < ((L4_CC || !MSGM_TC_MERGE_EPI) ? 2 : 3); ++l) {
             ok = ok && mbar_wait(my_d, pd, P.flags); pd ^= 1; tc_fence_after();
             pf.tick(1);  // wait for the accumulator
-            ok = swish_epilogue<DP, false>(taddr, sA, row, sW4f, a, xu, lane, P.flags) && ok;
+            ok = swish_epilogue<DP, false, 0, (L::HELP ? 2 : 4)>(taddr, sA, row, sW4f, a, xu, lane, P.flags) && ok;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             mbar_arrive(my_a);
@@ -595,16 +637,8 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
             for (int c = 0; c < DP; ++c) a[c] = __uint_as_float(r[c]);
             pf.tick(3);  // output layer on the tensor pipe
           }
-          [[maybe_unused]] float gy[L::TCG ? 64 : 1];  // sum_j G[i,j,k] y_j at index 8 i + k (tensor-pipe product)
-          if constexpr (L::TCG && KIND == MSGM_SDE_MSGM_DENSE) {
-            uint32_t r0[32], r1[32];
-            TMEM_LD32(taddr + 64, r0);
-            TMEM_LD32(taddr + 96, r1);
-            tc_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) { gy[c] = __uint_as_float(r0[c]); gy[32 + c] = __uint_as_float(r1[c]); }
-          }
-
+          // sum_j G[i,j,k] y_j (tensor-pipe product) sits in accumulator columns 64 + 8 i + k.  It is consumed below in two halves
+          // of 32 columns, each contracted with w right after its load: never 64 + 64 registers live at once.
           // ---- stage increment K = delta * drift + sigma . dW (same algebra as sampler_fp32.cu) --------------------------
           float K[DP];
           if (KIND == MSGM_SDE_SGM) {
@@ -632,12 +666,27 @@ __global__ void __launch_bounds__(TcLayout<DP>::THREADS, 1) sample_tc_kernel(con
                 K[c] = c < d ? acc : 0.0f;
               }
             } else {
+              [[maybe_unused]] float gw[L::TCG ? DP : 1];  // sum_k gy[i,k] w[k]
+              if constexpr (L::TCG) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t r32[32];
+                  TMEM_LD32(taddr + 64 + 32 * hh, r32);
+                  tc_wait_ld();
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < DP; ++k) acc = fmaf(__uint_as_float(r32[8 * i + k]), w[k], acc);
+                    gw[4 * hh + i] = acc;
+                  }
+                }
+              }
 #pragma unroll
               for (int i = 0; i < DP; ++i) {
                 float acc = 0.0f, fc = 0.0f;
                 if constexpr (L::TCG) {
-#pragma unroll
-                  for (int k = 0; k < DP; ++k) acc = fmaf(gy[8 * i + k], w[k], acc);
+                  acc = gw[i];
                 } else if constexpr (DP >= 4) {
 #pragma unroll
                   for (int k4 = 0; k4 < DP; k4 += 4) {

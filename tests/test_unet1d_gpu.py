@@ -551,3 +551,30 @@ def test_step_graph_sampler_is_bit_identical_to_the_eager_loop(which, mode):
         assert torch.isfinite(res[True]).all()
         assert torch.equal(res[True], res[False]), float((res[True] - res[False]).abs().max())
     Bd.report(test="step-graph-sampler", which=which, mode=mode, host_launches_graphed=launches)
+
+
+def test_step_graph_is_the_default_for_long_calls():
+    """Calls of >= generic_sampler.GRAPH_MIN_STEPS (256) steps take the one-graph-per-step path without any switch: same result
+    as the eager loop, and the host issues ~3 launches per step instead of one per kernel."""
+    from sdeflow_light_b200 import generic_sampler as GS
+    torch.manual_seed(6)
+    N, B, d = GS.GRAPH_MIN_STEPS, 3, 64
+    net = P.UNet1D(d, base_channels=8, channel_mults=(1, 2), num_res_blocks=1, premodule="NormalizeLogRadius", emb_dim=16)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(torch.randn(64, d), beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=16, device=DEV, estim_cst_norm_dens_r_T=False)
+    gen = P.PluginReverseSDE(base, net.to(DEV), T, deviceReverseSDE=DEV).to(DEV)
+    x0 = torch.randn(B, d).to(DEV)
+    kw = dict(lmbd=0., norm_correction=True, keep_all_samples=False, seed=3, device_out=True)
+    l0 = P._lib.launch_count(DEV)
+    got = P.rk4_stratonovich_sampler(gen, x0, N, **kw).clone()
+    n_graph = P._lib.launch_count(DEV) - l0
+    GS.STEP_GRAPH = False
+    try:
+        l0 = P._lib.launch_count(DEV)
+        ref = P.rk4_stratonovich_sampler(gen, x0, N, **kw).clone()
+        n_eager = P._lib.launch_count(DEV) - l0
+    finally:
+        GS.STEP_GRAPH = True
+    assert torch.isfinite(got).all() and torch.equal(got, ref)
+    assert n_graph * 20 < n_eager, (n_graph, n_eager)  # launches are counted on the host: two bodies (eager step 0 + capture)

@@ -316,29 +316,37 @@ int msgm_conv_tc_pack_dgrad(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t
                             void* stream);
 /* Range scaling of the NEXT msgm_conv2d_tc / msgm_conv1d_tc / msgm_convt1d_tc launch of this context (one-shot: the launch
  * consumes it): the kernel stages its input times the power of two that brings amax (device word, max|input| as written by
- * msgm_amax) to 2^12 and scales its accumulators back before bias / residual terms.  Used by the data gradients of the U-Net
+ * msgm_amax) into [2^14, 2^15) and scales its accumulators back before bias / residual terms.  Used by the data gradients of the U-Net
  * training path, whose cotangents (~1e-7 in the deep layers) would otherwise fall into the fp16 subnormal range of the split
  * operands.  NULL clears a pending request. */
 int msgm_tc_range_scale(msgm_ctx* ctx, const float* amax_or_null);
 /* msgm_conv_wgrad on tcgen05 (csrc/conv_wgrad_tc.cu): the weight gradient as a product over positions with both operands read
  * MN-major from the forward conv's staged tile layout, split fp16 x 3 (fp32-level parity), cotangent range-scaled by the power of
- * two derived from amax (device word written by msgm_amax; NULL = no scaling).  Takes stride-1 convolutions with "same" padding:
- * 3x3 (KH = KW = 3, pad 1), 1-D k3 (KH = 1, KW = 3, pad 1) and 1x1, channel counts % 16 == 0 (C1 % 16 == 0), up in {1, 2};
+ * two derived from amax (device word written by msgm_amax; NULL = no scaling; amax_in does the same for the input operand, which
+ * is the small one when the call computes a ConvTranspose weight gradient: there the "input" is the cotangent).  Takes stride-1 convolutions with "same" padding
+ * -- 3x3 (KH = KW = 3, pad 1), 1-D k3 (KH = 1, KW = 3, pad 1) and 1x1, up in {1, 2} -- and the stride-2 convolutions of the
+ * U-Nets -- 1-D k4 pad 1 (KH = 1, KW = 4; also ConvTranspose1d(k4, s2, p1) with the two tensors' roles swapped) and 3x3 pad 1 on
+ * even sizes -- with channel counts % 16 == 0 (C1 % 16 == 0);
  * msgm_conv_wgrad_tc_ok tells (1 / 0) whether a shape is taken; otherwise the call returns MSGM_ERR_UNSUPPORTED and the caller
- * uses msgm_conv_wgrad.  (Hs, Ws) is the stored input size; cot is (N, Cout, Hs up, Ws up).  scratch: device buffer of
+ * uses msgm_conv_wgrad.  (Hs, Ws) is the stored input size; cot is (N, Cout, Hs up, Ws up) for stride 1, (N, Cout, Hs / 2 [or 1], Ws / 2)
+ * for stride 2.  scratch: device buffer of
  * msgm_conv_wgrad_tc_scratch_bytes(...) bytes (Cin = C1 + C2) for the per-slice partial tiles, summed by a second launch in a
  * fixed order (no atomics); accumulate = 0 overwrites the addressed block of gW instead of adding to it. */
 int msgm_conv_wgrad_tc_ok(int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
                           int32_t up, int32_t Hs, int32_t Ws);
 uint64_t msgm_conv_wgrad_tc_scratch_bytes(const msgm_ctx* ctx, int32_t N, int32_t Cout, int32_t Cin, int32_t KH, int32_t KW,
-                                          int32_t up, int32_t Hs, int32_t Ws);
+                                          int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws);
 int msgm_conv_wgrad_tc(msgm_ctx* ctx, const float* cot, const float* in1, const float* in2, float* gW_accumulate,
-                       const float* amax_or_null, void* scratch, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
+                       const float* amax_or_null, const float* amax_in_or_null, void* scratch, int32_t N, int32_t Cout, int32_t C1, int32_t C2, int32_t Cw, int32_t coff,
                        int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t up, int32_t Hs, int32_t Ws, int32_t accumulate,
                        void* stream);
 int msgm_pair_act(msgm_ctx* ctx, const float* z, const float* grad_h_or_null, float* out, int64_t half_elems, int32_t act,
                   void* stream);
 int msgm_amax(msgm_ctx* ctx, const float* x, int64_t n, float* amax_out, void* stream);
+/* Both range words of a convolution's backward in one launch: amax_out2[0] = max |cot|, amax_out2[1] = max |[x1, x2]| (x2 may be
+ * NULL): the data gradient scales its input by the first, the weight gradient scales both operands. */
+int msgm_amax2(msgm_ctx* ctx, const float* cot, int64_t n_cot, const float* x1, int64_t n1, const float* x2_or_null, int64_t n2,
+               float* amax_out2, void* stream);
 int msgm_pow2_scale(msgm_ctx* ctx, const float* x, float* y, int64_t n, const float* amax_dev, int32_t target_exp,
                     int32_t inverse, void* stream);
 int msgm_rows_bias_add(msgm_ctx* ctx, float* x, const float* bias, int64_t nrows, int32_t C, int64_t P, void* stream);

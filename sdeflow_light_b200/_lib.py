@@ -78,7 +78,7 @@ _ctx = {}
 
 # every symbol include/msgm_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy", "msgm_launch_count", "msgm_async_error", "msgm_row_norm_stats", "msgm_survival_counts", "msgm_moments", "msgm_adam_step", "msgm_p2p_create", "msgm_p2p_connect", "msgm_p2p_disconnect", "msgm_p2p_destroy",
-           "msgm_p2p_allreduce_adam", "msgm_pair_act", "msgm_amax", "msgm_pow2_scale", "msgm_rows_bias_add", "msgm_channel_sums", "msgm_tap_sums_1d",
+           "msgm_p2p_allreduce_adam", "msgm_pair_act", "msgm_amax", "msgm_amax2", "msgm_pow2_scale", "msgm_rows_bias_add", "msgm_channel_sums", "msgm_tap_sums_1d",
            "msgm_conv_wgrad", "msgm_tc_range_scale", "msgm_conv_tc_pack_dgrad", "msgm_conv_wgrad_tc_ok", "msgm_conv_wgrad_tc_scratch_bytes", "msgm_conv_wgrad_tc", "msgm_gemm_f32", "msgm_premodule_pair", "msgm_sparse_ssm_loss", "msgm_bgemm_f32", "msgm_gemm_group_f32", "msgm_gn_pair", "msgm_softmax_pair",
            "msgm_sincos_pair", "msgm_resample2",
            "msgm_sample_mlp", "msgm_noise_forward", "msgm_ssm_prepare", "msgm_mlp_forward", "msgm_debug_flags", "msgm_debug_counters",
@@ -189,11 +189,12 @@ def lib() -> C.CDLL:
                 L.msgm_tap_sums_1d.argtypes = [C.c_void_p] * 3 + [C.c_int64] + [C.c_int32] * 6 + [C.c_void_p]
                 L.msgm_conv_wgrad.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 15 + [C.c_void_p]
                 L.msgm_tc_range_scale.argtypes = [C.c_void_p, C.c_void_p]
+                L.msgm_amax2.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
                 L.msgm_conv_tc_pack_dgrad.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
                 L.msgm_conv_wgrad_tc_ok.argtypes = [C.c_int32] * 11
                 L.msgm_conv_wgrad_tc_scratch_bytes.restype = C.c_uint64
-                L.msgm_conv_wgrad_tc_scratch_bytes.argtypes = [C.c_void_p] + [C.c_int32] * 8
-                L.msgm_conv_wgrad_tc.argtypes = [C.c_void_p] * 7 + [C.c_int32] * 14 + [C.c_void_p]
+                L.msgm_conv_wgrad_tc_scratch_bytes.argtypes = [C.c_void_p] + [C.c_int32] * 10
+                L.msgm_conv_wgrad_tc.argtypes = [C.c_void_p] * 8 + [C.c_int32] * 14 + [C.c_void_p]
                 L.msgm_gemm_f32.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 9 + [C.c_void_p]
                 L.msgm_premodule_pair.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]
                 L.msgm_sparse_ssm_loss.argtypes = [C.c_void_p, C.POINTER(SdeDesc)] + [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]

@@ -49,7 +49,7 @@ struct ConvTcParams {
   uint32_t mul_img, shr_img, mul_row, shr_row;  // magic numbers: n / (Hp Wp) and n / Wp for n < 2^31
   int tmem_cols;
   int fast;                   // 1: single fp16 product (hi planes only; ~1e-3 relative), 0: three split products (fp32-level)
-  const unsigned int* in_amax;  // NULL or max|input| as float bits: the input is staged times 2^k (max -> 2^12) and the
+  const unsigned int* in_amax;  // NULL or max|input| as float bits: the input is staged times 2^k (max -> [2^14, 2^15)) and the
                               // accumulators are scaled back: data gradients of cotangents far below the fp16 range
   TcFlags flags;
 };
@@ -58,14 +58,14 @@ __device__ __forceinline__ float silu_acc(float v) { return __fdividef(v, 1.0f +
 
 constexpr int CTC_STAGERS = 256;
 
-// power of two that brings max|x| to 2^12 (exact scaling; 1 when no range word is given)
+// power of two that brings max|x| into [2^14, 2^15) (exact scaling, the top of the fp16 range; 1 when no range word is given)
 __device__ __forceinline__ float ctc_range_scale(const unsigned int* amax_bits) {
   if (!amax_bits) return 1.0f;
   const float m = __uint_as_float(*amax_bits);
   if (!(m > 0.0f)) return 1.0f;
   int e;
   frexpf(m, &e);
-  return ldexpf(1.0f, max(-120, min(120, 12 - e)));
+  return ldexpf(1.0f, max(-120, min(120, 15 - e)));
 }
 
 // n / d for n < 2^31 with the precomputed (mul, shr) of find_divisor below (d == 1: mul = 0)

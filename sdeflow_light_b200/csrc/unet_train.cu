@@ -80,6 +80,25 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, 
   if ((threadIdx.x & 31) == 0 && m > 0.0f && isfinite(m)) atomicMax(out, __float_as_uint(m));
 }
 
+// max|.| of up to three tensors in one launch: tensor i goes to word out[slot[i]] (words zeroed by the caller's memset)
+struct AmaxMulti {
+  const float* x[3];
+  long long n[3];
+  int slot[3];
+};
+__global__ void __launch_bounds__(256) amax_multi_kernel(const __grid_constant__ AmaxMulti A, unsigned int* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (!A.x[t]) continue;
+    float m = 0.0f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A.n[t]; i += stride) m = fmaxf(m, fabsf(A.x[t][i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f && isfinite(m)) atomicMax(out + A.slot[t], __float_as_uint(m));
+  }
+}
+
 __device__ __forceinline__ float pow2_factor(const unsigned int* amax_bits, int target_exp, int inverse) {
   const float m = __uint_as_float(*amax_bits);
   if (!(m > 0.0f)) return 1.0f;
@@ -718,6 +737,22 @@ int msgm_amax(msgm_ctx* ctx, const float* x, int64_t n, float* amax_out, void* s
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   MSGM_CUDA_TRY(cudaMemsetAsync(amax_out, 0, sizeof(float), (cudaStream_t)stream));
   amax_kernel<<<ut_grid(ctx, n), 256, 0, (cudaStream_t)stream>>>(x, n, reinterpret_cast<unsigned int*>(amax_out));
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int msgm_amax2(msgm_ctx* ctx, const float* cot, int64_t n_cot, const float* x1, int64_t n1, const float* x2_or_null, int64_t n2,
+               float* amax_out2, void* stream) {
+  if (!ctx || !cot || !x1 || !amax_out2 || n_cot < 1 || n1 < 1 || (x2_or_null && n2 < 1)) return ut_invalid("msgm_amax2: bad argument");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  MSGM_CUDA_TRY(cudaMemsetAsync(amax_out2, 0, 2 * sizeof(float), (cudaStream_t)stream));
+  AmaxMulti A{};
+  A.x[0] = cot; A.n[0] = n_cot; A.slot[0] = 0;
+  A.x[1] = x1; A.n[1] = n1; A.slot[1] = 1;
+  A.x[2] = x2_or_null; A.n[2] = x2_or_null ? n2 : 0; A.slot[2] = 1;
+  amax_multi_kernel<<<ut_grid(ctx, std::max<long long>(n_cot, n1)), 256, 0, (cudaStream_t)stream>>>(
+      A, reinterpret_cast<unsigned int*>(amax_out2));
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

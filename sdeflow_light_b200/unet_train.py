@@ -136,8 +136,17 @@ def amax_of(g):
     return amax
 
 
+def amax_pair(cot, in1, in2=None):
+    """(max|cot|, max|[in1, in2]|) as two device words from ONE launch: the range words of a conv's data and weight gradients."""
+    h, L, st = _h(cot.device)
+    out = torch.empty(2, device=cot.device, dtype=torch.float32)
+    _lib.check(L.msgm_amax2(h, _lib.ptr(cot), cot.numel(), _lib.ptr(in1), in1.numel(), _lib.ptr(in2),
+                            0 if in2 is None else in2.numel(), _lib.ptr(out), st))
+    return out[0:1], out[1:2]
+
+
 def ranged(conv, g, amax=None, tc=True):
-    """``conv(g)`` evaluated on g times the power of two that brings max|g| to 2^12, result scaled back (exact).  The tensor-core
+    """``conv(g)`` evaluated on g times the power of two that brings max|g| into [2^14, 2^15), result scaled back (exact).  The tensor-core
     convs split operands into fp16 hi + lo; cotangents of the deep layers (~1e-7) would fall into the fp16 subnormal range.
     tc=True: ``conv`` is ONE tensor-core conv launch, which scales while staging and unscales in its epilogue
     (msgm_tc_range_scale, one-shot); otherwise (CUDA-core fall-back shapes: fp32, no scaling needed) the conv runs as is."""
@@ -156,20 +165,20 @@ def ranged(conv, g, amax=None, tc=True):
 WGRAD_TC = True  # weight gradients on tcgen05 (csrc/conv_wgrad_tc.cu) where the shape allows; False: fp32 CUDA-core kernel
 
 
-def conv_wgrad(cot, in1, in2, Wshape, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, amax=None):
+def conv_wgrad(cot, in1, in2, Wshape, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, amax=None, amax_in=None):
     """Weight gradient (tensor of shape Wshape = (Cout, Cw, ...)) of a conv over the channels [0, C1 + C2) of its input axis; any
     further input channels of the weight (the 1-D U-Net's folded embedding channels) are left for the caller to fill."""
     h, L, st = _h(cot.device)
     C1, C2 = in1.shape[1], 0 if in2 is None else in2.shape[1]
     N, Cout, Cw = cot.shape[0], cot.shape[1], Wshape[1]
     if WGRAD_TC and L.msgm_conv_wgrad_tc_ok(N, Cout, C1, C2, KH, KW, stride, pad, up, Hi, Wi):
-        if amax is None:
-            amax = amax_of(cot)
+        if amax is None or amax_in is None:  # both operands are range-scaled: an activation tensor of small magnitude would
+            amax, amax_in = amax_pair(cot, in1, in2)  # otherwise lose the low part of its fp16 split in the subnormals
         gW = torch.empty(Wshape, device=cot.device, dtype=torch.float32)  # the kernel overwrites its block
-        nb = L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, C1 + C2, KH, KW, up, Hi, Wi)
+        nb = L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, C1 + C2, KH, KW, stride, pad, up, Hi, Wi)
         scratch = torch.empty(nb, device=cot.device, dtype=torch.uint8)
         _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), _lib.ptr(amax),
-                                        _lib.ptr(scratch), N, Cout, C1, C2, Cw, 0, KH, KW, stride, pad, up, Hi, Wi, 0, st))
+                                        _lib.ptr(amax_in), _lib.ptr(scratch), N, Cout, C1, C2, Cw, 0, KH, KW, stride, pad, up, Hi, Wi, 0, st))
         return gW
     gW = torch.zeros(Wshape, device=cot.device, dtype=torch.float32)
     _lib.check(L.msgm_conv_wgrad(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), N, Cout, C1, C2, Cw, 0, KH, KW,
@@ -261,7 +270,7 @@ class Conv1dPair(torch.autograd.Function):
         Cin = C1 + C2
         Cout, Cw, K = W.shape
         gx1 = gx2 = gemb = None
-        amax = amax_of(g)
+        amax, amax_in = amax_pair(g, x1, x2)
         if ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1]):
             if stride == 1:   # data gradient = the same conv with flipped taps and swapped channel roles
                 gx = ranged(lambda t_: conv1d_raw(t_, None, W, Cin, 1, pad, dgrad=True), g, amax)
@@ -272,7 +281,7 @@ class Conv1dPair(torch.autograd.Function):
                 gx = ranged(lambda t_: convt1d_raw(t_, Wt, Lin), g, amax)
             gx1 = gx[:, :C1]
             gx2 = gx[:, C1:] if x2 is not None else None
-        gW = conv_wgrad(g, x1, x2, W.shape, 1, K, stride, pad, 1, 1, Lin, 1, Lout, amax)
+        gW = conv_wgrad(g, x1, x2, W.shape, 1, K, stride, pad, 1, 1, Lin, 1, Lout, amax, amax_in)
         if emb is not None:
             Cemb = Cw - Cin
             Eb = torch.empty((N, Cout, K), device=dev, dtype=torch.float32)  # cotangent of the folded table
@@ -308,9 +317,11 @@ class ConvT1dPair(torch.autograd.Function):
         g = g.contiguous()
         N, Cin, Lin = x.shape
         # data gradient: Conv1d(k4, s2, p1) with the weight read as (out = Cin, in = Cout), no flip
-        gx = ranged(lambda t_: conv1d_raw(t_, None, W, None, 2, 1), g) if ctx.needs_input_grad[0] else None
-        # gW[ci][co][k] = sum x[ci][p] g[co][2p - 1 + k]: a conv weight gradient with the roles swapped
-        gW = conv_wgrad(x, g, None, W.shape, 1, 4, 2, 1, 1, 1, ctx.Lout, 1, Lin)
+        amax_x, amax = amax_pair(x, g)
+        gx = ranged(lambda t_: conv1d_raw(t_, None, W, None, 2, 1), g, amax) if ctx.needs_input_grad[0] else None
+        # gW[ci][co][k] = sum x[ci][p] g[co][2p - 1 + k]: a conv weight gradient with the roles swapped: the kernel's "input"
+        # operand is the cotangent here, so the range scaling goes to that side
+        gW = conv_wgrad(x, g, None, W.shape, 1, 4, 2, 1, 1, 1, ctx.Lout, 1, Lin, amax=amax_x, amax_in=amax)
         gb = channel_sums(g, N // 2)
         return gx, gW, gb, None
 
@@ -503,14 +514,14 @@ class Conv2dPair(torch.autograd.Function):
         Cout, K = W.shape[0], W.shape[-1]
         Ho, Wo = g.shape[-2:]
         gx = None
-        amax = amax_of(g)
+        amax, amax_in = amax_pair(g, x)
         if ctx.needs_input_grad[0]:
             # data gradient: the same conv with flipped taps and swapped channel roles (image packed straight from W)
             src = resample2(g, 0) if stride == 2 else g     # stride 2: cotangent back on the input grid (zeros in between)
             gx = ranged(lambda t_: conv2d_raw(t_, W, None, 1, 1, dgrad=True), src, amax)
             if up == 2:                                      # adjoint of the nearest-neighbour upsampling
                 gx = resample2(gx, 1)
-        gW = conv_wgrad(g, x, None, W.shape, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo, amax)
+        gW = conv_wgrad(g, x, None, W.shape, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo, amax, amax_in)
         gb = channel_sums(g, N // 2) if has_b else None
         ge = sample_channel_sums(g) if has_e else None
         return gx, gW, gb, ge, None, None

@@ -267,34 +267,42 @@ def test_tensor_core_kernels_write_inside_their_outputs():
     assert intact(buf, out.numel()) and torch.isfinite(out).all()
 
 
-@pytest.mark.parametrize("N,Cout,C1,C2,KH,KW,up,Hs,Ws,cscale", [
-    (6, 32, 32, 0, 3, 3, 1, 12, 12, 1.0),        # the 32-channel full-resolution layers (M padded from 32 to 128 channels)
-    (4, 64, 64, 32, 3, 3, 1, 8, 8, 1e-7),        # decoder concat; cotangents far below the fp16 range (range scaling)
-    (3, 128, 256, 0, 3, 3, 1, 8, 8, 3e-5),       # two input-channel tiles of 128
-    (5, 64, 64, 0, 3, 3, 2, 7, 5, 1.0),          # Upsample conv: the input is read through the nearest x2 index
-    (4, 192, 64, 0, 1, 1, 1, 16, 16, 1e-3),      # qkv 1x1 conv, two output-channel tiles
-    (3, 128, 128, 64, 1, 1, 1, 9, 9, 1.0),       # skip_connection 1x1 on a concat: 192 input channels -> 2 tiles of 96
-    (7, 64, 32, 32, 1, 3, 1, 1, 125, 1.0),       # 1-D k3 conv on a concat
-    (2, 1, 32, 0, 1, 1, 1, 1, 1000, 1e-6),       # 1-D final pointwise conv: one output channel
-    (64, 32, 32, 0, 3, 3, 1, 32, 32, 1.0),       # full config-4 size of one layer: 74 k padded positions, many slices
+@pytest.mark.parametrize("N,Cout,C1,C2,KH,KW,up,Hs,Ws,cscale,stride", [
+    (6, 32, 32, 0, 3, 3, 1, 12, 12, 1.0, 1),     # the 32-channel full-resolution layers (M padded from 32 to 128 channels)
+    (4, 64, 64, 32, 3, 3, 1, 8, 8, 1e-7, 1),     # decoder concat; cotangents far below the fp16 range (range scaling)
+    (3, 128, 256, 0, 3, 3, 1, 8, 8, 3e-5, 1),    # two input-channel tiles of 128
+    (5, 64, 64, 0, 3, 3, 2, 7, 5, 1.0, 1),       # Upsample conv: the input is read through the nearest x2 index
+    (4, 192, 64, 0, 1, 1, 1, 16, 16, 1e-3, 1),   # qkv 1x1 conv, two output-channel tiles
+    (3, 128, 128, 64, 1, 1, 1, 9, 9, 1.0, 1),    # skip_connection 1x1 on a concat: 192 input channels -> 2 tiles of 96
+    (7, 64, 32, 32, 1, 3, 1, 1, 125, 1.0, 1),    # 1-D k3 conv on a concat
+    (2, 1, 32, 0, 1, 1, 1, 1, 1000, 1e-6, 1),    # 1-D final pointwise conv: one output channel
+    (64, 32, 32, 0, 3, 3, 1, 32, 32, 1.0, 1),    # full config-4 size of one layer: 74 k padded positions, many slices
+    (6, 64, 32, 0, 1, 4, 1, 1, 250, 1.0, 2),     # 1-D k4 stride-2 down conv: two phase windows (even / odd input columns)
+    (5, 128, 64, 0, 1, 4, 1, 1, 126, 1e-5, 2),   # the same structure as the ConvTranspose1d weight gradient (roles swapped)
+    (4, 64, 64, 0, 3, 3, 1, 16, 16, 1.0, 2),     # Downsample: 3x3 stride 2
+    (3, 128, 128, 0, 3, 3, 1, 8, 6, 1e-4, 2),
+    (12, 16, 16, 0, 1, 4, 1, 1, 32, 1.0, 2),     # tiny 1-D layers of the small fixture net
+    (12, 32, 32, 0, 1, 4, 1, 1, 16, 1.0, 2),
+    (12, 32, 16, 0, 1, 4, 1, 1, 16, 1.0, 2),
+    (12, 16, 16, 0, 1, 3, 1, 1, 32, 1.0, 1),
 ])
-def test_conv_wgrad_tc_matches_float64(N, Cout, C1, C2, KH, KW, up, Hs, Ws, cscale):
+def test_conv_wgrad_tc_matches_float64(N, Cout, C1, C2, KH, KW, up, Hs, Ws, cscale, stride):
     """csrc/conv_wgrad_tc.cu: the conv weight gradient as a tcgen05 product over positions (both operands MN-major from the
     staged tile layout, split fp16 x 3, power-of-two range scaling of the cotangent) against torch's float64 weight gradient;
     the result is accumulated into gW at a channel offset, and entries outside the written block must stay untouched."""
     torch.manual_seed(N * 1000 + Cout + C1 + KH)
     dev = torch.device(DEV)
     h, L = _lib.ctx(dev), _lib.lib()
-    Cin, pad = C1 + C2, KW // 2
-    assert L.msgm_conv_wgrad_tc_ok(N, Cout, C1, C2, KH, KW, 1, pad, up, Hs, Ws) == 1
+    Cin, pad = C1 + C2, (1 if KW == 4 else KW // 2)
+    assert L.msgm_conv_wgrad_tc_ok(N, Cout, C1, C2, KH, KW, stride, pad, up, Hs, Ws) == 1
     x1 = torch.randn(N, C1, Hs, Ws)
     x2 = torch.randn(N, C2, Hs, Ws) if C2 else None
-    cot = torch.randn(N, Cout, Hs * up, Ws * up) * cscale
     xin = x1 if x2 is None else torch.cat([x1, x2], 1)
     if up == 2:
         xin = F.interpolate(xin, scale_factor=2, mode="nearest")
     Wd = torch.zeros(Cout, Cin, KH, KW, dtype=torch.float64, requires_grad=True)
-    out = F.conv2d(xin.double(), Wd, padding=(KH // 2, KW // 2))
+    out = F.conv2d(xin.double(), Wd, stride=(1 if KH == 1 else stride, stride), padding=(KH // 2, pad))
+    cot = torch.randn(out.shape) * cscale
     (out * cot.double()).sum().backward()
     ref = Wd.grad
     coff, Cw = 3, Cin + 5                       # written block inside a wider weight tensor (the 1-D U-Net's folded channels)
@@ -304,13 +312,40 @@ def test_conv_wgrad_tc_matches_float64(N, Cout, C1, C2, KH, KW, up, Hs, Ws, csca
     x2d = None if x2 is None else x2.to(dev)
     amax = torch.empty(1, device=dev, dtype=torch.float32)
     _lib.check(L.msgm_amax(h, _lib.ptr(cd), cd.numel(), _lib.ptr(amax), _lib.stream_ptr(dev)))
-    scratch = torch.empty(L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, Cin, KH, KW, up, Hs, Ws), device=dev, dtype=torch.uint8)
-    _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cd), _lib.ptr(x1d), _lib.ptr(x2d), _lib.ptr(gW), _lib.ptr(amax), _lib.ptr(scratch),
-                                    N, Cout, C1, C2, Cw, coff, KH, KW, 1, pad, up, Hs, Ws, 1, _lib.stream_ptr(dev)))
+    scratch = torch.empty(L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, Cin, KH, KW, stride, pad, up, Hs, Ws), device=dev, dtype=torch.uint8)
+    _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cd), _lib.ptr(x1d), _lib.ptr(x2d), _lib.ptr(gW), _lib.ptr(amax), None, _lib.ptr(scratch),
+                                    N, Cout, C1, C2, Cw, coff, KH, KW, stride, pad, up, Hs, Ws, 1, _lib.stream_ptr(dev)))
     torch.cuda.synchronize()
     _lib.check_async(dev)
     got = gW.cpu()
     err = float((got[:, coff:coff + Cin].double() - g0[:, coff:coff + Cin].double() - ref).abs().max() / ref.abs().max())
     untouched = torch.equal(got[:, :coff], g0[:, :coff]) and torch.equal(got[:, coff + Cin:], g0[:, coff + Cin:])
     assert untouched
+    print(f"wgrad_tc N={N} {C1}+{C2}->{Cout} {KH}x{KW} s{stride} up{up} {Hs}x{Ws} cscale={cscale:g}: rel err {err:.2e}")
+    assert err < 2e-5, err
+
+
+def test_conv_wgrad_tc_range_scales_the_input_operand():
+    """ConvTranspose1d(k4, s2, p1) weight gradient = the stride-2 weight gradient with the two tensors' roles swapped: the kernel's
+    "input" operand is then the cotangent (~1e-7 in the deep layers), so the power-of-two range scaling must act on that side
+    (amax_in); without it the fp16 hi/lo split of the small operand loses its low part (observed 9e-3 on the fixture net)."""
+    torch.manual_seed(77)
+    dev = torch.device(DEV)
+    h, L = _lib.ctx(dev), _lib.lib()
+    N, Cx, Cg, Lin = 6, 32, 32, 40                      # x: (N, Cx, Lin) activations; g: (N, Cg, 2 Lin) cotangent of the up-sampled signal
+    x = torch.randn(N, Cx, 1, Lin)
+    g = torch.randn(N, Cg, 1, 2 * Lin) * 3e-7
+    Wd = torch.zeros(Cx, Cg, 1, 4, dtype=torch.float64, requires_grad=True)
+    out = F.conv2d(g.double(), Wd, stride=(1, 2), padding=(0, 1))     # (N, Cx, 1, Lin): gW[cx][cg][k] = sum x[cx][p] g[cg][2p - 1 + k]
+    (out * x.double()).sum().backward()
+    ref = Wd.grad
+    xd, gd = x.to(dev), g.to(dev)
+    amax = torch.empty(1, device=dev, dtype=torch.float32)
+    _lib.check(L.msgm_amax(h, _lib.ptr(gd), gd.numel(), _lib.ptr(amax), _lib.stream_ptr(dev)))
+    scratch = torch.empty(L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cx, Cg, 1, 4, 2, 1, 1, 1, 2 * Lin), device=dev, dtype=torch.uint8)
+    gW = torch.empty(Cx, Cg, 1, 4, device=dev)
+    _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(xd), _lib.ptr(gd), None, _lib.ptr(gW), None, _lib.ptr(amax), _lib.ptr(scratch),
+                                    N, Cx, Cg, 0, Cg, 0, 1, 4, 2, 1, 1, 1, 2 * Lin, 0, _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    err = float((gW.cpu().double() - ref).abs().max() / ref.abs().max())
     assert err < 2e-5, err

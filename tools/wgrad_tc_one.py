@@ -17,10 +17,10 @@ for (N, Cout, Cin, KH, KW, Hs, Ws) in ((64, 128, 128, 3, 3, 16, 16), (128, 128, 
     gW = torch.empty(Cout, Cin, KH, KW, device=dev)
     amax = torch.empty(1, device=dev)
     _lib.check(L.msgm_amax(h, _lib.ptr(cot), cot.numel(), _lib.ptr(amax), st))
-    scratch = torch.empty(L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, Cin, KH, KW, 1, Hs, Ws), device=dev, dtype=torch.uint8)
+    scratch = torch.empty(L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, Cin, KH, KW, 1, KW // 2, 1, Hs, Ws), device=dev, dtype=torch.uint8)
 
     def run():
-        _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cot), _lib.ptr(x), None, _lib.ptr(gW), _lib.ptr(amax), _lib.ptr(scratch), N, Cout,
+        _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cot), _lib.ptr(x), None, _lib.ptr(gW), _lib.ptr(amax), None, _lib.ptr(scratch), N, Cout,
                                         Cin, 0, Cin, 0, KH, KW, 1, KW // 2, 1, Hs, Ws, 0, st))
 
     for _ in range(3):

@@ -128,6 +128,26 @@ def test_tensor_core_layer_shape_queries_need_no_gpu():
     assert not _tc_shape_ok(32, 32, 0, 3, 2, 31, 32) and not _tc_shape_ok(64, 40, 24, 1, 1, 8, 8)
 
 
+def test_weight_gradient_shape_query_and_structs_need_no_gpu():
+    """Which convolutions of the U-Net training path get their weight gradient from the tcgen05 kernel (csrc/conv_wgrad_tc.cu) is a
+    pure host decision; the step-clock and product-group descriptors have the sizes the header's field lists give on LP64."""
+    L = _lib.lib()
+    ok = L.msgm_conv_wgrad_tc_ok  # (N, Cout, C1, C2, KH, KW, stride, pad, up, Hs, Ws)
+    assert ok(64, 128, 128, 0, 3, 3, 1, 1, 1, 16, 16) == 1          # ResBlock 3x3
+    assert ok(64, 64, 64, 32, 3, 3, 1, 1, 1, 32, 32) == 1           # decoder concat
+    assert ok(64, 64, 64, 0, 3, 3, 1, 1, 2, 8, 8) == 1              # Upsample conv (nearest x2 input)
+    assert ok(64, 192, 64, 0, 1, 1, 1, 0, 1, 16, 16) == 1           # qkv 1x1
+    assert ok(128, 64, 32, 32, 1, 3, 1, 1, 1, 1, 1000) == 1         # 1-D k3 on a concat
+    assert ok(128, 32, 32, 0, 1, 4, 2, 1, 1, 1, 1000) == 1          # 1-D k4 stride 2 (and ConvTranspose1d, roles swapped)
+    assert ok(64, 64, 64, 0, 3, 3, 2, 1, 1, 32, 32) == 1            # Downsample 3x3 stride 2
+    assert ok(128, 32, 1, 0, 1, 3, 1, 1, 1, 1, 1000) == 0           # first conv: one input channel -> CUDA-core kernel
+    assert ok(128, 32, 24, 8, 1, 3, 1, 1, 1, 1, 1000) == 0          # concat boundary not a multiple of 16
+    assert ok(64, 64, 64, 0, 3, 3, 2, 1, 1, 31, 32) == 0            # odd size at a stride-2 conv
+    assert ok(64, 64, 64, 0, 5, 5, 1, 2, 1, 16, 16) == 0
+    assert ctypes.sizeof(_lib.StepClock) == 6 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.GemmProblem) == 5 * 8 + 5 * 8 + 5 * 4 + 4 * 4 + 2 * 4 + 4 + 4 + 4  # 136 with tail padding
+
+
 def test_training_path_host_policies():
     """Host-side policies of the U-Net training path: which states the one-launch prologue covers, and the process-wide
     library precision switch (fp32 unless a net opts into TF32)."""

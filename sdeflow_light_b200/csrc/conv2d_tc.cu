@@ -57,6 +57,10 @@ struct ConvTcParams {
 __device__ __forceinline__ float silu_acc(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 constexpr int CTC_STAGERS = 256;
+// staged items (position x 8-channel k-chunk) whose global loads a stager thread keeps in flight together (1, 2, 3 or 6)
+#ifndef CTC_ILP
+#define CTC_ILP 2
+#endif
 
 // power of two that brings max|x| into [2^14, 2^15) (exact scaling, the top of the fp16 range; 1 when no range word is given)
 __device__ __forceinline__ float ctc_range_scale(const unsigned int* amax_bits) {
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(CTC_STAGERS + 32, 2) conv2d_tc_kernel(const __
       const float* xb = from1 ? P.x1 + (size_t)ch0 * HWs : P.x2 + (size_t)(ch0 - P.C1) * HWs;
       const size_t bstride = (size_t)(from1 ? P.C1 : P.C2) * HWs;
       // ILP items (position x 8-channel k-chunk) per step: 8 ILP independent global loads in flight per thread
-      constexpr int ILP = 2;
+      constexpr int ILP = CTC_ILP;
 #pragma unroll
       for (int i0 = 0; i0 < NI_MAX; i0 += ILP) {
         if (tid + i0 * CTC_STAGERS >= nitem) break;

@@ -458,6 +458,47 @@ int msgm_conv1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cw,
 int msgm_convt1d_tc_pack(msgm_ctx* ctx, const float* W, int32_t Cout, int32_t Cin, void* wimg, void* stream);
 int msgm_convt1d_tc(msgm_ctx* ctx, const float* x, const void* wimg, const float* bias, float* out, int32_t B, int32_t Cin,
                     int32_t Cout, int32_t Lin, int32_t Lout, int32_t fast, void* stream);
+/* msgm_emb_fold for up to 16 convs of one forward in ONE launch (the tables depend on the embedding vector only): entry i
+ * is msgm_emb_fold(W[i], emb, E[i], Cw[i], Coff[i], Cemb, Cout[i], K[i], B); results are bit-identical. */
+typedef struct {
+  const float* W[16]; float* E[16];
+  int32_t Cw[16], Coff[16], Cout[16], K[16];
+  int32_t n, Cemb, B;
+  const float* emb;
+} msgm_emb_fold_multi_desc;
+int msgm_emb_fold_multi(msgm_ctx* ctx, const msgm_emb_fold_multi_desc* desc, void* stream);
+/* The time MLP and (u != NULL) the log-radius MLP of UNet1D in one launch: out (B,E) = MLP_a(t) [+ MLP_b(u)], as
+ * msgm_embed_mlp(.., accumulate = 0) followed by msgm_embed_mlp(.., accumulate = 1), bit-identical; E <= 256. */
+int msgm_embed_mlp2(msgm_ctx* ctx, const float* t, const float* W1a, const float* b1a, const float* W2a, const float* b2a,
+                    const float* u, const float* W1b, const float* b1b, const float* W2b, const float* b2b, float* out,
+                    int32_t B, int32_t E, void* stream);
+/* ---- TMA-fed 1-D convs on activation "planes" (csrc/conv1d_tcp.cu; NNUnet1D.py:13-33,81-102,165-169) ------------------
+ * Between the convs of the 1-D U-Net (conv -> GELU -> conv -> GELU, no normalisation) an activation (B, C, L), C % 8 == 0,
+ * is kept in the tensor cores' operand format instead of fp32 NCL:
+ *     planes = fp16 [hi | lo][C / 8][R][8],  R = 2 * 640 + B (L + 3) rows of 16 bytes,
+ *     row of (b, l) = 640 + b (L + 3) + 1 + l,  value = hi + lo (fp16 split of the fp32 value, ~22 mantissa bits).
+ * Rows that hold no position (one left / two right of every signal, 640 guard rows at both ends) must be ZERO: allocate a
+ * planes buffer zero-filled (msgm_planes_bytes) -- the kernels below only ever write rows of real positions.
+ * msgm_conv1d_tcp is msgm_conv1d_tc / msgm_convt1d_tc with planes in and planes and / or fp32 NCL out: the operand tiles
+ * are fetched by cp.async.bulk, products and epilogues of consecutive tiles overlap (persistent CTAs, double-buffered
+ * TMEM accumulators).  K = 3 (stride 1, padding 1), K = 4 (stride 2, padding 1) or transposed = 1 (ConvTranspose1d k4 s2
+ * p1, image of msgm_convt1d_tc_pack, K = 3, Lout >= 2 Lin given; rows beyond 2 Lin stay zero = the reference's right
+ * padding).  x2 / E / bias / out_planes / out_f32 may be NULL (at least one output).  Shapes as msgm_conv1d_tc.
+ * A planes buffer must not be the input and the output of one call. */
+typedef struct {
+  const void* x1; const void* x2; const void* wimg; const float* bias; const float* E; void* out_planes; float* out_f32;
+  int32_t B, C1, C2, Cout, K, Lin, Lout, gelu, transposed;
+  int32_t fast; /* as in msgm_conv2d_tc_desc */
+} msgm_conv1d_tcp_desc;
+int64_t msgm_planes_bytes(int64_t B, int32_t C, int32_t L);
+int msgm_conv1d_tcp(msgm_ctx* ctx, const msgm_conv1d_tcp_desc* desc, void* stream);
+/* fp32 (B, C, L) -> planes (rows of real positions only) and back (hi + lo). */
+int msgm_planes_pack(msgm_ctx* ctx, const float* x, void* planes, int32_t B, int32_t C, int32_t L, void* stream);
+int msgm_planes_unpack(msgm_ctx* ctx, const void* planes, float* x, int32_t B, int32_t C, int32_t L, void* stream);
+/* First conv of the 1-D U-Net (one real input channel + folded embedding table E (B, Cout, 3), k3 p1, W (Cout, Cw, 3)
+ * of which input channel 0 is used, optional exact GELU), written as planes.  Cout % 8 == 0, Cout <= 128. */
+int msgm_conv1d_first_planes(msgm_ctx* ctx, const float* x, const float* W, int32_t Cw, const float* bias, const float* E,
+                             void* planes, int32_t B, int32_t Cout, int32_t L, int32_t gelu, void* stream);
 /* ss[b, c] = (rstd gamma_c, beta_c - mean rstd gamma_c) with the GroupNorm32 statistics of [x1, x2] (eps 1e-5). */
 int msgm_gn_scale_shift(msgm_ctx* ctx, const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t HW, int32_t G,
                         int32_t B, const float* gamma, const float* beta, float* ss, void* stream);

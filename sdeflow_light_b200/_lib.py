@@ -72,6 +72,17 @@ class Conv1dTcDesc(C.Structure):
                [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "stride", "Lin", "gelu", "fast")]
 
 
+class Conv1dTcpDesc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x1", "x2", "wimg", "bias", "E", "out_planes", "out_f32")] + \
+               [(n, C.c_int32) for n in ("B", "C1", "C2", "Cout", "K", "Lin", "Lout", "gelu", "transposed", "fast")]
+
+
+class EmbFoldMultiDesc(C.Structure):
+    _fields_ = [("W", C.c_void_p * 16), ("E", C.c_void_p * 16), ("Cw", C.c_int32 * 16), ("Coff", C.c_int32 * 16),
+                ("Cout", C.c_int32 * 16), ("K", C.c_int32 * 16), ("n", C.c_int32), ("Cemb", C.c_int32), ("B", C.c_int32),
+                ("emb", C.c_void_p)]
+
+
 _lib = None
 _lock = threading.Lock()
 _ctx = {}
@@ -90,7 +101,8 @@ SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy",
            "msgm_conv2d", "msgm_gn_stats", "msgm_emb_proj", "msgm_sincos_embed_mlp", "msgm_attention", "msgm_vort_pre",
            "msgm_vort_post", "msgm_conv2d_tc", "msgm_conv2d_tc_pack_bytes", "msgm_conv2d_tc_pack", "msgm_gn_scale_shift",
            "msgm_attention_tc_supported", "msgm_attention_tc", "msgm_conv1d_tc", "msgm_conv1d_tc_pack_bytes",
-           "msgm_conv1d_tc_pack", "msgm_convt1d_tc_pack", "msgm_convt1d_tc", "msgm_emb_proj_multi"]
+           "msgm_conv1d_tc_pack", "msgm_convt1d_tc_pack", "msgm_convt1d_tc", "msgm_emb_proj_multi",
+           "msgm_emb_fold_multi", "msgm_embed_mlp2", "msgm_planes_bytes", "msgm_conv1d_tcp", "msgm_planes_pack", "msgm_planes_unpack", "msgm_conv1d_first_planes"]
 
 
 def lib() -> C.CDLL:
@@ -136,6 +148,15 @@ def lib() -> C.CDLL:
                 L.msgm_mmd_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                             C.c_void_p]
                 L.msgm_conv1d.argtypes = [C.c_void_p, C.POINTER(Conv1dDesc), C.c_void_p]
+                L.msgm_emb_fold_multi.argtypes = [C.c_void_p, C.POINTER(EmbFoldMultiDesc), C.c_void_p]
+                L.msgm_embed_mlp2.argtypes = [C.c_void_p] * 12 + [C.c_int32, C.c_int32, C.c_void_p]
+                L.msgm_planes_bytes.restype = C.c_int64
+                L.msgm_planes_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+                L.msgm_conv1d_tcp.argtypes = [C.c_void_p, C.POINTER(Conv1dTcpDesc), C.c_void_p]
+                L.msgm_planes_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+                L.msgm_planes_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+                L.msgm_conv1d_first_planes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                                       C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
                 L.msgm_emb_fold.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 6 + [C.c_void_p]
                 L.msgm_convt1d_k4s2.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]
                 L.msgm_embed_mlp.argtypes = [C.c_void_p] * 7 + [C.c_int32] * 3 + [C.c_void_p]

@@ -64,6 +64,15 @@ int conv2d_tc(msgm_ctx*, const msgm_conv2d_tc_desc*, cudaStream_t);
 size_t conv2d_tc_pack_bytes(int, int, int);
 int conv2d_tc_pack(msgm_ctx*, const float*, int, int, int, int, void*, cudaStream_t, int dgrad = 0);
 int conv1d_tc(msgm_ctx*, const msgm_conv1d_tc_desc*, cudaStream_t);
+int conv1d_tcp(msgm_ctx*, const msgm_conv1d_tcp_desc*, cudaStream_t);
+int emb_fold_multi(msgm_ctx*, const msgm_emb_fold_multi_desc*, cudaStream_t);
+int embed_mlp2(msgm_ctx*, const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+               const float*, const float*, const float*, float*, int, int, cudaStream_t);
+int64_t planes_bytes(int64_t, int, int);
+int planes_pack(msgm_ctx*, const float*, void*, int, int, int, cudaStream_t);
+int planes_unpack(msgm_ctx*, const void*, float*, int, int, int, cudaStream_t);
+int conv1d_first_planes(msgm_ctx*, const float*, const float*, int, const float*, const float*, void*, int, int, int, int,
+                        cudaStream_t);
 int convt1d_tc_pack(msgm_ctx*, const float*, int, int, void*, cudaStream_t);
 int convt1d_tc(msgm_ctx*, const float*, const void*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int gn_scale_shift(msgm_ctx*, const float*, int, const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
@@ -511,6 +520,71 @@ int msgm_conv1d_tc(msgm_ctx* ctx, const msgm_conv1d_tc_desc* D, void* stream) {
   if (D->B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return conv1d_tc(ctx, D, (cudaStream_t)stream);
+}
+
+int msgm_emb_fold_multi(msgm_ctx* ctx, const msgm_emb_fold_multi_desc* D, void* stream) {
+  if (!ctx || !D || !D->emb) return invalid("msgm_emb_fold_multi: NULL argument");
+  if (D->n < 0 || D->n > 16 || D->B < 0 || D->Cemb < 1 || D->Cemb > 1024) return invalid("msgm_emb_fold_multi: n <= 16, Cemb in 1..1024");
+  for (int i = 0; i < D->n; ++i)
+    if (!D->W[i] || !D->E[i] || D->Cout[i] < 1 || D->K[i] < 1 || D->Coff[i] < 0 || D->Cw[i] < D->Coff[i] + D->Cemb)
+      return invalid("msgm_emb_fold_multi: bad layer entry");
+  if (D->n == 0 || D->B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return emb_fold_multi(ctx, D, (cudaStream_t)stream);
+}
+
+int msgm_embed_mlp2(msgm_ctx* ctx, const float* t, const float* W1a, const float* b1a, const float* W2a, const float* b2a,
+                    const float* u, const float* W1b, const float* b1b, const float* W2b, const float* b2b, float* out,
+                    int32_t B, int32_t E, void* stream) {
+  if (!ctx || !t || !W1a || !b1a || !W2a || !b2a || !out || (u && (!W1b || !b1b || !W2b || !b2b)))
+    return invalid("msgm_embed_mlp2: NULL argument");
+  if (B < 0 || E < 1 || E > 256) return invalid("msgm_embed_mlp2: E in 1..256");
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return embed_mlp2(ctx, t, W1a, b1a, W2a, b2a, u, W1b, b1b, W2b, b2b, out, B, E, (cudaStream_t)stream);
+}
+
+int64_t msgm_planes_bytes(int64_t B, int32_t C, int32_t L) {
+  if (B < 0 || C < 8 || C % 8 != 0 || L < 1) return -1;
+  return planes_bytes(B, C, L);
+}
+
+int msgm_conv1d_tcp(msgm_ctx* ctx, const msgm_conv1d_tcp_desc* D, void* stream) {
+  if (!ctx || !D || !D->x1 || !D->wimg || (!D->out_planes && !D->out_f32)) return invalid("msgm_conv1d_tcp: NULL argument");
+  const int Cin = D->C1 + (D->x2 ? D->C2 : 0);
+  const bool shape_ok = D->transposed
+                            ? (D->K == 3 && Cin % 16 == 0 && D->C1 % 16 == 0 && D->Cout % 16 == 0 && D->Cout > 0 && D->Lout >= 2 * D->Lin)
+                            : (conv1d_tc_shape_ok(D->Cout, Cin, D->C1, D->K) && (D->K == 3 || (D->K == 4 && D->Lin >= 2)));
+  if (!shape_ok || D->Lin < 1 || D->B < 0 || Cin <= 0)
+    return invalid("msgm_conv1d_tcp: unsupported shape (k3 stride 1, k4 stride 2 or transposed k4 s2; Cin % 16 == 0, C1 % 16 == 0, Cout % 32 == 0)");
+  if (D->out_planes && (D->out_planes == D->x1 || (D->x2 && D->out_planes == D->x2)))
+    return invalid("msgm_conv1d_tcp: the output planes alias an input");
+  if (D->B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv1d_tcp(ctx, D, (cudaStream_t)stream);
+}
+
+int msgm_planes_pack(msgm_ctx* ctx, const float* x, void* planes, int32_t B, int32_t C, int32_t L, void* stream) {
+  if (!ctx || !x || !planes) return invalid("msgm_planes_pack: NULL argument");
+  if (B < 0 || C < 8 || C % 8 != 0 || L < 1) return invalid("msgm_planes_pack: C % 8 == 0, L >= 1");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return planes_pack(ctx, x, planes, B, C, L, (cudaStream_t)stream);
+}
+
+int msgm_planes_unpack(msgm_ctx* ctx, const void* planes, float* x, int32_t B, int32_t C, int32_t L, void* stream) {
+  if (!ctx || !x || !planes) return invalid("msgm_planes_unpack: NULL argument");
+  if (B < 0 || C < 8 || C % 8 != 0 || L < 1) return invalid("msgm_planes_unpack: C % 8 == 0, L >= 1");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return planes_unpack(ctx, planes, x, B, C, L, (cudaStream_t)stream);
+}
+
+int msgm_conv1d_first_planes(msgm_ctx* ctx, const float* x, const float* W, int32_t Cw, const float* bias, const float* E,
+                             void* planes, int32_t B, int32_t Cout, int32_t L, int32_t gelu, void* stream) {
+  if (!ctx || !x || !W || !planes) return invalid("msgm_conv1d_first_planes: NULL argument");
+  if (B < 0 || Cout < 8 || Cout % 8 != 0 || Cout > 128 || L < 1 || Cw < 1)
+    return invalid("msgm_conv1d_first_planes: Cout % 8 == 0, Cout <= 128");
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return conv1d_first_planes(ctx, x, W, Cw, bias, E, planes, B, Cout, L, gelu, (cudaStream_t)stream);
 }
 
 int64_t msgm_conv1d_tc_pack_bytes(int32_t Cout, int32_t Cin, int32_t K) {

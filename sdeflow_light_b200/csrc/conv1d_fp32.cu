@@ -179,6 +179,37 @@ __global__ void __launch_bounds__(256) emb_fold_kernel(const float* __restrict__
   (void)run;
 }
 
+// Every embedding table of one forward in ONE launch (grid.z = layer): the tables depend on the embedding vector only, so
+// the seven launches of a forward (one per ConvBlock1D) collapse into one that runs ahead of the first conv.
+__global__ void __launch_bounds__(256) emb_fold_multi_kernel(const __grid_constant__ msgm_emb_fold_multi_desc D) {
+  extern __shared__ float semb[];  // [EF_S][Cemb]
+  const int z = blockIdx.z, Cemb = D.Cemb, B = D.B;
+  const float* __restrict__ W = D.W[z];
+  float* __restrict__ E = D.E[z];
+  const int Cw = D.Cw[z], Coff = D.Coff[z], Cout = D.Cout[z], K = D.K[z];
+  const int b0 = blockIdx.x * EF_S, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < EF_S * Cemb; e += 256) semb[e] = b0 + e / Cemb < B ? D.emb[(size_t)b0 * Cemb + e] : 0.0f;
+  __syncthreads();
+  for (int co = blockIdx.y * 8 + warp; co < Cout; co += 8 * gridDim.y) {
+    const float* w = W + ((size_t)co * Cw + Coff) * K;
+    for (int k = 0; k < K; ++k) {
+      float acc[EF_S] = {};
+      for (int ci = lane; ci < Cemb; ci += 32) {
+        const float wv = __ldg(w + ci * K + k);
+#pragma unroll
+        for (int sidx = 0; sidx < EF_S; ++sidx) acc[sidx] = fmaf(wv, semb[sidx * Cemb + ci], acc[sidx]);
+      }
+#pragma unroll
+      for (int sidx = 0; sidx < EF_S; ++sidx) {
+        float v = acc[sidx];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && b0 + sidx < B) E[((size_t)(b0 + sidx) * Cout + co) * K + k] = v;
+      }
+    }
+  }
+}
+
 // ConvTranspose1d(k=4, s=2, p=1): out[b,co,l] = bias[co] + sum_ci sum_{k: (l+1-k) even, 0 <= (l+1-k)/2 < Lin} W[ci,co,k] x[b,ci,(l+1-k)/2]
 // Positions l >= 2*Lin (right zero padding up to Lout, NNUnet1D.py:168-169) are written as 0.
 __global__ void __launch_bounds__(256) convt1d_kernel(const float* __restrict__ x, const float* __restrict__ W,
@@ -243,6 +274,63 @@ __global__ void __launch_bounds__(256) embed_mlp_kernel(const float* __restrict_
   }
 }
 
+// Both embedding MLPs of a forward in one launch: out[b,:] = MLP_a(t[b]) (+ MLP_b(u[b]) when u != NULL), each
+// Linear(1,E) -> GELU -> Linear(E,E) (NNUnet1D.py:52-68,132-141).  CTA = 8 samples: W2 is read ONCE per CTA in coalesced
+// [E][16] tiles through shared memory (embed_mlp_kernel reads it once per sample, a row per thread); the sums run in the
+// same order as embed_mlp_kernel's, so the result is bit-identical to two of its launches.  E <= 256.
+constexpr int EM_S = 8, EM_T = 16;
+__global__ void __launch_bounds__(256) embed_mlp2_kernel(const float* __restrict__ t, const float* __restrict__ W1a,
+                                                         const float* __restrict__ b1a, const float* __restrict__ W2a,
+                                                         const float* __restrict__ b2a, const float* __restrict__ u,
+                                                         const float* __restrict__ W1b, const float* __restrict__ b1b,
+                                                         const float* __restrict__ W2b, const float* __restrict__ b2b,
+                                                         float* __restrict__ out, int B, int E) {
+  __shared__ float h[EM_S][256];
+  __shared__ float sw[256][EM_T + 1];
+  const int b0 = blockIdx.x * EM_S, tid = threadIdx.x;
+  float tot[EM_S];
+#pragma unroll
+  for (int si = 0; si < EM_S; ++si) tot[si] = 0.0f;
+  for (int m = 0; m < (u ? 2 : 1); ++m) {
+    const float* val = m ? u : t;
+    const float* W1 = m ? W1b : W1a;
+    const float* b1 = m ? b1b : b1a;
+    const float* W2 = m ? W2b : W2a;
+    const float* b2 = m ? b2b : b2a;
+    __syncthreads();
+    if (tid < E) {
+#pragma unroll
+      for (int si = 0; si < EM_S; ++si) h[si][tid] = b0 + si < B ? gelu_erf(fmaf(W1[tid], val[b0 + si], b1[tid])) : 0.0f;
+    }
+    float acc[EM_S];
+#pragma unroll
+    for (int si = 0; si < EM_S; ++si) acc[si] = tid < E ? b2[tid] : 0.0f;
+    for (int j0 = 0; j0 < E; j0 += EM_T) {
+      __syncthreads();
+      for (int e = tid; e < E * EM_T; e += 256) {
+        const int r = e / EM_T, c = e % EM_T;
+        sw[r][c] = j0 + c < E ? W2[(size_t)r * E + j0 + c] : 0.0f;
+      }
+      __syncthreads();
+      if (tid < E) {
+        const int jn = min(EM_T, E - j0);
+        for (int jj = 0; jj < jn; ++jj) {
+          const float w = sw[tid][jj];
+#pragma unroll
+          for (int si = 0; si < EM_S; ++si) acc[si] = fmaf(w, h[si][j0 + jj], acc[si]);
+        }
+      }
+    }
+#pragma unroll
+    for (int si = 0; si < EM_S; ++si) tot[si] = m ? tot[si] + acc[si] : acc[si];
+  }
+  if (tid < E) {
+#pragma unroll
+    for (int si = 0; si < EM_S; ++si)
+      if (b0 + si < B) out[(size_t)(b0 + si) * E + tid] = tot[si];
+  }
+}
+
 // x -> x / (|x| + eps) * sqrt(L), lognorm = log(|x| + eps)   (NN.py:64-70 + NNUnet1D.py:139)
 __global__ void __launch_bounds__(256) normalize_log_radius_kernel(const float* __restrict__ x, float* __restrict__ xn,
                                                                    float* __restrict__ lognorm, int L) {
@@ -293,6 +381,25 @@ int emb_fold(msgm_ctx* ctx, const float* W, const float* emb, float* E, int Cw, 
   const int gy = std::max(1, std::min((Cout + 7) / 8, 4));
   emb_fold_kernel<<<dim3((B + EF_S - 1) / EF_S, gy), 256, sizeof(float) * EF_S * Cemb, stream>>>(W, emb, E, Cw, Coff, Cemb, Cout,
                                                                                              K, B);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int emb_fold_multi(msgm_ctx* ctx, const msgm_emb_fold_multi_desc* D, cudaStream_t stream) {
+  int cmax = 1;
+  for (int i = 0; i < D->n; ++i) cmax = std::max(cmax, D->Cout[i]);
+  const int gy = std::max(1, std::min((cmax + 7) / 8, 4));
+  emb_fold_multi_kernel<<<dim3((D->B + EF_S - 1) / EF_S, gy, D->n), 256, sizeof(float) * EF_S * D->Cemb, stream>>>(*D);
+  ctx->launches += 1;
+  MSGM_CUDA_TRY(cudaGetLastError());
+  return MSGM_OK;
+}
+
+int embed_mlp2(msgm_ctx* ctx, const float* t, const float* W1a, const float* b1a, const float* W2a, const float* b2a,
+               const float* u, const float* W1b, const float* b1b, const float* W2b, const float* b2b, float* out, int B, int E,
+               cudaStream_t stream) {
+  embed_mlp2_kernel<<<(B + EM_S - 1) / EM_S, 256, 0, stream>>>(t, W1a, b1a, W2a, b2a, u, W1b, b1b, W2b, b2b, out, B, E);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

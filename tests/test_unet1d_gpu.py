@@ -569,12 +569,12 @@ def test_step_graph_is_the_default_for_long_calls():
     l0 = P._lib.launch_count(DEV)
     got = P.rk4_stratonovich_sampler(gen, x0, N, **kw).clone()
     n_graph = P._lib.launch_count(DEV) - l0
-    GS.STEP_GRAPH = False
+    GS.STEP_GRAPH, net.cuda_graph = False, False  # reference: every kernel of every step launched from the host
     try:
         l0 = P._lib.launch_count(DEV)
         ref = P.rk4_stratonovich_sampler(gen, x0, N, **kw).clone()
         n_eager = P._lib.launch_count(DEV) - l0
     finally:
-        GS.STEP_GRAPH = True
+        GS.STEP_GRAPH, net.cuda_graph = True, True
     assert torch.isfinite(got).all() and torch.equal(got, ref)
     assert n_graph * 20 < n_eager, (n_graph, n_eager)  # launches are counted on the host: two bodies (eager step 0 + capture)

@@ -316,6 +316,7 @@ def time_unet_forward(P, dev):
             ("vorticity_unet2d_32x32_base32", P.VorticityUNet(32, (1, 2, 4), 2, premodule="NormalizeLogRadius", in_space=32,
                                                               attention_resolutions=(2, 4), flatten_order="F").to(dev), 128,
              1024, 1.204)]
+    large = {"unet1d_L1000_base32": 1024, "vorticity_unet2d_32x32_base32": 512}  # second, larger particle batch per net
     with torch.no_grad():
         for name, net, B, d, gflop in nets:
             for p_ in net.parameters():  # the reference zero-initialises some convs: give them weights so that work is real
@@ -330,9 +331,13 @@ def time_unet_forward(P, dev):
                 ref = net._forward(x, t)
                 torch.backends.cuda.matmul.allow_tf32 = prev
             err = float((net(x, t) - ref).abs().max() / ref.abs().max())
+            xl, tl = torch.randn(large[name], d, device=dev), torch.rand(large[name], device=dev)
+            ms_l = timeit(lambda: net(xl, tl), 5)
             out["runs"].append({"net": name, "batch": B, "ms_per_forward": ms, "value": B / ms * 1e3,
                                 "algorithmic_tflops": gflop * B / ms, "torch_fp32_ms": ms_t,
-                                "rel_diff_vs_torch_fp32": err})
+                                "rel_diff_vs_torch_fp32": err,
+                                "large_batch": {"batch": large[name], "ms_per_forward": ms_l, "value": large[name] / ms_l * 1e3,
+                                                "algorithmic_tflops": gflop * large[name] / ms_l}})
     # (i) RK4 reverse sampling of BASELINE configs 3 / 4 through the drop-in sampler (sparse multiplicative SDE, norm correction,
     # in-kernel Philox): one CUDA graph per step (4 net evaluations + 4 stage updates), against SURVEY 8d's tensor bounds;
     # (ii) one SSM training iteration of the same nets on the hand-written training path (unet_train.py: forward-mode pairs on the
@@ -353,6 +358,13 @@ def time_unet_forward(P, dev):
             entry = {"sampling_batch": Bs, "sampling_steps": nst, "sampling_ms_per_call": ms_s,
                      "sampling_particle_steps_per_sec": Bs * nst / ms_s * 1e3,
                      "sampling_frac_of_tensor_bound": Bs * nst / ms_s * 1e3 / bounds[name]}
+            Bl = large[name]
+            xl0 = gen.latent_sample(Bl, d)
+            ms_l = timeit(lambda: P.rk4_stratonovich_sampler(gen, xl0, nst, keep_all_samples=False, norm_correction=True,
+                                                             seed=1, device_out=True), 2)
+            entry["sampling_large_batch"] = {"batch": Bl, "steps": nst, "ms_per_call": ms_l,
+                                             "particle_steps_per_sec": Bl * nst / ms_l * 1e3,
+                                             "frac_of_tensor_bound": Bl * nst / ms_l * 1e3 / bounds[name]}
             xs = data[:Bt].to(dev)
             entry["train_path"] = "hand-written kernels" if unet_train.supported(gen, xs) else "library autograd"
             step = GraphedSsmStep(gen, (Bt, d), lr=1e-4)

@@ -30,6 +30,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "msgm_common.cuh"
 #include "tc_ptx.cuh"
@@ -63,6 +64,19 @@ struct TcpParams {
   uint32_t mul_row, shr_row;               // n / Wp for n < 2^31
   int tmem_cols;
   TcFlags flags;
+  long long* prof;  // NULL, or 24 cycle counters of CTA 0 (MSGM_TCP_PROF=1; msgm_debug_counters): [0] epilogue warp 0 waits for
+                    // an accumulator, [1] drains it; [8] MMA warp waits for a free accumulator, [9] for a stage, [10] issues;
+                    // [16] producer waits for a free stage, [17] issues copies; [2] / [11] / [18] = tiles / chunks seen
+};
+
+struct TcpProf {
+  long long* c;
+  long long t;
+  __device__ __forceinline__ void start() { if (c) t = clock64(); }
+  __device__ __forceinline__ void tick(int slot) {
+    if (c) { const long long n = clock64(); c[slot] += n - t; t = n; }
+  }
+  __device__ __forceinline__ void count(int slot) { if (c) c[slot] += 1; }
 };
 
 __device__ __forceinline__ int tcp_div(int n, uint32_t mul, uint32_t shr) { return (int)(__umulhi((uint32_t)n, mul) >> shr); }
@@ -87,6 +101,58 @@ __device__ __forceinline__ float gelu_rational(float v) {
   q = fmaf(q, x2, -1.42647390514189e-02f);
   const float e = __fdividef(p * x, q), hv = 0.5f * v;
   return fmaf(hv, e, hv);
+}
+
+// The same function on two values with the packed fp32 instructions of sm_100 (FFMA2 / FMUL2: two IEEE fp32 operations per
+// issue slot, bit-identical to the scalar form): the epilogue is issue-bound, and the two Horner chains are 11 of its ~28
+// instructions per value.
+#ifndef MSGM_TCP_GELU2
+#define MSGM_TCP_GELU2 1
+#endif
+__device__ __forceinline__ unsigned long long f2pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2dup(float c) { return f2pack(c, c); }
+__device__ __forceinline__ unsigned long long f2fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void gelu_rational_x2(float& v0, float& v1) {
+#if MSGM_TCP_GELU2
+  const float x0 = fminf(fmaxf(v0 * 0.70710678118654752440f, -4.0f), 4.0f);
+  const float x1 = fminf(fmaxf(v1 * 0.70710678118654752440f, -4.0f), 4.0f);
+  const unsigned long long x = f2pack(x0, x1), x2 = f2mul(x, x);
+  unsigned long long p = f2dup(-2.72614225801306e-10f);
+  p = f2fma(p, x2, f2dup(2.77068142495902e-08f));
+  p = f2fma(p, x2, f2dup(-2.10102402082508e-06f));
+  p = f2fma(p, x2, f2dup(-5.69250639462346e-05f));
+  p = f2fma(p, x2, f2dup(-7.34990630326855e-04f));
+  p = f2fma(p, x2, f2dup(-2.95459980854025e-03f));
+  p = f2fma(p, x2, f2dup(-1.60960333262415e-02f));
+  unsigned long long q = f2dup(-1.45660718464996e-05f);
+  q = f2fma(q, x2, f2dup(-2.13374055278905e-04f));
+  q = f2fma(q, x2, f2dup(-1.68282697438203e-03f));
+  q = f2fma(q, x2, f2dup(-7.37332916720468e-03f));
+  q = f2fma(q, x2, f2dup(-1.42647390514189e-02f));
+  p = f2mul(p, x);
+  float p0, p1, q0, q1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(p));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(q));
+  const float e0 = __fdividef(p0, q0), e1 = __fdividef(p1, q1), h0 = 0.5f * v0, h1 = 0.5f * v1;
+  v0 = fmaf(h0, e0, h0);
+  v1 = fmaf(h1, e1, h1);
+#else
+  v0 = gelu_rational(v0);
+  v1 = gelu_rational(v1);
+#endif
 }
 
 template <int NOUT, int NT, bool CONST_BASE>
@@ -131,33 +197,57 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) conv1d_tcp_kernel(const __grid
 
   if (warp == TCP_EPI_WARPS) {
     // ================================================= producer ===================================================
-    if (lane == 0) {
+    // Lane 0 waits for the stage and posts the byte count; lanes 0..4 then issue one bulk copy each (a single thread needs
+    // ~700 clk to issue the five copies of a chunk, measured with MSGM_TCP_PROF: more than the chunk's MMAs take in the
+    // single-product mode).  MSGM_TCP_PROD5=0 keeps everything on lane 0.
+#ifndef MSGM_TCP_PROD5
+#define MSGM_TCP_PROD5 1
+#endif
+    {
       int s = 0;
       uint32_t ph = 1;  // a fresh barrier passes a wait on parity 1: the first S stages are free
       bool ok = true;
       const size_t G1 = (size_t)(P.C1 >> 3) * (size_t)P.Rin * 16, G2 = (size_t)(P.C2 >> 3) * (size_t)P.Rin * 16;  // hi -> lo plane
+      TcpProf pf{(P.prof && blockIdx.x == 0 && lane == 0) ? P.prof + 16 : nullptr, 0};
+      pf.start();
       for (long long tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x) {
         const long long m = tile / P.ntile_n;
         const int n = (int)(tile - m * P.ntile_n);
         const long long row0 = PL_GUARD + m * (128LL * MB) - PL_HALO;
         for (int k = 0; k < P.NC && ok; ++k) {
-          ok = mbar_wait(bar_empty + s, ph, P.flags);
+          if (lane == 0) {
+            ok = mbar_wait(bar_empty + s, ph, P.flags);
+            if (ok) mbar_expect_tx(bar_full + s, (uint32_t)(ASTAGE + WSTAGE));
+          }
+          ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
           if (!ok) break;
+          pf.tick(0);
           unsigned char* dst = stage0 + (size_t)s * STAGE;
-          mbar_expect_tx(bar_full + s, (uint32_t)(ASTAGE + WSTAGE));
           const int ch0 = k * 16;
           const bool from1 = ch0 < P.C1;
           const unsigned char* xb = from1 ? P.x1 : P.x2;
           const int kc0 = (from1 ? ch0 : ch0 - P.C1) >> 3;
           const size_t glo = from1 ? G1 : G2;
           const unsigned char* src = xb + ((size_t)kc0 * (size_t)P.Rin + (size_t)row0) * 16;
-          tma_bulk_g2s(dst, src, (uint32_t)PS, bar_full + s);
-          tma_bulk_g2s(dst + PS, src + (size_t)P.Rin * 16, (uint32_t)PS, bar_full + s);
-          if (!P.fast) {
-            tma_bulk_g2s(dst + 2 * PS, src + glo, (uint32_t)PS, bar_full + s);
-            tma_bulk_g2s(dst + 3 * PS, src + glo + (size_t)P.Rin * 16, (uint32_t)PS, bar_full + s);
+          // copy i of the chunk: 0, 1 = hi planes of the two 8-channel groups, 2, 3 = their lo planes, 4 = weights
+          const int nA = P.fast ? 2 : 4;
+#if MSGM_TCP_PROD5
+          if (lane < nA) {
+            tma_bulk_g2s(dst + lane * PS, src + (size_t)(lane >> 1) * glo + (size_t)(lane & 1) * (size_t)P.Rin * 16, (uint32_t)PS,
+                         bar_full + s);
+          } else if (lane == 4) {
+            tma_bulk_g2s(dst + ASTAGE, P.wimg + ((size_t)n * P.NC + k) * WCHUNK, (uint32_t)WSTAGE, bar_full + s);
           }
-          tma_bulk_g2s(dst + ASTAGE, P.wimg + ((size_t)n * P.NC + k) * WCHUNK, (uint32_t)WSTAGE, bar_full + s);
+#else
+          if (lane == 0) {
+            for (int i = 0; i < nA; ++i)
+              tma_bulk_g2s(dst + i * PS, src + (size_t)(i >> 1) * glo + (size_t)(i & 1) * (size_t)P.Rin * 16, (uint32_t)PS,
+                           bar_full + s);
+            tma_bulk_g2s(dst + ASTAGE, P.wimg + ((size_t)n * P.NC + k) * WCHUNK, (uint32_t)WSTAGE, bar_full + s);
+          }
+#endif
+          pf.tick(1);
+          pf.count(2);
           if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
@@ -174,15 +264,19 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) conv1d_tcp_kernel(const __grid
       uint32_t ph = 0;
       bool ok = true;
       int tl = 0;
+      TcpProf pf{(P.prof && blockIdx.x == 0 && lane == 0) ? P.prof + 8 : nullptr, 0};
+      pf.start();
       for (long long tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, ++tl) {
         const int ab = tl & 1;
         ok = __all_sync(0xffffffffu, mbar_wait(bar_acce + ab, (uint32_t)(((tl >> 1) & 1) ^ 1), P.flags));
         if (!ok) break;
         tc_fence_after();
+        pf.tick(0);
         const uint32_t dbase = tbase + (uint32_t)(ab * MB * NOUT);
         for (int k = 0; k < P.NC; ++k) {
           if (!__all_sync(0xffffffffu, mbar_wait(bar_full + s, ph, P.flags))) { ok = false; break; }
           tc_fence_after();
+          pf.tick(1);
           // descriptors: only the 14-bit start-address field (16-byte units) moves between the MMAs of a chunk
           const uint32_t a_base = sbase + 256u + (uint32_t)(s * STAGE);
           const uint64_t dA0 = umma_desc(a_base + (uint32_t)((PL_HALO - 1) * 16), PS, 128);  // tap 0 of block 0, hi planes
@@ -203,6 +297,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) conv1d_tcp_kernel(const __grid
             }
           }
           umma_commit(bar_empty + s, 0);
+          pf.tick(2);
+          pf.count(3);
           if (++s == S) { s = 0; ph ^= 1u; }
         }
         if (ok) umma_commit(bar_accf + ab, 0);
@@ -216,12 +312,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) conv1d_tcp_kernel(const __grid
     bool ok = true;
     int tl = 0;
     const size_t olo = (size_t)(P.CoutT >> 3) * (size_t)P.Rout * 16;  // hi -> lo plane of the output
+    TcpProf pf{(P.prof && blockIdx.x == 0 && tid == 0) ? P.prof : nullptr, 0};
+    pf.start();
     for (long long tile = blockIdx.x; tile < P.ntiles && ok; tile += gridDim.x, ++tl) {
       const int ab = tl & 1;
       const long long m = tile / P.ntile_n;
       const int co0 = (int)(tile - m * P.ntile_n) * NOUT;
       ok = mbar_wait(bar_accf + ab, (uint32_t)((tl >> 1) & 1), P.flags);
       tc_fence_after();
+      pf.tick(0);
       for (int mb = mb0; mb < MB; mb += 2) {
         const long long p = m * (128LL * MB) + mb * 128 + q4 * 32 + lane;
         bool valid = ok && p < P.total;
@@ -273,7 +372,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) conv1d_tcp_kernel(const __grid
           }
           if (P.gelu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = gelu_rational(v[j]);
+            for (int j = 0; j < 16; j += 2) gelu_rational_x2(v[j], v[j + 1]);
           }
           if (P.outf) {
             float* op = P.outf + ((size_t)b * P.CoutT + cb) * P.Lout + oc;
@@ -298,6 +397,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) conv1d_tcp_kernel(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce + ab);
+      pf.tick(1);
+      pf.count(2);
     }
   }
 
@@ -481,6 +582,8 @@ int conv1d_tcp(msgm_ctx* ctx, const msgm_conv1d_tcp_desc* D, cudaStream_t stream
   P.Wpo = P.Lout + PL_PAD;
   P.Rout = planes_rows(D->B, P.Lout);
   P.flags = next_tc_flags(ctx);
+  P.prof = std::getenv("MSGM_TCP_PROF") ? reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(ctx->ws) + 64) : nullptr;
+  if (P.prof) MSGM_CUDA_TRY(cudaMemsetAsync(P.prof, 0, 192, stream));
   return (D->K == 4 && !D->transposed) ? launch_tcp_n<4>(ctx, P, stream) : launch_tcp_n<3>(ctx, P, stream);
 }
 

@@ -468,7 +468,8 @@ typedef struct {
 } msgm_emb_fold_multi_desc;
 int msgm_emb_fold_multi(msgm_ctx* ctx, const msgm_emb_fold_multi_desc* desc, void* stream);
 /* The time MLP and (u != NULL) the log-radius MLP of UNet1D in one launch: out (B,E) = MLP_a(t) [+ MLP_b(u)], as
- * msgm_embed_mlp(.., accumulate = 0) followed by msgm_embed_mlp(.., accumulate = 1), bit-identical; E <= 256. */
+ * msgm_embed_mlp(.., accumulate = 0) followed by msgm_embed_mlp(.., accumulate = 1), bit-identical; E <= 224 (the whole
+ * second-layer weight sits in shared memory). */
 int msgm_embed_mlp2(msgm_ctx* ctx, const float* t, const float* W1a, const float* b1a, const float* W2a, const float* b2a,
                     const float* u, const float* W1b, const float* b1b, const float* W2b, const float* b2b, float* out,
                     int32_t B, int32_t E, void* stream);

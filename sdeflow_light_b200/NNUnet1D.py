@@ -194,7 +194,7 @@ class UNet1D(nn.Module):
             _lib.check(L.msgm_normalize_log_radius(h, _lib.ptr(xs), _lib.ptr(xn), _lib.ptr(logn), B, Lsig,
                                                    _lib.stream_ptr(dev)))
             xs = xn
-        if E <= 256:  # both embedding MLPs in one launch (bit-identical to the two-launch form below)
+        if E <= 224:  # both embedding MLPs in one launch (bit-identical to the two-launch form below)
             wa = [_lib.f32c(p_, dev) for p_ in (self.time_mlp[0].weight, self.time_mlp[0].bias, self.time_mlp[2].weight,
                                                 self.time_mlp[2].bias)]
             wb = [None] * 4 if logn is None else [_lib.f32c(p_, dev) for p_ in (

@@ -538,7 +538,7 @@ int msgm_embed_mlp2(msgm_ctx* ctx, const float* t, const float* W1a, const float
                     int32_t B, int32_t E, void* stream) {
   if (!ctx || !t || !W1a || !b1a || !W2a || !b2a || !out || (u && (!W1b || !b1b || !W2b || !b2b)))
     return invalid("msgm_embed_mlp2: NULL argument");
-  if (B < 0 || E < 1 || E > 256) return invalid("msgm_embed_mlp2: E in 1..256");
+  if (B < 0 || E < 1 || E > 224) return invalid("msgm_embed_mlp2: E in 1..224");
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return embed_mlp2(ctx, t, W1a, b1a, W2a, b2a, u, W1b, b1b, W2b, b2b, out, B, E, (cudaStream_t)stream);

@@ -275,19 +275,24 @@ __global__ void __launch_bounds__(256) embed_mlp_kernel(const float* __restrict_
 }
 
 // Both embedding MLPs of a forward in one launch: out[b,:] = MLP_a(t[b]) (+ MLP_b(u[b]) when u != NULL), each
-// Linear(1,E) -> GELU -> Linear(E,E) (NNUnet1D.py:52-68,132-141).  CTA = 8 samples: W2 is read ONCE per CTA in coalesced
-// [E][16] tiles through shared memory (embed_mlp_kernel reads it once per sample, a row per thread); the sums run in the
-// same order as embed_mlp_kernel's, so the result is bit-identical to two of its launches.  E <= 256.
-constexpr int EM_S = 8, EM_T = 16;
+// Linear(1,E) -> GELU -> Linear(E,E) (NNUnet1D.py:52-68,132-141).  CTA = 8 samples; W2 is read ONCE per CTA, whole, into
+// shared memory with every load in flight at once (embed_mlp_kernel reads it once per sample, a row per thread); for
+// E <= 128 the 256 threads split the samples (thread = output feature x sample half).  The sums run in the same order as
+// embed_mlp_kernel's, so the result is bit-identical to two of its launches.  E <= 224.
+constexpr int EM_S = 8;
 __global__ void __launch_bounds__(256) embed_mlp2_kernel(const float* __restrict__ t, const float* __restrict__ W1a,
                                                          const float* __restrict__ b1a, const float* __restrict__ W2a,
                                                          const float* __restrict__ b2a, const float* __restrict__ u,
                                                          const float* __restrict__ W1b, const float* __restrict__ b1b,
                                                          const float* __restrict__ W2b, const float* __restrict__ b2b,
                                                          float* __restrict__ out, int B, int E) {
-  __shared__ float h[EM_S][256];
-  __shared__ float sw[256][EM_T + 1];
+  extern __shared__ float em_smem[];
+  float* h = em_smem;                  // [EM_S][E]
+  float* sw = em_smem + EM_S * E;      // [E][E + 1]
   const int b0 = blockIdx.x * EM_S, tid = threadIdx.x;
+  const int groups = E <= 128 ? 2 : 1, ns = EM_S / groups;  // sample groups handled by different threads
+  const int o = groups == 2 ? (tid & 127) : tid, s0 = groups == 2 ? (tid >> 7) * ns : 0;
+  const bool active = o < E;
   float tot[EM_S];
 #pragma unroll
   for (int si = 0; si < EM_S; ++si) tot[si] = 0.0f;
@@ -298,36 +303,30 @@ __global__ void __launch_bounds__(256) embed_mlp2_kernel(const float* __restrict
     const float* W2 = m ? W2b : W2a;
     const float* b2 = m ? b2b : b2a;
     __syncthreads();
-    if (tid < E) {
-#pragma unroll
-      for (int si = 0; si < EM_S; ++si) h[si][tid] = b0 + si < B ? gelu_erf(fmaf(W1[tid], val[b0 + si], b1[tid])) : 0.0f;
+    for (int e = tid; e < E * E; e += 256) sw[(e / E) * (E + 1) + e % E] = __ldg(W2 + e);
+    for (int e = tid; e < EM_S * E; e += 256) {
+      const int si = e / E, i = e % E;
+      h[e] = b0 + si < B ? gelu_erf(fmaf(W1[i], val[b0 + si], b1[i])) : 0.0f;
     }
-    float acc[EM_S];
+    __syncthreads();
+    if (active) {
+      float acc[EM_S];
 #pragma unroll
-    for (int si = 0; si < EM_S; ++si) acc[si] = tid < E ? b2[tid] : 0.0f;
-    for (int j0 = 0; j0 < E; j0 += EM_T) {
-      __syncthreads();
-      for (int e = tid; e < E * EM_T; e += 256) {
-        const int r = e / EM_T, c = e % EM_T;
-        sw[r][c] = j0 + c < E ? W2[(size_t)r * E + j0 + c] : 0.0f;
-      }
-      __syncthreads();
-      if (tid < E) {
-        const int jn = min(EM_T, E - j0);
-        for (int jj = 0; jj < jn; ++jj) {
-          const float w = sw[tid][jj];
+      for (int si = 0; si < EM_S; ++si) acc[si] = b2[o];
+      for (int j = 0; j < E; ++j) {
+        const float w = sw[o * (E + 1) + j];
 #pragma unroll
-          for (int si = 0; si < EM_S; ++si) acc[si] = fmaf(w, h[si][j0 + jj], acc[si]);
-        }
+        for (int si = 0; si < EM_S; ++si)
+          if (si < ns) acc[si] = fmaf(w, h[(s0 + si) * E + j], acc[si]);
       }
+#pragma unroll
+      for (int si = 0; si < EM_S; ++si) tot[si] = m ? tot[si] + acc[si] : acc[si];
     }
-#pragma unroll
-    for (int si = 0; si < EM_S; ++si) tot[si] = m ? tot[si] + acc[si] : acc[si];
   }
-  if (tid < E) {
+  if (active) {
 #pragma unroll
     for (int si = 0; si < EM_S; ++si)
-      if (b0 + si < B) out[(size_t)(b0 + si) * E + tid] = tot[si];
+      if (si < ns && b0 + s0 + si < B) out[(size_t)(b0 + s0 + si) * E + o] = tot[si];
   }
 }
 
@@ -399,7 +398,17 @@ int emb_fold_multi(msgm_ctx* ctx, const msgm_emb_fold_multi_desc* D, cudaStream_
 int embed_mlp2(msgm_ctx* ctx, const float* t, const float* W1a, const float* b1a, const float* W2a, const float* b2a,
                const float* u, const float* W1b, const float* b1b, const float* W2b, const float* b2b, float* out, int B, int E,
                cudaStream_t stream) {
-  embed_mlp2_kernel<<<(B + EM_S - 1) / EM_S, 256, 0, stream>>>(t, W1a, b1a, W2a, b2a, u, W1b, b1b, W2b, b2b, out, B, E);
+  const size_t smem = sizeof(float) * ((size_t)EM_S * E + (size_t)E * (E + 1));
+  static bool attr_set = false;  // up to 8 KB + 257 KB of floats at E = 256: raise the dynamic shared-memory limit once
+  if (!attr_set) {
+    MSGM_CUDA_TRY(cudaFuncSetAttribute(embed_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (smem > 227 * 1024) {
+    set_error("msgm_embed_mlp2: embedding width too large for one shared-memory weight tile (E <= 224)");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  embed_mlp2_kernel<<<(B + EM_S - 1) / EM_S, 256, smem, stream>>>(t, W1a, b1a, W2a, b2a, u, W1b, b1b, W2b, b2b, out, B, E);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

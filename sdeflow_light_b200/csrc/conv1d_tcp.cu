@@ -482,7 +482,11 @@ __global__ void __launch_bounds__(256) conv1d_first_planes_kernel(const float* _
         if (hasl) a += __ldg(e);
         if (hasr) a += __ldg(e + 2);
       }
-      v[j] = gelu ? 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f)) : a;
+      v[j] = a;
+    }
+    if (gelu) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) gelu_rational_x2(v[j], v[j + 1]);
     }
     uint4 hi, lo;
     split2_f16(v[0], v[1], hi.x, lo.x); split2_f16(v[2], v[3], hi.y, lo.y);

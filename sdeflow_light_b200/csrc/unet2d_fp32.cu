@@ -189,46 +189,45 @@ __global__ void __launch_bounds__(256) conv2d_cin1_kernel(const float* __restric
   }
 }
 
-// Cout = 1, 3x3, stride 1, GroupNorm(+SiLU) prologue: CTA = one sample x a band of rows; per input channel the
-// normalised (+SiLU) band with its zero ring is staged once in shared memory and every thread accumulates its 9 taps.
-// HBM-bound on the (B, Cin, H, W) input.
-__global__ void __launch_bounds__(256) conv2d_cout1_kernel(const __grid_constant__ Conv2dParams P, int TR) {
-  extern __shared__ float sband[];  // [2][(TR + 2) * (Wi + 2)]
+// Cout = 1, 3x3, stride 1, GroupNorm(+SiLU) prologue: CTA = one sample x a band of rows; the normalised (+SiLU) bands of
+// CH input channels with their zero rings are staged in shared memory per barrier (every global load of the stage in
+// flight at once: one channel per barrier made this kernel a chain of 32 load latencies, 72 us for 17 MB), then every
+// thread accumulates its 9 taps per channel.  HBM-bound on the (B, Cin, H, W) input.
+__global__ void __launch_bounds__(256) conv2d_cout1_kernel(const __grid_constant__ Conv2dParams P, int TR, int CH) {
+  extern __shared__ float sband[];  // [CH][(TR + 2) * (Wi + 2)]
   const int Hi = P.Hs, Wi = P.Ws, wc = Wi + 2, bandsz = (TR + 2) * wc;
   const int b = blockIdx.y, y0 = blockIdx.x * TR, tid = threadIdx.x;
   const int ry = tid / Wi, xx = tid % Wi;
   const bool active = ry < TR && y0 + ry < Hi;
   const int Cin = P.C1, cpg = P.G > 0 ? Cin / P.G : 1, HW = Hi * Wi;
   float acc = P.bias ? P.bias[0] : 0.0f;
-  for (int c = 0; c < Cin; ++c) {
-    float* sb = sband + (c & 1) * bandsz;
-    float mean = 0.f, rstd = 1.f, ga = 1.f, be = 0.f;
-    if (P.prologue) {
-      mean = P.stats[((size_t)b * P.G + c / cpg) * 2];
-      rstd = P.stats[((size_t)b * P.G + c / cpg) * 2 + 1];
-      ga = P.gamma[c];
-      be = P.beta[c];
-    }
-    const float* src = P.x1 + ((size_t)b * Cin + c) * HW;
-    for (int e = tid; e < bandsz; e += 256) {
-      const int iy = y0 + e / wc - 1, ix = e % wc - 1;
+  for (int c0 = 0; c0 < Cin; c0 += CH) {
+    const int nch = min(CH, Cin - c0);
+    if (c0 > 0) __syncthreads();  // the previous stage has been consumed
+    for (int e = tid; e < nch * bandsz; e += 256) {
+      const int cl = e / bandsz, r = e - cl * bandsz, c = c0 + cl;
+      const int iy = y0 + r / wc - 1, ix = r % wc - 1;
       float v = 0.0f;
       if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) {
-        v = __ldg(src + iy * Wi + ix);
+        v = __ldg(P.x1 + ((size_t)b * Cin + c) * HW + iy * Wi + ix);
         if (P.prologue) {
-          v = fmaf((v - mean) * rstd, ga, be);
+          const float mean = P.stats[((size_t)b * P.G + c / cpg) * 2], rstd = P.stats[((size_t)b * P.G + c / cpg) * 2 + 1];
+          v = fmaf((v - mean) * rstd, P.gamma[c], P.beta[c]);
           if (P.prologue == 2) v = siluf(v);
         }
       }
-      sb[e] = v;
+      sband[e] = v;
     }
-    __syncthreads();  // double-buffered band: one barrier per channel
+    __syncthreads();
     if (active) {
-      const float* w = P.W + c * 9;
+      for (int cl = 0; cl < nch; ++cl) {  // channel order and tap order as before: bit-identical sums
+        const float* w = P.W + (c0 + cl) * 9;
+        const float* sb = sband + cl * bandsz;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) acc = fmaf(__ldg(w + ky * 3 + kx), sb[(ry + ky) * wc + xx + kx], acc);
+          for (int kx = 0; kx < 3; ++kx) acc = fmaf(__ldg(w + ky * 3 + kx), sb[(ry + ky) * wc + xx + kx], acc);
+      }
     }
   }
   if (active) {
@@ -260,23 +259,35 @@ __global__ void __launch_bounds__(256) emb_proj_kernel(const float* __restrict__
 // layers stacked along the output dimension; segment i = rows [seg[i], seg[i+1]) is written as its own contiguous
 // (B, len_i) matrix at out + B * seg[i], which is what the conv epilogue of that block reads as ebias.
 struct EmbSegs { int n; int start[65]; };
+constexpr int EP_S = 4;  // samples per CTA: every weight row is read once per EP_S samples (sums in emb_proj_kernel's order)
 __global__ void __launch_bounds__(256) emb_proj_multi_kernel(const float* __restrict__ emb, const float* __restrict__ W,
                                                              const float* __restrict__ bias, float* __restrict__ out, int E,
                                                              int Ctot, int B, const __grid_constant__ EmbSegs S) {
-  extern __shared__ float se_[];  // silu(emb[b, :])
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < E; i += 256) se_[i] = siluf(emb[(size_t)b * E + i]);
+  extern __shared__ float se_[];  // [EP_S][E] silu(emb[b0 + s, :])
+  const int b0 = blockIdx.x * EP_S, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < EP_S * E; i += 256) se_[i] = b0 + i / E < B ? siluf(emb[(size_t)b0 * E + i]) : 0.0f;
   __syncthreads();
   for (int co = blockIdx.y * 8 + warp; co < Ctot; co += 8 * gridDim.y) {
-    float s = 0.0f;
-    for (int i = lane; i < E; i += 32) s = fmaf(__ldg(W + (size_t)co * E + i), se_[i], s);
+    float s[EP_S];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int q = 0; q < EP_S; ++q) s[q] = 0.0f;
+    for (int i = lane; i < E; i += 32) {
+      const float w = __ldg(W + (size_t)co * E + i);
+#pragma unroll
+      for (int q = 0; q < EP_S; ++q) s[q] = fmaf(w, se_[q * E + i], s[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < EP_S; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    }
     if (lane == 0) {
       int sg = 0;
       while (sg + 1 < S.n && co >= S.start[sg + 1]) ++sg;
       const int s0 = S.start[sg], len = S.start[sg + 1] - s0;
-      out[(size_t)B * s0 + (size_t)b * len + (co - s0)] = s + bias[co];
+#pragma unroll
+      for (int q = 0; q < EP_S; ++q)
+        if (b0 + q < B) out[(size_t)B * s0 + (size_t)(b0 + q) * len + (co - s0)] = s[q] + bias[co];
     }
   }
 }
@@ -470,8 +481,9 @@ int conv2d(msgm_ctx* ctx, const msgm_conv2d_desc* D, cudaStream_t stream) {
   }
   if (D->K == 3 && D->stride == 1 && D->up == 1 && P.C2 == 0 && D->Cout == 1 && P.Ws <= 256) {
     const int TR = std::max(1, std::min(256 / P.Ws, 8));
-    const size_t smem = sizeof(float) * 2 * (TR + 2) * (P.Ws + 2);
-    conv2d_cout1_kernel<<<dim3((P.Hs + TR - 1) / TR, D->B), 256, smem, stream>>>(P, TR);
+    const size_t band = sizeof(float) * (TR + 2) * (P.Ws + 2);
+    const int CH = (int)std::max<size_t>(1, std::min<size_t>(32, (size_t)(44 * 1024) / band));  // channels staged per barrier
+    conv2d_cout1_kernel<<<dim3((P.Hs + TR - 1) / TR, D->B), 256, CH * band, stream>>>(P, TR, CH);
     ctx->launches += 1;
     MSGM_CUDA_TRY(cudaGetLastError());
     return MSGM_OK;
@@ -510,7 +522,7 @@ int emb_proj_multi(msgm_ctx* ctx, const float* emb, const float* W, const float*
   EmbSegs S{};
   S.n = nseg;
   for (int i = 0; i <= nseg; ++i) S.start[i] = seg_start[i];
-  emb_proj_multi_kernel<<<dim3(B, 4), 256, sizeof(float) * E, stream>>>(emb, W, bias, out, E, Ctot, B, S);
+  emb_proj_multi_kernel<<<dim3((B + EP_S - 1) / EP_S, 16), 256, sizeof(float) * EP_S * E, stream>>>(emb, W, bias, out, E, Ctot, B, S);
   ctx->launches += 1;
   MSGM_CUDA_TRY(cudaGetLastError());
   return MSGM_OK;

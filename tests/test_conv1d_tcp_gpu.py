@@ -181,3 +181,42 @@ def test_one_launch_embedding_kernels_are_bit_identical():
             _lib.check(Lb.msgm_embed_mlp2(h, _lib.ptr(t), *[_lib.ptr(p) for p in pa], _lib.ptr(u) if both else None,
                                           *[(_lib.ptr(p) if both else None) for p in pb], _lib.ptr(o2), B, E, st))
             assert torch.equal(o1, o2), float((o1 - o2).abs().max())
+
+
+@pytest.mark.parametrize("kind,B,Cin,Cout,L", [("k3", 3, 64, 64, 301), ("k4", 5, 32, 64, 130), ("t", 2, 64, 32, 77)])
+def test_conv1d_tcp_writes_stay_inside_its_outputs(kind, B, Cin, Cout, L):
+    """Both outputs sit in the middle of larger allocations filled with a byte pattern: no byte outside them changes, and
+    nothing but rows of real positions changes inside the planes (compute-sanitizer is not available on the GPU pool)."""
+    torch.manual_seed(4)
+    Lb, h, st = _lib.lib(), _lib.ctx(DEV), _lib.stream_ptr(DEV)
+    x = torch.randn(B, Cin, L, device=DEV)
+    bias = torch.randn(Cout, device=DEV)
+    if kind == "t":
+        W = torch.randn(Cin, Cout, 4, device=DEV)
+        img = torch.empty(24 * Cin * Cout, device=DEV, dtype=torch.uint8)
+        _lib.check(Lb.msgm_convt1d_tc_pack(h, _lib.ptr(W), Cout, Cin, _lib.ptr(img), st))
+        K, Lout = 3, 2 * L + 5
+    else:
+        K = 3 if kind == "k3" else 4
+        W = torch.randn(Cout, Cin, K, device=DEV)
+        img = torch.empty(Lb.msgm_conv1d_tc_pack_bytes(Cout, Cin, K), device=DEV, dtype=torch.uint8)
+        _lib.check(Lb.msgm_conv1d_tc_pack(h, _lib.ptr(W), Cout, Cin, Cin, K, _lib.ptr(img), st))
+        Lout = L if K == 3 else (L - 2) // 2 + 1
+    pad = 1 << 16
+    nb = Lb.msgm_planes_bytes(B, Cout, Lout)
+    big_p = torch.full((nb + 2 * pad,), 0xAB, device=DEV, dtype=torch.uint8)
+    big_p[pad:pad + nb] = 0
+    nf = B * Cout * Lout * 4
+    big_f = torch.full((nf + 2 * pad,), 0xCD, device=DEV, dtype=torch.uint8)
+    d = _lib.Conv1dTcpDesc(_pack(x).data_ptr(), None, img.data_ptr(), bias.data_ptr(), None, big_p.data_ptr() + pad,
+                           big_f.data_ptr() + pad, B, Cin, 0, Cout, K, L, Lout, 1, int(kind == "t"), 0)
+    _lib.check(Lb.msgm_conv1d_tcp(h, C.byref(d), st))
+    torch.cuda.synchronize()
+    assert _lib.debug_flags(DEV) == 0
+    for big, n, pat in ((big_p, nb, 0xAB), (big_f, nf, 0xCD)):
+        assert bool((big[:pad] == pat).all()) and bool((big[pad + n:] == pat).all())
+    assert _ring_is_zero(big_p[pad:pad + nb], B, Cout, Lout)
+    covered = 2 * L if kind == "t" else Lout  # a transposed conv leaves the reference's right padding untouched
+    fo = big_f[pad:pad + nf].view(torch.float32).view(B, Cout, Lout)
+    assert bool(torch.isfinite(fo[:, :, :covered]).all())
+    assert bool((big_f[pad:pad + nf].view(B, Cout, Lout, 4)[:, :, covered:] == 0xCD).all())

@@ -365,6 +365,18 @@ def time_unet_forward(P, dev):
             entry["sampling_large_batch"] = {"batch": Bl, "steps": nst, "ms_per_call": ms_l,
                                              "particle_steps_per_sec": Bl * nst / ms_l * 1e3,
                                              "frac_of_tensor_bound": Bl * nst / ms_l * 1e3 / bounds[name]}
+            # the same call with the convs in the single-product mode (`conv_mode = "tc16"`: one fp16 product per contraction
+            # instead of the fp16 x 3 split; forward 4e-4 (1-D) / 2e-3 (2-D) of max|y| from the split mode, sampling only)
+            holder = net.core if hasattr(net, "core") else net
+            holder.conv_mode = "tc16"
+            try:
+                ms_h = timeit(lambda: P.rk4_stratonovich_sampler(gen, xl0, nst, keep_all_samples=False, norm_correction=True,
+                                                                 seed=1, device_out=True), 2)
+            finally:
+                holder.conv_mode = "tc"
+            entry["sampling_large_batch_tc16"] = {"batch": Bl, "steps": nst, "ms_per_call": ms_h,
+                                                  "particle_steps_per_sec": Bl * nst / ms_h * 1e3,
+                                                  "frac_of_tensor_bound": Bl * nst / ms_h * 1e3 / bounds[name]}
             xs = data[:Bt].to(dev)
             entry["train_path"] = "hand-written kernels" if unet_train.supported(gen, xs) else "library autograd"
             step = GraphedSsmStep(gen, (Bt, d), lr=1e-4)

@@ -174,8 +174,11 @@ class UNet1D(nn.Module):
                 sout = self._forward_kernels_eager(sx, st)
             if len(cache) >= 4:
                 cache.pop(next(iter(cache)))
-            ent = cache[key] = (ver, graph, sx, st, sout)
-        _, graph, sx, st, sout = ent
+            # the entry also pins the plane buffers the captured kernels write to: they may be dropped from `_plane_bufs`
+            # (which keeps the most recent batch sizes only) while this graph is still replayed
+            pinned = self.__dict__.get("_plane_bufs", {}).get((B, xs.shape[1], dev.index))
+            ent = cache[key] = (ver, graph, sx, st, sout, pinned)
+        _, graph, sx, st, sout, _ = ent
         sx.copy_(xs)
         st.copy_(tt)
         graph.replay()
@@ -314,9 +317,12 @@ class UNet1D(nn.Module):
         B, Lsig = xs.shape
         Et = self._emb_tables(h, dev, emb, [b_.net[0] for b_ in self.enc_blocks] + [self.middle.net[0]] +
                               [b_.net[0] for b_ in self.dec_blocks])
+        # one set of zero-initialised plane buffers per (batch size, length, device), the 8 most recent kept.  A CUDA graph
+        # captured by a CALLER around this forward must keep using the same batch size among those, or call the net once
+        # eagerly before capturing (the captured kernels write into these buffers); the net's own graphs pin theirs.
         allb = self.__dict__.setdefault("_plane_bufs", {})
         bkey = (B, Lsig, dev.index)
-        if bkey not in allb and len(allb) >= 4:
+        if bkey not in allb and len(allb) >= 8 and not torch.cuda.is_current_stream_capturing():
             allb.pop(next(iter(allb)))
         bufs = allb.setdefault(bkey, {})
         buf = lambda name, Cc, Lc: self._plane_buf(bufs, name, B, Cc, Lc, dev)  # noqa: E731

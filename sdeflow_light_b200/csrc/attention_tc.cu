@@ -60,39 +60,75 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
   }
 
   // ---- stage Q (this tile's queries), K, V: fp32 -> fp16 hi / lo core-matrix planes ----------------------------------
-  for (int e = tid; e < (C / 8) * 128; e += ATC_THREADS) {
-    const int kc = e >> 7, t = e & 127;
-    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-    if (t0 + t < T) {
-      float x[8];
+  // ATC_ILP items (8 values each) per thread and step: every global load of a step is issued before the first conversion,
+  // so a thread pays one memory round trip per ATC_ILP items instead of one per item (staging was ~half of the kernel).
+  constexpr int ATC_ILP = 4;
+  for (int e0 = tid; e0 < (C / 8) * 128; e0 += ATC_ILP * ATC_THREADS) {
+    float x[ATC_ILP][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = __ldg(q + (size_t)(kc * 8 + j) * T + t0 + t);
-      split2_f16(x[0], x[1], hi.x, lo.x); split2_f16(x[2], x[3], hi.y, lo.y);
-      split2_f16(x[4], x[5], hi.z, lo.z); split2_f16(x[6], x[7], hi.w, lo.w);
+    for (int u = 0; u < ATC_ILP; ++u) {
+      const int e = e0 + u * ATC_THREADS, kc = e >> 7, t = e & 127;
+      if (e < (C / 8) * 128 && t0 + t < T) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[u][j] = __ldg(q + (size_t)(kc * 8 + j) * T + t0 + t);
+      }
     }
-    *reinterpret_cast<uint4*>(sQ + e * 16) = hi;
-    *reinterpret_cast<uint4*>(sQ + QB + e * 16) = lo;
-  }
-  for (int e = tid; e < (C / 8) * T; e += ATC_THREADS) {
-    const int kc = e / T, s = e % T;
-    float x[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = __ldg(k + (size_t)(kc * 8 + j) * T + s);
-    uint4 hi, lo;
-    split2_f16(x[0], x[1], hi.x, lo.x); split2_f16(x[2], x[3], hi.y, lo.y);
-    split2_f16(x[4], x[5], hi.z, lo.z); split2_f16(x[6], x[7], hi.w, lo.w);
-    *reinterpret_cast<uint4*>(sK + e * 16) = hi;
-    *reinterpret_cast<uint4*>(sK + KB + e * 16) = lo;
+    for (int u = 0; u < ATC_ILP; ++u) {
+      const int e = e0 + u * ATC_THREADS, t = e & 127;
+      if (e >= (C / 8) * 128) break;
+      uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+      if (t0 + t < T) {
+        split2_f16(x[u][0], x[u][1], hi.x, lo.x); split2_f16(x[u][2], x[u][3], hi.y, lo.y);
+        split2_f16(x[u][4], x[u][5], hi.z, lo.z); split2_f16(x[u][6], x[u][7], hi.w, lo.w);
+      }
+      *reinterpret_cast<uint4*>(sQ + e * 16) = hi;
+      *reinterpret_cast<uint4*>(sQ + QB + e * 16) = lo;
+    }
   }
-  for (int e = tid; e < (T / 8) * C; e += ATC_THREADS) {
-    const int sc = e / C, c = e % C;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(v + (size_t)c * T + sc * 8));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(v + (size_t)c * T + sc * 8 + 4));
-    uint4 hi, lo;
-    split2_f16(a.x, a.y, hi.x, lo.x); split2_f16(a.z, a.w, hi.y, lo.y);
-    split2_f16(bq.x, bq.y, hi.z, lo.z); split2_f16(bq.z, bq.w, hi.w, lo.w);
-    *reinterpret_cast<uint4*>(sV + e * 16) = hi;
-    *reinterpret_cast<uint4*>(sV + KB + e * 16) = lo;
+  for (int e0 = tid; e0 < (C / 8) * T; e0 += ATC_ILP * ATC_THREADS) {
+    float x[ATC_ILP][8];
+#pragma unroll
+    for (int u = 0; u < ATC_ILP; ++u) {
+      const int e = e0 + u * ATC_THREADS;
+      if (e < (C / 8) * T) {
+        const int kc = e / T, sidx = e % T;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[u][j] = __ldg(k + (size_t)(kc * 8 + j) * T + sidx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ATC_ILP; ++u) {
+      const int e = e0 + u * ATC_THREADS;
+      if (e >= (C / 8) * T) break;
+      uint4 hi, lo;
+      split2_f16(x[u][0], x[u][1], hi.x, lo.x); split2_f16(x[u][2], x[u][3], hi.y, lo.y);
+      split2_f16(x[u][4], x[u][5], hi.z, lo.z); split2_f16(x[u][6], x[u][7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(sK + e * 16) = hi;
+      *reinterpret_cast<uint4*>(sK + KB + e * 16) = lo;
+    }
+  }
+  for (int e0 = tid; e0 < (T / 8) * C; e0 += ATC_ILP * ATC_THREADS) {
+    float4 xa[ATC_ILP], xb[ATC_ILP];
+#pragma unroll
+    for (int u = 0; u < ATC_ILP; ++u) {
+      const int e = e0 + u * ATC_THREADS;
+      if (e < (T / 8) * C) {
+        const int sc = e / C, c = e % C;
+        xa[u] = __ldg(reinterpret_cast<const float4*>(v + (size_t)c * T + sc * 8));
+        xb[u] = __ldg(reinterpret_cast<const float4*>(v + (size_t)c * T + sc * 8 + 4));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ATC_ILP; ++u) {
+      const int e = e0 + u * ATC_THREADS;
+      if (e >= (T / 8) * C) break;
+      uint4 hi, lo;
+      split2_f16(xa[u].x, xa[u].y, hi.x, lo.x); split2_f16(xa[u].z, xa[u].w, hi.y, lo.y);
+      split2_f16(xb[u].x, xb[u].y, hi.z, lo.z); split2_f16(xb[u].z, xb[u].w, hi.w, lo.w);
+      *reinterpret_cast<uint4*>(sV + e * 16) = hi;
+      *reinterpret_cast<uint4*>(sV + KB + e * 16) = lo;
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();

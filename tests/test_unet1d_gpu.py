@@ -578,3 +578,26 @@ def test_step_graph_is_the_default_for_long_calls():
         GS.STEP_GRAPH, net.cuda_graph = True, True
     assert torch.isfinite(got).all() and torch.equal(got, ref)
     assert n_graph * 20 < n_eager, (n_graph, n_eager)  # launches are counted on the host: two bodies (eager step 0 + capture)
+
+
+def test_unet1d_plane_buffers_survive_many_batch_sizes():
+    """The planes path keeps one set of zero-initialised activation buffers per batch size (the most recent ones) and one
+    CUDA graph per batch size; a graph must keep working after its buffers were dropped from the per-size table, and a
+    re-created buffer set must give the same values (padding rows are zero again)."""
+    torch.manual_seed(7)
+    net = P.UNet1D(96, premodule="NormalizeLogRadius").to(DEV)
+    xs = {B: torch.randn(B, 96, device=DEV) for B in range(1, 14)}
+    ts = {B: torch.rand(B, device=DEV) for B in xs}
+    with torch.no_grad():
+        net.planes = False
+        ref = {B: net(xs[B], ts[B]).clone() for B in xs}
+        net.planes = True
+        first = net(xs[3], ts[3]).clone()          # captures the graph of batch 3
+        for B in xs:                               # twelve more sizes: batch 3's buffers leave the table
+            got = net(xs[B], ts[B])
+            assert float((got - ref[B]).abs().max()) <= 5e-6 * float(ref[B].abs().max()), B
+        again = net(xs[3], ts[3])                  # replays or re-captures batch 3
+        assert torch.equal(first, again)
+        net.cuda_graph = False
+        assert torch.equal(first, net(xs[3], ts[3]))  # eager launches into a freshly allocated buffer set
+    assert len(net._plane_bufs) <= 8

@@ -523,6 +523,13 @@ int msgm_attention(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32
  * T in {64,128,192,256} within the shared-memory budget; msgm_attention_tc_supported says whether a shape is covered. */
 int msgm_attention_tc_supported(int32_t C, int32_t T);
 int msgm_attention_tc(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32_t C, int32_t T, void* stream);
+/* msgm_attention_tc with the AttentionBlock's output projection and residual in the same launch (model/unet.py:228-234:
+ * `x + proj_out(attention(qkv(norm(x))))`): out (B,C,T) = W a + bias + res, a = the attention output, W the 1x1 conv's
+ * weights packed by msgm_conv2d_tc_pack(W, C, C, 1, wimg); bias / res may be NULL; out must not alias res.
+ * C in {32, 64, 128} within msgm_attention_tc's shapes (msgm_attention_proj_tc_supported). */
+int msgm_attention_proj_tc_supported(int32_t C, int32_t T);
+int msgm_attention_proj_tc(msgm_ctx* ctx, const float* qkv, const void* wimg, const float* bias, const float* res, float* out,
+                           int32_t B, int32_t C, int32_t T, void* stream);
 /* VorticityUNet wrapper: flat (B,H*W) -> image (B,1,H,W) / 5 [after x/(|x|+eps)*sqrt(d) when pre] and back (x5). */
 int msgm_vort_pre(msgm_ctx* ctx, const float* x, float* img, float* lognorm, int32_t B, int32_t H, int32_t W, int32_t forder,
                   int32_t pre, void* stream);

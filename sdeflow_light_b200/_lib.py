@@ -100,7 +100,7 @@ SYMBOLS = ["msgm_abi_version", "msgm_last_error", "msgm_create", "msgm_destroy",
            "msgm_conv1d", "msgm_emb_fold", "msgm_convt1d_k4s2", "msgm_embed_mlp", "msgm_normalize_log_radius",
            "msgm_conv2d", "msgm_gn_stats", "msgm_emb_proj", "msgm_sincos_embed_mlp", "msgm_attention", "msgm_vort_pre",
            "msgm_vort_post", "msgm_conv2d_tc", "msgm_conv2d_tc_pack_bytes", "msgm_conv2d_tc_pack", "msgm_gn_scale_shift",
-           "msgm_attention_tc_supported", "msgm_attention_tc", "msgm_conv1d_tc", "msgm_conv1d_tc_pack_bytes",
+           "msgm_attention_tc_supported", "msgm_attention_tc", "msgm_attention_proj_tc_supported", "msgm_attention_proj_tc", "msgm_conv1d_tc", "msgm_conv1d_tc_pack_bytes",
            "msgm_conv1d_tc_pack", "msgm_convt1d_tc_pack", "msgm_convt1d_tc", "msgm_emb_proj_multi",
            "msgm_emb_fold_multi", "msgm_embed_mlp2", "msgm_planes_bytes", "msgm_conv1d_tcp", "msgm_planes_pack", "msgm_planes_unpack", "msgm_conv1d_first_planes"]
 
@@ -181,6 +181,8 @@ def lib() -> C.CDLL:
                 L.msgm_attention.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p]
                 L.msgm_attention_tc.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p]
                 L.msgm_attention_tc_supported.argtypes = [C.c_int32] * 2
+                L.msgm_attention_proj_tc_supported.argtypes = [C.c_int32] * 2
+                L.msgm_attention_proj_tc.argtypes = [C.c_void_p] * 6 + [C.c_int32] * 3 + [C.c_void_p]
                 L.msgm_vort_pre.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_void_p]
                 L.msgm_vort_post.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p]
                 L.msgm_noise_forward.argtypes = [C.c_void_p, C.POINTER(SdeDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

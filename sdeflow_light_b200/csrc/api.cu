@@ -82,7 +82,9 @@ int sincos_embed_mlp(msgm_ctx*, const float*, const float*, const float*, const 
 int attention(msgm_ctx*, const float*, float*, int, int, int, cudaStream_t);
 bool attention_tc_ok(int, int);
 int emb_proj_multi(msgm_ctx*, const float*, const float*, const float*, float*, int, int, int, int, const int*, cudaStream_t);
-int attention_tc(msgm_ctx*, const float*, float*, int, int, int, cudaStream_t);
+int attention_tc(msgm_ctx*, const float*, float*, int, int, int, cudaStream_t, const void* wimg = nullptr,
+                 const float* pbias = nullptr, const float* res = nullptr);
+bool attention_proj_tc_ok(int, int);
 int vort_pre(msgm_ctx*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
 int vort_post(msgm_ctx*, const float*, float*, int, int, int, int, cudaStream_t);
 
@@ -685,6 +687,21 @@ int msgm_attention_tc(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, in
   if (B == 0) return MSGM_OK;
   MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
   return attention_tc(ctx, qkv, out, B, C, T, (cudaStream_t)stream);
+}
+
+int msgm_attention_proj_tc_supported(int32_t C, int32_t T) { return attention_proj_tc_ok(C, T) ? 1 : 0; }
+
+int msgm_attention_proj_tc(msgm_ctx* ctx, const float* qkv, const void* wimg, const float* bias, const float* res, float* out,
+                           int32_t B, int32_t C, int32_t T, void* stream) {
+  if (!ctx || !qkv || !wimg || !out || B < 0) return invalid("msgm_attention_proj_tc: bad argument");
+  if (out == res) return invalid("msgm_attention_proj_tc: out aliases res");
+  if (!attention_proj_tc_ok(C, T)) {
+    set_error("msgm_attention_proj_tc: shape not covered (C in {32, 64, 128}, T % 64 == 0, T <= 256, C <= 2 T)");
+    return MSGM_ERR_UNSUPPORTED;
+  }
+  if (B == 0) return MSGM_OK;
+  MSGM_CUDA_TRY(cudaSetDevice(ctx->device));
+  return attention_tc(ctx, qkv, out, B, C, T, (cudaStream_t)stream, wimg, bias, res);
 }
 
 int msgm_attention(msgm_ctx* ctx, const float* qkv, float* out, int32_t B, int32_t C, int32_t T, void* stream) {

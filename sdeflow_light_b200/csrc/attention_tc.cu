@@ -10,6 +10,10 @@
 //   3. O = P V         M = 128, N = C, K = T: accumulator = C TMEM columns after S; 1 / rowsum applied in the epilogue.
 // q and k are channel-major in memory, which IS the K-major core-matrix order after an 8-channel gather (lanes =
 // consecutive tokens: coalesced); v[c, s..s+7] is already contiguous.  The P tiles reuse the Q / K operand space.
+//   4. (optional) the block's 1x1 output projection and residual in the same launch: the normalised O rows are split and
+//      written as an A operand into the Q space, the projection's packed weights are copied into the K | V space, one more
+//      product (M = 128, N = C, K = C) lands in the S columns, and the epilogue adds bias and the block input.  Saves the
+//      separate conv launch and the round trip of the attention output (11 launches of ~15 us per 2-D U-Net forward).
 #include <cuda_fp16.h>
 
 #include "msgm_common.cuh"
@@ -23,6 +27,11 @@ struct AttnTcParams {
   int C, T;
   float scale2;
   TcFlags flags;
+  // fused output projection (AttentionBlock.proj_out + residual, model/unet.py:228-234): out = W_proj a + bias + res.
+  // wimg = the 1x1 conv's packed image (conv2d_tc_pack_kernel, one N tile of C columns) or NULL (out = a)
+  const unsigned char* wimg;
+  const float* pbias;
+  const float* res;
 };
 
 constexpr int ATC_THREADS = 256;
@@ -33,6 +42,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
   uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem);   // S complete
   uint64_t* bar_p = bar_s + 1;                           // [4] P chunk consumed (its MMAs complete)
+  uint64_t* bar_w = bar_s + 5;                           // projection product complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 6);
   const int C = P.C, T = P.T;
   const int QB = C * 128 * 2, KB = C * T * 2;            // bytes of one hi (or lo) plane set
@@ -52,6 +62,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
   if (tid == 0) {
     mbar_init(bar_s, 1);
     for (int i = 0; i < 4; ++i) mbar_init(bar_p + i, 1);
+    mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -224,14 +235,84 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tc_kernel(const __gr
     }
     const float inv = 1.0f / sum;
     const bool live = ok && t0 + row < T;
-    float* o = P.out + (size_t)b * C * T + t0 + row;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      uint32_t r[32];
-      TMEM_LD32(trow + 256 + c0, r);
-      tc_wait_ld();
-      if (live) {
+    if (!P.wimg) {
+      float* o = P.out + (size_t)b * C * T + t0 + row;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t r[32];
+        TMEM_LD32(trow + 256 + c0, r);
+        tc_wait_ld();
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[(size_t)(c0 + j) * T] = __uint_as_float(r[j]) * inv;
+          for (int j = 0; j < 32; ++j) o[(size_t)(c0 + j) * T] = __uint_as_float(r[j]) * inv;
+        }
+      }
+    } else {
+      // normalised attention output of this row -> A operand of the projection, [hi|lo][C/8][128][8] in the Q space (every
+      // product that read Q, K, V or a P chunk has completed: the last commit covers all earlier tcgen05 operations)
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t r[32];
+        TMEM_LD32(trow + 256 + c0, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 hi, lo;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[g * 8 + j]) * inv;
+          split2_f16(f[0], f[1], hi.x, lo.x); split2_f16(f[2], f[3], hi.y, lo.y);
+          split2_f16(f[4], f[5], hi.z, lo.z); split2_f16(f[6], f[7], hi.w, lo.w);
+          unsigned char* dst = sQ + ((c0 >> 3) + g) * 2048 + row * 16;
+          *reinterpret_cast<uint4*>(dst) = hi;
+          *reinterpret_cast<uint4*>(dst + QB) = lo;
+        }
+      }
+    }
+  }
+  if (P.wimg) {  // launch-uniform
+    __syncthreads();  // every warp now knows that K and V are dead
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(P.wimg);
+      uint4* dst = reinterpret_cast<uint4*>(sK);
+      for (int e = tid; e < C * C / 4; e += ATC_THREADS) dst[e] = __ldg(src + e);  // 4 C^2 bytes: [chunk][hi|lo][kc][C][8]
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+      const uint32_t idesc_c = umma_idesc_f16(128, C);
+      const uint32_t ah = smem_u32(sQ), wh = smem_u32(sK);
+      for (int kk = 0; kk < C / 16; ++kk) {
+        const uint64_t dAh = umma_desc(ah + kk * 4096, 2048, 128), dAl = umma_desc(ah + QB + kk * 4096, 2048, 128);
+        const uint32_t wk = wh + (uint32_t)(kk * 64 * C);
+        const uint64_t dWh = umma_desc(wk, C * 16, 128), dWl = umma_desc(wk + 32 * C, C * 16, 128);
+        umma_ss(tbase, dAh, dWh, idesc_c, kk > 0 ? 1u : 0u, 0);
+        umma_ss(tbase, dAl, dWh, idesc_c, 1u, 0);
+        umma_ss(tbase, dAh, dWl, idesc_c, 1u, 0);
+      }
+      umma_commit(bar_w, 0);
+      __syncwarp();
+    }
+    if (warp < 4) {
+      ok = mbar_wait(bar_w, 0, P.flags) && ok;
+      tc_fence_after();
+      const int row = tid;
+      const bool live = ok && t0 + row < T;
+      const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
+      const size_t base = (size_t)b * C * T + t0 + row;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t r[32];
+        TMEM_LD32(trow + c0, r);
+        tc_wait_ld();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]);
+            if (P.pbias) v += __ldg(P.pbias + c0 + j);
+            if (P.res) v += __ldg(P.res + base + (size_t)(c0 + j) * T);
+            P.out[base + (size_t)(c0 + j) * T] = v;
+          }
+        }
       }
     }
   }
@@ -245,8 +326,14 @@ bool attention_tc_ok(int C, int T) {
   return 128 + 128 + 4 * (size_t)C * (128 + 2 * T) <= 227 * 1024 && (4 * C * 128 + 4 * C * T) >= ATC_PBUF;
 }
 
-int attention_tc(msgm_ctx* ctx, const float* qkv, float* out, int B, int C, int T, cudaStream_t stream) {
-  AttnTcParams P{qkv, out, C, T, 1.0f / sqrtf((float)C), next_tc_flags(ctx)};
+int conv2d_tc_nout(int Cout, int taps);  // conv2d_tc.cu
+
+// the fused projection needs the 1x1 conv's packed image to be ONE N tile of C columns
+bool attention_proj_tc_ok(int C, int T) { return attention_tc_ok(C, T) && conv2d_tc_nout(C, 1) == C && C <= 2 * T; }
+
+int attention_tc(msgm_ctx* ctx, const float* qkv, float* out, int B, int C, int T, cudaStream_t stream, const void* wimg,
+                 const float* pbias, const float* res) {
+  AttnTcParams P{qkv, out, C, T, 1.0f / sqrtf((float)C), next_tc_flags(ctx), reinterpret_cast<const unsigned char*>(wimg), pbias, res};
   const size_t smem = 128 + 128 + 4 * (size_t)C * (128 + 2 * T);
   MSGM_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_tc_kernel<<<dim3((T + 127) / 128, B), ATC_THREADS, smem, stream>>>(P);

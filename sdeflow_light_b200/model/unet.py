@@ -252,6 +252,7 @@ class UNetModel(nn.Module):
     # "tc": tcgen05 implicit GEMM with split fp16 x3 operands (fp32-level parity) where the shape allows; "tc16": the same
     # with ONE fp16 product (3x fewer MMAs, ~1e-3 relative: sampling only); "fp32": CUDA-core kernels only
     conv_mode = "tc"
+    fuse_attention_proj = True  # AttentionBlock: attention, proj_out and the residual in one launch (attention_tc.cu, step 4)
 
     def _k_conv_tc(self, dev, conv, W, bias, x1, x2, gn, silu, ebias, res, up, stride):
         """Tensor-core conv (csrc/conv2d_tc.cu): packed weights cached per weight version, GroupNorm folded to scale/shift."""
@@ -328,6 +329,23 @@ class UNetModel(nn.Module):
         h, L = _lib.ctx(dev), _lib.lib()
         B, Cc, Hh, Ww = x.shape
         qkv = self._k_conv(dev, _as2d(blk.qkv), x, gn=blk.norm, silu=False)
+        if (self.fuse_attention_proj and self.conv_mode in ("tc", "tc16") and
+                L.msgm_attention_proj_tc_supported(Cc, Hh * Ww)):
+            # attention + output projection + residual in one launch (packed 1x1 weights cached like every conv's)
+            proj = _as2d(blk.proj_out)
+            W = _lib.f32c(proj.weight, dev)
+            cache = self.__dict__.setdefault("_tc_wimg", {})
+            key = (W.data_ptr(), proj.weight._version, _lib.weight_epoch(), tuple(W.shape), dev.index)
+            ent = cache.get(W.data_ptr())
+            if ent is None or ent[0] != key:
+                img = torch.empty(L.msgm_conv2d_tc_pack_bytes(Cc, Cc, 1), device=dev, dtype=torch.uint8)
+                _lib.check(L.msgm_conv2d_tc_pack(h, _lib.ptr(W), Cc, Cc, 1, _lib.ptr(img), _lib.stream_ptr(dev)))
+                ent = cache[W.data_ptr()] = (key, img)
+            out = torch.empty((B, Cc, Hh, Ww), device=dev, dtype=torch.float32)
+            bias = None if proj.bias is None else _lib.f32c(proj.bias, dev)
+            _lib.check(L.msgm_attention_proj_tc(h, _lib.ptr(qkv), _lib.ptr(ent[1]), _lib.ptr(bias), _lib.ptr(x), _lib.ptr(out), B, Cc,
+                                                Hh * Ww, _lib.stream_ptr(dev)))
+            return out
         att = torch.empty((B, Cc, Hh, Ww), device=dev, dtype=torch.float32)
         fn = L.msgm_attention_tc if self.conv_mode in ("tc", "tc16") and L.msgm_attention_tc_supported(Cc, Hh * Ww) else L.msgm_attention
         _lib.check(fn(h, _lib.ptr(qkv), _lib.ptr(att), B, Cc, Hh * Ww, _lib.stream_ptr(dev)))

@@ -119,6 +119,36 @@ def test_conv2d_tc_rejects_unsupported_shapes():
         _lib.check(L.msgm_conv2d_tc(_lib.ctx(dev), C.byref(d), _lib.stream_ptr(dev)))
 
 
+@pytest.mark.parametrize("B,Cc,T", [(5, 64, 256), (3, 128, 64), (2, 32, 128), (4, 128, 128), (2, 64, 64)])
+def test_attention_with_fused_projection_matches_float64(B, Cc, T):
+    """AttentionBlock tail in one launch (model/unet.py:228-234): x + proj_out(attention(qkv)) vs float64."""
+    dev = torch.device(DEV)
+    h, L = _lib.ctx(dev), _lib.lib()
+    assert L.msgm_attention_proj_tc_supported(Cc, T) == 1
+    assert L.msgm_attention_proj_tc_supported(96, 192) == 0  # the 1x1 image of 96 channels is three N tiles
+    torch.manual_seed(T + Cc + 1)
+    qkv = torch.randn(B, 3 * Cc, T, device=dev) * 1.5
+    W = torch.randn(Cc, Cc, 1, 1, device=dev) / Cc ** 0.5
+    bias, x = torch.randn(Cc, device=dev), torch.randn(B, Cc, T, device=dev)
+    img = torch.empty(L.msgm_conv2d_tc_pack_bytes(Cc, Cc, 1), device=dev, dtype=torch.uint8)
+    _lib.check(L.msgm_conv2d_tc_pack(h, _lib.ptr(W), Cc, Cc, 1, _lib.ptr(img), _lib.stream_ptr(dev)))
+    out = torch.full((B, Cc, T), float("nan"), device=dev)
+    _lib.check(L.msgm_attention_proj_tc(h, _lib.ptr(qkv), _lib.ptr(img), _lib.ptr(bias), _lib.ptr(x), _lib.ptr(out), B, Cc, T,
+                                        _lib.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert _lib.debug_flags(dev) == 0
+    q, k, v = qkv.double().split(Cc, dim=1)
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q, k) / Cc ** 0.5, dim=-1)
+    att = torch.einsum("bts,bcs->bct", w, v)
+    ref = torch.einsum("oc,bct->bot", W.double()[:, :, 0, 0], att) + bias.double()[None, :, None] + x.double()
+    err = float((out.double() - ref).abs().max()) / float(ref.abs().max())
+    assert torch.isfinite(out).all() and err < 2e-5, f"attention + projection rel err {err:.3e}"
+    # bias / residual are optional
+    _lib.check(L.msgm_attention_proj_tc(h, _lib.ptr(qkv), _lib.ptr(img), None, None, _lib.ptr(out), B, Cc, T, _lib.stream_ptr(dev)))
+    ref0 = torch.einsum("oc,bct->bot", W.double()[:, :, 0, 0], att)
+    assert float((out.double() - ref0).abs().max()) / float(ref0.abs().max()) < 2e-5
+
+
 @pytest.mark.parametrize("B,Cc,T", [(5, 64, 256), (3, 128, 64), (2, 32, 128), (2, 96, 192)])
 def test_attention_tc_matches_float64(B, Cc, T):
     """QKVAttention (model/unet.py:236-250) on the tensor pipe vs float64: softmax((q s)^T (k s)) v, s = C^-1/4."""

@@ -318,12 +318,31 @@ class UNetModel(nn.Module):
             _lib.check(L.msgm_emb_proj(h, _lib.ptr(emb), _lib.ptr(_lib.f32c(lin.weight, dev)),
                                        _lib.ptr(_lib.f32c(lin.bias, dev)), _lib.ptr(eb), E, blk.out_channels, B,
                                        _lib.stream_ptr(dev)))
+        # While a CUDA graph is being captured, the 1x1 skip conv of a channel-changing block (it reads the block input only)
+        # goes on a side stream: in the replayed graph it is a parallel branch beside GroupNorm -> conv1 -> GroupNorm, joined
+        # in front of conv2, which adds it as the residual.  Eager launches stay on one stream.
+        has_skip = not isinstance(blk.skip_connection, nn.Identity)
+        fork = has_skip and self.graph_branches and torch.cuda.is_current_stream_capturing()
+        skip = x1  # channels unchanged: the block input is a single tensor
+        if fork:
+            main, side = torch.cuda.current_stream(dev), self._side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                skip = self._k_conv(dev, blk.skip_connection, x1, x2)
         h1 = self._k_conv(dev, blk.in_layers[2], x1, x2, gn=blk.in_layers[0], ebias=eb)
-        if isinstance(blk.skip_connection, nn.Identity):
-            skip = x1  # channels unchanged: the block input is a single tensor
-        else:
+        if fork:
+            main.wait_stream(side)
+        elif has_skip:
             skip = self._k_conv(dev, blk.skip_connection, x1, x2)
         return self._k_conv(dev, blk.out_layers[3], h1, gn=blk.out_layers[0], res=skip)
+
+    graph_branches = True  # independent kernels of a block as parallel branches of a captured graph (see _k_resblock)
+
+    def _side_stream(self, dev):
+        streams = self.__dict__.setdefault("_side_streams", {})
+        if dev.index not in streams:
+            streams[dev.index] = torch.cuda.Stream(device=dev)
+        return streams[dev.index]
 
     def _k_attention(self, dev, blk, x):
         h, L = _lib.ctx(dev), _lib.lib()

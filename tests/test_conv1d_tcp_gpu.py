@@ -220,3 +220,39 @@ def test_conv1d_tcp_writes_stay_inside_its_outputs(kind, B, Cin, Cout, L):
     fo = big_f[pad:pad + nf].view(torch.float32).view(B, Cout, Lout)
     assert bool(torch.isfinite(fo[:, :, :covered]).all())
     assert bool((big_f[pad:pad + nf].view(B, Cout, Lout, 4)[:, :, covered:] == 0xCD).all())
+
+
+def test_conv1d_tcp_full_size_properties():
+    """BASELINE config 3 sizes (L = 1000, batch 256, 32 -> 32 and 128 + 128 -> 128 channels), where a float64 reference is too
+    slow to be worth it: size-independent properties of a bias-free conv without activation -- linearity in the input,
+    sample independence (a sample's output does not depend on its neighbours in the batch: tiles straddle samples), and
+    agreement of the planes output with the fp32 output of the same call."""
+    torch.manual_seed(5)
+    Lb, h, st = _lib.lib(), _lib.ctx(DEV), _lib.stream_ptr(DEV)
+    for (B, C1, C2, Cout, L) in [(256, 32, 0, 32, 1000), (256, 128, 128, 128, 250)]:
+        Cin = C1 + C2
+        W = torch.randn(Cout, Cin, 3, device=DEV) / (3 * Cin) ** 0.5
+        img = torch.empty(Lb.msgm_conv1d_tc_pack_bytes(Cout, Cin, 3), device=DEV, dtype=torch.uint8)
+        _lib.check(Lb.msgm_conv1d_tc_pack(h, _lib.ptr(W), Cout, Cin, Cin, 3, _lib.ptr(img), st))
+
+        def conv(xa, xb, nb):
+            outp = _planes(nb, Cout, L)
+            outf = torch.empty((nb, Cout, L), device=DEV, dtype=torch.float32)
+            d = _lib.Conv1dTcpDesc(_pack(xa).data_ptr(), None if xb is None else _pack(xb).data_ptr(), img.data_ptr(), None, None,
+                                   outp.data_ptr(), outf.data_ptr(), nb, C1, C2, Cout, 3, L, 0, 0, 0, 0)
+            _lib.check(Lb.msgm_conv1d_tcp(h, C.byref(d), st))
+            return outf, outp
+
+        xa, ya = torch.randn(B, C1, L, device=DEV), torch.randn(B, C1, L, device=DEV)
+        xb = torch.randn(B, C2, L, device=DEV) if C2 else None
+        yb = torch.randn(B, C2, L, device=DEV) if C2 else None
+        fx, px = conv(xa, xb, B)
+        fy, _ = conv(ya, yb, B)
+        fz, _ = conv(2.0 * xa - 0.5 * ya, None if xb is None else 2.0 * xb - 0.5 * yb, B)
+        scale = float(fx.abs().max())
+        assert float((fz - (2.0 * fx - 0.5 * fy)).abs().max()) <= 2e-5 * scale           # linearity
+        assert float((_unpack(px, B, Cout, L) - fx).abs().max()) <= 4e-6 * scale          # planes == fp32 output
+        sub = slice(100, 117)                                                             # 17 samples out of the middle
+        fs, _ = conv(xa[sub].contiguous(), None if xb is None else xb[sub].contiguous(), 17)
+        assert torch.equal(fs, fx[sub])                                                   # sample independence, bit for bit
+        assert _lib.debug_flags(DEV) == 0

@@ -192,6 +192,8 @@ class GraphedSsmStep:
         loss = torch.func.functional_call(self._mod, {"gen." + n: l for n, l in zip(self._names, leaves)},
                                           (self.x,)).mean()
         grads = torch.autograd.grad(loss, leaves)
+        from . import unet_train
+        unet_train.join_leaf_stream(self.dev)  # weight gradients of the U-Net convs run on a side branch of the graph
         torch._foreach_copy_(self._grads, list(grads))
         self.loss.copy_(loss.detach())
         self._iter.add_(1)

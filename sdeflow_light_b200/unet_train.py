@@ -18,6 +18,8 @@ from __future__ import annotations
 import ctypes as C
 import math
 
+import os
+
 import torch
 
 from . import _lib
@@ -38,6 +40,48 @@ def _zeros(dev, n):
     if z is None:
         z = _zero_cache[key] = torch.zeros(n, device=dev, dtype=torch.float32)
     return z
+
+
+# ---- weight gradients as a parallel branch of a captured iteration graph ----------------------------------------------------
+# A conv's weight gradient is a LEAF of the backward pass: nothing but the optimiser reads it, while the data gradient next
+# to it is on the critical path of the chain.  While a CUDA graph is being captured (train.GraphedSsmStep) the tensor-core
+# weight-gradient launches therefore go on a side stream -- forked after the cotangent and its range words exist, joined once
+# in front of the optimiser (join_leaf_stream) -- and run beside the data-gradient chain when the graph is replayed.  Every
+# tensor the branch reads is handed to the allocator with record_stream, so its block is not reused for the rest of the
+# capture (the main stream could otherwise overwrite it before the branch has run).  Eager iterations stay on one stream.
+LEAF_STREAM = os.environ.get("MSGM_LEAF_STREAM", "1") != "0"
+_leaf_streams: dict = {}
+_leaf_forked: set = set()
+
+
+class _leaf_branch:
+    def __init__(self, dev, *reads):
+        self.dev, self.reads, self.cm = dev, [t for t in reads if t is not None], None
+
+    def __enter__(self):
+        if LEAF_STREAM and torch.cuda.is_current_stream_capturing():
+            side = _leaf_streams.get(self.dev.index)
+            if side is None:
+                side = _leaf_streams[self.dev.index] = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            for t in self.reads:
+                t.record_stream(side)
+            _leaf_forked.add(self.dev.index)
+            self.cm = torch.cuda.stream(side)
+            self.cm.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.cm is not None:
+            self.cm.__exit__(*exc)
+        return False
+
+
+def join_leaf_stream(dev):
+    """The current stream waits for the weight-gradient branch (no-op when nothing was forked)."""
+    if dev.index in _leaf_forked:
+        torch.cuda.current_stream(dev).wait_stream(_leaf_streams[dev.index])
+        _leaf_forked.discard(dev.index)
 
 
 # ---- raw kernel calls -------------------------------------------------------------------------------------------------------
@@ -174,11 +218,13 @@ def conv_wgrad(cot, in1, in2, Wshape, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, a
     if WGRAD_TC and L.msgm_conv_wgrad_tc_ok(N, Cout, C1, C2, KH, KW, stride, pad, up, Hi, Wi):
         if amax is None or amax_in is None:  # both operands are range-scaled: an activation tensor of small magnitude would
             amax, amax_in = amax_pair(cot, in1, in2)  # otherwise lose the low part of its fp16 split in the subnormals
-        gW = torch.empty(Wshape, device=cot.device, dtype=torch.float32)  # the kernel overwrites its block
         nb = L.msgm_conv_wgrad_tc_scratch_bytes(h, N, Cout, C1 + C2, KH, KW, stride, pad, up, Hi, Wi)
-        scratch = torch.empty(nb, device=cot.device, dtype=torch.uint8)
-        _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), _lib.ptr(amax),
-                                        _lib.ptr(amax_in), _lib.ptr(scratch), N, Cout, C1, C2, Cw, 0, KH, KW, stride, pad, up, Hi, Wi, 0, st))
+        with _leaf_branch(cot.device, cot, in1, in2, amax, amax_in):
+            gW = torch.empty(Wshape, device=cot.device, dtype=torch.float32)  # the kernel overwrites its block
+            scratch = torch.empty(nb, device=cot.device, dtype=torch.uint8)
+            _lib.check(L.msgm_conv_wgrad_tc(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), _lib.ptr(amax),
+                                            _lib.ptr(amax_in), _lib.ptr(scratch), N, Cout, C1, C2, Cw, 0, KH, KW, stride, pad, up,
+                                            Hi, Wi, 0, _lib.stream_ptr(cot.device)))
         return gW
     gW = torch.zeros(Wshape, device=cot.device, dtype=torch.float32)
     _lib.check(L.msgm_conv_wgrad(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), N, Cout, C1, C2, Cw, 0, KH, KW,
@@ -271,6 +317,8 @@ class Conv1dPair(torch.autograd.Function):
         Cout, Cw, K = W.shape
         gx1 = gx2 = gemb = None
         amax, amax_in = amax_pair(g, x1, x2)
+        # the weight gradient first: in a captured graph it is a side branch (conv_wgrad) beside the data gradient below
+        gW = conv_wgrad(g, x1, x2, W.shape, 1, K, stride, pad, 1, 1, Lin, 1, Lout, amax, amax_in)
         if ctx.needs_input_grad[0] or (x2 is not None and ctx.needs_input_grad[1]):
             if stride == 1:   # data gradient = the same conv with flipped taps and swapped channel roles
                 gx = ranged(lambda t_: conv1d_raw(t_, None, W, Cin, 1, pad, dgrad=True), g, amax)
@@ -281,7 +329,6 @@ class Conv1dPair(torch.autograd.Function):
                 gx = ranged(lambda t_: convt1d_raw(t_, Wt, Lin), g, amax)
             gx1 = gx[:, :C1]
             gx2 = gx[:, C1:] if x2 is not None else None
-        gW = conv_wgrad(g, x1, x2, W.shape, 1, K, stride, pad, 1, 1, Lin, 1, Lout, amax, amax_in)
         if emb is not None:
             Cemb = Cw - Cin
             Eb = torch.empty((N, Cout, K), device=dev, dtype=torch.float32)  # cotangent of the folded table
@@ -318,10 +365,10 @@ class ConvT1dPair(torch.autograd.Function):
         N, Cin, Lin = x.shape
         # data gradient: Conv1d(k4, s2, p1) with the weight read as (out = Cin, in = Cout), no flip
         amax_x, amax = amax_pair(x, g)
-        gx = ranged(lambda t_: conv1d_raw(t_, None, W, None, 2, 1), g, amax) if ctx.needs_input_grad[0] else None
         # gW[ci][co][k] = sum x[ci][p] g[co][2p - 1 + k]: a conv weight gradient with the roles swapped: the kernel's "input"
         # operand is the cotangent here, so the range scaling goes to that side
         gW = conv_wgrad(x, g, None, W.shape, 1, 4, 2, 1, 1, 1, ctx.Lout, 1, Lin, amax=amax_x, amax_in=amax)
+        gx = ranged(lambda t_: conv1d_raw(t_, None, W, None, 2, 1), g, amax) if ctx.needs_input_grad[0] else None
         gb = channel_sums(g, N // 2)
         return gx, gW, gb, None
 
@@ -515,13 +562,13 @@ class Conv2dPair(torch.autograd.Function):
         Ho, Wo = g.shape[-2:]
         gx = None
         amax, amax_in = amax_pair(g, x)
+        gW = conv_wgrad(g, x, None, W.shape, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo, amax, amax_in)  # side branch when captured
         if ctx.needs_input_grad[0]:
             # data gradient: the same conv with flipped taps and swapped channel roles (image packed straight from W)
             src = resample2(g, 0) if stride == 2 else g     # stride 2: cotangent back on the input grid (zeros in between)
             gx = ranged(lambda t_: conv2d_raw(t_, W, None, 1, 1, dgrad=True), src, amax)
             if up == 2:                                      # adjoint of the nearest-neighbour upsampling
                 gx = resample2(gx, 1)
-        gW = conv_wgrad(g, x, None, W.shape, K, K, stride, K // 2, up, Hs, Ws, Ho, Wo, amax, amax_in)
         gb = channel_sums(g, N // 2) if has_b else None
         ge = sample_channel_sums(g) if has_e else None
         return gx, gW, gb, ge, None, None

@@ -601,3 +601,56 @@ def test_unet1d_plane_buffers_survive_many_batch_sizes():
         net.cuda_graph = False
         assert torch.equal(first, net(xs[3], ts[3]))  # eager launches into a freshly allocated buffer set
     assert len(net._plane_bufs) <= 8
+
+
+@pytest.mark.parametrize("which", ["unet1d", "unet2d"])
+def test_graphed_unet_gradients_equal_the_eager_ones(which):
+    """The captured iteration runs the convs' weight gradients on a side branch of the graph (unet_train._leaf_branch); an
+    eager iteration runs everything on one stream.  With the learning rate at zero and the trainer's device counter reset,
+    both see the same t, v, noise and weights: the flat gradient buffers must agree to the last bits, replay after replay
+    (measured: <= 3e-8 of max|g| between replays AND between eager runs -- a few reductions of the path use float atomics --
+    and <= 3e-7 of each tensor's own maximum; a branch that ran too early or read a reused buffer would be off by O(1))."""
+    from sdeflow_light_b200.train import GraphedSsmStep
+    torch.manual_seed(1)
+    if which == "unet1d":
+        d, net = 250, P.UNet1D(250, premodule="NormalizeLogRadius")
+    else:
+        d, net = 256, _build_unet2d(16, "NormalizeLogRadius", "F", 3)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            if p_.dim() > 1 and float(p_.abs().sum()) == 0.0:
+                p_.normal_(0, 0.05)
+    data = torch.randn(256, d)
+    T = Bd.T_param(1.0)
+    base = P.MSGMsde(data, beta_min=0.1, beta_max=20., T=T, t_epsilon=1e-3, denseTensor=False, norm_map="log",
+                     num_steps_forward=16, device=DEV, estim_cst_norm_dens_r_T=False)
+    gen = P.PluginReverseSDE(base, net.to(DEV), T, deviceReverseSDE=DEV).to(DEV)
+    step = GraphedSsmStep(gen, (16, d), lr=0.0, seed=11)
+    x = data[:16].to(DEV)
+    replayed = []
+    for _ in range(3):
+        step._iter.zero_()
+        step(x)
+        replayed.append(step.flat.clone())
+    scale = float(replayed[0].abs().max())
+    assert scale > 0.0
+    assert max(float((replayed[0] - r).abs().max()) for r in replayed[1:]) <= 1e-6 * scale
+    # the same iteration eagerly, on the current stream (nothing is being captured: no side branch)
+    old_rng, old_dev = getattr(gen, "_rng", None), getattr(gen, "device_rng", False)
+    gen._rng, gen.device_rng = (step._seed, step._iter, step._row_offset), True
+    try:
+        step._iter.zero_()
+        step.x.copy_(x)
+        step.flat.zero_()
+        step._fwd_bwd()
+        torch.cuda.synchronize()
+        eager = step.flat.clone()
+    finally:
+        gen._rng, gen.device_rng = old_rng, old_dev
+    assert float((eager - replayed[0]).abs().max()) <= 1e-6 * scale
+    o = 0
+    for n, p_ in zip(step._names, step.params):  # per tensor, relative to its own size
+        k = p_.numel()
+        e, r = eager[o:o + k], replayed[0][o:o + k]
+        assert float((e - r).abs().max()) <= 1e-5 * max(float(e.abs().max()), 1e-12 * scale), n
+        o += k

@@ -172,6 +172,12 @@ def channel_sums(x, nrows):
     return out
 
 
+def bias_grad(g, nrows):
+    """Bias gradient = channel sums of the cotangent: a leaf of the backward pass (side branch of a captured graph)."""
+    with _leaf_branch(g.device, g):
+        return channel_sums(g, nrows)
+
+
 def amax_of(g):
     """Device word holding max|g| (float bits): the range scaling of the tensor-core data / weight gradient kernels."""
     h, L, st = _h(g.device)
@@ -226,7 +232,13 @@ def conv_wgrad(cot, in1, in2, Wshape, KH, KW, stride, pad, up, Hi, Wi, Ho, Wo, a
                                             _lib.ptr(amax_in), _lib.ptr(scratch), N, Cout, C1, C2, Cw, 0, KH, KW, stride, pad, up,
                                             Hi, Wi, 0, _lib.stream_ptr(cot.device)))
         return gW
-    gW = torch.zeros(Wshape, device=cot.device, dtype=torch.float32)
+    if Cw == C1 + C2:  # the whole tensor is this kernel's: zero fill + accumulation on the side branch as well
+        with _leaf_branch(cot.device, cot, in1, in2):
+            gW = torch.zeros(Wshape, device=cot.device, dtype=torch.float32)
+            _lib.check(L.msgm_conv_wgrad(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), N, Cout, C1, C2, Cw, 0, KH,
+                                         KW, stride, pad, up, Hi, Wi, Ho, Wo, _lib.stream_ptr(cot.device)))
+        return gW
+    gW = torch.zeros(Wshape, device=cot.device, dtype=torch.float32)  # the caller fills the other channels: one stream
     _lib.check(L.msgm_conv_wgrad(h, _lib.ptr(cot), _lib.ptr(in1), _lib.ptr(in2), _lib.ptr(gW), N, Cout, C1, C2, Cw, 0, KH, KW,
                                  stride, pad, up, Hi, Wi, Ho, Wo, st))
     return gW
@@ -337,7 +349,7 @@ class Conv1dPair(torch.autograd.Function):
             gemb = gemm(Eb.view(N, Cout * K), Wemb, N, Cemb, Cout * K, Cout * K, Cemb)
             gWe = gemm(Eb.view(N, Cout * K), emb, Cout * K, Cemb, N, Cout * K, Cemb, ta=True)
             gW[:, Cin:, :] = gWe.view(Cout, K, Cemb).permute(0, 2, 1)
-        gb = channel_sums(g, N // 2)
+        gb = bias_grad(g, N // 2)
         return gx1, gx2, gemb, gW, gb, None, None
 
 
@@ -369,7 +381,7 @@ class ConvT1dPair(torch.autograd.Function):
         # operand is the cotangent here, so the range scaling goes to that side
         gW = conv_wgrad(x, g, None, W.shape, 1, 4, 2, 1, 1, 1, ctx.Lout, 1, Lin, amax=amax_x, amax_in=amax)
         gx = ranged(lambda t_: conv1d_raw(t_, None, W, None, 2, 1), g, amax) if ctx.needs_input_grad[0] else None
-        gb = channel_sums(g, N // 2)
+        gb = bias_grad(g, N // 2)
         return gx, gW, gb, None
 
 
@@ -569,7 +581,7 @@ class Conv2dPair(torch.autograd.Function):
             gx = ranged(lambda t_: conv2d_raw(t_, W, None, 1, 1, dgrad=True), src, amax)
             if up == 2:                                      # adjoint of the nearest-neighbour upsampling
                 gx = resample2(gx, 1)
-        gb = channel_sums(g, N // 2) if has_b else None
+        gb = bias_grad(g, N // 2) if has_b else None
         ge = sample_channel_sums(g) if has_e else None
         return gx, gW, gb, ge, None, None
 

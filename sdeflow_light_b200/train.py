@@ -126,12 +126,18 @@ class GraphedSsmStep:
         # Adam), the round-1 arrangement, for process groups that cannot be captured.
         l0 = _lib.launch_count(dev)
         self.g_fb, self.g_opt = torch.cuda.CUDAGraph(), None
-        if self.world == 1 or graph_allreduce:
-            with torch.cuda.graph(self.g_fb):
-                self._iteration()
-        else:
-            with torch.cuda.graph(self.g_fb):
-                self._fwd_bwd()
+        from . import unet_train
+        unet_train.LEAF_CAPTURE = True  # this capture joins the weight-gradient branch (_fwd_bwd): it may be forked
+        try:
+            if self.world == 1 or graph_allreduce:
+                with torch.cuda.graph(self.g_fb):
+                    self._iteration()
+            else:
+                with torch.cuda.graph(self.g_fb):
+                    self._fwd_bwd()
+        finally:
+            unet_train.LEAF_CAPTURE = False
+        if not (self.world == 1 or graph_allreduce):
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt):
                 self._opt_step()

@@ -44,12 +44,13 @@ def _zeros(dev, n):
 
 # ---- weight gradients as a parallel branch of a captured iteration graph ----------------------------------------------------
 # A conv's weight gradient is a LEAF of the backward pass: nothing but the optimiser reads it, while the data gradient next
-# to it is on the critical path of the chain.  While a CUDA graph is being captured (train.GraphedSsmStep) the tensor-core
+# to it is on the critical path of the chain.  While train.GraphedSsmStep captures its iteration graph the tensor-core
 # weight-gradient launches therefore go on a side stream -- forked after the cotangent and its range words exist, joined once
 # in front of the optimiser (join_leaf_stream) -- and run beside the data-gradient chain when the graph is replayed.  Every
 # tensor the branch reads is handed to the allocator with record_stream, so its block is not reused for the rest of the
 # capture (the main stream could otherwise overwrite it before the branch has run).  Eager iterations stay on one stream.
 LEAF_STREAM = os.environ.get("MSGM_LEAF_STREAM", "1") != "0"
+LEAF_CAPTURE = False  # set by train.GraphedSsmStep around its own captures: only a capture that joins the branch may fork it
 _leaf_streams: dict = {}
 _leaf_forked: set = set()
 
@@ -59,7 +60,7 @@ class _leaf_branch:
         self.dev, self.reads, self.cm = dev, [t for t in reads if t is not None], None
 
     def __enter__(self):
-        if LEAF_STREAM and torch.cuda.is_current_stream_capturing():
+        if LEAF_STREAM and LEAF_CAPTURE and torch.cuda.is_current_stream_capturing():
             side = _leaf_streams.get(self.dev.index)
             if side is None:
                 side = _leaf_streams[self.dev.index] = torch.cuda.Stream(device=self.dev)

@@ -172,3 +172,23 @@ def test_training_path_host_policies():
         assert torch.backends.cudnn.allow_tf32 and torch.backends.cuda.matmul.allow_tf32
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_plane_format_and_late_round2_queries_need_no_gpu():
+    """Host-only facts of the 1-D U-Net's activation-plane path (include/msgm_b200.h, csrc/conv1d_tcp.cu): buffer size of
+    the plane format, descriptor layouts, which nets take the path, the fused attention projection's shape query."""
+    L = _lib.lib()
+    # planes of (B, C, L): fp16 [hi | lo][C / 8][2 * 640 + B (L + 3)][8]
+    for B, Cc, Ln in ((1, 8, 1), (256, 32, 1000), (1024, 128, 125), (0, 16, 7)):
+        assert L.msgm_planes_bytes(B, Cc, Ln) == 2 * (Cc // 8) * (2 * 640 + B * (Ln + 3)) * 16
+    assert L.msgm_planes_bytes(4, 12, 10) == -1 and L.msgm_planes_bytes(4, 16, 0) == -1   # C % 8, L >= 1
+    assert ctypes.sizeof(_lib.Conv1dTcpDesc) == 7 * 8 + 10 * 4            # 7 pointers, 10 int32
+    assert ctypes.sizeof(_lib.EmbFoldMultiDesc) == 2 * 16 * 8 + 4 * 16 * 4 + 3 * 4 + 4 + 8   # arrays, n / Cemb / B (+ pad), emb
+    # attention + projection in one launch: C must be one N tile of the packed 1x1 image (32, 64, 128)
+    assert L.msgm_attention_proj_tc_supported(64, 256) == 1 and L.msgm_attention_proj_tc_supported(128, 64) == 1
+    assert L.msgm_attention_proj_tc_supported(96, 192) == 0 and L.msgm_attention_proj_tc_supported(128, 256) == 0
+    # which UNet1D configurations run on planes: every width a multiple of 32, first width <= 128, one real input channel
+    assert P.UNet1D(1000)._planes_ok(1000) and P.UNet1D(64, premodule="NormalizeLogRadius")._planes_ok(64)
+    assert not P.UNet1D(64, base_channels=8, channel_mults=(1, 2))._planes_ok(64)      # widths 8, 16
+    assert not P.UNet1D(64, base_channels=48)._planes_ok(64)                           # widths 48, 96, 192
+    assert not P.UNet1D(4)._planes_ok(4)                                               # shorter than 2^levels
